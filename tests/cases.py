@@ -1,0 +1,123 @@
+"""Shared parity-test cases (geometry lists follow the reference's own gradient tests,
+/root/reference/test/gradient_test.cpp:143-369, plus the BASELINE.json configs at reduced batch)."""
+import numpy as np
+
+# (n, h, w, c, f, rh, rw, ph, pw, sh, sw, dh, dw)
+CONV_CASES = {
+    # test/gradient_test.cpp:168-180 -- rank-1 {32} viewed as 32x1x1, F=5, R=3, pad 2
+    "gt_rank1": (5, 32, 1, 1, 5, 3, 1, 2, 0, 1, 1, 1, 0),
+    # rank-2 {10,10} viewed as 10x10x1: F=5, R=3x2, pad 1x2, stride 1x2, dilation 1x0
+    "gt_rank2": (5, 10, 10, 1, 5, 3, 2, 1, 2, 1, 2, 1, 0),
+    # rank-3 {8,8,2}, same hyper-parameters
+    "gt_rank3": (5, 8, 8, 2, 5, 3, 2, 1, 2, 1, 2, 1, 0),
+    # second layer of the same tests: F=1, R=2x2 (defaults otherwise: pad 1, stride 1)
+    "gt_second": (5, 6, 5, 5, 1, 2, 2, 1, 1, 1, 1, 0, 0),
+    # config 1 (examples/cifar_convnet.cpp:25,28) at batch 8
+    "cifar_conv0": (8, 32, 32, 3, 8, 3, 3, 1, 1, 1, 1, 0, 0),
+    "cifar_conv1": (8, 16, 16, 8, 8, 3, 3, 1, 1, 1, 1, 0, 0),
+    # config 3 (examples/mnist_autoencoder.cpp:27,29): 4x4 stride 2 / 4x4, no padding given -> pad 1
+    "mnist_conv0": (8, 28, 28, 1, 3, 4, 4, 1, 1, 2, 2, 0, 0),
+    # config 2 geometry at reduced size: 3x3 pad 1, TMA-friendly batch (n % 32 == 0, c % 32 == 0)
+    "c2_small": (32, 12, 10, 64, 32, 3, 3, 1, 1, 1, 1, 0, 0),
+    "c2_small_f256": (64, 7, 6, 64, 256, 3, 3, 1, 1, 1, 1, 0, 0),
+    "c2_stride2": (32, 12, 10, 32, 48, 3, 3, 1, 1, 2, 2, 0, 0),
+    "c2_dil1": (32, 12, 10, 32, 16, 3, 3, 2, 2, 1, 1, 1, 1),
+    "c2_1x1": (64, 9, 9, 64, 64, 1, 1, 0, 0, 1, 1, 0, 0),
+    "ragged_c": (32, 9, 7, 20, 24, 3, 3, 1, 1, 1, 1, 0, 0),
+    # ragged everything: odd batch, odd channels
+    "ragged": (7, 9, 11, 5, 3, 3, 4, 2, 1, 2, 1, 0, 1),
+    "single": (1, 3, 3, 1, 1, 3, 3, 1, 1, 1, 1, 0, 0),
+}
+
+TCONV_CASES = {
+    # test/gradient_test.cpp:192-204
+    "gt_rank1": (5, 16, 1, 1, 5, 4, 1, 1, 0, 1, 1, 0, 0),
+    "gt_rank2": (5, 4, 5, 1, 5, 5, 3, 1, 0, 1, 2, 0, 1),
+    "gt_rank3": (5, 2, 3, 2, 5, 5, 3, 1, 0, 1, 2, 0, 1),
+    # config 3 (examples/mnist_autoencoder.cpp:43,45) at batch 8
+    "mnist_t0": (8, 10, 10, 3, 3, 4, 4, 1, 1, 1, 1, 0, 0),
+    "mnist_t1": (8, 13, 13, 3, 1, 4, 4, 1, 1, 2, 2, 0, 0),
+    "wide": (32, 6, 5, 32, 16, 3, 3, 1, 1, 2, 2, 0, 0),
+    "ragged": (3, 4, 3, 5, 2, 2, 3, 0, 1, 2, 1, 1, 0),
+}
+
+# (n, in, out)
+DENSE_CASES = {
+    "gt_rank1": (5, 32, 16),   # test/gradient_test.cpp:143-156
+    "gt_rank3": (5, 32, 16),
+    "cifar_fc0": (64, 512, 50),  # examples/cifar_convnet.cpp:32,35
+    "cifar_fc1": (64, 50, 10),
+    "mnist_fc": (32, 300, 100),
+    "ragged": (7, 13, 3),
+    "single": (1, 1, 1),
+}
+
+# (kind, alpha) -- kinds as CATTL3_ACT_*; test/gradient_test.cpp:215-282 uses 0.2 / 0.2 / 1.2
+ACT_CASES = {
+    "relu": (0, 0.0), "leaky": (1, 0.2), "elu": (2, 0.2), "swish": (3, 1.2),
+    "sigmoid": (4, 0.0), "tanh": (5, 0.0), "softplus": (6, 0.0), "softmax": (7, 0.0),
+}
+
+# (kind, n, h, w, c, rh, rw, sh, sw); test/gradient_test.cpp:292-315
+POOL_CASES = {
+    "max_1d_r2s2": (0, 5, 16, 1, 1, 2, 1, 2, 1),
+    "max_1d_r3s1": (0, 5, 16, 1, 1, 3, 1, 1, 1),
+    "max_2d_overlap": (0, 5, 8, 8, 2, 3, 2, 1, 2),
+    "max_cifar": (0, 8, 32, 32, 8, 2, 2, 2, 2),
+    "mean_1d_r2s2": (1, 5, 16, 1, 1, 2, 1, 2, 1),
+    "mean_2d_overlap": (1, 5, 8, 8, 2, 3, 2, 1, 2),
+    "mean_cifar": (1, 8, 16, 16, 8, 2, 2, 2, 2),
+}
+
+# (per_channel, n, h, w, c, steps); test/gradient_test.cpp:346-369
+BN_CASES = {
+    "pc_rank3": (1, 5, 4, 4, 3, 1),
+    "pc_running": (1, 8, 5, 3, 4, 3),
+    "pa_rank3": (0, 5, 4, 4, 2, 1),
+    "pa_running": (0, 6, 3, 2, 2, 3),
+    "pc_wide": (1, 32, 6, 6, 16, 2),
+}
+
+# kind -> hyper {lr, a, b, eps} (reference defaults)
+OPT_CASES = {
+    "sgd": (0, (1e-3, 0, 0, 0)),
+    "momentum": (1, (1e-3, 1e-3, 0.9, 0)),
+    "nesterov": (2, (1e-3, 1e-3, 0.9, 0)),
+    "adagrad": (3, (1e-2, 0, 0, 1e-5)),
+    "rmsprop": (4, (1e-3, 0, 1e-1, 1e-5)),
+    "adadelta": (5, (0, 5e-2, 0, 1e-5)),
+    "adam": (6, (1e-3, 1e-1, 1e-3, 1e-5)),
+    "adamax": (7, (1e-3, 1e-1, 1e-3, 1e-5)),
+    "nadam": (8, (1e-3, 1e-1, 1e-3, 1e-5)),
+    "amsgrad": (9, (1e-3, 1e-1, 1e-3, 1e-5)),
+}
+
+
+def rand(rng, shape, dtype, lo=-1.0, hi=1.0):
+    return np.asfortranarray(rng.uniform(lo, hi, size=shape).astype(dtype))
+
+
+def relerr(a, b):
+    """Norm-relative error max|a-b| / max(max|b|, tiny): the metric SURVEY.md section 8c prescribes."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(float(np.max(np.abs(b))), 1e-30))
+
+
+TOL = {np.dtype(np.float32): 1e-4, np.dtype(np.float64): 1e-10}  # BASELINE.json north_star
+
+
+def conv_inputs(case, dtype, seed, transposed=False):
+    from oracle.binding import Geom, conv_out_dims
+    g = Geom(*case)
+    rng = np.random.default_rng(seed)
+    x = rand(rng, (g.n, g.h, g.w, g.c), dtype)
+    oh, ow = conv_out_dims(g, transposed)
+    if transposed:
+        w = rand(rng, (g.c, g.rh * g.rw * g.f), dtype, -0.5, 0.5)
+        b = rand(rng, (1, oh * ow * g.f), dtype)
+    else:
+        w = rand(rng, (g.rh * g.rw * g.c, g.f), dtype, -0.5, 0.5)
+        b = rand(rng, (1, g.f), dtype)
+    dy = rand(rng, (g.n, oh, ow, g.f), dtype)
+    return g, x, w, b, dy
