@@ -1,0 +1,238 @@
+"""Python-side loader for libcattl3_b200.so (the C ABI of include/cattl3_b200.h).
+
+The product is the shared library plus the header-only C++ classes in ``cattle/``; this module only
+exists so that the Python test-suite and ``bench.py`` can drive the same C ABI through ctypes, with
+PyTorch used purely for device memory, streams and ``torch.distributed`` plumbing.
+
+The directory name contains a hyphen, so import it through ``load_package()`` in
+``__graft_entry__.py`` (``importlib`` by path, module name ``cattl3_b200``).
+
+There is no CPU fallback and no alternative implementation: if the library is missing or a call
+fails, an exception is raised.
+"""
+import ctypes
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcattl3_b200.so")
+INCLUDE_DIR = os.path.join(os.path.dirname(HERE), "include")
+CATTLE_INCLUDE_DIR = os.path.join(HERE, "cattle")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = 0, 1, 2, 3, 4
+ACT = dict(relu=0, leaky_relu=1, elu=2, swish=3, sigmoid=4, tanh=5, softplus=6, softmax=7)
+POOL = dict(max=0, mean=1)
+OPT = dict(sgd=0, momentum=1, nesterov=2, adagrad=3, rmsprop=4, adadelta=5, adam=6, adamax=7, nadam=8,
+           amsgrad=9)
+PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
+
+
+class Cattl3Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("cattl3 error %d: %s" % (code, message))
+        self.code = code
+
+
+class ConvGeom(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in
+                ("n", "h", "w", "c", "f", "rh", "rw", "ph", "pw", "sh", "sw", "dh", "dw")]
+
+
+class PoolGeom(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in ("n", "h", "w", "c", "rh", "rw", "sh", "sw")]
+
+
+class OptStep(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("reset_grad", ctypes.c_int32)] + \
+               [(k, ctypes.c_double) for k in ("lr", "a", "b", "eps", "lr_epoch", "c1", "c1n", "c2", "l2_lambda")]
+
+
+def build(verbose=False):
+    """Compile every CUDA translation unit for sm_100a into libcattl3_b200.so (in-tree)."""
+    subprocess.run(["make", "-C", HERE, "-j8", "all"], check=True,
+                   stdout=None if verbose else subprocess.DEVNULL)
+
+
+_lib = None
+
+# every symbol include/cattl3_b200.h declares (tests/test_abi.py checks the header against this)
+_VOID_P = ctypes.c_void_p
+_SYMBOLS = [
+    "cattl3_abi_version", "cattl3_last_error", "cattl3_device_count", "cattl3_ctx_create",
+    "cattl3_ctx_destroy", "cattl3_ctx_synchronize", "cattl3_ctx_set_conv_path", "cattl3_ctx_launch_count",
+    "cattl3_ctx_last_path", "cattl3_ctx_stream", "cattl3_malloc", "cattl3_free", "cattl3_memset",
+    "cattl3_memcpy_h2d", "cattl3_memcpy_d2h", "cattl3_memcpy_d2d", "cattl3_host_alloc", "cattl3_host_free",
+    "cattl3_conv_output_dims", "cattl3_pool_output_dims",
+    "cattl3_conv_forward_host_f32", "cattl3_conv_backward_host_f32",
+] + [n + s for s in ("_f32", "_f64") for n in (
+    "cattl3_conv_forward", "cattl3_conv_backward", "cattl3_transconv_forward", "cattl3_transconv_backward",
+    "cattl3_dense_forward", "cattl3_dense_backward", "cattl3_activation_forward", "cattl3_activation_backward",
+    "cattl3_pool_forward", "cattl3_pool_backward", "cattl3_batchnorm_forward", "cattl3_batchnorm_backward",
+    "cattl3_optimizer_step", "cattl3_add_inplace", "cattl3_scale")]
+
+
+def lib():
+    """Loads the shared library (raises if it has not been built: there is no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError("%s is missing: run __graft_entry__.build() (nvcc, sm_100a); "
+                                    "there is no CPU or PyTorch fallback" % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name in _SYMBOLS:
+            getattr(L, name).restype = ctypes.c_int
+        L.cattl3_last_error.restype = ctypes.c_char_p
+        L.cattl3_ctx_last_path.restype = ctypes.c_char_p
+        L.cattl3_ctx_last_path.argtypes = [_VOID_P]
+        L.cattl3_ctx_launch_count.restype = ctypes.c_int64
+        L.cattl3_ctx_launch_count.argtypes = [_VOID_P]
+        L.cattl3_ctx_stream.restype = _VOID_P
+        L.cattl3_ctx_stream.argtypes = [_VOID_P]
+        _lib = L
+    return _lib
+
+
+def _p(t):
+    """Device (or host) address of a torch tensor / numpy array / int / None."""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return ctypes.c_void_p(t)
+    if hasattr(t, "data_ptr"):
+        return ctypes.c_void_p(t.data_ptr())
+    if hasattr(t, "ctypes"):
+        return ctypes.c_void_p(t.ctypes.data)
+    raise TypeError(type(t))
+
+
+def _suffix(dtype):
+    s = str(dtype)
+    if s.endswith("float32"):
+        return "f32", ctypes.c_float
+    if s.endswith("float64"):
+        return "f64", ctypes.c_double
+    raise TypeError("cattl3 supports float32 and float64 only (the reference's Scalar types), got %s" % s)
+
+
+class Context:
+    """One cattl3_ctx: a device, a stream and its workspaces."""
+
+    def __init__(self, device=0, stream=None):
+        self.L = lib()
+        self.h = ctypes.c_void_p()
+        sp = ctypes.c_void_p(stream) if stream else None
+        self._chk(self.L.cattl3_ctx_create(ctypes.byref(self.h), int(device), sp))
+
+    def _chk(self, rc):
+        if rc != OK:
+            raise Cattl3Error(rc, (self.L.cattl3_last_error() or b"").decode())
+
+    def close(self):
+        if self.h:
+            self.L.cattl3_ctx_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self._chk(self.L.cattl3_ctx_synchronize(self.h))
+
+    def set_conv_path(self, path):
+        self._chk(self.L.cattl3_ctx_set_conv_path(self.h, int(path)))
+
+    @property
+    def launches(self):
+        return int(self.L.cattl3_ctx_launch_count(self.h))
+
+    @property
+    def last_path(self):
+        return self.L.cattl3_ctx_last_path(self.h).decode()
+
+    def _call(self, name, dtype, *args):
+        suf, _ = _suffix(dtype)
+        self._chk(getattr(self.L, "%s_%s" % (name, suf))(self.h, *args))
+
+    # ---- kernel layers (device pointers; tensors are torch CUDA tensors in the reference layout) ----
+    def conv_forward(self, g, x, w, b, y, transposed=False):
+        self._call("cattl3_transconv_forward" if transposed else "cattl3_conv_forward", x.dtype,
+                   ctypes.byref(g), _p(x), _p(w), _p(b), _p(y))
+
+    def conv_backward(self, g, x, w, dy, dw, db, dx, transposed=False):
+        self._call("cattl3_transconv_backward" if transposed else "cattl3_conv_backward", x.dtype,
+                   ctypes.byref(g), _p(x), _p(w), _p(dy), _p(dw), _p(db), _p(dx))
+
+    def dense_forward(self, n, i, o, x, w, b, y):
+        self._call("cattl3_dense_forward", x.dtype, n, i, o, _p(x), _p(w), _p(b), _p(y))
+
+    def dense_backward(self, n, i, o, x, w, dy, dw, db, dx):
+        self._call("cattl3_dense_backward", x.dtype, n, i, o, _p(x), _p(w), _p(dy), _p(dw), _p(db), _p(dx))
+
+    def conv_forward_host(self, g, x_host, w, b, y_host, x_dev_keep=None):
+        self._chk(self.L.cattl3_conv_forward_host_f32(self.h, ctypes.byref(g), _p(x_host), _p(w), _p(b),
+                                                      _p(y_host), _p(x_dev_keep)))
+
+    def conv_backward_host(self, g, x_dev, w, dy_host, dw, db, dx_host):
+        self._chk(self.L.cattl3_conv_backward_host_f32(self.h, ctypes.byref(g), _p(x_dev), _p(w), _p(dy_host),
+                                                       _p(dw), _p(db), _p(dx_host)))
+
+    def activation_forward(self, kind, alpha, rows, vol, x, y):
+        _, ct = _suffix(x.dtype)
+        self._call("cattl3_activation_forward", x.dtype, int(kind), ct(alpha), ctypes.c_int64(rows),
+                   ctypes.c_int64(vol), _p(x), _p(y))
+
+    def activation_backward(self, kind, alpha, rows, vol, x, y, dy, dx):
+        _, ct = _suffix(dy.dtype)
+        self._call("cattl3_activation_backward", dy.dtype, int(kind), ct(alpha), ctypes.c_int64(rows),
+                   ctypes.c_int64(vol), _p(x), _p(y), _p(dy), _p(dx))
+
+    def pool_forward(self, kind, g, x, y, argmax):
+        self._call("cattl3_pool_forward", x.dtype, int(kind), ctypes.byref(g), _p(x), _p(y), _p(argmax))
+
+    def pool_backward(self, kind, g, dy, argmax, dx):
+        self._call("cattl3_pool_backward", dy.dtype, int(kind), ctypes.byref(g), _p(dy), _p(argmax), _p(dx))
+
+    def batchnorm_forward(self, per_channel, n, h, w, c, training, running_init, decay, eps, x, gamma, beta,
+                          running_mean, running_inv_sd, saved_mean, saved_inv_sd, y):
+        _, ct = _suffix(x.dtype)
+        self._call("cattl3_batchnorm_forward", x.dtype, int(per_channel), n, h, w, c, int(training),
+                   int(running_init), ct(decay), ct(eps), _p(x), _p(gamma), _p(beta), _p(running_mean),
+                   _p(running_inv_sd), _p(saved_mean), _p(saved_inv_sd), _p(y))
+
+    def batchnorm_backward(self, per_channel, n, h, w, c, x, gamma, saved_mean, saved_inv_sd, dy, dgamma, dbeta,
+                           dx):
+        self._call("cattl3_batchnorm_backward", x.dtype, int(per_channel), n, h, w, c, _p(x), _p(gamma),
+                   _p(saved_mean), _p(saved_inv_sd), _p(dy), _p(dgamma), _p(dbeta), _p(dx))
+
+    def optimizer_step(self, step, count, p, g, s1=None, s2=None, s3=None):
+        self._call("cattl3_optimizer_step", p.dtype, ctypes.byref(step), ctypes.c_int64(count), _p(p), _p(g),
+                   _p(s1), _p(s2), _p(s3))
+
+    def add_inplace(self, count, y, x):
+        self._call("cattl3_add_inplace", y.dtype, ctypes.c_int64(count), _p(y), _p(x))
+
+    def scale(self, count, alpha, x, y):
+        _, ct = _suffix(x.dtype)
+        self._call("cattl3_scale", x.dtype, ctypes.c_int64(count), ct(alpha), _p(x), _p(y))
+
+
+def make_opt_step(kind, hyper, timestep, epoch, l2_lambda=0.0, reset_grad=True, dtype="float32"):
+    """Evaluates the step-dependent scalars the way the reference's optimizers do (in double, then
+    rounded to the Scalar type): AdamOptimizer.hpp:67-68, NadamOptimizer.hpp:45-47,
+    MomentumSGDOptimizer.hpp:70-72."""
+    import numpy as np
+    S = np.float32 if str(dtype).endswith("32") else np.float64
+    lr, a, b, eps = (S(v) for v in hyper)
+    st = OptStep()
+    st.kind, st.reset_grad = int(kind), int(bool(reset_grad))
+    st.lr, st.a, st.b, st.eps = float(lr), float(a), float(b), float(eps)
+    st.lr_epoch = float(S(lr / S(S(1) + a * S(epoch))))
+    one = S(1)
+    st.c1 = float(S(one / (1.0 - float(one - a) ** (timestep + 1) + float(eps))))
+    st.c1n = float(S(one / (1.0 - float(one - a) ** (timestep + 2) + float(eps))))
+    st.c2 = float(S(one / (1.0 - float(one - b) ** (timestep + 1) + float(eps))))
+    st.l2_lambda = float(S(l2_lambda))
+    return st

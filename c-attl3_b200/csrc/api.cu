@@ -1,0 +1,406 @@
+// api.cu -- context / memory management and the kernel-layer entry points of the C ABI
+// (include/cattl3_b200.h).  Each kernel-layer call is lowered to one or more "gather GEMM" passes
+// (common.cuh: GatherGeom) that either the tcgen05 path (conv_tc.cu) or the SIMT path
+// (conv_simt.cu) executes; there is no CPU fallback.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace cattl3 {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_error, sizeof(g_error), fmt, ap);
+	va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+	set_error("CUDA error %d (%s) at %s:%d: %s", (int) e, cudaGetErrorString(e), file, line, what);
+	if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+		return CATTL3_ERR_NO_DEVICE;
+	return CATTL3_ERR_CUDA;
+}
+
+int ensure_buffer(cattl3_ctx* ctx, void** buf, size_t* cur, size_t need) {
+	if (*cur >= need)
+		return CATTL3_OK;
+	if (*buf) {
+		// the old buffer may still be in use by work queued on the stream
+		CATTL3_CUDA(cudaStreamSynchronize(ctx->stream));
+		CATTL3_CUDA(cudaFree(*buf));
+		*buf = nullptr;
+		*cur = 0;
+	}
+	size_t bytes = (need + ((size_t) 1 << 20) - 1) & ~(((size_t) 1 << 20) - 1);
+	CATTL3_CUDA(cudaMalloc(buf, bytes));
+	*cur = bytes;
+	return CATTL3_OK;
+}
+
+static int conv_out(int in, int r, int p, int d, int s) { return (in - r - (r - 1) * d + 2 * p) / s + 1; }
+static int tconv_out(int in, int r, int p, int d, int s) { return (in - 1) * s + r + (r - 1) * d - 2 * p; }
+
+static int check_geom(const cattl3_conv_geom* g, int transposed, int* oh, int* ow) {
+	CATTL3_REQUIRE(g, "null geometry");
+	CATTL3_REQUIRE(g->n > 0 && g->h > 0 && g->w > 0 && g->c > 0 && g->f > 0, "conv geometry: non-positive size");
+	CATTL3_REQUIRE(g->rh > 0 && g->rw > 0 && g->sh > 0 && g->sw > 0, "conv geometry: receptor/stride must be > 0");
+	CATTL3_REQUIRE(g->ph >= 0 && g->pw >= 0 && g->dh >= 0 && g->dw >= 0, "conv geometry: negative padding/dilation");
+	const int erh = g->rh + (g->rh - 1) * g->dh, erw = g->rw + (g->rw - 1) * g->dw;
+	if (!transposed) {
+		CATTL3_REQUIRE(g->h + 2 * g->ph >= erh && g->w + 2 * g->pw >= erw, "conv geometry: receptor larger than padded input");
+		*oh = conv_out(g->h, g->rh, g->ph, g->dh, g->sh);
+		*ow = conv_out(g->w, g->rw, g->pw, g->dw, g->sw);
+	} else {
+		*oh = tconv_out(g->h, g->rh, g->ph, g->dh, g->sh);
+		*ow = tconv_out(g->w, g->rw, g->pw, g->dw, g->sw);
+		CATTL3_REQUIRE(*oh > 0 && *ow > 0, "transposed conv geometry: empty output");
+	}
+	return CATTL3_OK;
+}
+
+// ---- lowering of the kernel layers to gather-GEMM passes ------------------------------------------
+// Forward-style gather: source coordinate = o * stride + r * (dilation + 1) - pad.
+static GatherGeom fwd_gather(int N, int SH, int SW, int SC, int OH, int OW, int J, const cattl3_conv_geom* g) {
+	GatherGeom gg;
+	gg.N = N; gg.SH = SH; gg.SW = SW; gg.SC = SC; gg.OH = OH; gg.OW = OW; gg.J = J;
+	gg.RH = g->rh; gg.RW = g->rw;
+	gg.ah = g->sh; gg.bh = g->dh + 1; gg.ch = -g->ph; gg.denh = 1;
+	gg.aw = g->sw; gg.bw = g->dw + 1; gg.cw = -g->pw; gg.denw = 1;
+	gg.w_stap = gg.w_sr = gg.w_sj = 0;
+	return gg;
+}
+// Transposed-style gather: source coordinate = (o + pad - r * (dilation + 1)) / stride when divisible.
+static GatherGeom bwd_gather(int N, int SH, int SW, int SC, int OH, int OW, int J, const cattl3_conv_geom* g) {
+	GatherGeom gg;
+	gg.N = N; gg.SH = SH; gg.SW = SW; gg.SC = SC; gg.OH = OH; gg.OW = OW; gg.J = J;
+	gg.RH = g->rh; gg.RW = g->rw;
+	gg.ah = 1; gg.bh = -(g->dh + 1); gg.ch = g->ph; gg.denh = g->sh;
+	gg.aw = 1; gg.bw = -(g->dw + 1); gg.cw = g->pw; gg.denw = g->sw;
+	gg.w_stap = gg.w_sr = gg.w_sj = 0;
+	return gg;
+}
+
+template<typename S> struct IsFloat { static constexpr bool value = false; };
+template<> struct IsFloat<float> { static constexpr bool value = true; };
+
+template<typename S>
+static int run_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* w, const S* bias,
+		int bias_mode, S* out) {
+	if (IsFloat<S>::value && ctx->conv_path != CATTL3_PATH_SIMT && tc_gather_gemm_supported(ctx, gg)) {
+		ctx->last_path = "tcgen05";
+		return tc_gather_gemm_f32(ctx, gg, (const float*) src, (const float*) w, (const float*) bias, bias_mode,
+				(float*) out);
+	}
+	if (ctx->conv_path == CATTL3_PATH_TCGEN05) {
+		set_error("tcgen05 path requested but the shape/type does not qualify (needs float, batch %% 32 == 0)");
+		return CATTL3_ERR_UNSUPPORTED;
+	}
+	ctx->last_path = "simt";
+	return simt_gather_gemm<S>(ctx, gg, src, w, bias, bias_mode, out);
+}
+
+template<typename S>
+static int run_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* plain, S* dw) {
+	if (IsFloat<S>::value && ctx->conv_path != CATTL3_PATH_SIMT && tc_wgrad_supported(ctx, gg)) {
+		ctx->last_path = "tcgen05";
+		return tc_wgrad_f32(ctx, gg, (const float*) src, (const float*) plain, (float*) dw);
+	}
+	if (ctx->conv_path == CATTL3_PATH_TCGEN05) {
+		set_error("tcgen05 weight-gradient path requested but the shape/type does not qualify");
+		return CATTL3_ERR_UNSUPPORTED;
+	}
+	ctx->last_path = "simt";
+	return simt_wgrad<S>(ctx, gg, src, plain, dw);
+}
+
+template<typename S>
+static int conv_forward(cattl3_ctx* ctx, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y) {
+	CATTL3_CHECK(check_ctx(ctx));
+	int oh, ow;
+	CATTL3_CHECK(check_geom(g, 0, &oh, &ow));
+	CATTL3_REQUIRE(x && w && b && y, "conv_forward: null tensor");
+	const long long T = (long long) g->rh * g->rw;
+	GatherGeom gg = fwd_gather(g->n, g->h, g->w, g->c, oh, ow, g->f, g);
+	gg.w_stap = 1; gg.w_sr = T; gg.w_sj = T * g->c;
+	return run_gather_gemm<S>(ctx, gg, x, w, b, 1, y);
+}
+
+template<typename S>
+static int conv_backward(cattl3_ctx* ctx, const cattl3_conv_geom* g, const S* x, const S* w, const S* dy, S* dw,
+		S* db, S* dx) {
+	CATTL3_CHECK(check_ctx(ctx));
+	int oh, ow;
+	CATTL3_CHECK(check_geom(g, 0, &oh, &ow));
+	CATTL3_REQUIRE(x && w && dy && dw && db, "conv_backward: null tensor");
+	const long long T = (long long) g->rh * g->rw;
+	// dW += cols^T dY (ConvKernelLayer.hpp:154)
+	GatherGeom gw = fwd_gather(g->n, g->h, g->w, g->c, oh, ow, g->f, g);
+	gw.w_stap = 1; gw.w_sr = T; gw.w_sj = T * g->c;
+	CATTL3_CHECK(run_wgrad<S>(ctx, gw, x, dy, dw));
+	// db += colsum(dY) (:155)
+	CATTL3_CHECK(colsum_accumulate<S>(ctx, (int64_t) g->n * oh * ow, g->f, dy, db));
+	if (!dx)
+		return CATTL3_OK;  // input layer (:156-157)
+	// dX = crop(col2im(dY W^T)) (:159-188) as a gather over (tap, f)
+	GatherGeom gd = bwd_gather(g->n, oh, ow, g->f, g->h, g->w, g->c, g);
+	gd.w_stap = 1; gd.w_sr = T * g->c; gd.w_sj = T;
+	return run_gather_gemm<S>(ctx, gd, dy, w, (const S*) nullptr, 0, dx);
+}
+
+template<typename S>
+static int transconv_forward(cattl3_ctx* ctx, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y) {
+	CATTL3_CHECK(check_ctx(ctx));
+	int oh, ow;
+	CATTL3_CHECK(check_geom(g, 1, &oh, &ow));
+	CATTL3_REQUIRE(x && w && b && y, "transconv_forward: null tensor");
+	const long long T = (long long) g->rh * g->rw;
+	GatherGeom gg = bwd_gather(g->n, g->h, g->w, g->c, oh, ow, g->f, g);
+	gg.w_stap = g->c; gg.w_sr = 1; gg.w_sj = (long long) g->c * T;
+	return run_gather_gemm<S>(ctx, gg, x, w, b, 2, y);
+}
+
+template<typename S>
+static int transconv_backward(cattl3_ctx* ctx, const cattl3_conv_geom* g, const S* x, const S* w, const S* dy,
+		S* dw, S* db, S* dx) {
+	CATTL3_CHECK(check_ctx(ctx));
+	int oh, ow;
+	CATTL3_CHECK(check_geom(g, 1, &oh, &ow));
+	CATTL3_REQUIRE(x && w && dy && dw && db, "transconv_backward: null tensor");
+	const long long T = (long long) g->rh * g->rw;
+	// db += sum_n dY, one bias per output element (TransConvKernelLayer.hpp:160-161)
+	CATTL3_CHECK(colsum_accumulate<S>(ctx, g->n, (int64_t) oh * ow * g->f, dy, db));
+	// G = im2col(pad(dY)); dW += x^T G (:165-182); dX = G W^T (:185-187): an ordinary conv of dY
+	GatherGeom gg = fwd_gather(g->n, oh, ow, g->f, g->h, g->w, g->c, g);
+	gg.w_stap = g->c; gg.w_sr = (long long) g->c * T; gg.w_sj = 1;
+	CATTL3_CHECK(run_wgrad<S>(ctx, gg, dy, x, dw));
+	if (!dx)
+		return CATTL3_OK;
+	return run_gather_gemm<S>(ctx, gg, dy, w, (const S*) nullptr, 0, dx);
+}
+
+static cattl3_conv_geom dense_geom(int n, int in, int out) {
+	cattl3_conv_geom g;
+	g.n = n; g.h = 1; g.w = 1; g.c = in; g.f = out;
+	g.rh = g.rw = 1; g.ph = g.pw = 0; g.sh = g.sw = 1; g.dh = g.dw = 0;
+	return g;
+}
+
+} // namespace cattl3
+
+using namespace cattl3;
+
+extern "C" {
+
+int cattl3_abi_version(void) { return CATTL3_ABI_VERSION; }
+const char* cattl3_last_error(void) { return g_error; }
+
+int cattl3_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+int cattl3_ctx_create(cattl3_ctx** out, int device, void* cuda_stream) {
+	CATTL3_REQUIRE(out, "ctx_create: null out pointer");
+	*out = nullptr;
+	int n = cattl3_device_count();
+	if (n <= 0) {
+		set_error("no CUDA device available (libcattl3_b200 has no CPU fallback)");
+		return CATTL3_ERR_NO_DEVICE;
+	}
+	CATTL3_REQUIRE(device >= 0 && device < n, "ctx_create: device %d out of range (%d devices)", device, n);
+	CATTL3_CUDA(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CATTL3_CUDA(cudaGetDeviceProperties(&prop, device));
+	if (prop.major != 10) {
+		set_error("device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+		return CATTL3_ERR_UNSUPPORTED;
+	}
+	cattl3_ctx* ctx = new cattl3_ctx();
+	ctx->device = device;
+	ctx->sm_count = prop.multiProcessorCount;
+	if (cuda_stream) {
+		ctx->stream = (cudaStream_t) cuda_stream;
+	} else {
+		cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+		if (e != cudaSuccess) {
+			delete ctx;
+			return cuda_fail(e, "cudaStreamCreateWithFlags", __FILE__, __LINE__);
+		}
+		ctx->own_stream = true;
+	}
+	*out = ctx;
+	return CATTL3_OK;
+}
+
+int cattl3_ctx_destroy(cattl3_ctx* ctx) {
+	if (!ctx)
+		return CATTL3_OK;
+	cudaSetDevice(ctx->device);
+	cudaStreamSynchronize(ctx->stream);
+	if (ctx->ws) cudaFree(ctx->ws);
+	if (ctx->tc_w) cudaFree(ctx->tc_w);
+	if (ctx->tc_a) cudaFree(ctx->tc_a);
+	for (int i = 0; i < 3; ++i)
+		if (ctx->stage_dev[i]) cudaFree(ctx->stage_dev[i]);
+	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+	delete ctx;
+	return CATTL3_OK;
+}
+
+int cattl3_ctx_synchronize(cattl3_ctx* ctx) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_CUDA(cudaStreamSynchronize(ctx->stream));
+	return CATTL3_OK;
+}
+
+int cattl3_ctx_set_conv_path(cattl3_ctx* ctx, int path) {
+	CATTL3_REQUIRE(ctx && path >= CATTL3_PATH_AUTO && path <= CATTL3_PATH_TCGEN05, "set_conv_path: bad arguments");
+	ctx->conv_path = path;
+	return CATTL3_OK;
+}
+
+int64_t cattl3_ctx_launch_count(const cattl3_ctx* ctx) { return ctx ? ctx->launches : 0; }
+const char* cattl3_ctx_last_path(const cattl3_ctx* ctx) { return ctx ? ctx->last_path : "none"; }
+void* cattl3_ctx_stream(const cattl3_ctx* ctx) { return ctx ? (void*) ctx->stream : nullptr; }
+
+int cattl3_malloc(cattl3_ctx* ctx, void** p, size_t bytes) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(p, "malloc: null out pointer");
+	CATTL3_CUDA(cudaMalloc(p, bytes ? bytes : 1));
+	return CATTL3_OK;
+}
+int cattl3_free(cattl3_ctx* ctx, void* p) {
+	CATTL3_CHECK(check_ctx(ctx));
+	if (p) {
+		CATTL3_CUDA(cudaStreamSynchronize(ctx->stream));
+		CATTL3_CUDA(cudaFree(p));
+	}
+	return CATTL3_OK;
+}
+int cattl3_memset(cattl3_ctx* ctx, void* p, int value, size_t bytes) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_CUDA(cudaMemsetAsync(p, value, bytes, ctx->stream));
+	return CATTL3_OK;
+}
+int cattl3_memcpy_h2d(cattl3_ctx* ctx, void* dst, const void* src, size_t bytes) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	return CATTL3_OK;
+}
+int cattl3_memcpy_d2h(cattl3_ctx* ctx, void* dst, const void* src, size_t bytes) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	CATTL3_CUDA(cudaStreamSynchronize(ctx->stream));
+	return CATTL3_OK;
+}
+int cattl3_memcpy_d2d(cattl3_ctx* ctx, void* dst, const void* src, size_t bytes) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+	return CATTL3_OK;
+}
+int cattl3_host_alloc(void** p, size_t bytes) {
+	CATTL3_REQUIRE(p, "host_alloc: null out pointer");
+	CATTL3_CUDA(cudaMallocHost(p, bytes ? bytes : 1));
+	return CATTL3_OK;
+}
+int cattl3_host_free(void* p) {
+	if (p) CATTL3_CUDA(cudaFreeHost(p));
+	return CATTL3_OK;
+}
+
+int cattl3_conv_output_dims(const cattl3_conv_geom* g, int transposed, int32_t* oh, int32_t* ow) {
+	int a, b;
+	CATTL3_CHECK(check_geom(g, transposed, &a, &b));
+	if (oh) *oh = a;
+	if (ow) *ow = b;
+	return CATTL3_OK;
+}
+
+int cattl3_pool_output_dims(const cattl3_pool_geom* g, int32_t* oh, int32_t* ow) {
+	CATTL3_REQUIRE(g, "null pool geometry");
+	CATTL3_REQUIRE(g->n > 0 && g->h > 0 && g->w > 0 && g->c > 0 && g->rh > 0 && g->rw > 0 && g->sh > 0 && g->sw > 0,
+			"pool geometry: non-positive size");
+	CATTL3_REQUIRE(g->h >= g->rh && g->w >= g->rw, "pool geometry: receptor larger than input");
+	if (oh) *oh = (g->h - g->rh) / g->sh + 1;
+	if (ow) *ow = (g->w - g->rw) / g->sw + 1;
+	return CATTL3_OK;
+}
+
+#define KERNEL_LAYER_API(S, SUF) \
+int cattl3_conv_forward_##SUF(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y) { \
+	return conv_forward<S>(c, g, x, w, b, y); } \
+int cattl3_conv_backward_##SUF(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* dy, S* dw, S* db, S* dx) { \
+	return conv_backward<S>(c, g, x, w, dy, dw, db, dx); } \
+int cattl3_transconv_forward_##SUF(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y) { \
+	return transconv_forward<S>(c, g, x, w, b, y); } \
+int cattl3_transconv_backward_##SUF(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* dy, S* dw, S* db, S* dx) { \
+	return transconv_backward<S>(c, g, x, w, dy, dw, db, dx); } \
+int cattl3_dense_forward_##SUF(cattl3_ctx* c, int32_t n, int32_t in, int32_t out, const S* x, const S* w, const S* b, S* y) { \
+	CATTL3_REQUIRE(n > 0 && in > 0 && out > 0, "dense_forward: non-positive size"); \
+	cattl3_conv_geom g = dense_geom(n, in, out); \
+	return conv_forward<S>(c, &g, x, w, b, y); } \
+int cattl3_dense_backward_##SUF(cattl3_ctx* c, int32_t n, int32_t in, int32_t out, const S* x, const S* w, const S* dy, S* dw, S* db, S* dx) { \
+	CATTL3_REQUIRE(n > 0 && in > 0 && out > 0, "dense_backward: non-positive size"); \
+	cattl3_conv_geom g = dense_geom(n, in, out); \
+	return conv_backward<S>(c, &g, x, w, dy, dw, db, dx); }
+
+KERNEL_LAYER_API(float, f32)
+KERNEL_LAYER_API(double, f64)
+
+// Host-buffer convolution: H2D of the activations, the device kernels, D2H of the result, all on
+// the context's stream; the final D2H synchronises.  x_dev_keep (n*h*w*c floats, optional) receives
+// the device copy of x so that the matching backward call needs no second upload.
+int cattl3_conv_forward_host_f32(cattl3_ctx* ctx, const cattl3_conv_geom* g, const float* x_host, const float* w_dev,
+		const float* b_dev, float* y_host, float* x_dev_keep) {
+	CATTL3_CHECK(check_ctx(ctx));
+	int oh, ow;
+	CATTL3_CHECK(check_geom(g, 0, &oh, &ow));
+	CATTL3_REQUIRE(x_host && y_host, "conv_forward_host: null host tensor");
+	const size_t xb = sizeof(float) * (size_t) g->n * g->h * g->w * g->c;
+	const size_t yb = sizeof(float) * (size_t) g->n * oh * ow * g->f;
+	float* xd = x_dev_keep;
+	if (!xd) {
+		CATTL3_CHECK(ensure_buffer(ctx, &ctx->stage_dev[0], &ctx->stage_dev_bytes[0], xb));
+		xd = (float*) ctx->stage_dev[0];
+	}
+	CATTL3_CHECK(ensure_buffer(ctx, &ctx->stage_dev[1], &ctx->stage_dev_bytes[1], yb));
+	float* yd = (float*) ctx->stage_dev[1];
+	CATTL3_CUDA(cudaMemcpyAsync(xd, x_host, xb, cudaMemcpyHostToDevice, ctx->stream));
+	CATTL3_CHECK(conv_forward<float>(ctx, g, xd, w_dev, b_dev, yd));
+	CATTL3_CUDA(cudaMemcpyAsync(y_host, yd, yb, cudaMemcpyDeviceToHost, ctx->stream));
+	CATTL3_CUDA(cudaStreamSynchronize(ctx->stream));
+	return CATTL3_OK;
+}
+
+int cattl3_conv_backward_host_f32(cattl3_ctx* ctx, const cattl3_conv_geom* g, const float* x_dev, const float* w_dev,
+		const float* dy_host, float* dw_dev, float* db_dev, float* dx_host) {
+	CATTL3_CHECK(check_ctx(ctx));
+	int oh, ow;
+	CATTL3_CHECK(check_geom(g, 0, &oh, &ow));
+	CATTL3_REQUIRE(x_dev && dy_host, "conv_backward_host: null tensor");
+	const size_t xb = sizeof(float) * (size_t) g->n * g->h * g->w * g->c;
+	const size_t yb = sizeof(float) * (size_t) g->n * oh * ow * g->f;
+	CATTL3_CHECK(ensure_buffer(ctx, &ctx->stage_dev[1], &ctx->stage_dev_bytes[1], yb));
+	float* dyd = (float*) ctx->stage_dev[1];
+	float* dxd = nullptr;
+	if (dx_host) {
+		CATTL3_CHECK(ensure_buffer(ctx, &ctx->stage_dev[2], &ctx->stage_dev_bytes[2], xb));
+		dxd = (float*) ctx->stage_dev[2];
+	}
+	CATTL3_CUDA(cudaMemcpyAsync(dyd, dy_host, yb, cudaMemcpyHostToDevice, ctx->stream));
+	CATTL3_CHECK(conv_backward<float>(ctx, g, x_dev, w_dev, dyd, dw_dev, db_dev, dxd));
+	if (dx_host)
+		CATTL3_CUDA(cudaMemcpyAsync(dx_host, dxd, xb, cudaMemcpyDeviceToHost, ctx->stream));
+	CATTL3_CUDA(cudaStreamSynchronize(ctx->stream));
+	return CATTL3_OK;
+}
+
+}

@@ -1,0 +1,104 @@
+// common.cuh -- context, error handling and launch helpers shared by all translation units of
+// libcattl3_b200.so.  sm_100a only.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/cattl3_b200.h"
+
+struct cattl3_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	int conv_path = CATTL3_PATH_AUTO;
+	int64_t launches = 0;
+	const char* last_path = "none";
+	int sm_count = 148;
+	// general scratch (split-K partials, batch-norm partial sums); grown on demand, never shrunk
+	void* ws = nullptr;
+	size_t ws_bytes = 0;
+	// tcgen05 path scratch: packed / split weights and the low-order activation split
+	void* tc_w = nullptr;
+	size_t tc_w_bytes = 0;
+	void* tc_a = nullptr;
+	size_t tc_a_bytes = 0;
+	// pinned staging for the *_host entry points
+	void* stage_dev[3] = { nullptr, nullptr, nullptr };
+	size_t stage_dev_bytes[3] = { 0, 0, 0 };
+};
+
+namespace cattl3 {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+int ensure_buffer(cattl3_ctx* ctx, void** buf, size_t* cur, size_t need);
+
+#define CATTL3_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) \
+	return cattl3::cuda_fail(e__, #call, __FILE__, __LINE__); } while (0)
+
+#define CATTL3_REQUIRE(cond, ...) do { if (!(cond)) { cattl3::set_error(__VA_ARGS__); \
+	return CATTL3_ERR_INVALID; } } while (0)
+
+#define CATTL3_CHECK(expr) do { int rc__ = (expr); if (rc__ != CATTL3_OK) return rc__; } while (0)
+
+// Checks the launch and counts it (bench.py reports the count as gpu_launches).
+#define CATTL3_LAUNCHED(ctx) do { (ctx)->launches++; cudaError_t e__ = cudaGetLastError(); \
+	if (e__ != cudaSuccess) return cattl3::cuda_fail(e__, "kernel launch", __FILE__, __LINE__); } while (0)
+
+inline int check_ctx(cattl3_ctx* ctx) {
+	if (!ctx) {
+		set_error("null context");
+		return CATTL3_ERR_INVALID;
+	}
+	cudaError_t e = cudaSetDevice(ctx->device);
+	if (e != cudaSuccess)
+		return cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__);
+	return CATTL3_OK;
+}
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Grid for a grid-stride element-wise kernel: enough CTAs for `work` items at `per_block`
+// items each, capped at a multiple of the SM count (8 resident 256-thread CTAs per SM).
+inline int ew_grid(const cattl3_ctx* ctx, int64_t work, int per_block) {
+	int64_t blocks = ceil_div(work, per_block);
+	int64_t cap = (int64_t) ctx->sm_count * 8;
+	if (blocks > cap) blocks = cap;
+	if (blocks < 1) blocks = 1;
+	return (int) blocks;
+}
+
+// ---- kernel-layer entry points implemented per translation unit ------------------------------
+
+// Description of one implicit-GEMM pass over a gathered tensor.  See conv_simt.cu.
+struct GatherGeom {
+	int N;              // batch (fastest dim of every tensor)
+	int SH, SW, SC;     // gathered ("source") tensor spatial dims and channels (reduce channels R)
+	int OH, OW;         // grid of the output / plain tensor; M = N*OH*OW
+	int J;              // output channels
+	int RH, RW;         // taps
+	// source coordinate: t = o*a + r*b + c; valid iff t % den == 0 and 0 <= t/den < S
+	int ah, bh, ch, denh;
+	int aw, bw, cw, denw;
+	// weight element (tap = rh + RH*rw, reduce channel r, output channel j)
+	long long w_stap, w_sr, w_sj;
+};
+
+template<typename S>
+int simt_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* w, const S* bias,
+		int bias_mode, S* out);
+template<typename S>
+int simt_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* plain, S* dw);
+template<typename S>
+int colsum_accumulate(cattl3_ctx* ctx, int64_t rows, int64_t cols, const S* a, S* out);
+
+// tcgen05 path (conv_tc.cu): returns CATTL3_ERR_UNSUPPORTED when the shape does not qualify.
+bool tc_gather_gemm_supported(const cattl3_ctx* ctx, const GatherGeom& gg);
+int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const float* w,
+		const float* bias, int bias_mode, float* out);
+bool tc_wgrad_supported(const cattl3_ctx* ctx, const GatherGeom& gg);
+int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const float* plain, float* dw);
+
+} // namespace cattl3

@@ -1,0 +1,292 @@
+// conv_simt.cu -- FFMA / DFMA implicit-GEMM kernels: the any-shape path of the kernel layers
+// (float and double) and the product path of the double instantiation.
+//
+// One "gather GEMM" covers ConvKernelLayer forward and input-gradient, TransConvKernelLayer
+// forward and input-gradient and DenseKernelLayer forward / input-gradient: the A operand is
+// never materialised (no im2col buffer in HBM, unlike C-ATTL3/layer/kernel/ConvKernelLayer.hpp:127);
+// its element (m, tap, r) is read straight from the source tensor at the coordinate the
+// GatherGeom describes.  The batch index n is the fastest dimension of every tensor
+// (C-ATTL3/core/EigenProxy.hpp:56-57), so a run of consecutive m for a fixed tap / channel is
+// contiguous in HBM: global loads and the output stores are coalesced along m.
+//
+// The weight gradient is a split-K reduction over m = N*OH*OW with a deterministic second stage
+// that ACCUMULATES into the gradient (Parameters::accumulate_grad semantics,
+// C-ATTL3/parameters/StandardParameters.hpp:115-123).
+#include "common.cuh"
+
+namespace cattl3 {
+
+template<typename S> struct Vec;
+template<> struct Vec<float> { typedef float4 type; static constexpr int G = 4; };
+template<> struct Vec<double> { typedef double2 type; static constexpr int G = 2; };
+
+// ------------------------------------------------------------------------------------------------
+// gather GEMM: out[m + M*j] = bias + sum_{tap, r} src(m, tap, r) * w(tap, r, j)
+// block tile BM x 64, BK = 16, 256 threads, each thread 2 groups of G rows x 4 columns.
+// ------------------------------------------------------------------------------------------------
+template<typename S>
+__global__ void __launch_bounds__(256) gather_gemm_kernel(GatherGeom gg, const S* __restrict__ src,
+		const S* __restrict__ w, const S* __restrict__ bias, int bias_mode, S* __restrict__ out) {
+	constexpr int G = Vec<S>::G;
+	constexpr int BM = 32 * G, BN = 64, BK = 16;
+	constexpr int A_ROWS = 256 / BM, A_ITERS = BK / A_ROWS;
+	typedef typename Vec<S>::type V;
+	__shared__ __align__(16) S As[BK][BM];
+	__shared__ __align__(16) S Bs[BK][BN];
+
+	const int tid = threadIdx.x, tm = tid & 15, tn = tid >> 4;
+	const long long M = (long long) gg.N * gg.OH * gg.OW;
+	const long long m0 = (long long) blockIdx.x * BM;
+	const int j0 = blockIdx.y * BN;
+	const int T = gg.RH * gg.RW, R = gg.SC, J = gg.J;
+	const long long plane = (long long) gg.N * gg.SH * gg.SW;
+
+	// A-loader coordinates: this thread always loads row a_ml of the tile
+	const int a_ml = tid % BM, a_k0 = tid / BM;
+	const long long am = m0 + a_ml;
+	const bool m_ok = am < M;
+	const int an = (int) (am % gg.N);
+	const long long apix = am / gg.N;
+	const int aoh = (int) (apix % gg.OH), aow = (int) (apix / gg.OH);
+	// B-loader coordinates
+	const int b_jj = tid & 63, b_k0 = tid >> 6;
+
+	S acc[2 * G][4];
+	#pragma unroll
+	for (int i = 0; i < 2 * G; ++i)
+		#pragma unroll
+		for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+
+	for (int tap = 0; tap < T; ++tap) {
+		const int rh = tap % gg.RH, rw = tap / gg.RH;
+		const int th = aoh * gg.ah + rh * gg.bh + gg.ch;
+		const int tw = aow * gg.aw + rw * gg.bw + gg.cw;
+		bool ok = m_ok && th >= 0 && tw >= 0 && (th % gg.denh) == 0 && (tw % gg.denw) == 0;
+		const int ih = th / gg.denh, iw = tw / gg.denw;
+		ok = ok && ih < gg.SH && iw < gg.SW;
+		const long long base = an + (long long) gg.N * (ih + (long long) gg.SH * iw);
+		const long long wtap = tap * gg.w_stap;
+		for (int r0 = 0; r0 < R; r0 += BK) {
+			#pragma unroll
+			for (int i = 0; i < A_ITERS; ++i) {
+				const int kk = a_k0 + A_ROWS * i, r = r0 + kk;
+				As[kk][a_ml] = (ok && r < R) ? src[base + r * plane] : (S) 0;
+			}
+			#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				const int kk = b_k0 + 4 * i, r = r0 + kk, j = j0 + b_jj;
+				Bs[kk][b_jj] = (r < R && j < J) ? w[wtap + r * gg.w_sr + j * gg.w_sj] : (S) 0;
+			}
+			__syncthreads();
+			#pragma unroll
+			for (int kk = 0; kk < BK; ++kk) {
+				S a[2 * G], b[4];
+				*reinterpret_cast<V*>(&a[0]) = *reinterpret_cast<const V*>(&As[kk][tm * G]);
+				*reinterpret_cast<V*>(&a[G]) = *reinterpret_cast<const V*>(&As[kk][BM / 2 + tm * G]);
+				if (G == 4) {
+					*reinterpret_cast<V*>(&b[0]) = *reinterpret_cast<const V*>(&Bs[kk][tn * 4]);
+				} else {
+					*reinterpret_cast<V*>(&b[0]) = *reinterpret_cast<const V*>(&Bs[kk][tn * 4]);
+					*reinterpret_cast<V*>(&b[2]) = *reinterpret_cast<const V*>(&Bs[kk][tn * 4 + 2]);
+				}
+				#pragma unroll
+				for (int i = 0; i < 2 * G; ++i)
+					#pragma unroll
+					for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+			}
+			__syncthreads();
+		}
+	}
+	const long long P = (long long) gg.OH * gg.OW;
+	#pragma unroll
+	for (int g = 0; g < 2; ++g) {
+		#pragma unroll
+		for (int jj = 0; jj < 4; ++jj) {
+			const int j = j0 + tn * 4 + jj;
+			if (j >= J) continue;
+			#pragma unroll
+			for (int e = 0; e < G; ++e) {
+				const long long m = m0 + g * (BM / 2) + tm * G + e;
+				if (m >= M) continue;
+				S v = acc[g * G + e][jj];
+				if (bias_mode == 1) v += bias[j];
+				else if (bias_mode == 2) v += bias[m / gg.N + P * j];
+				out[m + M * j] = v;
+			}
+		}
+	}
+}
+
+template<typename S>
+int simt_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* w, const S* bias,
+		int bias_mode, S* out) {
+	constexpr int BM = 32 * Vec<S>::G;
+	const long long M = (long long) gg.N * gg.OH * gg.OW;
+	dim3 grid((unsigned) ceil_div(M, BM), (unsigned) ceil_div(gg.J, 64));
+	gather_gemm_kernel<S><<<grid, 256, 0, ctx->stream>>>(gg, src, w, bias, bias_mode, out);
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+template int simt_gather_gemm<float>(cattl3_ctx*, const GatherGeom&, const float*, const float*, const float*, int, float*);
+template int simt_gather_gemm<double>(cattl3_ctx*, const GatherGeom&, const double*, const double*, const double*, int, double*);
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient: dw(tap, r, j) += sum_m src(m, tap, r) * plain[m + M*j]
+// grid (T * ceil(R/64), ceil(J/64), splits); each block reduces its m range into a 64 x 64 tile
+// of a per-split partial buffer; wgrad_reduce_kernel then adds the partials to dw in split order.
+// ------------------------------------------------------------------------------------------------
+template<typename S>
+__global__ void __launch_bounds__(256) wgrad_kernel(GatherGeom gg, const S* __restrict__ src,
+		const S* __restrict__ plain, S* __restrict__ partial, long long m_per_split, long long dw_elems) {
+	constexpr int BKM = 32, BT = 64;
+	typedef typename Vec<S>::type V;
+	constexpr int G = Vec<S>::G;
+	// +4 padding: the loaders write a column at a time (consecutive threads = consecutive m)
+	__shared__ __align__(16) S As[BKM][BT + 4];
+	__shared__ __align__(16) S Bs[BKM][BT + 4];
+	const int tid = threadIdx.x, tr = tid & 15, tj = tid >> 4;
+	const int T = gg.RH * gg.RW, R = gg.SC, J = gg.J;
+	const int tap = blockIdx.x % T, r0 = (blockIdx.x / T) * BT, j0 = blockIdx.y * BT;
+	const int rh = tap % gg.RH, rw = tap / gg.RH;
+	const long long M = (long long) gg.N * gg.OH * gg.OW;
+	const long long ms = (long long) blockIdx.z * m_per_split;
+	const long long me = (ms + m_per_split < M) ? ms + m_per_split : M;
+	const long long plane = (long long) gg.N * gg.SH * gg.SW;
+	const int l_mm = tid & 31, l_c0 = tid >> 5;
+
+	S acc[4][4];
+	#pragma unroll
+	for (int i = 0; i < 4; ++i)
+		#pragma unroll
+		for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+
+	for (long long mc = ms; mc < me; mc += BKM) {
+		const long long m = mc + l_mm;
+		bool ok = m < me;
+		const int n = (int) (m % gg.N);
+		const long long pix = m / gg.N;
+		const int oh = (int) (pix % gg.OH), ow = (int) (pix / gg.OH);
+		const int th = oh * gg.ah + rh * gg.bh + gg.ch;
+		const int tw = ow * gg.aw + rw * gg.bw + gg.cw;
+		bool aok = ok && th >= 0 && tw >= 0 && (th % gg.denh) == 0 && (tw % gg.denw) == 0;
+		const int ih = th / gg.denh, iw = tw / gg.denw;
+		aok = aok && ih < gg.SH && iw < gg.SW;
+		const long long base = n + (long long) gg.N * (ih + (long long) gg.SH * iw);
+		#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			const int col = l_c0 + 8 * i;
+			const int r = r0 + col, j = j0 + col;
+			As[l_mm][col] = (aok && r < R) ? src[base + r * plane] : (S) 0;
+			Bs[l_mm][col] = (ok && j < J) ? plain[m + M * j] : (S) 0;
+		}
+		__syncthreads();
+		#pragma unroll
+		for (int mk = 0; mk < BKM; ++mk) {
+			S a[4], b[4];
+			if (G == 4) {
+				*reinterpret_cast<V*>(&a[0]) = *reinterpret_cast<const V*>(&As[mk][tr * 4]);
+				*reinterpret_cast<V*>(&b[0]) = *reinterpret_cast<const V*>(&Bs[mk][tj * 4]);
+			} else {
+				*reinterpret_cast<V*>(&a[0]) = *reinterpret_cast<const V*>(&As[mk][tr * 4]);
+				*reinterpret_cast<V*>(&a[2]) = *reinterpret_cast<const V*>(&As[mk][tr * 4 + 2]);
+				*reinterpret_cast<V*>(&b[0]) = *reinterpret_cast<const V*>(&Bs[mk][tj * 4]);
+				*reinterpret_cast<V*>(&b[2]) = *reinterpret_cast<const V*>(&Bs[mk][tj * 4 + 2]);
+			}
+			#pragma unroll
+			for (int i = 0; i < 4; ++i)
+				#pragma unroll
+				for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+		}
+		__syncthreads();
+	}
+	S* dst = partial + (long long) blockIdx.z * dw_elems;
+	#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		const int r = r0 + tr * 4 + i;
+		if (r >= R) continue;
+		#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int jj = j0 + tj * 4 + j;
+			if (jj < J) dst[tap * gg.w_stap + r * gg.w_sr + jj * gg.w_sj] = acc[i][j];
+		}
+	}
+}
+
+template<typename S>
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const S* __restrict__ partial, int splits,
+		long long elems, S* __restrict__ dw) {
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < elems; i += (long long) gridDim.x * 256) {
+		S s = 0;
+		for (int z = 0; z < splits; ++z) s += partial[(long long) z * elems + i];
+		dw[i] += s;
+	}
+}
+
+template<typename S>
+int simt_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* plain, S* dw) {
+	const int T = gg.RH * gg.RW, R = gg.SC, J = gg.J;
+	const long long M = (long long) gg.N * gg.OH * gg.OW;
+	const long long elems = (long long) T * R * J;
+	const long long gx = (long long) T * ceil_div(R, 64), gy = ceil_div(J, 64);
+	long long splits = ceil_div(4ll * ctx->sm_count, gx * gy);
+	const long long max_splits = ceil_div(M, 256);
+	if (splits > max_splits) splits = max_splits;
+	if (splits < 1) splits = 1;
+	long long m_per_split = ceil_div(ceil_div(M, splits), 32) * 32;
+	splits = ceil_div(M, m_per_split);
+	CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, (size_t) (splits * elems) * sizeof(S)));
+	dim3 grid((unsigned) gx, (unsigned) gy, (unsigned) splits);
+	wgrad_kernel<S><<<grid, 256, 0, ctx->stream>>>(gg, src, plain, (S*) ctx->ws, m_per_split, elems);
+	CATTL3_LAUNCHED(ctx);
+	wgrad_reduce_kernel<S><<<ew_grid(ctx, elems, 256), 256, 0, ctx->stream>>>((const S*) ctx->ws,
+			(int) splits, elems, dw);
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+template int simt_wgrad<float>(cattl3_ctx*, const GatherGeom&, const float*, const float*, float*);
+template int simt_wgrad<double>(cattl3_ctx*, const GatherGeom&, const double*, const double*, double*);
+
+// ------------------------------------------------------------------------------------------------
+// out[col] += sum_{row} a[row + rows*col]   (bias gradients: ConvKernelLayer.hpp:155,
+// TransConvKernelLayer.hpp:160-161, DenseKernelLayer.hpp:109).  Fixed reduction tree => deterministic.
+// ------------------------------------------------------------------------------------------------
+template<typename S>
+__global__ void __launch_bounds__(256) colsum_block_kernel(long long rows, const S* __restrict__ a,
+		S* __restrict__ out) {
+	__shared__ S red[256];
+	const S* col = a + rows * (long long) blockIdx.x;
+	S s = 0;
+	for (long long i = threadIdx.x; i < rows; i += 256) s += col[i];
+	red[threadIdx.x] = s;
+	__syncthreads();
+	for (int o = 128; o > 0; o >>= 1) {
+		if ((int) threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) out[blockIdx.x] += red[0];
+}
+
+template<typename S>
+__global__ void __launch_bounds__(256) colsum_thread_kernel(long long rows, long long cols,
+		const S* __restrict__ a, S* __restrict__ out) {
+	for (long long c = blockIdx.x * 256ll + threadIdx.x; c < cols; c += (long long) gridDim.x * 256) {
+		S s = 0;
+		for (long long i = 0; i < rows; ++i) s += a[i + rows * c];
+		out[c] += s;
+	}
+}
+
+template<typename S>
+int colsum_accumulate(cattl3_ctx* ctx, int64_t rows, int64_t cols, const S* a, S* out) {
+	if (rows >= 128) {
+		colsum_block_kernel<S><<<(unsigned) cols, 256, 0, ctx->stream>>>(rows, a, out);
+	} else {
+		colsum_thread_kernel<S><<<ew_grid(ctx, cols, 256), 256, 0, ctx->stream>>>(rows, cols, a, out);
+	}
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+template int colsum_accumulate<float>(cattl3_ctx*, int64_t, int64_t, const float*, float*);
+template int colsum_accumulate<double>(cattl3_ctx*, int64_t, int64_t, const double*, double*);
+
+} // namespace cattl3

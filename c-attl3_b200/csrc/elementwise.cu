@@ -1,0 +1,655 @@
+// elementwise.cu -- the HBM-bound layers around the kernel layers: activations, pooling, batch
+// normalisation, the fused optimizer step and the small network-glue helpers.  All kernels are
+// grid-stride with 16-byte vector accesses where alignment allows, sized in multiples of the SM
+// count (common.cuh: ew_grid); none of them stages through shared memory except reductions.
+#include "common.cuh"
+
+namespace cattl3 {
+
+template<typename S> struct V16;
+template<> struct V16<float> { typedef float4 type; static constexpr int G = 4; };
+template<> struct V16<double> { typedef double2 type; static constexpr int G = 2; };
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template<typename S> __device__ __forceinline__ S dev_exp(S v);
+template<> __device__ __forceinline__ float dev_exp<float>(float v) { return expf(v); }
+template<> __device__ __forceinline__ double dev_exp<double>(double v) { return exp(v); }
+template<typename S> __device__ __forceinline__ S dev_log(S v);
+template<> __device__ __forceinline__ float dev_log<float>(float v) { return logf(v); }
+template<> __device__ __forceinline__ double dev_log<double>(double v) { return log(v); }
+template<typename S> __device__ __forceinline__ S dev_tanh(S v);
+template<> __device__ __forceinline__ float dev_tanh<float>(float v) { return tanhf(v); }
+template<> __device__ __forceinline__ double dev_tanh<double>(double v) { return tanh(v); }
+template<typename S> __device__ __forceinline__ S dev_sqrt(S v);
+template<> __device__ __forceinline__ float dev_sqrt<float>(float v) { return sqrtf(v); }
+template<> __device__ __forceinline__ double dev_sqrt<double>(double v) { return sqrt(v); }
+
+// ---- activations -------------------------------------------------------------------------------
+// Formulas follow the reference layer by layer (see include/cattl3_b200.h for file:line).
+template<typename S, int KIND>
+__device__ __forceinline__ S act_fwd(S x, S a) {
+	if (KIND == CATTL3_ACT_RELU) return x > (S) 0 ? x : (S) 0;              // cwiseMax(0)
+	if (KIND == CATTL3_ACT_LEAKY_RELU) { S ax = x * a; return x > ax ? x : ax; } // cwiseMax(x * alpha)
+	if (KIND == CATTL3_ACT_ELU) return x >= (S) 0 ? x : a * (dev_exp<S>(x) - (S) 1);
+	if (KIND == CATTL3_ACT_SWISH) return x * ((S) 1 / (dev_exp<S>(-a * x) + (S) 1));
+	if (KIND == CATTL3_ACT_SIGMOID) return (S) 1 / (dev_exp<S>(-x) + (S) 1);
+	if (KIND == CATTL3_ACT_TANH) return dev_tanh<S>(x);
+	if (KIND == CATTL3_ACT_SOFTPLUS) return dev_log<S>(dev_exp<S>(x) + (S) 1);
+	return x;
+}
+
+template<typename S, int KIND>
+__device__ __forceinline__ S act_bwd(S x, S y, S g, S a) {
+	if (KIND == CATTL3_ACT_RELU) return x >= (S) 0 ? g : (S) 0;             // derivative 1 at x == 0
+	if (KIND == CATTL3_ACT_LEAKY_RELU) return x >= (S) 0 ? g : a * g;
+	if (KIND == CATTL3_ACT_ELU) return x >= (S) 0 ? g : (y + a) * g;
+	if (KIND == CATTL3_ACT_SWISH) {
+		S s = (S) 1 / (dev_exp<S>(-a * x) + (S) 1);
+		return s * (((S) 1 - s) * a * x + (S) 1) * g;
+	}
+	if (KIND == CATTL3_ACT_SIGMOID) return (y * ((S) 1 - y)) * g;
+	if (KIND == CATTL3_ACT_TANH) return ((S) 1 - y * y) * g;
+	if (KIND == CATTL3_ACT_SOFTPLUS) return ((S) 1 / (dev_exp<S>(-x) + (S) 1)) * g;
+	return g;
+}
+
+template<typename S, int KIND>
+__global__ void __launch_bounds__(256) act_fwd_kernel(long long count, int vec_ok, S alpha,
+		const S* __restrict__ x, S* __restrict__ y) {
+	typedef typename V16<S>::type V;
+	constexpr int G = V16<S>::G;
+	const long long nvec = vec_ok ? count / G : 0;
+	const long long stride = (long long) gridDim.x * 256;
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < nvec; i += stride) {
+		V v = reinterpret_cast<const V*>(x)[i];
+		S* e = reinterpret_cast<S*>(&v);
+		#pragma unroll
+		for (int k = 0; k < G; ++k) e[k] = act_fwd<S, KIND>(e[k], alpha);
+		reinterpret_cast<V*>(y)[i] = v;
+	}
+	for (long long i = nvec * G + blockIdx.x * 256ll + threadIdx.x; i < count; i += stride)
+		y[i] = act_fwd<S, KIND>(x[i], alpha);
+}
+
+template<typename S, int KIND>
+__global__ void __launch_bounds__(256) act_bwd_kernel(long long count, int vec_ok, S alpha,
+		const S* __restrict__ x, const S* __restrict__ y, const S* __restrict__ dy, S* __restrict__ dx) {
+	typedef typename V16<S>::type V;
+	constexpr int G = V16<S>::G;
+	constexpr bool NEED_X = KIND == CATTL3_ACT_RELU || KIND == CATTL3_ACT_LEAKY_RELU ||
+			KIND == CATTL3_ACT_ELU || KIND == CATTL3_ACT_SWISH || KIND == CATTL3_ACT_SOFTPLUS;
+	constexpr bool NEED_Y = KIND == CATTL3_ACT_ELU || KIND == CATTL3_ACT_SIGMOID || KIND == CATTL3_ACT_TANH;
+	const long long nvec = vec_ok ? count / G : 0;
+	const long long stride = (long long) gridDim.x * 256;
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < nvec; i += stride) {
+		V vx, vy, vg = reinterpret_cast<const V*>(dy)[i];
+		if (NEED_X) vx = reinterpret_cast<const V*>(x)[i];
+		if (NEED_Y) vy = reinterpret_cast<const V*>(y)[i];
+		S* ex = reinterpret_cast<S*>(&vx);
+		S* ey = reinterpret_cast<S*>(&vy);
+		S* eg = reinterpret_cast<S*>(&vg);
+		#pragma unroll
+		for (int k = 0; k < G; ++k)
+			eg[k] = act_bwd<S, KIND>(NEED_X ? ex[k] : (S) 0, NEED_Y ? ey[k] : (S) 0, eg[k], alpha);
+		reinterpret_cast<V*>(dx)[i] = vg;
+	}
+	for (long long i = nvec * G + blockIdx.x * 256ll + threadIdx.x; i < count; i += stride)
+		dx[i] = act_bwd<S, KIND>(NEED_X ? x[i] : (S) 0, NEED_Y ? y[i] : (S) 0, dy[i], alpha);
+}
+
+// Softmax over `vol` for each of `rows` rows (rows fastest): one thread per row keeps the accesses
+// of a warp coalesced (consecutive rows are adjacent in memory).  SoftmaxActivationLayer.hpp:49-78.
+template<typename S>
+__global__ void __launch_bounds__(128) softmax_fwd_kernel(long long rows, long long vol, S eps,
+		const S* __restrict__ x, S* __restrict__ y) {
+	for (long long r = blockIdx.x * 128ll + threadIdx.x; r < rows; r += (long long) gridDim.x * 128) {
+		S mx = x[r];
+		for (long long j = 1; j < vol; ++j) { S v = x[r + rows * j]; mx = v > mx ? v : mx; }
+		S sum = 0;
+		for (long long j = 0; j < vol; ++j) sum += dev_exp<S>(x[r + rows * j] - mx);
+		const S den = sum + eps;
+		for (long long j = 0; j < vol; ++j) y[r + rows * j] = dev_exp<S>(x[r + rows * j] - mx) / den;
+	}
+}
+
+template<typename S>
+__global__ void __launch_bounds__(128) softmax_bwd_kernel(long long rows, long long vol,
+		const S* __restrict__ y, const S* __restrict__ dy, S* __restrict__ dx) {
+	for (long long r = blockIdx.x * 128ll + threadIdx.x; r < rows; r += (long long) gridDim.x * 128) {
+		S dot = 0;
+		for (long long j = 0; j < vol; ++j) dot += y[r + rows * j] * dy[r + rows * j];
+		for (long long j = 0; j < vol; ++j) dx[r + rows * j] = y[r + rows * j] * (dy[r + rows * j] - dot);
+	}
+}
+
+template<typename S>
+int activation_forward(cattl3_ctx* ctx, int kind, S alpha, int64_t rows, int64_t vol, const S* x, S* y) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(rows > 0 && vol > 0 && x && y, "activation_forward: bad arguments");
+	const long long count = rows * vol;
+	const int grid = ew_grid(ctx, ceil_div(count, V16<S>::G), 256);
+	const int vec_ok = aligned16(x) && aligned16(y);
+	switch (kind) {
+#define CASE(K) case K: act_fwd_kernel<S, K><<<grid, 256, 0, ctx->stream>>>(count, vec_ok, alpha, x, y); break;
+		CASE(CATTL3_ACT_RELU) CASE(CATTL3_ACT_LEAKY_RELU) CASE(CATTL3_ACT_ELU) CASE(CATTL3_ACT_SWISH)
+		CASE(CATTL3_ACT_SIGMOID) CASE(CATTL3_ACT_TANH) CASE(CATTL3_ACT_SOFTPLUS)
+#undef CASE
+		case CATTL3_ACT_SOFTMAX:
+			softmax_fwd_kernel<S><<<ew_grid(ctx, rows, 128), 128, 0, ctx->stream>>>(rows, vol, alpha, x, y);
+			break;
+		default:
+			set_error("activation_forward: unknown kind %d", kind);
+			return CATTL3_ERR_INVALID;
+	}
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+
+template<typename S>
+int activation_backward(cattl3_ctx* ctx, int kind, S alpha, int64_t rows, int64_t vol, const S* x,
+		const S* y, const S* dy, S* dx) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(rows > 0 && vol > 0 && dy && dx, "activation_backward: bad arguments");
+	const long long count = rows * vol;
+	const int grid = ew_grid(ctx, ceil_div(count, V16<S>::G), 256);
+	const int vec_ok = aligned16(x) && aligned16(y) && aligned16(dy) && aligned16(dx);
+	switch (kind) {
+#define CASE(K) case K: act_bwd_kernel<S, K><<<grid, 256, 0, ctx->stream>>>(count, vec_ok, alpha, x, y, dy, dx); break;
+		CASE(CATTL3_ACT_RELU) CASE(CATTL3_ACT_LEAKY_RELU) CASE(CATTL3_ACT_ELU) CASE(CATTL3_ACT_SWISH)
+		CASE(CATTL3_ACT_SIGMOID) CASE(CATTL3_ACT_TANH) CASE(CATTL3_ACT_SOFTPLUS)
+#undef CASE
+		case CATTL3_ACT_SOFTMAX:
+			CATTL3_REQUIRE(y, "softmax backward needs the cached output");
+			softmax_bwd_kernel<S><<<ew_grid(ctx, rows, 128), 128, 0, ctx->stream>>>(rows, vol, y, dy, dx);
+			break;
+		default:
+			set_error("activation_backward: unknown kind %d", kind);
+			return CATTL3_ERR_INVALID;
+	}
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+
+// ---- pooling -------------------------------------------------------------------------------------
+// One thread per output element, n fastest => coalesced reads of every window tap and coalesced
+// writes.  Max: strict '>' from lowest(), width-outer / height-inner scan (MaxPoolLayer.hpp:45-58).
+template<typename S> __device__ __forceinline__ S lowest();
+template<> __device__ __forceinline__ float lowest<float>() { return -3.402823466e+38f; }
+template<> __device__ __forceinline__ double lowest<double>() { return -1.7976931348623157e+308; }
+
+template<typename S, int KIND>
+__global__ void __launch_bounds__(256) pool_fwd_kernel(cattl3_pool_geom g, int OH, int OW,
+		const S* __restrict__ x, S* __restrict__ y, uint8_t* __restrict__ argmax) {
+	const long long total = (long long) g.n * OH * OW * g.c;
+	for (long long o = blockIdx.x * 256ll + threadIdx.x; o < total; o += (long long) gridDim.x * 256) {
+		const int n = (int) (o % g.n);
+		long long t = o / g.n;
+		const int oh = (int) (t % OH); t /= OH;
+		const int ow = (int) (t % OW);
+		const int c = (int) (t / OW);
+		const S* base = x + n + (long long) g.n * (oh * g.sh + (long long) g.h * (ow * g.sw + (long long) g.w * c));
+		if (KIND == CATTL3_POOL_MAX) {
+			S best = lowest<S>();
+			int bi = 0;
+			for (int k = 0; k < g.rw; ++k)
+				for (int l = 0; l < g.rh; ++l) {
+					const S v = base[(long long) g.n * (l + (long long) g.h * k)];
+					if (v > best) { best = v; bi = k * g.rh + l; }
+				}
+			y[o] = best;
+			if (argmax) argmax[o] = (uint8_t) bi;
+		} else {
+			S s = 0;
+			for (int k = 0; k < g.rw; ++k)
+				for (int l = 0; l < g.rh; ++l)
+					s += base[(long long) g.n * (l + (long long) g.h * k)];
+			y[o] = s / (S) (g.rh * g.rw);
+		}
+	}
+}
+
+// Gather form of PoolLayer::_pass_back (PoolLayer.hpp:98-116): one thread per INPUT element sums
+// the contributions of every window that covers it (overlapping windows accumulate), no atomics.
+template<typename S, int KIND>
+__global__ void __launch_bounds__(256) pool_bwd_kernel(cattl3_pool_geom g, int OH, int OW,
+		const S* __restrict__ dy, const uint8_t* __restrict__ argmax, S* __restrict__ dx) {
+	const long long total = (long long) g.n * g.h * g.w * g.c;
+	const S inv_area = (S) 1 / (S) (g.rh * g.rw);
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long) gridDim.x * 256) {
+		const int n = (int) (i % g.n);
+		long long t = i / g.n;
+		const int h = (int) (t % g.h); t /= g.h;
+		const int w = (int) (t % g.w);
+		const int c = (int) (t / g.w);
+		int oh_lo = h - g.rh + 1; oh_lo = oh_lo <= 0 ? 0 : (oh_lo + g.sh - 1) / g.sh;
+		int ow_lo = w - g.rw + 1; ow_lo = ow_lo <= 0 ? 0 : (ow_lo + g.sw - 1) / g.sw;
+		int oh_hi = h / g.sh; if (oh_hi > OH - 1) oh_hi = OH - 1;
+		int ow_hi = w / g.sw; if (ow_hi > OW - 1) ow_hi = OW - 1;
+		S s = 0;
+		for (int ow = ow_lo; ow <= ow_hi; ++ow)
+			for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+				const long long o = n + (long long) g.n * (oh + (long long) OH * (ow + (long long) OW * c));
+				if (KIND == CATTL3_POOL_MAX) {
+					const int idx = (w - ow * g.sw) * g.rh + (h - oh * g.sh);
+					if ((int) argmax[o] == idx) s += dy[o];
+				} else {
+					s += dy[o] * inv_area;
+				}
+			}
+		dx[i] = s;
+	}
+}
+
+template<typename S>
+int pool_forward(cattl3_ctx* ctx, int kind, const cattl3_pool_geom* g, const S* x, S* y, uint8_t* argmax) {
+	CATTL3_CHECK(check_ctx(ctx));
+	int32_t oh, ow;
+	CATTL3_CHECK(cattl3_pool_output_dims(g, &oh, &ow));
+	CATTL3_REQUIRE(x && y, "pool_forward: null tensor");
+	const long long total = (long long) g->n * oh * ow * g->c;
+	const int grid = ew_grid(ctx, total, 256);
+	if (kind == CATTL3_POOL_MAX) {
+		if (g->rh * g->rw > 256) {
+			set_error("pool_forward: max-pool windows above 256 elements are unsupported");
+			return CATTL3_ERR_UNSUPPORTED;
+		}
+		pool_fwd_kernel<S, CATTL3_POOL_MAX><<<grid, 256, 0, ctx->stream>>>(*g, oh, ow, x, y, argmax);
+	} else if (kind == CATTL3_POOL_MEAN) {
+		pool_fwd_kernel<S, CATTL3_POOL_MEAN><<<grid, 256, 0, ctx->stream>>>(*g, oh, ow, x, y, nullptr);
+	} else {
+		set_error("pool_forward: unknown kind %d", kind);
+		return CATTL3_ERR_INVALID;
+	}
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+
+template<typename S>
+int pool_backward(cattl3_ctx* ctx, int kind, const cattl3_pool_geom* g, const S* dy, const uint8_t* argmax, S* dx) {
+	CATTL3_CHECK(check_ctx(ctx));
+	int32_t oh, ow;
+	CATTL3_CHECK(cattl3_pool_output_dims(g, &oh, &ow));
+	CATTL3_REQUIRE(dy && dx, "pool_backward: null tensor");
+	const long long total = (long long) g->n * g->h * g->w * g->c;
+	const int grid = ew_grid(ctx, total, 256);
+	if (kind == CATTL3_POOL_MAX) {
+		CATTL3_REQUIRE(argmax, "pool_backward: max pooling needs the argmax cache");
+		pool_bwd_kernel<S, CATTL3_POOL_MAX><<<grid, 256, 0, ctx->stream>>>(*g, oh, ow, dy, argmax, dx);
+	} else if (kind == CATTL3_POOL_MEAN) {
+		pool_bwd_kernel<S, CATTL3_POOL_MEAN><<<grid, 256, 0, ctx->stream>>>(*g, oh, ow, dy, nullptr, dx);
+	} else {
+		set_error("pool_backward: unknown kind %d", kind);
+		return CATTL3_ERR_INVALID;
+	}
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+
+// ---- batch normalisation -------------------------------------------------------------------------
+// Every group (a channel, or one activation) is L contiguous elements.  Statistics use a two-stage
+// deterministic reduction in double: stage 1 (grid = chunks x groups) produces shifted partial sums
+// sum(x - K), sum((x - K)^2) with K = first element of the group (guards the E[x^2] - mu^2
+// cancellation); stage 2 (one thread per group) combines them in chunk order.
+struct BnPartial { double s1, s2; };
+
+__device__ __forceinline__ void block_reduce2(double& a, double& b) {
+	__shared__ double ra[8], rb[8];
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		a += __shfl_xor_sync(0xffffffffu, a, o);
+		b += __shfl_xor_sync(0xffffffffu, b, o);
+	}
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (lane == 0) { ra[warp] = a; rb[warp] = b; }
+	__syncthreads();
+	if (warp == 0) {
+		a = lane < (int) (blockDim.x >> 5) ? ra[lane] : 0.0;
+		b = lane < (int) (blockDim.x >> 5) ? rb[lane] : 0.0;
+		#pragma unroll
+		for (int o = 4; o > 0; o >>= 1) {
+			a += __shfl_xor_sync(0xffffffffu, a, o);
+			b += __shfl_xor_sync(0xffffffffu, b, o);
+		}
+	}
+}
+
+template<typename S>
+__global__ void __launch_bounds__(256) bn_stats_partial_kernel(long long L, long long chunk,
+		const S* __restrict__ x, BnPartial* __restrict__ part) {
+	const long long g = blockIdx.x;
+	const S* xg = x + g * L;
+	const double K = (double) xg[0];
+	const long long lo = (long long) blockIdx.y * chunk;
+	const long long hi = lo + chunk < L ? lo + chunk : L;
+	double s1 = 0, s2 = 0;
+	for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+		const double d = (double) xg[i] - K;
+		s1 += d;
+		s2 += d * d;
+	}
+	block_reduce2(s1, s2);
+	if (threadIdx.x == 0) part[g * gridDim.y + blockIdx.y] = BnPartial{ s1, s2 };
+}
+
+template<typename S>
+__global__ void __launch_bounds__(128) bn_stats_final_kernel(long long groups, long long L, int chunks,
+		const S* __restrict__ x, const BnPartial* __restrict__ part, S eps, S decay, int running_init,
+		S* __restrict__ running_mean, S* __restrict__ running_inv_sd, S* __restrict__ saved_mean,
+		S* __restrict__ saved_inv_sd) {
+	const long long g = blockIdx.x * 128ll + threadIdx.x;
+	if (g >= groups) return;
+	double s1 = 0, s2 = 0;
+	for (int c = 0; c < chunks; ++c) { s1 += part[g * chunks + c].s1; s2 += part[g * chunks + c].s2; }
+	const double K = (double) x[g * L];
+	const double m1 = s1 / (double) L;
+	double var = s2 / (double) L - m1 * m1;
+	var = var < 0 ? 0 : var;
+	const S mean = (S) (K + m1);
+	const S inv_sd = (S) (1.0 / sqrt(var + (double) eps));
+	saved_mean[g] = mean;
+	saved_inv_sd[g] = inv_sd;
+	if (running_init) {  // BatchNormLayer.hpp:234-238
+		running_mean[g] = ((S) 1 - decay) * running_mean[g] + decay * mean;
+		running_inv_sd[g] = ((S) 1 - decay) * running_inv_sd[g] + decay * inv_sd;
+	} else {             // :239-242
+		running_mean[g] = mean;
+		running_inv_sd[g] = inv_sd;
+	}
+}
+
+template<typename S>
+__global__ void __launch_bounds__(256) bn_apply_kernel(long long L, long long chunk, const S* __restrict__ x,
+		const S* __restrict__ mean, const S* __restrict__ inv_sd, const S* __restrict__ gamma,
+		const S* __restrict__ beta, S* __restrict__ y) {
+	const long long g = blockIdx.x;
+	const S mu = mean[g], sc = inv_sd[g], gm = gamma[g], bt = beta[g];
+	const long long lo = (long long) blockIdx.y * chunk;
+	const long long hi = lo + chunk < L ? lo + chunk : L;
+	for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x)
+		y[g * L + i] = ((x[g * L + i] - mu) * sc) * gm + bt;
+}
+
+template<typename S>
+__global__ void __launch_bounds__(256) bn_bwd_partial_kernel(long long L, long long chunk,
+		const S* __restrict__ x, const S* __restrict__ mean, const S* __restrict__ inv_sd,
+		const S* __restrict__ dy, BnPartial* __restrict__ part) {
+	const long long g = blockIdx.x;
+	const S mu = mean[g], sc = inv_sd[g];
+	const long long lo = (long long) blockIdx.y * chunk;
+	const long long hi = lo + chunk < L ? lo + chunk : L;
+	double s1 = 0, s2 = 0;  // sum dy, sum dy * xhat
+	for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+		const S gy = dy[g * L + i];
+		s1 += (double) gy;
+		s2 += (double) (gy * ((x[g * L + i] - mu) * sc));
+	}
+	block_reduce2(s1, s2);
+	if (threadIdx.x == 0) part[g * gridDim.y + blockIdx.y] = BnPartial{ s1, s2 };
+}
+
+// sums[g] = (sum dy, sum dy*xhat); dgamma/dbeta accumulate (BatchNormLayer.hpp:252-254).
+template<typename S>
+__global__ void __launch_bounds__(128) bn_bwd_final_kernel(long long groups, int chunks,
+		BnPartial* __restrict__ part, S* __restrict__ dgamma, S* __restrict__ dbeta) {
+	const long long g = blockIdx.x * 128ll + threadIdx.x;
+	if (g >= groups) return;
+	double s1 = 0, s2 = 0;
+	for (int c = 0; c < chunks; ++c) { s1 += part[g * chunks + c].s1; s2 += part[g * chunks + c].s2; }
+	part[g * chunks] = BnPartial{ s1, s2 };
+	dbeta[g] += (S) s1;
+	dgamma[g] += (S) s2;
+}
+
+// dx = (L*g - sum g - xhat * sum(xhat g)) * inv_sd / L with g = gamma * dy (BatchNormLayer.hpp:257-261).
+template<typename S>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(long long L, long long chunk, int chunks,
+		const S* __restrict__ x, const S* __restrict__ mean, const S* __restrict__ inv_sd,
+		const S* __restrict__ gamma, const BnPartial* __restrict__ part, const S* __restrict__ dy,
+		S* __restrict__ dx) {
+	const long long g = blockIdx.x;
+	const S mu = mean[g], sc = inv_sd[g], gm = gamma[g];
+	const S sum_g = gm * (S) part[g * chunks].s1, sum_xg = gm * (S) part[g * chunks].s2;
+	const S scale = ((S) 1 / (S) L) * sc;
+	const long long lo = (long long) blockIdx.y * chunk;
+	const long long hi = lo + chunk < L ? lo + chunk : L;
+	for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+		const S xh = (x[g * L + i] - mu) * sc;
+		dx[g * L + i] = (((S) L * (gm * dy[g * L + i]) - sum_g) - xh * sum_xg) * scale;
+	}
+}
+
+static void bn_partition(const cattl3_ctx* ctx, long long groups, long long L, int* chunks, long long* chunk,
+		int* threads) {
+	// aim for ~8 CTAs per SM in total; chunks of at least 2048 elements
+	long long want = ceil_div(8ll * ctx->sm_count, groups);
+	long long maxc = ceil_div(L, 2048);
+	long long c = want < maxc ? want : maxc;
+	if (c < 1) c = 1;
+	*chunk = ceil_div(L, c);
+	*chunks = (int) ceil_div(L, *chunk);
+	*threads = L >= 1024 ? 256 : (L >= 128 ? 128 : 32);
+}
+
+template<typename S>
+int batchnorm_forward(cattl3_ctx* ctx, int per_channel, int n, int h, int w, int c, int training,
+		int running_init, S decay, S eps, const S* x, const S* gamma, const S* beta, S* running_mean,
+		S* running_inv_sd, S* saved_mean, S* saved_inv_sd, S* y) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && x && y && gamma && beta && running_mean &&
+			running_inv_sd, "batchnorm_forward: bad arguments");
+	const long long groups = per_channel ? c : (long long) h * w * c;
+	const long long L = per_channel ? (long long) n * h * w : n;
+	int chunks, threads;
+	long long chunk;
+	bn_partition(ctx, groups, L, &chunks, &chunk, &threads);
+	CATTL3_REQUIRE(groups <= 2147483647ll, "batchnorm: too many groups");
+	dim3 grid((unsigned) groups, (unsigned) chunks);
+	if (training) {
+		CATTL3_REQUIRE(saved_mean && saved_inv_sd, "batchnorm_forward: training needs saved statistics");
+		CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, sizeof(BnPartial) * groups * chunks));
+		bn_stats_partial_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, x, (BnPartial*) ctx->ws);
+		CATTL3_LAUNCHED(ctx);
+		bn_stats_final_kernel<S><<<(unsigned) ceil_div(groups, 128), 128, 0, ctx->stream>>>(groups, L, chunks, x,
+				(const BnPartial*) ctx->ws, eps, decay, running_init, running_mean, running_inv_sd, saved_mean,
+				saved_inv_sd);
+		CATTL3_LAUNCHED(ctx);
+		bn_apply_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, x, saved_mean, saved_inv_sd, gamma, beta, y);
+	} else {
+		bn_apply_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, x, running_mean, running_inv_sd, gamma, beta, y);
+	}
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+
+template<typename S>
+int batchnorm_backward(cattl3_ctx* ctx, int per_channel, int n, int h, int w, int c, const S* x,
+		const S* gamma, const S* saved_mean, const S* saved_inv_sd, const S* dy, S* dgamma, S* dbeta, S* dx) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && x && gamma && saved_mean && saved_inv_sd && dy &&
+			dgamma && dbeta, "batchnorm_backward: bad arguments");
+	const long long groups = per_channel ? c : (long long) h * w * c;
+	const long long L = per_channel ? (long long) n * h * w : n;
+	CATTL3_REQUIRE(groups <= 2147483647ll, "batchnorm: too many groups");
+	int chunks, threads;
+	long long chunk;
+	bn_partition(ctx, groups, L, &chunks, &chunk, &threads);
+	dim3 grid((unsigned) groups, (unsigned) chunks);
+	CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, sizeof(BnPartial) * groups * chunks));
+	bn_bwd_partial_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, x, saved_mean, saved_inv_sd, dy,
+			(BnPartial*) ctx->ws);
+	CATTL3_LAUNCHED(ctx);
+	bn_bwd_final_kernel<S><<<(unsigned) ceil_div(groups, 128), 128, 0, ctx->stream>>>(groups, chunks,
+			(BnPartial*) ctx->ws, dgamma, dbeta);
+	CATTL3_LAUNCHED(ctx);
+	if (dx) {
+		bn_bwd_apply_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, chunks, x, saved_mean, saved_inv_sd,
+				gamma, (const BnPartial*) ctx->ws, dy, dx);
+		CATTL3_LAUNCHED(ctx);
+	}
+	return CATTL3_OK;
+}
+
+// ---- fused optimizer step ------------------------------------------------------------------------
+// One launch over the whole parameter arena: L2 regularisation (g += lambda p), the update rule and
+// the gradient reset, i.e. SGDOptimizer::_train lines 57-70 collapsed.  Expression order follows the
+// reference's Eigen expressions so that float results agree to rounding.
+template<typename S>
+struct OptScalars { S lr, a, b, eps, lr_epoch, c1, c1n, c2, l2; int reset; };
+
+template<typename S, int KIND>
+__global__ void __launch_bounds__(256) opt_step_kernel(long long count, OptScalars<S> h, S* __restrict__ p,
+		S* __restrict__ g, S* __restrict__ s1, S* __restrict__ s2, S* __restrict__ s3) {
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < count; i += (long long) gridDim.x * 256) {
+		S pv = p[i];
+		S gv = g[i];
+		if (h.l2 > (S) 0) gv += pv * h.l2;
+		if (KIND == CATTL3_OPT_VANILLA_SGD) {
+			pv = pv - gv * h.lr;
+		} else if (KIND == CATTL3_OPT_MOMENTUM) {
+			const S v = s1[i] * h.b + gv * h.lr_epoch;
+			s1[i] = v;
+			pv = pv - v;
+		} else if (KIND == CATTL3_OPT_NESTEROV) {
+			const S old = s1[i];
+			const S v = old * h.b - gv * h.lr_epoch;
+			s1[i] = v;
+			pv = pv + old * -h.b + v * ((S) 1 + h.b);
+		} else if (KIND == CATTL3_OPT_ADAGRAD) {
+			const S s = s1[i] + gv * gv;
+			s1[i] = s;
+			pv = pv - gv * h.lr / (dev_sqrt<S>(s) + h.eps);
+		} else if (KIND == CATTL3_OPT_RMSPROP) {
+			const S s = s1[i] * ((S) 1 - h.b) + gv * gv * h.b;
+			s1[i] = s;
+			pv = pv - gv * h.lr / (dev_sqrt<S>(s) + h.eps);
+		} else if (KIND == CATTL3_OPT_ADADELTA) {
+			const S s = s1[i] * ((S) 1 - h.a) + gv * gv * h.a;
+			s1[i] = s;
+			const S u = -gv * dev_sqrt<S>(s2[i] + h.eps) / dev_sqrt<S>(s + h.eps);
+			pv = pv + u;
+			s2[i] = s2[i] * ((S) 1 - h.a) + u * u * h.a;
+		} else if (KIND == CATTL3_OPT_ADAM) {
+			const S m = s1[i] * ((S) 1 - h.a) + gv * h.a;
+			const S v = s2[i] * ((S) 1 - h.b) + gv * gv * h.b;
+			s1[i] = m; s2[i] = v;
+			pv = pv - (m * (h.lr * h.c1)) / dev_sqrt<S>(v * h.c2 + h.eps);
+		} else if (KIND == CATTL3_OPT_ADAMAX) {
+			const S m = s1[i] * ((S) 1 - h.a) + gv * h.a;
+			const S d = s2[i] * ((S) 1 - h.b);
+			const S ag = gv < (S) 0 ? -gv : gv;
+			const S v = d > ag ? d : ag;
+			s1[i] = m; s2[i] = v;
+			pv = pv - (m * (h.lr * h.c1)) / (v + h.eps);
+		} else if (KIND == CATTL3_OPT_NADAM) {
+			const S m = s1[i] * ((S) 1 - h.a) + gv * h.a;
+			const S v = s2[i] * ((S) 1 - h.b) + gv * gv * h.b;
+			s1[i] = m; s2[i] = v;
+			pv = pv - (gv * (h.a * h.c1) + m * (((S) 1 - h.a) * h.c1n)) * h.lr / dev_sqrt<S>(v * h.c2 + h.eps);
+		} else if (KIND == CATTL3_OPT_AMSGRAD) {
+			const S m = s1[i] * ((S) 1 - h.a) + gv * h.a;
+			const S v = s2[i] * ((S) 1 - h.b) + gv * gv * h.b;
+			const S mx = v > s3[i] ? v : s3[i];
+			s1[i] = m; s2[i] = v; s3[i] = mx;
+			pv = pv - m * h.lr / dev_sqrt<S>(mx + h.eps);
+		}
+		p[i] = pv;
+		if (h.reset) g[i] = (S) 0;
+	}
+}
+
+template<typename S>
+int optimizer_step(cattl3_ctx* ctx, const cattl3_opt_step* st, int64_t count, S* p, S* g, S* s1, S* s2, S* s3) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(st && count > 0 && p && g, "optimizer_step: bad arguments");
+	OptScalars<S> h{ (S) st->lr, (S) st->a, (S) st->b, (S) st->eps, (S) st->lr_epoch, (S) st->c1, (S) st->c1n,
+			(S) st->c2, (S) st->l2_lambda, st->reset_grad };
+	const int grid = ew_grid(ctx, count, 256);
+	const int k = st->kind;
+	const int need = (k == 0) ? 0 : (k <= 4 ? 1 : (k == 9 ? 3 : 2));
+	CATTL3_REQUIRE((need < 1 || s1) && (need < 2 || s2) && (need < 3 || s3), "optimizer_step: missing state vector");
+	switch (k) {
+#define CASE(K) case K: opt_step_kernel<S, K><<<grid, 256, 0, ctx->stream>>>(count, h, p, g, s1, s2, s3); break;
+		CASE(CATTL3_OPT_VANILLA_SGD) CASE(CATTL3_OPT_MOMENTUM) CASE(CATTL3_OPT_NESTEROV) CASE(CATTL3_OPT_ADAGRAD)
+		CASE(CATTL3_OPT_RMSPROP) CASE(CATTL3_OPT_ADADELTA) CASE(CATTL3_OPT_ADAM) CASE(CATTL3_OPT_ADAMAX)
+		CASE(CATTL3_OPT_NADAM) CASE(CATTL3_OPT_AMSGRAD)
+#undef CASE
+		default:
+			set_error("optimizer_step: unknown kind %d", k);
+			return CATTL3_ERR_INVALID;
+	}
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+
+// ---- glue ----------------------------------------------------------------------------------------
+template<typename S>
+__global__ void __launch_bounds__(256) add_inplace_kernel(long long count, S* __restrict__ y, const S* __restrict__ x) {
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < count; i += (long long) gridDim.x * 256) y[i] += x[i];
+}
+template<typename S>
+__global__ void __launch_bounds__(256) scale_kernel(long long count, S alpha, const S* __restrict__ x, S* __restrict__ y) {
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < count; i += (long long) gridDim.x * 256) y[i] = x[i] * alpha;
+}
+
+template<typename S>
+int add_inplace(cattl3_ctx* ctx, int64_t count, S* y, const S* x) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(count > 0 && y && x, "add_inplace: bad arguments");
+	add_inplace_kernel<S><<<ew_grid(ctx, count, 256), 256, 0, ctx->stream>>>(count, y, x);
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+template<typename S>
+int scale(cattl3_ctx* ctx, int64_t count, S alpha, const S* x, S* y) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(count > 0 && y && x, "scale: bad arguments");
+	scale_kernel<S><<<ew_grid(ctx, count, 256), 256, 0, ctx->stream>>>(count, alpha, x, y);
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+
+} // namespace cattl3
+
+using namespace cattl3;
+
+extern "C" {
+
+int cattl3_activation_forward_f32(cattl3_ctx* c, int kind, float alpha, int64_t rows, int64_t vol, const float* x, float* y) {
+	return activation_forward<float>(c, kind, alpha, rows, vol, x, y); }
+int cattl3_activation_forward_f64(cattl3_ctx* c, int kind, double alpha, int64_t rows, int64_t vol, const double* x, double* y) {
+	return activation_forward<double>(c, kind, alpha, rows, vol, x, y); }
+int cattl3_activation_backward_f32(cattl3_ctx* c, int kind, float alpha, int64_t rows, int64_t vol, const float* x, const float* y, const float* dy, float* dx) {
+	return activation_backward<float>(c, kind, alpha, rows, vol, x, y, dy, dx); }
+int cattl3_activation_backward_f64(cattl3_ctx* c, int kind, double alpha, int64_t rows, int64_t vol, const double* x, const double* y, const double* dy, double* dx) {
+	return activation_backward<double>(c, kind, alpha, rows, vol, x, y, dy, dx); }
+
+int cattl3_pool_forward_f32(cattl3_ctx* c, int kind, const cattl3_pool_geom* g, const float* x, float* y, uint8_t* am) {
+	return pool_forward<float>(c, kind, g, x, y, am); }
+int cattl3_pool_forward_f64(cattl3_ctx* c, int kind, const cattl3_pool_geom* g, const double* x, double* y, uint8_t* am) {
+	return pool_forward<double>(c, kind, g, x, y, am); }
+int cattl3_pool_backward_f32(cattl3_ctx* c, int kind, const cattl3_pool_geom* g, const float* dy, const uint8_t* am, float* dx) {
+	return pool_backward<float>(c, kind, g, dy, am, dx); }
+int cattl3_pool_backward_f64(cattl3_ctx* c, int kind, const cattl3_pool_geom* g, const double* dy, const uint8_t* am, double* dx) {
+	return pool_backward<double>(c, kind, g, dy, am, dx); }
+
+int cattl3_batchnorm_forward_f32(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, int training, int rinit, float decay, float eps, const float* x, const float* gamma, const float* beta, float* rm, float* rs, float* sm, float* ss, float* y) {
+	return batchnorm_forward<float>(c, pc, n, h, w, ch, training, rinit, decay, eps, x, gamma, beta, rm, rs, sm, ss, y); }
+int cattl3_batchnorm_forward_f64(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, int training, int rinit, double decay, double eps, const double* x, const double* gamma, const double* beta, double* rm, double* rs, double* sm, double* ss, double* y) {
+	return batchnorm_forward<double>(c, pc, n, h, w, ch, training, rinit, decay, eps, x, gamma, beta, rm, rs, sm, ss, y); }
+int cattl3_batchnorm_backward_f32(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, const float* x, const float* gamma, const float* sm, const float* ss, const float* dy, float* dgamma, float* dbeta, float* dx) {
+	return batchnorm_backward<float>(c, pc, n, h, w, ch, x, gamma, sm, ss, dy, dgamma, dbeta, dx); }
+int cattl3_batchnorm_backward_f64(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, const double* x, const double* gamma, const double* sm, const double* ss, const double* dy, double* dgamma, double* dbeta, double* dx) {
+	return batchnorm_backward<double>(c, pc, n, h, w, ch, x, gamma, sm, ss, dy, dgamma, dbeta, dx); }
+
+int cattl3_optimizer_step_f32(cattl3_ctx* c, const cattl3_opt_step* st, int64_t count, float* p, float* g, float* s1, float* s2, float* s3) {
+	return optimizer_step<float>(c, st, count, p, g, s1, s2, s3); }
+int cattl3_optimizer_step_f64(cattl3_ctx* c, const cattl3_opt_step* st, int64_t count, double* p, double* g, double* s1, double* s2, double* s3) {
+	return optimizer_step<double>(c, st, count, p, g, s1, s2, s3); }
+
+int cattl3_add_inplace_f32(cattl3_ctx* c, int64_t count, float* y, const float* x) { return add_inplace<float>(c, count, y, x); }
+int cattl3_add_inplace_f64(cattl3_ctx* c, int64_t count, double* y, const double* x) { return add_inplace<double>(c, count, y, x); }
+int cattl3_scale_f32(cattl3_ctx* c, int64_t count, float alpha, const float* x, float* y) { return scale<float>(c, count, alpha, x, y); }
+int cattl3_scale_f64(cattl3_ctx* c, int64_t count, double alpha, const double* x, double* y) { return scale<double>(c, count, alpha, x, y); }
+
+}

@@ -1,0 +1,249 @@
+/*
+ * cattl3_b200.h -- C ABI of the B200-native C-ATTL3 hot path (libcattl3_b200.so).
+ *
+ * The reference (ViktorC/C-ATTL3) is a header-only C++ template library whose plug-in boundary
+ * is the virtual cattle::Layer / cattle::Parameters / cattle::SGDOptimizer API; it has no FFI.
+ * This header is the thin extern "C" layer underneath the header-only replacement classes in
+ * c-attl3_b200/cattle/ (namespace cattle, same class names and constructor signatures as the
+ * reference).  Each entry point names the reference function it replaces (paths relative to the
+ * reference checkout, C-ATTL3/...).
+ *
+ * Conventions
+ *  - All tensors use the reference's memory layout: Eigen column-major rank-4 tensors
+ *    (N, H, W, C) with N FASTEST: offset(n,h,w,c) = n + N*(h + H*(w + W*c))
+ *    (C-ATTL3/core/EigenProxy.hpp:56-57).  Parameter matrices are column-major.
+ *  - Plain pointers and sizes only.  Unless a function name ends in `_host`, data pointers are
+ *    DEVICE pointers valid on the context's device; work is enqueued on the context's stream and
+ *    the call returns without synchronising.
+ *  - `_f32` / `_f64` mirror the reference's float / double Scalar template instantiations.
+ *  - Every function returns CATTL3_OK (0) or an error code; cattl3_last_error() gives the message
+ *    of the calling thread's last failure.  Nothing throws across this boundary; the C++ headers
+ *    turn non-zero codes into std::runtime_error (the convention of the reference's own
+ *    C-ATTL3/core/gpu/cuda/CUDAError.hpp:17-52).
+ *  - There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *    CATTL3_ERR_NO_DEVICE.
+ *  - Entry points are re-entrant across distinct contexts (one context per host thread / stream;
+ *    the reference runs network lanes on pthreads, C-ATTL3/neural_network/ParallelNeuralNetwork.hpp:142-197).
+ */
+#ifndef CATTL3_B200_H_
+#define CATTL3_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CATTL3_ABI_VERSION 1
+
+enum {
+	CATTL3_OK = 0,
+	CATTL3_ERR_INVALID = 1,      /* bad argument / inconsistent geometry */
+	CATTL3_ERR_CUDA = 2,         /* a CUDA runtime / driver call failed */
+	CATTL3_ERR_UNSUPPORTED = 3,  /* valid request outside what the kernels cover */
+	CATTL3_ERR_NO_DEVICE = 4     /* no usable CUDA device (there is no CPU fallback) */
+};
+
+/* Activation kinds: ReLU / LeakyReLU / ELU / Swish are the hot-path set;
+ * Sigmoid / Tanh / Softplus / Softmax are the "next" set (section 8f rank 1). */
+enum {
+	CATTL3_ACT_RELU = 0,      /* C-ATTL3/layer/activation/ReLUActivationLayer.hpp:45-57 */
+	CATTL3_ACT_LEAKY_RELU = 1,/* C-ATTL3/layer/activation/LeakyReLUActivationLayer.hpp:50-62 (alpha) */
+	CATTL3_ACT_ELU = 2,       /* C-ATTL3/layer/activation/ELUActivationLayer.hpp:55-78 (alpha) */
+	CATTL3_ACT_SWISH = 3,     /* C-ATTL3/layer/activation/SwishActivationLayer.hpp:45-61 (alpha = beta) */
+	CATTL3_ACT_SIGMOID = 4,   /* C-ATTL3/layer/activation/SigmoidActivationLayer.hpp */
+	CATTL3_ACT_TANH = 5,      /* C-ATTL3/layer/activation/TanhActivationLayer.hpp */
+	CATTL3_ACT_SOFTPLUS = 6,  /* C-ATTL3/layer/activation/SoftplusActivationLayer.hpp:40-52 */
+	CATTL3_ACT_SOFTMAX = 7    /* C-ATTL3/layer/activation/SoftmaxActivationLayer.hpp:49-78 (alpha = epsilon) */
+};
+
+enum {
+	CATTL3_POOL_MAX = 0,      /* C-ATTL3/layer/pool/MaxPoolLayer.hpp:38-80 */
+	CATTL3_POOL_MEAN = 1      /* C-ATTL3/layer/pool/MeanPoolLayer.hpp:35-41 */
+};
+
+enum {
+	CATTL3_OPT_VANILLA_SGD = 0, /* C-ATTL3/optimizer/VanillaSGDOptimizer.hpp:38-43 */
+	CATTL3_OPT_MOMENTUM = 1,    /* C-ATTL3/optimizer/MomentumSGDOptimizer.hpp:54-63 */
+	CATTL3_OPT_NESTEROV = 2,    /* C-ATTL3/optimizer/NesterovMomentumSGDOptimizer.hpp:43-55 */
+	CATTL3_OPT_ADAGRAD = 3,     /* C-ATTL3/optimizer/AdaGradOptimizer.hpp:49-71 */
+	CATTL3_OPT_RMSPROP = 4,     /* C-ATTL3/optimizer/RMSPropOptimizer.hpp:42-46 */
+	CATTL3_OPT_ADADELTA = 5,    /* C-ATTL3/optimizer/AdaDeltaOptimizer.hpp:53-67 */
+	CATTL3_OPT_ADAM = 6,        /* C-ATTL3/optimizer/AdamOptimizer.hpp:66-82 */
+	CATTL3_OPT_ADAMAX = 7,      /* C-ATTL3/optimizer/AdaMaxOptimizer.hpp:44-60 */
+	CATTL3_OPT_NADAM = 8,       /* C-ATTL3/optimizer/NadamOptimizer.hpp:44-63 */
+	CATTL3_OPT_AMSGRAD = 9      /* C-ATTL3/optimizer/AMSGradOptimizer.hpp:50-67 */
+};
+
+/* Which kernel family a kernel-layer call may use (cattl3_ctx_set_conv_path). */
+enum {
+	CATTL3_PATH_AUTO = 0,       /* tcgen05 where the shape allows it (float only), else SIMT */
+	CATTL3_PATH_SIMT = 1,       /* FFMA / DFMA implicit GEMM (any shape, float and double) */
+	CATTL3_PATH_TCGEN05 = 2     /* TMA + tcgen05 3xTF32 implicit GEMM; CATTL3_ERR_UNSUPPORTED if not applicable */
+};
+
+/*
+ * Convolution geometry, in the reference's own terms (constructor arguments of
+ * ConvKernelLayer / TransConvKernelLayer, C-ATTL3/layer/kernel/ConvKernelLayer.hpp:282-296):
+ * input n x h x w x c, f filters, receptor rh x rw, padding (ph, pw) on both sides, stride
+ * (sh, sw), dilation (dh, dw) where 0 means dense (effective tap step = d + 1).
+ */
+typedef struct cattl3_conv_geom {
+	int32_t n, h, w, c;
+	int32_t f;
+	int32_t rh, rw;
+	int32_t ph, pw;
+	int32_t sh, sw;
+	int32_t dh, dw;
+} cattl3_conv_geom;
+
+/* Pooling geometry (PoolLayer constructor, C-ATTL3/layer/PoolLayer.hpp:47-70): no padding. */
+typedef struct cattl3_pool_geom {
+	int32_t n, h, w, c;
+	int32_t rh, rw;
+	int32_t sh, sw;
+} cattl3_pool_geom;
+
+/*
+ * One optimizer update.  lr/a/b/eps are the constructor hyper-parameters in the order the
+ * reference declares them (kind 1,2: a = annealing_rate, b = momentum; 4: b = l2_decay;
+ * 5: a = decay; 6-9: a = l1_decay, b = l2_decay).  The host evaluates the step-dependent scalars
+ * exactly as the reference does and passes them in:
+ *   lr_epoch = init_learning_rate / (1 + annealing_rate * epoch)      (MomentumSGDOptimizer.hpp:70-72)
+ *   c1  = 1 / (1 - (1-a)^(t+1) + eps), c1n = 1 / (1 - (1-a)^(t+2) + eps),
+ *   c2  = 1 / (1 - (1-b)^(t+1) + eps)                                 (AdamOptimizer.hpp:67-68, NadamOptimizer.hpp:45-47)
+ * l2_lambda > 0 folds Parameters::regularize() of an L2ParameterRegularization into the step
+ * (g += lambda * p, C-ATTL3/parameter_regularization/L2ParameterRegularization.hpp:31-33);
+ * reset_grad != 0 zeroes the gradient afterwards (SGDOptimizer.hpp:69-70).
+ */
+typedef struct cattl3_opt_step {
+	int32_t kind;
+	int32_t reset_grad;
+	double lr, a, b, eps;
+	double lr_epoch, c1, c1n, c2;
+	double l2_lambda;
+} cattl3_opt_step;
+
+typedef struct cattl3_ctx cattl3_ctx; /* opaque: device, stream, workspaces, cached TMA descriptors */
+
+/* ---- library / context ------------------------------------------------------------------- */
+int cattl3_abi_version(void);
+const char* cattl3_last_error(void);
+/* Number of visible CUDA devices (0 when there is none; never fails). */
+int cattl3_device_count(void);
+/* cuda_stream: a cudaStream_t to enqueue on (e.g. the caller's framework stream) or NULL to let
+ * the context create its own non-blocking stream. */
+int cattl3_ctx_create(cattl3_ctx** out, int device, void* cuda_stream);
+int cattl3_ctx_destroy(cattl3_ctx* ctx);
+int cattl3_ctx_synchronize(cattl3_ctx* ctx);
+int cattl3_ctx_set_conv_path(cattl3_ctx* ctx, int path);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+int64_t cattl3_ctx_launch_count(const cattl3_ctx* ctx);
+/* Name of the kernel family the last kernel-layer call on this context used ("tcgen05"/"simt"). */
+const char* cattl3_ctx_last_path(const cattl3_ctx* ctx);
+void* cattl3_ctx_stream(const cattl3_ctx* ctx);
+
+/* ---- memory helpers (so g++-only hosts need no CUDA headers) ------------------------------ */
+int cattl3_malloc(cattl3_ctx* ctx, void** dev_ptr, size_t bytes);
+int cattl3_free(cattl3_ctx* ctx, void* dev_ptr);
+int cattl3_memset(cattl3_ctx* ctx, void* dev_ptr, int value, size_t bytes);
+int cattl3_memcpy_h2d(cattl3_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes);
+int cattl3_memcpy_d2h(cattl3_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes); /* synchronises */
+int cattl3_memcpy_d2d(cattl3_ctx* ctx, void* dev_dst, const void* dev_src, size_t bytes);
+int cattl3_host_alloc(void** host_ptr, size_t bytes); /* pinned */
+int cattl3_host_free(void* host_ptr);
+
+/* ---- shape helpers ------------------------------------------------------------------------ */
+/* ConvKernelLayer.hpp:194-197 (transposed = 0) / TransConvKernelLayer.hpp:200-203 (transposed = 1). */
+int cattl3_conv_output_dims(const cattl3_conv_geom* g, int transposed, int32_t* oh, int32_t* ow);
+/* PoolLayer.hpp:145-148. */
+int cattl3_pool_output_dims(const cattl3_pool_geom* g, int32_t* oh, int32_t* ow);
+
+/* ---- kernel layers ------------------------------------------------------------------------ */
+/*
+ * ConvKernelLayerBase::_pass_forward (ConvKernelLayer.hpp:115-148) without the im2col buffer:
+ *   y(n,oh,ow,f) = b(f) + sum_{c,rw,rh} x(n, oh*sh + rh*(dh+1) - ph, ow*sw + rw*(dw+1) - pw, c) * W(rh + RH*(rw + RW*c), f)
+ * x: n*h*w*c, w: (rh*rw*c) x f col-major, b: f, y: n*oh*ow*f.
+ */
+int cattl3_conv_forward_f32(cattl3_ctx*, const cattl3_conv_geom*, const float* x, const float* w, const float* b, float* y);
+int cattl3_conv_forward_f64(cattl3_ctx*, const cattl3_conv_geom*, const double* x, const double* w, const double* b, double* y);
+/*
+ * ConvKernelLayerBase::_pass_back (ConvKernelLayer.hpp:149-189).  dw and db ACCUMULATE (beta = 1,
+ * Parameters::accumulate_grad, StandardParameters.hpp:115-123); dx is overwritten and may be NULL
+ * for an input layer (Layer.hpp:82-90).  The weight gradient is a deterministic split-K reduction.
+ */
+int cattl3_conv_backward_f32(cattl3_ctx*, const cattl3_conv_geom*, const float* x, const float* w, const float* dy, float* dw, float* db, float* dx);
+int cattl3_conv_backward_f64(cattl3_ctx*, const cattl3_conv_geom*, const double* x, const double* w, const double* dy, double* dw, double* db, double* dx);
+/*
+ * TransConvKernelLayerBase::_pass_forward / _pass_back (TransConvKernelLayer.hpp:115-151, 152-187).
+ * geom.h/w/c describe the INPUT (ih x iw x c); w: c x (rh*rw*f) col-major with column
+ * rh + RH*(rw + RW*f); b: one bias PER OUTPUT ELEMENT, oh*ow*f; y: n*oh*ow*f.
+ */
+int cattl3_transconv_forward_f32(cattl3_ctx*, const cattl3_conv_geom*, const float* x, const float* w, const float* b, float* y);
+int cattl3_transconv_forward_f64(cattl3_ctx*, const cattl3_conv_geom*, const double* x, const double* w, const double* b, double* y);
+int cattl3_transconv_backward_f32(cattl3_ctx*, const cattl3_conv_geom*, const float* x, const float* w, const float* dy, float* dw, float* db, float* dx);
+int cattl3_transconv_backward_f64(cattl3_ctx*, const cattl3_conv_geom*, const double* x, const double* w, const double* dy, double* dw, double* db, double* dx);
+/*
+ * DenseKernelLayer::pass_forward / pass_back (DenseKernelLayer.hpp:92-102, 103-115):
+ * x: n x in col-major (the free view of an (N,H,W,C) tensor), w: in x out, b: out, y: n x out.
+ */
+int cattl3_dense_forward_f32(cattl3_ctx*, int32_t n, int32_t in, int32_t out, const float* x, const float* w, const float* b, float* y);
+int cattl3_dense_forward_f64(cattl3_ctx*, int32_t n, int32_t in, int32_t out, const double* x, const double* w, const double* b, double* y);
+int cattl3_dense_backward_f32(cattl3_ctx*, int32_t n, int32_t in, int32_t out, const float* x, const float* w, const float* dy, float* dw, float* db, float* dx);
+int cattl3_dense_backward_f64(cattl3_ctx*, int32_t n, int32_t in, int32_t out, const double* x, const double* w, const double* dy, double* dw, double* db, double* dx);
+
+/* Host-buffer forms of the convolution layer: what the reference's Layer API hands over
+ * (pass_forward(Data in, bool) / pass_back(Data out_grad), Layer.hpp:126,137) -- host tensors in,
+ * host tensors out, host<->device copies inside the call.  Parameters stay device resident. */
+int cattl3_conv_forward_host_f32(cattl3_ctx*, const cattl3_conv_geom*, const float* x_host, const float* w_dev, const float* b_dev, float* y_host, float* x_dev_keep);
+int cattl3_conv_backward_host_f32(cattl3_ctx*, const cattl3_conv_geom*, const float* x_dev, const float* w_dev, const float* dy_host, float* dw_dev, float* db_dev, float* dx_host);
+
+/* ---- activation layers -------------------------------------------------------------------- */
+/* x, y: rows x vol elements, rows (= batch) fastest.  Softmax normalises each row over `vol`. */
+int cattl3_activation_forward_f32(cattl3_ctx*, int kind, float alpha, int64_t rows, int64_t vol, const float* x, float* y);
+int cattl3_activation_forward_f64(cattl3_ctx*, int kind, double alpha, int64_t rows, int64_t vol, const double* x, double* y);
+/* dx = f'(x) * dy, using the cached input x and output y exactly where the reference does. */
+int cattl3_activation_backward_f32(cattl3_ctx*, int kind, float alpha, int64_t rows, int64_t vol, const float* x, const float* y, const float* dy, float* dx);
+int cattl3_activation_backward_f64(cattl3_ctx*, int kind, double alpha, int64_t rows, int64_t vol, const double* x, const double* y, const double* dy, double* dx);
+
+/* ---- pooling layers (PoolLayer.hpp:77-116) -------------------------------------------------- */
+/* argmax: one byte per output element, index rw*RH + rh of the first maximum in the reference's
+ * scan order (MaxPoolLayer.hpp:45-58); required for CATTL3_POOL_MAX, ignored for MEAN. */
+int cattl3_pool_forward_f32(cattl3_ctx*, int kind, const cattl3_pool_geom*, const float* x, float* y, uint8_t* argmax);
+int cattl3_pool_forward_f64(cattl3_ctx*, int kind, const cattl3_pool_geom*, const double* x, double* y, uint8_t* argmax);
+int cattl3_pool_backward_f32(cattl3_ctx*, int kind, const cattl3_pool_geom*, const float* dy, const uint8_t* argmax, float* dx);
+int cattl3_pool_backward_f64(cattl3_ctx*, int kind, const cattl3_pool_geom*, const double* dy, const uint8_t* argmax, double* dx);
+
+/* ---- batch normalisation (BatchNormLayer.hpp:170-262 per channel, 337-391 per activation) ---- */
+/*
+ * groups = c (per_channel) or h*w*c; every group is L = n*h*w (or n) contiguous elements.
+ * training != 0: batch statistics; saved_mean / saved_inv_sd (groups) are written for backward and
+ * the running averages are updated (assigned when *first* batch, i.e. running_initialised == 0,
+ * else (1-decay)*avg + decay*new).  training == 0: running averages are used.
+ */
+int cattl3_batchnorm_forward_f32(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, int training, int running_initialised, float decay, float eps, const float* x, const float* gamma, const float* beta, float* running_mean, float* running_inv_sd, float* saved_mean, float* saved_inv_sd, float* y);
+int cattl3_batchnorm_forward_f64(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, int training, int running_initialised, double decay, double eps, const double* x, const double* gamma, const double* beta, double* running_mean, double* running_inv_sd, double* saved_mean, double* saved_inv_sd, double* y);
+/* dgamma / dbeta ACCUMULATE; dx may be NULL (input layer). */
+int cattl3_batchnorm_backward_f32(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, const float* x, const float* gamma, const float* saved_mean, const float* saved_inv_sd, const float* dy, float* dgamma, float* dbeta, float* dx);
+int cattl3_batchnorm_backward_f64(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, const double* x, const double* gamma, const double* saved_mean, const double* saved_inv_sd, const double* dy, double* dgamma, double* dbeta, double* dx);
+
+/* ---- optimizer step (SGDOptimizer::_train's regularize -> _update_params -> reset_grad) ----- */
+/* One fused launch over `count` contiguous parameters (a whole network's parameter arena).
+ * s1/s2/s3: optimizer state vectors (unused ones may be NULL). */
+int cattl3_optimizer_step_f32(cattl3_ctx*, const cattl3_opt_step*, int64_t count, float* p, float* g, float* s1, float* s2, float* s3);
+int cattl3_optimizer_step_f64(cattl3_ctx*, const cattl3_opt_step*, int64_t count, double* p, double* g, double* s1, double* s2, double* s3);
+
+/* ---- small element-wise helpers for the network glue ---------------------------------------- */
+/* y += x (ResidualNeuralNetwork::propagate, C-ATTL3/neural_network/ResidualNeuralNetwork.hpp:112-117). */
+int cattl3_add_inplace_f32(cattl3_ctx*, int64_t count, float* y, const float* x);
+int cattl3_add_inplace_f64(cattl3_ctx*, int64_t count, double* y, const double* x);
+/* y = alpha * x (the 1/batch_size scaling of the loss gradient, SGDOptimizer.hpp:55-56). */
+int cattl3_scale_f32(cattl3_ctx*, int64_t count, float alpha, const float* x, float* y);
+int cattl3_scale_f64(cattl3_ctx*, int64_t count, double alpha, const double* x, double* y);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* CATTL3_B200_H_ */

@@ -1,0 +1,188 @@
+"""-m gpu: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs, and
+against the committed golden vectors of the unmodified reference.  Tolerances are the north star's:
+1e-4 relative (float), 1e-10 (double), measured norm-relative (cases.relerr)."""
+import numpy as np
+import pytest
+
+import cases as C
+from oracle.binding import Geom, conv_out_dims
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [np.float32, np.float64]
+
+
+def _conv_gpu(U, case, x, w, b, dy, transposed, want_dx=True, reps=1, path=None):
+    c = U.ctx(path)
+    g = U.pkg.ConvGeom(*case)
+    og = Geom(*case)
+    oh, ow = conv_out_dims(og, transposed)
+    dt = x.dtype
+    xd, wd, bd, dyd = U.dev(x), U.dev(w), U.dev(b), U.dev(dy)
+    yd = U.zeros((og.n, oh, ow, og.f), dt)
+    dxd = U.zeros(x.shape, dt) if want_dx else None
+    dwd, dbd = U.zeros(w.shape, dt), U.zeros(b.shape, dt)
+    c.conv_forward(g, xd, wd, bd, yd, transposed)
+    fpath = c.last_path
+    for _ in range(reps):
+        c.conv_backward(g, xd, wd, dyd, dwd, dbd, dxd, transposed)
+    c.synchronize()
+    return dict(y=U.host(yd, (og.n, oh, ow, og.f)), dx=U.host(dxd, x.shape) if want_dx else None,
+                dw=U.host(dwd, w.shape), db=U.host(dbd, b.shape), path=fpath)
+
+
+@pytest.fixture(scope="module")
+def U():
+    import gpu_util
+    return gpu_util
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("tr", [False, True])
+def test_conv_simt_vs_oracle(U, orc, dt, tr):
+    table = C.TCONV_CASES if tr else C.CONV_CASES
+    for name, case in table.items():
+        g, x, w, b, dy = C.conv_inputs(case, dt, 21, tr)
+        r = orc.conv(g, x, w, b, dy, transposed=tr, back_reps=2)
+        a = _conv_gpu(U, case, x, w, b, dy, tr, reps=2, path=U.pkg.PATH_SIMT)
+        assert a["path"] == "simt"
+        for k in ("y", "dx", "dw", "db"):
+            assert C.relerr(a[k], r[k]) < C.TOL[np.dtype(dt)], (name, k, C.relerr(a[k], r[k]))
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_conv_golden(U, golden, dt):
+    suf = "f32" if dt == np.float32 else "f64"
+    for tr, fam, table in ((False, "conv", C.CONV_CASES), (True, "tconv", C.TCONV_CASES)):
+        names = sorted({k.split("/")[1] for k in golden.files if k.startswith(fam + "/")})
+        for name in names:
+            k = "%s/%s/%s/" % (fam, name, suf)
+            x, w, b, dy = (np.asfortranarray(golden[k + s]) for s in ("x", "w", "b", "dy"))
+            a = _conv_gpu(U, table[name], x, w, b, dy, tr, reps=2)
+            for out in ("y", "dx", "dw", "db"):
+                assert C.relerr(a[out], golden[k + out]) < C.TOL[np.dtype(dt)], (name, out)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_conv_input_layer_and_accumulation(U, orc, dt):
+    """dx == NULL skips the input gradient; a second pass_back doubles dW/db (beta = 1)."""
+    case = C.CONV_CASES["gt_rank3"]
+    g, x, w, b, dy = C.conv_inputs(case, dt, 22)
+    r1 = orc.conv(g, x, w, b, dy, back_reps=1)
+    a1 = _conv_gpu(U, case, x, w, b, dy, False, want_dx=False, reps=1)
+    a3 = _conv_gpu(U, case, x, w, b, dy, False, want_dx=False, reps=3)
+    assert a1["dx"] is None
+    assert C.relerr(a1["dw"], r1["dw"]) < C.TOL[np.dtype(dt)]
+    assert C.relerr(a3["dw"], 3 * r1["dw"]) < C.TOL[np.dtype(dt)]
+    assert C.relerr(a3["db"], 3 * r1["db"]) < C.TOL[np.dtype(dt)]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_dense_vs_oracle(U, orc, dt):
+    rng = np.random.default_rng(23)
+    c = U.ctx()
+    for name, (n, i, o) in C.DENSE_CASES.items():
+        x, w, b, dy = C.rand(rng, (n, i), dt), C.rand(rng, (i, o), dt), C.rand(rng, (1, o), dt), C.rand(rng, (n, o), dt)
+        r = orc.dense(x, w, b, dy)
+        xd, wd, bd, dyd = U.dev(x), U.dev(w), U.dev(b), U.dev(dy)
+        yd, dxd, dwd, dbd = U.zeros((n, o), dt), U.zeros((n, i), dt), U.zeros((i, o), dt), U.zeros((1, o), dt)
+        c.dense_forward(n, i, o, xd, wd, bd, yd)
+        c.dense_backward(n, i, o, xd, wd, dyd, dwd, dbd, dxd)
+        c.synchronize()
+        got = dict(y=U.host(yd, (n, o)), dx=U.host(dxd, (n, i)), dw=U.host(dwd, (i, o)), db=U.host(dbd, (1, o)))
+        for k in got:
+            assert C.relerr(got[k], r[k]) < C.TOL[np.dtype(dt)], (name, k)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_activation_vs_golden_and_oracle(U, orc, golden, dt):
+    suf = "f32" if dt == np.float32 else "f64"
+    c = U.ctx()
+    rng = np.random.default_rng(24)
+    for name, (kind, alpha) in C.ACT_CASES.items():
+        k = "act/%s/%s/" % (name, suf)
+        sets = [(np.asfortranarray(golden[k + "x"]), np.asfortranarray(golden[k + "dy"]), golden[k + "y"], golden[k + "dx"])]
+        xb = C.rand(rng, (33, 7, 5, 3), dt, -3, 3)  # odd element count exercises the scalar tail
+        dyb = C.rand(rng, xb.shape, dt)
+        rb = orc.activation(kind, alpha, xb, dyb)
+        sets.append((xb, dyb, rb["y"], rb["dx"]))
+        al = 1e-5 if name == "softmax" else alpha  # softmax: alpha carries epsilon (NumericUtils EPSILON2)
+        for x, dy, ry, rdx in sets:
+            rows, vol = x.shape[0], x.size // x.shape[0]
+            xd, dyd = U.dev(x), U.dev(dy)
+            yd, dxd = U.zeros(x.shape, dt), U.zeros(x.shape, dt)
+            c.activation_forward(kind, al, rows, vol, xd, yd)
+            c.activation_backward(kind, al, rows, vol, xd, yd, dyd, dxd)
+            c.synchronize()
+            tol = C.TOL[np.dtype(dt)]
+            assert C.relerr(U.host(yd, x.shape), ry) < tol, name
+            assert C.relerr(U.host(dxd, x.shape), rdx) < tol, name
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_pool_vs_oracle(U, orc, dt):
+    import torch
+    c = U.ctx()
+    rng = np.random.default_rng(25)
+    for name, (kind, n, h, w, ch, rh, rw, sh, sw) in C.POOL_CASES.items():
+        x = np.asfortranarray(np.round(C.rand(rng, (n, h, w, ch), dt) * 4) / 4)  # ties on purpose
+        oh, ow = (h - rh) // sh + 1, (w - rw) // sw + 1
+        dy = C.rand(rng, (n, oh, ow, ch), dt)
+        r = orc.pool(kind, x, rh, rw, sh, sw, dy)
+        g = U.pkg.PoolGeom(n, h, w, ch, rh, rw, sh, sw)
+        xd, dyd = U.dev(x), U.dev(dy)
+        yd, dxd = U.zeros(dy.shape, dt), U.zeros(x.shape, dt)
+        am = torch.zeros(dy.size, dtype=torch.uint8, device="cuda")
+        c.pool_forward(kind, g, xd, yd, am)
+        c.pool_backward(kind, g, dyd, am, dxd)
+        c.synchronize()
+        if kind == 0:  # selection / routing only: bit-exact
+            assert np.array_equal(U.host(yd, dy.shape), r["y"]), name
+        assert C.relerr(U.host(yd, dy.shape), r["y"]) < C.TOL[np.dtype(dt)], name
+        assert C.relerr(U.host(dxd, x.shape), r["dx"]) < C.TOL[np.dtype(dt)], name
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_batchnorm_vs_oracle(U, orc, dt):
+    c = U.ctx()
+    rng = np.random.default_rng(26)
+    for name, (pc, n, h, w, ch, steps) in C.BN_CASES.items():
+        xs = [C.rand(rng, (n, h, w, ch), dt, -1, 2) for _ in range(steps)]
+        G = ch if pc else h * w * ch
+        gm, bt, dy = C.rand(rng, (G,), dt, 0.5, 1.5), C.rand(rng, (G,), dt), C.rand(rng, (n, h, w, ch), dt)
+        r = orc.batchnorm(pc, xs, gm, bt, dy)
+        gmd, btd, dyd = U.dev(gm), U.dev(bt), U.dev(dy)
+        rm, rs, sm, ss = (U.zeros((G,), dt) for _ in range(4))
+        yd, yi, dxd = U.zeros(dy.shape, dt), U.zeros(dy.shape, dt), U.zeros(dy.shape, dt)
+        dg, db = U.zeros((G,), dt), U.zeros((G,), dt)
+        for s, x in enumerate(xs):
+            xd = U.dev(x)
+            c.batchnorm_forward(pc, n, h, w, ch, 1, s > 0, 0.1, 1e-5, xd, gmd, btd, rm, rs, sm, ss, yd)
+        c.batchnorm_backward(pc, n, h, w, ch, xd, gmd, sm, ss, dyd, dg, db, dxd)
+        c.batchnorm_forward(pc, n, h, w, ch, 0, 1, 0.1, 1e-5, xd, gmd, btd, rm, rs, None, None, yi)
+        c.synchronize()
+        got = dict(y=U.host(yd, dy.shape), dx=U.host(dxd, dy.shape), dgamma=U.host(dg, (G,)), dbeta=U.host(db, (G,)),
+                   run_mean=U.host(rm, (G,)), run_inv_sd=U.host(rs, (G,)), y_infer=U.host(yi, dy.shape))
+        tol = 10 * C.TOL[np.dtype(dt)] if dt == np.float64 else C.TOL[np.dtype(dt)]
+        for k in got:
+            assert C.relerr(got[k], r[k]) < tol, (name, k, C.relerr(got[k], r[k]))
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_optimizer_vs_golden(U, golden, dt):
+    suf = "f32" if dt == np.float32 else "f64"
+    c = U.ctx()
+    for name, (kind, hy) in C.OPT_CASES.items():
+        for lam in (0.0, 0.01):
+            k = "opt/%s_l2_%g/%s/" % (name, lam, suf)
+            p0, grads = np.asfortranarray(golden[k + "p0"]), golden[k + "grads"]
+            pd = U.dev(p0)
+            s1, s2, s3 = (U.zeros(p0.shape, dt) for _ in range(3))
+            for t, gr in enumerate(grads):
+                gd = U.dev(np.asfortranarray(gr))
+                st = U.pkg.make_opt_step(kind, hy, t, t // 3, lam, True, np.dtype(dt).name)
+                c.optimizer_step(st, p0.size, pd, gd, s1, s2, s3)
+                assert float(gd.abs().max()) == 0.0  # reset_grad
+            c.synchronize()
+            tol = 2e-6 if dt == np.float32 else 1e-12
+            assert C.relerr(U.host(pd, p0.shape), golden[k + "p"]) < tol, (name, lam)
