@@ -186,3 +186,38 @@ def test_optimizer_vs_golden(U, golden, dt):
             c.synchronize()
             tol = 2e-6 if dt == np.float32 else 1e-12
             assert C.relerr(U.host(pd, p0.shape), golden[k + "p"]) < tol, (name, lam)
+
+
+TC_CASES = ["c2_small", "c2_small_f256", "c2_stride2", "c2_dil1", "c2_1x1", "ragged_c"]
+
+
+def test_conv_tcgen05_vs_oracle(U, orc):
+    """The TMA + tcgen05 3xTF32 implicit GEMM (forward and stride-1 input gradient) against the
+    oracle at the float tolerance; also checks that the tensor-core path is the one that ran."""
+    for name in TC_CASES:
+        case = C.CONV_CASES[name]
+        g, x, w, b, dy = C.conv_inputs(case, np.float32, 31)
+        r = orc.conv(g, x, w, b, dy)
+        a = _conv_gpu(U, case, x, w, b, dy, False, path=U.pkg.PATH_AUTO)
+        assert a["path"] == "tcgen05", name
+        for k in ("y", "dx", "dw", "db"):
+            assert C.relerr(a[k], r[k]) < C.TOL[np.dtype(np.float32)], (name, k, C.relerr(a[k], r[k]))
+
+
+def test_conv_tcgen05_matches_simt_tightly(U):
+    """3xTF32 must sit at FP32-GEMM accuracy (not 1xTF32's ~3e-4): tcgen05 vs the FFMA kernel."""
+    case = C.CONV_CASES["c2_small_f256"]
+    g, x, w, b, dy = C.conv_inputs(case, np.float32, 32)
+    a = _conv_gpu(U, case, x, w, b, dy, False, path=U.pkg.PATH_AUTO)
+    s = _conv_gpu(U, case, x, w, b, dy, False, path=U.pkg.PATH_SIMT)
+    assert a["path"] == "tcgen05" and s["path"] == "simt"
+    assert C.relerr(a["y"], s["y"]) < 5e-6
+    assert C.relerr(a["dx"], s["dx"]) < 5e-6
+
+
+def test_tcgen05_path_refuses_unsupported_shapes(U):
+    case = C.CONV_CASES["gt_rank3"]  # batch 5: no 32-row TMA boxes
+    g, x, w, b, dy = C.conv_inputs(case, np.float32, 33)
+    with pytest.raises(U.pkg.Cattl3Error) as e:
+        _conv_gpu(U, case, x, w, b, dy, False, path=U.pkg.PATH_TCGEN05)
+    assert e.value.code == U.pkg.ERR_UNSUPPORTED
