@@ -120,7 +120,9 @@ class Context:
     def __init__(self, device=0, stream=None):
         self.L = lib()
         self.h = ctypes.c_void_p()
-        sp = ctypes.c_void_p(stream) if stream else None
+        # stream None -> the context creates its own stream; 0 -> the legacy default stream, passed
+        # as the explicit handle cudaStreamLegacy (0x1) because NULL means "create one" in the C ABI
+        sp = None if stream is None else ctypes.c_void_p(stream if stream else 1)
         self._chk(self.L.cattl3_ctx_create(ctypes.byref(self.h), int(device), sp))
 
     def _chk(self, rc):

@@ -247,7 +247,8 @@ int cattl3_ctx_destroy(cattl3_ctx* ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->ws) cudaFree(ctx->ws);
 	if (ctx->tc_w) cudaFree(ctx->tc_w);
-	if (ctx->tc_a) cudaFree(ctx->tc_a);
+	for (int i = 0; i < 2; ++i)
+		if (ctx->lo_buf[i]) cudaFree(ctx->lo_buf[i]);
 	for (int i = 0; i < 3; ++i)
 		if (ctx->stage_dev[i]) cudaFree(ctx->stage_dev[i]);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

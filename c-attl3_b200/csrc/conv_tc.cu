@@ -121,10 +121,18 @@ __device__ __forceinline__ void tmem_ld_16(uint32_t taddr, float* v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address, leading /
-// stride byte offsets (all >> 4), version = 1 (Blackwell), layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// stride byte offsets (all >> 4), version = 1 (Blackwell), layout type (2 = SWIZZLE_128B,
+// 1 = SWIZZLE_128B_BASE32B).
+//
+// Measured on B200 (scripts/umma_probe.cu): an MN-major kind::tf32 operand is only honoured with
+// layout type 1 (128-byte rows, 32-byte swizzle atom, Swizzle<2,5,2>): K atoms of 4 rows (512 B,
+// SBO apart), 32-element MN groups LBO apart; every other swizzle mode yields zeros.  TMA writes
+// that layout with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  K-major operands use the ordinary
+// SWIZZLE_128B (8-row atoms, SBO = 1024).
+constexpr uint32_t LT_SW128 = 2, LT_SW128_BASE32B = 1;
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
 	return (uint64_t) ((smem_addr >> 4) & 0x3FFF) | ((uint64_t) ((lbo_bytes >> 4) & 0x3FFF) << 16) |
-			((uint64_t) ((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | (2ull << 61);
+			((uint64_t) ((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t) layout_type << 61);
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, M = 128, N runtime.
 __host__ __device__ inline uint32_t make_idesc_tf32(int n, bool a_mn_major, bool b_mn_major) {
@@ -133,20 +141,24 @@ __host__ __device__ inline uint32_t make_idesc_tf32(int n, bool a_mn_major, bool
 }
 
 // ---- operand preparation ---------------------------------------------------------------------------
-// lo = x - trunc_tf32(x): the part of x the tensor core does not see when it reads the raw word.
+// lo = rn_tf32(x - trunc_tf32(x)): the part of x the tensor core does not see when it reads the raw
+// fp32 word (kind::tf32 uses the top 19 bits), rounded to nearest-even at TF32 precision so that the
+// hardware's own truncation of lo is exact and the split error is unbiased (~2^-22 relative).
+__device__ __forceinline__ float tf32_lo(float v) {
+	const float r = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+	const uint32_t u = __float_as_uint(r);
+	return __uint_as_float((u + 0xFFFu + ((u >> 13) & 1u)) & 0xFFFFE000u);
+}
 __global__ void __launch_bounds__(256) split_lo_kernel(long long count, const float* __restrict__ x, float* __restrict__ lo) {
 	const long long nvec = count >> 2;
 	const long long stride = (long long) gridDim.x * 256;
 	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < nvec; i += stride) {
 		float4 v = reinterpret_cast<const float4*>(x)[i];
-		v.x -= __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-		v.y -= __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-		v.z -= __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-		v.w -= __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+		v.x = tf32_lo(v.x); v.y = tf32_lo(v.y); v.z = tf32_lo(v.z); v.w = tf32_lo(v.w);
 		reinterpret_cast<float4*>(lo)[i] = v;
 	}
 	for (long long i = (nvec << 2) + blockIdx.x * 256ll + threadIdx.x; i < count; i += stride)
-		lo[i] = x[i] - __uint_as_float(__float_as_uint(x[i]) & 0xFFFFE000u);
+		lo[i] = tf32_lo(x[i]);
 }
 
 // Packs the weights of one gather-GEMM pass into K-major tiles [tap][j_pad][r_pad] (r contiguous),
@@ -161,9 +173,8 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(GatherGeom gg, int r_
 		const int tap = (int) (i / ((long long) r_pad * j_pad));
 		float v = 0.f;
 		if (r < gg.SC && j < gg.J) v = w[tap * gg.w_stap + r * gg.w_sr + j * gg.w_sj];
-		const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-		hi[i] = h;
-		lo[i] = v - h;
+		hi[i] = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+		lo[i] = tf32_lo(v);
 	}
 }
 
@@ -280,10 +291,11 @@ __global__ void __launch_bounds__(192, 1) tc_gather_gemm_kernel(const __grid_con
 						const uint32_t b = pass == 1 ? b_lo : b_hi;
 						#pragma unroll
 						for (int ks = 0; ks < TC_KB / 8; ++ks) {
-							// A: MN-major, 8 k-rows of 128 B per K step (1024 B), 32-row M groups LBO = KB*128 apart
-							const uint64_t da = make_smem_desc(a + ks * 1024, TC_KB * 128, 1024);
+							// A: MN-major, 128 B rows of 32 consecutive m; one K step = 8 rows = two 4-row atoms
+							// (SBO = 512); the four 32-row M groups are LBO = KB*128 apart
+							const uint64_t da = make_smem_desc(a + ks * 1024, TC_KB * 128, 512, LT_SW128_BASE32B);
 							// B: K-major, 128 B rows, 8-row groups SBO = 1024 apart, K step = 32 B inside the row
-							const uint64_t db = make_smem_desc(b + ks * 32, 16, 1024);
+							const uint64_t db = make_smem_desc(b + ks * 32, 16, 1024, LT_SW128);
 							umma_tf32(d, da, db, idesc, (kb | pass | ks) != 0 ? 1u : 0u);
 						}
 					}
@@ -350,7 +362,7 @@ static EncodeTiledFn get_encode() {
 }
 
 static int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-		const cuuint32_t* box) {
+		const cuuint32_t* box, CUtensorMapSwizzle swizzle) {
 	EncodeTiledFn enc = get_encode();
 	if (!enc) {
 		set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -358,7 +370,7 @@ static int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint6
 	}
 	cuuint32_t estr[5] = { 1, 1, 1, 1, 1 };
 	CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t) rank, const_cast<void*>(base), dims, strides_bytes, box,
-			estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+			estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
 			CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) {
 		set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int) r, rank);
@@ -368,6 +380,20 @@ static int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint6
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Low-order split of a tensor into one of the context's two scratch slots; a split made earlier in
+// the same API call (ctx->lo_src[slot] == ptr) is reused -- conv_backward needs lo(dY) twice.
+static int get_lo_split(cattl3_ctx* ctx, const float* ptr, long long elems, int slot, const float** lo_out) {
+	for (int s = 0; s < 2; ++s)
+		if (ctx->lo_src[s] == ptr && ctx->lo_elems[s] == elems) { *lo_out = (const float*) ctx->lo_buf[s]; return CATTL3_OK; }
+	CATTL3_CHECK(ensure_buffer(ctx, &ctx->lo_buf[slot], &ctx->lo_bytes[slot], (size_t) elems * 4));
+	split_lo_kernel<<<ew_grid(ctx, elems / 4 + 1, 256), 256, 0, ctx->stream>>>(elems, ptr, (float*) ctx->lo_buf[slot]);
+	CATTL3_LAUNCHED(ctx);
+	ctx->lo_src[slot] = ptr;
+	ctx->lo_elems[slot] = elems;
+	*lo_out = (const float*) ctx->lo_buf[slot];
+	return CATTL3_OK;
+}
 
 bool tc_gather_gemm_supported(const cattl3_ctx*, const GatherGeom& gg) {
 	// 32-row TMA boxes along n; no per-pixel divisibility tests (strided transposed gathers go to SIMT)
@@ -393,13 +419,11 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 	const long long w_elems = (long long) T * j_pad * r_pad;
 
 	// operand preparation: low-order split of the activations, packed + split weights
-	CATTL3_CHECK(ensure_buffer(ctx, &ctx->tc_a, &ctx->tc_a_bytes, (size_t) src_elems * 4));
 	CATTL3_CHECK(ensure_buffer(ctx, &ctx->tc_w, &ctx->tc_w_bytes, (size_t) w_elems * 8));
-	float* a_lo = (float*) ctx->tc_a;
+	const float* a_lo = nullptr;
+	CATTL3_CHECK(get_lo_split(ctx, src, src_elems, 0, &a_lo));
 	float* w_hi = (float*) ctx->tc_w;
 	float* w_lo = w_hi + w_elems;
-	split_lo_kernel<<<ew_grid(ctx, src_elems / 4 + 1, 256), 256, 0, ctx->stream>>>(src_elems, src, a_lo);
-	CATTL3_LAUNCHED(ctx);
 	pack_weights_kernel<<<ew_grid(ctx, w_elems, 256), 256, 0, ctx->stream>>>(gg, r_pad, j_pad, w, w_hi, w_lo);
 	CATTL3_LAUNCHED(ctx);
 
@@ -408,15 +432,15 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 		cuuint64_t dims[4] = { (cuuint64_t) gg.N, (cuuint64_t) gg.SH, (cuuint64_t) gg.SW, (cuuint64_t) gg.SC };
 		cuuint64_t str[3] = { (cuuint64_t) gg.N * 4, (cuuint64_t) gg.N * gg.SH * 4, (cuuint64_t) gg.N * gg.SH * gg.SW * 4 };
 		cuuint32_t box[4] = { 32, 1, 1, (cuuint32_t) TC_KB };
-		CATTL3_CHECK(encode_map(&tm_a_hi, src, 4, dims, str, box));
-		CATTL3_CHECK(encode_map(&tm_a_lo, a_lo, 4, dims, str, box));
+		CATTL3_CHECK(encode_map(&tm_a_hi, src, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+		CATTL3_CHECK(encode_map(&tm_a_lo, a_lo, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
 	}
 	{
 		cuuint64_t dims[3] = { (cuuint64_t) r_pad, (cuuint64_t) j_pad, (cuuint64_t) T };
 		cuuint64_t str[2] = { (cuuint64_t) r_pad * 4, (cuuint64_t) r_pad * j_pad * 4 };
 		cuuint32_t box[3] = { 32, (cuuint32_t) BN, 1 };
-		CATTL3_CHECK(encode_map(&tm_b_hi, w_hi, 3, dims, str, box));
-		CATTL3_CHECK(encode_map(&tm_b_lo, w_lo, 3, dims, str, box));
+		CATTL3_CHECK(encode_map(&tm_b_hi, w_hi, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+		CATTL3_CHECK(encode_map(&tm_b_lo, w_lo, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
 	}
 
 	TcGemmParams p;
@@ -442,10 +466,234 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 	return CATTL3_OK;
 }
 
-bool tc_wgrad_supported(const cattl3_ctx*, const GatherGeom&) { return false; }
-int tc_wgrad_f32(cattl3_ctx*, const GatherGeom&, const float*, const float*, float*) {
-	set_error("tcgen05 weight-gradient path not built");
-	return CATTL3_ERR_UNSUPPORTED;
+// ---- the weight-gradient kernel ---------------------------------------------------------------------
+// dw(tap, r, j) += sum_m src(m, tap, r) * plain(m, j): a GEMM whose reduction runs over
+// m = N*OH*OW.  Both operands are K-major here (m is contiguous in HBM for both):
+//   A tile: 128 rows = (tap, channel) pairs, built from 128/RB TMA boxes [32 m][1][1][RB channels]
+//           of the gathered tensor (one box per tap, at that tap's spatial coordinate);
+//   B tile: BN rows = output channels, one 2-D box [32 m][BN] of the plain tensor.
+// One k-block = one 32-row m-group (32 batch entries of one pixel).  Each CTA owns one
+// (row tile, column tile) and one contiguous range of m-groups (split-K); the fp32 partial tile is
+// written to scratch and reduced into dw in split order by wgrad_reduce_tc_kernel (deterministic,
+// accumulating: Parameters::accumulate_grad, C-ATTL3/parameters/StandardParameters.hpp:115-123).
+struct TcWgradParams {
+	int N, OH, OW, R, J, RH, RW;
+	int ah, bh, ch, aw, bw, cw;
+	int RB;            // channel rows per TMA box (32 / 64 / 128)
+	int rchunks;       // r_pad / RB
+	int row_blocks;    // T * rchunks
+	int row_tiles, j_tiles, splits;
+	long long mgroups, mg_per_split;
+	int BN, stages, tmem_cols;
+	long long w_stap, w_sr, w_sj, dw_elems;
+	float* partial;
+};
+
+__global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
+		const __grid_constant__ CUtensorMap tm_a_lo, const __grid_constant__ CUtensorMap tm_b_hi,
+		const __grid_constant__ CUtensorMap tm_b_lo, const TcWgradParams p) {
+	extern __shared__ __align__(1024) uint8_t smem_raw[];
+	uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
+	const int b_bytes = p.BN * 128;
+	const int stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
+	uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t) p.stages * stage_bytes);
+	uint64_t* full = bars;
+	uint64_t* empty = bars + p.stages;
+	uint64_t* acc_full = bars + 2 * p.stages;
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int tile = blockIdx.x % (p.row_tiles * p.j_tiles), z = blockIdx.x / (p.row_tiles * p.j_tiles);
+	const int rt = tile % p.row_tiles, jt = tile / p.row_tiles;
+	const int boxes_per_tile = 128 / p.RB;
+	const int rb0 = rt * boxes_per_tile;
+	int nboxes = p.row_blocks - rb0;
+	if (nboxes > boxes_per_tile) nboxes = boxes_per_tile;
+	const long long mg0 = (long long) z * p.mg_per_split;
+	long long mg1 = mg0 + p.mg_per_split;
+	if (mg1 > p.mgroups) mg1 = p.mgroups;
+	const long long kblocks = mg1 > mg0 ? mg1 - mg0 : 0;
+
+	if (warp == 0 && elect_one()) {
+		tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo);
+		tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
+		for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+		mbar_init(acc_full, 1);
+		fence_barrier_init();
+	}
+	if (warp == 1) tmem_alloc(tmem_slot, (uint32_t) p.tmem_cols);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot;
+
+	if (warp == 0) {
+		if (elect_one()) {
+			int s = 0; uint32_t ph = 0;
+			const uint32_t tx = (uint32_t) (2 * nboxes * p.RB * 128 + 2 * b_bytes);
+			for (long long kb = 0; kb < kblocks; ++kb) {
+				const long long m = (mg0 + kb) * 32;
+				const int n0 = (int) (m % p.N);
+				const long long pix = m / p.N;
+				const int oh = (int) (pix % p.OH), ow = (int) (pix / p.OH);
+				mbar_wait(&empty[s], ph ^ 1);
+				uint8_t* st = smem + (size_t) s * stage_bytes;
+				mbar_expect_tx(&full[s], tx);
+				for (int bx = 0; bx < nboxes; ++bx) {
+					const int rb = rb0 + bx;
+					const int tap = rb / p.rchunks, c0 = (rb % p.rchunks) * p.RB;
+					const int rh = tap % p.RH, rw = tap / p.RH;
+					const int ih = oh * p.ah + rh * p.bh + p.ch, iw = ow * p.aw + rw * p.bw + p.cw;
+					tma_load_4d(st + bx * p.RB * 128, &tm_a_hi, &full[s], n0, ih, iw, c0);
+					tma_load_4d(st + TC_A_BYTES + bx * p.RB * 128, &tm_a_lo, &full[s], n0, ih, iw, c0);
+				}
+				tma_load_2d(st + 2 * TC_A_BYTES, &tm_b_hi, &full[s], (int) m, jt * p.BN);
+				tma_load_2d(st + 2 * TC_A_BYTES + b_bytes, &tm_b_lo, &full[s], (int) m, jt * p.BN);
+				if (++s == p.stages) { s = 0; ph ^= 1; }
+			}
+		}
+	} else if (warp == 1) {
+		if (elect_one()) {
+			const uint32_t idesc = make_idesc_tf32(p.BN, false, false);
+			int s = 0; uint32_t ph = 0;
+			for (long long kb = 0; kb < kblocks; ++kb) {
+				mbar_wait(&full[s], ph);
+				tc_fence_after();
+				const uint32_t a_hi = smem_u32(smem + (size_t) s * stage_bytes);
+				const uint32_t a_lo = a_hi + TC_A_BYTES;
+				const uint32_t b_hi = a_hi + 2 * TC_A_BYTES;
+				const uint32_t b_lo = b_hi + b_bytes;
+				#pragma unroll
+				for (int pass = 0; pass < 3; ++pass) {
+					const uint32_t a = pass == 0 ? a_lo : a_hi;
+					const uint32_t b = pass == 1 ? b_lo : b_hi;
+					#pragma unroll
+					for (int ks = 0; ks < 4; ++ks) {
+						const uint64_t da = make_smem_desc(a + ks * 32, 16, 1024, LT_SW128);
+						const uint64_t db = make_smem_desc(b + ks * 32, 16, 1024, LT_SW128);
+						umma_tf32(tmem_base, da, db, idesc, (kb != 0 || pass != 0 || ks != 0) ? 1u : 0u);
+					}
+				}
+				umma_commit(&empty[s]);
+				if (++s == p.stages) { s = 0; ph ^= 1; }
+			}
+			umma_commit(acc_full);
+		}
+	} else {
+		const int q = warp & 3;
+		float* dst = p.partial + (long long) z * p.dw_elems;
+		const int row = 32 * q + lane;                 // accumulator lane = row of the tile
+		const int rb = rb0 + row / p.RB;
+		const bool row_ok = rb < p.row_blocks;
+		const int tap = row_ok ? rb / p.rchunks : 0;
+		const int r = (rb % p.rchunks) * p.RB + row % p.RB;
+		const bool ok = row_ok && r < p.R;
+		const long long base = tap * p.w_stap + r * p.w_sr;
+		if (kblocks > 0) {
+			mbar_wait(acc_full, 0);
+			tc_fence_after();
+		}
+		const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16);
+		for (int c0 = 0; c0 < p.BN; c0 += 16) {
+			float v[16];
+			if (kblocks > 0) {
+				tmem_ld_16(taddr + c0, v);
+				tmem_ld_wait();
+			} else {
+				#pragma unroll
+				for (int i = 0; i < 16; ++i) v[i] = 0.f;
+			}
+			#pragma unroll
+			for (int i = 0; i < 16; ++i) {
+				const int j = jt * p.BN + c0 + i;
+				if (ok && j < p.J) dst[base + j * p.w_sj] = v[i];
+			}
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 1) tmem_dealloc(tmem_base, (uint32_t) p.tmem_cols);
+}
+
+__global__ void __launch_bounds__(256) wgrad_reduce_tc_kernel(const float* __restrict__ partial, int splits, long long elems,
+		float* __restrict__ dw) {
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < elems; i += (long long) gridDim.x * 256) {
+		float s = 0.f;
+		for (int z = 0; z < splits; ++z) s += partial[(long long) z * elems + i];
+		dw[i] += s;
+	}
+}
+
+bool tc_wgrad_supported(const cattl3_ctx*, const GatherGeom& gg) {
+	if (gg.N % 32 != 0 || gg.denh != 1 || gg.denw != 1) return false;
+	if (gg.SC < 16 || gg.J < 16) return false;
+	const long long M = (long long) gg.N * gg.OH * gg.OW;
+	if (M >= (1ll << 31)) return false;  // TMA coordinates are 32-bit
+	return get_encode() != nullptr;
+}
+
+int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const float* plain, float* dw) {
+	CATTL3_REQUIRE(aligned16(src) && aligned16(plain), "tcgen05 path needs 16-byte aligned tensors");
+	const int T = gg.RH * gg.RW;
+	const int r_pad = round_up(gg.SC, 32);
+	const int RB = r_pad % 128 == 0 ? 128 : (r_pad % 64 == 0 ? 64 : 32);
+	const int BN = gg.J >= 256 ? 256 : round_up(gg.J, 16);
+	const long long M = (long long) gg.N * gg.OH * gg.OW;
+	const long long src_elems = (long long) gg.N * gg.SH * gg.SW * gg.SC;
+	const long long plain_elems = M * gg.J;
+
+	const float *a_lo = nullptr, *b_lo = nullptr;
+	CATTL3_CHECK(get_lo_split(ctx, src, src_elems, 0, &a_lo));
+	CATTL3_CHECK(get_lo_split(ctx, plain, plain_elems, 1, &b_lo));
+
+	CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
+	{
+		cuuint64_t dims[4] = { (cuuint64_t) gg.N, (cuuint64_t) gg.SH, (cuuint64_t) gg.SW, (cuuint64_t) gg.SC };
+		cuuint64_t str[3] = { (cuuint64_t) gg.N * 4, (cuuint64_t) gg.N * gg.SH * 4, (cuuint64_t) gg.N * gg.SH * gg.SW * 4 };
+		cuuint32_t box[4] = { 32, 1, 1, (cuuint32_t) RB };
+		CATTL3_CHECK(encode_map(&tm_a_hi, src, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+		CATTL3_CHECK(encode_map(&tm_a_lo, a_lo, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+	}
+	{
+		cuuint64_t dims[2] = { (cuuint64_t) M, (cuuint64_t) gg.J };
+		cuuint64_t str[1] = { (cuuint64_t) M * 4 };
+		cuuint32_t box[2] = { 32, (cuuint32_t) BN };
+		CATTL3_CHECK(encode_map(&tm_b_hi, plain, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+		CATTL3_CHECK(encode_map(&tm_b_lo, b_lo, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+	}
+
+	TcWgradParams p;
+	p.N = gg.N; p.OH = gg.OH; p.OW = gg.OW; p.R = gg.SC; p.J = gg.J; p.RH = gg.RH; p.RW = gg.RW;
+	p.ah = gg.ah; p.bh = gg.bh; p.ch = gg.ch; p.aw = gg.aw; p.bw = gg.bw; p.cw = gg.cw;
+	p.RB = RB; p.rchunks = r_pad / RB; p.row_blocks = T * p.rchunks;
+	p.row_tiles = (p.row_blocks * RB + 127) / 128;
+	p.j_tiles = (gg.J + BN - 1) / BN;
+	p.mgroups = M / 32;
+	const int tiles = p.row_tiles * p.j_tiles;
+	long long splits = ctx->sm_count / tiles;
+	if (splits < 1) splits = 1;
+	if (splits > p.mgroups) splits = p.mgroups;
+	p.mg_per_split = ceil_div(p.mgroups, splits);
+	p.splits = (int) ceil_div(p.mgroups, p.mg_per_split);
+	p.BN = BN;
+	const int stage_bytes = 2 * TC_A_BYTES + 2 * BN * 128;
+	int stages = (227 * 1024 - 2048) / stage_bytes;
+	if (stages > 6) stages = 6;
+	p.stages = stages;
+	int cols = 32;
+	while (cols < BN) cols <<= 1;
+	p.tmem_cols = cols;
+	p.w_stap = gg.w_stap; p.w_sr = gg.w_sr; p.w_sj = gg.w_sj;
+	p.dw_elems = (long long) T * gg.SC * gg.J;
+	CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, (size_t) p.splits * p.dw_elems * 4));
+	p.partial = (float*) ctx->ws;
+	const size_t smem_bytes = (size_t) stages * stage_bytes + 1024 + 256;
+	CATTL3_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+	tc_wgrad_kernel<<<tiles * p.splits, 192, smem_bytes, ctx->stream>>>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p);
+	CATTL3_LAUNCHED(ctx);
+	wgrad_reduce_tc_kernel<<<ew_grid(ctx, p.dw_elems, 256), 256, 0, ctx->stream>>>(p.partial, p.splits, p.dw_elems, dw);
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
 }
 
 } // namespace cattl3

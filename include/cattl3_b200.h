@@ -132,8 +132,9 @@ int cattl3_abi_version(void);
 const char* cattl3_last_error(void);
 /* Number of visible CUDA devices (0 when there is none; never fails). */
 int cattl3_device_count(void);
-/* cuda_stream: a cudaStream_t to enqueue on (e.g. the caller's framework stream) or NULL to let
- * the context create its own non-blocking stream. */
+/* cuda_stream: a cudaStream_t to enqueue on (e.g. the caller's framework stream; pass
+ * cudaStreamLegacy = (cudaStream_t) 0x1 for the default stream) or NULL to let the context create
+ * its own non-blocking stream. */
 int cattl3_ctx_create(cattl3_ctx** out, int device, void* cuda_stream);
 int cattl3_ctx_destroy(cattl3_ctx* ctx);
 int cattl3_ctx_synchronize(cattl3_ctx* ctx);
