@@ -485,10 +485,16 @@ struct TcWgradParams {
 	int row_tiles, j_tiles, splits;
 	long long mgroups, mg_per_split;
 	int BN, stages, tmem_cols;
+	int flush;         // k-blocks accumulated in TMEM before the partial tile is folded into fp32 scratch
 	long long w_stap, w_sr, w_sj, dw_elems;
-	float* partial;
+	float* partial;    // [split][tile][BN columns][128 rows]
 };
 
+// Tensor-core accumulation truncates (round-toward-zero) at every MMA, so a reduction of n MMA steps
+// carries a bias of ~n * 2^-24 relative (measured: 2e-4 on the 10^4-step config-2 weight gradient).
+// The kernel therefore closes a TMEM accumulator every `flush` k-blocks; the epilogue warps fold it
+// into a CTA-private fp32 tile with round-to-nearest adds while the MMA warp fills the other
+// accumulator.
 __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
 		const __grid_constant__ CUtensorMap tm_a_lo, const __grid_constant__ CUtensorMap tm_b_hi,
 		const __grid_constant__ CUtensorMap tm_b_lo, const TcWgradParams p) {
@@ -500,10 +506,12 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
 	uint64_t* full = bars;
 	uint64_t* empty = bars + p.stages;
 	uint64_t* acc_full = bars + 2 * p.stages;
-	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+	uint64_t* acc_empty = acc_full + 2;
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int tile = blockIdx.x % (p.row_tiles * p.j_tiles), z = blockIdx.x / (p.row_tiles * p.j_tiles);
+	const int tiles = p.row_tiles * p.j_tiles;
+	const int tile = blockIdx.x % tiles, z = blockIdx.x / tiles;
 	const int rt = tile % p.row_tiles, jt = tile / p.row_tiles;
 	const int boxes_per_tile = 128 / p.RB;
 	const int rb0 = rt * boxes_per_tile;
@@ -513,12 +521,13 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
 	long long mg1 = mg0 + p.mg_per_split;
 	if (mg1 > p.mgroups) mg1 = p.mgroups;
 	const long long kblocks = mg1 > mg0 ? mg1 - mg0 : 0;
+	const long long chunks = (kblocks + p.flush - 1) / p.flush;
 
 	if (warp == 0 && elect_one()) {
 		tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo);
 		tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
 		for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-		mbar_init(acc_full, 1);
+		for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
 		fence_barrier_init();
 	}
 	if (warp == 1) tmem_alloc(tmem_slot, (uint32_t) p.tmem_cols);
@@ -556,58 +565,66 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
 		if (elect_one()) {
 			const uint32_t idesc = make_idesc_tf32(p.BN, false, false);
 			int s = 0; uint32_t ph = 0;
-			for (long long kb = 0; kb < kblocks; ++kb) {
-				mbar_wait(&full[s], ph);
+			int acc = 0; uint32_t acc_ph = 0;
+			long long kb = 0;
+			for (long long c = 0; c < chunks; ++c) {
+				mbar_wait(&acc_empty[acc], acc_ph ^ 1);
 				tc_fence_after();
-				const uint32_t a_hi = smem_u32(smem + (size_t) s * stage_bytes);
-				const uint32_t a_lo = a_hi + TC_A_BYTES;
-				const uint32_t b_hi = a_hi + 2 * TC_A_BYTES;
-				const uint32_t b_lo = b_hi + b_bytes;
-				#pragma unroll
-				for (int pass = 0; pass < 3; ++pass) {
-					const uint32_t a = pass == 0 ? a_lo : a_hi;
-					const uint32_t b = pass == 1 ? b_lo : b_hi;
+				const uint32_t d = tmem_base + (uint32_t) (acc * p.BN);
+				const long long kend = kb + p.flush < kblocks ? kb + p.flush : kblocks;
+				for (bool first = true; kb < kend; ++kb) {
+					mbar_wait(&full[s], ph);
+					tc_fence_after();
+					const uint32_t a_hi = smem_u32(smem + (size_t) s * stage_bytes);
+					const uint32_t a_lo = a_hi + TC_A_BYTES;
+					const uint32_t b_hi = a_hi + 2 * TC_A_BYTES;
+					const uint32_t b_lo = b_hi + b_bytes;
 					#pragma unroll
-					for (int ks = 0; ks < 4; ++ks) {
-						const uint64_t da = make_smem_desc(a + ks * 32, 16, 1024, LT_SW128);
-						const uint64_t db = make_smem_desc(b + ks * 32, 16, 1024, LT_SW128);
-						umma_tf32(tmem_base, da, db, idesc, (kb != 0 || pass != 0 || ks != 0) ? 1u : 0u);
+					for (int pass = 0; pass < 3; ++pass) {
+						const uint32_t a = pass == 0 ? a_lo : a_hi;
+						const uint32_t b = pass == 1 ? b_lo : b_hi;
+						#pragma unroll
+						for (int ks = 0; ks < 4; ++ks) {
+							const uint64_t da = make_smem_desc(a + ks * 32, 16, 1024, LT_SW128);
+							const uint64_t db = make_smem_desc(b + ks * 32, 16, 1024, LT_SW128);
+							umma_tf32(d, da, db, idesc, (first && pass == 0 && ks == 0) ? 0u : 1u);
+						}
 					}
+					first = false;
+					umma_commit(&empty[s]);
+					if (++s == p.stages) { s = 0; ph ^= 1; }
 				}
-				umma_commit(&empty[s]);
-				if (++s == p.stages) { s = 0; ph ^= 1; }
+				umma_commit(&acc_full[acc]);
+				if (++acc == 2) { acc = 0; acc_ph ^= 1; }
 			}
-			umma_commit(acc_full);
 		}
 	} else {
 		const int q = warp & 3;
-		float* dst = p.partial + (long long) z * p.dw_elems;
-		const int row = 32 * q + lane;                 // accumulator lane = row of the tile
-		const int rb = rb0 + row / p.RB;
-		const bool row_ok = rb < p.row_blocks;
-		const int tap = row_ok ? rb / p.rchunks : 0;
-		const int r = (rb % p.rchunks) * p.RB + row % p.RB;
-		const bool ok = row_ok && r < p.R;
-		const long long base = tap * p.w_stap + r * p.w_sr;
-		if (kblocks > 0) {
-			mbar_wait(acc_full, 0);
-			tc_fence_after();
+		const int row = 32 * q + lane;  // accumulator lane = row of the tile
+		float* dst = p.partial + ((long long) z * tiles + tile) * p.BN * 128 + row;
+		if (chunks == 0) {
+			for (int c0 = 0; c0 < p.BN; ++c0) dst[(long long) c0 * 128] = 0.f;
 		}
-		const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16);
-		for (int c0 = 0; c0 < p.BN; c0 += 16) {
-			float v[16];
-			if (kblocks > 0) {
+		int acc = 0; uint32_t acc_ph = 0;
+		for (long long c = 0; c < chunks; ++c) {
+			mbar_wait(&acc_full[acc], acc_ph);
+			tc_fence_after();
+			const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16) + (uint32_t) (acc * p.BN);
+			for (int c0 = 0; c0 < p.BN; c0 += 16) {
+				float v[16];
 				tmem_ld_16(taddr + c0, v);
 				tmem_ld_wait();
-			} else {
+				if (c > 0) {
+					#pragma unroll
+					for (int i = 0; i < 16; ++i) v[i] += dst[(long long) (c0 + i) * 128];
+				}
 				#pragma unroll
-				for (int i = 0; i < 16; ++i) v[i] = 0.f;
+				for (int i = 0; i < 16; ++i) dst[(long long) (c0 + i) * 128] = v[i];
 			}
-			#pragma unroll
-			for (int i = 0; i < 16; ++i) {
-				const int j = jt * p.BN + c0 + i;
-				if (ok && j < p.J) dst[base + j * p.w_sj] = v[i];
-			}
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&acc_empty[acc]);
+			if (++acc == 2) { acc = 0; acc_ph ^= 1; }
 		}
 	}
 	tc_fence_before();
@@ -615,12 +632,23 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
 	if (warp == 1) tmem_dealloc(tmem_base, (uint32_t) p.tmem_cols);
 }
 
-__global__ void __launch_bounds__(256) wgrad_reduce_tc_kernel(const float* __restrict__ partial, int splits, long long elems,
-		float* __restrict__ dw) {
-	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < elems; i += (long long) gridDim.x * 256) {
+// dw(tap, r, j) += sum over splits of the scratch tiles, in split order (deterministic).
+__global__ void __launch_bounds__(256) wgrad_reduce_tc_kernel(const TcWgradParams p, int T, float* __restrict__ dw) {
+	const long long total = (long long) T * p.R * p.J;
+	const int tiles = p.row_tiles * p.j_tiles;
+	const int boxes_per_tile = 128 / p.RB;
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long) gridDim.x * 256) {
+		const int r = (int) (i % p.R);
+		const int tap = (int) ((i / p.R) % T);
+		const int j = (int) (i / ((long long) p.R * T));
+		const int rb = tap * p.rchunks + r / p.RB;
+		const int rt = rb / boxes_per_tile;
+		const int row = (rb % boxes_per_tile) * p.RB + r % p.RB;
+		const int jt = j / p.BN, col = j % p.BN;
+		const long long off = ((long long) (rt + p.row_tiles * jt) * p.BN + col) * 128 + row;
 		float s = 0.f;
-		for (int z = 0; z < splits; ++z) s += partial[(long long) z * elems + i];
-		dw[i] += s;
+		for (int z = 0; z < p.splits; ++z) s += p.partial[(long long) z * tiles * p.BN * 128 + off];
+		dw[tap * p.w_stap + r * p.w_sr + j * p.w_sj] += s;
 	}
 }
 
@@ -681,17 +709,18 @@ int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const 
 	if (stages > 6) stages = 6;
 	p.stages = stages;
 	int cols = 32;
-	while (cols < BN) cols <<= 1;
+	while (cols < 2 * BN) cols <<= 1;
 	p.tmem_cols = cols;
+	p.flush = 32;
 	p.w_stap = gg.w_stap; p.w_sr = gg.w_sr; p.w_sj = gg.w_sj;
 	p.dw_elems = (long long) T * gg.SC * gg.J;
-	CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, (size_t) p.splits * p.dw_elems * 4));
+	CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, (size_t) p.splits * tiles * BN * 128 * 4));
 	p.partial = (float*) ctx->ws;
 	const size_t smem_bytes = (size_t) stages * stage_bytes + 1024 + 256;
 	CATTL3_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 	tc_wgrad_kernel<<<tiles * p.splits, 192, smem_bytes, ctx->stream>>>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p);
 	CATTL3_LAUNCHED(ctx);
-	wgrad_reduce_tc_kernel<<<ew_grid(ctx, p.dw_elems, 256), 256, 0, ctx->stream>>>(p.partial, p.splits, p.dw_elems, dw);
+	wgrad_reduce_tc_kernel<<<ew_grid(ctx, p.dw_elems, 256), 256, 0, ctx->stream>>>(p, T, dw);
 	CATTL3_LAUNCHED(ctx);
 	return CATTL3_OK;
 }

@@ -27,3 +27,6 @@ t = timeit(lambda: ctx.conv_forward(g, x, w, b, y))
 print("fwd  %.3f ms  %.1f TFLOP/s  path=%s" % (t, flop / t / 1e9, ctx.last_path))
 t = timeit(lambda: ctx.conv_backward(g, x, w, dy, dw, db, dx))
 print("bwd  %.3f ms  %.1f TFLOP/s (2 GEMMs) path=%s" % (t, 2 * flop / t / 1e9, ctx.last_path))
+t2 = timeit(lambda: ctx.conv_backward(g, x, w, dy, dw, db, None))
+print("bwd(no dx: wgrad+bgrad) %.3f ms -> dgrad(+split) %.3f ms" % (t2, t - t2))
+print("launches", ctx.launches)
