@@ -64,11 +64,14 @@ _SYMBOLS = [
     "cattl3_memcpy_h2d", "cattl3_memcpy_d2h", "cattl3_memcpy_d2d", "cattl3_host_alloc", "cattl3_host_free",
     "cattl3_conv_output_dims", "cattl3_pool_output_dims",
     "cattl3_conv_forward_host_f32", "cattl3_conv_backward_host_f32",
+    "cattl3_comm_unique_id", "cattl3_comm_create", "cattl3_comm_create_from_env", "cattl3_comm_destroy",
+    "cattl3_comm_world_size", "cattl3_comm_rank", "cattl3_comm_group_start", "cattl3_comm_group_end",
+    "cattl3_comm_allreduce_sum_f32", "cattl3_comm_allreduce_sum_f64",
 ] + [n + s for s in ("_f32", "_f64") for n in (
     "cattl3_conv_forward", "cattl3_conv_backward", "cattl3_transconv_forward", "cattl3_transconv_backward",
     "cattl3_dense_forward", "cattl3_dense_backward", "cattl3_activation_forward", "cattl3_activation_backward",
     "cattl3_pool_forward", "cattl3_pool_backward", "cattl3_batchnorm_forward", "cattl3_batchnorm_backward",
-    "cattl3_optimizer_step", "cattl3_add_inplace", "cattl3_scale")]
+    "cattl3_optimizer_step", "cattl3_add_inplace", "cattl3_scale", "cattl3_axpy")]
 
 
 def lib():

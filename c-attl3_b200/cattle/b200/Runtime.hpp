@@ -1,0 +1,250 @@
+/*
+ * b200/Runtime.hpp -- C++ face of the C ABI in include/cattl3_b200.h: status codes become
+ * exceptions, device memory becomes RAII, and the float / double entry points are selected by
+ * the Scalar template parameter.  Header-only, no CUDA headers needed: g++ is enough.
+ *
+ * The shape follows the reference's own (unfinished) device plumbing: status -> exception as in
+ * C-ATTL3/core/gpu/cuda/CUDAError.hpp:17-52, owning device array as in
+ * C-ATTL3/core/gpu/cuda/CUDAArray.hpp:46-118 -- but every transfer here is enqueued on one
+ * stream and only device-to-host reads synchronise.
+ */
+#ifndef C_ATTL3_B200_RUNTIME_H_
+#define C_ATTL3_B200_RUNTIME_H_
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <utility>
+
+#include "cattl3_b200.h"
+
+namespace cattle {
+namespace b200 {
+
+/** Thrown whenever a libcattl3_b200 call fails; there is no fallback path to fall back to. */
+class Error : public std::runtime_error {
+public:
+	inline Error(int code, const std::string& what) :
+			std::runtime_error(what),
+			code(code) { }
+	const int code;
+};
+
+inline void check(int rc, const char* expr, const char* file, int line) {
+	if (rc != CATTL3_OK) {
+		throw Error(rc, std::string("libcattl3_b200: ") + cattl3_last_error() + " [" + expr + " at " +
+				file + ":" + std::to_string(line) + "]");
+	}
+}
+
+#define CATTLE_B200_CHECK(expr) ::cattle::b200::check((expr), #expr, __FILE__, __LINE__)
+
+/**
+ * The process-wide device context: one device (CATTL3_DEVICE, else LOCAL_RANK, else 0 -- one
+ * process per GPU), one stream.  All layers of all networks enqueue on that stream, so work
+ * issued from the pthread lanes of a ParallelNeuralNetwork
+ * (C-ATTL3/neural_network/ParallelNeuralNetwork.hpp:142-197) is ordered with respect to the
+ * optimizer's parameter updates without any cross-stream events; the lock serialises the
+ * host-side bookkeeping of the context's workspaces.
+ */
+class Context {
+public:
+	typedef std::unique_lock<std::recursive_mutex> Lock;
+	inline static Context& get() {
+		static Context instance;
+		return instance;
+	}
+	inline cattl3_ctx* handle() const {
+		return ctx;
+	}
+	inline Lock lock() {
+		return Lock(mutex);
+	}
+	inline int device() const {
+		return device_index;
+	}
+	inline void synchronize() {
+		Lock l(mutex);
+		CATTLE_B200_CHECK(cattl3_ctx_synchronize(ctx));
+	}
+	inline std::int64_t launch_count() const {
+		return cattl3_ctx_launch_count(ctx);
+	}
+	inline const char* last_path() const {
+		return cattl3_ctx_last_path(ctx);
+	}
+	/** CATTL3_PATH_AUTO / _SIMT / _TCGEN05. */
+	inline void set_conv_path(int path) {
+		Lock l(mutex);
+		CATTLE_B200_CHECK(cattl3_ctx_set_conv_path(ctx, path));
+	}
+	Context(const Context&) = delete;
+	Context& operator=(const Context&) = delete;
+private:
+	inline Context() :
+			ctx(nullptr),
+			device_index(0) {
+		const char* dev = std::getenv("CATTL3_DEVICE");
+		if (!dev)
+			dev = std::getenv("LOCAL_RANK");
+		if (dev)
+			device_index = std::atoi(dev);
+		CATTLE_B200_CHECK(cattl3_ctx_create(&ctx, device_index, nullptr));
+	}
+	inline ~Context() {
+		cattl3_ctx_destroy(ctx);
+	}
+	cattl3_ctx* ctx;
+	int device_index;
+	std::recursive_mutex mutex;
+};
+
+/** Scalar -> `_f32` / `_f64` entry points. */
+template<typename Scalar> struct Api;
+
+#define CATTLE_B200_API(S, SUF) \
+template<> struct Api<S> { \
+	static int conv_forward(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y) { \
+		return cattl3_conv_forward_##SUF(c, g, x, w, b, y); } \
+	static int conv_backward(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* dy, S* dw, S* db, S* dx) { \
+		return cattl3_conv_backward_##SUF(c, g, x, w, dy, dw, db, dx); } \
+	static int transconv_forward(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y) { \
+		return cattl3_transconv_forward_##SUF(c, g, x, w, b, y); } \
+	static int transconv_backward(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* dy, S* dw, S* db, S* dx) { \
+		return cattl3_transconv_backward_##SUF(c, g, x, w, dy, dw, db, dx); } \
+	static int dense_forward(cattl3_ctx* c, std::int32_t n, std::int32_t in, std::int32_t out, const S* x, const S* w, const S* b, S* y) { \
+		return cattl3_dense_forward_##SUF(c, n, in, out, x, w, b, y); } \
+	static int dense_backward(cattl3_ctx* c, std::int32_t n, std::int32_t in, std::int32_t out, const S* x, const S* w, const S* dy, S* dw, S* db, S* dx) { \
+		return cattl3_dense_backward_##SUF(c, n, in, out, x, w, dy, dw, db, dx); } \
+	static int activation_forward(cattl3_ctx* c, int kind, S alpha, std::int64_t rows, std::int64_t vol, const S* x, S* y) { \
+		return cattl3_activation_forward_##SUF(c, kind, alpha, rows, vol, x, y); } \
+	static int activation_backward(cattl3_ctx* c, int kind, S alpha, std::int64_t rows, std::int64_t vol, const S* x, const S* y, const S* dy, S* dx) { \
+		return cattl3_activation_backward_##SUF(c, kind, alpha, rows, vol, x, y, dy, dx); } \
+	static int pool_forward(cattl3_ctx* c, int kind, const cattl3_pool_geom* g, const S* x, S* y, std::uint8_t* arg) { \
+		return cattl3_pool_forward_##SUF(c, kind, g, x, y, arg); } \
+	static int pool_backward(cattl3_ctx* c, int kind, const cattl3_pool_geom* g, const S* dy, const std::uint8_t* arg, S* dx) { \
+		return cattl3_pool_backward_##SUF(c, kind, g, dy, arg, dx); } \
+	static int batchnorm_forward(cattl3_ctx* c, int pc, std::int32_t n, std::int32_t h, std::int32_t w, std::int32_t ch, int training, int init, S decay, S eps, const S* x, const S* gamma, const S* beta, S* rm, S* rs, S* sm, S* ss, S* y) { \
+		return cattl3_batchnorm_forward_##SUF(c, pc, n, h, w, ch, training, init, decay, eps, x, gamma, beta, rm, rs, sm, ss, y); } \
+	static int batchnorm_backward(cattl3_ctx* c, int pc, std::int32_t n, std::int32_t h, std::int32_t w, std::int32_t ch, const S* x, const S* gamma, const S* sm, const S* ss, const S* dy, S* dg, S* db, S* dx) { \
+		return cattl3_batchnorm_backward_##SUF(c, pc, n, h, w, ch, x, gamma, sm, ss, dy, dg, db, dx); } \
+	static int optimizer_step(cattl3_ctx* c, const cattl3_opt_step* st, std::int64_t count, S* p, S* g, S* s1, S* s2, S* s3) { \
+		return cattl3_optimizer_step_##SUF(c, st, count, p, g, s1, s2, s3); } \
+	static int add_inplace(cattl3_ctx* c, std::int64_t count, S* y, const S* x) { \
+		return cattl3_add_inplace_##SUF(c, count, y, x); } \
+	static int scale(cattl3_ctx* c, std::int64_t count, S alpha, const S* x, S* y) { \
+		return cattl3_scale_##SUF(c, count, alpha, x, y); } \
+	static int axpy(cattl3_ctx* c, std::int64_t count, S alpha, const S* x, S* y) { \
+		return cattl3_axpy_##SUF(c, count, alpha, x, y); } \
+};
+
+CATTLE_B200_API(float, f32)
+CATTLE_B200_API(double, f64)
+#undef CATTLE_B200_API
+
+/**
+ * An owning array of `count` Scalars in the HBM of the context's device.  Copying is a deep
+ * device-to-device copy (layers are cloned with their caches, e.g.
+ * C-ATTL3/layer/kernel/DenseKernelLayer.hpp:78-82); moving transfers ownership.
+ */
+template<typename Scalar>
+class DeviceBuffer {
+public:
+	inline DeviceBuffer() :
+			ptr(nullptr),
+			count(0) { }
+	inline explicit DeviceBuffer(std::size_t count, bool zero = false) :
+			ptr(nullptr),
+			count(count) {
+		if (count == 0)
+			return;
+		Context& c = Context::get();
+		Context::Lock l = c.lock();
+		void* p = nullptr;
+		CATTLE_B200_CHECK(cattl3_malloc(c.handle(), &p, count * sizeof(Scalar)));
+		ptr = static_cast<Scalar*>(p);
+		if (zero)
+			CATTLE_B200_CHECK(cattl3_memset(c.handle(), ptr, 0, count * sizeof(Scalar)));
+	}
+	inline DeviceBuffer(const DeviceBuffer<Scalar>& other) :
+			DeviceBuffer(other.count) {
+		if (count > 0) {
+			Context& c = Context::get();
+			Context::Lock l = c.lock();
+			CATTLE_B200_CHECK(cattl3_memcpy_d2d(c.handle(), ptr, other.ptr, count * sizeof(Scalar)));
+		}
+	}
+	inline DeviceBuffer(DeviceBuffer<Scalar>&& other) noexcept :
+			ptr(other.ptr),
+			count(other.count) {
+		other.ptr = nullptr;
+		other.count = 0;
+	}
+	inline ~DeviceBuffer() {
+		release();
+	}
+	inline DeviceBuffer<Scalar>& operator=(DeviceBuffer<Scalar> other) noexcept {
+		std::swap(ptr, other.ptr);
+		std::swap(count, other.count);
+		return *this;
+	}
+	inline Scalar* data() {
+		return ptr;
+	}
+	inline const Scalar* data() const {
+		return ptr;
+	}
+	inline std::size_t size() const {
+		return count;
+	}
+	inline bool empty() const {
+		return count == 0;
+	}
+	inline void zero() {
+		if (count == 0)
+			return;
+		Context& c = Context::get();
+		Context::Lock l = c.lock();
+		CATTLE_B200_CHECK(cattl3_memset(c.handle(), ptr, 0, count * sizeof(Scalar)));
+	}
+	/** Host -> device, `n` elements into [offset, offset + n). */
+	inline void upload(const Scalar* host, std::size_t n, std::size_t offset = 0) {
+		if (n == 0)
+			return;
+		if (offset + n > count)
+			throw Error(CATTL3_ERR_INVALID, "DeviceBuffer::upload out of range");
+		Context& c = Context::get();
+		Context::Lock l = c.lock();
+		CATTLE_B200_CHECK(cattl3_memcpy_h2d(c.handle(), ptr + offset, host, n * sizeof(Scalar)));
+	}
+	/** Device -> host (synchronises the stream). */
+	inline void download(Scalar* host, std::size_t n, std::size_t offset = 0) const {
+		if (n == 0)
+			return;
+		if (offset + n > count)
+			throw Error(CATTL3_ERR_INVALID, "DeviceBuffer::download out of range");
+		Context& c = Context::get();
+		Context::Lock l = c.lock();
+		CATTLE_B200_CHECK(cattl3_memcpy_d2h(c.handle(), host, ptr + offset, n * sizeof(Scalar)));
+	}
+private:
+	inline void release() {
+		if (ptr) {
+			Context& c = Context::get();
+			Context::Lock l = c.lock();
+			cattl3_free(c.handle(), ptr);  // destructors must not throw
+			ptr = nullptr;
+			count = 0;
+		}
+	}
+	Scalar* ptr;
+	std::size_t count;
+};
+
+} /* namespace b200 */
+} /* namespace cattle */
+
+#endif /* C_ATTL3_B200_RUNTIME_H_ */

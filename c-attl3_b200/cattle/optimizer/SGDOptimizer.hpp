@@ -1,0 +1,305 @@
+/*
+ * optimizer/SGDOptimizer.hpp -- B200 replacement of the reference's mini-batch loop
+ * (C-ATTL3/optimizer/SGDOptimizer.hpp:21-128): same class template, same constructor, same protected
+ * virtuals (_fit, _update_params), so user-defined optimizers derived from it keep working; defines the
+ * reference header's include guard.
+ *
+ * What the loop does per mini-batch is what the reference does (:44-71) -- propagate, loss, back-propagate
+ * the loss gradient divided by the NOMINAL batch size, regularise, update, reset the gradients, with a
+ * time step that keeps counting across epochs and is only reset by fit() (:28-32,66-67).  What changes:
+ *
+ *  - the network runs on the device; parameter values, gradients and optimizer state never leave HBM
+ *    (parameters/B200Parameters.hpp), and a derived optimizer's whole update rule is ONE fused kernel per
+ *    parameter array (fused_step(): update + gradient reset, cattl3_optimizer_step in
+ *    include/cattl3_b200.h) instead of a chain of whole-matrix Eigen expressions
+ *    (e.g. C-ATTL3/optimizer/NadamOptimizer.hpp:44-63);
+ *  - data parallelism (absent from the reference): with a b200::Communicator of world size G > 1, one
+ *    process per GPU, every rank draws the same mini-batch from its (identical, deterministic) provider,
+ *    keeps rows [r*B/G, (r+1)*B/G), and the parameter gradients are sum-all-reduced over NVLink before
+ *    the update.  Because the loss gradient is divided by the nominal *global* batch size, the reduced
+ *    gradient is exactly the single-process gradient, and every rank applies the identical update.
+ */
+#ifndef C_ATTL3_OPTIMIZER_SGDOPTIMIZER_H_
+#define C_ATTL3_OPTIMIZER_SGDOPTIMIZER_H_
+
+#include <array>
+#include <cassert>
+#include <iomanip>
+#include <iostream>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "core/Optimizer.hpp"
+#include "parameters/B200Parameters.hpp"
+#include "b200/Communicator.hpp"
+#include "b200/Runtime.hpp"
+
+namespace cattle {
+
+template<typename Scalar, std::size_t Rank, bool Sequential>
+class SGDOptimizer : public Optimizer<Scalar,Rank,Sequential> {
+	typedef Optimizer<Scalar,Rank,Sequential> Base;
+public:
+	/**
+	 * @param loss The loss function to minimise.
+	 * @param batch_size The nominal (global) mini-batch size.
+	 */
+	inline SGDOptimizer(LossSharedPtr<Scalar,Rank,Sequential> loss, std::size_t batch_size) :
+			Base::Optimizer(loss),
+			batch_size(batch_size),
+			timestep(0),
+			target_net_ptr(nullptr) {
+		assert(batch_size > 0);
+	}
+	virtual ~SGDOptimizer() = default;
+	inline void fit(typename Base::Net& net) {
+		timestep = 0;
+		target_net_ptr = &net;
+		device_states.clear();
+		host_states.clear();
+		_fit(net.get_all_unique_params());
+	}
+protected:
+	inline Scalar _train(typename Base::Net& net, typename Base::Provider& training_prov, std::size_t epoch,
+			bool verbose) {
+		assert(target_net_ptr == &net);
+		b200::Communicator& comm = b200::Communicator::get();
+		double obj_loss = 0, reg_loss = 0;
+		std::size_t instances = 0, updates = 0;
+		std::vector<Parameters<Scalar>*> params_vec = net.get_all_unique_params();
+		while (training_prov.has_more()) {
+			DataPair<Scalar,Rank,Sequential> data_pair = training_prov.get_data(batch_size);
+			instances += data_pair.first.dimension(0);
+			if (comm.world_size() > 1)
+				data_pair = shard(std::move(data_pair), comm);
+			if (data_pair.first.dimension(0) > 0) {
+				typename Base::Data out = net.propagate(std::move(data_pair.first), true);
+				obj_loss += Base::loss->function(out, data_pair.second).sum();
+				// dividing by the nominal batch size decouples the learning rate from the batch size and
+				// makes the shard gradients add up to the full-batch gradient
+				net.backpropagate(Base::loss->d_function(std::move(out), std::move(data_pair.second)) /
+						(Scalar) batch_size);
+			}
+			if (comm.world_size() > 1)
+				all_reduce_gradients(params_vec, comm);
+			for (Parameters<Scalar>* params_ptr : params_vec) {
+				if (!params_ptr->are_optimizable() || params_ptr->are_frozen())
+					continue;
+				reg_loss += params_ptr->get_regularization_penalty();
+				params_ptr->regularize();
+			}
+			_update_params(params_vec, epoch - 1, timestep);
+			++updates;
+			++timestep;
+			for (Parameters<Scalar>* params_ptr : params_vec)
+				params_ptr->reset_grad();  // a no-op where the fused step already cleared the gradient
+		}
+		if (comm.world_size() > 1)
+			obj_loss = comm.all_reduce_sum(obj_loss);
+		const Scalar mean_obj_loss = (Scalar) (obj_loss / instances);
+		const Scalar mean_reg_loss = (Scalar) (reg_loss / updates);
+		if (verbose && comm.rank() == 0) {
+			std::cout << std::left << std::setw(20) << "\ttraining obj loss: " << std::right <<
+					std::to_string(mean_obj_loss) << std::endl;
+			std::cout << std::left << std::setw(20) << "\ttraining reg loss: " << std::right <<
+					std::to_string(mean_reg_loss) << std::endl;
+		}
+		return mean_obj_loss + mean_reg_loss;
+	}
+	inline Scalar _test(typename Base::Net& net, typename Base::Provider& test_prov, std::size_t epoch,
+			bool verbose) {
+		assert(target_net_ptr == &net);
+		double obj_loss = 0;
+		std::size_t instances = 0;
+		while (test_prov.has_more()) {
+			DataPair<Scalar,Rank,Sequential> data_pair = test_prov.get_data(batch_size);
+			instances += data_pair.first.dimension(0);
+			obj_loss += Base::loss->function(net.infer(std::move(data_pair.first)),
+					std::move(data_pair.second)).sum();
+		}
+		const Scalar mean_obj_loss = (Scalar) (obj_loss / instances);
+		Scalar reg_loss = 0;
+		for (Parameters<Scalar>* params_ptr : net.get_all_unique_params()) {
+			if (params_ptr->are_optimizable() && !params_ptr->are_frozen())
+				reg_loss += params_ptr->get_regularization_penalty();
+		}
+		if (verbose && b200::Communicator::get().rank() == 0) {
+			std::cout << std::left << std::setw(20) << "\ttest obj loss: " << std::right <<
+					std::to_string(mean_obj_loss) << std::endl;
+			std::cout << std::left << std::setw(20) << "\ttest reg loss: " << std::right <<
+					std::to_string(reg_loss) << std::endl;
+		}
+		return mean_obj_loss + reg_loss;
+	}
+	/**
+	 * It fits the optimizer to the parameters of the network (called by fit()).
+	 */
+	virtual void _fit(const std::vector<Parameters<Scalar>*>& params_vec) = 0;
+	/**
+	 * It updates the optimizable, non-frozen parameters using their accumulated gradients.
+	 *
+	 * @param epoch The index of the epoch, starting from 0.
+	 * @param timestep The index of the update since fit(), starting from 0.
+	 */
+	virtual void _update_params(const std::vector<Parameters<Scalar>*>& params_vec, std::size_t epoch,
+			std::size_t timestep) = 0;
+	/**
+	 * One fused device kernel per parameter array: the update rule `step.kind` with the scalars in
+	 * `step`, followed by the gradient reset.  Optimizer state (up to three arrays per parameter
+	 * array, zero-initialised, discarded by fit()) lives in HBM.  Views into one shared array that are
+	 * adjacent (BatchNormLayer's per-channel gamma / beta) are updated by a single launch.  Parameters
+	 * that are not device resident (reference layers mixed into the network) are staged through the
+	 * same kernel, so there is exactly one implementation of every update rule.
+	 */
+	inline void fused_step(const std::vector<Parameters<Scalar>*>& params_vec, cattl3_opt_step step) {
+		step.reset_grad = 1;
+		step.l2_lambda = 0;  // Parameters::regularize() has already added the penalty's derivative
+		struct Run { B200Parameters<Scalar>* first; std::size_t count; std::vector<B200Parameters<Scalar>*> members; };
+		std::vector<Run> runs;
+		b200::Context& c = b200::Context::get();
+		for (Parameters<Scalar>* params_ptr : params_vec) {
+			if (!params_ptr->are_optimizable() || params_ptr->are_frozen())
+				continue;
+			B200Parameters<Scalar>* dev = dynamic_cast<B200Parameters<Scalar>*>(params_ptr);
+			if (!dev) {
+				staged_step(*params_ptr, step);
+				continue;
+			}
+			bool merged = false;
+			for (Run& run : runs) {
+				if (run.first->device_values() + run.count == dev->device_values() &&
+						run.first->device_grad() + run.count == dev->device_grad() &&
+						!dev->has_value_constraints() && !run.first->has_value_constraints()) {
+					run.count += dev->count();
+					run.members.push_back(dev);
+					merged = true;
+					break;
+				}
+			}
+			if (!merged)
+				runs.push_back(Run{ dev, dev->count(), { dev } });
+		}
+		for (Run& run : runs) {
+			StateArrays& state = device_states[run.first->device_values()];
+			for (int s = 0; s < states_needed(step.kind); ++s) {
+				if (state[s].size() < run.count) {
+					if (!state[s].empty())
+						throw b200::Error(CATTL3_ERR_INVALID, "optimizer state does not match the parameters; call fit()");
+					state[s] = b200::DeviceBuffer<Scalar>(run.count, true);
+				}
+			}
+			{
+				b200::Context::Lock l = c.lock();
+				CATTLE_B200_CHECK(b200::Api<Scalar>::optimizer_step(c.handle(), &step, (std::int64_t) run.count,
+						run.first->device_values(), run.first->device_grad(), state[0].data(), state[1].data(),
+						state[2].data()));
+			}
+			for (B200Parameters<Scalar>* member : run.members) {
+				member->values_written_on_device();
+				member->grad_zeroed_on_device();
+			}
+		}
+	}
+	/** Fills the hyper-parameter part of a step descriptor (meaning of a / b per kind: cattl3_b200.h). */
+	inline static cattl3_opt_step make_step(int kind, Scalar lr, Scalar a, Scalar b, Scalar eps) {
+		cattl3_opt_step step;
+		step.kind = kind;
+		step.reset_grad = 1;
+		step.lr = lr; step.a = a; step.b = b; step.eps = eps;
+		step.lr_epoch = lr; step.c1 = 1; step.c1n = 1; step.c2 = 1;
+		step.l2_lambda = 0;
+		return step;
+	}
+	const std::size_t batch_size;
+private:
+	typedef std::array<b200::DeviceBuffer<Scalar>,3> StateArrays;
+	inline static int states_needed(int kind) {
+		if (kind == CATTL3_OPT_VANILLA_SGD)
+			return 0;
+		if (kind == CATTL3_OPT_AMSGRAD)
+			return 3;
+		return kind <= CATTL3_OPT_RMSPROP ? 1 : 2;
+	}
+	/** The same kernel for host-resident parameters: upload, step, download. */
+	inline void staged_step(Parameters<Scalar>& params, cattl3_opt_step step) {
+		const std::size_t count = params.get_rows() * params.get_cols();
+		b200::DeviceBuffer<Scalar> values(count), grad(count);
+		values.upload(params.get_values().data(), count);
+		grad.upload(params.get_grad().data(), count);
+		StateArrays& state = host_states[&params];
+		for (int s = 0; s < states_needed(step.kind); ++s) {
+			if (state[s].size() != count)
+				state[s] = b200::DeviceBuffer<Scalar>(count, true);
+		}
+		step.reset_grad = 0;
+		b200::Context& c = b200::Context::get();
+		{
+			b200::Context::Lock l = c.lock();
+			CATTLE_B200_CHECK(b200::Api<Scalar>::optimizer_step(c.handle(), &step, (std::int64_t) count,
+					values.data(), grad.data(), state[0].data(), state[1].data(), state[2].data()));
+		}
+		Matrix<Scalar> updated(params.get_rows(), params.get_cols());
+		values.download(updated.data(), count);
+		params.set_values(std::move(updated));
+	}
+	/** Rows [r*n/G, (r+1)*n/G) of the mini-batch (the last batch of an epoch may be short). */
+	inline static DataPair<Scalar,Rank,Sequential> shard(DataPair<Scalar,Rank,Sequential> pair,
+			const b200::Communicator& comm) {
+		const std::size_t n = pair.first.dimension(0);
+		const std::size_t lo = n * comm.rank() / comm.world_size();
+		const std::size_t hi = n * (comm.rank() + 1) / comm.world_size();
+		return std::make_pair(rows_of(pair.first, lo, hi), rows_of(pair.second, lo, hi));
+	}
+	inline static typename Base::Data rows_of(const typename Base::Data& data, std::size_t lo, std::size_t hi) {
+		typename Base::Data::Dimensions offsets, extents = data.dimensions();
+		for (std::size_t i = 0; i < (std::size_t) data.NumDimensions; ++i)
+			offsets[i] = 0;
+		offsets[0] = lo;
+		extents[0] = hi - lo;
+		if (hi == lo)
+			return typename Base::Data();
+		return data.slice(offsets, extents);
+	}
+	/** Sum over ranks of every optimizable parameter gradient, in place, on the device. */
+	inline static void all_reduce_gradients(const std::vector<Parameters<Scalar>*>& params_vec,
+			b200::Communicator& comm) {
+		std::vector<B200Parameters<Scalar>*> reduced;
+		Scalar* run_begin = nullptr;
+		std::size_t run_count = 0;
+		comm.group_start();
+		for (Parameters<Scalar>* params_ptr : params_vec) {
+			if (!params_ptr->are_optimizable())
+				continue;
+			B200Parameters<Scalar>* dev = dynamic_cast<B200Parameters<Scalar>*>(params_ptr);
+			if (!dev)
+				throw b200::Error(CATTL3_ERR_UNSUPPORTED, "data-parallel training needs device-resident parameters");
+			// adjacent views of one array (BatchNormLayer's per-channel parameters) travel as one message
+			if (run_count > 0 && run_begin + run_count == dev->device_grad()) {
+				run_count += dev->count();
+			} else {
+				if (run_count > 0)
+					comm.all_reduce_sum(run_begin, run_count);
+				run_begin = dev->device_grad();
+				run_count = dev->count();
+			}
+			reduced.push_back(dev);
+		}
+		if (run_count > 0)
+			comm.all_reduce_sum(run_begin, run_count);
+		comm.group_end();
+		for (B200Parameters<Scalar>* dev : reduced)
+			dev->grad_written_on_device();
+	}
+	std::size_t timestep;
+	const typename Base::Net* target_net_ptr;
+	// optimizer state per device parameter array (keyed by the device address of its first value) and
+	// per host-resident Parameters object
+	std::map<const Scalar*,StateArrays> device_states;
+	std::map<const Parameters<Scalar>*,StateArrays> host_states;
+};
+
+} /* namespace cattle */
+
+#endif /* C_ATTL3_OPTIMIZER_SGDOPTIMIZER_H_ */

@@ -223,6 +223,14 @@ int cattl3_ctx_create(cattl3_ctx** out, int device, void* cuda_stream) {
 		set_error("device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
 		return CATTL3_ERR_UNSUPPORTED;
 	}
+	{
+		// keep freed blocks cached in the stream-ordered pool instead of returning them to the driver
+		cudaMemPool_t pool;
+		if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+			uint64_t keep = UINT64_MAX;
+			cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+		}
+	}
 	cattl3_ctx* ctx = new cattl3_ctx();
 	ctx->device = device;
 	ctx->sm_count = prop.multiProcessorCount;
@@ -275,15 +283,15 @@ void* cattl3_ctx_stream(const cattl3_ctx* ctx) { return ctx ? (void*) ctx->strea
 int cattl3_malloc(cattl3_ctx* ctx, void** p, size_t bytes) {
 	CATTL3_CHECK(check_ctx(ctx));
 	CATTL3_REQUIRE(p, "malloc: null out pointer");
-	CATTL3_CUDA(cudaMalloc(p, bytes ? bytes : 1));
+	// stream-ordered allocation from the device's default pool (kept warm: see ctx_create), so a
+	// layer's activation buffers are recycled without a cudaMalloc / cudaFree synchronisation per call
+	CATTL3_CUDA(cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream));
 	return CATTL3_OK;
 }
 int cattl3_free(cattl3_ctx* ctx, void* p) {
 	CATTL3_CHECK(check_ctx(ctx));
-	if (p) {
-		CATTL3_CUDA(cudaStreamSynchronize(ctx->stream));
-		CATTL3_CUDA(cudaFree(p));
-	}
+	if (p)
+		CATTL3_CUDA(cudaFreeAsync(p, ctx->stream));
 	return CATTL3_OK;
 }
 int cattl3_memset(cattl3_ctx* ctx, void* p, int value, size_t bytes) {

@@ -1,0 +1,207 @@
+// comm.cu -- gradient all-reduce for data-parallel training: NCCL over NVLink 5 / NVSwitch, one
+// process per GPU.  The reference has no distributed training at all; this is the
+// exchange step of the data-parallel batch loop (cattle/optimizer/SGDOptimizer.hpp).
+//
+// libnccl is opened at run time (dlopen) so that single-GPU users, and the CPU-side symbol checks,
+// do not need it.  Rendezvous needs no MPI: rank 0 publishes the ncclUniqueId in a file that the
+// other ranks of the same host poll (one host, 1/2/4/8 GPUs -- BASELINE.json).
+#include <dlfcn.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <string>
+
+#include "common.cuh"
+
+namespace {
+
+typedef struct { char internal[128]; } NcclUniqueId;
+typedef void* NcclComm;
+enum { NCCL_SUCCESS = 0 };
+enum { NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+
+struct NcclApi {
+	void* lib = nullptr;
+	int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+	int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int) = nullptr;
+	int (*CommDestroy)(NcclComm) = nullptr;
+	int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+	int (*GroupStart)() = nullptr;
+	int (*GroupEnd)() = nullptr;
+	const char* (*GetErrorString)(int) = nullptr;
+};
+
+NcclApi* nccl() {
+	static NcclApi api;
+	static bool tried = false;
+	if (!tried) {
+		tried = true;
+		const char* names[] = { getenv("CATTL3_NCCL_LIB"), "libnccl.so.2", "libnccl.so" };
+		for (const char* n : names) {
+			if (n && (api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL)))
+				break;
+		}
+		if (api.lib) {
+			api.GetUniqueId = (int (*)(NcclUniqueId*)) dlsym(api.lib, "ncclGetUniqueId");
+			api.CommInitRank = (int (*)(NcclComm*, int, NcclUniqueId, int)) dlsym(api.lib, "ncclCommInitRank");
+			api.CommDestroy = (int (*)(NcclComm)) dlsym(api.lib, "ncclCommDestroy");
+			api.AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t)) dlsym(api.lib, "ncclAllReduce");
+			api.GroupStart = (int (*)()) dlsym(api.lib, "ncclGroupStart");
+			api.GroupEnd = (int (*)()) dlsym(api.lib, "ncclGroupEnd");
+			api.GetErrorString = (const char* (*)(int)) dlsym(api.lib, "ncclGetErrorString");
+			if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.GroupStart ||
+					!api.GroupEnd) {
+				dlclose(api.lib);
+				api.lib = nullptr;
+			}
+		}
+	}
+	return api.lib ? &api : nullptr;
+}
+
+int nccl_fail(int rc, const char* what) {
+	NcclApi* n = nccl();
+	cattl3::set_error("NCCL error %d (%s) in %s", rc, n && n->GetErrorString ? n->GetErrorString(rc) : "?", what);
+	return CATTL3_ERR_CUDA;
+}
+
+#define CATTL3_NCCL(call, what) do { int rc__ = (call); if (rc__ != NCCL_SUCCESS) return nccl_fail(rc__, what); } while (0)
+
+} // namespace
+
+struct cattl3_comm {
+	cattl3_ctx* ctx = nullptr;
+	NcclComm comm = nullptr;
+	int world = 1, rank = 0;
+};
+
+using namespace cattl3;
+
+extern "C" {
+
+int cattl3_comm_unique_id(void* id128) {
+	CATTL3_REQUIRE(id128, "comm_unique_id: null buffer");
+	NcclApi* n = nccl();
+	if (!n) {
+		set_error("libnccl.so.2 could not be loaded (set CATTL3_NCCL_LIB)");
+		return CATTL3_ERR_UNSUPPORTED;
+	}
+	NcclUniqueId id;
+	CATTL3_NCCL(n->GetUniqueId(&id), "ncclGetUniqueId");
+	memcpy(id128, &id, sizeof(id));
+	return CATTL3_OK;
+}
+
+int cattl3_comm_create(cattl3_comm** out, cattl3_ctx* ctx, int world_size, int rank, const void* id128) {
+	CATTL3_REQUIRE(out, "comm_create: null out pointer");
+	*out = nullptr;
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(world_size >= 1 && rank >= 0 && rank < world_size, "comm_create: rank %d outside world of %d", rank, world_size);
+	cattl3_comm* c = new cattl3_comm();
+	c->ctx = ctx; c->world = world_size; c->rank = rank;
+	if (world_size > 1) {
+		NcclApi* n = nccl();
+		if (!n) {
+			delete c;
+			set_error("libnccl.so.2 could not be loaded (set CATTL3_NCCL_LIB)");
+			return CATTL3_ERR_UNSUPPORTED;
+		}
+		if (!id128) {
+			delete c;
+			set_error("comm_create: a unique id is required for world_size > 1");
+			return CATTL3_ERR_INVALID;
+		}
+		NcclUniqueId id;
+		memcpy(&id, id128, sizeof(id));
+		int rc = n->CommInitRank(&c->comm, world_size, id, rank);
+		if (rc != NCCL_SUCCESS) {
+			delete c;
+			return nccl_fail(rc, "ncclCommInitRank");
+		}
+	}
+	*out = c;
+	return CATTL3_OK;
+}
+
+// WORLD_SIZE / RANK from the environment (the torchrun convention); the unique id travels through the
+// file CATTL3_COMM_ID_FILE (default /tmp/cattl3_nccl_id.<MASTER_PORT or 0>), written by rank 0 with an
+// atomic rename and removed by rank 0 when the communicator is destroyed.
+int cattl3_comm_create_from_env(cattl3_comm** out, cattl3_ctx* ctx) {
+	CATTL3_REQUIRE(out, "comm_create_from_env: null out pointer");
+	const char* ws = getenv("WORLD_SIZE");
+	const char* rk = getenv("RANK");
+	const int world = ws ? atoi(ws) : 1, rank = rk ? atoi(rk) : 0;
+	if (world <= 1)
+		return cattl3_comm_create(out, ctx, 1, 0, nullptr);
+	std::string path;
+	if (const char* p = getenv("CATTL3_COMM_ID_FILE")) {
+		path = p;
+	} else {
+		const char* port = getenv("MASTER_PORT");
+		path = std::string("/tmp/cattl3_nccl_id.") + (port ? port : "0");
+	}
+	NcclUniqueId id;
+	if (rank == 0) {
+		CATTL3_CHECK(cattl3_comm_unique_id(&id));
+		const std::string tmp = path + ".tmp";
+		FILE* f = fopen(tmp.c_str(), "wb");
+		CATTL3_REQUIRE(f, "cannot write %s", tmp.c_str());
+		fwrite(&id, sizeof(id), 1, f);
+		fclose(f);
+		CATTL3_REQUIRE(rename(tmp.c_str(), path.c_str()) == 0, "cannot publish %s", path.c_str());
+	} else {
+		bool got = false;
+		for (int i = 0; i < 6000 && !got; ++i) {  // up to 60 s
+			FILE* f = fopen(path.c_str(), "rb");
+			if (f) {
+				got = fread(&id, sizeof(id), 1, f) == 1;
+				fclose(f);
+			}
+			if (!got) usleep(10000);
+		}
+		CATTL3_REQUIRE(got, "timed out waiting for the NCCL id file %s", path.c_str());
+	}
+	int rc = cattl3_comm_create(out, ctx, world, rank, &id);
+	if (rank == 0 && rc == CATTL3_OK)
+		unlink(path.c_str());  // every rank has joined once ncclCommInitRank returns
+	return rc;
+}
+
+int cattl3_comm_destroy(cattl3_comm* c) {
+	if (!c) return CATTL3_OK;
+	if (c->comm) {
+		cudaSetDevice(c->ctx->device);
+		cudaStreamSynchronize(c->ctx->stream);
+		if (NcclApi* n = nccl()) n->CommDestroy(c->comm);
+	}
+	delete c;
+	return CATTL3_OK;
+}
+
+int cattl3_comm_world_size(const cattl3_comm* c) { return c ? c->world : 1; }
+int cattl3_comm_rank(const cattl3_comm* c) { return c ? c->rank : 0; }
+
+int cattl3_comm_group_start(cattl3_comm* c) {
+	CATTL3_REQUIRE(c, "null communicator");
+	if (c->world > 1) CATTL3_NCCL(nccl()->GroupStart(), "ncclGroupStart");
+	return CATTL3_OK;
+}
+int cattl3_comm_group_end(cattl3_comm* c) {
+	CATTL3_REQUIRE(c, "null communicator");
+	if (c->world > 1) CATTL3_NCCL(nccl()->GroupEnd(), "ncclGroupEnd");
+	return CATTL3_OK;
+}
+
+static int allreduce(cattl3_comm* c, void* buf, int64_t count, int dtype) {
+	CATTL3_REQUIRE(c && buf && count > 0, "comm_allreduce: bad arguments");
+	CATTL3_CHECK(check_ctx(c->ctx));
+	if (c->world == 1)
+		return CATTL3_OK;
+	CATTL3_NCCL(nccl()->AllReduce(buf, buf, (size_t) count, dtype, NCCL_SUM, c->comm, c->ctx->stream), "ncclAllReduce");
+	return CATTL3_OK;
+}
+int cattl3_comm_allreduce_sum_f32(cattl3_comm* c, float* buf, int64_t count) { return allreduce(c, buf, count, NCCL_FLOAT32); }
+int cattl3_comm_allreduce_sum_f64(cattl3_comm* c, double* buf, int64_t count) { return allreduce(c, buf, count, NCCL_FLOAT64); }
+
+}

@@ -593,6 +593,19 @@ __global__ void __launch_bounds__(256) scale_kernel(long long count, S alpha, co
 }
 
 template<typename S>
+__global__ void __launch_bounds__(256) axpy_kernel(long long count, S alpha, const S* __restrict__ x, S* __restrict__ y) {
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < count; i += (long long) gridDim.x * 256) y[i] = fma(alpha, x[i], y[i]);
+}
+template<typename S>
+int axpy(cattl3_ctx* ctx, int64_t count, S alpha, const S* x, S* y) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(count > 0 && y && x, "axpy: bad arguments");
+	axpy_kernel<S><<<ew_grid(ctx, count, 256), 256, 0, ctx->stream>>>(count, alpha, x, y);
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+
+template<typename S>
 int add_inplace(cattl3_ctx* ctx, int64_t count, S* y, const S* x) {
 	CATTL3_CHECK(check_ctx(ctx));
 	CATTL3_REQUIRE(count > 0 && y && x, "add_inplace: bad arguments");
@@ -651,5 +664,7 @@ int cattl3_add_inplace_f32(cattl3_ctx* c, int64_t count, float* y, const float* 
 int cattl3_add_inplace_f64(cattl3_ctx* c, int64_t count, double* y, const double* x) { return add_inplace<double>(c, count, y, x); }
 int cattl3_scale_f32(cattl3_ctx* c, int64_t count, float alpha, const float* x, float* y) { return scale<float>(c, count, alpha, x, y); }
 int cattl3_scale_f64(cattl3_ctx* c, int64_t count, double alpha, const double* x, double* y) { return scale<double>(c, count, alpha, x, y); }
+int cattl3_axpy_f32(cattl3_ctx* c, int64_t count, float alpha, const float* x, float* y) { return axpy<float>(c, count, alpha, x, y); }
+int cattl3_axpy_f64(cattl3_ctx* c, int64_t count, double alpha, const double* x, double* y) { return axpy<double>(c, count, alpha, x, y); }
 
 }

@@ -146,6 +146,8 @@ const char* cattl3_ctx_last_path(const cattl3_ctx* ctx);
 void* cattl3_ctx_stream(const cattl3_ctx* ctx);
 
 /* ---- memory helpers (so g++-only hosts need no CUDA headers) ------------------------------ */
+/* Stream-ordered (cudaMallocAsync / cudaFreeAsync on the context's stream, pool kept warm): neither
+ * call synchronises, and a freed block may be reused by later work on the same stream. */
 int cattl3_malloc(cattl3_ctx* ctx, void** dev_ptr, size_t bytes);
 int cattl3_free(cattl3_ctx* ctx, void* dev_ptr);
 int cattl3_memset(cattl3_ctx* ctx, void* dev_ptr, int value, size_t bytes);
@@ -242,6 +244,32 @@ int cattl3_add_inplace_f64(cattl3_ctx*, int64_t count, double* y, const double* 
 /* y = alpha * x (the 1/batch_size scaling of the loss gradient, SGDOptimizer.hpp:55-56). */
 int cattl3_scale_f32(cattl3_ctx*, int64_t count, float alpha, const float* x, float* y);
 int cattl3_scale_f64(cattl3_ctx*, int64_t count, double alpha, const double* x, double* y);
+/* y += alpha * x (Parameters::regularize() with an L2 penalty: grad += lambda * values,
+ * C-ATTL3/parameter_regularization/L2ParameterRegularization.hpp:31-33). */
+int cattl3_axpy_f32(cattl3_ctx*, int64_t count, float alpha, const float* x, float* y);
+int cattl3_axpy_f64(cattl3_ctx*, int64_t count, double alpha, const double* x, double* y);
+
+/* ---- data-parallel exchange (no counterpart in the reference, which is single-process: SURVEY.md F6) --- */
+/*
+ * One communicator per process (one process per GPU).  The only exchange of the hot path is the sum
+ * all-reduce of the parameter gradients between ConvKernelLayer::pass_back and the optimizer step
+ * (between C-ATTL3/optimizer/SGDOptimizer.hpp:56 and :59), done in place with NCCL on the context's
+ * stream.  world_size 1 makes every call a no-op, so single-GPU code needs no NCCL library.
+ */
+typedef struct cattl3_comm cattl3_comm;
+/* 128-byte ncclUniqueId for rank 0 to hand to its peers. */
+int cattl3_comm_unique_id(void* id128);
+int cattl3_comm_create(cattl3_comm** out, cattl3_ctx* ctx, int world_size, int rank, const void* id128);
+/* WORLD_SIZE / RANK from the environment (torchrun convention); the id travels through the file
+ * CATTL3_COMM_ID_FILE (default /tmp/cattl3_nccl_id.<MASTER_PORT>). */
+int cattl3_comm_create_from_env(cattl3_comm** out, cattl3_ctx* ctx);
+int cattl3_comm_destroy(cattl3_comm* comm);
+int cattl3_comm_world_size(const cattl3_comm* comm);
+int cattl3_comm_rank(const cattl3_comm* comm);
+int cattl3_comm_group_start(cattl3_comm* comm);
+int cattl3_comm_group_end(cattl3_comm* comm);
+int cattl3_comm_allreduce_sum_f32(cattl3_comm* comm, float* dev_buf, int64_t count);
+int cattl3_comm_allreduce_sum_f64(cattl3_comm* comm, double* dev_buf, int64_t count);
 
 #ifdef __cplusplus
 }

@@ -60,9 +60,12 @@ def F(shape, dtype):
 class Oracle:
     """One of the two libraries (prefix 'orc' or 'ref') behind a numpy API."""
 
-    def __init__(self, prefix):
+    def __init__(self, prefix, path=None):
+        """``path`` overrides the library: tests/cpp builds oracle/ref_shim.cpp a second time against the
+        B200 headers (same ``ref_*`` entry points, product arithmetic) for the drop-in tests."""
         self.prefix = prefix
-        path = ORC_PATH if prefix == "orc" else REF_PATH
+        if path is None:
+            path = ORC_PATH if prefix == "orc" else REF_PATH
         if not os.path.exists(path):
             raise FileNotFoundError(path)
         self.lib = ctypes.CDLL(path)
@@ -148,7 +151,7 @@ class Oracle:
         assert rc == 0, rc
         return dict(y=y, dx=dx, dgamma=dgamma, dbeta=dbeta, run_mean=rm, run_inv_sd=rs, y_infer=yi)
 
-    def optimizer(self, kind, hyper, l2_lambda, p0, grads, steps_per_epoch):
+    def optimizer(self, kind, hyper, l2_lambda, p0, grads, steps_per_epoch, hostparams=False):
         """p0: rows x cols; grads: list of rows x cols arrays (one per step)."""
         dt = p0.dtype
         rows, cols = p0.shape
@@ -156,14 +159,13 @@ class Oracle:
         gcat = np.concatenate([g.ravel(order="F") for g in grads])
         hy = np.asarray(hyper, dtype=dt)
         out = F(p0.shape, dt)
-        rc = self._fn("optimizer", dt)(kind, _ptr(hy), _CT[np.dtype(dt)](l2_lambda), rows, cols, steps,
+        rc = self._fn("optimizer_hostparams" if hostparams else "optimizer", dt)(kind, _ptr(hy), _CT[np.dtype(dt)](l2_lambda), rows, cols, steps,
                                        steps_per_epoch, _ptr(p0), _ptr(gcat), _ptr(out))
         assert rc == 0, rc
         return out
 
     def train_cifar(self, x, obj, batch, epochs, params_in=None, n_params=26968):
         """Reference only: config-1 network, Nadam; returns (params, loss, train_ms)."""
-        assert self.prefix == "ref"
         dt = x.dtype
         total = x.shape[0]
         out = np.zeros(n_params, dt)

@@ -287,14 +287,17 @@ struct Open : public Opt {
 //  7 AdaMax  8 Nadam  9 AMSGrad (same as Adam)
 // Applies `steps` updates of one rows x cols parameter matrix with L2 penalty `l2_lambda` (0 = none)
 // from the raw gradients grads[step]; epoch = step / steps_per_epoch, timestep = step.
-template<typename S>
+// ParamsT: the Parameters implementation the optimizer updates -- StandardParameters (host matrices, the
+// reference's own) or, when this file is compiled against the B200 headers (tests/cpp/Makefile), the
+// device-resident B200Parameters.
+template<typename S, typename ParamsT>
 int opt_impl(int kind, const S* hyper, S l2_lambda, int rows, int cols, int steps, int steps_per_epoch,
 		const S* p0, const S* grads, S* p_out) {
 	typedef LossSharedPtr<S,1,false> LossPtr;
 	LossPtr loss = std::make_shared<SquaredLoss<S,1,false>>();
 	ParamRegSharedPtr<S> reg = l2_lambda > 0 ?
 			std::make_shared<L2ParameterRegularization<S>>(l2_lambda) : nullptr;
-	StandardParameters<S> params(rows, cols, true, nullptr, reg);
+	ParamsT params(rows, cols, true, nullptr, reg);
 	params.init();
 	params.set_values(Eigen::Map<const Matrix<S>>(p0, rows, cols));
 	std::vector<Parameters<S>*> vec({ &params });
@@ -386,7 +389,22 @@ int cifar_impl(int total, int batch, int epochs, const S* x, const S* obj, const
 
 } /* namespace */
 
+#ifdef C_ATTL3_B200_CATTLE_H_
+template<typename S> using DefaultParams = B200Parameters<S>;
+#else
+template<typename S> using DefaultParams = StandardParameters<S>;
+#endif
+
 extern "C" {
+
+/* 1 when this driver was compiled against the B200 headers (c-attl3_b200/cattle), 0 for the reference. */
+int ref_is_b200_build() {
+#ifdef C_ATTL3_B200_CATTLE_H_
+	return 1;
+#else
+	return 0;
+#endif
+}
 
 int ref_num_threads() { return num_of_eval_threads(); }
 void ref_set_num_threads(int n) { set_num_of_eval_threads(n); }
@@ -410,7 +428,10 @@ int ref_batchnorm_##SUF(int per_channel, int n, int h, int w, int c, S decay, S 
 			run_mean, run_inv_sd, y_infer); } \
 int ref_optimizer_##SUF(int kind, const S* hyper, S l2_lambda, int rows, int cols, int steps, \
 		int steps_per_epoch, const S* p0, const S* grads, S* p_out) { \
-	return opt_impl<S>(kind, hyper, l2_lambda, rows, cols, steps, steps_per_epoch, p0, grads, p_out); } \
+	return opt_impl<S,DefaultParams<S>>(kind, hyper, l2_lambda, rows, cols, steps, steps_per_epoch, p0, grads, p_out); } \
+int ref_optimizer_hostparams_##SUF(int kind, const S* hyper, S l2_lambda, int rows, int cols, int steps, \
+		int steps_per_epoch, const S* p0, const S* grads, S* p_out) { \
+	return opt_impl<S,StandardParameters<S>>(kind, hyper, l2_lambda, rows, cols, steps, steps_per_epoch, p0, grads, p_out); } \
 int ref_train_cifar_##SUF(int total, int batch, int epochs, const S* x, const S* obj, const S* params_in, \
 		S* params_out, double* loss_out, double* train_ms) { \
 	return cifar_impl<S>(total, batch, epochs, x, obj, params_in, params_out, loss_out, train_ms); }

@@ -1,0 +1,159 @@
+"""-m gpu: the header-only C++ host side (c-attl3_b200/cattle) as a drop-in for the reference.
+
+tests/cpp/Makefile compiles code written against the reference, UNCHANGED, with the B200 headers first
+on the include path:
+
+* ``libcattle_b200_shim.so`` -- oracle/ref_shim.cpp, the driver that wraps the reference's layers,
+  optimizers and the config-1 training loop for the oracle, now instantiating the B200 classes of the
+  same names.  Its results are compared with the C oracle, with the golden vectors of the unmodified
+  reference and -- where oracle/_ref travelled -- with the reference itself, at the north-star
+  tolerances (1e-4 float, 1e-10 double, norm-relative).
+* ``gradient_test_b200`` -- the reference's own test/gradient_test.cpp (finite-difference gradient
+  checks, double, N=5), "the repo's own gradient_test" of BASELINE.json's north star.
+
+Both binaries are built where /root/reference exists (``__graft_entry__.build()``) and travel to the GPU box.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases as C
+from oracle import binding
+from oracle.binding import Geom
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "tests", "cpp", "_build")
+SHIM = os.path.join(BUILD, "libcattle_b200_shim.so")
+GRADIENT_TEST = os.path.join(BUILD, "gradient_test_b200")
+DTYPES = [np.float32, np.float64]
+
+# the hot-path tests of the reference's gradient_test.cpp and the networks built on them
+GTEST_FILTER = ":".join("GradientTest." + t for t in (
+    "DenseKernelLayer", "ConvKernelLayer", "TransConvKernelLayer", "ActivationLayer", "PoolLayer",
+    "BatchNormLayer", "ResidualNet", "DenseNet", "ParallelNet", "SequentialNet", "LSTMNet"))
+
+
+@pytest.fixture(scope="module")
+def b200():
+    if not os.path.exists(SHIM):
+        pytest.fail("%s missing: run __graft_entry__.build() where /root/reference exists" % SHIM)
+    lib = binding.Oracle("ref", path=SHIM)
+    assert lib.lib.ref_is_b200_build() == 1
+    return lib
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("tr", [False, True])
+def test_kernel_layers_match_oracle(b200, orc, dt, tr):
+    """ConvKernelLayer / TransConvKernelLayer<S,3>::pass_forward / pass_back (host tensors in and out)."""
+    table = C.TCONV_CASES if tr else C.CONV_CASES
+    for name, case in table.items():
+        g, x, w, b, dy = C.conv_inputs(case, dt, 41, tr)
+        r = orc.conv(g, x, w, b, dy, transposed=tr, back_reps=2)
+        a = b200.conv(g, x, w, b, dy, transposed=tr, back_reps=2)
+        for k in ("y", "dx", "dw", "db"):
+            assert C.relerr(a[k], r[k]) < C.TOL[np.dtype(dt)], (name, k, C.relerr(a[k], r[k]))
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_dense_layer_matches_oracle(b200, orc, dt):
+    rng = np.random.default_rng(42)
+    for name, (n, i, o) in C.DENSE_CASES.items():
+        x, w, b, dy = C.rand(rng, (n, i), dt), C.rand(rng, (i, o), dt), C.rand(rng, (1, o), dt), C.rand(rng, (n, o), dt)
+        r = orc.dense(x, w, b, dy, back_reps=2)
+        a = b200.dense(x, w, b, dy, back_reps=2)
+        for k in ("y", "dx", "dw", "db"):
+            assert C.relerr(a[k], r[k]) < C.TOL[np.dtype(dt)], (name, k)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_activation_pool_batchnorm_match_golden(b200, golden, dt):
+    suf = "f32" if dt == np.float32 else "f64"
+    tol = C.TOL[np.dtype(dt)]
+    for name, (kind, alpha) in C.ACT_CASES.items():
+        k = "act/%s/%s/" % (name, suf)
+        x, dy = np.asfortranarray(golden[k + "x"]), np.asfortranarray(golden[k + "dy"])
+        a = b200.activation(kind, alpha, x, dy)
+        assert C.relerr(a["y"], golden[k + "y"]) < tol, name
+        assert C.relerr(a["dx"], golden[k + "dx"]) < tol, name
+    for name, (kind, n, h, w, c, rh, rw, sh, sw) in C.POOL_CASES.items():
+        k = "pool/%s/%s/" % (name, suf)
+        if k + "x" not in golden.files:
+            continue
+        x, dy = np.asfortranarray(golden[k + "x"]), np.asfortranarray(golden[k + "dy"])
+        a = b200.pool(kind, x, rh, rw, sh, sw, dy)
+        if kind == 0:
+            assert np.array_equal(a["y"], golden[k + "y"]), name
+        assert C.relerr(a["y"], golden[k + "y"]) < tol, name
+        assert C.relerr(a["dx"], golden[k + "dx"]) < tol, name
+    for name, (pc, n, h, w, c, steps) in C.BN_CASES.items():
+        k = "bn/%s/%s/" % (name, suf)
+        if k + "x0" not in golden.files:
+            continue
+        xs = [np.asfortranarray(golden[k + "x%d" % s]) for s in range(steps)]
+        a = b200.batchnorm(pc, xs, golden[k + "gamma"], golden[k + "beta"], np.asfortranarray(golden[k + "dy"]))
+        btol = 10 * tol if dt == np.float64 else tol
+        for out in ("y", "dx", "dgamma", "dbeta", "run_mean", "run_inv_sd", "y_infer"):
+            assert C.relerr(a[out], golden[k + out]) < btol, (name, out, C.relerr(a[out], golden[k + out]))
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("hostparams", [False, True])
+def test_optimizers_match_golden(b200, golden, dt, hostparams):
+    """Every SGDOptimizer subclass: device-resident B200Parameters (fused step in place) and host
+    StandardParameters (staged through the same kernel)."""
+    suf = "f32" if dt == np.float32 else "f64"
+    for name, (kind, hy) in C.OPT_CASES.items():
+        for lam in (0.0, 0.01):
+            k = "opt/%s_l2_%g/%s/" % (name, lam, suf)
+            p0, grads = np.asfortranarray(golden[k + "p0"]), [np.asfortranarray(g) for g in golden[k + "grads"]]
+            p = b200.optimizer(kind, hy, lam, p0, grads, 3, hostparams=hostparams)
+            tol = 2e-6 if dt == np.float32 else 1e-12
+            assert C.relerr(p, golden[k + "p"]) < tol, (name, lam, C.relerr(p, golden[k + "p"]))
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_config1_training_matches_reference(b200, golden, dt):
+    """BASELINE.json configs[0]: the cifar ConvNet (Dropout removed) under NadamOptimizer::train through the
+    B200 FeedforwardNeuralNetwork / SGDOptimizer batch loop; parameters after the epoch and the epoch
+    loss against the unmodified reference (golden fixture; and live where oracle/_ref travelled)."""
+    suf = "f32" if dt == np.float32 else "f64"
+    rng = np.random.default_rng(1001)
+    x = C.rand(rng, (8, 32, 32, 3), dt)
+    obj = np.zeros((8, 1, 1, 10), dtype=dt, order="F")
+    for i in range(8):
+        obj[i, 0, 0, i % 10] = 1
+    p0 = np.ascontiguousarray(golden["cifar/%s/p0" % suf])
+    p1, loss, _ = b200.train_cifar(x, obj, 4, 1, params_in=p0)
+    tol = 1e-4 if dt == np.float32 else 1e-9
+    assert C.relerr(p1, golden["cifar/%s/p1" % suf]) < tol, C.relerr(p1, golden["cifar/%s/p1" % suf])
+    assert abs(loss - float(golden["cifar/%s/loss" % suf][0])) < tol * max(1.0, abs(loss))
+    if binding.have_ref():
+        ref = binding.Oracle("ref")
+        rng = np.random.default_rng(1002)
+        n = 64
+        x = C.rand(rng, (n, 32, 32, 3), dt)
+        obj = np.zeros((n, 1, 1, 10), dtype=dt, order="F")
+        obj[np.arange(n), 0, 0, np.arange(n) % 10] = 1
+        pr, lr, _ = ref.train_cifar(x, obj, 16, 2, params_in=p0)
+        pb, lb, _ = b200.train_cifar(x, obj, 16, 2, params_in=p0)
+        print("config 1, 2 epochs of 64 samples (8 Nadam steps): loss ref %.6f b200 %.6f, param err %.2e"
+              % (lr, lb, C.relerr(pb, pr)))
+        assert C.relerr(pb, pr) < (5e-4 if dt == np.float32 else 1e-8)
+        assert abs(lr - lb) < (1e-4 if dt == np.float32 else 1e-9) * max(1.0, abs(lr))
+
+
+def test_reference_gradient_test_passes():
+    """The reference's own gradient_test.cpp, compiled unchanged against the B200 headers."""
+    if not os.path.exists(GRADIENT_TEST):
+        pytest.fail("%s missing: run __graft_entry__.build() where /root/reference exists" % GRADIENT_TEST)
+    r = subprocess.run([GRADIENT_TEST, "--gtest_filter=" + GTEST_FILTER], capture_output=True, text=True,
+                       timeout=1500)
+    tail = "\n".join(r.stdout.splitlines()[-25:])
+    print(tail)
+    assert r.returncode == 0, tail + "\n" + r.stderr[-2000:]
+    assert "PASSED" in r.stdout and "FAILED" not in r.stdout
