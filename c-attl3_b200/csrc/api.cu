@@ -255,8 +255,7 @@ int cattl3_ctx_destroy(cattl3_ctx* ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->ws) cudaFree(ctx->ws);
 	if (ctx->tc_w) cudaFree(ctx->tc_w);
-	for (int i = 0; i < 2; ++i)
-		if (ctx->lo_buf[i]) cudaFree(ctx->lo_buf[i]);
+	if (ctx->lo_buf) cudaFree(ctx->lo_buf);
 	for (int i = 0; i < 3; ++i)
 		if (ctx->stage_dev[i]) cudaFree(ctx->stage_dev[i]);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

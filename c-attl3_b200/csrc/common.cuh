@@ -19,13 +19,12 @@ struct cattl3_ctx {
 	// general scratch (split-K partials, batch-norm partial sums); grown on demand, never shrunk
 	void* ws = nullptr;
 	size_t ws_bytes = 0;
-	// tcgen05 path scratch: packed / split weights and the low-order activation split
+	// tcgen05 path scratch: the weights repacked K-major and split hi | lo for TMA, and the low-order copy
+	// of the gathered tensor for the weight gradient
 	void* tc_w = nullptr;
 	size_t tc_w_bytes = 0;
-	void* lo_buf[2] = { nullptr, nullptr };
-	size_t lo_bytes[2] = { 0, 0 };
-	const void* lo_src[2] = { nullptr, nullptr };  // which tensor each slot currently holds (valid within one API call)
-	long long lo_elems[2] = { 0, 0 };
+	void* lo_buf = nullptr;
+	size_t lo_bytes = 0;
 	// pinned staging for the *_host entry points
 	void* stage_dev[3] = { nullptr, nullptr, nullptr };
 	size_t stage_dev_bytes[3] = { 0, 0, 0 };
@@ -57,7 +56,6 @@ inline int check_ctx(cattl3_ctx* ctx) {
 	cudaError_t e = cudaSetDevice(ctx->device);
 	if (e != cudaSuccess)
 		return cuda_fail(e, "cudaSetDevice", __FILE__, __LINE__);
-	ctx->lo_src[0] = ctx->lo_src[1] = nullptr;  // operand splits are only reusable within one API call
 	return CATTL3_OK;
 }
 

@@ -96,6 +96,24 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 		"tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
 		:: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: the A operand (128 rows = TMEM lanes, K elements = consecutive columns)
+// is read from tensor memory, so only B costs shared-memory bandwidth.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"setp.ne.b32 p, %4, 0;\n\t"
+		"tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+		:: "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// registers -> 32 lanes x 16 consecutive columns of TMEM (lane = thread of the warp's lane quarter)
+__device__ __forceinline__ void tmem_st_16(uint32_t taddr, const uint32_t* r) {
+	asm volatile(
+		"tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+		"{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+		:: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+		   "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (lane = thread).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float* v) {
 	uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -121,50 +139,40 @@ __device__ __forceinline__ void tmem_ld_16(uint32_t taddr, float* v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start address, leading /
-// stride byte offsets (all >> 4), version = 1 (Blackwell), layout type (2 = SWIZZLE_128B,
-// 1 = SWIZZLE_128B_BASE32B).
-//
-// Measured on B200 (scripts/umma_probe.cu): an MN-major kind::tf32 operand is only honoured with
-// layout type 1 (128-byte rows, 32-byte swizzle atom, Swizzle<2,5,2>): K atoms of 4 rows (512 B,
-// SBO apart), 32-element MN groups LBO apart; every other swizzle mode yields zeros.  TMA writes
-// that layout with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  K-major operands use the ordinary
-// SWIZZLE_128B (8-row atoms, SBO = 1024).
-constexpr uint32_t LT_SW128 = 2, LT_SW128_BASE32B = 1;
+// stride byte offsets (all >> 4), version = 1 (Blackwell), layout type (2 = SWIZZLE_128B, 4 = SWIZZLE_64B).
+// K-major operand, measured on B200 (scripts/umma_probe.cu, scripts/umma_probe2.cu): rows of 32 fp32
+// (128 B) use SWIZZLE_128B with 8-row atoms SBO = 1024 apart, rows of 16 fp32 (64 B) use SWIZZLE_64B with
+// 8-row atoms SBO = 512 apart; one K step of 8 elements = +32 B on the start address.
+constexpr uint32_t LT_SW128 = 2, LT_SW64 = 4;
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
 	return (uint64_t) ((smem_addr >> 4) & 0x3FFF) | ((uint64_t) ((lbo_bytes >> 4) & 0x3FFF) << 16) |
 			((uint64_t) ((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((uint64_t) layout_type << 61);
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, M = 128, N runtime.
-__host__ __device__ inline uint32_t make_idesc_tf32(int n, bool a_mn_major, bool b_mn_major) {
-	return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
-			((uint32_t) (n >> 3) << 17) | ((uint32_t) (128 >> 4) << 24);
+template<int KB>
+__device__ __forceinline__ uint64_t kmajor_desc(uint32_t tile_addr, int kstep) {
+	return KB == 32 ? make_smem_desc(tile_addr + kstep * 32, 16, 1024, LT_SW128)
+			: make_smem_desc(tile_addr + kstep * 32, 16, 512, LT_SW64);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128, N runtime.
+__host__ __device__ inline uint32_t make_idesc_tf32(int n) {
+	return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (n >> 3) << 17) | ((uint32_t) (128 >> 4) << 24);
 }
 
-// ---- operand preparation ---------------------------------------------------------------------------
-// lo = rn_tf32(x - trunc_tf32(x)): the part of x the tensor core does not see when it reads the raw
-// fp32 word (kind::tf32 uses the top 19 bits), rounded to nearest-even at TF32 precision so that the
-// hardware's own truncation of lo is exact and the split error is unbiased (~2^-22 relative).
-__device__ __forceinline__ float tf32_lo(float v) {
+// ---- 3xTF32 operand split -------------------------------------------------------------------------------
+// kind::tf32 uses the top 19 bits of an fp32 word.  x = hi + lo with hi = x truncated to TF32 and
+// lo = x - hi (exact in fp32), D += lo_a*hi_b + hi_a*lo_b + hi_a*hi_b in an FP32 accumulator.  Adding half a
+// TF32 ulp to lo's magnitude turns the hardware's truncation of lo into a round-to-nearest: unbiased,
+// ~2^-22 relative to x; the carry cannot leave a finite exponent.
+__device__ __forceinline__ uint32_t tf32_hi_bits(float v) { return __float_as_uint(v) & 0xFFFFE000u; }
+__device__ __forceinline__ uint32_t tf32_lo_bits(float v) {
 	const float r = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-	const uint32_t u = __float_as_uint(r);
-	return __uint_as_float((u + 0xFFFu + ((u >> 13) & 1u)) & 0xFFFFE000u);
-}
-__global__ void __launch_bounds__(256) split_lo_kernel(long long count, const float* __restrict__ x, float* __restrict__ lo) {
-	const long long nvec = count >> 2;
-	const long long stride = (long long) gridDim.x * 256;
-	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < nvec; i += stride) {
-		float4 v = reinterpret_cast<const float4*>(x)[i];
-		v.x = tf32_lo(v.x); v.y = tf32_lo(v.y); v.z = tf32_lo(v.z); v.w = tf32_lo(v.w);
-		reinterpret_cast<float4*>(lo)[i] = v;
-	}
-	for (long long i = (nvec << 2) + blockIdx.x * 256ll + threadIdx.x; i < count; i += stride)
-		lo[i] = tf32_lo(x[i]);
+	return __float_as_uint(r) + 0x1000u;
 }
 
-// Packs the weights of one gather-GEMM pass into K-major tiles [tap][j_pad][r_pad] (r contiguous),
-// split into hi (truncated to TF32) and lo, zero padded.
+// The operand that stays in shared memory is split once in HBM: weights for the gather GEMM (repacked
+// K-major as [part][tap][j_pad][r_pad], r contiguous, zero padded; part 0 = hi, 1 = lo) ...
 __global__ void __launch_bounds__(256) pack_weights_kernel(GatherGeom gg, int r_pad, int j_pad, const float* __restrict__ w,
-		float* __restrict__ hi, float* __restrict__ lo) {
+		float* __restrict__ packed) {
 	const int T = gg.RH * gg.RW;
 	const long long total = (long long) T * j_pad * r_pad;
 	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long) gridDim.x * 256) {
@@ -173,56 +181,90 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(GatherGeom gg, int r_
 		const int tap = (int) (i / ((long long) r_pad * j_pad));
 		float v = 0.f;
 		if (r < gg.SC && j < gg.J) v = w[tap * gg.w_stap + r * gg.w_sr + j * gg.w_sj];
-		hi[i] = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-		lo[i] = tf32_lo(v);
+		packed[i] = __uint_as_float(tf32_hi_bits(v));
+		packed[total + i] = __uint_as_float(tf32_lo_bits(v));
 	}
 }
+// ... and the gathered activations for the weight gradient (only their low part needs a copy).
+__global__ void __launch_bounds__(256) split_lo_kernel(long long count, const float* __restrict__ x, float* __restrict__ lo) {
+	const long long nvec = count >> 2;
+	const long long stride = (long long) gridDim.x * 256;
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < nvec; i += stride) {
+		float4 v = reinterpret_cast<const float4*>(x)[i];
+		v.x = __uint_as_float(tf32_lo_bits(v.x)); v.y = __uint_as_float(tf32_lo_bits(v.y));
+		v.z = __uint_as_float(tf32_lo_bits(v.z)); v.w = __uint_as_float(tf32_lo_bits(v.w));
+		reinterpret_cast<float4*>(lo)[i] = v;
+	}
+	for (long long i = (nvec << 2) + blockIdx.x * 256ll + threadIdx.x; i < count; i += stride)
+		lo[i] = __uint_as_float(tf32_lo_bits(x[i]));
+}
 
-// ---- the gather-GEMM kernel --------------------------------------------------------------------------
+// ---- pipeline shared by the two kernels ------------------------------------------------------------------
+// Shared memory is the scarce resource: measured on B200, the TMA writes, the converters' reads and writes
+// and the tensor core's operand reads of one SM together sustain ~95 B/clk (profiles/README.md), while one
+// 128 x 256 x 8 kind::tf32 MMA alone wants 96 B/clk when both operands come from shared memory.  So the
+// 128-row operand -- always the big activation tensor -- goes to TENSOR MEMORY: TMA lands the raw fp32 tile
+// in shared memory once, the converter warps read it once, split it and store hi / lo into TMEM
+// (tcgen05.st), and tcgen05.mma takes A from TMEM; only the B operand is read from shared memory.
+//
+// 320 threads: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM allocation), warps 2-5 = epilogue,
+// warps 6-9 = converters (a warp may only touch TMEM lanes 32*(warp % 4) ...).  Per stage:
+//   TMA --full--> converters --ready--> MMA --empty (tcgen05.commit)--> TMA.
+// TMEM (512 columns): accumulator(s) first, then per stage 2*KB columns holding A hi | A lo.
+constexpr int TC_BM = 128, TC_THREADS = 320, TC_MAX_STAGES = 8;
+
 struct TcGemmParams {
-	int N, SH, SW, OH, OW, J, RH, RW;
+	int N, OH, OW, J, RH, RW;
 	int ah, bh, ch, aw, bw, cw;
 	long long M, P;
 	int m_tiles, j_tiles;
 	int BN;          // filter tile (multiple of 16, <= 256)
-	int kc;          // channel chunks of 32 per tap
-	int stages;
-	int tmem_cols;   // power of two >= 2 * BN
+	int r_pad;       // reduce channels, padded to a multiple of KB
+	int nb;          // batch entries per A box (32 / 64 / 128): a tile is 128 / nb boxes of [nb n][KB channels]
+	int stages, nacc;
 	int bias_mode;
 	const float* bias;
 	float* out;
 };
 
-constexpr int TC_BM = 128, TC_KB = 32;
-constexpr int TC_A_BYTES = TC_BM * TC_KB * 4;  // 16 KB per split part
-
-__global__ void __launch_bounds__(192, 1) tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
-		const __grid_constant__ CUtensorMap tm_a_lo, const __grid_constant__ CUtensorMap tm_b_hi,
-		const __grid_constant__ CUtensorMap tm_b_lo, const TcGemmParams p) {
+// Gather GEMM (conv / dense forward, stride-1 input gradient):
+//   out[m + M*j] = bias + sum_{tap, r} src(m, tap, r) * w(tap, r, j),  m = n + N*(oh + OH*ow).
+// A: 128 / nb TMA boxes [nb n][1][1][KB channels] of the source tensor at the tap's coordinate (nb = 32, 64 or
+// 128 consecutive batch entries of one pixel), unswizzled; padding = TMA out-of-bounds zero fill.
+// B: one TMA box [KB r][BN j] of the packed weights, hi and lo.
+// The reduction walks channel chunks OUTER and taps INNER: the 148 CTAs then work on the same few channels
+// of neighbouring pixels at the same time, so every source byte is fetched from HBM once and the tap-shifted
+// re-reads hit L2.
+template<int KB>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tm_a,
+		const __grid_constant__ CUtensorMap tm_b, const TcGemmParams p) {
 	extern __shared__ __align__(1024) uint8_t smem_raw[];
 	uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
-	const int b_bytes = p.BN * TC_KB * 4;
-	const int stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
+	constexpr int A_BYTES = TC_BM * KB * 4;
+	const int b_bytes = p.BN * KB * 4;
+	const int stage_bytes = A_BYTES + 2 * b_bytes;
 	uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t) p.stages * stage_bytes);
 	uint64_t* full = bars;
-	uint64_t* empty = bars + p.stages;
-	uint64_t* acc_full = bars + 2 * p.stages;
+	uint64_t* ready = bars + TC_MAX_STAGES;
+	uint64_t* empty = bars + 2 * TC_MAX_STAGES;
+	uint64_t* acc_full = bars + 3 * TC_MAX_STAGES;
 	uint64_t* acc_empty = acc_full + 2;
 	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+	float* sbias = reinterpret_cast<float*>(bars + 32);  // 256 floats behind the barriers
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int T = p.RH * p.RW;
-	const int kblocks = T * p.kc;
+	const int kblocks = T * (p.r_pad / KB);
 	const int tiles = p.m_tiles * p.j_tiles;
+	const uint32_t a_col0 = (uint32_t) (p.nacc * p.BN);
 
 	if (warp == 0 && elect_one()) {
-		tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo);
-		tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
-		for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+		tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b);
+		for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
 		for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
 		fence_barrier_init();
 	}
-	if (warp == 1) tmem_alloc(tmem_slot, (uint32_t) p.tmem_cols);
+	if (warp == 1) tmem_alloc(tmem_slot, 512u);
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
@@ -234,44 +276,47 @@ __global__ void __launch_bounds__(192, 1) tc_gather_gemm_kernel(const __grid_con
 			int s = 0; uint32_t ph = 0;
 			for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
 				const int mt = tile % p.m_tiles, jt = tile / p.m_tiles;
-				// the four 32-row groups of this tile: (n0, oh, ow) each, or out of range
-				int gn[4], goh[4], gow[4];
+				int gn[4], goh[4], gow[4];  // the 128 / nb row groups of this tile: (n0, oh, ow) each, or out of range
+				const int ngroups = TC_BM / p.nb;
 				#pragma unroll
 				for (int g = 0; g < 4; ++g) {
-					const long long m = (long long) mt * TC_BM + 32 * g;
-					if (m < p.M) {
+					const long long m = (long long) mt * TC_BM + p.nb * g;
+					if (g < ngroups && m < p.M) {
 						gn[g] = (int) (m % p.N);
 						const long long pix = m / p.N;
 						goh[g] = (int) (pix % p.OH);
 						gow[g] = (int) (pix / p.OH);
 					} else {
-						gn[g] = 0; goh[g] = -0x40000; gow[g] = -0x40000;  // far out of bounds: zero fill
+						gn[g] = 0; goh[g] = -0x40000; gow[g] = -0x40000;
 					}
 				}
+				int rh = 0, rw = 0, tap = 0, c0 = 0;
 				for (int kb = 0; kb < kblocks; ++kb) {
-					const int tap = kb / p.kc, c0 = (kb % p.kc) * TC_KB;
-					const int rh = tap % p.RH, rw = tap / p.RH;
 					mbar_wait(&empty[s], ph ^ 1);
 					uint8_t* st = smem + (size_t) s * stage_bytes;
 					mbar_expect_tx(&full[s], (uint32_t) stage_bytes);
 					#pragma unroll
 					for (int g = 0; g < 4; ++g) {
-						int ih = goh[g] * p.ah + rh * p.bh + p.ch;
-						int iw = gow[g] * p.aw + rw * p.bw + p.cw;
-						if (goh[g] < -0x10000) { ih = -0x40000; iw = -0x40000; }
-						tma_load_4d(st + g * (TC_KB * 128), &tm_a_hi, &full[s], gn[g], ih, iw, c0);
-						tma_load_4d(st + TC_A_BYTES + g * (TC_KB * 128), &tm_a_lo, &full[s], gn[g], ih, iw, c0);
+						if (g < ngroups) {
+							int ih = goh[g] * p.ah + rh * p.bh + p.ch;
+							int iw = gow[g] * p.aw + rw * p.bw + p.cw;
+							if (goh[g] < -0x10000) { ih = -0x40000; iw = -0x40000; }  // far out of bounds: zero fill
+							tma_load_4d(st + g * (KB * p.nb * 4), &tm_a, &full[s], gn[g], ih, iw, c0);
+						}
 					}
-					tma_load_3d(st + 2 * TC_A_BYTES, &tm_b_hi, &full[s], c0, jt * p.BN, tap);
-					tma_load_3d(st + 2 * TC_A_BYTES + b_bytes, &tm_b_lo, &full[s], c0, jt * p.BN, tap);
+					tma_load_4d(st + A_BYTES, &tm_b, &full[s], c0, jt * p.BN, tap, 0);
+					tma_load_4d(st + A_BYTES + b_bytes, &tm_b, &full[s], c0, jt * p.BN, tap, 1);
 					if (++s == p.stages) { s = 0; ph ^= 1; }
+					// next k-block: taps inner, channel chunks outer
+					++tap;
+					if (++rh == p.RH) { rh = 0; if (++rw == p.RW) { rw = 0; tap = 0; c0 += KB; } }
 				}
 			}
 		}
 	} else if (warp == 1) {
 		// ===== MMA issuer (one elected thread) =====
 		if (elect_one()) {
-			const uint32_t idesc = make_idesc_tf32(p.BN, true, false);
+			const uint32_t idesc = make_idesc_tf32(p.BN);
 			int s = 0; uint32_t ph = 0;
 			int acc = 0; uint32_t acc_ph = 0;
 			for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -279,69 +324,125 @@ __global__ void __launch_bounds__(192, 1) tc_gather_gemm_kernel(const __grid_con
 				tc_fence_after();
 				const uint32_t d = tmem_base + (uint32_t) (acc * p.BN);
 				for (int kb = 0; kb < kblocks; ++kb) {
-					mbar_wait(&full[s], ph);
+					mbar_wait(&ready[s], ph);
 					tc_fence_after();
-					const uint32_t a_hi = smem_u32(smem + (size_t) s * stage_bytes);
-					const uint32_t a_lo = a_hi + TC_A_BYTES;
-					const uint32_t b_hi = a_hi + 2 * TC_A_BYTES;
+					const uint32_t b_hi = smem_u32(smem + (size_t) s * stage_bytes + A_BYTES);
 					const uint32_t b_lo = b_hi + b_bytes;
+					const uint32_t a_hi = tmem_base + a_col0 + (uint32_t) (s * 2 * KB);
+					const uint32_t a_lo = a_hi + KB;
 					#pragma unroll
 					for (int pass = 0; pass < 3; ++pass) {
 						const uint32_t a = pass == 0 ? a_lo : a_hi;
 						const uint32_t b = pass == 1 ? b_lo : b_hi;
 						#pragma unroll
-						for (int ks = 0; ks < TC_KB / 8; ++ks) {
-							// A: MN-major, 128 B rows of 32 consecutive m; one K step = 8 rows = two 4-row atoms
-							// (SBO = 512); the four 32-row M groups are LBO = KB*128 apart
-							const uint64_t da = make_smem_desc(a + ks * 1024, TC_KB * 128, 512, LT_SW128_BASE32B);
-							// B: K-major, 128 B rows, 8-row groups SBO = 1024 apart, K step = 32 B inside the row
-							const uint64_t db = make_smem_desc(b + ks * 32, 16, 1024, LT_SW128);
-							umma_tf32(d, da, db, idesc, (kb | pass | ks) != 0 ? 1u : 0u);
-						}
+						for (int ks = 0; ks < KB / 8; ++ks)
+							umma_tf32_ts(d, a + 8 * ks, kmajor_desc<KB>(b, ks), idesc, (kb | pass | ks) != 0 ? 1u : 0u);
 					}
-					umma_commit(&empty[s]);   // frees the smem stage once these MMAs have read it
+					umma_commit(&empty[s]);   // frees the smem stage and its TMEM columns once these MMAs have read them
 					if (++s == p.stages) { s = 0; ph ^= 1; }
 				}
 				umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
-				if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+				if (++acc == p.nacc) { acc = 0; acc_ph ^= 1; }
 			}
 		}
-	} else {
+	} else if (warp < 6) {
 		// ===== epilogue warps 2..5: TMEM -> registers -> (+bias) -> coalesced global stores =====
+		// The per-filter bias of the tile is staged in shared memory while the MMAs of the tile still run,
+		// so the drain itself is tcgen05.ld + add + store with no dependent global loads.
 		const int q = warp & 3;  // TMEM lane quarter this warp may access
+		const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
 		int acc = 0; uint32_t acc_ph = 0;
+		int staged_jt = -1;
 		for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
 			const int mt = tile % p.m_tiles, jt = tile / p.m_tiles;
+			if (p.bias_mode == 1 && jt != staged_jt) {
+				asm volatile("bar.sync 1, 128;" ::: "memory");  // nobody still reads the previous tile's bias
+				for (int c = et; c < p.BN; c += 128) {
+					const int j = jt * p.BN + c;
+					sbias[c] = j < p.J ? __ldg(p.bias + j) : 0.f;
+				}
+				asm volatile("bar.sync 1, 128;" ::: "memory");
+				staged_jt = jt;
+			}
 			mbar_wait(&acc_full[acc], acc_ph);
 			tc_fence_after();
 			const long long m = (long long) mt * TC_BM + 32 * q + lane;
 			const bool m_ok = m < p.M;
 			const long long pix = m / p.N;
 			const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16) + (uint32_t) (acc * p.BN);
+			float* out_m = p.out + m + p.M * (long long) (jt * p.BN);
+			const int jn = p.J - jt * p.BN < p.BN ? p.J - jt * p.BN : p.BN;  // valid columns of this tile
 			for (int c0 = 0; c0 < p.BN; c0 += 16) {
-				float v[16];
+				float v[16], bv[16];
 				tmem_ld_16(taddr + c0, v);
+				if (p.bias_mode == 1) {
+					#pragma unroll
+					for (int i = 0; i < 16; ++i) bv[i] = sbias[c0 + i];
+				} else if (p.bias_mode == 2) {
+					// one bias per output element (TransConvKernelLayer): independent loads, issued together
+					#pragma unroll
+					for (int i = 0; i < 16; ++i) {
+						const int c = c0 + i < jn ? c0 + i : jn - 1;
+						bv[i] = m_ok ? __ldg(p.bias + pix + p.P * (long long) (jt * p.BN + c)) : 0.f;
+					}
+				} else {
+					#pragma unroll
+					for (int i = 0; i < 16; ++i) bv[i] = 0.f;
+				}
 				tmem_ld_wait();
-				#pragma unroll
-				for (int i = 0; i < 16; ++i) {
-					const int j = jt * p.BN + c0 + i;
-					if (m_ok && j < p.J) {
-						float r = v[i];
-						if (p.bias_mode == 1) r += __ldg(p.bias + j);
-						else if (p.bias_mode == 2) r += __ldg(p.bias + pix + p.P * j);
-						p.out[m + p.M * j] = r;
+				if (m_ok) {
+					if (c0 + 16 <= jn) {
+						#pragma unroll
+						for (int i = 0; i < 16; ++i) out_m[p.M * (long long) (c0 + i)] = v[i] + bv[i];
+					} else {
+						#pragma unroll
+						for (int i = 0; i < 16; ++i)
+							if (c0 + i < jn) out_m[p.M * (long long) (c0 + i)] = v[i] + bv[i];
 					}
 				}
 			}
 			tc_fence_before();
 			__syncwarp();
 			if (lane == 0) mbar_arrive(&acc_empty[acc]);
-			if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+			if (++acc == p.nacc) { acc = 0; acc_ph ^= 1; }
+		}
+	} else {
+		// ===== converter warps 6..9: raw A tile (shared memory) -> hi | lo (tensor memory) =====
+		// The tile lies in shared memory as 128 / nb unswizzled boxes of KB rows x nb batch entries; row m of the
+		// tile is entry m % nb of box m / nb.  Lane = row within the quarter, so a warp reads 32 consecutive
+		// floats per k (conflict free) and owns TMEM lanes 32q .. 32q+31.
+		const int q = warp & 3;
+		const int row = 32 * q + lane;
+		const uint32_t row_off = (uint32_t) ((row / p.nb) * (KB * p.nb * 4) + (row % p.nb) * 4);
+		const uint32_t k_stride = (uint32_t) (p.nb * 4);
+		int s = 0; uint32_t ph = 0;
+		for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+			for (int kb = 0; kb < kblocks; ++kb) {
+				mbar_wait(&full[s], ph);
+				const uint8_t* grp = smem + (size_t) s * stage_bytes + row_off;
+				const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16) + a_col0 + (uint32_t) (s * 2 * KB);
+				#pragma unroll
+				for (int k0 = 0; k0 < KB; k0 += 16) {
+					uint32_t hi[16], lo[16];
+					#pragma unroll
+					for (int k = 0; k < 16; ++k) {
+						const float v = *reinterpret_cast<const float*>(grp + (uint32_t) (k0 + k) * k_stride);
+						hi[k] = tf32_hi_bits(v);
+						lo[k] = tf32_lo_bits(v);
+					}
+					tmem_st_16(taddr + k0, hi);
+					tmem_st_16(taddr + KB + k0, lo);
+				}
+				tmem_st_wait();
+				tc_fence_before();
+				mbar_arrive(&ready[s]);
+				if (++s == p.stages) { s = 0; ph ^= 1; }
+			}
 		}
 	}
 	tc_fence_before();
 	__syncthreads();
-	if (warp == 1) tmem_dealloc(tmem_base, (uint32_t) p.tmem_cols);
+	if (warp == 1) tmem_dealloc(tmem_base, 512u);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
@@ -380,20 +481,8 @@ static int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint6
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-
-// Low-order split of a tensor into one of the context's two scratch slots; a split made earlier in
-// the same API call (ctx->lo_src[slot] == ptr) is reused -- conv_backward needs lo(dY) twice.
-static int get_lo_split(cattl3_ctx* ctx, const float* ptr, long long elems, int slot, const float** lo_out) {
-	for (int s = 0; s < 2; ++s)
-		if (ctx->lo_src[s] == ptr && ctx->lo_elems[s] == elems) { *lo_out = (const float*) ctx->lo_buf[s]; return CATTL3_OK; }
-	CATTL3_CHECK(ensure_buffer(ctx, &ctx->lo_buf[slot], &ctx->lo_bytes[slot], (size_t) elems * 4));
-	split_lo_kernel<<<ew_grid(ctx, elems / 4 + 1, 256), 256, 0, ctx->stream>>>(elems, ptr, (float*) ctx->lo_buf[slot]);
-	CATTL3_LAUNCHED(ctx);
-	ctx->lo_src[slot] = ptr;
-	ctx->lo_elems[slot] = elems;
-	*lo_out = (const float*) ctx->lo_buf[slot];
-	return CATTL3_OK;
-}
+static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+constexpr int TC_SMEM_LIMIT = 227 * 1024 - 2560;
 
 bool tc_gather_gemm_supported(const cattl3_ctx*, const GatherGeom& gg) {
 	// 32-row TMA boxes along n; no per-pixel divisibility tests (strided transposed gathers go to SIMT)
@@ -404,133 +493,142 @@ bool tc_gather_gemm_supported(const cattl3_ctx*, const GatherGeom& gg) {
 	return get_encode() != nullptr;
 }
 
-static int round_up(int v, int m) { return (v + m - 1) / m * m; }
-
 int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const float* w, const float* bias,
 		int bias_mode, float* out) {
 	CATTL3_REQUIRE(aligned16(src) && aligned16(out), "tcgen05 path needs 16-byte aligned tensors");
 	const int T = gg.RH * gg.RW;
-	const int r_pad = round_up(gg.SC, TC_KB);
 	const int BN = gg.J >= 256 ? 256 : round_up(gg.J, 16);
+	// 32-element k-blocks (128 B weight rows) where shared and tensor memory allow four stages of them
+	const int KB = BN <= 128 ? 32 : 16;
+	const int r_pad = round_up(gg.SC, KB);
+	// the A operand goes through registers into tensor memory, so its shared-memory image needs no MMA layout:
+	// take the longest contiguous run of batch entries TMA can deliver per row (up to 128 = 512 B)
+	const int nb = gg.N % 128 == 0 ? 128 : (gg.N % 64 == 0 ? 64 : 32);
 	const int j_tiles = (gg.J + BN - 1) / BN;
 	const int j_pad = j_tiles * BN;
 	const long long M = (long long) gg.N * gg.OH * gg.OW;
-	const long long src_elems = (long long) gg.N * gg.SH * gg.SW * gg.SC;
 	const long long w_elems = (long long) T * j_pad * r_pad;
 
-	// operand preparation: low-order split of the activations, packed + split weights
 	CATTL3_CHECK(ensure_buffer(ctx, &ctx->tc_w, &ctx->tc_w_bytes, (size_t) w_elems * 8));
-	const float* a_lo = nullptr;
-	CATTL3_CHECK(get_lo_split(ctx, src, src_elems, 0, &a_lo));
-	float* w_hi = (float*) ctx->tc_w;
-	float* w_lo = w_hi + w_elems;
-	pack_weights_kernel<<<ew_grid(ctx, w_elems, 256), 256, 0, ctx->stream>>>(gg, r_pad, j_pad, w, w_hi, w_lo);
+	float* w_packed = (float*) ctx->tc_w;
+	pack_weights_kernel<<<ew_grid(ctx, w_elems, 256), 256, 0, ctx->stream>>>(gg, r_pad, j_pad, w, w_packed);
 	CATTL3_LAUNCHED(ctx);
 
-	CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
+	CUtensorMap tm_a, tm_b;
 	{
 		cuuint64_t dims[4] = { (cuuint64_t) gg.N, (cuuint64_t) gg.SH, (cuuint64_t) gg.SW, (cuuint64_t) gg.SC };
 		cuuint64_t str[3] = { (cuuint64_t) gg.N * 4, (cuuint64_t) gg.N * gg.SH * 4, (cuuint64_t) gg.N * gg.SH * gg.SW * 4 };
-		cuuint32_t box[4] = { 32, 1, 1, (cuuint32_t) TC_KB };
-		CATTL3_CHECK(encode_map(&tm_a_hi, src, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
-		CATTL3_CHECK(encode_map(&tm_a_lo, a_lo, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+		cuuint32_t box[4] = { (cuuint32_t) nb, 1, 1, (cuuint32_t) KB };
+		CATTL3_CHECK(encode_map(&tm_a, src, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE));
 	}
 	{
-		cuuint64_t dims[3] = { (cuuint64_t) r_pad, (cuuint64_t) j_pad, (cuuint64_t) T };
-		cuuint64_t str[2] = { (cuuint64_t) r_pad * 4, (cuuint64_t) r_pad * j_pad * 4 };
-		cuuint32_t box[3] = { 32, (cuuint32_t) BN, 1 };
-		CATTL3_CHECK(encode_map(&tm_b_hi, w_hi, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
-		CATTL3_CHECK(encode_map(&tm_b_lo, w_lo, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+		cuuint64_t dims[4] = { (cuuint64_t) r_pad, (cuuint64_t) j_pad, (cuuint64_t) T, 2 };
+		cuuint64_t str[3] = { (cuuint64_t) r_pad * 4, (cuuint64_t) r_pad * j_pad * 4, (cuuint64_t) w_elems * 4 };
+		cuuint32_t box[4] = { (cuuint32_t) KB, (cuuint32_t) BN, 1, 1 };
+		CATTL3_CHECK(encode_map(&tm_b, w_packed, 4, dims, str, box,
+				KB == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B));
 	}
 
 	TcGemmParams p;
-	p.N = gg.N; p.SH = gg.SH; p.SW = gg.SW; p.OH = gg.OH; p.OW = gg.OW; p.J = gg.J; p.RH = gg.RH; p.RW = gg.RW;
+	p.N = gg.N; p.OH = gg.OH; p.OW = gg.OW; p.J = gg.J; p.RH = gg.RH; p.RW = gg.RW;
 	p.ah = gg.ah; p.bh = gg.bh; p.ch = gg.ch; p.aw = gg.aw; p.bw = gg.bw; p.cw = gg.cw;
 	p.M = M; p.P = (long long) gg.OH * gg.OW;
 	p.m_tiles = (int) ceil_div(M, TC_BM); p.j_tiles = j_tiles;
-	p.BN = BN; p.kc = r_pad / TC_KB;
-	const int stage_bytes = 2 * TC_A_BYTES + 2 * BN * TC_KB * 4;
-	int stages = (227 * 1024 - 2048) / stage_bytes;
-	if (stages > 6) stages = 6;
+	p.BN = BN; p.r_pad = r_pad; p.nb = nb;
+	// one accumulator of 256 columns leaves room for the A stages; narrower tiles double-buffer it so that the
+	// epilogue of one tile overlaps the MMAs of the next
+	p.nacc = 2 * BN + 4 * 2 * KB <= 512 ? 2 : 1;
+	const int stage_bytes = TC_BM * KB * 4 + 2 * BN * KB * 4;
+	int stages = TC_SMEM_LIMIT / stage_bytes;
+	const int tmem_stages = (512 - p.nacc * BN) / (2 * KB);
+	if (stages > tmem_stages) stages = tmem_stages;
+	if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
 	p.stages = stages;
-	int cols = 32;
-	while (cols < 2 * BN) cols <<= 1;
-	p.tmem_cols = cols;
 	p.bias_mode = bias_mode; p.bias = bias; p.out = out;
-	const size_t smem_bytes = (size_t) stages * stage_bytes + 1024 + 256;
-	CATTL3_CUDA(cudaFuncSetAttribute(tc_gather_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+	// at least half of the shared memory: two co-resident CTAs would deadlock allocating 512 TMEM columns each
+	size_t smem_bytes = (size_t) stages * stage_bytes + 1024 + 256 + 1024;  // alignment slack, barriers, bias
+	if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
 	const int tiles = p.m_tiles * p.j_tiles;
 	const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
-	tc_gather_gemm_kernel<<<grid, 192, smem_bytes, ctx->stream>>>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p);
+	if (KB == 32) {
+		CATTL3_CUDA(cudaFuncSetAttribute(tc_gather_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		tc_gather_gemm_kernel<32><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(tm_a, tm_b, p);
+	} else {
+		CATTL3_CUDA(cudaFuncSetAttribute(tc_gather_gemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+		tc_gather_gemm_kernel<16><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(tm_a, tm_b, p);
+	}
 	CATTL3_LAUNCHED(ctx);
 	return CATTL3_OK;
 }
 
 // ---- the weight-gradient kernel ---------------------------------------------------------------------
-// dw(tap, r, j) += sum_m src(m, tap, r) * plain(m, j): a GEMM whose reduction runs over
-// m = N*OH*OW.  Both operands are K-major here (m is contiguous in HBM for both):
-//   A tile: 128 rows = (tap, channel) pairs, built from 128/RB TMA boxes [32 m][1][1][RB channels]
-//           of the gathered tensor (one box per tap, at that tap's spatial coordinate);
-//   B tile: BN rows = output channels, one 2-D box [32 m][BN] of the plain tensor.
-// One k-block = one 32-row m-group (32 batch entries of one pixel).  Each CTA owns one
-// (row tile, column tile) and one contiguous range of m-groups (split-K); the fp32 partial tile is
-// written to scratch and reduced into dw in split order by wgrad_reduce_tc_kernel (deterministic,
-// accumulating: Parameters::accumulate_grad, C-ATTL3/parameters/StandardParameters.hpp:115-123).
+// dw(tap, r, j) += sum_m src(m, tap, r) * plain(m, j): a GEMM whose reduction runs over m = N*OH*OW, so m
+// is the K dimension and both operands are K-major where they lie (m is contiguous in HBM for both).
+//   A (tensor memory, 128 rows = output channels j): one 2-D TMA box [16 m][128 j] of the plain tensor
+//     (dY: the big one, read once), split by the converters;
+//   B (shared memory, up to 192 rows = (tap, channel) pairs): per tap one box [16 m][RB channels] of the
+//     gathered tensor at that tap's coordinate, from the raw tensor (hi: the tensor core truncates) and from
+//     its low-order copy made by split_lo_kernel.
+// One k-block = 16 consecutive batch entries of one pixel.  Each CTA owns one (j tile, column tile) and one
+// contiguous range of k-blocks (split-K); the fp32 partial tile goes to scratch and wgrad_reduce_tc_kernel
+// adds the partials to dw in split order (deterministic, accumulating: Parameters::accumulate_grad,
+// C-ATTL3/parameters/StandardParameters.hpp:115-123).
 struct TcWgradParams {
 	int N, OH, OW, R, J, RH, RW;
 	int ah, bh, ch, aw, bw, cw;
-	int RB;            // channel rows per TMA box (32 / 64 / 128)
+	int RB;            // channel rows per TMA box (16 / 32 / 64)
 	int rchunks;       // r_pad / RB
-	int row_blocks;    // T * rchunks
-	int row_tiles, j_tiles, splits;
+	int boxes;         // T * rchunks
+	int boxes_per_tile, col_tiles, j_tiles, splits;
+	int BNW;           // boxes_per_tile * RB: columns of the accumulator
 	long long mgroups, mg_per_split;
-	int BN, stages, tmem_cols;
+	int stages;
 	int flush;         // k-blocks accumulated in TMEM before the partial tile is folded into fp32 scratch
 	long long w_stap, w_sr, w_sj, dw_elems;
-	float* partial;    // [split][tile][BN columns][128 rows]
+	float* partial;    // [split][tile][BNW columns][128 rows]
 };
 
 // Tensor-core accumulation truncates (round-toward-zero) at every MMA, so a reduction of n MMA steps
 // carries a bias of ~n * 2^-24 relative (measured: 2e-4 on the 10^4-step config-2 weight gradient).
 // The kernel therefore closes a TMEM accumulator every `flush` k-blocks; the epilogue warps fold it
-// into a CTA-private fp32 tile with round-to-nearest adds while the MMA warp fills the other
-// accumulator.
-__global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a_hi,
-		const __grid_constant__ CUtensorMap tm_a_lo, const __grid_constant__ CUtensorMap tm_b_hi,
-		const __grid_constant__ CUtensorMap tm_b_lo, const TcWgradParams p) {
+// into a CTA-private fp32 tile with round-to-nearest adds while the MMA warp fills the other accumulator.
+constexpr int WG_KB = 16;
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a,
+		const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const TcWgradParams p) {
 	extern __shared__ __align__(1024) uint8_t smem_raw[];
 	uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
-	const int b_bytes = p.BN * 128;
-	const int stage_bytes = 2 * TC_A_BYTES + 2 * b_bytes;
+	constexpr int A_BYTES = TC_BM * WG_KB * 4;  // 8 KB
+	const int b_bytes = p.BNW * WG_KB * 4;
+	const int stage_bytes = A_BYTES + 2 * b_bytes;
 	uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t) p.stages * stage_bytes);
 	uint64_t* full = bars;
-	uint64_t* empty = bars + p.stages;
-	uint64_t* acc_full = bars + 2 * p.stages;
+	uint64_t* ready = bars + TC_MAX_STAGES;
+	uint64_t* empty = bars + 2 * TC_MAX_STAGES;
+	uint64_t* acc_full = bars + 3 * TC_MAX_STAGES;
 	uint64_t* acc_empty = acc_full + 2;
 	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int tiles = p.row_tiles * p.j_tiles;
+	const int tiles = p.col_tiles * p.j_tiles;
 	const int tile = blockIdx.x % tiles, z = blockIdx.x / tiles;
-	const int rt = tile % p.row_tiles, jt = tile / p.row_tiles;
-	const int boxes_per_tile = 128 / p.RB;
-	const int rb0 = rt * boxes_per_tile;
-	int nboxes = p.row_blocks - rb0;
-	if (nboxes > boxes_per_tile) nboxes = boxes_per_tile;
+	const int ct = tile % p.col_tiles, jt = tile / p.col_tiles;  // CTAs sharing a dY tile are neighbours
+	const int box0 = ct * p.boxes_per_tile;
+	int nboxes = p.boxes - box0;
+	if (nboxes > p.boxes_per_tile) nboxes = p.boxes_per_tile;
 	const long long mg0 = (long long) z * p.mg_per_split;
 	long long mg1 = mg0 + p.mg_per_split;
 	if (mg1 > p.mgroups) mg1 = p.mgroups;
 	const long long kblocks = mg1 > mg0 ? mg1 - mg0 : 0;
 	const long long chunks = (kblocks + p.flush - 1) / p.flush;
+	const uint32_t a_col0 = (uint32_t) (2 * p.BNW);
 
 	if (warp == 0 && elect_one()) {
-		tma_prefetch_desc(&tm_a_hi); tma_prefetch_desc(&tm_a_lo);
-		tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
-		for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+		tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
+		for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
 		for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
 		fence_barrier_init();
 	}
-	if (warp == 1) tmem_alloc(tmem_slot, (uint32_t) p.tmem_cols);
+	if (warp == 1) tmem_alloc(tmem_slot, 512u);
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
@@ -539,56 +637,52 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
 	if (warp == 0) {
 		if (elect_one()) {
 			int s = 0; uint32_t ph = 0;
-			const uint32_t tx = (uint32_t) (2 * nboxes * p.RB * 128 + 2 * b_bytes);
+			const uint32_t tx = (uint32_t) (A_BYTES + 2 * nboxes * p.RB * WG_KB * 4);
 			for (long long kb = 0; kb < kblocks; ++kb) {
-				const long long m = (mg0 + kb) * 32;
+				const long long m = (mg0 + kb) * WG_KB;
 				const int n0 = (int) (m % p.N);
 				const long long pix = m / p.N;
 				const int oh = (int) (pix % p.OH), ow = (int) (pix / p.OH);
 				mbar_wait(&empty[s], ph ^ 1);
 				uint8_t* st = smem + (size_t) s * stage_bytes;
 				mbar_expect_tx(&full[s], tx);
+				tma_load_2d(st, &tm_a, &full[s], (int) m, jt * TC_BM);
 				for (int bx = 0; bx < nboxes; ++bx) {
-					const int rb = rb0 + bx;
-					const int tap = rb / p.rchunks, c0 = (rb % p.rchunks) * p.RB;
+					const int box = box0 + bx;
+					const int tap = box / p.rchunks, c0 = (box % p.rchunks) * p.RB;
 					const int rh = tap % p.RH, rw = tap / p.RH;
 					const int ih = oh * p.ah + rh * p.bh + p.ch, iw = ow * p.aw + rw * p.bw + p.cw;
-					tma_load_4d(st + bx * p.RB * 128, &tm_a_hi, &full[s], n0, ih, iw, c0);
-					tma_load_4d(st + TC_A_BYTES + bx * p.RB * 128, &tm_a_lo, &full[s], n0, ih, iw, c0);
+					tma_load_4d(st + A_BYTES + bx * p.RB * (WG_KB * 4), &tm_b_hi, &full[s], n0, ih, iw, c0);
+					tma_load_4d(st + A_BYTES + b_bytes + bx * p.RB * (WG_KB * 4), &tm_b_lo, &full[s], n0, ih, iw, c0);
 				}
-				tma_load_2d(st + 2 * TC_A_BYTES, &tm_b_hi, &full[s], (int) m, jt * p.BN);
-				tma_load_2d(st + 2 * TC_A_BYTES + b_bytes, &tm_b_lo, &full[s], (int) m, jt * p.BN);
 				if (++s == p.stages) { s = 0; ph ^= 1; }
 			}
 		}
 	} else if (warp == 1) {
 		if (elect_one()) {
-			const uint32_t idesc = make_idesc_tf32(p.BN, false, false);
+			const uint32_t idesc = make_idesc_tf32(p.BNW);
 			int s = 0; uint32_t ph = 0;
 			int acc = 0; uint32_t acc_ph = 0;
 			long long kb = 0;
 			for (long long c = 0; c < chunks; ++c) {
 				mbar_wait(&acc_empty[acc], acc_ph ^ 1);
 				tc_fence_after();
-				const uint32_t d = tmem_base + (uint32_t) (acc * p.BN);
+				const uint32_t d = tmem_base + (uint32_t) (acc * p.BNW);
 				const long long kend = kb + p.flush < kblocks ? kb + p.flush : kblocks;
 				for (bool first = true; kb < kend; ++kb) {
-					mbar_wait(&full[s], ph);
+					mbar_wait(&ready[s], ph);
 					tc_fence_after();
-					const uint32_t a_hi = smem_u32(smem + (size_t) s * stage_bytes);
-					const uint32_t a_lo = a_hi + TC_A_BYTES;
-					const uint32_t b_hi = a_hi + 2 * TC_A_BYTES;
+					const uint32_t b_hi = smem_u32(smem + (size_t) s * stage_bytes + A_BYTES);
 					const uint32_t b_lo = b_hi + b_bytes;
+					const uint32_t a_hi = tmem_base + a_col0 + (uint32_t) (s * 2 * WG_KB);
+					const uint32_t a_lo = a_hi + WG_KB;
 					#pragma unroll
 					for (int pass = 0; pass < 3; ++pass) {
 						const uint32_t a = pass == 0 ? a_lo : a_hi;
 						const uint32_t b = pass == 1 ? b_lo : b_hi;
 						#pragma unroll
-						for (int ks = 0; ks < 4; ++ks) {
-							const uint64_t da = make_smem_desc(a + ks * 32, 16, 1024, LT_SW128);
-							const uint64_t db = make_smem_desc(b + ks * 32, 16, 1024, LT_SW128);
-							umma_tf32(d, da, db, idesc, (first && pass == 0 && ks == 0) ? 0u : 1u);
-						}
+						for (int ks = 0; ks < WG_KB / 8; ++ks)
+							umma_tf32_ts(d, a + 8 * ks, kmajor_desc<WG_KB>(b, ks), idesc, (first && pass == 0 && ks == 0) ? 0u : 1u);
 					}
 					first = false;
 					umma_commit(&empty[s]);
@@ -598,19 +692,19 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
 				if (++acc == 2) { acc = 0; acc_ph ^= 1; }
 			}
 		}
-	} else {
+	} else if (warp < 6) {
 		const int q = warp & 3;
-		const int row = 32 * q + lane;  // accumulator lane = row of the tile
-		float* dst = p.partial + ((long long) z * tiles + tile) * p.BN * 128 + row;
+		const int row = 32 * q + lane;  // accumulator lane = output channel within the j tile
+		float* dst = p.partial + ((long long) z * tiles + tile) * p.BNW * 128 + row;
 		if (chunks == 0) {
-			for (int c0 = 0; c0 < p.BN; ++c0) dst[(long long) c0 * 128] = 0.f;
+			for (int c0 = 0; c0 < p.BNW; ++c0) dst[(long long) c0 * 128] = 0.f;
 		}
 		int acc = 0; uint32_t acc_ph = 0;
 		for (long long c = 0; c < chunks; ++c) {
 			mbar_wait(&acc_full[acc], acc_ph);
 			tc_fence_after();
-			const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16) + (uint32_t) (acc * p.BN);
-			for (int c0 = 0; c0 < p.BN; c0 += 16) {
+			const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16) + (uint32_t) (acc * p.BNW);
+			for (int c0 = 0; c0 < p.BNW; c0 += 16) {
 				float v[16];
 				tmem_ld_16(taddr + c0, v);
 				tmem_ld_wait();
@@ -626,28 +720,54 @@ __global__ void __launch_bounds__(192, 1) tc_wgrad_kernel(const __grid_constant_
 			if (lane == 0) mbar_arrive(&acc_empty[acc]);
 			if (++acc == 2) { acc = 0; acc_ph ^= 1; }
 		}
+	} else {
+		// converters: row (= output channel) 32q + lane of the dY tile, 16 m values = one 64 B row (SWIZZLE_64B)
+		const int q = warp & 3;
+		const int row = 32 * q + lane;
+		int s = 0; uint32_t ph = 0;
+		for (long long kb = 0; kb < kblocks; ++kb) {
+			mbar_wait(&full[s], ph);
+			const uint8_t* tile_a = smem + (size_t) s * stage_bytes;
+			const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16) + a_col0 + (uint32_t) (s * 2 * WG_KB);
+			uint32_t hi[16], lo[16];
+			#pragma unroll
+			for (int c = 0; c < 4; ++c) {
+				uint32_t off = (uint32_t) (row * 64 + c * 16);
+				off ^= ((off >> 7) & 3u) << 4;
+				const float4 v = *reinterpret_cast<const float4*>(tile_a + off);
+				hi[4 * c + 0] = tf32_hi_bits(v.x); lo[4 * c + 0] = tf32_lo_bits(v.x);
+				hi[4 * c + 1] = tf32_hi_bits(v.y); lo[4 * c + 1] = tf32_lo_bits(v.y);
+				hi[4 * c + 2] = tf32_hi_bits(v.z); lo[4 * c + 2] = tf32_lo_bits(v.z);
+				hi[4 * c + 3] = tf32_hi_bits(v.w); lo[4 * c + 3] = tf32_lo_bits(v.w);
+			}
+			tmem_st_16(taddr, hi);
+			tmem_st_16(taddr + WG_KB, lo);
+			tmem_st_wait();
+			tc_fence_before();
+			mbar_arrive(&ready[s]);
+			if (++s == p.stages) { s = 0; ph ^= 1; }
+		}
 	}
 	tc_fence_before();
 	__syncthreads();
-	if (warp == 1) tmem_dealloc(tmem_base, (uint32_t) p.tmem_cols);
+	if (warp == 1) tmem_dealloc(tmem_base, 512u);
 }
 
 // dw(tap, r, j) += sum over splits of the scratch tiles, in split order (deterministic).
 __global__ void __launch_bounds__(256) wgrad_reduce_tc_kernel(const TcWgradParams p, int T, float* __restrict__ dw) {
 	const long long total = (long long) T * p.R * p.J;
-	const int tiles = p.row_tiles * p.j_tiles;
-	const int boxes_per_tile = 128 / p.RB;
+	const int tiles = p.col_tiles * p.j_tiles;
 	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long) gridDim.x * 256) {
-		const int r = (int) (i % p.R);
-		const int tap = (int) ((i / p.R) % T);
-		const int j = (int) (i / ((long long) p.R * T));
-		const int rb = tap * p.rchunks + r / p.RB;
-		const int rt = rb / boxes_per_tile;
-		const int row = (rb % boxes_per_tile) * p.RB + r % p.RB;
-		const int jt = j / p.BN, col = j % p.BN;
-		const long long off = ((long long) (rt + p.row_tiles * jt) * p.BN + col) * 128 + row;
+		const int j = (int) (i % p.J);
+		const int r = (int) ((i / p.J) % p.R);
+		const int tap = (int) (i / ((long long) p.J * p.R));
+		const int box = tap * p.rchunks + r / p.RB;
+		const int ct = box / p.boxes_per_tile;
+		const int col = (box % p.boxes_per_tile) * p.RB + r % p.RB;
+		const int jt = j / TC_BM, row = j % TC_BM;
+		const long long off = ((long long) (ct + p.col_tiles * jt) * p.BNW + col) * 128 + row;
 		float s = 0.f;
-		for (int z = 0; z < p.splits; ++z) s += p.partial[(long long) z * tiles * p.BN * 128 + off];
+		for (int z = 0; z < p.splits; ++z) s += p.partial[(long long) z * tiles * p.BNW * 128 + off];
 		dw[tap * p.w_stap + r * p.w_sr + j * p.w_sj] += s;
 	}
 }
@@ -663,62 +783,65 @@ bool tc_wgrad_supported(const cattl3_ctx*, const GatherGeom& gg) {
 int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const float* plain, float* dw) {
 	CATTL3_REQUIRE(aligned16(src) && aligned16(plain), "tcgen05 path needs 16-byte aligned tensors");
 	const int T = gg.RH * gg.RW;
-	const int r_pad = round_up(gg.SC, 32);
-	const int RB = r_pad % 128 == 0 ? 128 : (r_pad % 64 == 0 ? 64 : 32);
-	const int BN = gg.J >= 256 ? 256 : round_up(gg.J, 16);
+	const int r_pad = round_up(gg.SC, 16);
+	const int RB = r_pad % 64 == 0 ? 64 : (r_pad % 32 == 0 ? 32 : 16);
 	const long long M = (long long) gg.N * gg.OH * gg.OW;
 	const long long src_elems = (long long) gg.N * gg.SH * gg.SW * gg.SC;
-	const long long plain_elems = M * gg.J;
 
-	const float *a_lo = nullptr, *b_lo = nullptr;
-	CATTL3_CHECK(get_lo_split(ctx, src, src_elems, 0, &a_lo));
-	CATTL3_CHECK(get_lo_split(ctx, plain, plain_elems, 1, &b_lo));
+	// low-order copy of the gathered tensor (the shared-memory operand)
+	CATTL3_CHECK(ensure_buffer(ctx, &ctx->lo_buf, &ctx->lo_bytes, (size_t) src_elems * 4));
+	float* src_lo = (float*) ctx->lo_buf;
+	split_lo_kernel<<<ew_grid(ctx, src_elems / 4 + 1, 256), 256, 0, ctx->stream>>>(src_elems, src, src_lo);
+	CATTL3_LAUNCHED(ctx);
 
-	CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
-	{
-		cuuint64_t dims[4] = { (cuuint64_t) gg.N, (cuuint64_t) gg.SH, (cuuint64_t) gg.SW, (cuuint64_t) gg.SC };
-		cuuint64_t str[3] = { (cuuint64_t) gg.N * 4, (cuuint64_t) gg.N * gg.SH * 4, (cuuint64_t) gg.N * gg.SH * gg.SW * 4 };
-		cuuint32_t box[4] = { 32, 1, 1, (cuuint32_t) RB };
-		CATTL3_CHECK(encode_map(&tm_a_hi, src, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
-		CATTL3_CHECK(encode_map(&tm_a_lo, a_lo, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
-	}
+	CUtensorMap tm_a, tm_b_hi, tm_b_lo;
 	{
 		cuuint64_t dims[2] = { (cuuint64_t) M, (cuuint64_t) gg.J };
 		cuuint64_t str[1] = { (cuuint64_t) M * 4 };
-		cuuint32_t box[2] = { 32, (cuuint32_t) BN };
-		CATTL3_CHECK(encode_map(&tm_b_hi, plain, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
-		CATTL3_CHECK(encode_map(&tm_b_lo, b_lo, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+		cuuint32_t box[2] = { (cuuint32_t) WG_KB, (cuuint32_t) TC_BM };
+		CATTL3_CHECK(encode_map(&tm_a, plain, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B));
+	}
+	{
+		cuuint64_t dims[4] = { (cuuint64_t) gg.N, (cuuint64_t) gg.SH, (cuuint64_t) gg.SW, (cuuint64_t) gg.SC };
+		cuuint64_t str[3] = { (cuuint64_t) gg.N * 4, (cuuint64_t) gg.N * gg.SH * 4, (cuuint64_t) gg.N * gg.SH * gg.SW * 4 };
+		cuuint32_t box[4] = { (cuuint32_t) WG_KB, 1, 1, (cuuint32_t) RB };
+		CATTL3_CHECK(encode_map(&tm_b_hi, src, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B));
+		CATTL3_CHECK(encode_map(&tm_b_lo, src_lo, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B));
 	}
 
 	TcWgradParams p;
 	p.N = gg.N; p.OH = gg.OH; p.OW = gg.OW; p.R = gg.SC; p.J = gg.J; p.RH = gg.RH; p.RW = gg.RW;
 	p.ah = gg.ah; p.bh = gg.bh; p.ch = gg.ch; p.aw = gg.aw; p.bw = gg.bw; p.cw = gg.cw;
-	p.RB = RB; p.rchunks = r_pad / RB; p.row_blocks = T * p.rchunks;
-	p.row_tiles = (p.row_blocks * RB + 127) / 128;
-	p.j_tiles = (gg.J + BN - 1) / BN;
-	p.mgroups = M / 32;
-	const int tiles = p.row_tiles * p.j_tiles;
+	p.RB = RB; p.rchunks = r_pad / RB; p.boxes = T * p.rchunks;
+	// two accumulators of <= 192 columns + four A stages of 32 columns = 512 TMEM columns
+	const int max_boxes = 192 / RB;
+	p.col_tiles = (p.boxes + max_boxes - 1) / max_boxes;
+	p.boxes_per_tile = (p.boxes + p.col_tiles - 1) / p.col_tiles;  // balanced: 9 boxes of 64 -> 3 tiles of 192 columns
+	p.col_tiles = (p.boxes + p.boxes_per_tile - 1) / p.boxes_per_tile;
+	p.BNW = p.boxes_per_tile * RB;
+	p.j_tiles = (gg.J + TC_BM - 1) / TC_BM;
+	p.mgroups = M / WG_KB;
+	const int tiles = p.col_tiles * p.j_tiles;
 	long long splits = ctx->sm_count / tiles;
 	if (splits < 1) splits = 1;
 	if (splits > p.mgroups) splits = p.mgroups;
 	p.mg_per_split = ceil_div(p.mgroups, splits);
 	p.splits = (int) ceil_div(p.mgroups, p.mg_per_split);
-	p.BN = BN;
-	const int stage_bytes = 2 * TC_A_BYTES + 2 * BN * 128;
-	int stages = (227 * 1024 - 2048) / stage_bytes;
-	if (stages > 6) stages = 6;
+	const int stage_bytes = TC_BM * WG_KB * 4 + 2 * p.BNW * WG_KB * 4;
+	int stages = TC_SMEM_LIMIT / stage_bytes;
+	const int tmem_stages = (512 - 2 * p.BNW) / (2 * WG_KB);
+	if (stages > tmem_stages) stages = tmem_stages;
+	if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
 	p.stages = stages;
-	int cols = 32;
-	while (cols < 2 * BN) cols <<= 1;
-	p.tmem_cols = cols;
-	p.flush = 32;
+	p.flush = 64;
 	p.w_stap = gg.w_stap; p.w_sr = gg.w_sr; p.w_sj = gg.w_sj;
 	p.dw_elems = (long long) T * gg.SC * gg.J;
-	CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, (size_t) p.splits * tiles * BN * 128 * 4));
+	CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, (size_t) p.splits * tiles * p.BNW * 128 * 4));
 	p.partial = (float*) ctx->ws;
-	const size_t smem_bytes = (size_t) stages * stage_bytes + 1024 + 256;
+	size_t smem_bytes = (size_t) stages * stage_bytes + 1024 + 512;
+	if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
 	CATTL3_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-	tc_wgrad_kernel<<<tiles * p.splits, 192, smem_bytes, ctx->stream>>>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, p);
+	tc_wgrad_kernel<<<tiles * p.splits, TC_THREADS, smem_bytes, ctx->stream>>>(tm_a, tm_b_hi, tm_b_lo, p);
 	CATTL3_LAUNCHED(ctx);
 	wgrad_reduce_tc_kernel<<<ew_grid(ctx, p.dw_elems, 256), 256, 0, ctx->stream>>>(p, T, dw);
 	CATTL3_LAUNCHED(ctx);
