@@ -255,7 +255,6 @@ int cattl3_ctx_destroy(cattl3_ctx* ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->ws) cudaFree(ctx->ws);
 	if (ctx->tc_w) cudaFree(ctx->tc_w);
-	if (ctx->lo_buf) cudaFree(ctx->lo_buf);
 	for (int i = 0; i < 3; ++i)
 		if (ctx->stage_dev[i]) cudaFree(ctx->stage_dev[i]);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

@@ -19,12 +19,9 @@ struct cattl3_ctx {
 	// general scratch (split-K partials, batch-norm partial sums); grown on demand, never shrunk
 	void* ws = nullptr;
 	size_t ws_bytes = 0;
-	// tcgen05 path scratch: the weights repacked K-major and split hi | lo for TMA, and the low-order copy
-	// of the gathered tensor for the weight gradient
+	// tcgen05 path scratch: the weights repacked K-major and split hi | lo for TMA
 	void* tc_w = nullptr;
 	size_t tc_w_bytes = 0;
-	void* lo_buf = nullptr;
-	size_t lo_bytes = 0;
 	// pinned staging for the *_host entry points
 	void* stage_dev[3] = { nullptr, nullptr, nullptr };
 	size_t stage_dev_bytes[3] = { 0, 0, 0 };

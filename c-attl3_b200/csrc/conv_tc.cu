@@ -169,8 +169,8 @@ __device__ __forceinline__ uint32_t tf32_lo_bits(float v) {
 	return __float_as_uint(r) + 0x1000u;
 }
 
-// The operand that stays in shared memory is split once in HBM: weights for the gather GEMM (repacked
-// K-major as [part][tap][j_pad][r_pad], r contiguous, zero padded; part 0 = hi, 1 = lo) ...
+// The weights of the gather GEMM -- its shared-memory operand -- are split once in HBM while being repacked
+// K-major as [part][tap][j_pad][r_pad] (r contiguous, zero padded; part 0 = hi, 1 = lo).
 __global__ void __launch_bounds__(256) pack_weights_kernel(GatherGeom gg, int r_pad, int j_pad, const float* __restrict__ w,
 		float* __restrict__ packed) {
 	const int T = gg.RH * gg.RW;
@@ -185,20 +185,6 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(GatherGeom gg, int r_
 		packed[total + i] = __uint_as_float(tf32_lo_bits(v));
 	}
 }
-// ... and the gathered activations for the weight gradient (only their low part needs a copy).
-__global__ void __launch_bounds__(256) split_lo_kernel(long long count, const float* __restrict__ x, float* __restrict__ lo) {
-	const long long nvec = count >> 2;
-	const long long stride = (long long) gridDim.x * 256;
-	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < nvec; i += stride) {
-		float4 v = reinterpret_cast<const float4*>(x)[i];
-		v.x = __uint_as_float(tf32_lo_bits(v.x)); v.y = __uint_as_float(tf32_lo_bits(v.y));
-		v.z = __uint_as_float(tf32_lo_bits(v.z)); v.w = __uint_as_float(tf32_lo_bits(v.w));
-		reinterpret_cast<float4*>(lo)[i] = v;
-	}
-	for (long long i = (nvec << 2) + blockIdx.x * 256ll + threadIdx.x; i < count; i += stride)
-		lo[i] = __uint_as_float(tf32_lo_bits(x[i]));
-}
-
 // ---- pipeline shared by the two kernels ------------------------------------------------------------------
 // Shared memory is the scarce resource: measured on B200, the TMA writes, the converters' reads and writes
 // and the tensor core's operand reads of one SM together sustain ~95 B/clk (profiles/README.md), while one
@@ -564,15 +550,18 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 // ---- the weight-gradient kernel ---------------------------------------------------------------------
 // dw(tap, r, j) += sum_m src(m, tap, r) * plain(m, j): a GEMM whose reduction runs over m = N*OH*OW, so m
 // is the K dimension and both operands are K-major where they lie (m is contiguous in HBM for both).
-//   A (tensor memory, 128 rows = output channels j): one 2-D TMA box [16 m][128 j] of the plain tensor
-//     (dY: the big one, read once), split by the converters;
-//   B (shared memory, up to 192 rows = (tap, channel) pairs): per tap one box [16 m][RB channels] of the
-//     gathered tensor at that tap's coordinate, from the raw tensor (hi: the tensor core truncates) and from
-//     its low-order copy made by split_lo_kernel.
-// One k-block = 16 consecutive batch entries of one pixel.  Each CTA owns one (j tile, column tile) and one
-// contiguous range of k-blocks (split-K); the fp32 partial tile goes to scratch and wgrad_reduce_tc_kernel
-// adds the partials to dw in split order (deterministic, accumulating: Parameters::accumulate_grad,
-// C-ATTL3/parameters/StandardParameters.hpp:115-123).
+//   A (tensor memory, 128 rows = output channels j): one 2-D TMA box [32 m][128 j] of the plain tensor
+//     (dY), split hi / lo into TMEM by the converter warps;
+//   B (shared memory, up to 192 rows = (tap, channel) pairs): per tap one box [32 m][RB channels] of the
+//     gathered tensor at that tap's coordinate.  The tensor core truncates the raw tile itself (= hi); the
+//     converters write the lo tile next to it (element-wise, so the swizzled layout is preserved).
+// One k-block = 32 consecutive batch entries of one pixel.  What limits this kernel is the NUMBER OF TMA ROWS:
+// every row of either operand lies in a different 2 MB page (the channel stride is N*H*W*4 bytes), and the
+// TMA unit sustains only ~1 such row per 6-8 clocks (measured; profiles/README.md).  Hence raw-only loads
+// (no second, pre-split copy of an operand) and 128-byte rows.
+// Each CTA owns one (j tile, column tile) and one contiguous range of k-blocks (split-K); the fp32 partial
+// tile goes to scratch and wgrad_reduce_tc_kernel adds the partials to dw in split order (deterministic,
+// accumulating: Parameters::accumulate_grad, C-ATTL3/parameters/StandardParameters.hpp:115-123).
 struct TcWgradParams {
 	int N, OH, OW, R, J, RH, RW;
 	int ah, bh, ch, aw, bw, cw;
@@ -580,7 +569,7 @@ struct TcWgradParams {
 	int rchunks;       // r_pad / RB
 	int boxes;         // T * rchunks
 	int boxes_per_tile, col_tiles, j_tiles, splits;
-	int BNW;           // boxes_per_tile * RB: columns of the accumulator
+	int BNW;           // boxes_per_tile * RB: columns of the accumulator (<= 192)
 	long long mgroups, mg_per_split;
 	int stages;
 	int flush;         // k-blocks accumulated in TMEM before the partial tile is folded into fp32 scratch
@@ -590,14 +579,16 @@ struct TcWgradParams {
 
 // Tensor-core accumulation truncates (round-toward-zero) at every MMA, so a reduction of n MMA steps
 // carries a bias of ~n * 2^-24 relative (measured: 2e-4 on the 10^4-step config-2 weight gradient).
-// The kernel therefore closes a TMEM accumulator every `flush` k-blocks; the epilogue warps fold it
-// into a CTA-private fp32 tile with round-to-nearest adds while the MMA warp fills the other accumulator.
-constexpr int WG_KB = 16;
+// The kernel therefore closes the TMEM accumulator every `flush` k-blocks and the epilogue warps fold it
+// into a CTA-private fp32 tile with round-to-nearest adds (TMA and the converters keep filling the stages
+// meanwhile; the MMA warp idles for the few thousand clocks of the drain, ~4 % of a flush period).
+constexpr int WG_KB = 32;
+constexpr uint32_t WG_A_COL0 = 256;   // TMEM: accumulator in columns [0, 192], A stages from column 256
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a,
-		const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo, const TcWgradParams p) {
+		const __grid_constant__ CUtensorMap tm_b, const TcWgradParams p) {
 	extern __shared__ __align__(1024) uint8_t smem_raw[];
 	uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
-	constexpr int A_BYTES = TC_BM * WG_KB * 4;  // 8 KB
+	constexpr int A_BYTES = TC_BM * WG_KB * 4;  // 16 KB
 	const int b_bytes = p.BNW * WG_KB * 4;
 	const int stage_bytes = A_BYTES + 2 * b_bytes;
 	uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t) p.stages * stage_bytes);
@@ -620,12 +611,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 	if (mg1 > p.mgroups) mg1 = p.mgroups;
 	const long long kblocks = mg1 > mg0 ? mg1 - mg0 : 0;
 	const long long chunks = (kblocks + p.flush - 1) / p.flush;
-	const uint32_t a_col0 = (uint32_t) (2 * p.BNW);
 
 	if (warp == 0 && elect_one()) {
-		tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b_hi); tma_prefetch_desc(&tm_b_lo);
+		tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b);
 		for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
-		for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+		mbar_init(&acc_full[0], 1); mbar_init(&acc_empty[0], 4);
 		fence_barrier_init();
 	}
 	if (warp == 1) tmem_alloc(tmem_slot, 512u);
@@ -637,7 +627,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 	if (warp == 0) {
 		if (elect_one()) {
 			int s = 0; uint32_t ph = 0;
-			const uint32_t tx = (uint32_t) (A_BYTES + 2 * nboxes * p.RB * WG_KB * 4);
+			const uint32_t tx = (uint32_t) (A_BYTES + nboxes * p.RB * WG_KB * 4);
 			for (long long kb = 0; kb < kblocks; ++kb) {
 				const long long m = (mg0 + kb) * WG_KB;
 				const int n0 = (int) (m % p.N);
@@ -652,8 +642,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 					const int tap = box / p.rchunks, c0 = (box % p.rchunks) * p.RB;
 					const int rh = tap % p.RH, rw = tap / p.RH;
 					const int ih = oh * p.ah + rh * p.bh + p.ch, iw = ow * p.aw + rw * p.bw + p.cw;
-					tma_load_4d(st + A_BYTES + bx * p.RB * (WG_KB * 4), &tm_b_hi, &full[s], n0, ih, iw, c0);
-					tma_load_4d(st + A_BYTES + b_bytes + bx * p.RB * (WG_KB * 4), &tm_b_lo, &full[s], n0, ih, iw, c0);
+					tma_load_4d(st + A_BYTES + bx * p.RB * (WG_KB * 4), &tm_b, &full[s], n0, ih, iw, c0);
 				}
 				if (++s == p.stages) { s = 0; ph ^= 1; }
 			}
@@ -662,19 +651,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 		if (elect_one()) {
 			const uint32_t idesc = make_idesc_tf32(p.BNW);
 			int s = 0; uint32_t ph = 0;
-			int acc = 0; uint32_t acc_ph = 0;
+			uint32_t acc_ph = 0;
 			long long kb = 0;
 			for (long long c = 0; c < chunks; ++c) {
-				mbar_wait(&acc_empty[acc], acc_ph ^ 1);
+				mbar_wait(&acc_empty[0], acc_ph ^ 1);
 				tc_fence_after();
-				const uint32_t d = tmem_base + (uint32_t) (acc * p.BNW);
+				const uint32_t d = tmem_base;
 				const long long kend = kb + p.flush < kblocks ? kb + p.flush : kblocks;
 				for (bool first = true; kb < kend; ++kb) {
 					mbar_wait(&ready[s], ph);
 					tc_fence_after();
 					const uint32_t b_hi = smem_u32(smem + (size_t) s * stage_bytes + A_BYTES);
 					const uint32_t b_lo = b_hi + b_bytes;
-					const uint32_t a_hi = tmem_base + a_col0 + (uint32_t) (s * 2 * WG_KB);
+					const uint32_t a_hi = tmem_base + WG_A_COL0 + (uint32_t) (s * 2 * WG_KB);
 					const uint32_t a_lo = a_hi + WG_KB;
 					#pragma unroll
 					for (int pass = 0; pass < 3; ++pass) {
@@ -688,8 +677,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 					umma_commit(&empty[s]);
 					if (++s == p.stages) { s = 0; ph ^= 1; }
 				}
-				umma_commit(&acc_full[acc]);
-				if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+				umma_commit(&acc_full[0]);
+				acc_ph ^= 1;
 			}
 		}
 	} else if (warp < 6) {
@@ -699,11 +688,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 		if (chunks == 0) {
 			for (int c0 = 0; c0 < p.BNW; ++c0) dst[(long long) c0 * 128] = 0.f;
 		}
-		int acc = 0; uint32_t acc_ph = 0;
+		uint32_t acc_ph = 0;
 		for (long long c = 0; c < chunks; ++c) {
-			mbar_wait(&acc_full[acc], acc_ph);
+			mbar_wait(&acc_full[0], acc_ph);
 			tc_fence_after();
-			const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16) + (uint32_t) (acc * p.BNW);
+			const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16);
 			for (int c0 = 0; c0 < p.BNW; c0 += 16) {
 				float v[16];
 				tmem_ld_16(taddr + c0, v);
@@ -717,31 +706,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 			}
 			tc_fence_before();
 			__syncwarp();
-			if (lane == 0) mbar_arrive(&acc_empty[acc]);
-			if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+			if (lane == 0) mbar_arrive(&acc_empty[0]);
+			acc_ph ^= 1;
 		}
 	} else {
-		// converters: row (= output channel) 32q + lane of the dY tile, 16 m values = one 64 B row (SWIZZLE_64B)
+		// converters.  A: row (= output channel) 32q + lane of the dY tile is one 128 B row of 32 m values, its
+		// eight 16-byte chunks XOR-swizzled with the row index (SWIZZLE_128B) so that the 32 row-per-lane reads
+		// of a warp spread over all banks.  B: lo tile of the whole gathered operand, element-wise.
 		const int q = warp & 3;
 		const int row = 32 * q + lane;
+		const int tid = threadIdx.x - 192;
 		int s = 0; uint32_t ph = 0;
 		for (long long kb = 0; kb < kblocks; ++kb) {
 			mbar_wait(&full[s], ph);
-			const uint8_t* tile_a = smem + (size_t) s * stage_bytes;
-			const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16) + a_col0 + (uint32_t) (s * 2 * WG_KB);
-			uint32_t hi[16], lo[16];
+			uint8_t* st = smem + (size_t) s * stage_bytes;
+			const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16) + WG_A_COL0 + (uint32_t) (s * 2 * WG_KB);
 			#pragma unroll
-			for (int c = 0; c < 4; ++c) {
-				uint32_t off = (uint32_t) (row * 64 + c * 16);
-				off ^= ((off >> 7) & 3u) << 4;
-				const float4 v = *reinterpret_cast<const float4*>(tile_a + off);
-				hi[4 * c + 0] = tf32_hi_bits(v.x); lo[4 * c + 0] = tf32_lo_bits(v.x);
-				hi[4 * c + 1] = tf32_hi_bits(v.y); lo[4 * c + 1] = tf32_lo_bits(v.y);
-				hi[4 * c + 2] = tf32_hi_bits(v.z); lo[4 * c + 2] = tf32_lo_bits(v.z);
-				hi[4 * c + 3] = tf32_hi_bits(v.w); lo[4 * c + 3] = tf32_lo_bits(v.w);
+			for (int h = 0; h < 2; ++h) {
+				uint32_t hi[16], lo[16];
+				#pragma unroll
+				for (int c = 0; c < 4; ++c) {
+					const uint32_t off = (uint32_t) (row * 128 + (((4 * h + c) ^ (row & 7)) << 4));
+					const float4 v = *reinterpret_cast<const float4*>(st + off);
+					hi[4 * c + 0] = tf32_hi_bits(v.x); lo[4 * c + 0] = tf32_lo_bits(v.x);
+					hi[4 * c + 1] = tf32_hi_bits(v.y); lo[4 * c + 1] = tf32_lo_bits(v.y);
+					hi[4 * c + 2] = tf32_hi_bits(v.z); lo[4 * c + 2] = tf32_lo_bits(v.z);
+					hi[4 * c + 3] = tf32_hi_bits(v.w); lo[4 * c + 3] = tf32_lo_bits(v.w);
+				}
+				tmem_st_16(taddr + 16 * h, hi);
+				tmem_st_16(taddr + WG_KB + 16 * h, lo);
 			}
-			tmem_st_16(taddr, hi);
-			tmem_st_16(taddr + WG_KB, lo);
+			{
+				const float4* src = reinterpret_cast<const float4*>(st + A_BYTES);
+				float4* dst = reinterpret_cast<float4*>(st + A_BYTES + b_bytes);
+				#pragma unroll 4
+				for (int i = tid; i < (b_bytes >> 4); i += 128) {
+					float4 v = src[i];
+					v.x = __uint_as_float(tf32_lo_bits(v.x)); v.y = __uint_as_float(tf32_lo_bits(v.y));
+					v.z = __uint_as_float(tf32_lo_bits(v.z)); v.w = __uint_as_float(tf32_lo_bits(v.w));
+					dst[i] = v;
+				}
+			}
+			fence_proxy_async();  // the lo tile was written through the generic proxy; the MMA reads it through the async proxy
 			tmem_st_wait();
 			tc_fence_before();
 			mbar_arrive(&ready[s]);
@@ -786,34 +792,25 @@ int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const 
 	const int r_pad = round_up(gg.SC, 16);
 	const int RB = r_pad % 64 == 0 ? 64 : (r_pad % 32 == 0 ? 32 : 16);
 	const long long M = (long long) gg.N * gg.OH * gg.OW;
-	const long long src_elems = (long long) gg.N * gg.SH * gg.SW * gg.SC;
 
-	// low-order copy of the gathered tensor (the shared-memory operand)
-	CATTL3_CHECK(ensure_buffer(ctx, &ctx->lo_buf, &ctx->lo_bytes, (size_t) src_elems * 4));
-	float* src_lo = (float*) ctx->lo_buf;
-	split_lo_kernel<<<ew_grid(ctx, src_elems / 4 + 1, 256), 256, 0, ctx->stream>>>(src_elems, src, src_lo);
-	CATTL3_LAUNCHED(ctx);
-
-	CUtensorMap tm_a, tm_b_hi, tm_b_lo;
+	CUtensorMap tm_a, tm_b;
 	{
 		cuuint64_t dims[2] = { (cuuint64_t) M, (cuuint64_t) gg.J };
 		cuuint64_t str[1] = { (cuuint64_t) M * 4 };
 		cuuint32_t box[2] = { (cuuint32_t) WG_KB, (cuuint32_t) TC_BM };
-		CATTL3_CHECK(encode_map(&tm_a, plain, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B));
+		CATTL3_CHECK(encode_map(&tm_a, plain, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
 	}
 	{
 		cuuint64_t dims[4] = { (cuuint64_t) gg.N, (cuuint64_t) gg.SH, (cuuint64_t) gg.SW, (cuuint64_t) gg.SC };
 		cuuint64_t str[3] = { (cuuint64_t) gg.N * 4, (cuuint64_t) gg.N * gg.SH * 4, (cuuint64_t) gg.N * gg.SH * gg.SW * 4 };
 		cuuint32_t box[4] = { (cuuint32_t) WG_KB, 1, 1, (cuuint32_t) RB };
-		CATTL3_CHECK(encode_map(&tm_b_hi, src, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B));
-		CATTL3_CHECK(encode_map(&tm_b_lo, src_lo, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B));
+		CATTL3_CHECK(encode_map(&tm_b, src, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
 	}
 
 	TcWgradParams p;
 	p.N = gg.N; p.OH = gg.OH; p.OW = gg.OW; p.R = gg.SC; p.J = gg.J; p.RH = gg.RH; p.RW = gg.RW;
 	p.ah = gg.ah; p.bh = gg.bh; p.ch = gg.ch; p.aw = gg.aw; p.bw = gg.bw; p.cw = gg.cw;
 	p.RB = RB; p.rchunks = r_pad / RB; p.boxes = T * p.rchunks;
-	// two accumulators of <= 192 columns + four A stages of 32 columns = 512 TMEM columns
 	const int max_boxes = 192 / RB;
 	p.col_tiles = (p.boxes + max_boxes - 1) / max_boxes;
 	p.boxes_per_tile = (p.boxes + p.col_tiles - 1) / p.col_tiles;  // balanced: 9 boxes of 64 -> 3 tiles of 192 columns
@@ -829,11 +826,10 @@ int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const 
 	p.splits = (int) ceil_div(p.mgroups, p.mg_per_split);
 	const int stage_bytes = TC_BM * WG_KB * 4 + 2 * p.BNW * WG_KB * 4;
 	int stages = TC_SMEM_LIMIT / stage_bytes;
-	const int tmem_stages = (512 - 2 * p.BNW) / (2 * WG_KB);
+	const int tmem_stages = (512 - (int) WG_A_COL0) / (2 * WG_KB);
 	if (stages > tmem_stages) stages = tmem_stages;
-	if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
 	p.stages = stages;
-	p.flush = 64;
+	p.flush = 32;
 	p.w_stap = gg.w_stap; p.w_sr = gg.w_sr; p.w_sj = gg.w_sj;
 	p.dw_elems = (long long) T * gg.SC * gg.J;
 	CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, (size_t) p.splits * tiles * p.BNW * 128 * 4));
@@ -841,7 +837,7 @@ int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const 
 	size_t smem_bytes = (size_t) stages * stage_bytes + 1024 + 512;
 	if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
 	CATTL3_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-	tc_wgrad_kernel<<<tiles * p.splits, TC_THREADS, smem_bytes, ctx->stream>>>(tm_a, tm_b_hi, tm_b_lo, p);
+	tc_wgrad_kernel<<<tiles * p.splits, TC_THREADS, smem_bytes, ctx->stream>>>(tm_a, tm_b, p);
 	CATTL3_LAUNCHED(ctx);
 	wgrad_reduce_tc_kernel<<<ew_grid(ctx, p.dw_elems, 256), 256, 0, ctx->stream>>>(p, T, dw);
 	CATTL3_LAUNCHED(ctx);
