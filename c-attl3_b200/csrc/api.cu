@@ -103,11 +103,16 @@ static int run_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, 
 	return simt_gather_gemm<S>(ctx, gg, src, w, bias, bias_mode, out);
 }
 
+// db_colsum != null: the caller also wants db += column sums of `plain`; the tcgen05 kernel produces them from
+// the same read of `plain` (*db_done = true), otherwise the caller runs colsum_accumulate.
 template<typename S>
-static int run_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* plain, S* dw) {
+static int run_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* plain, S* dw, S* db_colsum = nullptr,
+		bool* db_done = nullptr) {
+	if (db_done) *db_done = false;
 	if (IsFloat<S>::value && ctx->conv_path != CATTL3_PATH_SIMT && tc_wgrad_supported(ctx, gg)) {
 		ctx->last_path = "tcgen05";
-		return tc_wgrad_f32(ctx, gg, (const float*) src, (const float*) plain, (float*) dw);
+		if (db_done) *db_done = db_colsum != nullptr;
+		return tc_wgrad_f32(ctx, gg, (const float*) src, (const float*) plain, (float*) dw, (float*) db_colsum);
 	}
 	if (ctx->conv_path == CATTL3_PATH_TCGEN05) {
 		set_error("tcgen05 weight-gradient path requested but the shape/type does not qualify");
@@ -140,9 +145,11 @@ static int conv_backward(cattl3_ctx* ctx, const cattl3_conv_geom* g, const S* x,
 	// dW += cols^T dY (ConvKernelLayer.hpp:154)
 	GatherGeom gw = fwd_gather(g->n, g->h, g->w, g->c, oh, ow, g->f, g);
 	gw.w_stap = 1; gw.w_sr = T; gw.w_sj = T * g->c;
-	CATTL3_CHECK(run_wgrad<S>(ctx, gw, x, dy, dw));
-	// db += colsum(dY) (:155)
-	CATTL3_CHECK(colsum_accumulate<S>(ctx, (int64_t) g->n * oh * ow, g->f, dy, db));
+	bool db_done = false;
+	CATTL3_CHECK(run_wgrad<S>(ctx, gw, x, dy, dw, db, &db_done));
+	// db += colsum(dY) (:155), unless the weight-gradient kernel already produced it from its own read of dY
+	if (!db_done)
+		CATTL3_CHECK(colsum_accumulate<S>(ctx, (int64_t) g->n * oh * ow, g->f, dy, db));
 	if (!dx)
 		return CATTL3_OK;  // input layer (:156-157)
 	// dX = crop(col2im(dY W^T)) (:159-188) as a gather over (tap, f)

@@ -97,6 +97,7 @@ bool tc_gather_gemm_supported(const cattl3_ctx* ctx, const GatherGeom& gg);
 int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const float* w,
 		const float* bias, int bias_mode, float* out);
 bool tc_wgrad_supported(const cattl3_ctx* ctx, const GatherGeom& gg);
-int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const float* plain, float* dw);
+// db != null: also accumulates the column sums of `plain` (the bias gradient of a convolution) into db.
+int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const float* plain, float* dw, float* db);
 
 } // namespace cattl3

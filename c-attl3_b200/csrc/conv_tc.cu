@@ -575,6 +575,7 @@ struct TcWgradParams {
 	int flush;         // k-blocks accumulated in TMEM before the partial tile is folded into fp32 scratch
 	long long w_stap, w_sr, w_sj, dw_elems;
 	float* partial;    // [split][tile][BNW columns][128 rows]
+	float* db_partial; // [split][j_tiles * 128] column sums of the plain tensor (bias gradient), or null
 };
 
 // Tensor-core accumulation truncates (round-toward-zero) at every MMA, so a reduction of n MMA steps
@@ -716,11 +717,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 		const int q = warp & 3;
 		const int row = 32 * q + lane;
 		const int tid = threadIdx.x - 192;
+		// the bias gradient db(j) = sum_m dY(m, j) falls out of the same read: every dY value passes through this
+		// thread's registers exactly once (in the CTAs of column tile 0)
+		const bool want_db = p.db_partial != nullptr && ct == 0;
+		float db_sum = 0.f;
 		int s = 0; uint32_t ph = 0;
 		for (long long kb = 0; kb < kblocks; ++kb) {
 			mbar_wait(&full[s], ph);
 			uint8_t* st = smem + (size_t) s * stage_bytes;
 			const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16) + WG_A_COL0 + (uint32_t) (s * 2 * WG_KB);
+			float blk_sum = 0.f;
 			#pragma unroll
 			for (int h = 0; h < 2; ++h) {
 				uint32_t hi[16], lo[16];
@@ -728,6 +734,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 				for (int c = 0; c < 4; ++c) {
 					const uint32_t off = (uint32_t) (row * 128 + (((4 * h + c) ^ (row & 7)) << 4));
 					const float4 v = *reinterpret_cast<const float4*>(st + off);
+					blk_sum += (v.x + v.y) + (v.z + v.w);
 					hi[4 * c + 0] = tf32_hi_bits(v.x); lo[4 * c + 0] = tf32_lo_bits(v.x);
 					hi[4 * c + 1] = tf32_hi_bits(v.y); lo[4 * c + 1] = tf32_lo_bits(v.y);
 					hi[4 * c + 2] = tf32_hi_bits(v.z); lo[4 * c + 2] = tf32_lo_bits(v.z);
@@ -747,12 +754,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 					dst[i] = v;
 				}
 			}
+			db_sum += blk_sum;
 			fence_proxy_async();  // the lo tile was written through the generic proxy; the MMA reads it through the async proxy
 			tmem_st_wait();
 			tc_fence_before();
 			mbar_arrive(&ready[s]);
 			if (++s == p.stages) { s = 0; ph ^= 1; }
 		}
+		if (want_db) p.db_partial[(long long) z * p.j_tiles * TC_BM + jt * TC_BM + row] = db_sum;
 	}
 	tc_fence_before();
 	__syncthreads();
@@ -760,9 +769,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 }
 
 // dw(tap, r, j) += sum over splits of the scratch tiles, in split order (deterministic).
-__global__ void __launch_bounds__(256) wgrad_reduce_tc_kernel(const TcWgradParams p, int T, float* __restrict__ dw) {
+__global__ void __launch_bounds__(256) wgrad_reduce_tc_kernel(const TcWgradParams p, int T, float* __restrict__ dw,
+		float* __restrict__ db) {
 	const long long total = (long long) T * p.R * p.J;
 	const int tiles = p.col_tiles * p.j_tiles;
+	if (db != nullptr && blockIdx.x == 0) {
+		for (int j = threadIdx.x; j < p.J; j += 256) {
+			float s = 0.f;
+			for (int z = 0; z < p.splits; ++z) s += p.db_partial[(long long) z * p.j_tiles * TC_BM + j];
+			db[j] += s;
+		}
+	}
 	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long) gridDim.x * 256) {
 		const int j = (int) (i % p.J);
 		const int r = (int) ((i / p.J) % p.R);
@@ -786,7 +803,7 @@ bool tc_wgrad_supported(const cattl3_ctx*, const GatherGeom& gg) {
 	return get_encode() != nullptr;
 }
 
-int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const float* plain, float* dw) {
+int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const float* plain, float* dw, float* db) {
 	CATTL3_REQUIRE(aligned16(src) && aligned16(plain), "tcgen05 path needs 16-byte aligned tensors");
 	const int T = gg.RH * gg.RW;
 	const int r_pad = round_up(gg.SC, 16);
@@ -832,14 +849,16 @@ int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const 
 	p.flush = 32;
 	p.w_stap = gg.w_stap; p.w_sr = gg.w_sr; p.w_sj = gg.w_sj;
 	p.dw_elems = (long long) T * gg.SC * gg.J;
-	CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, (size_t) p.splits * tiles * p.BNW * 128 * 4));
+	const size_t partial_elems = (size_t) p.splits * tiles * p.BNW * 128;
+	CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, (partial_elems + (size_t) p.splits * p.j_tiles * TC_BM) * 4));
 	p.partial = (float*) ctx->ws;
+	p.db_partial = db ? p.partial + partial_elems : nullptr;
 	size_t smem_bytes = (size_t) stages * stage_bytes + 1024 + 512;
 	if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
 	CATTL3_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 	tc_wgrad_kernel<<<tiles * p.splits, TC_THREADS, smem_bytes, ctx->stream>>>(tm_a, tm_b, p);
 	CATTL3_LAUNCHED(ctx);
-	wgrad_reduce_tc_kernel<<<ew_grid(ctx, p.dw_elems, 256), 256, 0, ctx->stream>>>(p, T, dw);
+	wgrad_reduce_tc_kernel<<<ew_grid(ctx, p.dw_elems, 256), 256, 0, ctx->stream>>>(p, T, dw, db);
 	CATTL3_LAUNCHED(ctx);
 	return CATTL3_OK;
 }
