@@ -241,3 +241,10 @@ def make_opt_step(kind, hyper, timestep, epoch, l2_lambda=0.0, reset_grad=True, 
     st.c2 = float(S(one / (1.0 - float(one - b) ** (timestep + 1) + float(eps))))
     st.l2_lambda = float(S(l2_lambda))
     return st
+
+
+def shard_rows(n, rank, world):
+    """Rows [lo, hi) of an n-row mini-batch that rank `rank` of `world` keeps -- the same split as
+    cattle::SGDOptimizer::shard (cattle/optimizer/SGDOptimizer.hpp): contiguous, covers every row once,
+    sizes differ by at most one."""
+    return n * rank // world, n * (rank + 1) // world
