@@ -73,6 +73,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, ui
 		"cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
 		:: "r"(smem_u32(dst)), "l"((uint64_t) tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// 16-byte asynchronous global -> shared copy (LDGSTS); src_bytes = 0 zero-fills the destination.
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src, uint32_t src_bytes) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
 	asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t) tm) : "memory");
 }
@@ -576,6 +582,8 @@ struct TcWgradParams {
 	long long w_stap, w_sr, w_sj, dw_elems;
 	float* partial;    // [split][tile][BNW columns][128 rows]
 	float* db_partial; // [split][j_tiles * 128] column sums of the plain tensor (bias gradient), or null
+	const float* plain;  // the A operand: M x J, m contiguous
+	long long M;
 };
 
 // Tensor-core accumulation truncates (round-toward-zero) at every MMA, so a reduction of n MMA steps
@@ -585,13 +593,13 @@ struct TcWgradParams {
 // meanwhile; the MMA warp idles for the few thousand clocks of the drain, ~4 % of a flush period).
 constexpr int WG_KB = 32;
 constexpr uint32_t WG_A_COL0 = 256;   // TMEM: accumulator in columns [0, 192], A stages from column 256
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_a,
-		const __grid_constant__ CUtensorMap tm_b, const TcWgradParams p) {
+constexpr int WG_RING = 4;             // k-blocks of dY in flight per converter warp (cp.async ring of 4 KB patches)
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_b,
+		const TcWgradParams p) {
 	extern __shared__ __align__(1024) uint8_t smem_raw[];
 	uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
-	constexpr int A_BYTES = TC_BM * WG_KB * 4;  // 16 KB
 	const int b_bytes = p.BNW * WG_KB * 4;
-	const int stage_bytes = A_BYTES + 2 * b_bytes;
+	const int stage_bytes = 2 * b_bytes;   // [B raw][B lo]; the A operand has its own cp.async ring
 	uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t) p.stages * stage_bytes);
 	uint64_t* full = bars;
 	uint64_t* ready = bars + TC_MAX_STAGES;
@@ -614,7 +622,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 	const long long chunks = (kblocks + p.flush - 1) / p.flush;
 
 	if (warp == 0 && elect_one()) {
-		tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b);
+		tma_prefetch_desc(&tm_b);
 		for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
 		mbar_init(&acc_full[0], 1); mbar_init(&acc_empty[0], 4);
 		fence_barrier_init();
@@ -628,7 +636,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 	if (warp == 0) {
 		if (elect_one()) {
 			int s = 0; uint32_t ph = 0;
-			const uint32_t tx = (uint32_t) (A_BYTES + nboxes * p.RB * WG_KB * 4);
+			const uint32_t tx = (uint32_t) (nboxes * p.RB * WG_KB * 4);
 			for (long long kb = 0; kb < kblocks; ++kb) {
 				const long long m = (mg0 + kb) * WG_KB;
 				const int n0 = (int) (m % p.N);
@@ -637,13 +645,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 				mbar_wait(&empty[s], ph ^ 1);
 				uint8_t* st = smem + (size_t) s * stage_bytes;
 				mbar_expect_tx(&full[s], tx);
-				tma_load_2d(st, &tm_a, &full[s], (int) m, jt * TC_BM);
 				for (int bx = 0; bx < nboxes; ++bx) {
 					const int box = box0 + bx;
 					const int tap = box / p.rchunks, c0 = (box % p.rchunks) * p.RB;
 					const int rh = tap % p.RH, rw = tap / p.RH;
 					const int ih = oh * p.ah + rh * p.bh + p.ch, iw = ow * p.aw + rw * p.bw + p.cw;
-					tma_load_4d(st + A_BYTES + bx * p.RB * (WG_KB * 4), &tm_b, &full[s], n0, ih, iw, c0);
+					tma_load_4d(st + bx * p.RB * (WG_KB * 4), &tm_b, &full[s], n0, ih, iw, c0);
 				}
 				if (++s == p.stages) { s = 0; ph ^= 1; }
 			}
@@ -662,7 +669,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 				for (bool first = true; kb < kend; ++kb) {
 					mbar_wait(&ready[s], ph);
 					tc_fence_after();
-					const uint32_t b_hi = smem_u32(smem + (size_t) s * stage_bytes + A_BYTES);
+					const uint32_t b_hi = smem_u32(smem + (size_t) s * stage_bytes);
 					const uint32_t b_lo = b_hi + b_bytes;
 					const uint32_t a_hi = tmem_base + WG_A_COL0 + (uint32_t) (s * 2 * WG_KB);
 					const uint32_t a_lo = a_hi + WG_KB;
@@ -711,19 +718,63 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 			acc_ph ^= 1;
 		}
 	} else {
-		// converters.  A: row (= output channel) 32q + lane of the dY tile is one 128 B row of 32 m values, its
-		// eight 16-byte chunks XOR-swizzled with the row index (SWIZZLE_128B) so that the 32 row-per-lane reads
-		// of a warp spread over all banks.  B: lo tile of the whole gathered operand, element-wise.
+		// converters.  A (dY): each warp owns 32 rows (= output channels) of the tile.  A k-block of a row is 128
+		// contiguous bytes in HBM.  TMA pays 6-9 clocks for every such row (each lies in another 2 MB page), so the
+		// warp fetches its rows itself with 16-byte cp.async copies -- eight lanes per row, four whole 128-byte
+		// lines per instruction, WG_RING k-blocks in flight -- into a private ring of 4 KB patches whose 16-byte
+		// chunks are XOR-swizzled with the row so that the later one-row-per-lane read is conflict free.  The values
+		// are split and stored to TMEM with tcgen05.st.
+		// B: lo tile of the gathered operand, element-wise in shared memory.
 		const int q = warp & 3;
 		const int row = 32 * q + lane;
 		const int tid = threadIdx.x - 192;
+		uint8_t* ring = smem + (size_t) p.stages * stage_bytes + 512 + q * (WG_RING * 4096);
+		const int lrow = lane >> 3, lchunk = lane & 7;   // this lane copies chunk lchunk of rows lrow, lrow + 4, ...
+		const float* a_src[8];
+		uint32_t a_dst[8], a_bytes[8];
+		#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			const int r = 4 * i + lrow;
+			const int j = jt * TC_BM + 32 * q + r;
+			a_bytes[i] = j < p.J ? 16u : 0u;   // rows past the last output channel are zero filled
+			a_src[i] = p.plain + (long long) (j < p.J ? j : 0) * p.M + mg0 * WG_KB + 4 * lchunk;
+			a_dst[i] = (uint32_t) (r * 128 + ((lchunk ^ (r & 7)) << 4));
+		}
+		#pragma unroll
+		for (int d = 0; d < WG_RING - 1; ++d) {
+			if (d < kblocks) {
+				#pragma unroll
+				for (int i = 0; i < 8; ++i) cp_async_16(ring + d * 4096 + a_dst[i], a_src[i] + (long long) d * WG_KB, a_bytes[i]);
+			}
+			cp_async_commit();
+		}
 		// the bias gradient db(j) = sum_m dY(m, j) falls out of the same read: every dY value passes through this
 		// thread's registers exactly once (in the CTAs of column tile 0)
 		const bool want_db = p.db_partial != nullptr && ct == 0;
 		float db_sum = 0.f;
 		int s = 0; uint32_t ph = 0;
+		int slot = 0;
 		for (long long kb = 0; kb < kblocks; ++kb) {
-			mbar_wait(&full[s], ph);
+			{
+				// refill the slot read in the previous iteration with k-block kb + WG_RING - 1
+				const long long nk = kb + WG_RING - 1;
+				const int nslot = slot == 0 ? WG_RING - 1 : slot - 1;
+				if (nk < kblocks) {
+					#pragma unroll
+					for (int i = 0; i < 8; ++i) cp_async_16(ring + nslot * 4096 + a_dst[i], a_src[i] + nk * WG_KB, a_bytes[i]);
+				}
+				cp_async_commit();
+			}
+			cp_async_wait<WG_RING - 1>();   // this thread's copies of k-block kb have landed ...
+			__syncwarp();                   // ... and so have the other lanes'
+			const uint8_t* patch = ring + slot * 4096;
+			float4 mine[8];
+			#pragma unroll
+			for (int c = 0; c < 8; ++c)
+				mine[c] = *reinterpret_cast<const float4*>(patch + lane * 128 + ((c ^ (lane & 7)) << 4));
+			__syncwarp();
+			if (++slot == WG_RING) slot = 0;
+			mbar_wait(&full[s], ph);   // B landed; the producer saw empty[s], so TMEM slot s is free as well
 			uint8_t* st = smem + (size_t) s * stage_bytes;
 			const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16) + WG_A_COL0 + (uint32_t) (s * 2 * WG_KB);
 			float blk_sum = 0.f;
@@ -732,8 +783,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 				uint32_t hi[16], lo[16];
 				#pragma unroll
 				for (int c = 0; c < 4; ++c) {
-					const uint32_t off = (uint32_t) (row * 128 + (((4 * h + c) ^ (row & 7)) << 4));
-					const float4 v = *reinterpret_cast<const float4*>(st + off);
+					const float4 v = mine[4 * h + c];
 					blk_sum += (v.x + v.y) + (v.z + v.w);
 					hi[4 * c + 0] = tf32_hi_bits(v.x); lo[4 * c + 0] = tf32_lo_bits(v.x);
 					hi[4 * c + 1] = tf32_hi_bits(v.y); lo[4 * c + 1] = tf32_lo_bits(v.y);
@@ -744,8 +794,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 				tmem_st_16(taddr + WG_KB + 16 * h, lo);
 			}
 			{
-				const float4* src = reinterpret_cast<const float4*>(st + A_BYTES);
-				float4* dst = reinterpret_cast<float4*>(st + A_BYTES + b_bytes);
+				const float4* src = reinterpret_cast<const float4*>(st);
+				float4* dst = reinterpret_cast<float4*>(st + b_bytes);
 				#pragma unroll 4
 				for (int i = tid; i < (b_bytes >> 4); i += 128) {
 					float4 v = src[i];
@@ -810,13 +860,7 @@ int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const 
 	const int RB = r_pad % 64 == 0 ? 64 : (r_pad % 32 == 0 ? 32 : 16);
 	const long long M = (long long) gg.N * gg.OH * gg.OW;
 
-	CUtensorMap tm_a, tm_b;
-	{
-		cuuint64_t dims[2] = { (cuuint64_t) M, (cuuint64_t) gg.J };
-		cuuint64_t str[1] = { (cuuint64_t) M * 4 };
-		cuuint32_t box[2] = { (cuuint32_t) WG_KB, (cuuint32_t) TC_BM };
-		CATTL3_CHECK(encode_map(&tm_a, plain, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
-	}
+	CUtensorMap tm_b;
 	{
 		cuuint64_t dims[4] = { (cuuint64_t) gg.N, (cuuint64_t) gg.SH, (cuuint64_t) gg.SW, (cuuint64_t) gg.SC };
 		cuuint64_t str[3] = { (cuuint64_t) gg.N * 4, (cuuint64_t) gg.N * gg.SH * 4, (cuuint64_t) gg.N * gg.SH * gg.SW * 4 };
@@ -841,8 +885,9 @@ int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const 
 	if (splits > p.mgroups) splits = p.mgroups;
 	p.mg_per_split = ceil_div(p.mgroups, splits);
 	p.splits = (int) ceil_div(p.mgroups, p.mg_per_split);
-	const int stage_bytes = TC_BM * WG_KB * 4 + 2 * p.BNW * WG_KB * 4;
-	int stages = TC_SMEM_LIMIT / stage_bytes;
+	const int ring_bytes = 4 * WG_RING * 4096;   // the converters' dY rings
+	const int stage_bytes = 2 * p.BNW * WG_KB * 4;
+	int stages = (TC_SMEM_LIMIT - ring_bytes) / stage_bytes;
 	const int tmem_stages = (512 - (int) WG_A_COL0) / (2 * WG_KB);
 	if (stages > tmem_stages) stages = tmem_stages;
 	p.stages = stages;
@@ -853,10 +898,11 @@ int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const 
 	CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, (partial_elems + (size_t) p.splits * p.j_tiles * TC_BM) * 4));
 	p.partial = (float*) ctx->ws;
 	p.db_partial = db ? p.partial + partial_elems : nullptr;
-	size_t smem_bytes = (size_t) stages * stage_bytes + 1024 + 512;
+	p.plain = plain; p.M = M;
+	size_t smem_bytes = (size_t) stages * stage_bytes + 1024 + 512 + ring_bytes;
 	if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
 	CATTL3_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-	tc_wgrad_kernel<<<tiles * p.splits, TC_THREADS, smem_bytes, ctx->stream>>>(tm_a, tm_b, p);
+	tc_wgrad_kernel<<<tiles * p.splits, TC_THREADS, smem_bytes, ctx->stream>>>(tm_b, p);
 	CATTL3_LAUNCHED(ctx);
 	wgrad_reduce_tc_kernel<<<ew_grid(ctx, p.dw_elems, 256), 256, 0, ctx->stream>>>(p, T, dw, db);
 	CATTL3_LAUNCHED(ctx);
