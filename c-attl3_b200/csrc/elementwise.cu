@@ -178,67 +178,165 @@ template<typename S> __device__ __forceinline__ S lowest();
 template<> __device__ __forceinline__ float lowest<float>() { return -3.402823466e+38f; }
 template<> __device__ __forceinline__ double lowest<double>() { return -1.7976931348623157e+308; }
 
-template<typename S, int KIND>
-__global__ void __launch_bounds__(256) pool_fwd_kernel(cattl3_pool_geom g, int OH, int OW,
+// Thread mapping shared by the two pooling kernels: the batch index n is the fastest dimension, so a thread owns
+// G consecutive batch entries (one 16-byte vector; G = 1 when n or the alignment forbids it) of one
+// (pixel, channel) row.  tv threads cover a row, 256 / tv rows share a CTA; the (h, w, c) decomposition of the row
+// index is 32-bit and paid once per row, not per element.
+template<typename S, bool VEC> struct PoolVec { typedef typename V16<S>::type type; static constexpr int G = V16<S>::G; };
+template<typename S> struct PoolVec<S, false> { typedef S type; static constexpr int G = 1; };
+template<int G> struct ByteVec;
+template<> struct ByteVec<1> { typedef uint8_t type; };
+template<> struct ByteVec<2> { typedef uchar2 type; };
+template<> struct ByteVec<4> { typedef uchar4 type; };
+
+template<typename S, int KIND, bool VEC>
+__global__ void __launch_bounds__(256) pool_fwd_kernel(cattl3_pool_geom g, int OH, int OW, int tv,
 		const S* __restrict__ x, S* __restrict__ y, uint8_t* __restrict__ argmax) {
-	const long long total = (long long) g.n * OH * OW * g.c;
-	for (long long o = blockIdx.x * 256ll + threadIdx.x; o < total; o += (long long) gridDim.x * 256) {
-		const int n = (int) (o % g.n);
-		long long t = o / g.n;
-		const int oh = (int) (t % OH); t /= OH;
-		const int ow = (int) (t % OW);
-		const int c = (int) (t / OW);
-		const S* base = x + n + (long long) g.n * (oh * g.sh + (long long) g.h * (ow * g.sw + (long long) g.w * c));
-		if (KIND == CATTL3_POOL_MAX) {
-			S best = lowest<S>();
-			int bi = 0;
+	typedef typename PoolVec<S, VEC>::type V;
+	constexpr int G = PoolVec<S, VEC>::G;
+	typedef typename ByteVec<G>::type BV;
+	const int nv = g.n / G;
+	const int rows_per_cta = 256 / tv;
+	const int v0 = threadIdx.x % tv, rsub = threadIdx.x / tv;
+	if (rsub >= rows_per_cta) return;
+	const unsigned rows = (unsigned) OH * OW * g.c;
+	for (unsigned r = blockIdx.x * rows_per_cta + rsub; r < rows; r += gridDim.x * rows_per_cta) {
+		const unsigned oh = r % OH, t = r / OH;
+		const unsigned ow = t % OW, c = t / OW;
+		const S* base = x + (long long) g.n * (oh * g.sh + (long long) g.h * (ow * g.sw + (long long) g.w * c));
+		for (int v = v0; v < nv; v += tv) {
+			__align__(16) S best[G];
+			__align__(4) uint8_t bi[G];
+			#pragma unroll
+			for (int e = 0; e < G; ++e) { best[e] = KIND == CATTL3_POOL_MAX ? lowest<S>() : (S) 0; bi[e] = 0; }
 			for (int k = 0; k < g.rw; ++k)
 				for (int l = 0; l < g.rh; ++l) {
-					const S v = base[(long long) g.n * (l + (long long) g.h * k)];
-					if (v > best) { best = v; bi = k * g.rh + l; }
+					const V vv = *reinterpret_cast<const V*>(base + (long long) g.n * (l + (long long) g.h * k) + v * G);
+					const S* ev = reinterpret_cast<const S*>(&vv);
+					#pragma unroll
+					for (int e = 0; e < G; ++e) {
+						if (KIND == CATTL3_POOL_MAX) {
+							if (ev[e] > best[e]) { best[e] = ev[e]; bi[e] = (uint8_t) (k * g.rh + l); }
+						} else {
+							best[e] += ev[e];
+						}
+					}
 				}
-			y[o] = best;
-			if (argmax) argmax[o] = (uint8_t) bi;
-		} else {
-			S s = 0;
-			for (int k = 0; k < g.rw; ++k)
-				for (int l = 0; l < g.rh; ++l)
-					s += base[(long long) g.n * (l + (long long) g.h * k)];
-			y[o] = s / (S) (g.rh * g.rw);
+			if (KIND == CATTL3_POOL_MEAN) {
+				#pragma unroll
+				for (int e = 0; e < G; ++e) best[e] = best[e] / (S) (g.rh * g.rw);
+			}
+			const long long o = (long long) g.n * r + v * G;
+			*reinterpret_cast<V*>(y + o) = *reinterpret_cast<const V*>(best);
+			if (KIND == CATTL3_POOL_MAX && argmax) *reinterpret_cast<BV*>(argmax + o) = *reinterpret_cast<const BV*>(bi);
 		}
 	}
 }
 
-// Gather form of PoolLayer::_pass_back (PoolLayer.hpp:98-116): one thread per INPUT element sums
-// the contributions of every window that covers it (overlapping windows accumulate), no atomics.
-template<typename S, int KIND>
-__global__ void __launch_bounds__(256) pool_bwd_kernel(cattl3_pool_geom g, int OH, int OW,
+// Gather form of PoolLayer::_pass_back (PoolLayer.hpp:98-116): a thread owns G batch entries of one INPUT
+// (pixel, channel) row and sums the contributions of every window that covers it (overlapping windows
+// accumulate), no atomics.
+template<typename S, int KIND, bool VEC>
+__global__ void __launch_bounds__(256) pool_bwd_kernel(cattl3_pool_geom g, int OH, int OW, int tv,
 		const S* __restrict__ dy, const uint8_t* __restrict__ argmax, S* __restrict__ dx) {
-	const long long total = (long long) g.n * g.h * g.w * g.c;
+	typedef typename PoolVec<S, VEC>::type V;
+	constexpr int G = PoolVec<S, VEC>::G;
+	typedef typename ByteVec<G>::type BV;
+	const int nv = g.n / G;
+	const int rows_per_cta = 256 / tv;
+	const int v0 = threadIdx.x % tv, rsub = threadIdx.x / tv;
+	if (rsub >= rows_per_cta) return;
+	const unsigned rows = (unsigned) g.h * g.w * g.c;
 	const S inv_area = (S) 1 / (S) (g.rh * g.rw);
-	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long) gridDim.x * 256) {
-		const int n = (int) (i % g.n);
-		long long t = i / g.n;
-		const int h = (int) (t % g.h); t /= g.h;
-		const int w = (int) (t % g.w);
-		const int c = (int) (t / g.w);
+	for (unsigned r = blockIdx.x * rows_per_cta + rsub; r < rows; r += gridDim.x * rows_per_cta) {
+		const int h = (int) (r % g.h);
+		const unsigned t = r / g.h;
+		const int w = (int) (t % g.w), c = (int) (t / g.w);
 		int oh_lo = h - g.rh + 1; oh_lo = oh_lo <= 0 ? 0 : (oh_lo + g.sh - 1) / g.sh;
 		int ow_lo = w - g.rw + 1; ow_lo = ow_lo <= 0 ? 0 : (ow_lo + g.sw - 1) / g.sw;
 		int oh_hi = h / g.sh; if (oh_hi > OH - 1) oh_hi = OH - 1;
 		int ow_hi = w / g.sw; if (ow_hi > OW - 1) ow_hi = OW - 1;
-		S s = 0;
-		for (int ow = ow_lo; ow <= ow_hi; ++ow)
-			for (int oh = oh_lo; oh <= oh_hi; ++oh) {
-				const long long o = n + (long long) g.n * (oh + (long long) OH * (ow + (long long) OW * c));
-				if (KIND == CATTL3_POOL_MAX) {
-					const int idx = (w - ow * g.sw) * g.rh + (h - oh * g.sh);
-					if ((int) argmax[o] == idx) s += dy[o];
-				} else {
-					s += dy[o] * inv_area;
+		for (int v = v0; v < nv; v += tv) {
+			__align__(16) S s[G];
+			#pragma unroll
+			for (int e = 0; e < G; ++e) s[e] = (S) 0;
+			for (int ow = ow_lo; ow <= ow_hi; ++ow)
+				for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+					const long long o = (long long) g.n * (oh + (long long) OH * (ow + (long long) OW * c)) + v * G;
+					const V vg = *reinterpret_cast<const V*>(dy + o);
+					const S* eg = reinterpret_cast<const S*>(&vg);
+					if (KIND == CATTL3_POOL_MAX) {
+						const int idx = (w - ow * g.sw) * g.rh + (h - oh * g.sh);
+						const BV vb = *reinterpret_cast<const BV*>(argmax + o);
+						const uint8_t* eb = reinterpret_cast<const uint8_t*>(&vb);
+						#pragma unroll
+						for (int e = 0; e < G; ++e) if ((int) eb[e] == idx) s[e] += eg[e];
+					} else {
+						#pragma unroll
+						for (int e = 0; e < G; ++e) s[e] += eg[e] * inv_area;
+					}
 				}
-			}
-		dx[i] = s;
+			*reinterpret_cast<V*>(dx + (long long) g.n * r + v * G) = *reinterpret_cast<const V*>(s);
+		}
 	}
+}
+
+// Disjoint windows (stride >= window in both directions, the usual 2x2 / 2 case): every input element belongs to
+// at most one window, so the backward pass streams: a thread owns G batch entries of one OUTPUT row, reads dy and
+// the argmax once and writes its whole stride cell of dx (zeros outside the window; the last cell of a row / column
+// extends to the input's edge), so dx is written exactly once and nothing is read twice.
+template<typename S, int KIND, bool VEC>
+__global__ void __launch_bounds__(256) pool_bwd_disjoint_kernel(cattl3_pool_geom g, int OH, int OW, int tv,
+		const S* __restrict__ dy, const uint8_t* __restrict__ argmax, S* __restrict__ dx) {
+	typedef typename PoolVec<S, VEC>::type V;
+	constexpr int G = PoolVec<S, VEC>::G;
+	typedef typename ByteVec<G>::type BV;
+	const int nv = g.n / G;
+	const int rows_per_cta = 256 / tv;
+	const int v0 = threadIdx.x % tv, rsub = threadIdx.x / tv;
+	if (rsub >= rows_per_cta) return;
+	const unsigned rows = (unsigned) OH * OW * g.c;
+	const S inv_area = (S) 1 / (S) (g.rh * g.rw);
+	for (unsigned r = blockIdx.x * rows_per_cta + rsub; r < rows; r += gridDim.x * rows_per_cta) {
+		const int oh = (int) (r % OH);
+		const unsigned t = r / OH;
+		const int ow = (int) (t % OW), c = (int) (t / OW);
+		const int h0 = oh * g.sh, w0 = ow * g.sw;
+		const int h1 = oh == OH - 1 ? g.h : h0 + g.sh, w1 = ow == OW - 1 ? g.w : w0 + g.sw;
+		for (int v = v0; v < nv; v += tv) {
+			const long long o = (long long) g.n * r + v * G;
+			const V vg = *reinterpret_cast<const V*>(dy + o);
+			const S* eg = reinterpret_cast<const S*>(&vg);
+			BV vb;
+			if (KIND == CATTL3_POOL_MAX) vb = *reinterpret_cast<const BV*>(argmax + o);
+			const uint8_t* eb = reinterpret_cast<const uint8_t*>(&vb);
+			for (int w = w0; w < w1; ++w)
+				for (int h = h0; h < h1; ++h) {
+					const int k = w - w0, l = h - h0;
+					const bool inside = k < g.rw && l < g.rh;
+					const int idx = k * g.rh + l;
+					__align__(16) S out[G];
+					#pragma unroll
+					for (int e = 0; e < G; ++e) {
+						if (KIND == CATTL3_POOL_MAX) out[e] = (inside && (int) eb[e] == idx) ? eg[e] : (S) 0;
+						else out[e] = inside ? eg[e] * inv_area : (S) 0;
+					}
+					*reinterpret_cast<V*>(dx + (long long) g.n * (h + (long long) g.h * (w + (long long) g.w * c)) + v * G) =
+							*reinterpret_cast<const V*>(out);
+				}
+		}
+	}
+	// columns / rows of the input in front of which no window starts cannot exist (windows start at 0); cells cover
+	// [0, H) x [0, W) completely because the last cell extends to the edge.
+}
+
+// tv = threads along the batch vectors of a row; grid = enough CTAs for all rows, capped at 8 per SM
+static inline void pool_launch_shape(const cattl3_ctx* ctx, int nv, long long rows, int* tv, int* grid) {
+	*tv = nv < 256 ? nv : 256;
+	const int rows_per_cta = 256 / *tv;
+	long long blocks = ceil_div(rows, rows_per_cta);
+	const long long cap = (long long) ctx->sm_count * 8;
+	*grid = (int) (blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 
 template<typename S>
@@ -247,19 +345,23 @@ int pool_forward(cattl3_ctx* ctx, int kind, const cattl3_pool_geom* g, const S* 
 	int32_t oh, ow;
 	CATTL3_CHECK(cattl3_pool_output_dims(g, &oh, &ow));
 	CATTL3_REQUIRE(x && y, "pool_forward: null tensor");
-	const long long total = (long long) g->n * oh * ow * g->c;
-	const int grid = ew_grid(ctx, total, 256);
+	CATTL3_REQUIRE(kind == CATTL3_POOL_MAX || kind == CATTL3_POOL_MEAN, "pool_forward: unknown kind %d", kind);
+	if (kind == CATTL3_POOL_MAX && g->rh * g->rw > 256) {
+		set_error("pool_forward: max-pool windows above 256 elements are unsupported");
+		return CATTL3_ERR_UNSUPPORTED;
+	}
+	const long long rows = (long long) oh * ow * g->c;
+	CATTL3_REQUIRE(rows < (1ll << 31) && (long long) g->h * g->w * g->c < (1ll << 31), "pool: more than 2^31 rows");
+	constexpr int G = V16<S>::G;
+	const bool vec = g->n % G == 0 && aligned16(x) && aligned16(y) && (!argmax || (reinterpret_cast<uintptr_t>(argmax) % G) == 0);
+	int tv, grid;
+	pool_launch_shape(ctx, vec ? g->n / G : g->n, rows, &tv, &grid);
 	if (kind == CATTL3_POOL_MAX) {
-		if (g->rh * g->rw > 256) {
-			set_error("pool_forward: max-pool windows above 256 elements are unsupported");
-			return CATTL3_ERR_UNSUPPORTED;
-		}
-		pool_fwd_kernel<S, CATTL3_POOL_MAX><<<grid, 256, 0, ctx->stream>>>(*g, oh, ow, x, y, argmax);
-	} else if (kind == CATTL3_POOL_MEAN) {
-		pool_fwd_kernel<S, CATTL3_POOL_MEAN><<<grid, 256, 0, ctx->stream>>>(*g, oh, ow, x, y, nullptr);
+		if (vec) pool_fwd_kernel<S, CATTL3_POOL_MAX, true><<<grid, 256, 0, ctx->stream>>>(*g, oh, ow, tv, x, y, argmax);
+		else pool_fwd_kernel<S, CATTL3_POOL_MAX, false><<<grid, 256, 0, ctx->stream>>>(*g, oh, ow, tv, x, y, argmax);
 	} else {
-		set_error("pool_forward: unknown kind %d", kind);
-		return CATTL3_ERR_INVALID;
+		if (vec) pool_fwd_kernel<S, CATTL3_POOL_MEAN, true><<<grid, 256, 0, ctx->stream>>>(*g, oh, ow, tv, x, y, nullptr);
+		else pool_fwd_kernel<S, CATTL3_POOL_MEAN, false><<<grid, 256, 0, ctx->stream>>>(*g, oh, ow, tv, x, y, nullptr);
 	}
 	CATTL3_LAUNCHED(ctx);
 	return CATTL3_OK;
@@ -271,17 +373,26 @@ int pool_backward(cattl3_ctx* ctx, int kind, const cattl3_pool_geom* g, const S*
 	int32_t oh, ow;
 	CATTL3_CHECK(cattl3_pool_output_dims(g, &oh, &ow));
 	CATTL3_REQUIRE(dy && dx, "pool_backward: null tensor");
-	const long long total = (long long) g->n * g->h * g->w * g->c;
-	const int grid = ew_grid(ctx, total, 256);
+	CATTL3_REQUIRE(kind == CATTL3_POOL_MAX || kind == CATTL3_POOL_MEAN, "pool_backward: unknown kind %d", kind);
+	CATTL3_REQUIRE(kind != CATTL3_POOL_MAX || argmax, "pool_backward: max pooling needs the argmax cache");
+	const bool disjoint = g->sh >= g->rh && g->sw >= g->rw;
+	const long long rows = disjoint ? (long long) oh * ow * g->c : (long long) g->h * g->w * g->c;
+	CATTL3_REQUIRE((long long) g->h * g->w * g->c < (1ll << 31), "pool: more than 2^31 rows");
+	constexpr int G = V16<S>::G;
+	const bool vec = g->n % G == 0 && aligned16(dy) && aligned16(dx) && (!argmax || (reinterpret_cast<uintptr_t>(argmax) % G) == 0);
+	int tv, grid;
+	pool_launch_shape(ctx, vec ? g->n / G : g->n, rows, &tv, &grid);
+#define POOL_BWD(KERNEL, K, AM) do { \
+		if (vec) KERNEL<S, K, true><<<grid, 256, 0, ctx->stream>>>(*g, oh, ow, tv, dy, AM, dx); \
+		else KERNEL<S, K, false><<<grid, 256, 0, ctx->stream>>>(*g, oh, ow, tv, dy, AM, dx); } while (0)
 	if (kind == CATTL3_POOL_MAX) {
-		CATTL3_REQUIRE(argmax, "pool_backward: max pooling needs the argmax cache");
-		pool_bwd_kernel<S, CATTL3_POOL_MAX><<<grid, 256, 0, ctx->stream>>>(*g, oh, ow, dy, argmax, dx);
-	} else if (kind == CATTL3_POOL_MEAN) {
-		pool_bwd_kernel<S, CATTL3_POOL_MEAN><<<grid, 256, 0, ctx->stream>>>(*g, oh, ow, dy, nullptr, dx);
+		if (disjoint) POOL_BWD(pool_bwd_disjoint_kernel, CATTL3_POOL_MAX, argmax);
+		else POOL_BWD(pool_bwd_kernel, CATTL3_POOL_MAX, argmax);
 	} else {
-		set_error("pool_backward: unknown kind %d", kind);
-		return CATTL3_ERR_INVALID;
+		if (disjoint) POOL_BWD(pool_bwd_disjoint_kernel, CATTL3_POOL_MEAN, nullptr);
+		else POOL_BWD(pool_bwd_kernel, CATTL3_POOL_MEAN, nullptr);
 	}
+#undef POOL_BWD
 	CATTL3_LAUNCHED(ctx);
 	return CATTL3_OK;
 }
@@ -314,20 +425,33 @@ __device__ __forceinline__ void block_reduce2(double& a, double& b) {
 	}
 }
 
+// Applies fn(element index within the group range, G consecutive elements) over [lo, hi) of one group: 16-byte
+// vectors when `vec` (group base, lo and hi are then multiples of G elements and the tensors 16-byte aligned).
+#define BN_FOREACH(S, vec, lo, hi, BODY_VEC, BODY_SCALAR) \
+	if (vec) { \
+		constexpr int G_ = V16<S>::G; \
+		_Pragma("unroll 4") \
+		for (long long i = (lo) + (long long) threadIdx.x * G_; i < (hi); i += (long long) blockDim.x * G_) { BODY_VEC } \
+	} else { \
+		for (long long i = (lo) + threadIdx.x; i < (hi); i += blockDim.x) { BODY_SCALAR } \
+	}
+
 template<typename S>
-__global__ void __launch_bounds__(256) bn_stats_partial_kernel(long long L, long long chunk,
+__global__ void __launch_bounds__(256) bn_stats_partial_kernel(long long L, long long chunk, int vec,
 		const S* __restrict__ x, BnPartial* __restrict__ part) {
+	typedef typename V16<S>::type V;
 	const long long g = blockIdx.x;
 	const S* xg = x + g * L;
 	const double K = (double) xg[0];
 	const long long lo = (long long) blockIdx.y * chunk;
 	const long long hi = lo + chunk < L ? lo + chunk : L;
 	double s1 = 0, s2 = 0;
-	for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-		const double d = (double) xg[i] - K;
-		s1 += d;
-		s2 += d * d;
-	}
+	BN_FOREACH(S, vec, lo, hi,
+		const V v = *reinterpret_cast<const V*>(xg + i);
+		const S* e = reinterpret_cast<const S*>(&v);
+		_Pragma("unroll")
+		for (int k = 0; k < G_; ++k) { const double d = (double) e[k] - K; s1 += d; s2 += d * d; },
+		const double d = (double) xg[i] - K; s1 += d; s2 += d * d;)
 	block_reduce2(s1, s2);
 	if (threadIdx.x == 0) part[g * gridDim.y + blockIdx.y] = BnPartial{ s1, s2 };
 }
@@ -359,31 +483,45 @@ __global__ void __launch_bounds__(128) bn_stats_final_kernel(long long groups, l
 }
 
 template<typename S>
-__global__ void __launch_bounds__(256) bn_apply_kernel(long long L, long long chunk, const S* __restrict__ x,
+__global__ void __launch_bounds__(256) bn_apply_kernel(long long L, long long chunk, int vec, const S* __restrict__ x,
 		const S* __restrict__ mean, const S* __restrict__ inv_sd, const S* __restrict__ gamma,
 		const S* __restrict__ beta, S* __restrict__ y) {
+	typedef typename V16<S>::type V;
 	const long long g = blockIdx.x;
 	const S mu = mean[g], sc = inv_sd[g], gm = gamma[g], bt = beta[g];
 	const long long lo = (long long) blockIdx.y * chunk;
 	const long long hi = lo + chunk < L ? lo + chunk : L;
-	for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x)
-		y[g * L + i] = ((x[g * L + i] - mu) * sc) * gm + bt;
+	const S* xg = x + g * L;
+	S* yg = y + g * L;
+	BN_FOREACH(S, vec, lo, hi,
+		V v = *reinterpret_cast<const V*>(xg + i);
+		S* e = reinterpret_cast<S*>(&v);
+		_Pragma("unroll")
+		for (int k = 0; k < G_; ++k) e[k] = ((e[k] - mu) * sc) * gm + bt;
+		*reinterpret_cast<V*>(yg + i) = v;,
+		yg[i] = ((xg[i] - mu) * sc) * gm + bt;)
 }
 
 template<typename S>
-__global__ void __launch_bounds__(256) bn_bwd_partial_kernel(long long L, long long chunk,
+__global__ void __launch_bounds__(256) bn_bwd_partial_kernel(long long L, long long chunk, int vec,
 		const S* __restrict__ x, const S* __restrict__ mean, const S* __restrict__ inv_sd,
 		const S* __restrict__ dy, BnPartial* __restrict__ part) {
+	typedef typename V16<S>::type V;
 	const long long g = blockIdx.x;
 	const S mu = mean[g], sc = inv_sd[g];
 	const long long lo = (long long) blockIdx.y * chunk;
 	const long long hi = lo + chunk < L ? lo + chunk : L;
+	const S* xg = x + g * L;
+	const S* dyg = dy + g * L;
 	double s1 = 0, s2 = 0;  // sum dy, sum dy * xhat
-	for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-		const S gy = dy[g * L + i];
-		s1 += (double) gy;
-		s2 += (double) (gy * ((x[g * L + i] - mu) * sc));
-	}
+	BN_FOREACH(S, vec, lo, hi,
+		const V vx = *reinterpret_cast<const V*>(xg + i);
+		const V vg = *reinterpret_cast<const V*>(dyg + i);
+		const S* ex = reinterpret_cast<const S*>(&vx);
+		const S* eg = reinterpret_cast<const S*>(&vg);
+		_Pragma("unroll")
+		for (int k = 0; k < G_; ++k) { s1 += (double) eg[k]; s2 += (double) (eg[k] * ((ex[k] - mu) * sc)); },
+		const S gy = dyg[i]; s1 += (double) gy; s2 += (double) (gy * ((xg[i] - mu) * sc));)
 	block_reduce2(s1, s2);
 	if (threadIdx.x == 0) part[g * gridDim.y + blockIdx.y] = BnPartial{ s1, s2 };
 }
@@ -403,20 +541,33 @@ __global__ void __launch_bounds__(128) bn_bwd_final_kernel(long long groups, int
 
 // dx = (L*g - sum g - xhat * sum(xhat g)) * inv_sd / L with g = gamma * dy (BatchNormLayer.hpp:257-261).
 template<typename S>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(long long L, long long chunk, int chunks,
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(long long L, long long chunk, int chunks, int vec,
 		const S* __restrict__ x, const S* __restrict__ mean, const S* __restrict__ inv_sd,
 		const S* __restrict__ gamma, const BnPartial* __restrict__ part, const S* __restrict__ dy,
 		S* __restrict__ dx) {
+	typedef typename V16<S>::type V;
 	const long long g = blockIdx.x;
 	const S mu = mean[g], sc = inv_sd[g], gm = gamma[g];
 	const S sum_g = gm * (S) part[g * chunks].s1, sum_xg = gm * (S) part[g * chunks].s2;
 	const S scale = ((S) 1 / (S) L) * sc;
 	const long long lo = (long long) blockIdx.y * chunk;
 	const long long hi = lo + chunk < L ? lo + chunk : L;
-	for (long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-		const S xh = (x[g * L + i] - mu) * sc;
-		dx[g * L + i] = (((S) L * (gm * dy[g * L + i]) - sum_g) - xh * sum_xg) * scale;
-	}
+	const S* xg = x + g * L;
+	const S* dyg = dy + g * L;
+	S* dxg = dx + g * L;
+	BN_FOREACH(S, vec, lo, hi,
+		const V vx = *reinterpret_cast<const V*>(xg + i);
+		V vg = *reinterpret_cast<const V*>(dyg + i);
+		const S* ex = reinterpret_cast<const S*>(&vx);
+		S* eg = reinterpret_cast<S*>(&vg);
+		_Pragma("unroll")
+		for (int k = 0; k < G_; ++k) {
+			const S xh = (ex[k] - mu) * sc;
+			eg[k] = (((S) L * (gm * eg[k]) - sum_g) - xh * sum_xg) * scale;
+		}
+		*reinterpret_cast<V*>(dxg + i) = vg;,
+		const S xh = (xg[i] - mu) * sc;
+		dxg[i] = (((S) L * (gm * dyg[i]) - sum_g) - xh * sum_xg) * scale;)
 }
 
 static void bn_partition(const cattl3_ctx* ctx, long long groups, long long L, int* chunks, long long* chunk,
@@ -426,7 +577,7 @@ static void bn_partition(const cattl3_ctx* ctx, long long groups, long long L, i
 	long long maxc = ceil_div(L, 2048);
 	long long c = want < maxc ? want : maxc;
 	if (c < 1) c = 1;
-	*chunk = ceil_div(L, c);
+	*chunk = ceil_div(ceil_div(L, c), 4) * 4;   // chunk starts stay 16-byte aligned for the vector loops
 	*chunks = (int) ceil_div(L, *chunk);
 	*threads = L >= 1024 ? 256 : (L >= 128 ? 128 : 32);
 }
@@ -445,18 +596,19 @@ int batchnorm_forward(cattl3_ctx* ctx, int per_channel, int n, int h, int w, int
 	bn_partition(ctx, groups, L, &chunks, &chunk, &threads);
 	CATTL3_REQUIRE(groups <= 2147483647ll, "batchnorm: too many groups");
 	dim3 grid((unsigned) groups, (unsigned) chunks);
+	const int vec = L % V16<S>::G == 0 && aligned16(x) && aligned16(y);
 	if (training) {
 		CATTL3_REQUIRE(saved_mean && saved_inv_sd, "batchnorm_forward: training needs saved statistics");
 		CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, sizeof(BnPartial) * groups * chunks));
-		bn_stats_partial_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, x, (BnPartial*) ctx->ws);
+		bn_stats_partial_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, vec, x, (BnPartial*) ctx->ws);
 		CATTL3_LAUNCHED(ctx);
 		bn_stats_final_kernel<S><<<(unsigned) ceil_div(groups, 128), 128, 0, ctx->stream>>>(groups, L, chunks, x,
 				(const BnPartial*) ctx->ws, eps, decay, running_init, running_mean, running_inv_sd, saved_mean,
 				saved_inv_sd);
 		CATTL3_LAUNCHED(ctx);
-		bn_apply_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, x, saved_mean, saved_inv_sd, gamma, beta, y);
+		bn_apply_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, vec, x, saved_mean, saved_inv_sd, gamma, beta, y);
 	} else {
-		bn_apply_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, x, running_mean, running_inv_sd, gamma, beta, y);
+		bn_apply_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, vec, x, running_mean, running_inv_sd, gamma, beta, y);
 	}
 	CATTL3_LAUNCHED(ctx);
 	return CATTL3_OK;
@@ -475,15 +627,16 @@ int batchnorm_backward(cattl3_ctx* ctx, int per_channel, int n, int h, int w, in
 	long long chunk;
 	bn_partition(ctx, groups, L, &chunks, &chunk, &threads);
 	dim3 grid((unsigned) groups, (unsigned) chunks);
+	const int vec = L % V16<S>::G == 0 && aligned16(x) && aligned16(dy) && (!dx || aligned16(dx));
 	CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, sizeof(BnPartial) * groups * chunks));
-	bn_bwd_partial_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, x, saved_mean, saved_inv_sd, dy,
+	bn_bwd_partial_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, vec, x, saved_mean, saved_inv_sd, dy,
 			(BnPartial*) ctx->ws);
 	CATTL3_LAUNCHED(ctx);
 	bn_bwd_final_kernel<S><<<(unsigned) ceil_div(groups, 128), 128, 0, ctx->stream>>>(groups, chunks,
 			(BnPartial*) ctx->ws, dgamma, dbeta);
 	CATTL3_LAUNCHED(ctx);
 	if (dx) {
-		bn_bwd_apply_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, chunks, x, saved_mean, saved_inv_sd,
+		bn_bwd_apply_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, chunks, vec, x, saved_mean, saved_inv_sd,
 				gamma, (const BnPartial*) ctx->ws, dy, dx);
 		CATTL3_LAUNCHED(ctx);
 	}
@@ -497,63 +650,100 @@ int batchnorm_backward(cattl3_ctx* ctx, int per_channel, int n, int h, int w, in
 template<typename S>
 struct OptScalars { S lr, a, b, eps, lr_epoch, c1, c1n, c2, l2; int reset; };
 
+// One element of the update: reads (p, g, state), writes them back in place.
 template<typename S, int KIND>
-__global__ void __launch_bounds__(256) opt_step_kernel(long long count, OptScalars<S> h, S* __restrict__ p,
+__device__ __forceinline__ void opt_update(const OptScalars<S>& h, S& pv, S& gv, S& a1, S& a2, S& a3) {
+	if (h.l2 > (S) 0) gv += pv * h.l2;
+	if (KIND == CATTL3_OPT_VANILLA_SGD) {
+		pv = pv - gv * h.lr;
+	} else if (KIND == CATTL3_OPT_MOMENTUM) {
+		const S v = a1 * h.b + gv * h.lr_epoch;
+		a1 = v;
+		pv = pv - v;
+	} else if (KIND == CATTL3_OPT_NESTEROV) {
+		const S old = a1;
+		const S v = old * h.b - gv * h.lr_epoch;
+		a1 = v;
+		pv = pv + old * -h.b + v * ((S) 1 + h.b);
+	} else if (KIND == CATTL3_OPT_ADAGRAD) {
+		const S s = a1 + gv * gv;
+		a1 = s;
+		pv = pv - gv * h.lr / (dev_sqrt<S>(s) + h.eps);
+	} else if (KIND == CATTL3_OPT_RMSPROP) {
+		const S s = a1 * ((S) 1 - h.b) + gv * gv * h.b;
+		a1 = s;
+		pv = pv - gv * h.lr / (dev_sqrt<S>(s) + h.eps);
+	} else if (KIND == CATTL3_OPT_ADADELTA) {
+		const S s = a1 * ((S) 1 - h.a) + gv * gv * h.a;
+		a1 = s;
+		const S u = -gv * dev_sqrt<S>(a2 + h.eps) / dev_sqrt<S>(s + h.eps);
+		pv = pv + u;
+		a2 = a2 * ((S) 1 - h.a) + u * u * h.a;
+	} else if (KIND == CATTL3_OPT_ADAM) {
+		const S m = a1 * ((S) 1 - h.a) + gv * h.a;
+		const S v = a2 * ((S) 1 - h.b) + gv * gv * h.b;
+		a1 = m; a2 = v;
+		pv = pv - (m * (h.lr * h.c1)) / dev_sqrt<S>(v * h.c2 + h.eps);
+	} else if (KIND == CATTL3_OPT_ADAMAX) {
+		const S m = a1 * ((S) 1 - h.a) + gv * h.a;
+		const S d = a2 * ((S) 1 - h.b);
+		const S ag = gv < (S) 0 ? -gv : gv;
+		const S v = d > ag ? d : ag;
+		a1 = m; a2 = v;
+		pv = pv - (m * (h.lr * h.c1)) / (v + h.eps);
+	} else if (KIND == CATTL3_OPT_NADAM) {
+		const S m = a1 * ((S) 1 - h.a) + gv * h.a;
+		const S v = a2 * ((S) 1 - h.b) + gv * gv * h.b;
+		a1 = m; a2 = v;
+		pv = pv - (gv * (h.a * h.c1) + m * (((S) 1 - h.a) * h.c1n)) * h.lr / dev_sqrt<S>(v * h.c2 + h.eps);
+	} else if (KIND == CATTL3_OPT_AMSGRAD) {
+		const S m = a1 * ((S) 1 - h.a) + gv * h.a;
+		const S v = a2 * ((S) 1 - h.b) + gv * gv * h.b;
+		const S mx = v > a3 ? v : a3;
+		a1 = m; a2 = v; a3 = mx;
+		pv = pv - m * h.lr / dev_sqrt<S>(mx + h.eps);
+	}
+}
+
+// 16-byte vector body (every stream of the arena is 16-byte aligned at the same element offsets) + scalar tail.
+template<typename S, int KIND>
+__global__ void __launch_bounds__(256) opt_step_kernel(long long count, int vec_ok, OptScalars<S> h, S* __restrict__ p,
 		S* __restrict__ g, S* __restrict__ s1, S* __restrict__ s2, S* __restrict__ s3) {
-	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < count; i += (long long) gridDim.x * 256) {
-		S pv = p[i];
-		S gv = g[i];
-		if (h.l2 > (S) 0) gv += pv * h.l2;
-		if (KIND == CATTL3_OPT_VANILLA_SGD) {
-			pv = pv - gv * h.lr;
-		} else if (KIND == CATTL3_OPT_MOMENTUM) {
-			const S v = s1[i] * h.b + gv * h.lr_epoch;
-			s1[i] = v;
-			pv = pv - v;
-		} else if (KIND == CATTL3_OPT_NESTEROV) {
-			const S old = s1[i];
-			const S v = old * h.b - gv * h.lr_epoch;
-			s1[i] = v;
-			pv = pv + old * -h.b + v * ((S) 1 + h.b);
-		} else if (KIND == CATTL3_OPT_ADAGRAD) {
-			const S s = s1[i] + gv * gv;
-			s1[i] = s;
-			pv = pv - gv * h.lr / (dev_sqrt<S>(s) + h.eps);
-		} else if (KIND == CATTL3_OPT_RMSPROP) {
-			const S s = s1[i] * ((S) 1 - h.b) + gv * gv * h.b;
-			s1[i] = s;
-			pv = pv - gv * h.lr / (dev_sqrt<S>(s) + h.eps);
-		} else if (KIND == CATTL3_OPT_ADADELTA) {
-			const S s = s1[i] * ((S) 1 - h.a) + gv * gv * h.a;
-			s1[i] = s;
-			const S u = -gv * dev_sqrt<S>(s2[i] + h.eps) / dev_sqrt<S>(s + h.eps);
-			pv = pv + u;
-			s2[i] = s2[i] * ((S) 1 - h.a) + u * u * h.a;
-		} else if (KIND == CATTL3_OPT_ADAM) {
-			const S m = s1[i] * ((S) 1 - h.a) + gv * h.a;
-			const S v = s2[i] * ((S) 1 - h.b) + gv * gv * h.b;
-			s1[i] = m; s2[i] = v;
-			pv = pv - (m * (h.lr * h.c1)) / dev_sqrt<S>(v * h.c2 + h.eps);
-		} else if (KIND == CATTL3_OPT_ADAMAX) {
-			const S m = s1[i] * ((S) 1 - h.a) + gv * h.a;
-			const S d = s2[i] * ((S) 1 - h.b);
-			const S ag = gv < (S) 0 ? -gv : gv;
-			const S v = d > ag ? d : ag;
-			s1[i] = m; s2[i] = v;
-			pv = pv - (m * (h.lr * h.c1)) / (v + h.eps);
-		} else if (KIND == CATTL3_OPT_NADAM) {
-			const S m = s1[i] * ((S) 1 - h.a) + gv * h.a;
-			const S v = s2[i] * ((S) 1 - h.b) + gv * gv * h.b;
-			s1[i] = m; s2[i] = v;
-			pv = pv - (gv * (h.a * h.c1) + m * (((S) 1 - h.a) * h.c1n)) * h.lr / dev_sqrt<S>(v * h.c2 + h.eps);
-		} else if (KIND == CATTL3_OPT_AMSGRAD) {
-			const S m = s1[i] * ((S) 1 - h.a) + gv * h.a;
-			const S v = s2[i] * ((S) 1 - h.b) + gv * gv * h.b;
-			const S mx = v > s3[i] ? v : s3[i];
-			s1[i] = m; s2[i] = v; s3[i] = mx;
-			pv = pv - m * h.lr / dev_sqrt<S>(mx + h.eps);
+	typedef typename V16<S>::type V;
+	constexpr int G = V16<S>::G;
+	constexpr int NS = KIND == CATTL3_OPT_VANILLA_SGD ? 0 : (KIND <= CATTL3_OPT_RMSPROP ? 1 : (KIND == CATTL3_OPT_AMSGRAD ? 3 : 2));
+	const long long nvec = vec_ok ? count / G : 0;
+	const long long stride = (long long) gridDim.x * 256;
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < nvec; i += stride) {
+		V vp = reinterpret_cast<V*>(p)[i], vg = reinterpret_cast<V*>(g)[i], v1, v2, v3;
+		if (NS >= 1) v1 = reinterpret_cast<V*>(s1)[i];
+		if (NS >= 2) v2 = reinterpret_cast<V*>(s2)[i];
+		if (NS >= 3) v3 = reinterpret_cast<V*>(s3)[i];
+		S* ep = reinterpret_cast<S*>(&vp); S* eg = reinterpret_cast<S*>(&vg);
+		S* e1 = reinterpret_cast<S*>(&v1); S* e2 = reinterpret_cast<S*>(&v2); S* e3 = reinterpret_cast<S*>(&v3);
+		#pragma unroll
+		for (int k = 0; k < G; ++k) {
+			S d1 = NS >= 1 ? e1[k] : (S) 0, d2 = NS >= 2 ? e2[k] : (S) 0, d3 = NS >= 3 ? e3[k] : (S) 0;
+			opt_update<S, KIND>(h, ep[k], eg[k], d1, d2, d3);
+			if (NS >= 1) e1[k] = d1;
+			if (NS >= 2) e2[k] = d2;
+			if (NS >= 3) e3[k] = d3;
+			eg[k] = (S) 0;
 		}
+		reinterpret_cast<V*>(p)[i] = vp;
+		if (NS >= 1) reinterpret_cast<V*>(s1)[i] = v1;
+		if (NS >= 2) reinterpret_cast<V*>(s2)[i] = v2;
+		if (NS >= 3) reinterpret_cast<V*>(s3)[i] = v3;
+		if (h.reset) reinterpret_cast<V*>(g)[i] = vg;
+	}
+	for (long long i = nvec * G + blockIdx.x * 256ll + threadIdx.x; i < count; i += stride) {
+		S pv = p[i], gv = g[i];
+		S d1 = NS >= 1 ? s1[i] : (S) 0, d2 = NS >= 2 ? s2[i] : (S) 0, d3 = NS >= 3 ? s3[i] : (S) 0;
+		opt_update<S, KIND>(h, pv, gv, d1, d2, d3);
 		p[i] = pv;
+		if (NS >= 1) s1[i] = d1;
+		if (NS >= 2) s2[i] = d2;
+		if (NS >= 3) s3[i] = d3;
 		if (h.reset) g[i] = (S) 0;
 	}
 }
@@ -564,12 +754,14 @@ int optimizer_step(cattl3_ctx* ctx, const cattl3_opt_step* st, int64_t count, S*
 	CATTL3_REQUIRE(st && count > 0 && p && g, "optimizer_step: bad arguments");
 	OptScalars<S> h{ (S) st->lr, (S) st->a, (S) st->b, (S) st->eps, (S) st->lr_epoch, (S) st->c1, (S) st->c1n,
 			(S) st->c2, (S) st->l2_lambda, st->reset_grad };
-	const int grid = ew_grid(ctx, count, 256);
+	const int grid = ew_grid(ctx, ceil_div(count, V16<S>::G), 256);
 	const int k = st->kind;
 	const int need = (k == 0) ? 0 : (k <= 4 ? 1 : (k == 9 ? 3 : 2));
 	CATTL3_REQUIRE((need < 1 || s1) && (need < 2 || s2) && (need < 3 || s3), "optimizer_step: missing state vector");
+	const int vec_ok = aligned16(p) && aligned16(g) && (need < 1 || aligned16(s1)) && (need < 2 || aligned16(s2)) &&
+			(need < 3 || aligned16(s3));
 	switch (k) {
-#define CASE(K) case K: opt_step_kernel<S, K><<<grid, 256, 0, ctx->stream>>>(count, h, p, g, s1, s2, s3); break;
+#define CASE(K) case K: opt_step_kernel<S, K><<<grid, 256, 0, ctx->stream>>>(count, vec_ok, h, p, g, s1, s2, s3); break;
 		CASE(CATTL3_OPT_VANILLA_SGD) CASE(CATTL3_OPT_MOMENTUM) CASE(CATTL3_OPT_NESTEROV) CASE(CATTL3_OPT_ADAGRAD)
 		CASE(CATTL3_OPT_RMSPROP) CASE(CATTL3_OPT_ADADELTA) CASE(CATTL3_OPT_ADAM) CASE(CATTL3_OPT_ADAMAX)
 		CASE(CATTL3_OPT_NADAM) CASE(CATTL3_OPT_AMSGRAD)
@@ -583,44 +775,36 @@ int optimizer_step(cattl3_ctx* ctx, const cattl3_opt_step* st, int64_t count, S*
 }
 
 // ---- glue ----------------------------------------------------------------------------------------
-template<typename S>
-__global__ void __launch_bounds__(256) add_inplace_kernel(long long count, S* __restrict__ y, const S* __restrict__ x) {
-	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < count; i += (long long) gridDim.x * 256) y[i] += x[i];
+// y = OP(x, y) over 16-byte vectors with a scalar tail; OP 0: y + x, 1: x * alpha, 2: fma(alpha, x, y)
+template<typename S, int OP>
+__global__ void __launch_bounds__(256) glue_kernel(long long count, int vec_ok, S alpha, const S* __restrict__ x, S* __restrict__ y) {
+	typedef typename V16<S>::type V;
+	constexpr int G = V16<S>::G;
+	const long long nvec = vec_ok ? count / G : 0;
+	const long long stride = (long long) gridDim.x * 256;
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < nvec; i += stride) {
+		V vx = reinterpret_cast<const V*>(x)[i], vy;
+		if (OP != 1) vy = reinterpret_cast<V*>(y)[i];
+		S* ex = reinterpret_cast<S*>(&vx); S* ey = reinterpret_cast<S*>(&vy);
+		#pragma unroll
+		for (int k = 0; k < G; ++k) ey[k] = OP == 0 ? ey[k] + ex[k] : (OP == 1 ? ex[k] * alpha : fma(alpha, ex[k], ey[k]));
+		reinterpret_cast<V*>(y)[i] = vy;
+	}
+	for (long long i = nvec * G + blockIdx.x * 256ll + threadIdx.x; i < count; i += stride)
+		y[i] = OP == 0 ? y[i] + x[i] : (OP == 1 ? x[i] * alpha : fma(alpha, x[i], y[i]));
 }
-template<typename S>
-__global__ void __launch_bounds__(256) scale_kernel(long long count, S alpha, const S* __restrict__ x, S* __restrict__ y) {
-	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < count; i += (long long) gridDim.x * 256) y[i] = x[i] * alpha;
-}
-
-template<typename S>
-__global__ void __launch_bounds__(256) axpy_kernel(long long count, S alpha, const S* __restrict__ x, S* __restrict__ y) {
-	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < count; i += (long long) gridDim.x * 256) y[i] = fma(alpha, x[i], y[i]);
-}
-template<typename S>
-int axpy(cattl3_ctx* ctx, int64_t count, S alpha, const S* x, S* y) {
+template<typename S, int OP>
+static int glue(cattl3_ctx* ctx, const char* what, int64_t count, S alpha, const S* x, S* y) {
 	CATTL3_CHECK(check_ctx(ctx));
-	CATTL3_REQUIRE(count > 0 && y && x, "axpy: bad arguments");
-	axpy_kernel<S><<<ew_grid(ctx, count, 256), 256, 0, ctx->stream>>>(count, alpha, x, y);
+	CATTL3_REQUIRE(count > 0 && y && x, "%s: bad arguments", what);
+	glue_kernel<S, OP><<<ew_grid(ctx, ceil_div(count, V16<S>::G), 256), 256, 0, ctx->stream>>>(count,
+			aligned16(x) && aligned16(y), alpha, x, y);
 	CATTL3_LAUNCHED(ctx);
 	return CATTL3_OK;
 }
-
-template<typename S>
-int add_inplace(cattl3_ctx* ctx, int64_t count, S* y, const S* x) {
-	CATTL3_CHECK(check_ctx(ctx));
-	CATTL3_REQUIRE(count > 0 && y && x, "add_inplace: bad arguments");
-	add_inplace_kernel<S><<<ew_grid(ctx, count, 256), 256, 0, ctx->stream>>>(count, y, x);
-	CATTL3_LAUNCHED(ctx);
-	return CATTL3_OK;
-}
-template<typename S>
-int scale(cattl3_ctx* ctx, int64_t count, S alpha, const S* x, S* y) {
-	CATTL3_CHECK(check_ctx(ctx));
-	CATTL3_REQUIRE(count > 0 && y && x, "scale: bad arguments");
-	scale_kernel<S><<<ew_grid(ctx, count, 256), 256, 0, ctx->stream>>>(count, alpha, x, y);
-	CATTL3_LAUNCHED(ctx);
-	return CATTL3_OK;
-}
+template<typename S> int axpy(cattl3_ctx* ctx, int64_t count, S alpha, const S* x, S* y) { return glue<S, 2>(ctx, "axpy", count, alpha, x, y); }
+template<typename S> int add_inplace(cattl3_ctx* ctx, int64_t count, S* y, const S* x) { return glue<S, 0>(ctx, "add_inplace", count, (S) 0, x, y); }
+template<typename S> int scale(cattl3_ctx* ctx, int64_t count, S alpha, const S* x, S* y) { return glue<S, 1>(ctx, "scale", count, alpha, x, y); }
 
 } // namespace cattl3
 

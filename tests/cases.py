@@ -67,6 +67,12 @@ POOL_CASES = {
     "mean_1d_r2s2": (1, 5, 16, 1, 1, 2, 1, 2, 1),
     "mean_2d_overlap": (1, 5, 8, 8, 2, 3, 2, 1, 2),
     "mean_cifar": (1, 8, 16, 16, 8, 2, 2, 2, 2),
+    # stride > window: input rows / columns no window covers, ragged trailing edge; vector and scalar batch
+    "max_gap": (0, 8, 9, 7, 3, 2, 2, 3, 2),
+    "max_gap_scalar": (0, 5, 10, 7, 2, 2, 3, 3, 3),
+    "mean_gap": (1, 6, 9, 7, 3, 2, 2, 3, 3),
+    "max_vec_overlap": (0, 8, 8, 8, 2, 3, 2, 1, 2),
+    "mean_vec_overlap": (1, 12, 7, 8, 2, 3, 3, 2, 1),
 }
 
 # (per_channel, n, h, w, c, steps); test/gradient_test.cpp:346-369
