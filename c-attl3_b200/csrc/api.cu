@@ -87,6 +87,28 @@ static GatherGeom bwd_gather(int N, int SH, int SW, int SC, int OH, int OW, int 
 template<typename S> struct IsFloat { static constexpr bool value = false; };
 template<> struct IsFloat<float> { static constexpr bool value = true; };
 
+// One dimension of a strided transposed gather (source = (o + c - r*d) / s where divisible), split by the residue
+// class a = (o + c) mod s: outputs o = o0 + s*i take only the taps r = r0 + q*k, and for those
+// source = i - (d/g)*k + c_sub -- an ordinary stride-1 gather.  (g = gcd(d, s), q = s/g.)
+struct LatticeDim { int o0, n_o, r0, q, n_r, b_sub, c_sub; };
+static LatticeDim lattice_dim(int a, int O, int R, int c, int d, int s) {
+	LatticeDim L;
+	L.o0 = ((a - c) % s + s) % s;
+	L.n_o = L.o0 < O ? (O - L.o0 + s - 1) / s : 0;
+	L.r0 = -1; L.q = 1; L.n_r = 0;
+	for (int r = 0; r < R; ++r)
+		if ((r * d) % s == a) {
+			if (L.n_r == 0) L.r0 = r;
+			else if (L.n_r == 1) L.q = r - L.r0;
+			++L.n_r;
+		}
+	int g = d, t = s;
+	while (t) { int u = g % t; g = t; t = u; }   // gcd(d, s)
+	L.b_sub = -(d / g);
+	L.c_sub = L.n_r ? (L.o0 + c - L.r0 * d) / s : 0;  // exact: the numerator is a multiple of s
+	return L;
+}
+
 template<typename S>
 static int run_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* w, const S* bias,
 		int bias_mode, S* out) {
@@ -95,6 +117,45 @@ static int run_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, 
 		return tc_gather_gemm_f32(ctx, gg, (const float*) src, (const float*) w, (const float*) bias, bias_mode,
 				(float*) out);
 	}
+	if (IsFloat<S>::value && ctx->conv_path != CATTL3_PATH_SIMT && (gg.denh > 1 || gg.denw > 1) && gg.ah == 1 && gg.aw == 1) {
+		// strided transposed gather (input gradient of a strided convolution, forward of a strided transposed
+		// convolution): denh * denw stride-1 sub-problems, one per residue class of the output pixel, each writing
+		// its own sub-lattice of the output through the tensor-core kernel
+		GatherGeom probe = gg;
+		probe.denh = probe.denw = 1;
+		if (tc_gather_gemm_supported(ctx, probe)) {
+			bool need_zero = false;
+			for (int a = 0; a < gg.denh && !need_zero; ++a)
+				for (int b = 0; b < gg.denw && !need_zero; ++b) {
+					const LatticeDim Lh = lattice_dim(a, gg.OH, gg.RH, gg.ch, -gg.bh, gg.denh);
+					const LatticeDim Lw = lattice_dim(b, gg.OW, gg.RW, gg.cw, -gg.bw, gg.denw);
+					if (Lh.n_o > 0 && Lw.n_o > 0 && (Lh.n_r == 0 || Lw.n_r == 0)) need_zero = bias_mode == 0;
+					if (Lh.n_o > 0 && Lw.n_o > 0 && (Lh.n_r == 0 || Lw.n_r == 0) && bias_mode != 0) goto simt;  // bias-only pixels
+				}
+			if (need_zero)
+				CATTL3_CUDA(cudaMemsetAsync(out, 0, sizeof(S) * (size_t) gg.N * gg.OH * gg.OW * gg.J, ctx->stream));
+			const long long srw = gg.w_srw ? gg.w_srw : gg.w_stap * gg.RH;
+			for (int a = 0; a < gg.denh; ++a)
+				for (int b = 0; b < gg.denw; ++b) {
+					const LatticeDim Lh = lattice_dim(a, gg.OH, gg.RH, gg.ch, -gg.bh, gg.denh);
+					const LatticeDim Lw = lattice_dim(b, gg.OW, gg.RW, gg.cw, -gg.bw, gg.denw);
+					if (Lh.n_o == 0 || Lw.n_o == 0 || Lh.n_r == 0 || Lw.n_r == 0) continue;
+					GatherGeom sub = gg;
+					sub.OH = Lh.n_o; sub.OW = Lw.n_o; sub.RH = Lh.n_r; sub.RW = Lw.n_r;
+					sub.ah = 1; sub.bh = Lh.b_sub; sub.ch = Lh.c_sub; sub.denh = 1;
+					sub.aw = 1; sub.bw = Lw.b_sub; sub.cw = Lw.c_sub; sub.denw = 1;
+					sub.w_off = gg.w_off + Lh.r0 * gg.w_stap + Lw.r0 * srw;
+					sub.w_stap = gg.w_stap * Lh.q; sub.w_srw = srw * Lw.q;
+					sub.out_h0 = Lh.o0; sub.out_hs = gg.denh; sub.out_H = gg.OH;
+					sub.out_w0 = Lw.o0; sub.out_ws = gg.denw; sub.out_W = gg.OW;
+					CATTL3_CHECK(tc_gather_gemm_f32(ctx, sub, (const float*) src, (const float*) w, (const float*) bias,
+							bias_mode, (float*) out));
+				}
+			ctx->last_path = "tcgen05";
+			return CATTL3_OK;
+		}
+	}
+simt:
 	if (ctx->conv_path == CATTL3_PATH_TCGEN05) {
 		set_error("tcgen05 path requested but the shape/type does not qualify (needs float, batch %% 32 == 0)");
 		return CATTL3_ERR_UNSUPPORTED;

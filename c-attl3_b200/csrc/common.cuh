@@ -82,6 +82,12 @@ struct GatherGeom {
 	int aw, bw, cw, denw;
 	// weight element (tap = rh + RH*rw, reduce channel r, output channel j)
 	long long w_stap, w_sr, w_sj;
+	// ---- used by the tcgen05 gather GEMM only (sub-problems of a strided transposed gather, api.cu) ----
+	// weight element = w_off + rh*w_stap + rw*w_srw + r*w_sr + j*w_sj; w_srw == 0 means w_stap*RH
+	long long w_off = 0, w_srw = 0;
+	// output lattice: element (n, i, j) of the OH x OW grid is stored at pixel (out_h0 + out_hs*i, out_w0 + out_ws*j)
+	// of an out_H x out_W tensor; out_H == 0 means the dense OH x OW tensor itself
+	int out_h0 = 0, out_hs = 1, out_H = 0, out_w0 = 0, out_ws = 1, out_W = 0;
 };
 
 template<typename S>

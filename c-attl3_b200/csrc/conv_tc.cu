@@ -186,7 +186,10 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(GatherGeom gg, int r_
 		const int j = (int) ((i / r_pad) % j_pad);
 		const int tap = (int) (i / ((long long) r_pad * j_pad));
 		float v = 0.f;
-		if (r < gg.SC && j < gg.J) v = w[tap * gg.w_stap + r * gg.w_sr + j * gg.w_sj];
+		if (r < gg.SC && j < gg.J) {
+			const int rh = tap % gg.RH, rw = tap / gg.RH;
+			v = w[gg.w_off + rh * gg.w_stap + rw * (gg.w_srw ? gg.w_srw : gg.w_stap * gg.RH) + r * gg.w_sr + j * gg.w_sj];
+		}
 		packed[i] = __uint_as_float(tf32_hi_bits(v));
 		packed[total + i] = __uint_as_float(tf32_lo_bits(v));
 	}
@@ -217,6 +220,10 @@ struct TcGemmParams {
 	int bias_mode;
 	const float* bias;
 	float* out;
+	// where row m = n + N*(i + OH*j) of the GEMM lives in the output tensor: pixel (h0 + hs*i, w0 + ws*j) of an
+	// oH x oW image (dense: h0 = w0 = 0, hs = ws = 1, oH = OH, oW = OW); out_cs = N*oH*oW is the channel stride
+	int h0, hs, oH, w0, ws, oW;
+	long long out_cs;
 };
 
 // Gather GEMM (conv / dense forward, stride-1 input gradient):
@@ -360,9 +367,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 			tc_fence_after();
 			const long long m = (long long) mt * TC_BM + 32 * q + lane;
 			const bool m_ok = m < p.M;
-			const long long pix = m / p.N;
+			const long long gpix = m / p.N;
+			const int gi = (int) (gpix % p.OH), gj = (int) (gpix / p.OH);
+			const long long pix = (p.h0 + p.hs * gi) + (long long) p.oH * (p.w0 + p.ws * gj);  // pixel in the output tensor
 			const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16) + (uint32_t) (acc * p.BN);
-			float* out_m = p.out + m + p.M * (long long) (jt * p.BN);
+			float* out_m = p.out + (m % p.N) + p.N * pix + p.out_cs * (long long) (jt * p.BN);
 			const int jn = p.J - jt * p.BN < p.BN ? p.J - jt * p.BN : p.BN;  // valid columns of this tile
 			for (int c0 = 0; c0 < p.BN; c0 += 16) {
 				float v[16], bv[16];
@@ -385,11 +394,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 				if (m_ok) {
 					if (c0 + 16 <= jn) {
 						#pragma unroll
-						for (int i = 0; i < 16; ++i) out_m[p.M * (long long) (c0 + i)] = v[i] + bv[i];
+						for (int i = 0; i < 16; ++i) out_m[p.out_cs * (long long) (c0 + i)] = v[i] + bv[i];
 					} else {
 						#pragma unroll
 						for (int i = 0; i < 16; ++i)
-							if (c0 + i < jn) out_m[p.M * (long long) (c0 + i)] = v[i] + bv[i];
+							if (c0 + i < jn) out_m[p.out_cs * (long long) (c0 + i)] = v[i] + bv[i];
 					}
 				}
 			}
@@ -524,7 +533,11 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 	TcGemmParams p;
 	p.N = gg.N; p.OH = gg.OH; p.OW = gg.OW; p.J = gg.J; p.RH = gg.RH; p.RW = gg.RW;
 	p.ah = gg.ah; p.bh = gg.bh; p.ch = gg.ch; p.aw = gg.aw; p.bw = gg.bw; p.cw = gg.cw;
-	p.M = M; p.P = (long long) gg.OH * gg.OW;
+	p.M = M;
+	p.h0 = gg.out_h0; p.hs = gg.out_hs; p.w0 = gg.out_w0; p.ws = gg.out_ws;
+	p.oH = gg.out_H ? gg.out_H : gg.OH; p.oW = gg.out_H ? gg.out_W : gg.OW;
+	p.P = (long long) p.oH * p.oW;
+	p.out_cs = (long long) gg.N * p.P;
 	p.m_tiles = (int) ceil_div(M, TC_BM); p.j_tiles = j_tiles;
 	p.BN = BN; p.r_pad = r_pad; p.nb = nb;
 	// one accumulator of 256 columns leaves room for the A stages; narrower tiles double-buffer it so that the

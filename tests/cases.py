@@ -24,6 +24,13 @@ CONV_CASES = {
     "c2_dil1": (32, 12, 10, 32, 16, 3, 3, 2, 2, 1, 1, 1, 1),
     "c2_1x1": (64, 9, 9, 64, 64, 1, 1, 0, 0, 1, 1, 0, 0),
     "ragged_c": (32, 9, 7, 20, 24, 3, 3, 1, 1, 1, 1, 0, 0),
+    # strided input gradients on the tensor-core path (one stride-1 sub-problem per residue class of the input pixel)
+    "s2_d1": (32, 11, 9, 32, 32, 3, 3, 2, 2, 2, 2, 1, 1),    # classes without taps: zero-filled
+    "s3": (32, 13, 11, 16, 32, 3, 3, 1, 1, 3, 3, 0, 0),
+    "s21": (32, 9, 8, 32, 16, 3, 2, 1, 0, 2, 1, 0, 0),
+    "s2_1x1": (32, 8, 8, 32, 32, 1, 1, 0, 0, 2, 2, 0, 0),
+    "s2_4x4": (32, 10, 10, 16, 16, 4, 4, 1, 1, 2, 2, 0, 0),
+    "s2_ragged_edge": (64, 12, 9, 16, 24, 3, 3, 0, 1, 2, 2, 0, 0),
     # ragged everything: odd batch, odd channels
     "ragged": (7, 9, 11, 5, 3, 3, 4, 2, 1, 2, 1, 0, 1),
     "single": (1, 3, 3, 1, 1, 3, 3, 1, 1, 1, 1, 0, 0),
@@ -38,6 +45,9 @@ TCONV_CASES = {
     "mnist_t0": (8, 10, 10, 3, 3, 4, 4, 1, 1, 1, 1, 0, 0),
     "mnist_t1": (8, 13, 13, 3, 1, 4, 4, 1, 1, 2, 2, 0, 0),
     "wide": (32, 6, 5, 32, 16, 3, 3, 1, 1, 2, 2, 0, 0),
+    "wide_s2_k4": (32, 5, 6, 16, 16, 4, 4, 1, 1, 2, 2, 0, 0),
+    "wide_s3_k2": (32, 4, 4, 16, 16, 2, 2, 0, 0, 3, 3, 0, 0),   # output pixels that receive the bias only
+    "wide_s1": (32, 6, 5, 16, 32, 3, 3, 1, 1, 1, 1, 0, 0),
     "ragged": (3, 4, 3, 5, 2, 2, 3, 0, 1, 2, 1, 1, 0),
 }
 
