@@ -21,6 +21,7 @@ CATTLE_INCLUDE_DIR = os.path.join(HERE, "cattle")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = 0, 1, 2, 3, 4
 ACT = dict(relu=0, leaky_relu=1, elu=2, swish=3, sigmoid=4, tanh=5, softplus=6, softmax=7)
+ACT_NONE = -1
 POOL = dict(max=0, mean=1)
 OPT = dict(sgd=0, momentum=1, nesterov=2, adagrad=3, rmsprop=4, adadelta=5, adam=6, adamax=7, nadam=8,
            amsgrad=9)
@@ -40,6 +41,12 @@ class ConvGeom(ctypes.Structure):
 
 class PoolGeom(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int32) for k in ("n", "h", "w", "c", "rh", "rw", "sh", "sw")]
+
+
+class Epilogue(ctypes.Structure):
+    """cattl3_epilogue: what a kernel layer's forward pass fuses besides the bias."""
+    _fields_ = [("act_kind", ctypes.c_int32), ("reserved", ctypes.c_int32), ("act_param", ctypes.c_double),
+                ("act_out", ctypes.c_void_p), ("col_stats", ctypes.c_void_p)]
 
 
 class OptStep(ctypes.Structure):
@@ -71,7 +78,8 @@ _SYMBOLS = [
     "cattl3_conv_forward", "cattl3_conv_backward", "cattl3_transconv_forward", "cattl3_transconv_backward",
     "cattl3_dense_forward", "cattl3_dense_backward", "cattl3_activation_forward", "cattl3_activation_backward",
     "cattl3_pool_forward", "cattl3_pool_backward", "cattl3_batchnorm_forward", "cattl3_batchnorm_backward",
-    "cattl3_optimizer_step", "cattl3_add_inplace", "cattl3_scale", "cattl3_axpy")]
+    "cattl3_optimizer_step", "cattl3_add_inplace", "cattl3_scale", "cattl3_axpy",
+    "cattl3_conv_forward_fused", "cattl3_dense_forward_fused", "cattl3_batchnorm_forward_stats")]
 
 
 def lib():
@@ -175,6 +183,33 @@ class Context:
 
     def dense_backward(self, n, i, o, x, w, dy, dw, db, dx):
         self._call("cattl3_dense_backward", x.dtype, n, i, o, _p(x), _p(w), _p(dy), _p(dw), _p(db), _p(dx))
+
+    @staticmethod
+    def _epilogue(act_kind, act_param, act_out, col_stats):
+        ep = Epilogue()
+        ep.act_kind = ACT_NONE if act_kind is None else int(act_kind)
+        ep.act_param = float(act_param)
+        ep.act_out = act_out.data_ptr() if act_out is not None else None
+        ep.col_stats = col_stats.data_ptr() if col_stats is not None else None
+        return ep
+
+    def conv_forward_fused(self, g, x, w, b, y, act_kind=None, act_param=0.0, act_out=None, col_stats=None):
+        """Forward with a fused epilogue: act_out = f(y) and / or col_stats (2*F float64) for a BatchNormLayer."""
+        ep = self._epilogue(act_kind, act_param, act_out, col_stats)
+        self._call("cattl3_conv_forward_fused", x.dtype, ctypes.byref(g), _p(x), _p(w), _p(b), _p(y), ctypes.byref(ep))
+
+    def dense_forward_fused(self, n, i, o, x, w, b, y, act_kind=None, act_param=0.0, act_out=None, col_stats=None):
+        ep = self._epilogue(act_kind, act_param, act_out, col_stats)
+        self._call("cattl3_dense_forward_fused", x.dtype, n, i, o, _p(x), _p(w), _p(b), _p(y), ctypes.byref(ep))
+
+    def batchnorm_forward_stats(self, per_channel, n, h, w, c, running_init, decay, eps, x, col_stats, shift, gamma,
+                                beta, running_mean, running_inv_sd, saved_mean, saved_inv_sd, y, act_kind=None,
+                                act_param=0.0, act_out=None):
+        _, ct = _suffix(x.dtype)
+        self._call("cattl3_batchnorm_forward_stats", x.dtype, int(per_channel), n, h, w, c, int(running_init),
+                   ct(decay), ct(eps), _p(x), _p(col_stats), _p(shift), _p(gamma), _p(beta), _p(running_mean),
+                   _p(running_inv_sd), _p(saved_mean), _p(saved_inv_sd), _p(y),
+                   ACT_NONE if act_kind is None else int(act_kind), ct(act_param), _p(act_out))
 
     def conv_forward_host(self, g, x_host, w, b, y_host, x_dev_keep=None):
         self._chk(self.L.cattl3_conv_forward_host_f32(self.h, ctypes.byref(g), _p(x_host), _p(w), _p(b),

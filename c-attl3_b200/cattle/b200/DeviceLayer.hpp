@@ -103,6 +103,59 @@ public:
 	virtual DeviceTensor<Scalar> pass_back_dev(DeviceTensor<Scalar> out_grad) = 0;
 };
 
+/**
+ * What the layer FOLLOWING a kernel layer asks that layer's epilogue to do while the output tile is still
+ * on chip (cattl3_epilogue, include/cattl3_b200.h): apply its element-wise activation and / or produce the
+ * per-column sums a BatchNormLayer starts with.  The consumer fills in the request, the producer the results.
+ */
+template<typename Scalar>
+struct FusedEpilogue {
+	// request
+	int act_kind = CATTL3_ACT_NONE;
+	Scalar act_param = 0;
+	bool keep_pre = true;      // the consumer caches the producer's plain output for its backward pass
+	bool want_stats = false;
+	// results
+	DeviceTensor<Scalar> act_out;                      // f(plain output)
+	std::shared_ptr<DeviceBuffer<double>> col_stats;   // 2 * columns sums, shifted by `shift`
+	const Scalar* shift = nullptr;                     // the producer's bias (device), valid during the step
+};
+
+/** A layer whose forward kernel can run a FusedEpilogue (the kernel layers). */
+template<typename Scalar>
+class EpilogueProducer {
+public:
+	virtual ~EpilogueProducer() = default;
+	virtual bool can_fuse_epilogue() const = 0;
+	/** Columns of the layer's GEMM (filters / outputs): the groups column statistics are produced for. */
+	virtual std::size_t stat_columns() const = 0;
+	/**
+	 * pass_forward_dev with the epilogue `ep`.  Returns the plain output (empty when !ep.keep_pre and an
+	 * activation was requested); ep.act_out / ep.col_stats / ep.shift are filled in.
+	 */
+	virtual DeviceTensor<Scalar> pass_forward_dev_fused(DeviceTensor<Scalar> in, bool training, FusedEpilogue<Scalar>& ep) = 0;
+};
+
+/** A layer whose forward pass can be (partly) done by its producer's epilogue (activations, batch norm). */
+template<typename Scalar>
+class EpilogueConsumer {
+public:
+	virtual ~EpilogueConsumer() = default;
+	/** Fills in the request; false = run the layer on its own. */
+	virtual bool request_epilogue(FusedEpilogue<Scalar>& ep, std::size_t producer_stat_columns, bool training) const = 0;
+	/** Whether accept_epilogue() can itself apply a following activation (`next`). */
+	virtual bool chains_epilogue() const {
+		return false;
+	}
+	/**
+	 * Completes the layer's forward pass from the producer's results and sets up its backward caches exactly
+	 * as pass_forward_dev would.  `next` (only if chains_epilogue()): an activation request of the layer
+	 * after this one, to be applied in the same pass.  Returns the layer's own output.
+	 */
+	virtual DeviceTensor<Scalar> accept_epilogue(DeviceTensor<Scalar> pre, FusedEpilogue<Scalar>& ep, bool training,
+			FusedEpilogue<Scalar>* next) = 0;
+};
+
 /** extents = { rows, dims... } */
 template<std::size_t Rank, typename Dims>
 inline std::array<std::size_t,Rank + 1> batch_extents(std::size_t rows, const Dims& dims) {

@@ -109,6 +109,12 @@ template<typename Scalar> struct Api;
 template<> struct Api<S> { \
 	static int conv_forward(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y) { \
 		return cattl3_conv_forward_##SUF(c, g, x, w, b, y); } \
+	static int conv_forward_fused(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y, const cattl3_epilogue* ep) { \
+		return cattl3_conv_forward_fused_##SUF(c, g, x, w, b, y, ep); } \
+	static int dense_forward_fused(cattl3_ctx* c, std::int32_t n, std::int32_t in, std::int32_t out, const S* x, const S* w, const S* b, S* y, const cattl3_epilogue* ep) { \
+		return cattl3_dense_forward_fused_##SUF(c, n, in, out, x, w, b, y, ep); } \
+	static int batchnorm_forward_stats(cattl3_ctx* c, int pc, std::int32_t n, std::int32_t h, std::int32_t w, std::int32_t ch, int init, S decay, S eps, const S* x, const double* cs, const S* shift, const S* gamma, const S* beta, S* rm, S* rs, S* sm, S* ss, S* y, int ak, S ap, S* ao) { \
+		return cattl3_batchnorm_forward_stats_##SUF(c, pc, n, h, w, ch, init, decay, eps, x, cs, shift, gamma, beta, rm, rs, sm, ss, y, ak, ap, ao); } \
 	static int conv_backward(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* dy, S* dw, S* db, S* dx) { \
 		return cattl3_conv_backward_##SUF(c, g, x, w, dy, dw, db, dx); } \
 	static int transconv_forward(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y) { \

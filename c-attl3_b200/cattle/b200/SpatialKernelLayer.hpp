@@ -27,7 +27,8 @@ namespace cattle {
 namespace b200 {
 
 template<typename Scalar, std::size_t Rank, bool Transposed>
-class SpatialKernelLayer : public KernelLayer<Scalar,Rank>, public DeviceLayer<Scalar,Rank> {
+class SpatialKernelLayer : public KernelLayer<Scalar,Rank>, public DeviceLayer<Scalar,Rank>,
+		public EpilogueProducer<Scalar> {
 	typedef Layer<Scalar,Rank> Root;
 	typedef KernelLayer<Scalar,Rank> Base;
 	typedef Api<Scalar> Device;
@@ -64,6 +65,45 @@ public:
 				CATTLE_B200_CHECK(Device::conv_forward(c.handle(), &g, in.data(), w.device_values(),
 						b.device_values(), out.data()));
 			}
+		}
+		in_cache = std::move(in);
+		return out;
+	}
+	/** The convolution's epilogue can do the next layer's work; the transposed layer's (per-element bias) does not. */
+	inline bool can_fuse_epilogue() const {
+		return !Transposed;
+	}
+	inline std::size_t stat_columns() const {
+		return Transposed ? 0 : filters;
+	}
+	inline DeviceTensor<Scalar> pass_forward_dev_fused(DeviceTensor<Scalar> in, bool training, FusedEpilogue<Scalar>& ep) {
+		if (Transposed)
+			throw Error(CATTL3_ERR_UNSUPPORTED, "TransConvKernelLayer has no fused epilogue");
+		cattl3_conv_geom g = geometry(in.rows);
+		const std::size_t volume = Base::output_dims.get_volume();
+		const bool act = ep.act_kind != CATTL3_ACT_NONE;
+		DeviceTensor<Scalar> out;
+		if (!act || ep.keep_pre || ep.want_stats)
+			out = DeviceTensor<Scalar>(in.rows, volume);
+		B200Parameters<Scalar>& w = device_params(*Base::weights);
+		B200Parameters<Scalar>& b = device_params(*Base::bias);
+		cattl3_epilogue e;
+		e.act_kind = ep.act_kind; e.reserved = 0; e.act_param = (double) ep.act_param;
+		e.act_out = nullptr; e.col_stats = nullptr;
+		if (act) {
+			ep.act_out = DeviceTensor<Scalar>(in.rows, volume);
+			e.act_out = ep.act_out.data();
+		}
+		if (ep.want_stats) {
+			ep.col_stats = std::make_shared<DeviceBuffer<double>>(2 * filters);
+			e.col_stats = ep.col_stats->data();
+			ep.shift = b.device_values();
+		}
+		Context& c = Context::get();
+		{
+			Context::Lock l = c.lock();
+			CATTLE_B200_CHECK(Device::conv_forward_fused(c.handle(), &g, in.data(), w.device_values(),
+					b.device_values(), out.data(), &e));
 		}
 		in_cache = std::move(in);
 		return out;

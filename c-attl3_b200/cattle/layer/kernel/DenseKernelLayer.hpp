@@ -86,6 +86,42 @@ public:
 		in_cache = std::move(in);
 		return out;
 	}
+	inline bool can_fuse_epilogue() const {
+		return true;
+	}
+	inline std::size_t stat_columns() const {
+		return Base::output_dims.get_volume();
+	}
+	inline DevTensor pass_forward_dev_fused(DevTensor in, bool training, b200::FusedEpilogue<Scalar>& ep) {
+		const std::size_t volume = Base::output_dims.get_volume();
+		const bool act = ep.act_kind != CATTL3_ACT_NONE;
+		DevTensor out;
+		if (!act || ep.keep_pre || ep.want_stats)
+			out = DevTensor(in.rows, volume);
+		B200Parameters<Scalar>& w = static_cast<B200Parameters<Scalar>&>(*Base::weights);
+		B200Parameters<Scalar>& b = static_cast<B200Parameters<Scalar>&>(*Base::bias);
+		cattl3_epilogue e;
+		e.act_kind = ep.act_kind; e.reserved = 0; e.act_param = (double) ep.act_param;
+		e.act_out = nullptr; e.col_stats = nullptr;
+		if (act) {
+			ep.act_out = DevTensor(in.rows, volume);
+			e.act_out = ep.act_out.data();
+		}
+		if (ep.want_stats) {
+			ep.col_stats = std::make_shared<b200::DeviceBuffer<double>>(2 * volume);
+			e.col_stats = ep.col_stats->data();
+			ep.shift = b.device_values();
+		}
+		b200::Context& c = b200::Context::get();
+		{
+			b200::Context::Lock l = c.lock();
+			CATTLE_B200_CHECK(b200::Api<Scalar>::dense_forward_fused(c.handle(), (std::int32_t) in.rows,
+					(std::int32_t) Base::input_dims.get_volume(), (std::int32_t) volume, in.data(), w.device_values(),
+					b.device_values(), out.data(), &e));
+		}
+		in_cache = std::move(in);
+		return out;
+	}
 	inline DevTensor pass_back_dev(DevTensor out_grad) {
 		if (in_cache.empty() || in_cache.rows != out_grad.rows)
 			throw b200::Error(CATTL3_ERR_INVALID, "DenseKernelLayer: pass_back without a matching pass_forward");

@@ -111,12 +111,15 @@ static LatticeDim lattice_dim(int a, int O, int R, int c, int d, int s) {
 
 template<typename S>
 static int run_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* w, const S* bias,
-		int bias_mode, S* out) {
+		int bias_mode, S* out, const EpilogueArgs* ep = nullptr) {
+	// ep: fused activation and / or column statistics.  The tcgen05 kernel does both in its epilogue; the SIMT kernel
+	// fuses the activation, and the statistics are then one reduction pass over the finished output.
 	if (IsFloat<S>::value && ctx->conv_path != CATTL3_PATH_SIMT && tc_gather_gemm_supported(ctx, gg)) {
 		ctx->last_path = "tcgen05";
 		return tc_gather_gemm_f32(ctx, gg, (const float*) src, (const float*) w, (const float*) bias, bias_mode,
-				(float*) out);
+				(float*) out, ep);
 	}
+	CATTL3_REQUIRE(!(ep && ep->col_stats) || (bias_mode == 1 && out), "column statistics need a per-column bias and y");
 	if (IsFloat<S>::value && ctx->conv_path != CATTL3_PATH_SIMT && (gg.denh > 1 || gg.denw > 1) && gg.ah == 1 && gg.aw == 1) {
 		// strided transposed gather (input gradient of a strided convolution, forward of a strided transposed
 		// convolution): denh * denw stride-1 sub-problems, one per residue class of the output pixel, each writing
@@ -149,7 +152,7 @@ static int run_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, 
 					sub.out_h0 = Lh.o0; sub.out_hs = gg.denh; sub.out_H = gg.OH;
 					sub.out_w0 = Lw.o0; sub.out_ws = gg.denw; sub.out_W = gg.OW;
 					CATTL3_CHECK(tc_gather_gemm_f32(ctx, sub, (const float*) src, (const float*) w, (const float*) bias,
-							bias_mode, (float*) out));
+							bias_mode, (float*) out, ep));  // every output pixel belongs to exactly one sub-lattice
 				}
 			ctx->last_path = "tcgen05";
 			return CATTL3_OK;
@@ -161,7 +164,10 @@ simt:
 		return CATTL3_ERR_UNSUPPORTED;
 	}
 	ctx->last_path = "simt";
-	return simt_gather_gemm<S>(ctx, gg, src, w, bias, bias_mode, out);
+	CATTL3_CHECK(simt_gather_gemm<S>(ctx, gg, src, w, bias, bias_mode, out, ep));
+	if (ep && ep->col_stats)
+		CATTL3_CHECK(colstats_shifted<S>(ctx, (int64_t) gg.N * gg.OH * gg.OW, gg.J, out, bias, ep->col_stats));
+	return CATTL3_OK;
 }
 
 // db_colsum != null: the caller also wants db += column sums of `plain`; the tcgen05 kernel produces them from
@@ -183,16 +189,33 @@ static int run_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const 
 	return simt_wgrad<S>(ctx, gg, src, plain, dw);
 }
 
+static int check_epilogue(const cattl3_epilogue* ep, const void* y, EpilogueArgs* ea) {
+	if (!ep) {
+		CATTL3_REQUIRE(y, "forward: null output tensor");
+		return CATTL3_OK;
+	}
+	CATTL3_REQUIRE(ep->act_kind >= CATTL3_ACT_NONE && ep->act_kind < CATTL3_ACT_SOFTMAX,
+			"epilogue: activation kind %d cannot be fused (element-wise kinds 0-6 only)", ep->act_kind);
+	CATTL3_REQUIRE(ep->act_kind == CATTL3_ACT_NONE || ep->act_out, "epilogue: activation without act_out");
+	CATTL3_REQUIRE(y || ep->act_kind != CATTL3_ACT_NONE, "forward: neither y nor act_out given");
+	CATTL3_REQUIRE(!ep->col_stats || y, "epilogue: column statistics need y (the batch-norm input)");
+	ea->act_kind = ep->act_kind; ea->act_param = ep->act_param; ea->act_out = ep->act_out; ea->col_stats = ep->col_stats;
+	return CATTL3_OK;
+}
+
 template<typename S>
-static int conv_forward(cattl3_ctx* ctx, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y) {
+static int conv_forward(cattl3_ctx* ctx, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y,
+		const cattl3_epilogue* ep = nullptr) {
 	CATTL3_CHECK(check_ctx(ctx));
 	int oh, ow;
 	CATTL3_CHECK(check_geom(g, 0, &oh, &ow));
-	CATTL3_REQUIRE(x && w && b && y, "conv_forward: null tensor");
+	CATTL3_REQUIRE(x && w && b, "conv_forward: null tensor");
+	EpilogueArgs ea;
+	CATTL3_CHECK(check_epilogue(ep, y, &ea));
 	const long long T = (long long) g->rh * g->rw;
 	GatherGeom gg = fwd_gather(g->n, g->h, g->w, g->c, oh, ow, g->f, g);
 	gg.w_stap = 1; gg.w_sr = T; gg.w_sj = T * g->c;
-	return run_gather_gemm<S>(ctx, gg, x, w, b, 1, y);
+	return run_gather_gemm<S>(ctx, gg, x, w, b, 1, y, ep ? &ea : nullptr);
 }
 
 template<typename S>
@@ -323,6 +346,7 @@ int cattl3_ctx_destroy(cattl3_ctx* ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->ws) cudaFree(ctx->ws);
 	if (ctx->tc_w) cudaFree(ctx->tc_w);
+	if (ctx->stat_ws) cudaFree(ctx->stat_ws);
 	for (int i = 0; i < 3; ++i)
 		if (ctx->stage_dev[i]) cudaFree(ctx->stage_dev[i]);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
@@ -414,6 +438,16 @@ int cattl3_conv_forward_##SUF(cattl3_ctx* c, const cattl3_conv_geom* g, const S*
 	return conv_forward<S>(c, g, x, w, b, y); } \
 int cattl3_conv_backward_##SUF(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* dy, S* dw, S* db, S* dx) { \
 	return conv_backward<S>(c, g, x, w, dy, dw, db, dx); } \
+int cattl3_conv_forward_fused_##SUF(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y, \
+		const cattl3_epilogue* ep) { \
+	CATTL3_REQUIRE(ep, "conv_forward_fused: null epilogue"); \
+	return conv_forward<S>(c, g, x, w, b, y, ep); } \
+int cattl3_dense_forward_fused_##SUF(cattl3_ctx* c, int32_t n, int32_t in, int32_t out, const S* x, const S* w, const S* b, \
+		S* y, const cattl3_epilogue* ep) { \
+	CATTL3_REQUIRE(n > 0 && in > 0 && out > 0, "dense_forward: non-positive size"); \
+	CATTL3_REQUIRE(ep, "dense_forward_fused: null epilogue"); \
+	cattl3_conv_geom g = dense_geom(n, in, out); \
+	return conv_forward<S>(c, &g, x, w, b, y, ep); } \
 int cattl3_transconv_forward_##SUF(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y) { \
 	return transconv_forward<S>(c, g, x, w, b, y); } \
 int cattl3_transconv_backward_##SUF(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* dy, S* dw, S* db, S* dx) { \

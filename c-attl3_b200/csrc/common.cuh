@@ -22,6 +22,9 @@ struct cattl3_ctx {
 	// tcgen05 path scratch: the weights repacked K-major and split hi | lo for TMA
 	void* tc_w = nullptr;
 	size_t tc_w_bytes = 0;
+	// per-CTA column sums of a fused batch-norm statistics epilogue (conv_tc.cu)
+	void* stat_ws = nullptr;
+	size_t stat_ws_bytes = 0;
 	// pinned staging for the *_host entry points
 	void* stage_dev[3] = { nullptr, nullptr, nullptr };
 	size_t stage_dev_bytes[3] = { 0, 0, 0 };
@@ -90,9 +93,22 @@ struct GatherGeom {
 	int out_h0 = 0, out_hs = 1, out_H = 0, out_w0 = 0, out_ws = 1, out_W = 0;
 };
 
+// A kernel layer's fused epilogue (cattl3_epilogue, already validated): activation and / or column statistics.
+struct EpilogueArgs {
+	int act_kind = CATTL3_ACT_NONE;
+	double act_param = 0;
+	void* act_out = nullptr;
+	double* col_stats = nullptr;
+};
+
+// out may be null when ep->act_out is given.  The SIMT kernels fuse the activation only (ep->col_stats is ignored:
+// the caller runs colstats_shifted over the finished output).
 template<typename S>
 int simt_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* w, const S* bias,
-		int bias_mode, S* out);
+		int bias_mode, S* out, const EpilogueArgs* ep = nullptr);
+// col_stats[j] = sum_m (a[m + rows*j] - shift[j]), col_stats[cols + j] = the sum of squares; double accumulation.
+template<typename S>
+int colstats_shifted(cattl3_ctx* ctx, int64_t rows, int64_t cols, const S* a, const S* shift, double* col_stats);
 template<typename S>
 int simt_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* plain, S* dw);
 template<typename S>
@@ -101,7 +117,7 @@ int colsum_accumulate(cattl3_ctx* ctx, int64_t rows, int64_t cols, const S* a, S
 // tcgen05 path (conv_tc.cu): returns CATTL3_ERR_UNSUPPORTED when the shape does not qualify.
 bool tc_gather_gemm_supported(const cattl3_ctx* ctx, const GatherGeom& gg);
 int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const float* w,
-		const float* bias, int bias_mode, float* out);
+		const float* bias, int bias_mode, float* out, const EpilogueArgs* ep = nullptr);
 bool tc_wgrad_supported(const cattl3_ctx* ctx, const GatherGeom& gg);
 // db != null: also accumulates the column sums of `plain` (the bias gradient of a convolution) into db.
 int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const float* plain, float* dw, float* db);

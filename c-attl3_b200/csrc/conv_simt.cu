@@ -12,7 +12,7 @@
 // The weight gradient is a split-K reduction over m = N*OH*OW with a deterministic second stage
 // that ACCUMULATES into the gradient (Parameters::accumulate_grad semantics,
 // C-ATTL3/parameters/StandardParameters.hpp:115-123).
-#include "common.cuh"
+#include "activations.cuh"
 
 namespace cattl3 {
 
@@ -26,7 +26,8 @@ template<> struct Vec<double> { typedef double2 type; static constexpr int G = 2
 // ------------------------------------------------------------------------------------------------
 template<typename S>
 __global__ void __launch_bounds__(256) gather_gemm_kernel(GatherGeom gg, const S* __restrict__ src,
-		const S* __restrict__ w, const S* __restrict__ bias, int bias_mode, S* __restrict__ out) {
+		const S* __restrict__ w, const S* __restrict__ bias, int bias_mode, S* __restrict__ out, int act_kind, S act_param,
+		S* __restrict__ act_out) {
 	constexpr int G = Vec<S>::G;
 	constexpr int BM = 32 * G, BN = 64, BK = 16;
 	constexpr int A_ROWS = 256 / BM, A_ITERS = BK / A_ROWS;
@@ -111,7 +112,8 @@ __global__ void __launch_bounds__(256) gather_gemm_kernel(GatherGeom gg, const S
 				S v = acc[g * G + e][jj];
 				if (bias_mode == 1) v += bias[j];
 				else if (bias_mode == 2) v += bias[m / gg.N + P * j];
-				out[m + M * j] = v;
+				if (out) out[m + M * j] = v;
+				if (act_out) act_out[m + M * j] = act_fwd_rt<S>(act_kind, v, act_param);
 			}
 		}
 	}
@@ -119,16 +121,21 @@ __global__ void __launch_bounds__(256) gather_gemm_kernel(GatherGeom gg, const S
 
 template<typename S>
 int simt_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* w, const S* bias,
-		int bias_mode, S* out) {
+		int bias_mode, S* out, const EpilogueArgs* ep) {
 	constexpr int BM = 32 * Vec<S>::G;
 	const long long M = (long long) gg.N * gg.OH * gg.OW;
 	dim3 grid((unsigned) ceil_div(M, BM), (unsigned) ceil_div(gg.J, 64));
-	gather_gemm_kernel<S><<<grid, 256, 0, ctx->stream>>>(gg, src, w, bias, bias_mode, out);
+	const bool act = ep && ep->act_kind != CATTL3_ACT_NONE;
+	CATTL3_REQUIRE(out || act, "gather GEMM: no output tensor");
+	gather_gemm_kernel<S><<<grid, 256, 0, ctx->stream>>>(gg, src, w, bias, bias_mode, out,
+			act ? ep->act_kind : CATTL3_ACT_NONE, act ? (S) ep->act_param : (S) 0, act ? (S*) ep->act_out : (S*) nullptr);
 	CATTL3_LAUNCHED(ctx);
 	return CATTL3_OK;
 }
-template int simt_gather_gemm<float>(cattl3_ctx*, const GatherGeom&, const float*, const float*, const float*, int, float*);
-template int simt_gather_gemm<double>(cattl3_ctx*, const GatherGeom&, const double*, const double*, const double*, int, double*);
+template int simt_gather_gemm<float>(cattl3_ctx*, const GatherGeom&, const float*, const float*, const float*, int, float*,
+		const EpilogueArgs*);
+template int simt_gather_gemm<double>(cattl3_ctx*, const GatherGeom&, const double*, const double*, const double*, int, double*,
+		const EpilogueArgs*);
 
 // ------------------------------------------------------------------------------------------------
 // weight gradient: dw(tap, r, j) += sum_m src(m, tap, r) * plain[m + M*j]
@@ -286,6 +293,59 @@ int colsum_accumulate(cattl3_ctx* ctx, int64_t rows, int64_t cols, const S* a, S
 	CATTL3_LAUNCHED(ctx);
 	return CATTL3_OK;
 }
+// Shifted column statistics for a following BatchNormLayer where the GEMM epilogue did not produce them (SIMT path):
+// grid (cols, chunks); per-chunk double partials, then a fixed-order sum.
+template<typename S>
+__global__ void __launch_bounds__(256) colstats_partial_kernel(long long rows, long long chunk, const S* __restrict__ a,
+		const S* __restrict__ shift, double* __restrict__ partial) {
+	__shared__ double r1[256], r2[256];
+	const long long j = blockIdx.x;
+	const S* col = a + rows * j;
+	const double K = (double) shift[j];
+	const long long lo = (long long) blockIdx.y * chunk, hi = lo + chunk < rows ? lo + chunk : rows;
+	double s1 = 0, s2 = 0;
+	for (long long i = lo + threadIdx.x; i < hi; i += 256) { const double d = (double) col[i] - K; s1 += d; s2 += d * d; }
+	r1[threadIdx.x] = s1; r2[threadIdx.x] = s2;
+	__syncthreads();
+	for (int o = 128; o > 0; o >>= 1) {
+		if ((int) threadIdx.x < o) { r1[threadIdx.x] += r1[threadIdx.x + o]; r2[threadIdx.x] += r2[threadIdx.x + o]; }
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		partial[(j * gridDim.y + blockIdx.y) * 2] = r1[0];
+		partial[(j * gridDim.y + blockIdx.y) * 2 + 1] = r2[0];
+	}
+}
+__global__ void __launch_bounds__(256) colstats_final_kernel(long long cols, int chunks, const double* __restrict__ partial,
+		double* __restrict__ col_stats) {
+	const long long j = blockIdx.x * 256ll + threadIdx.x;
+	if (j >= cols) return;
+	double s1 = 0, s2 = 0;
+	for (int c = 0; c < chunks; ++c) { s1 += partial[(j * chunks + c) * 2]; s2 += partial[(j * chunks + c) * 2 + 1]; }
+	col_stats[j] = s1;
+	col_stats[cols + j] = s2;
+}
+
+template<typename S>
+int colstats_shifted(cattl3_ctx* ctx, int64_t rows, int64_t cols, const S* a, const S* shift, double* col_stats) {
+	long long chunks = ceil_div(8ll * ctx->sm_count, cols);
+	const long long maxc = ceil_div(rows, 2048);
+	if (chunks > maxc) chunks = maxc;
+	if (chunks < 1) chunks = 1;
+	const long long chunk = ceil_div(rows, chunks);
+	chunks = ceil_div(rows, chunk);
+	CATTL3_CHECK(ensure_buffer(ctx, &ctx->stat_ws, &ctx->stat_ws_bytes, (size_t) (cols * chunks * 2) * sizeof(double)));
+	dim3 grid((unsigned) cols, (unsigned) chunks);
+	colstats_partial_kernel<S><<<grid, 256, 0, ctx->stream>>>(rows, chunk, a, shift, (double*) ctx->stat_ws);
+	CATTL3_LAUNCHED(ctx);
+	colstats_final_kernel<<<(unsigned) ceil_div(cols, 256), 256, 0, ctx->stream>>>(cols, (int) chunks,
+			(const double*) ctx->stat_ws, col_stats);
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+template int colstats_shifted<float>(cattl3_ctx*, int64_t, int64_t, const float*, const float*, double*);
+template int colstats_shifted<double>(cattl3_ctx*, int64_t, int64_t, const double*, const double*, double*);
+
 template int colsum_accumulate<float>(cattl3_ctx*, int64_t, int64_t, const float*, float*);
 template int colsum_accumulate<double>(cattl3_ctx*, int64_t, int64_t, const double*, double*);
 

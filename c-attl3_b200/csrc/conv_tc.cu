@@ -17,7 +17,7 @@
 // column as 32 consecutive floats per warp: y(m + M*f) is written fully coalesced.
 #include <cuda.h>
 
-#include "common.cuh"
+#include "activations.cuh"
 
 namespace cattl3 {
 
@@ -224,6 +224,11 @@ struct TcGemmParams {
 	// oH x oW image (dense: h0 = w0 = 0, hs = ws = 1, oH = OH, oW = OW); out_cs = N*oH*oW is the channel stride
 	int h0, hs, oH, w0, ws, oW;
 	long long out_cs;
+	// fused epilogue (cattl3_epilogue): out may be null when act_out is given; stat_partial = per-CTA column sums
+	int act_kind;
+	float act_param;
+	float* act_out;
+	double* stat_partial;   // [gridDim.x][2][j_tiles * BN] or null
 };
 
 // Gather GEMM (conv / dense forward, stride-1 input gradient):
@@ -250,6 +255,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 	uint64_t* acc_empty = acc_full + 2;
 	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 	float* sbias = reinterpret_cast<float*>(bars + 32);  // 256 floats behind the barriers
+	double* sstat = reinterpret_cast<double*>(sbias + 256);  // [4 warps][2][BN] column sums (only with stat_partial)
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int T = p.RH * p.RW;
@@ -345,33 +351,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 			}
 		}
 	} else if (warp < 6) {
-		// ===== epilogue warps 2..5: TMEM -> registers -> (+bias) -> coalesced global stores =====
+		// ===== epilogue warps 2..5: TMEM -> registers -> (+bias, activation, column statistics) -> coalesced stores =====
 		// The per-filter bias of the tile is staged in shared memory while the MMAs of the tile still run,
 		// so the drain itself is tcgen05.ld + add + store with no dependent global loads.
 		const int q = warp & 3;  // TMEM lane quarter this warp may access
 		const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
 		int acc = 0; uint32_t acc_ph = 0;
 		int staged_jt = -1;
+		const bool stats = p.stat_partial != nullptr;
+		const int j_pad = p.j_tiles * p.BN;
+		double* my_stat = sstat + q * 2 * p.BN;
+		if (stats) {
+			for (int c = et; c < 8 * p.BN; c += 128) sstat[c] = 0.0;
+			asm volatile("bar.sync 1, 128;" ::: "memory");
+		}
+		// Column sums of this CTA's tiles of filter tile `jt` -> its slot of the partial buffer (plain stores:
+		// the tile order of a CTA visits every jt at most once, in increasing order).
+		auto flush_stats = [&](int jt) {
+			asm volatile("bar.sync 1, 128;" ::: "memory");
+			for (int c = et; c < 2 * p.BN; c += 128) {
+				const int k = c / p.BN, col = c % p.BN;
+				const double t = ((sstat[(0 * 2 + k) * p.BN + col] + sstat[(1 * 2 + k) * p.BN + col]) +
+						sstat[(2 * 2 + k) * p.BN + col]) + sstat[(3 * 2 + k) * p.BN + col];
+				p.stat_partial[((long long) blockIdx.x * 2 + k) * j_pad + jt * p.BN + col] = t;
+				sstat[(0 * 2 + k) * p.BN + col] = 0.0; sstat[(1 * 2 + k) * p.BN + col] = 0.0;
+				sstat[(2 * 2 + k) * p.BN + col] = 0.0; sstat[(3 * 2 + k) * p.BN + col] = 0.0;
+			}
+			asm volatile("bar.sync 1, 128;" ::: "memory");
+		};
 		for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
 			const int mt = tile % p.m_tiles, jt = tile / p.m_tiles;
-			if (p.bias_mode == 1 && jt != staged_jt) {
-				asm volatile("bar.sync 1, 128;" ::: "memory");  // nobody still reads the previous tile's bias
-				for (int c = et; c < p.BN; c += 128) {
-					const int j = jt * p.BN + c;
-					sbias[c] = j < p.J ? __ldg(p.bias + j) : 0.f;
+			if (jt != staged_jt) {
+				if (stats && staged_jt >= 0) flush_stats(staged_jt);
+				if (p.bias_mode == 1) {
+					asm volatile("bar.sync 1, 128;" ::: "memory");  // nobody still reads the previous tile's bias
+					for (int c = et; c < p.BN; c += 128) {
+						const int j = jt * p.BN + c;
+						sbias[c] = j < p.J ? __ldg(p.bias + j) : 0.f;
+					}
+					asm volatile("bar.sync 1, 128;" ::: "memory");
 				}
-				asm volatile("bar.sync 1, 128;" ::: "memory");
 				staged_jt = jt;
 			}
 			mbar_wait(&acc_full[acc], acc_ph);
 			tc_fence_after();
 			const long long m = (long long) mt * TC_BM + 32 * q + lane;
 			const bool m_ok = m < p.M;
+			// M is a multiple of 32 (N % 32 == 0), so the 32 rows of a warp are valid or invalid together
+			const bool warp_ok = (long long) mt * TC_BM + 32 * q < p.M;
 			const long long gpix = m / p.N;
 			const int gi = (int) (gpix % p.OH), gj = (int) (gpix / p.OH);
 			const long long pix = (p.h0 + p.hs * gi) + (long long) p.oH * (p.w0 + p.ws * gj);  // pixel in the output tensor
 			const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16) + (uint32_t) (acc * p.BN);
-			float* out_m = p.out + (m % p.N) + p.N * pix + p.out_cs * (long long) (jt * p.BN);
+			const long long out_off = (m % p.N) + p.N * pix + p.out_cs * (long long) (jt * p.BN);
+			float* out_m = p.out ? p.out + out_off : nullptr;
+			float* act_m = p.act_out ? p.act_out + out_off : nullptr;
 			const int jn = p.J - jt * p.BN < p.BN ? p.J - jt * p.BN : p.BN;  // valid columns of this tile
 			for (int c0 = 0; c0 < p.BN; c0 += 16) {
 				float v[16], bv[16];
@@ -391,14 +425,61 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 					for (int i = 0; i < 16; ++i) bv[i] = 0.f;
 				}
 				tmem_ld_wait();
+				if (stats && warp_ok) {
+					// Per column: sum and sum of squares of the 32 accumulators (= y - bias) of this warp's rows.
+					// Shifted by lane 0's value so that the fp32 part works on magnitudes ~ sigma; 32 values
+					// (16 sums, 16 square sums) are reduced over the 32 lanes by recursive halving (31 shuffles:
+					// lane L ends up with value L), then re-based to shift 0 and accumulated in double.
+					float t[32];
+					float kk = 0.f;
+					#pragma unroll
+					for (int i = 0; i < 16; ++i) {
+						const float k = __shfl_sync(0xffffffffu, v[i], 0);
+						const float d = v[i] - k;
+						t[i] = d; t[16 + i] = d * d;
+						if ((lane & 15) == i) kk = k;
+					}
+					#pragma unroll
+					for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+						const bool upper = (lane & off) != 0;
+						#pragma unroll
+						for (int i = 0; i < n / 2; ++i) {
+							const float send = upper ? t[i] : t[i + n / 2];
+							const float keep = upper ? t[i + n / 2] : t[i];
+							t[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+						}
+					}
+					const float other = __shfl_xor_sync(0xffffffffu, t[0], 16);
+					if (lane < 16) {
+						const double K = (double) kk, s1 = (double) t[0], s2 = (double) other;
+						my_stat[c0 + lane] += s1 + 32.0 * K;
+						my_stat[p.BN + c0 + lane] += s2 + 2.0 * K * s1 + 32.0 * K * K;
+					}
+				}
 				if (m_ok) {
-					if (c0 + 16 <= jn) {
+					#pragma unroll
+					for (int i = 0; i < 16; ++i) v[i] += bv[i];
+					if (out_m) {
+						if (c0 + 16 <= jn) {
+							#pragma unroll
+							for (int i = 0; i < 16; ++i) out_m[p.out_cs * (long long) (c0 + i)] = v[i];
+						} else {
+							#pragma unroll
+							for (int i = 0; i < 16; ++i)
+								if (c0 + i < jn) out_m[p.out_cs * (long long) (c0 + i)] = v[i];
+						}
+					}
+					if (act_m) {
 						#pragma unroll
-						for (int i = 0; i < 16; ++i) out_m[p.out_cs * (long long) (c0 + i)] = v[i] + bv[i];
-					} else {
-						#pragma unroll
-						for (int i = 0; i < 16; ++i)
-							if (c0 + i < jn) out_m[p.out_cs * (long long) (c0 + i)] = v[i] + bv[i];
+						for (int i = 0; i < 16; ++i) v[i] = act_fwd_rt<float>(p.act_kind, v[i], p.act_param);
+						if (c0 + 16 <= jn) {
+							#pragma unroll
+							for (int i = 0; i < 16; ++i) act_m[p.out_cs * (long long) (c0 + i)] = v[i];
+						} else {
+							#pragma unroll
+							for (int i = 0; i < 16; ++i)
+								if (c0 + i < jn) act_m[p.out_cs * (long long) (c0 + i)] = v[i];
+						}
 					}
 				}
 			}
@@ -407,6 +488,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 			if (lane == 0) mbar_arrive(&acc_empty[acc]);
 			if (++acc == p.nacc) { acc = 0; acc_ph ^= 1; }
 		}
+		if (stats && staged_jt >= 0) flush_stats(staged_jt);
 	} else {
 		// ===== converter warps 6..9: raw A tile (shared memory) -> hi | lo (tensor memory) =====
 		// The tile lies in shared memory as 128 / nb unswizzled boxes of KB rows x nb batch entries; row m of the
@@ -481,7 +563,6 @@ static int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint6
 	return CATTL3_OK;
 }
 
-static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 constexpr int TC_SMEM_LIMIT = 227 * 1024 - 2560;
 
@@ -494,9 +575,24 @@ bool tc_gather_gemm_supported(const cattl3_ctx*, const GatherGeom& gg) {
 	return get_encode() != nullptr;
 }
 
+// col_stats[k * J + j] = sum over the CTAs' partials, in CTA order (deterministic).
+__global__ void __launch_bounds__(256) colstats_reduce_tc_kernel(const double* __restrict__ partial, int ctas, int j_pad, int J,
+		double* __restrict__ col_stats) {
+	const int i = blockIdx.x * 256 + threadIdx.x;
+	if (i >= 2 * J) return;
+	const int k = i / J, j = i % J;
+	double s = 0.0;
+	for (int c = 0; c < ctas; ++c) s += partial[((long long) c * 2 + k) * j_pad + j];
+	col_stats[i] = s;
+}
+
 int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const float* w, const float* bias,
-		int bias_mode, float* out) {
-	CATTL3_REQUIRE(aligned16(src) && aligned16(out), "tcgen05 path needs 16-byte aligned tensors");
+		int bias_mode, float* out, const EpilogueArgs* ep) {
+	CATTL3_REQUIRE(aligned16(src) && (!out || aligned16(out)), "tcgen05 path needs 16-byte aligned tensors");
+	const bool want_stats = ep && ep->col_stats;
+	const bool want_act = ep && ep->act_kind != CATTL3_ACT_NONE;
+	CATTL3_REQUIRE(out || want_act, "gather GEMM: no output tensor");
+	CATTL3_REQUIRE(!want_stats || bias_mode == 1, "column statistics need a per-column bias");
 	const int T = gg.RH * gg.RW;
 	const int BN = gg.J >= 256 ? 256 : round_up(gg.J, 16);
 	// 32-element k-blocks (128 B weight rows) where shared and tensor memory allow four stages of them
@@ -544,17 +640,28 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 	// epilogue of one tile overlaps the MMAs of the next
 	p.nacc = 2 * BN + 4 * 2 * KB <= 512 ? 2 : 1;
 	const int stage_bytes = TC_BM * KB * 4 + 2 * BN * KB * 4;
-	int stages = TC_SMEM_LIMIT / stage_bytes;
+	const int stat_bytes = want_stats ? 4 * 2 * BN * 8 : 0;
+	int stages = (TC_SMEM_LIMIT - stat_bytes) / stage_bytes;
 	const int tmem_stages = (512 - p.nacc * BN) / (2 * KB);
 	if (stages > tmem_stages) stages = tmem_stages;
 	if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
 	p.stages = stages;
 	p.bias_mode = bias_mode; p.bias = bias; p.out = out;
 	// at least half of the shared memory: two co-resident CTAs would deadlock allocating 512 TMEM columns each
-	size_t smem_bytes = (size_t) stages * stage_bytes + 1024 + 256 + 1024;  // alignment slack, barriers, bias
+	size_t smem_bytes = (size_t) stages * stage_bytes + 1024 + 256 + 1024 + stat_bytes;  // alignment slack, barriers, bias, sums
 	if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
 	const int tiles = p.m_tiles * p.j_tiles;
 	const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+	p.act_kind = want_act ? ep->act_kind : CATTL3_ACT_NONE;
+	p.act_param = want_act ? (float) ep->act_param : 0.f;
+	p.act_out = want_act ? (float*) ep->act_out : nullptr;
+	p.stat_partial = nullptr;
+	if (want_stats) {
+		const size_t bytes = (size_t) grid * 2 * j_pad * sizeof(double);
+		CATTL3_CHECK(ensure_buffer(ctx, &ctx->stat_ws, &ctx->stat_ws_bytes, bytes));
+		CATTL3_CUDA(cudaMemsetAsync(ctx->stat_ws, 0, bytes, ctx->stream));
+		p.stat_partial = (double*) ctx->stat_ws;
+	}
 	if (KB == 32) {
 		CATTL3_CUDA(cudaFuncSetAttribute(tc_gather_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 		tc_gather_gemm_kernel<32><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(tm_a, tm_b, p);
@@ -563,6 +670,11 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 		tc_gather_gemm_kernel<16><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(tm_a, tm_b, p);
 	}
 	CATTL3_LAUNCHED(ctx);
+	if (want_stats) {
+		colstats_reduce_tc_kernel<<<(unsigned) ceil_div(2 * gg.J, 256), 256, 0, ctx->stream>>>(p.stat_partial, grid, j_pad,
+				gg.J, ep->col_stats);
+		CATTL3_LAUNCHED(ctx);
+	}
 	return CATTL3_OK;
 }
 

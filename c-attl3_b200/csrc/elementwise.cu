@@ -2,57 +2,9 @@
 // normalisation, the fused optimizer step and the small network-glue helpers.  All kernels are
 // grid-stride with 16-byte vector accesses where alignment allows, sized in multiples of the SM
 // count (common.cuh: ew_grid); none of them stages through shared memory except reductions.
-#include "common.cuh"
+#include "activations.cuh"
 
 namespace cattl3 {
-
-template<typename S> struct V16;
-template<> struct V16<float> { typedef float4 type; static constexpr int G = 4; };
-template<> struct V16<double> { typedef double2 type; static constexpr int G = 2; };
-
-static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-
-template<typename S> __device__ __forceinline__ S dev_exp(S v);
-template<> __device__ __forceinline__ float dev_exp<float>(float v) { return expf(v); }
-template<> __device__ __forceinline__ double dev_exp<double>(double v) { return exp(v); }
-template<typename S> __device__ __forceinline__ S dev_log(S v);
-template<> __device__ __forceinline__ float dev_log<float>(float v) { return logf(v); }
-template<> __device__ __forceinline__ double dev_log<double>(double v) { return log(v); }
-template<typename S> __device__ __forceinline__ S dev_tanh(S v);
-template<> __device__ __forceinline__ float dev_tanh<float>(float v) { return tanhf(v); }
-template<> __device__ __forceinline__ double dev_tanh<double>(double v) { return tanh(v); }
-template<typename S> __device__ __forceinline__ S dev_sqrt(S v);
-template<> __device__ __forceinline__ float dev_sqrt<float>(float v) { return sqrtf(v); }
-template<> __device__ __forceinline__ double dev_sqrt<double>(double v) { return sqrt(v); }
-
-// ---- activations -------------------------------------------------------------------------------
-// Formulas follow the reference layer by layer (see include/cattl3_b200.h for file:line).
-template<typename S, int KIND>
-__device__ __forceinline__ S act_fwd(S x, S a) {
-	if (KIND == CATTL3_ACT_RELU) return x > (S) 0 ? x : (S) 0;              // cwiseMax(0)
-	if (KIND == CATTL3_ACT_LEAKY_RELU) { S ax = x * a; return x > ax ? x : ax; } // cwiseMax(x * alpha)
-	if (KIND == CATTL3_ACT_ELU) return x >= (S) 0 ? x : a * (dev_exp<S>(x) - (S) 1);
-	if (KIND == CATTL3_ACT_SWISH) return x * ((S) 1 / (dev_exp<S>(-a * x) + (S) 1));
-	if (KIND == CATTL3_ACT_SIGMOID) return (S) 1 / (dev_exp<S>(-x) + (S) 1);
-	if (KIND == CATTL3_ACT_TANH) return dev_tanh<S>(x);
-	if (KIND == CATTL3_ACT_SOFTPLUS) return dev_log<S>(dev_exp<S>(x) + (S) 1);
-	return x;
-}
-
-template<typename S, int KIND>
-__device__ __forceinline__ S act_bwd(S x, S y, S g, S a) {
-	if (KIND == CATTL3_ACT_RELU) return x >= (S) 0 ? g : (S) 0;             // derivative 1 at x == 0
-	if (KIND == CATTL3_ACT_LEAKY_RELU) return x >= (S) 0 ? g : a * g;
-	if (KIND == CATTL3_ACT_ELU) return x >= (S) 0 ? g : (y + a) * g;
-	if (KIND == CATTL3_ACT_SWISH) {
-		S s = (S) 1 / (dev_exp<S>(-a * x) + (S) 1);
-		return s * (((S) 1 - s) * a * x + (S) 1) * g;
-	}
-	if (KIND == CATTL3_ACT_SIGMOID) return (y * ((S) 1 - y)) * g;
-	if (KIND == CATTL3_ACT_TANH) return ((S) 1 - y * y) * g;
-	if (KIND == CATTL3_ACT_SOFTPLUS) return ((S) 1 / (dev_exp<S>(-x) + (S) 1)) * g;
-	return g;
-}
 
 template<typename S, int KIND>
 __global__ void __launch_bounds__(256) act_fwd_kernel(long long count, int vec_ok, S alpha,
@@ -502,6 +454,59 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(long long L, long long ch
 		yg[i] = ((xg[i] - mu) * sc) * gm + bt;)
 }
 
+// Statistics from the column sums a kernel layer's epilogue produced (cattl3_epilogue::col_stats): S1 = sum (x - shift),
+// S2 = sum (x - shift)^2 per group.  Same outputs as bn_stats_final_kernel.
+template<typename S>
+__global__ void __launch_bounds__(128) bn_stats_from_sums_kernel(long long groups, long long L,
+		const double* __restrict__ col_stats, const S* __restrict__ shift, S eps, S decay, int running_init,
+		S* __restrict__ running_mean, S* __restrict__ running_inv_sd, S* __restrict__ saved_mean,
+		S* __restrict__ saved_inv_sd) {
+	const long long g = blockIdx.x * 128ll + threadIdx.x;
+	if (g >= groups) return;
+	const double m1 = col_stats[g] / (double) L;
+	double var = col_stats[groups + g] / (double) L - m1 * m1;
+	var = var < 0 ? 0 : var;
+	const S mean = (S) ((double) shift[g] + m1);
+	const S inv_sd = (S) (1.0 / sqrt(var + (double) eps));
+	saved_mean[g] = mean;
+	saved_inv_sd[g] = inv_sd;
+	if (running_init) {
+		running_mean[g] = ((S) 1 - decay) * running_mean[g] + decay * mean;
+		running_inv_sd[g] = ((S) 1 - decay) * running_inv_sd[g] + decay * inv_sd;
+	} else {
+		running_mean[g] = mean;
+		running_inv_sd[g] = inv_sd;
+	}
+}
+
+// bn_apply_kernel with the following element-wise activation layer applied in the same pass: y (the activation's
+// cached input; may be null) and act_out = f(y).
+template<typename S>
+__global__ void __launch_bounds__(256) bn_apply_act_kernel(long long L, long long chunk, int vec, const S* __restrict__ x,
+		const S* __restrict__ mean, const S* __restrict__ inv_sd, const S* __restrict__ gamma,
+		const S* __restrict__ beta, S* __restrict__ y, int act_kind, S act_param, S* __restrict__ act_out) {
+	typedef typename V16<S>::type V;
+	const long long g = blockIdx.x;
+	const S mu = mean[g], sc = inv_sd[g], gm = gamma[g], bt = beta[g];
+	const long long lo = (long long) blockIdx.y * chunk;
+	const long long hi = lo + chunk < L ? lo + chunk : L;
+	const S* xg = x + g * L;
+	S* yg = y ? y + g * L : nullptr;
+	S* ag = act_out + g * L;
+	BN_FOREACH(S, vec, lo, hi,
+		V v = *reinterpret_cast<const V*>(xg + i);
+		S* e = reinterpret_cast<S*>(&v);
+		_Pragma("unroll")
+		for (int k = 0; k < G_; ++k) e[k] = ((e[k] - mu) * sc) * gm + bt;
+		if (yg) *reinterpret_cast<V*>(yg + i) = v;
+		_Pragma("unroll")
+		for (int k = 0; k < G_; ++k) e[k] = act_fwd_rt<S>(act_kind, e[k], act_param);
+		*reinterpret_cast<V*>(ag + i) = v;,
+		const S t = ((xg[i] - mu) * sc) * gm + bt;
+		if (yg) yg[i] = t;
+		ag[i] = act_fwd_rt<S>(act_kind, t, act_param);)
+}
+
 template<typename S>
 __global__ void __launch_bounds__(256) bn_bwd_partial_kernel(long long L, long long chunk, int vec,
 		const S* __restrict__ x, const S* __restrict__ mean, const S* __restrict__ inv_sd,
@@ -610,6 +615,36 @@ int batchnorm_forward(cattl3_ctx* ctx, int per_channel, int n, int h, int w, int
 	} else {
 		bn_apply_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, vec, x, running_mean, running_inv_sd, gamma, beta, y);
 	}
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+
+template<typename S>
+int batchnorm_forward_stats(cattl3_ctx* ctx, int per_channel, int n, int h, int w, int c, int running_init, S decay,
+		S eps, const S* x, const double* col_stats, const S* shift, const S* gamma, const S* beta, S* running_mean,
+		S* running_inv_sd, S* saved_mean, S* saved_inv_sd, S* y, int act_kind, S act_param, S* act_out) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && x && col_stats && shift && gamma && beta && running_mean &&
+			running_inv_sd && saved_mean && saved_inv_sd, "batchnorm_forward_stats: bad arguments");
+	CATTL3_REQUIRE(act_kind >= CATTL3_ACT_NONE && act_kind < CATTL3_ACT_SOFTMAX, "batchnorm_forward_stats: activation kind %d "
+			"cannot be fused", act_kind);
+	CATTL3_REQUIRE(act_kind == CATTL3_ACT_NONE ? y != nullptr : act_out != nullptr, "batchnorm_forward_stats: no output tensor");
+	const long long groups = per_channel ? c : (long long) h * w * c;
+	const long long L = per_channel ? (long long) n * h * w : n;
+	CATTL3_REQUIRE(groups <= 2147483647ll, "batchnorm: too many groups");
+	int chunks, threads;
+	long long chunk;
+	bn_partition(ctx, groups, L, &chunks, &chunk, &threads);
+	dim3 grid((unsigned) groups, (unsigned) chunks);
+	bn_stats_from_sums_kernel<S><<<(unsigned) ceil_div(groups, 128), 128, 0, ctx->stream>>>(groups, L, col_stats, shift, eps,
+			decay, running_init, running_mean, running_inv_sd, saved_mean, saved_inv_sd);
+	CATTL3_LAUNCHED(ctx);
+	const int vec = L % V16<S>::G == 0 && aligned16(x) && (!y || aligned16(y)) && (!act_out || aligned16(act_out));
+	if (act_kind == CATTL3_ACT_NONE)
+		bn_apply_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, vec, x, saved_mean, saved_inv_sd, gamma, beta, y);
+	else
+		bn_apply_act_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, vec, x, saved_mean, saved_inv_sd, gamma, beta, y,
+				act_kind, act_param, act_out);
 	CATTL3_LAUNCHED(ctx);
 	return CATTL3_OK;
 }
@@ -834,6 +869,10 @@ int cattl3_batchnorm_forward_f32(cattl3_ctx* c, int pc, int32_t n, int32_t h, in
 	return batchnorm_forward<float>(c, pc, n, h, w, ch, training, rinit, decay, eps, x, gamma, beta, rm, rs, sm, ss, y); }
 int cattl3_batchnorm_forward_f64(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, int training, int rinit, double decay, double eps, const double* x, const double* gamma, const double* beta, double* rm, double* rs, double* sm, double* ss, double* y) {
 	return batchnorm_forward<double>(c, pc, n, h, w, ch, training, rinit, decay, eps, x, gamma, beta, rm, rs, sm, ss, y); }
+int cattl3_batchnorm_forward_stats_f32(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, int rinit, float decay, float eps, const float* x, const double* cs, const float* shift, const float* gamma, const float* beta, float* rm, float* rs, float* sm, float* ss, float* y, int ak, float ap, float* ao) {
+	return batchnorm_forward_stats<float>(c, pc, n, h, w, ch, rinit, decay, eps, x, cs, shift, gamma, beta, rm, rs, sm, ss, y, ak, ap, ao); }
+int cattl3_batchnorm_forward_stats_f64(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, int rinit, double decay, double eps, const double* x, const double* cs, const double* shift, const double* gamma, const double* beta, double* rm, double* rs, double* sm, double* ss, double* y, int ak, double ap, double* ao) {
+	return batchnorm_forward_stats<double>(c, pc, n, h, w, ch, rinit, decay, eps, x, cs, shift, gamma, beta, rm, rs, sm, ss, y, ak, ap, ao); }
 int cattl3_batchnorm_backward_f32(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, const float* x, const float* gamma, const float* sm, const float* ss, const float* dy, float* dgamma, float* dbeta, float* dx) {
 	return batchnorm_backward<float>(c, pc, n, h, w, ch, x, gamma, sm, ss, dy, dgamma, dbeta, dx); }
 int cattl3_batchnorm_backward_f64(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, const double* x, const double* gamma, const double* sm, const double* ss, const double* dy, double* dgamma, double* dbeta, double* dx) {

@@ -55,7 +55,8 @@ enum {
 	CATTL3_ACT_SIGMOID = 4,   /* C-ATTL3/layer/activation/SigmoidActivationLayer.hpp */
 	CATTL3_ACT_TANH = 5,      /* C-ATTL3/layer/activation/TanhActivationLayer.hpp */
 	CATTL3_ACT_SOFTPLUS = 6,  /* C-ATTL3/layer/activation/SoftplusActivationLayer.hpp:40-52 */
-	CATTL3_ACT_SOFTMAX = 7    /* C-ATTL3/layer/activation/SoftmaxActivationLayer.hpp:49-78 (alpha = epsilon) */
+	CATTL3_ACT_SOFTMAX = 7,   /* C-ATTL3/layer/activation/SoftmaxActivationLayer.hpp:49-78 (alpha = epsilon) */
+	CATTL3_ACT_NONE = -1      /* cattl3_epilogue: no activation fused */
 };
 
 enum {
@@ -124,6 +125,27 @@ typedef struct cattl3_opt_step {
 	double lr_epoch, c1, c1n, c2;
 	double l2_lambda;
 } cattl3_opt_step;
+
+/*
+ * What a kernel layer's forward pass does in its epilogue besides adding the bias -- the work of the layer that
+ * FOLLOWS it in the reference's layer loop (FeedforwardNeuralNetwork.hpp:112-118), done while the output tile is
+ * still on chip:
+ *  - act_kind != CATTL3_ACT_NONE: the element-wise ActivationLayer (kinds 0-6, formulas as cattl3_activation_forward):
+ *    act_out = f(y).  The pre-activation y is still written when the y argument of the call is non-null (ReLU,
+ *    LeakyReLU, ELU, Swish and Softplus layers cache their input for pass_back,
+ *    e.g. ReLUActivationLayer.hpp:45-57); pass y = NULL to skip it (inference, Sigmoid / Tanh).
+ *  - col_stats != NULL: the first reduction of a following BatchNormLayer (BatchNormLayer.hpp:225-233): per output
+ *    column j (filter / dense output), over all rows m = N*OH*OW: col_stats[j] = sum_m (y(m,j) - b(j)),
+ *    col_stats[J + j] = sum_m (y(m,j) - b(j))^2, in double whatever the scalar type (shifted by the bias so that the
+ *    later E[d^2] - E[d]^2 does not cancel).  cattl3_batchnorm_forward_stats_* consumes them.
+ */
+typedef struct cattl3_epilogue {
+	int32_t act_kind;
+	int32_t reserved;
+	double act_param;   /* alpha / beta of the activation */
+	void* act_out;      /* device, same type and shape as y */
+	double* col_stats;  /* device, 2 * J doubles */
+} cattl3_epilogue;
 
 typedef struct cattl3_ctx cattl3_ctx; /* opaque: device, stream, workspaces, cached TMA descriptors */
 
@@ -196,6 +218,17 @@ int cattl3_dense_forward_f64(cattl3_ctx*, int32_t n, int32_t in, int32_t out, co
 int cattl3_dense_backward_f32(cattl3_ctx*, int32_t n, int32_t in, int32_t out, const float* x, const float* w, const float* dy, float* dw, float* db, float* dx);
 int cattl3_dense_backward_f64(cattl3_ctx*, int32_t n, int32_t in, int32_t out, const double* x, const double* w, const double* dy, double* dw, double* db, double* dx);
 
+/*
+ * Forward passes with a fused epilogue (cattl3_epilogue above): ConvKernelLayer / DenseKernelLayer followed by an
+ * ActivationLayer and / or the statistics pass of a BatchNormLayer.  y may be NULL when ep->act_out is given.
+ * On the tcgen05 path everything happens in the GEMM's epilogue; on the SIMT path the activation is fused and the
+ * column statistics are a separate reduction over y (same results, one more read).
+ */
+int cattl3_conv_forward_fused_f32(cattl3_ctx*, const cattl3_conv_geom*, const float* x, const float* w, const float* b, float* y, const cattl3_epilogue* ep);
+int cattl3_conv_forward_fused_f64(cattl3_ctx*, const cattl3_conv_geom*, const double* x, const double* w, const double* b, double* y, const cattl3_epilogue* ep);
+int cattl3_dense_forward_fused_f32(cattl3_ctx*, int32_t n, int32_t in, int32_t out, const float* x, const float* w, const float* b, float* y, const cattl3_epilogue* ep);
+int cattl3_dense_forward_fused_f64(cattl3_ctx*, int32_t n, int32_t in, int32_t out, const double* x, const double* w, const double* b, double* y, const cattl3_epilogue* ep);
+
 /* Host-buffer forms of the convolution layer: what the reference's Layer API hands over
  * (pass_forward(Data in, bool) / pass_back(Data out_grad), Layer.hpp:126,137) -- host tensors in,
  * host tensors out, host<->device copies inside the call.  Parameters stay device resident. */
@@ -227,6 +260,16 @@ int cattl3_pool_backward_f64(cattl3_ctx*, int kind, const cattl3_pool_geom*, con
  */
 int cattl3_batchnorm_forward_f32(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, int training, int running_initialised, float decay, float eps, const float* x, const float* gamma, const float* beta, float* running_mean, float* running_inv_sd, float* saved_mean, float* saved_inv_sd, float* y);
 int cattl3_batchnorm_forward_f64(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, int training, int running_initialised, double decay, double eps, const double* x, const double* gamma, const double* beta, double* running_mean, double* running_inv_sd, double* saved_mean, double* saved_inv_sd, double* y);
+/*
+ * Training forward pass whose statistics reduction already happened in the producing kernel layer's epilogue:
+ * col_stats (2 * groups doubles, cattl3_epilogue) are the sums of (x - shift) and (x - shift)^2 per group, shift = the
+ * producer's bias (groups elements).  mean = shift + S1/L, var = S2/L - (S1/L)^2 in double; the rest (saved
+ * statistics, running averages, y) is cattl3_batchnorm_forward with training = 1.  The normalise pass can apply a
+ * following element-wise activation as well: act_kind != CATTL3_ACT_NONE writes act_out = f(y) (y, the activation's
+ * cached input, is still written unless NULL).
+ */
+int cattl3_batchnorm_forward_stats_f32(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, int running_initialised, float decay, float eps, const float* x, const double* col_stats, const float* shift, const float* gamma, const float* beta, float* running_mean, float* running_inv_sd, float* saved_mean, float* saved_inv_sd, float* y, int act_kind, float act_param, float* act_out);
+int cattl3_batchnorm_forward_stats_f64(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, int running_initialised, double decay, double eps, const double* x, const double* col_stats, const double* shift, const double* gamma, const double* beta, double* running_mean, double* running_inv_sd, double* saved_mean, double* saved_inv_sd, double* y, int act_kind, double act_param, double* act_out);
 /* dgamma / dbeta ACCUMULATE; dx may be NULL (input layer). */
 int cattl3_batchnorm_backward_f32(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, const float* x, const float* gamma, const float* saved_mean, const float* saved_inv_sd, const float* dy, float* dgamma, float* dbeta, float* dx);
 int cattl3_batchnorm_backward_f64(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, const double* x, const double* gamma, const double* saved_mean, const double* saved_inv_sd, const double* dy, double* dgamma, double* dbeta, double* dx);

@@ -1,0 +1,148 @@
+"""-m gpu: the fused forward epilogues (cattl3_epilogue: bias + ActivationLayer + BatchNorm statistics) of the
+kernel layers against the oracle's layer-by-layer chain conv -> activation / conv -> batch-norm (-> activation),
+i.e. what the reference's layer loop computes with separate layers (FeedforwardNeuralNetwork.hpp:112-118).
+Tolerances: 1e-4 float / 1e-10 double, norm-relative."""
+import numpy as np
+import pytest
+
+import cases as C
+from oracle.binding import Geom, conv_out_dims
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def U():
+    import gpu_util
+    return gpu_util
+
+
+def _tol(dt):
+    return C.TOL[np.dtype(dt)]
+
+
+# (case, dtype, path it must take)
+FUSED_CONV = [("c2_small", np.float32, "tcgen05"), ("c2_small_f256", np.float32, "tcgen05"),
+              ("ragged_c", np.float32, "tcgen05"), ("c2_stride2", np.float32, "tcgen05"),
+              ("cifar_conv1", np.float32, "simt"), ("gt_rank3", np.float64, "simt"), ("c2_small", np.float64, "simt"),
+              ("ragged", np.float64, "simt")]
+
+
+@pytest.mark.parametrize("name,dt,path", FUSED_CONV)
+def test_conv_fused_activation_matches_layer_chain(U, orc, name, dt, path):
+    case = C.CONV_CASES[name]
+    g, x, w, b, dy = C.conv_inputs(case, dt, 41)
+    oh, ow = conv_out_dims(g)
+    shape = (g.n, oh, ow, g.f)
+    ref_y = orc.conv(g, x, w, b)["y"]
+    c = U.ctx()
+    cg = U.pkg.ConvGeom(*case)
+    xd, wd, bd = U.dev(x), U.dev(w), U.dev(b)
+    for aname, (kind, alpha) in C.ACT_CASES.items():
+        if aname == "softmax":
+            continue
+        ref_a = orc.activation(kind, alpha, ref_y)["y"]
+        yd, ad = U.zeros(shape, dt), U.zeros(shape, dt)
+        c.conv_forward_fused(cg, xd, wd, bd, yd, act_kind=kind, act_param=alpha, act_out=ad)
+        assert c.last_path == path, (name, c.last_path)
+        c.synchronize()
+        assert C.relerr(U.host(yd, shape), ref_y) < _tol(dt), (name, aname, "pre")
+        assert C.relerr(U.host(ad, shape), ref_a) < _tol(dt), (name, aname, C.relerr(U.host(ad, shape), ref_a))
+        # pre-activation skipped (inference / output-caching activations): same activated tensor, bit for bit
+        a2 = U.zeros(shape, dt)
+        c.conv_forward_fused(cg, xd, wd, bd, None, act_kind=kind, act_param=alpha, act_out=a2)
+        c.synchronize()
+        assert np.array_equal(U.host(a2, shape), U.host(ad, shape)), (name, aname)
+
+
+@pytest.mark.parametrize("name,dt,path", FUSED_CONV)
+def test_conv_fused_batchnorm_statistics(U, orc, name, dt, path):
+    """conv (epilogue: column sums) -> batchnorm_forward_stats (+ fused ReLU) equals conv -> BatchNormLayer -> ReLU,
+    over two training steps so that the running averages take both branches (assign, then decay)."""
+    case = C.CONV_CASES[name]
+    oh, ow = conv_out_dims(Geom(*case))
+    c = U.ctx()
+    cg = U.pkg.ConvGeom(*case)
+    rng = np.random.default_rng(43)
+    F = case[4]
+    gm, bt = C.rand(rng, (F,), dt, 0.5, 1.5), C.rand(rng, (F,), dt)
+    gmd, btd = U.dev(gm), U.dev(bt)
+    rm, rs, sm, ss = (U.zeros((F,), dt) for _ in range(4))
+    ys = []
+    for step in range(2):
+        g, x, w, b, dy = C.conv_inputs(case, dt, 50 + step)
+        # a bias far from the column mean and a non-zero-mean input: the shifted sums must not cancel
+        x = np.asfortranarray(x + dt(0.75))
+        b = np.asfortranarray(b * dt(20))
+        shape = (g.n, oh, ow, g.f)
+        ys.append(orc.conv(g, x, w, b)["y"])
+        xd, wd, bd = U.dev(x), U.dev(w), U.dev(b)
+        import torch
+        yd, nd, ad = U.zeros(shape, dt), U.zeros(shape, dt), U.zeros(shape, dt)
+        stats = torch.zeros(2 * F, dtype=torch.float64, device="cuda")
+        c.conv_forward_fused(cg, xd, wd, bd, yd, col_stats=stats)
+        assert c.last_path == path
+        c.batchnorm_forward_stats(1, g.n, oh, ow, F, step > 0, 0.1, 1e-5, yd, stats, bd, gmd, btd, rm, rs, sm, ss, nd,
+                                  act_kind=0, act_out=ad)
+        c.synchronize()
+        # the statistics themselves, against numpy in double
+        d = ys[-1].astype(np.float64).reshape(-1, F, order="F") - b.astype(np.float64).reshape(1, F)
+        want = np.concatenate([d.sum(0), (d * d).sum(0)])
+        got = stats.cpu().numpy()
+        assert C.relerr(got[:F], want[:F]) < _tol(dt) and C.relerr(got[F:], want[F:]) < _tol(dt), name
+    r = orc.batchnorm(1, ys, gm, bt)
+    tol = 10 * _tol(dt) if dt == np.float64 else _tol(dt)
+    assert C.relerr(U.host(nd, shape), r["y"]) < tol, (name, C.relerr(U.host(nd, shape), r["y"]))
+    assert C.relerr(U.host(rm, (F,)), r["run_mean"]) < tol
+    assert C.relerr(U.host(rs, (F,)), r["run_inv_sd"]) < tol
+    relu = orc.activation(0, 0.0, r["y"])["y"]
+    assert C.relerr(U.host(ad, shape), relu) < tol
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+def test_dense_fused_matches_layer_chain(U, orc, dt):
+    """DenseKernelLayer -> activation, and DenseKernelLayer -> per-activation BatchNormLayer (rank 1: one statistic
+    per output column over the batch = the column statistics of the GEMM)."""
+    c = U.ctx()
+    rng = np.random.default_rng(44)
+    for name, (n, i, o) in dict(C.DENSE_CASES, tc=(64, 96, 48)).items():
+        x, w, b = C.rand(rng, (n, i), dt), C.rand(rng, (i, o), dt, -0.5, 0.5), C.rand(rng, (1, o), dt)
+        ref_y = orc.dense(x, w, b)["y"]
+        xd, wd, bd = U.dev(x), U.dev(w), U.dev(b)
+        import torch
+        yd, ad = U.zeros((n, o), dt), U.zeros((n, o), dt)
+        stats = torch.zeros(2 * o, dtype=torch.float64, device="cuda")
+        c.dense_forward_fused(n, i, o, xd, wd, bd, yd, act_kind=3, act_param=1.2, act_out=ad, col_stats=stats)
+        if name == "tc" and dt == np.float32:
+            assert c.last_path == "tcgen05"
+        c.synchronize()
+        assert C.relerr(U.host(yd, (n, o)), ref_y) < _tol(dt), name
+        assert C.relerr(U.host(ad, (n, o)), orc.activation(3, 1.2, ref_y)["y"]) < _tol(dt), name
+        if n < 2:
+            continue
+        gm, bt = C.rand(rng, (o,), dt, 0.5, 1.5), C.rand(rng, (o,), dt)
+        rm, rs, sm, ss = (U.zeros((o,), dt) for _ in range(4))
+        nd = U.zeros((n, o), dt)
+        c.batchnorm_forward_stats(0, n, 1, 1, o, 0, 0.1, 1e-5, yd, stats, bd, U.dev(gm), U.dev(bt), rm, rs, sm, ss, nd)
+        c.synchronize()
+        r = orc.batchnorm(0, [np.asfortranarray(ref_y.reshape(n, 1, 1, o, order="F"))], gm, bt)
+        tol = 100 * _tol(dt) if dt == np.float64 else 3 * _tol(dt)   # batches of 5-7 rows: 1/sd amplifies rounding
+        assert C.relerr(U.host(nd, (n, o)), r["y"].reshape(n, o, order="F")) < tol, (name, "bn")
+
+
+def test_fused_epilogue_rejects_bad_requests(U):
+    import torch
+    c = U.ctx()
+    case = C.CONV_CASES["c2_small"]
+    g, x, w, b, dy = C.conv_inputs(case, np.float32, 45)
+    oh, ow = conv_out_dims(g)
+    cg = U.pkg.ConvGeom(*case)
+    xd, wd, bd = U.dev(x), U.dev(w), U.dev(b)
+    yd = U.zeros((g.n, oh, ow, g.f), np.float32)
+    with pytest.raises(U.pkg.Cattl3Error):   # softmax is not element-wise
+        c.conv_forward_fused(cg, xd, wd, bd, yd, act_kind=7, act_out=yd)
+    with pytest.raises(U.pkg.Cattl3Error):   # activation without a destination
+        c.conv_forward_fused(cg, xd, wd, bd, yd, act_kind=0)
+    with pytest.raises(U.pkg.Cattl3Error):   # statistics without y
+        c.conv_forward_fused(cg, xd, wd, bd, None, act_kind=0, act_out=yd,
+                             col_stats=torch.zeros(2 * g.f, dtype=torch.float64, device="cuda"))
