@@ -23,6 +23,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = 0, 1, 2, 3, 4
 ACT = dict(relu=0, leaky_relu=1, elu=2, swish=3, sigmoid=4, tanh=5, softplus=6, softmax=7)
 ACT_NONE = -1
 POOL = dict(max=0, mean=1)
+LOSS = dict(squared=0, cross_entropy=1)
 OPT = dict(sgd=0, momentum=1, nesterov=2, adagrad=3, rmsprop=4, adadelta=5, adam=6, adamax=7, nadam=8,
            amsgrad=9)
 PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
@@ -79,7 +80,8 @@ _SYMBOLS = [
     "cattl3_dense_forward", "cattl3_dense_backward", "cattl3_activation_forward", "cattl3_activation_backward",
     "cattl3_pool_forward", "cattl3_pool_backward", "cattl3_batchnorm_forward", "cattl3_batchnorm_backward",
     "cattl3_optimizer_step", "cattl3_add_inplace", "cattl3_scale", "cattl3_axpy",
-    "cattl3_conv_forward_fused", "cattl3_dense_forward_fused", "cattl3_batchnorm_forward_stats")]
+    "cattl3_conv_forward_fused", "cattl3_dense_forward_fused", "cattl3_batchnorm_forward_stats",
+    "cattl3_dropout_forward", "cattl3_dropout_backward", "cattl3_loss")]
 
 
 def lib():
@@ -210,6 +212,21 @@ class Context:
                    ct(decay), ct(eps), _p(x), _p(col_stats), _p(shift), _p(gamma), _p(beta), _p(running_mean),
                    _p(running_inv_sd), _p(saved_mean), _p(saved_inv_sd), _p(y),
                    ACT_NONE if act_kind is None else int(act_kind), ct(act_param), _p(act_out))
+
+    def dropout_forward(self, count, prob, eps, seed, x, y, mask):
+        _, ct = _suffix(x.dtype)
+        self._call("cattl3_dropout_forward", x.dtype, ctypes.c_int64(count), ct(prob), ct(eps), ctypes.c_uint64(seed),
+                   _p(x), _p(y), _p(mask))
+
+    def dropout_backward(self, count, prob, eps, dy, mask, dx):
+        _, ct = _suffix(dy.dtype)
+        self._call("cattl3_dropout_backward", dy.dtype, ctypes.c_int64(count), ct(prob), ct(eps), _p(dy), _p(mask),
+                   _p(dx))
+
+    def loss(self, kind, rows, vol, eps, grad_div, out, obj, loss, grad):
+        _, ct = _suffix(out.dtype)
+        self._call("cattl3_loss", out.dtype, int(kind), ctypes.c_int64(rows), ctypes.c_int64(vol), ct(eps),
+                   ct(grad_div), _p(out), _p(obj), _p(loss), _p(grad))
 
     def conv_forward_host(self, g, x_host, w, b, y_host, x_dev_keep=None):
         self._chk(self.L.cattl3_conv_forward_host_f32(self.h, ctypes.byref(g), _p(x_host), _p(w), _p(b),

@@ -23,6 +23,7 @@
 #include "b200/Communicator.hpp"
 #include "b200/DeviceLayer.hpp"
 #include "b200/DeviceNetwork.hpp"
+#include "b200/DeviceLoss.hpp"
 #include "parameters/B200Parameters.hpp"
 
 // the hot path
@@ -40,6 +41,12 @@
 #include "layer/pool/MaxPoolLayer.hpp"
 #include "layer/pool/MeanPoolLayer.hpp"
 #include "layer/BatchNormLayer.hpp"
+// the callers and neighbours of the hot path that keep a training step device resident
+#include "layer/DropoutLayer.hpp"
+#include "layer/ReshapeLayer.hpp"
+#include "loss/SquaredLoss.hpp"
+#include "loss/CrossEntropyLoss.hpp"
+#include "neural_network/StackedNeuralNetwork.hpp"
 #include "neural_network/FeedforwardNeuralNetwork.hpp"
 #include "neural_network/ResidualNeuralNetwork.hpp"
 #include "optimizer/SGDOptimizer.hpp"

@@ -19,7 +19,8 @@ namespace cattle {
 namespace b200 {
 
 template<typename Scalar, std::size_t Rank, int Kind>
-class ElementwiseActivationLayer : public ActivationLayer<Scalar,Rank>, public DeviceLayer<Scalar,Rank> {
+class ElementwiseActivationLayer : public ActivationLayer<Scalar,Rank>, public DeviceLayer<Scalar,Rank>,
+		public EpilogueConsumer<Scalar> {
 	typedef Layer<Scalar,Rank> Root;
 	typedef ActivationLayer<Scalar,Rank> Base;
 	static constexpr bool KEEPS_INPUT = Kind == CATTL3_ACT_RELU || Kind == CATTL3_ACT_LEAKY_RELU ||
@@ -57,6 +58,28 @@ public:
 		in_cache = KEEPS_INPUT ? std::move(in) : DeviceTensor<Scalar>();
 		out_cache = KEEPS_OUTPUT ? out : DeviceTensor<Scalar>();  // shares the buffer with the returned tensor
 		return out;
+	}
+	/**
+	 * An element-wise activation can be applied by the epilogue of the kernel layer (or batch-norm pass) in
+	 * front of it: the producer then writes f(x) next to -- or, when this layer only caches its output, instead
+	 * of -- x.  Softmax normalises over a row and is not element-wise.
+	 */
+	inline bool request_epilogue(FusedEpilogue<Scalar>& ep, std::size_t, bool) const {
+		if (Kind == CATTL3_ACT_SOFTMAX)
+			return false;
+		ep.act_kind = Kind;
+		ep.act_param = param;
+		ep.keep_pre = KEEPS_INPUT;
+		return true;
+	}
+	inline DeviceTensor<Scalar> accept_epilogue(DeviceTensor<Scalar> pre, FusedEpilogue<Scalar>& ep, bool,
+			FusedEpilogue<Scalar>*) {
+		if (ep.act_out.empty() || (KEEPS_INPUT && pre.empty()))
+			throw Error(CATTL3_ERR_INVALID, "activation layer: incomplete fused epilogue");
+		cached_rows = ep.act_out.rows;
+		in_cache = KEEPS_INPUT ? std::move(pre) : DeviceTensor<Scalar>();
+		out_cache = KEEPS_OUTPUT ? ep.act_out : DeviceTensor<Scalar>();
+		return ep.act_out;
 	}
 	inline DeviceTensor<Scalar> pass_back_dev(DeviceTensor<Scalar> out_grad) {
 		if (cached_rows != out_grad.rows || (KEEPS_INPUT && in_cache.empty()) || (KEEPS_OUTPUT && out_cache.empty()))

@@ -39,7 +39,8 @@
 namespace cattle {
 
 template<typename Scalar, std::size_t Rank, bool PerLastRank = (Rank == 3)>
-class BatchNormLayer : public Layer<Scalar,Rank>, public b200::DeviceLayer<Scalar,Rank> {
+class BatchNormLayer : public Layer<Scalar,Rank>, public b200::DeviceLayer<Scalar,Rank>,
+		public b200::EpilogueConsumer<Scalar> {
 	typedef Layer<Scalar,Rank> Base;
 	typedef BatchNormLayer<Scalar,Rank,PerLastRank> Self;
 	typedef b200::DeviceTensor<Scalar> DevTensor;
@@ -205,6 +206,52 @@ public:
 			cached_rows = in.rows;
 			in_cache = std::move(in);
 		}
+		return out;
+	}
+	/**
+	 * In training mode the first of the layer's two passes over its input -- the per-group mean and variance
+	 * (BatchNormLayer.hpp:225-233) -- can come out of the producing kernel layer's epilogue, when that layer's
+	 * GEMM columns are this layer's groups (conv filters = channels; dense outputs = activations).
+	 */
+	inline bool request_epilogue(b200::FusedEpilogue<Scalar>& ep, std::size_t producer_stat_columns, bool training) const {
+		if (!training || producer_stat_columns != groups)
+			return false;
+		ep.want_stats = true;
+		ep.keep_pre = true;
+		return true;
+	}
+	inline bool chains_epilogue() const {
+		return true;
+	}
+	inline DevTensor accept_epilogue(DevTensor in, b200::FusedEpilogue<Scalar>& ep, bool training,
+			b200::FusedEpilogue<Scalar>* next) {
+		if (!training || in.empty() || !ep.col_stats || ep.col_stats->size() != 2 * groups || !ep.shift)
+			throw b200::Error(CATTL3_ERR_INVALID, "BatchNormLayer: incomplete fused epilogue");
+		const bool act = next != nullptr && next->act_kind != CATTL3_ACT_NONE;
+		DevTensor out;
+		if (!act || next->keep_pre)
+			out = DevTensor(in.rows, dims.get_volume());
+		if (act)
+			next->act_out = DevTensor(in.rows, dims.get_volume());
+		if (batch_means.size() != groups) {
+			batch_means = b200::DeviceBuffer<Scalar>(groups);
+			batch_inv_sds = b200::DeviceBuffer<Scalar>(groups);
+		}
+		b200::Context& c = b200::Context::get();
+		{
+			b200::Context::Lock l = c.lock();
+			CATTLE_B200_CHECK(b200::Api<Scalar>::batchnorm_forward_stats(c.handle(), PerLastRank ? 1 : 0,
+					(std::int32_t) in.rows, geom_h(), 1, geom_c(), avgs_init ? 1 : 0, norm_avg_decay, epsilon, in.data(),
+					ep.col_stats->data(), ep.shift, gammas[0]->device_values(), betas[0]->device_values(),
+					avg_means[0]->device_values(), avg_inv_sds[0]->device_values(), batch_means.data(),
+					batch_inv_sds.data(), out.data(), act ? next->act_kind : CATTL3_ACT_NONE,
+					act ? next->act_param : (Scalar) 0, act ? next->act_out.data() : nullptr));
+		}
+		avg_means[0]->values_written_on_device();
+		avg_inv_sds[0]->values_written_on_device();
+		avgs_init = true;
+		cached_rows = in.rows;
+		in_cache = std::move(in);
 		return out;
 	}
 	inline DevTensor pass_back_dev(DevTensor out_grad) {

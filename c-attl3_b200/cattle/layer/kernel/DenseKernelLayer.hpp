@@ -23,7 +23,8 @@
 namespace cattle {
 
 template<typename Scalar, std::size_t Rank = 1>
-class DenseKernelLayer : public KernelLayer<Scalar,Rank>, public b200::DeviceLayer<Scalar,Rank> {
+class DenseKernelLayer : public KernelLayer<Scalar,Rank>, public b200::DeviceLayer<Scalar,Rank>,
+		public b200::EpilogueProducer<Scalar> {
 	typedef Layer<Scalar,Rank> Root;
 	typedef KernelLayer<Scalar,Rank> Base;
 	typedef b200::DeviceTensor<Scalar> DevTensor;

@@ -15,6 +15,7 @@
 #define C_ATTL3_NEURAL_NETWORK_FEEDFORWARDNEURALNETWORK_H_
 
 #include <cassert>
+#include <cstdlib>
 #include <memory>
 #include <utility>
 #include <vector>
@@ -118,8 +119,8 @@ public:
 			// a run of device layers: upload once, chain in HBM, download once
 			DevTensor act = b200::to_device<Scalar,Base::DATA_RANK>(input);
 			input = typename Base::Data();
-			for (; i < layers.size() && device_layers[i]; ++i)
-				act = device_layers[i]->pass_forward_dev(std::move(act), training);
+			while (i < layers.size() && device_layers[i])
+				act = forward_from(i, std::move(act), training);
 			input = b200::to_host<Scalar,Base::DATA_RANK>(act,
 					b200::batch_extents<Rank>(act.rows, layers[i - 1]->get_output_dims()));
 		}
@@ -146,13 +147,15 @@ public:
 		return out_grad;
 	}
 	inline DevTensor propagate_dev(DevTensor input, bool training) {
-		for (std::size_t i = 0; i < layers.size(); ++i) {
+		std::size_t i = 0;
+		while (i < layers.size()) {
 			if (device_layers[i]) {
-				input = device_layers[i]->pass_forward_dev(std::move(input), training);
+				input = forward_from(i, std::move(input), training);
 			} else {
 				typename Base::Data host = b200::to_host<Scalar,Base::DATA_RANK>(input,
 						b200::batch_extents<Rank>(input.rows, layers[i]->get_input_dims()));
 				input = b200::to_device<Scalar,Base::DATA_RANK>(layers[i]->pass_forward(std::move(host), training));
+				++i;
 			}
 		}
 		return input;
@@ -183,6 +186,8 @@ public:
 		using std::swap;
 		swap(network1.layers, network2.layers);
 		swap(network1.device_layers, network2.device_layers);
+		swap(network1.producers, network2.producers);
+		swap(network1.consumers, network2.consumers);
 		swap(network1.foremost, network2.foremost);
 		swap(network1.input_dims, network2.input_dims);
 		swap(network1.output_dims, network2.output_dims);
@@ -195,12 +200,58 @@ private:
 	}
 	inline void find_device_layers() {
 		device_layers.clear();
-		for (const LayerPtr<Scalar,Rank>& layer : layers)
+		producers.clear();
+		consumers.clear();
+		for (const LayerPtr<Scalar,Rank>& layer : layers) {
 			device_layers.push_back(dynamic_cast<DevLayer*>(layer.get()));
+			producers.push_back(dynamic_cast<b200::EpilogueProducer<Scalar>*>(layer.get()));
+			consumers.push_back(dynamic_cast<b200::EpilogueConsumer<Scalar>*>(layer.get()));
+		}
+	}
+	/**
+	 * Forward pass of device layer i -- together with the one or two layers behind it when they can ride in
+	 * its epilogue: kernel layer -> activation, kernel layer -> batch norm (statistics) [-> activation].
+	 * Every layer still ends up with the caches its own pass_back needs.  Advances i past the layers run.
+	 */
+	inline DevTensor forward_from(std::size_t& i, DevTensor act, bool training) {
+		const std::size_t n = layers.size();
+		b200::EpilogueProducer<Scalar>* producer = producers[i];
+		b200::EpilogueConsumer<Scalar>* consumer = i + 1 < n ? consumers[i + 1] : nullptr;
+		b200::FusedEpilogue<Scalar> ep;
+		if (fuse_epilogues() && producer && consumer && producer->can_fuse_epilogue() &&
+				consumer->request_epilogue(ep, producer->stat_columns(), training)) {
+			b200::FusedEpilogue<Scalar> next;
+			b200::EpilogueConsumer<Scalar>* chained = nullptr;
+			if (consumer->chains_epilogue() && i + 2 < n && consumers[i + 2] &&
+					consumers[i + 2]->request_epilogue(next, 0, training))
+				chained = consumers[i + 2];
+			act = producer->pass_forward_dev_fused(std::move(act), training, ep);
+			act = consumer->accept_epilogue(std::move(act), ep, training, chained ? &next : nullptr);
+			i += 2;
+			if (chained) {
+				act = chained->accept_epilogue(std::move(act), next, training, nullptr);
+				++i;
+			}
+			return act;
+		}
+		act = device_layers[i]->pass_forward_dev(std::move(act), training);
+		++i;
+		return act;
+	}
+	/** CATTL3_NO_FUSION=1 in the environment runs every layer on its own (A/B measurements, debugging). */
+	inline static bool fuse_epilogues() {
+		static const bool on = [] {
+			const char* v = std::getenv("CATTL3_NO_FUSION");
+			return !(v && v[0] && v[0] != '0');
+		}();
+		return on;
 	}
 	std::vector<LayerPtr<Scalar,Rank>> layers;
 	// device_layers[i] is layers[i] seen through its device interface, or null for a host-only layer
 	std::vector<DevLayer*> device_layers;
+	// layers[i] seen as an epilogue producer / consumer (b200/DeviceLayer.hpp), or null
+	std::vector<b200::EpilogueProducer<Scalar>*> producers;
+	std::vector<b200::EpilogueConsumer<Scalar>*> consumers;
 	bool foremost;
 	typename Base::Dims input_dims, output_dims;
 };

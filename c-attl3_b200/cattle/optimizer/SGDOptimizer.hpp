@@ -24,6 +24,7 @@
 
 #include <array>
 #include <cassert>
+#include <cstdlib>
 #include <iomanip>
 #include <iostream>
 #include <map>
@@ -34,6 +35,8 @@
 #include "core/Optimizer.hpp"
 #include "parameters/B200Parameters.hpp"
 #include "b200/Communicator.hpp"
+#include "b200/DeviceLoss.hpp"
+#include "b200/DeviceNetwork.hpp"
 #include "b200/Runtime.hpp"
 
 namespace cattle {
@@ -69,12 +72,26 @@ protected:
 		double obj_loss = 0, reg_loss = 0;
 		std::size_t instances = 0, updates = 0;
 		std::vector<Parameters<Scalar>*> params_vec = net.get_all_unique_params();
+		b200::DeviceNetwork<Scalar,Rank>* dev_net = Sequential || !device_loop() ? nullptr :
+				dynamic_cast<b200::DeviceNetwork<Scalar,Rank>*>(&net);
+		const b200::DeviceLoss<Scalar>* dev_loss = dynamic_cast<const b200::DeviceLoss<Scalar>*>(Base::loss.get());
+		std::vector<b200::DeviceBuffer<Scalar>> step_losses;
 		while (training_prov.has_more()) {
 			DataPair<Scalar,Rank,Sequential> data_pair = training_prov.get_data(batch_size);
 			instances += data_pair.first.dimension(0);
 			if (comm.world_size() > 1)
 				data_pair = shard(std::move(data_pair), comm);
-			if (data_pair.first.dimension(0) > 0) {
+			if (data_pair.first.dimension(0) > 0 && dev_net && dev_loss) {
+				// the whole step in HBM: one upload of the mini-batch, then propagate -> loss -> back-propagate
+				// without a host round trip; the per-sample losses are collected at the end of the epoch
+				b200::DeviceTensor<Scalar> obj = b200::to_device<Scalar,Base::Data::NumDimensions>(data_pair.second);
+				b200::DeviceTensor<Scalar> out = dev_net->propagate_dev(
+						b200::to_device<Scalar,Base::Data::NumDimensions>(data_pair.first), true);
+				step_losses.emplace_back();
+				b200::DeviceTensor<Scalar> out_grad = dev_loss->loss_and_gradient_dev(out, obj, (Scalar) batch_size,
+						step_losses.back());
+				dev_net->backpropagate_dev(std::move(out_grad));
+			} else if (data_pair.first.dimension(0) > 0) {
 				typename Base::Data out = net.propagate(std::move(data_pair.first), true);
 				obj_loss += Base::loss->function(out, data_pair.second).sum();
 				// dividing by the nominal batch size decouples the learning rate from the batch size and
@@ -95,6 +112,12 @@ protected:
 			++timestep;
 			for (Parameters<Scalar>* params_ptr : params_vec)
 				params_ptr->reset_grad();  // a no-op where the fused step already cleared the gradient
+		}
+		for (const b200::DeviceBuffer<Scalar>& losses : step_losses) {
+			std::vector<Scalar> host(losses.size());
+			losses.download(host.data(), host.size());
+			for (Scalar l : host)
+				obj_loss += l;
 		}
 		if (comm.world_size() > 1)
 			obj_loss = comm.all_reduce_sum(obj_loss);
@@ -215,6 +238,14 @@ protected:
 	const std::size_t batch_size;
 private:
 	typedef std::array<b200::DeviceBuffer<Scalar>,3> StateArrays;
+	/** CATTL3_HOST_LOOP=1 keeps the reference's host protocol between network and loss (A/B, debugging). */
+	inline static bool device_loop() {
+		static const bool on = [] {
+			const char* v = std::getenv("CATTL3_HOST_LOOP");
+			return !(v && v[0] && v[0] != '0');
+		}();
+		return on;
+	}
 	inline static int states_needed(int kind) {
 		if (kind == CATTL3_OPT_VANILLA_SGD)
 			return 0;

@@ -841,11 +841,116 @@ template<typename S> int axpy(cattl3_ctx* ctx, int64_t count, S alpha, const S* 
 template<typename S> int add_inplace(cattl3_ctx* ctx, int64_t count, S* y, const S* x) { return glue<S, 0>(ctx, "add_inplace", count, (S) 0, x, y); }
 template<typename S> int scale(cattl3_ctx* ctx, int64_t count, S alpha, const S* x, S* y) { return glue<S, 1>(ctx, "scale", count, alpha, x, y); }
 
+// ---- dropout (C-ATTL3/layer/DropoutLayer.hpp:74-94) ------------------------------------------------------
+// Inverted dropout: mask = u <= p ? 0 : 1 / (1 - p + eps), y = x * mask, with u uniform in [0, 1) from a
+// counter-based generator (a 64-bit mix of seed and element index: the same (seed, index) always gives the
+// same draw, whatever the launch geometry).  The mask is kept as one byte per element for the backward pass.
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+__device__ __forceinline__ float uniform01(uint64_t seed, long long index) {
+	const uint64_t h = mix64(seed + 0x9E3779B97F4A7C15ull * (uint64_t) (index + 1));
+	return (float) (uint32_t) (h >> 40) * (1.0f / 16777216.0f);
+}
+
+template<typename S>
+__global__ void __launch_bounds__(256) dropout_fwd_kernel(long long count, float prob, S scale, uint64_t seed,
+		const S* __restrict__ x, S* __restrict__ y, uint8_t* __restrict__ mask) {
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < count; i += (long long) gridDim.x * 256) {
+		const bool keep = uniform01(seed, i) > prob;
+		mask[i] = keep ? 1 : 0;
+		y[i] = keep ? x[i] * scale : (S) 0;
+	}
+}
+template<typename S>
+__global__ void __launch_bounds__(256) dropout_bwd_kernel(long long count, S scale, const S* __restrict__ dy,
+		const uint8_t* __restrict__ mask, S* __restrict__ dx) {
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < count; i += (long long) gridDim.x * 256)
+		dx[i] = mask[i] ? dy[i] * scale : (S) 0;
+}
+
+template<typename S>
+int dropout_forward(cattl3_ctx* ctx, int64_t count, S prob, S eps, uint64_t seed, const S* x, S* y, uint8_t* mask) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(count > 0 && x && y && mask, "dropout_forward: bad arguments");
+	CATTL3_REQUIRE(prob > (S) 0 && prob <= (S) 1 && eps > (S) 0, "dropout_forward: probability must be in (0, 1], epsilon > 0");
+	const S scale = (S) 1 / ((S) 1 - prob + eps);
+	dropout_fwd_kernel<S><<<ew_grid(ctx, count, 256), 256, 0, ctx->stream>>>(count, (float) prob, scale, seed, x, y, mask);
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+template<typename S>
+int dropout_backward(cattl3_ctx* ctx, int64_t count, S prob, S eps, const S* dy, const uint8_t* mask, S* dx) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(count > 0 && dy && dx && mask, "dropout_backward: bad arguments");
+	const S scale = (S) 1 / ((S) 1 - prob + eps);
+	dropout_bwd_kernel<S><<<ew_grid(ctx, count, 256), 256, 0, ctx->stream>>>(count, scale, dy, mask, dx);
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+
+// ---- losses (C-ATTL3/loss/SquaredLoss.hpp:25-34, CrossEntropyLoss.hpp:33-42, UniversalLoss.hpp:24-58) ----
+// out, obj: rows x vol (rows = batch, fastest).  loss[r] = sum_j (out - obj)^2  |  -sum_j log(out + eps) * obj;
+// grad = 2 (out - obj)  |  -obj / (out + eps), divided by grad_div (the batch loop's nominal batch size,
+// SGDOptimizer.hpp:55-56).  One thread per row keeps a warp's accesses coalesced.
+template<typename S, int KIND>
+__global__ void __launch_bounds__(128) loss_kernel(long long rows, long long vol, S eps, S grad_div,
+		const S* __restrict__ out, const S* __restrict__ obj, S* __restrict__ loss, S* __restrict__ grad) {
+	for (long long r = blockIdx.x * 128ll + threadIdx.x; r < rows; r += (long long) gridDim.x * 128) {
+		S acc = 0;
+		for (long long j = 0; j < vol; ++j) {
+			const S o = out[r + rows * j], t = obj[r + rows * j];
+			if (KIND == CATTL3_LOSS_SQUARED) {
+				const S d = o - t;
+				acc += d * d;
+				if (grad) grad[r + rows * j] = ((S) 2 * d) / grad_div;
+			} else {
+				acc += dev_log<S>(o + eps) * t;
+				if (grad) grad[r + rows * j] = (-t / (o + eps)) / grad_div;
+			}
+		}
+		if (loss) loss[r] = KIND == CATTL3_LOSS_SQUARED ? acc : -acc;
+	}
+}
+
+template<typename S>
+int loss_forward_backward(cattl3_ctx* ctx, int kind, int64_t rows, int64_t vol, S eps, S grad_div, const S* out,
+		const S* obj, S* loss, S* grad) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(rows > 0 && vol > 0 && out && obj && (loss || grad) && grad_div != (S) 0, "loss: bad arguments");
+	const int grid = ew_grid(ctx, rows, 128);
+	if (kind == CATTL3_LOSS_SQUARED)
+		loss_kernel<S, CATTL3_LOSS_SQUARED><<<grid, 128, 0, ctx->stream>>>(rows, vol, eps, grad_div, out, obj, loss, grad);
+	else if (kind == CATTL3_LOSS_CROSS_ENTROPY)
+		loss_kernel<S, CATTL3_LOSS_CROSS_ENTROPY><<<grid, 128, 0, ctx->stream>>>(rows, vol, eps, grad_div, out, obj, loss, grad);
+	else {
+		set_error("loss: unknown kind %d", kind);
+		return CATTL3_ERR_INVALID;
+	}
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+
 } // namespace cattl3
 
 using namespace cattl3;
 
 extern "C" {
+
+int cattl3_dropout_forward_f32(cattl3_ctx* c, int64_t count, float prob, float eps, uint64_t seed, const float* x, float* y, uint8_t* mask) {
+	return dropout_forward<float>(c, count, prob, eps, seed, x, y, mask); }
+int cattl3_dropout_forward_f64(cattl3_ctx* c, int64_t count, double prob, double eps, uint64_t seed, const double* x, double* y, uint8_t* mask) {
+	return dropout_forward<double>(c, count, prob, eps, seed, x, y, mask); }
+int cattl3_dropout_backward_f32(cattl3_ctx* c, int64_t count, float prob, float eps, const float* dy, const uint8_t* mask, float* dx) {
+	return dropout_backward<float>(c, count, prob, eps, dy, mask, dx); }
+int cattl3_dropout_backward_f64(cattl3_ctx* c, int64_t count, double prob, double eps, const double* dy, const uint8_t* mask, double* dx) {
+	return dropout_backward<double>(c, count, prob, eps, dy, mask, dx); }
+int cattl3_loss_f32(cattl3_ctx* c, int kind, int64_t rows, int64_t vol, float eps, float grad_div, const float* out, const float* obj, float* loss, float* grad) {
+	return loss_forward_backward<float>(c, kind, rows, vol, eps, grad_div, out, obj, loss, grad); }
+int cattl3_loss_f64(cattl3_ctx* c, int kind, int64_t rows, int64_t vol, double eps, double grad_div, const double* out, const double* obj, double* loss, double* grad) {
+	return loss_forward_backward<double>(c, kind, rows, vol, eps, grad_div, out, obj, loss, grad); }
 
 int cattl3_activation_forward_f32(cattl3_ctx* c, int kind, float alpha, int64_t rows, int64_t vol, const float* x, float* y) {
 	return activation_forward<float>(c, kind, alpha, rows, vol, x, y); }

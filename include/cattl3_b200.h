@@ -77,6 +77,12 @@ enum {
 	CATTL3_OPT_AMSGRAD = 9      /* C-ATTL3/optimizer/AMSGradOptimizer.hpp:50-67 */
 };
 
+/* Device losses. */
+enum {
+	CATTL3_LOSS_SQUARED = 0,        /* C-ATTL3/loss/SquaredLoss.hpp:25-34 */
+	CATTL3_LOSS_CROSS_ENTROPY = 1   /* C-ATTL3/loss/CrossEntropyLoss.hpp:33-42 (eps inside the log and the quotient) */
+};
+
 /* Which kernel family a kernel-layer call may use (cattl3_ctx_set_conv_path). */
 enum {
 	CATTL3_PATH_AUTO = 0,       /* tcgen05 where the shape allows it (float only), else SIMT */
@@ -242,6 +248,22 @@ int cattl3_activation_forward_f64(cattl3_ctx*, int kind, double alpha, int64_t r
 /* dx = f'(x) * dy, using the cached input x and output y exactly where the reference does. */
 int cattl3_activation_backward_f32(cattl3_ctx*, int kind, float alpha, int64_t rows, int64_t vol, const float* x, const float* y, const float* dy, float* dx);
 int cattl3_activation_backward_f64(cattl3_ctx*, int kind, double alpha, int64_t rows, int64_t vol, const double* x, const double* y, const double* dy, double* dx);
+
+/* ---- dropout (DropoutLayer.hpp:74-94) ---------------------------------- */
+/* Inverted dropout in training mode: mask = u <= prob ? 0 : 1 / (1 - prob + eps), y = x * mask; u is a uniform [0,1)
+ * draw from a counter-based generator keyed by (seed, element index) -- deterministic per seed, NOT the reference's
+ * host RNG stream (its masks are not reproducible either way).  mask: one byte per element,
+ * kept for backward (dx = dy * mask). */
+int cattl3_dropout_forward_f32(cattl3_ctx*, int64_t count, float prob, float eps, uint64_t seed, const float* x, float* y, uint8_t* mask);
+int cattl3_dropout_forward_f64(cattl3_ctx*, int64_t count, double prob, double eps, uint64_t seed, const double* x, double* y, uint8_t* mask);
+int cattl3_dropout_backward_f32(cattl3_ctx*, int64_t count, float prob, float eps, const float* dy, const uint8_t* mask, float* dx);
+int cattl3_dropout_backward_f64(cattl3_ctx*, int64_t count, double prob, double eps, const double* dy, const uint8_t* mask, double* dx);
+
+/* ---- losses (UniversalLoss.hpp:24-58 -> SquaredLoss / CrossEntropyLoss) --------------------------------- */
+/* out, obj: rows x vol, rows (= batch) fastest.  loss (rows, may be NULL): per-sample loss; grad (rows x vol, may be
+ * NULL): d loss / d out divided by grad_div -- the batch loop's nominal batch size (SGDOptimizer.hpp:55-56). */
+int cattl3_loss_f32(cattl3_ctx*, int kind, int64_t rows, int64_t vol, float eps, float grad_div, const float* out, const float* obj, float* loss, float* grad);
+int cattl3_loss_f64(cattl3_ctx*, int kind, int64_t rows, int64_t vol, double eps, double grad_div, const double* out, const double* obj, double* loss, double* grad);
 
 /* ---- pooling layers (PoolLayer.hpp:77-116) -------------------------------------------------- */
 /* argmax: one byte per output element, index rw*RH + rh of the first maximum in the reference's

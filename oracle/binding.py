@@ -176,5 +176,42 @@ class Oracle:
         return out, loss.value, ms.value
 
 
+    def train_autoencoder(self, x, batch, epochs, params_in=None):
+        """Config-3 auto-encoder (mnist_autoencoder.cpp), SquaredLoss against the input, Nadam.
+        epochs < 0: only returns the parameter count.  Returns (params, loss, train_ms)."""
+        dt = x.dtype
+        n = ctypes.c_int()
+        fn = self._fn("train_autoencoder", dt)
+        rc = fn(0, 1, -1, None, None, None, ctypes.byref(n), None, None)
+        assert rc == 0, rc
+        if epochs < 0:
+            return n.value
+        out = np.zeros(n.value, dt)
+        loss, ms = ctypes.c_double(), ctypes.c_double()
+        rc = fn(x.shape[0], batch, epochs, _ptr(x), _ptr(params_in), _ptr(out), ctypes.byref(n), ctypes.byref(loss),
+                ctypes.byref(ms))
+        assert rc == 0, rc
+        return out, loss.value, ms.value
+
+    def train_resnet(self, x, obj, batch, epochs, arch, params_in=None):
+        """Config-4 ResNet-style network; arch = (stem_r, stem_s, stem_pool, width, blocks, head_pool).
+        x: total x h x w x c, obj: total x 1 x 1 x classes.  epochs < 0: parameter count only."""
+        dt = x.dtype
+        total, h, w, c = x.shape
+        classes = obj.shape[-1]
+        n = ctypes.c_int()
+        fn = self._fn("train_resnet", dt)
+        rc = fn(0, 1, -1, h, w, c, *arch, classes, None, None, None, None, ctypes.byref(n), None, None)
+        assert rc == 0, rc
+        if epochs < 0:
+            return n.value
+        out = np.zeros(n.value, dt)
+        loss, ms = ctypes.c_double(), ctypes.c_double()
+        rc = fn(total, batch, epochs, h, w, c, *arch, classes, _ptr(x), _ptr(obj), _ptr(params_in), _ptr(out),
+                ctypes.byref(n), ctypes.byref(loss), ctypes.byref(ms))
+        assert rc == 0, rc
+        return out, loss.value, ms.value
+
+
 def have_ref():
     return os.path.exists(REF_PATH)

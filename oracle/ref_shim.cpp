@@ -18,7 +18,9 @@
  *   pool      -> Max/MeanPoolLayer<S,3>             (C-ATTL3/layer/PoolLayer.hpp:77-116)
  *   batchnorm -> BatchNormLayer<S,3,true|false>     (C-ATTL3/layer/BatchNormLayer.hpp:170-262, 337-391)
  *   optimizer -> every SGDOptimizer subclass        (C-ATTL3/optimizer/ *.hpp)
- *   train     -> FeedforwardNeuralNetwork + NadamOptimizer::train (config 1 of BASELINE.json)
+ *   train     -> FeedforwardNeuralNetwork + NadamOptimizer::train (config 1 of BASELINE.json),
+ *                the StackedNeuralNetwork auto-encoder of config 3 and a ResidualNeuralNetwork of
+ *                conv + BatchNorm + ReLU modules (config 4)
  */
 #include <chrono>
 #include <cstring>
@@ -387,6 +389,133 @@ int cifar_impl(int total, int batch, int epochs, const S* x, const S* obj, const
 	return 0;
 }
 
+/* Shared tail of the network trainers: inject parameters, train without shuffling, copy the parameters out. */
+template<typename S, typename Opt>
+int train_and_export(NeuralNetwork<S,3,false>& net, Opt& opt, TensorPtr<S,4> obs, TensorPtr<S,4> objs, int epochs,
+		const S* params_in, S* params_out, int* n_params, double* loss_out, double* train_ms) {
+	net.init();
+	auto params = net.get_all_unique_params();
+	int count = 0;
+	for (auto p : params)
+		count += (int) (p->get_rows() * p->get_cols());
+	if (n_params) *n_params = count;
+	if (epochs < 0)
+		return 0;  /* size query only */
+	if (params_in) {
+		const S* src = params_in;
+		for (auto p : params) {
+			p->set_values(Eigen::Map<const Matrix<S>>(src, p->get_rows(), p->get_cols()));
+			src += p->get_rows() * p->get_cols();
+		}
+	}
+	MemoryDataProvider<S,3,false,false> prov(std::move(obs), std::move(objs));
+	opt.fit(net);
+	double t0 = now_ms();
+	S l = epochs > 0 ? opt.train(net, prov, epochs) : (S) 0;
+	double t1 = now_ms();
+	if (loss_out) *loss_out = (double) l;
+	if (train_ms) *train_ms = t1 - t0;
+	if (params_out) {
+		S* dst = params_out;
+		for (auto p : params) {
+			std::memcpy(dst, p->get_values().data(), sizeof(S) * p->get_rows() * p->get_cols());
+			dst += p->get_rows() * p->get_cols();
+		}
+	}
+	return 0;
+}
+
+/*
+ * BASELINE.json configs[2]: the auto-encoder of examples/mnist_autoencoder.cpp:26-48 (Conv 1->3 4x4 stride 2,
+ * Softplus, Conv 3->3 4x4, Softplus, Dense 300->100 | Dense 100->300, Softplus, Reshape 10x10x3,
+ * TransConv 3->3 4x4, Softplus, TransConv 3->1 4x4 stride 2) as a StackedNeuralNetwork, SquaredLoss against
+ * the input itself, NadamOptimizer(batch).  x: total x 28 x 28 x 1.
+ */
+template<typename S>
+int autoencoder_impl(int total, int batch, int epochs, const S* x, const S* params_in, S* params_out, int* n_params,
+		double* loss_out, double* train_ms) {
+	typedef std::size_t sz;
+	auto init = std::make_shared<HeParameterInitialization<S>>(1e-1);
+	std::vector<LayerPtr<S,3>> enc;
+	enc.emplace_back(new ConvKernelLayer<S>({ 28u, 28u, 1u }, 3, init, 4, 4, 0, 0, 2, 2));
+	enc.emplace_back(new SoftplusActivationLayer<S,3>(enc.back()->get_output_dims()));
+	enc.emplace_back(new ConvKernelLayer<S>(enc.back()->get_output_dims(), 3, init, 4, 4, 0, 0, 1, 1));
+	enc.emplace_back(new SoftplusActivationLayer<S,3>(enc.back()->get_output_dims()));
+	enc.emplace_back(new DenseKernelLayer<S,3>(enc.back()->get_output_dims(), 100, init));
+	NeuralNetPtr<S,3,false> encoder(new FeedforwardNeuralNetwork<S,3>(std::move(enc)));
+	std::vector<LayerPtr<S,3>> dec;
+	dec.emplace_back(new DenseKernelLayer<S,3>(encoder->get_output_dims(), 300, init));
+	dec.emplace_back(new SoftplusActivationLayer<S,3>(dec.back()->get_output_dims()));
+	dec.emplace_back(new ReshapeLayer<S,3>(dec.back()->get_output_dims(), { 10u, 10u, 3u }));
+	dec.emplace_back(new TransConvKernelLayer<S>(dec.back()->get_output_dims(), 3, init, 4, 4, 0, 0, 1, 1));
+	dec.emplace_back(new SoftplusActivationLayer<S,3>(dec.back()->get_output_dims()));
+	dec.emplace_back(new TransConvKernelLayer<S>(dec.back()->get_output_dims(), 1, init, 4, 4, 0, 0, 2, 2));
+	NeuralNetPtr<S,3,false> decoder(new FeedforwardNeuralNetwork<S,3>(std::move(dec)));
+	std::vector<NeuralNetPtr<S,3,false>> modules;
+	modules.push_back(std::move(encoder));
+	modules.push_back(std::move(decoder));
+	StackedNeuralNetwork<S,3,false> net(std::move(modules));
+	TensorPtr<S,4> obs(new Tensor<S,4>((sz) (total > 0 ? total : 1), 28u, 28u, 1u));
+	if (x) std::memcpy(obs->data(), x, sizeof(S) * obs->size());
+	TensorPtr<S,4> objs(new Tensor<S,4>(*obs));
+	auto loss = std::make_shared<SquaredLoss<S,3,false>>();
+	NadamOptimizer<S,3,false> opt(loss, batch > 0 ? batch : 1);
+	return train_and_export<S>(net, opt, std::move(obs), std::move(objs), epochs, params_in, params_out, n_params,
+			loss_out, train_ms);
+}
+
+/*
+ * BASELINE.json configs[3]: a ResNet-style network -- stem FeedforwardNeuralNetwork{Conv stem_r x stem_r
+ * (c -> width, stride stem_s, "same"-style padding stem_r / 2), BatchNorm, ReLU[, MaxPool 2x2]}, a
+ * ResidualNeuralNetwork of `blocks` modules FeedforwardNeuralNetwork{Conv 3x3 p1 (width -> width), BatchNorm,
+ * ReLU, Conv 3x3 p1, BatchNorm} (module input dims == output dims, ResidualNeuralNetwork.hpp:48-49), and a
+ * head {ReLU, MeanPool head_pool x head_pool, Dense -> classes, Softmax}; CrossEntropyLoss, NadamOptimizer.
+ * x: total x h x w x c, obj: total x 1 x 1 x classes (one-hot).
+ */
+template<typename S>
+int resnet_impl(int total, int batch, int epochs, int h, int w, int c, int stem_r, int stem_s, int stem_pool,
+		int width, int blocks, int head_pool, int classes, const S* x, const S* obj, const S* params_in,
+		S* params_out, int* n_params, double* loss_out, double* train_ms) {
+	typedef std::size_t sz;
+	auto he = std::make_shared<HeParameterInitialization<S>>(1e-1);
+	auto glorot = std::make_shared<GlorotParameterInitialization<S>>(1e-1);
+	std::vector<LayerPtr<S,3>> stem;
+	stem.emplace_back(new ConvKernelLayer<S>({ (sz) h, (sz) w, (sz) c }, width, he, stem_r, stem_r, stem_r / 2,
+			stem_r / 2, stem_s, stem_s));
+	stem.emplace_back(new BatchNormLayer<S,3>(stem.back()->get_output_dims()));
+	stem.emplace_back(new ReLUActivationLayer<S,3>(stem.back()->get_output_dims()));
+	if (stem_pool)
+		stem.emplace_back(new MaxPoolLayer<S>(stem.back()->get_output_dims()));
+	std::vector<NeuralNetPtr<S,3,false>> stack;
+	stack.emplace_back(new FeedforwardNeuralNetwork<S,3>(std::move(stem)));
+	std::vector<NeuralNetPtr<S,3,false>> modules;
+	for (int i = 0; i < blocks; ++i) {
+		std::vector<LayerPtr<S,3>> m;
+		m.emplace_back(new ConvKernelLayer<S>(stack[0]->get_output_dims(), width, he));
+		m.emplace_back(new BatchNormLayer<S,3>(m.back()->get_output_dims()));
+		m.emplace_back(new ReLUActivationLayer<S,3>(m.back()->get_output_dims()));
+		m.emplace_back(new ConvKernelLayer<S>(m.back()->get_output_dims(), width, he));
+		m.emplace_back(new BatchNormLayer<S,3>(m.back()->get_output_dims()));
+		modules.emplace_back(new FeedforwardNeuralNetwork<S,3>(std::move(m)));
+	}
+	stack.emplace_back(new ResidualNeuralNetwork<S,3>(std::move(modules)));
+	std::vector<LayerPtr<S,3>> head;
+	head.emplace_back(new ReLUActivationLayer<S,3>(stack.back()->get_output_dims()));
+	head.emplace_back(new MeanPoolLayer<S>(head.back()->get_output_dims(), head_pool, head_pool, head_pool, head_pool));
+	head.emplace_back(new DenseKernelLayer<S,3>(head.back()->get_output_dims(), classes, glorot));
+	head.emplace_back(new SoftmaxActivationLayer<S,3>(head.back()->get_output_dims()));
+	stack.emplace_back(new FeedforwardNeuralNetwork<S,3>(std::move(head)));
+	StackedNeuralNetwork<S,3,false> net(std::move(stack));
+	TensorPtr<S,4> obs(new Tensor<S,4>((sz) (total > 0 ? total : 1), (sz) h, (sz) w, (sz) c));
+	if (x) std::memcpy(obs->data(), x, sizeof(S) * obs->size());
+	TensorPtr<S,4> objs(new Tensor<S,4>((sz) (total > 0 ? total : 1), 1u, 1u, (sz) classes));
+	if (obj) std::memcpy(objs->data(), obj, sizeof(S) * objs->size());
+	auto loss = std::make_shared<CrossEntropyLoss<S,3,false>>();
+	NadamOptimizer<S,3,false> opt(loss, batch > 0 ? batch : 1);
+	return train_and_export<S>(net, opt, std::move(obs), std::move(objs), epochs, params_in, params_out, n_params,
+			loss_out, train_ms);
+}
+
 } /* namespace */
 
 #ifdef C_ATTL3_B200_CATTLE_H_
@@ -434,7 +563,15 @@ int ref_optimizer_hostparams_##SUF(int kind, const S* hyper, S l2_lambda, int ro
 	return opt_impl<S,StandardParameters<S>>(kind, hyper, l2_lambda, rows, cols, steps, steps_per_epoch, p0, grads, p_out); } \
 int ref_train_cifar_##SUF(int total, int batch, int epochs, const S* x, const S* obj, const S* params_in, \
 		S* params_out, double* loss_out, double* train_ms) { \
-	return cifar_impl<S>(total, batch, epochs, x, obj, params_in, params_out, loss_out, train_ms); }
+	return cifar_impl<S>(total, batch, epochs, x, obj, params_in, params_out, loss_out, train_ms); } \
+int ref_train_autoencoder_##SUF(int total, int batch, int epochs, const S* x, const S* params_in, S* params_out, \
+		int* n_params, double* loss_out, double* train_ms) { \
+	return autoencoder_impl<S>(total, batch, epochs, x, params_in, params_out, n_params, loss_out, train_ms); } \
+int ref_train_resnet_##SUF(int total, int batch, int epochs, int h, int w, int c, int stem_r, int stem_s, int stem_pool, \
+		int width, int blocks, int head_pool, int classes, const S* x, const S* obj, const S* params_in, S* params_out, \
+		int* n_params, double* loss_out, double* train_ms) { \
+	return resnet_impl<S>(total, batch, epochs, h, w, c, stem_r, stem_s, stem_pool, width, blocks, head_pool, classes, x, \
+			obj, params_in, params_out, n_params, loss_out, train_ms); }
 
 DEFINE_FOR(float, f32)
 DEFINE_FOR(double, f64)

@@ -137,3 +137,27 @@ def conv_inputs(case, dtype, seed, transposed=False):
         b = rand(rng, (1, g.f), dtype)
     dy = rand(rng, (g.n, oh, ow, g.f), dtype)
     return g, x, w, b, dy
+
+
+# ---- whole-network training cases (oracle/ref_shim.cpp: ref_train_autoencoder / ref_train_resnet) ----
+RESNET_SMALL = (3, 1, 0, 16, 2, 2)   # stem 3x3 stride 1, no stem pool, width 16, 2 residual modules, head mean-pool 2x2
+
+
+def autoencoder_inputs(dtype, total=8, seed=3001):
+    """BASELINE.json configs[2] at test size: synthetic 28x28x1 uniform [0, 1)."""
+    rng = np.random.default_rng(seed)
+    return rand(rng, (total, 28, 28, 1), dtype, 0.0, 1.0)
+
+
+def resnet_inputs(dtype, total=64, hw=8, seed=4001):
+    """BASELINE.json configs[3] at test size: synthetic hw x hw x 3, one-hot objectives i mod 10."""
+    rng = np.random.default_rng(seed)
+    x = rand(rng, (total, hw, hw, 3), dtype)
+    obj = np.zeros((total, 1, 1, 10), dtype=dtype, order="F")
+    obj[np.arange(total), 0, 0, np.arange(total) % 10] = 1
+    return x, obj
+
+
+def seeded_params(n, dtype, seed):
+    """Deterministic starting parameters (so that fixtures need not store them): uniform +-0.15."""
+    return np.random.default_rng(seed).uniform(-0.15, 0.15, n).astype(dtype)

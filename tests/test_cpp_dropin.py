@@ -147,6 +147,81 @@ def test_config1_training_matches_reference(b200, golden, dt):
         assert abs(lr - lb) < (1e-4 if dt == np.float32 else 1e-9) * max(1.0, abs(lr))
 
 
+@pytest.fixture(scope="module")
+def golden_nets():
+    return np.load(os.path.join(ROOT, "tests", "golden", "reference_networks.npz"))
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_config3_autoencoder_training_matches_reference(b200, golden_nets, dt):
+    """BASELINE.json configs[2]: examples/mnist_autoencoder.cpp's StackedNeuralNetwork (Conv, Softplus, Dense,
+    Reshape, TransConv) + SquaredLoss + Nadam through the device-resident batch loop: parameters and epoch loss
+    after 4 steps against the unmodified reference (fixture; live where oracle/_ref travelled)."""
+    suf = "f32" if dt == np.float32 else "f64"
+    x = C.autoencoder_inputs(dt)
+    n = b200.train_autoencoder(x, 4, -1)
+    assert n == golden_nets["autoencoder/%s/p1" % suf].size
+    p0 = C.seeded_params(n, dt, 3002)
+    p1, loss, _ = b200.train_autoencoder(x, 4, 2, params_in=p0)
+    tol = 1e-4 if dt == np.float32 else 1e-9
+    err = C.relerr(p1, golden_nets["autoencoder/%s/p1" % suf])
+    print("config 3 auto-encoder, 4 Nadam steps: loss %.6f (ref %.6f), param err %.2e"
+          % (loss, float(golden_nets["autoencoder/%s/loss" % suf][0]), err))
+    assert err < tol
+    assert abs(loss - float(golden_nets["autoencoder/%s/loss" % suf][0])) < tol * max(1.0, abs(loss))
+    if binding.have_ref():
+        ref = binding.Oracle("ref")
+        x = C.autoencoder_inputs(dt, total=64, seed=3003)
+        pr, lr, _ = ref.train_autoencoder(x, 32, 2, params_in=p0)
+        pb, lb, _ = b200.train_autoencoder(x, 32, 2, params_in=p0)
+        assert C.relerr(pb, pr) < (5e-4 if dt == np.float32 else 1e-8), C.relerr(pb, pr)
+        assert abs(lr - lb) < (1e-4 if dt == np.float32 else 1e-9) * max(1.0, abs(lr))
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_config4_resnet_training_matches_reference(b200, golden_nets, dt):
+    """BASELINE.json configs[3] at test size: stem + ResidualNeuralNetwork of conv + BatchNorm + ReLU modules +
+    head, CrossEntropyLoss, Nadam.  Exercises the fused epilogues (conv -> BatchNorm statistics -> ReLU) inside the
+    network loop, the device loss and the residual adds; compared with the unmodified reference."""
+    suf = "f32" if dt == np.float32 else "f64"
+    x, obj = C.resnet_inputs(dt)
+    n = b200.train_resnet(x, obj, 32, -1, C.RESNET_SMALL)
+    assert n == golden_nets["resnet/%s/p1" % suf].size
+    p0 = C.seeded_params(n, dt, 4002)
+    p1, loss, _ = b200.train_resnet(x, obj, 32, 2, C.RESNET_SMALL, params_in=p0)
+    tol = 2e-4 if dt == np.float32 else 1e-8   # batch statistics: 1 / sd amplifies the GEMM's rounding
+    err = C.relerr(p1, golden_nets["resnet/%s/p1" % suf])
+    print("config 4 ResNet (test size), 4 Nadam steps: loss %.6f (ref %.6f), param err %.2e"
+          % (loss, float(golden_nets["resnet/%s/loss" % suf][0]), err))
+    assert err < tol
+    assert abs(loss - float(golden_nets["resnet/%s/loss" % suf][0])) < tol * max(1.0, abs(loss))
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_fused_and_unfused_network_loops_agree(dt):
+    """CATTL3_NO_FUSION=1 / CATTL3_HOST_LOOP=1 switch the epilogue fusion and the device batch loop off: the same
+    training run must give the same parameters either way (fusion changes where work happens, not what is computed)."""
+    code = (
+        "import sys, numpy as np; sys.path[:0] = [%r, %r]\n"
+        "import cases as C; from oracle import binding\n"
+        "lib = binding.Oracle('ref', path=%r); dt = np.%s\n"
+        "x, obj = C.resnet_inputs(dt); n = lib.train_resnet(x, obj, 32, -1, C.RESNET_SMALL)\n"
+        "p, l, _ = lib.train_resnet(x, obj, 32, 1, C.RESNET_SMALL, params_in=C.seeded_params(n, dt, 4002))\n"
+        "np.save(sys.argv[1], p)\n" % (ROOT, os.path.join(ROOT, "tests"), SHIM, np.dtype(dt).name))
+    import tempfile
+    outs = []
+    with tempfile.TemporaryDirectory() as d:
+        for i, env in enumerate(({}, {"CATTL3_NO_FUSION": "1", "CATTL3_HOST_LOOP": "1"})):
+            path = os.path.join(d, "p%d.npy" % i)
+            r = subprocess.run([os.sys.executable, "-c", code, path], env=dict(os.environ, **env), capture_output=True,
+                               text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append(np.load(path))
+    err = C.relerr(outs[0], outs[1])
+    print("fused vs unfused parameters after 2 steps: %.2e" % err)
+    assert err < (2e-5 if dt == np.float32 else 1e-10)
+
+
 def test_reference_gradient_test_passes():
     """The reference's own gradient_test.cpp, compiled unchanged against the B200 headers."""
     if not os.path.exists(GRADIENT_TEST):

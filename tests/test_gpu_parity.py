@@ -269,3 +269,57 @@ def test_config2_full_size_properties(U):
     assert abs(lhs - mid) / scale < 1e-6 and abs(lhs - rhs) / scale < 1e-6
     colsum = dy.view(256, M).double().sum(dim=1)
     assert float((db.double() - colsum).abs().max() / colsum.abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_loss_kernels_vs_numpy(U, dt):
+    """SquaredLoss / CrossEntropyLoss on the device (loss/SquaredLoss.hpp:25-34, CrossEntropyLoss.hpp:33-42):
+    per-sample losses and the gradient divided by the batch size."""
+    import torch
+    c = U.ctx()
+    rng = np.random.default_rng(61)
+    for rows, vol in ((5, 10), (64, 784), (1, 1), (33, 7)):
+        out = C.rand(rng, (rows, vol), dt, 0.01, 1.0)
+        obj = C.rand(rng, (rows, vol), dt, 0.0, 1.0)
+        od, td = U.dev(out), U.dev(obj)
+        o64, t64 = out.astype(np.float64), obj.astype(np.float64)
+        for kind, eps, want_l, want_g in (
+                (0, 0.0, ((o64 - t64) ** 2).sum(1), 2 * (o64 - t64) / 32),
+                (1, 1e-5, -(np.log(o64 + 1e-5) * t64).sum(1), -t64 / (o64 + 1e-5) / 32)):
+            ld, gd = U.zeros((rows,), dt), U.zeros((rows, vol), dt)
+            c.loss(kind, rows, vol, eps, 32.0, od, td, ld, gd)
+            c.synchronize()
+            tol = 1e-5 if dt == np.float32 else 1e-12
+            assert C.relerr(U.host(ld, (rows,)), want_l) < tol, (kind, rows, vol)
+            assert C.relerr(U.host(gd, (rows, vol)), want_g) < tol, (kind, rows, vol)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_dropout_kernels(U, dt):
+    """DropoutLayer.hpp:74-94 on the device: y = x * mask with mask in {0, 1 / (1 - p + eps)}, the drop rate is p,
+    pass_back applies the same mask, a seed reproduces its mask and another seed gives another one."""
+    import torch
+    c = U.ctx()
+    rng = np.random.default_rng(62)
+    n, p, eps = 1 << 20, 0.25, 1e-5
+    x = C.rand(rng, (n,), dt, 0.5, 1.5)
+    dy = C.rand(rng, (n,), dt)
+    xd, dyd = U.dev(x), U.dev(dy)
+    yd, dxd = U.zeros((n,), dt), U.zeros((n,), dt)
+    mask = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    c.dropout_forward(n, p, eps, 1234, xd, yd, mask)
+    c.dropout_backward(n, p, eps, dyd, mask, dxd)
+    c.synchronize()
+    m = mask.cpu().numpy().astype(bool)
+    scale = dt(1) / (dt(1) - dt(p) + dt(eps))
+    y, dx = U.host(yd, (n,)), U.host(dxd, (n,))
+    assert np.array_equal(y, np.where(m, x * scale, 0).astype(dt))
+    assert np.array_equal(dx, np.where(m, dy * scale, 0).astype(dt))
+    assert abs((~m).mean() - p) < 4 * np.sqrt(p * (1 - p) / n)          # drop rate within 4 sigma
+    assert abs(np.corrcoef(m[:-1], m[1:])[0, 1]) < 0.01                   # neighbours are uncorrelated
+    mask2, mask3 = torch.zeros_like(mask), torch.zeros_like(mask)
+    c.dropout_forward(n, p, eps, 1234, xd, yd, mask2)
+    c.dropout_forward(n, p, eps, 1235, xd, yd, mask3)
+    c.synchronize()
+    assert torch.equal(mask, mask2)
+    assert 0.3 < (mask != mask3).float().mean().item() < 0.45            # 2 p (1 - p) = 0.375

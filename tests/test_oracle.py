@@ -111,3 +111,20 @@ def test_golden_reproducible_from_reference(ref, golden):
     r = ref.conv(g, x, w, b, dy, back_reps=2)
     assert C.relerr(r["y"], golden[k + "y"]) < 1e-14
     assert C.relerr(r["dw"], golden[k + "dw"]) < 1e-14
+
+
+@pytest.mark.parametrize("suf,dt", DTYPES)
+def test_network_fixtures_reproduce_from_the_reference(ref, suf, dt):
+    """tests/golden/reference_networks.npz (configs 3 and 4) is what the unmodified reference computes from the
+    seeded inputs of tests/cases.py: re-run it where oracle/_ref exists."""
+    import os
+    nets = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_networks.npz"))
+    x = C.autoencoder_inputs(dt)
+    n = ref.train_autoencoder(x, 4, -1)
+    p1, loss, _ = ref.train_autoencoder(x, 4, 2, params_in=C.seeded_params(n, dt, 3002))
+    assert C.relerr(p1, nets["autoencoder/%s/p1" % suf]) < 10 * OTOL[dt]
+    x, obj = C.resnet_inputs(dt)
+    n = ref.train_resnet(x, obj, 32, -1, C.RESNET_SMALL)
+    p1, loss, _ = ref.train_resnet(x, obj, 32, 2, C.RESNET_SMALL, params_in=C.seeded_params(n, dt, 4002))
+    assert C.relerr(p1, nets["resnet/%s/p1" % suf]) < 10 * OTOL[dt]
+    assert abs(loss - float(nets["resnet/%s/loss" % suf][0])) < 1e-5
