@@ -163,8 +163,15 @@ simt:
 		set_error("tcgen05 path requested but the shape/type does not qualify (needs float, batch %% 32 == 0)");
 		return CATTL3_ERR_UNSUPPORTED;
 	}
-	ctx->last_path = "simt";
-	CATTL3_CHECK(simt_gather_gemm<S>(ctx, gg, src, w, bias, bias_mode, out, ep));
+	if (!IsFloat<S>::value && ctx->conv_path != CATTL3_PATH_SIMT && dfma_gather_gemm_supported(gg)) {
+		// double at GEMM-sized shapes: the big-tile DFMA kernel (conv_dfma.cu)
+		ctx->last_path = "dfma";
+		CATTL3_CHECK(dfma_gather_gemm(ctx, gg, (const double*) src, (const double*) w, (const double*) bias, bias_mode,
+				(double*) out, ep));
+	} else {
+		ctx->last_path = "simt";
+		CATTL3_CHECK(simt_gather_gemm<S>(ctx, gg, src, w, bias, bias_mode, out, ep));
+	}
 	if (ep && ep->col_stats)
 		CATTL3_CHECK(colstats_shifted<S>(ctx, (int64_t) gg.N * gg.OH * gg.OW, gg.J, out, bias, ep->col_stats));
 	return CATTL3_OK;
@@ -184,6 +191,10 @@ static int run_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const 
 	if (ctx->conv_path == CATTL3_PATH_TCGEN05) {
 		set_error("tcgen05 weight-gradient path requested but the shape/type does not qualify");
 		return CATTL3_ERR_UNSUPPORTED;
+	}
+	if (!IsFloat<S>::value && ctx->conv_path != CATTL3_PATH_SIMT && dfma_wgrad_supported(gg)) {
+		ctx->last_path = "dfma";
+		return dfma_wgrad(ctx, gg, (const double*) src, (const double*) plain, (double*) dw);
 	}
 	ctx->last_path = "simt";
 	return simt_wgrad<S>(ctx, gg, src, plain, dw);

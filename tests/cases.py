@@ -31,6 +31,10 @@ CONV_CASES = {
     "s2_1x1": (32, 8, 8, 32, 32, 1, 1, 0, 0, 2, 2, 0, 0),
     "s2_4x4": (32, 10, 10, 16, 16, 4, 4, 1, 1, 2, 2, 0, 0),
     "s2_ragged_edge": (64, 12, 9, 16, 24, 3, 3, 0, 1, 2, 2, 0, 0),
+    # double at GEMM-sized filter counts (conv_dfma.cu): odd batch (scalar stores), 64- and 128-wide filter tiles
+    "dfma_odd": (5, 9, 7, 6, 40, 3, 3, 1, 1, 2, 1, 0, 1),
+    "dfma_mid": (6, 20, 18, 8, 72, 3, 3, 1, 1, 1, 1, 0, 0),
+    "dfma_wide": (4, 10, 9, 20, 136, 3, 2, 1, 0, 1, 1, 0, 0),
     # ragged everything: odd batch, odd channels
     "ragged": (7, 9, 11, 5, 3, 3, 4, 2, 1, 2, 1, 0, 1),
     "single": (1, 3, 3, 1, 1, 3, 3, 1, 1, 1, 1, 0, 0),
@@ -49,6 +53,7 @@ TCONV_CASES = {
     "wide_s3_k2": (32, 4, 4, 16, 16, 2, 2, 0, 0, 3, 3, 0, 0),   # output pixels that receive the bias only
     "wide_s1": (32, 6, 5, 16, 32, 3, 3, 1, 1, 1, 1, 0, 0),
     "ragged": (3, 4, 3, 5, 2, 2, 3, 0, 1, 2, 1, 1, 0),
+    "dfma_t": (8, 9, 8, 24, 48, 3, 3, 1, 1, 2, 2, 0, 0),
 }
 
 # (n, in, out)

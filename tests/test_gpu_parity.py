@@ -323,3 +323,33 @@ def test_dropout_kernels(U, dt):
     c.synchronize()
     assert torch.equal(mask, mask2)
     assert 0.3 < (mask != mask3).float().mean().item() < 0.45            # 2 p (1 - p) = 0.375
+
+
+DFMA_CASES = ["c2_small_f256", "c2_stride2", "c2_1x1", "dfma_odd", "dfma_mid", "dfma_wide"]
+
+
+@pytest.mark.parametrize("tr", [False, True])
+def test_conv_dfma_vs_oracle(U, orc, tr):
+    """The big-tile DFMA kernels (conv_dfma.cu): double, AUTO path, against the oracle at 1e-10; checks that the
+    DFMA path is the one that ran for the forward pass."""
+    table = C.TCONV_CASES if tr else C.CONV_CASES
+    names = ["dfma_t"] if tr else DFMA_CASES
+    for name in names:
+        g, x, w, b, dy = C.conv_inputs(table[name], np.float64, 71, tr)
+        r = orc.conv(g, x, w, b, dy, transposed=tr, back_reps=2)
+        a = _conv_gpu(U, table[name], x, w, b, dy, tr, reps=2, path=U.pkg.PATH_AUTO)
+        assert a["path"] == "dfma", (name, a["path"])
+        for k in ("y", "dx", "dw", "db"):
+            assert C.relerr(a[k], r[k]) < C.TOL[np.dtype(np.float64)], (name, k, C.relerr(a[k], r[k]))
+
+
+def test_conv_dfma_matches_simt_at_size(U):
+    """A mid-size double convolution (N=64, 14x14x64 -> 256, M = 12544, K = 576): the DFMA kernels against the
+    any-shape SIMT kernels, two independent implementations with different summation orders."""
+    case = (64, 14, 14, 64, 256, 3, 3, 1, 1, 1, 1, 0, 0)
+    g, x, w, b, dy = C.conv_inputs(case, np.float64, 72)
+    a = _conv_gpu(U, case, x, w, b, dy, False, path=U.pkg.PATH_AUTO)
+    s = _conv_gpu(U, case, x, w, b, dy, False, path=U.pkg.PATH_SIMT)
+    assert a["path"] == "dfma" and s["path"] == "simt"
+    for k in ("y", "dx", "dw", "db"):
+        assert C.relerr(a[k], s[k]) < 1e-13, (k, C.relerr(a[k], s[k]))
