@@ -81,7 +81,8 @@ _SYMBOLS = [
     "cattl3_pool_forward", "cattl3_pool_backward", "cattl3_batchnorm_forward", "cattl3_batchnorm_backward",
     "cattl3_optimizer_step", "cattl3_add_inplace", "cattl3_scale", "cattl3_axpy",
     "cattl3_conv_forward_fused", "cattl3_dense_forward_fused", "cattl3_batchnorm_forward_stats",
-    "cattl3_dropout_forward", "cattl3_dropout_backward", "cattl3_loss")]
+    "cattl3_dropout_forward", "cattl3_dropout_backward", "cattl3_loss",
+    "cattl3_batchnorm_stats", "cattl3_batchnorm_backward_sums", "cattl3_batchnorm_backward_apply")]
 
 
 def lib():
@@ -206,10 +207,10 @@ class Context:
 
     def batchnorm_forward_stats(self, per_channel, n, h, w, c, running_init, decay, eps, x, col_stats, shift, gamma,
                                 beta, running_mean, running_inv_sd, saved_mean, saved_inv_sd, y, act_kind=None,
-                                act_param=0.0, act_out=None):
+                                act_param=0.0, act_out=None, global_count=None):
         _, ct = _suffix(x.dtype)
         self._call("cattl3_batchnorm_forward_stats", x.dtype, int(per_channel), n, h, w, c, int(running_init),
-                   ct(decay), ct(eps), _p(x), _p(col_stats), _p(shift), _p(gamma), _p(beta), _p(running_mean),
+                   ct(decay), ct(eps), _p(x), _p(col_stats), _p(global_count), _p(shift), _p(gamma), _p(beta), _p(running_mean),
                    _p(running_inv_sd), _p(saved_mean), _p(saved_inv_sd), _p(y),
                    ACT_NONE if act_kind is None else int(act_kind), ct(act_param), _p(act_out))
 
@@ -263,6 +264,19 @@ class Context:
                            dx):
         self._call("cattl3_batchnorm_backward", x.dtype, int(per_channel), n, h, w, c, _p(x), _p(gamma),
                    _p(saved_mean), _p(saved_inv_sd), _p(dy), _p(dgamma), _p(dbeta), _p(dx))
+
+    def batchnorm_stats(self, per_channel, n, h, w, c, x, shift, col_stats):
+        self._call("cattl3_batchnorm_stats", x.dtype, int(per_channel), n, h, w, c, _p(x), _p(shift), _p(col_stats))
+
+    def batchnorm_backward_sums(self, per_channel, n, h, w, c, x, saved_mean, saved_inv_sd, dy, dgamma, dbeta, sums):
+        self._call("cattl3_batchnorm_backward_sums", x.dtype, int(per_channel), n, h, w, c, _p(x), _p(saved_mean),
+                   _p(saved_inv_sd), _p(dy), _p(dgamma), _p(dbeta), _p(sums))
+
+    def batchnorm_backward_apply(self, per_channel, n, h, w, c, global_count, x, gamma, saved_mean, saved_inv_sd, dy,
+                                 sums, dx):
+        self._call("cattl3_batchnorm_backward_apply", x.dtype, int(per_channel), n, h, w, c,
+                   _p(global_count), _p(x), _p(gamma), _p(saved_mean), _p(saved_inv_sd), _p(dy), _p(sums),
+                   _p(dx))
 
     def optimizer_step(self, step, count, p, g, s1=None, s2=None, s3=None):
         self._call("cattl3_optimizer_step", p.dtype, ctypes.byref(step), ctypes.c_int64(count), _p(p), _p(g),

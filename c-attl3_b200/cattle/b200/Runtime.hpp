@@ -113,14 +113,20 @@ template<> struct Api<S> { \
 		return cattl3_conv_forward_fused_##SUF(c, g, x, w, b, y, ep); } \
 	static int dense_forward_fused(cattl3_ctx* c, std::int32_t n, std::int32_t in, std::int32_t out, const S* x, const S* w, const S* b, S* y, const cattl3_epilogue* ep) { \
 		return cattl3_dense_forward_fused_##SUF(c, n, in, out, x, w, b, y, ep); } \
-	static int batchnorm_forward_stats(cattl3_ctx* c, int pc, std::int32_t n, std::int32_t h, std::int32_t w, std::int32_t ch, int init, S decay, S eps, const S* x, const double* cs, const S* shift, const S* gamma, const S* beta, S* rm, S* rs, S* sm, S* ss, S* y, int ak, S ap, S* ao) { \
-		return cattl3_batchnorm_forward_stats_##SUF(c, pc, n, h, w, ch, init, decay, eps, x, cs, shift, gamma, beta, rm, rs, sm, ss, y, ak, ap, ao); } \
+	static int batchnorm_forward_stats(cattl3_ctx* c, int pc, std::int32_t n, std::int32_t h, std::int32_t w, std::int32_t ch, int init, S decay, S eps, const S* x, const double* cs, const double* gc, const S* shift, const S* gamma, const S* beta, S* rm, S* rs, S* sm, S* ss, S* y, int ak, S ap, S* ao) { \
+		return cattl3_batchnorm_forward_stats_##SUF(c, pc, n, h, w, ch, init, decay, eps, x, cs, gc, shift, gamma, beta, rm, rs, sm, ss, y, ak, ap, ao); } \
 	static int dropout_forward(cattl3_ctx* c, std::int64_t count, S prob, S eps, std::uint64_t seed, const S* x, S* y, std::uint8_t* mask) { \
 		return cattl3_dropout_forward_##SUF(c, count, prob, eps, seed, x, y, mask); } \
 	static int dropout_backward(cattl3_ctx* c, std::int64_t count, S prob, S eps, const S* dy, const std::uint8_t* mask, S* dx) { \
 		return cattl3_dropout_backward_##SUF(c, count, prob, eps, dy, mask, dx); } \
 	static int loss(cattl3_ctx* c, int kind, std::int64_t rows, std::int64_t vol, S eps, S grad_div, const S* out, const S* obj, S* loss, S* grad) { \
 		return cattl3_loss_##SUF(c, kind, rows, vol, eps, grad_div, out, obj, loss, grad); } \
+	static int batchnorm_stats(cattl3_ctx* c, int pc, std::int32_t n, std::int32_t h, std::int32_t w, std::int32_t ch, const S* x, const S* shift, double* cs) { \
+		return cattl3_batchnorm_stats_##SUF(c, pc, n, h, w, ch, x, shift, cs); } \
+	static int batchnorm_backward_sums(cattl3_ctx* c, int pc, std::int32_t n, std::int32_t h, std::int32_t w, std::int32_t ch, const S* x, const S* sm, const S* ss, const S* dy, S* dg, S* db, double* sums) { \
+		return cattl3_batchnorm_backward_sums_##SUF(c, pc, n, h, w, ch, x, sm, ss, dy, dg, db, sums); } \
+	static int batchnorm_backward_apply(cattl3_ctx* c, int pc, std::int32_t n, std::int32_t h, std::int32_t w, std::int32_t ch, const double* total, const S* x, const S* gamma, const S* sm, const S* ss, const S* dy, const double* sums, S* dx) { \
+		return cattl3_batchnorm_backward_apply_##SUF(c, pc, n, h, w, ch, total, x, gamma, sm, ss, dy, sums, dx); } \
 	static int conv_backward(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* dy, S* dw, S* db, S* dx) { \
 		return cattl3_conv_backward_##SUF(c, g, x, w, dy, dw, db, dx); } \
 	static int transconv_forward(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y) { \

@@ -20,11 +20,19 @@
  * them), a channel is a contiguous run of N*H*W elements because the sample index is the fastest
  * dimension, and each pass is two reductions plus one apply kernel (cattl3_batchnorm_forward /
  * cattl3_batchnorm_backward, include/cattl3_b200.h) instead of a slice copy per channel (:182-188).
+ *
+ * Data-parallel training (b200::Communicator with more than one rank; the reference is single process): the
+ * batch statistics are SYNCHRONISED -- the per-group sums of the forward pass and of the backward pass are
+ * all-reduced over the ranks together with the element count (2 * groups + 1 doubles per direction, no host
+ * synchronisation), so that every rank normalises with the statistics of the whole mini-batch, the running
+ * averages stay identical on all replicas and G GPUs compute what one GPU computes on the full batch
+ * (SURVEY.md section 8e).  CATTL3_SYNC_BN=0 turns it off (each rank then uses its shard's statistics).
  */
 #ifndef C_ATTL3_LAYER_BATCHNORMLAYER_H_
 #define C_ATTL3_LAYER_BATCHNORMLAYER_H_
 
 #include <cassert>
+#include <cstdlib>
 #include <memory>
 #include <utility>
 #include <vector>
@@ -34,6 +42,7 @@
 #include "parameter_initialization/OneParameterInitialization.hpp"
 #include "parameter_initialization/ZeroParameterInitialization.hpp"
 #include "parameters/B200Parameters.hpp"
+#include "b200/Communicator.hpp"
 #include "b200/DeviceLayer.hpp"
 
 namespace cattle {
@@ -100,7 +109,8 @@ public:
 			cached_rows(layer.cached_rows),
 			in_cache(layer.in_cache),
 			batch_means(layer.batch_means),
-			batch_inv_sds(layer.batch_inv_sds) {
+			batch_inv_sds(layer.batch_inv_sds),
+			global_count(layer.global_count) {
 		if (share_params) {
 			avg_means = layer.avg_means;
 			avg_inv_sds = layer.avg_inv_sds;
@@ -182,6 +192,19 @@ public:
 		return b200::to_host<Scalar,Base::DATA_RANK>(prev_out_grad, b200::batch_extents<Rank>(prev_out_grad.rows, dims));
 	}
 	inline DevTensor pass_forward_dev(DevTensor in, bool training) {
+		if (training && synchronised()) {
+			// sums first (shifted by the running mean, which is identical on all ranks), then the shared path
+			b200::FusedEpilogue<Scalar> ep;
+			ep.col_stats = std::make_shared<b200::DeviceBuffer<double>>(2 * groups + 1);
+			ep.shift = avg_means[0]->device_values();
+			b200::Context& c = b200::Context::get();
+			{
+				b200::Context::Lock l = c.lock();
+				CATTLE_B200_CHECK(b200::Api<Scalar>::batchnorm_stats(c.handle(), PerLastRank ? 1 : 0,
+						(std::int32_t) in.rows, geom_h(), 1, geom_c(), in.data(), ep.shift, ep.col_stats->data()));
+			}
+			return accept_epilogue(std::move(in), ep, training, nullptr);
+		}
 		DevTensor out(in.rows, dims.get_volume());
 		if (training && batch_means.size() != groups) {
 			batch_means = b200::DeviceBuffer<Scalar>(groups);
@@ -205,6 +228,7 @@ public:
 			avgs_init = true;
 			cached_rows = in.rows;
 			in_cache = std::move(in);
+			global_count = b200::DeviceBuffer<double>();
 		}
 		return out;
 	}
@@ -225,8 +249,25 @@ public:
 	}
 	inline DevTensor accept_epilogue(DevTensor in, b200::FusedEpilogue<Scalar>& ep, bool training,
 			b200::FusedEpilogue<Scalar>* next) {
-		if (!training || in.empty() || !ep.col_stats || ep.col_stats->size() != 2 * groups || !ep.shift)
+		if (!training || in.empty() || !ep.col_stats || ep.col_stats->size() != 2 * groups + 1 || !ep.shift)
 			throw b200::Error(CATTL3_ERR_INVALID, "BatchNormLayer: incomplete fused epilogue");
+		const double* count_ptr = nullptr;
+		if (synchronised()) {
+			// [sums | element count] summed over the ranks in one message; the count stays on the device
+			const double local_count = (double) in.rows * (double) geom_h();
+			ep.col_stats->upload(&local_count, 1, 2 * groups);
+			b200::Communicator::get().all_reduce_sum(ep.col_stats->data(), 2 * groups + 1);
+			global_count = b200::DeviceBuffer<double>(1);
+			{
+				b200::Context& c = b200::Context::get();
+				b200::Context::Lock l = c.lock();
+				CATTLE_B200_CHECK(cattl3_memcpy_d2d(c.handle(), global_count.data(), ep.col_stats->data() + 2 * groups,
+						sizeof(double)));
+			}
+			count_ptr = global_count.data();
+		} else {
+			global_count = b200::DeviceBuffer<double>();
+		}
 		const bool act = next != nullptr && next->act_kind != CATTL3_ACT_NONE;
 		DevTensor out;
 		if (!act || next->keep_pre)
@@ -242,7 +283,7 @@ public:
 			b200::Context::Lock l = c.lock();
 			CATTLE_B200_CHECK(b200::Api<Scalar>::batchnorm_forward_stats(c.handle(), PerLastRank ? 1 : 0,
 					(std::int32_t) in.rows, geom_h(), 1, geom_c(), avgs_init ? 1 : 0, norm_avg_decay, epsilon, in.data(),
-					ep.col_stats->data(), ep.shift, gammas[0]->device_values(), betas[0]->device_values(),
+					ep.col_stats->data(), count_ptr, ep.shift, gammas[0]->device_values(), betas[0]->device_values(),
 					avg_means[0]->device_values(), avg_inv_sds[0]->device_values(), batch_means.data(),
 					batch_inv_sds.data(), out.data(), act ? next->act_kind : CATTL3_ACT_NONE,
 					act ? next->act_param : (Scalar) 0, act ? next->act_out.data() : nullptr));
@@ -261,7 +302,25 @@ public:
 		if (!input_layer)
 			prev_out_grad = DevTensor(out_grad.rows, dims.get_volume());
 		b200::Context& c = b200::Context::get();
-		{
+		if (!global_count.empty()) {
+			// synchronised statistics: the two sums of the backward pass are all-reduced as well; dgamma / dbeta get
+			// the local sums (the optimizer's gradient all-reduce adds the ranks' shares)
+			b200::DeviceBuffer<double> sums(2 * groups);
+			{
+				b200::Context::Lock l = c.lock();
+				CATTLE_B200_CHECK(b200::Api<Scalar>::batchnorm_backward_sums(c.handle(), PerLastRank ? 1 : 0,
+						(std::int32_t) out_grad.rows, geom_h(), 1, geom_c(), in_cache.data(), batch_means.data(),
+						batch_inv_sds.data(), out_grad.data(), gammas[0]->device_grad(), betas[0]->device_grad(), sums.data()));
+			}
+			if (!input_layer) {
+				b200::Communicator::get().all_reduce_sum(sums.data(), 2 * groups);
+				b200::Context::Lock l = c.lock();
+				CATTLE_B200_CHECK(b200::Api<Scalar>::batchnorm_backward_apply(c.handle(), PerLastRank ? 1 : 0,
+						(std::int32_t) out_grad.rows, geom_h(), 1, geom_c(), global_count.data(), in_cache.data(),
+						gammas[0]->device_values(), batch_means.data(), batch_inv_sds.data(), out_grad.data(), sums.data(),
+						prev_out_grad.data()));
+			}
+		} else {
 			b200::Context::Lock l = c.lock();
 			CATTLE_B200_CHECK(b200::Api<Scalar>::batchnorm_backward(c.handle(), PerLastRank ? 1 : 0,
 					(std::int32_t) out_grad.rows, geom_h(), 1, geom_c(), in_cache.data(), gammas[0]->device_values(),
@@ -286,6 +345,14 @@ private:
 	inline std::int32_t geom_h() const {
 		return (std::int32_t) (dims.get_volume() / groups);
 	}
+	/** Whether the batch statistics span all ranks of a data-parallel job (see the file comment). */
+	inline static bool synchronised() {
+		static const bool enabled = [] {
+			const char* v = std::getenv("CATTL3_SYNC_BN");
+			return !(v && v[0] == '0');
+		}();
+		return enabled && b200::Communicator::get().world_size() > 1;
+	}
 	inline static DevParamsSharedPtr rebased(const B200Parameters<Scalar>& original,
 			std::shared_ptr<Storage> value_store, std::shared_ptr<Storage> grad_store, std::size_t index) {
 		// clone() carries the hyper-parameters (initialisation, regularisation, constraints, frozen flag)
@@ -305,6 +372,8 @@ private:
 	std::size_t cached_rows;
 	DevTensor in_cache;
 	b200::DeviceBuffer<Scalar> batch_means, batch_inv_sds;
+	// elements per group over all ranks in the last training pass (device scalar); empty = local statistics
+	b200::DeviceBuffer<double> global_count;
 };
 
 } /* namespace cattle */

@@ -109,7 +109,7 @@ public:
 			e.act_out = ep.act_out.data();
 		}
 		if (ep.want_stats) {
-			ep.col_stats = std::make_shared<b200::DeviceBuffer<double>>(2 * volume);
+			ep.col_stats = std::make_shared<b200::DeviceBuffer<double>>(2 * volume + 1);  // + the element count (synchronised BN)
 			e.col_stats = ep.col_stats->data();
 			ep.shift = b.device_values();
 		}

@@ -457,14 +457,16 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(long long L, long long ch
 // Statistics from the column sums a kernel layer's epilogue produced (cattl3_epilogue::col_stats): S1 = sum (x - shift),
 // S2 = sum (x - shift)^2 per group.  Same outputs as bn_stats_final_kernel.
 template<typename S>
-__global__ void __launch_bounds__(128) bn_stats_from_sums_kernel(long long groups, long long L,
-		const double* __restrict__ col_stats, const S* __restrict__ shift, S eps, S decay, int running_init,
+__global__ void __launch_bounds__(128) bn_stats_from_sums_kernel(long long groups, long long L_local,
+		const double* __restrict__ global_count, const double* __restrict__ col_stats, const S* __restrict__ shift,
+		S eps, S decay, int running_init,
 		S* __restrict__ running_mean, S* __restrict__ running_inv_sd, S* __restrict__ saved_mean,
 		S* __restrict__ saved_inv_sd) {
 	const long long g = blockIdx.x * 128ll + threadIdx.x;
 	if (g >= groups) return;
-	const double m1 = col_stats[g] / (double) L;
-	double var = col_stats[groups + g] / (double) L - m1 * m1;
+	const double L = global_count ? *global_count : (double) L_local;   // elements behind the sums (all ranks)
+	const double m1 = col_stats[g] / L;
+	double var = col_stats[groups + g] / L - m1 * m1;
 	var = var < 0 ? 0 : var;
 	const S mean = (S) ((double) shift[g] + m1);
 	const S inv_sd = (S) (1.0 / sqrt(var + (double) eps));
@@ -534,27 +536,31 @@ __global__ void __launch_bounds__(256) bn_bwd_partial_kernel(long long L, long l
 // sums[g] = (sum dy, sum dy*xhat); dgamma/dbeta accumulate (BatchNormLayer.hpp:252-254).
 template<typename S>
 __global__ void __launch_bounds__(128) bn_bwd_final_kernel(long long groups, int chunks,
-		BnPartial* __restrict__ part, S* __restrict__ dgamma, S* __restrict__ dbeta) {
+		const BnPartial* __restrict__ part, S* __restrict__ dgamma, S* __restrict__ dbeta, double* __restrict__ sums) {
 	const long long g = blockIdx.x * 128ll + threadIdx.x;
 	if (g >= groups) return;
 	double s1 = 0, s2 = 0;
 	for (int c = 0; c < chunks; ++c) { s1 += part[g * chunks + c].s1; s2 += part[g * chunks + c].s2; }
-	part[g * chunks] = BnPartial{ s1, s2 };
+	sums[g] = s1;
+	sums[groups + g] = s2;
 	dbeta[g] += (S) s1;
 	dgamma[g] += (S) s2;
 }
 
 // dx = (L*g - sum g - xhat * sum(xhat g)) * inv_sd / L with g = gamma * dy (BatchNormLayer.hpp:257-261).
+// `sums` = (sum dy, sum dy*xhat) per group over ALL `Ltot` elements of the statistic (the local L, or the whole
+// data-parallel batch when the sums were all-reduced).
 template<typename S>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(long long L, long long chunk, int chunks, int vec,
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(long long L, const double* __restrict__ global_count, long long chunk, int vec,
 		const S* __restrict__ x, const S* __restrict__ mean, const S* __restrict__ inv_sd,
-		const S* __restrict__ gamma, const BnPartial* __restrict__ part, const S* __restrict__ dy,
+		const S* __restrict__ gamma, const double* __restrict__ sums, const S* __restrict__ dy,
 		S* __restrict__ dx) {
 	typedef typename V16<S>::type V;
 	const long long g = blockIdx.x;
 	const S mu = mean[g], sc = inv_sd[g], gm = gamma[g];
-	const S sum_g = gm * (S) part[g * chunks].s1, sum_xg = gm * (S) part[g * chunks].s2;
-	const S scale = ((S) 1 / (S) L) * sc;
+	const S sum_g = gm * (S) sums[g], sum_xg = gm * (S) sums[gridDim.x + g];
+	const S Ltot = global_count ? (S) *global_count : (S) L;
+	const S scale = ((S) 1 / Ltot) * sc;
 	const long long lo = (long long) blockIdx.y * chunk;
 	const long long hi = lo + chunk < L ? lo + chunk : L;
 	const S* xg = x + g * L;
@@ -568,11 +574,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(long long L, long lon
 		_Pragma("unroll")
 		for (int k = 0; k < G_; ++k) {
 			const S xh = (ex[k] - mu) * sc;
-			eg[k] = (((S) L * (gm * eg[k]) - sum_g) - xh * sum_xg) * scale;
+			eg[k] = ((Ltot * (gm * eg[k]) - sum_g) - xh * sum_xg) * scale;
 		}
 		*reinterpret_cast<V*>(dxg + i) = vg;,
 		const S xh = (xg[i] - mu) * sc;
-		dxg[i] = (((S) L * (gm * dyg[i]) - sum_g) - xh * sum_xg) * scale;)
+		dxg[i] = ((Ltot * (gm * dyg[i]) - sum_g) - xh * sum_xg) * scale;)
 }
 
 static void bn_partition(const cattl3_ctx* ctx, long long groups, long long L, int* chunks, long long* chunk,
@@ -621,8 +627,9 @@ int batchnorm_forward(cattl3_ctx* ctx, int per_channel, int n, int h, int w, int
 
 template<typename S>
 int batchnorm_forward_stats(cattl3_ctx* ctx, int per_channel, int n, int h, int w, int c, int running_init, S decay,
-		S eps, const S* x, const double* col_stats, const S* shift, const S* gamma, const S* beta, S* running_mean,
-		S* running_inv_sd, S* saved_mean, S* saved_inv_sd, S* y, int act_kind, S act_param, S* act_out) {
+		S eps, const S* x, const double* col_stats, const double* global_count, const S* shift, const S* gamma,
+		const S* beta, S* running_mean, S* running_inv_sd, S* saved_mean, S* saved_inv_sd, S* y, int act_kind,
+		S act_param, S* act_out) {
 	CATTL3_CHECK(check_ctx(ctx));
 	CATTL3_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && x && col_stats && shift && gamma && beta && running_mean &&
 			running_inv_sd && saved_mean && saved_inv_sd, "batchnorm_forward_stats: bad arguments");
@@ -636,8 +643,8 @@ int batchnorm_forward_stats(cattl3_ctx* ctx, int per_channel, int n, int h, int 
 	long long chunk;
 	bn_partition(ctx, groups, L, &chunks, &chunk, &threads);
 	dim3 grid((unsigned) groups, (unsigned) chunks);
-	bn_stats_from_sums_kernel<S><<<(unsigned) ceil_div(groups, 128), 128, 0, ctx->stream>>>(groups, L, col_stats, shift, eps,
-			decay, running_init, running_mean, running_inv_sd, saved_mean, saved_inv_sd);
+	bn_stats_from_sums_kernel<S><<<(unsigned) ceil_div(groups, 128), 128, 0, ctx->stream>>>(groups, L, global_count, col_stats,
+			shift, eps, decay, running_init, running_mean, running_inv_sd, saved_mean, saved_inv_sd);
 	CATTL3_LAUNCHED(ctx);
 	const int vec = L % V16<S>::G == 0 && aligned16(x) && (!y || aligned16(y)) && (!act_out || aligned16(act_out));
 	if (act_kind == CATTL3_ACT_NONE)
@@ -649,12 +656,15 @@ int batchnorm_forward_stats(cattl3_ctx* ctx, int per_channel, int n, int h, int 
 	return CATTL3_OK;
 }
 
+// The backward pass in two halves (they are one call for a single process): `sums` = (sum dy, sum dy*xhat) per group,
+// with the LOCAL sums accumulated into dgamma / dbeta; then dx from sums that may have been all-reduced over the
+// data-parallel ranks (synchronised batch statistics), `total_count` = elements per group over all ranks.
 template<typename S>
-int batchnorm_backward(cattl3_ctx* ctx, int per_channel, int n, int h, int w, int c, const S* x,
-		const S* gamma, const S* saved_mean, const S* saved_inv_sd, const S* dy, S* dgamma, S* dbeta, S* dx) {
+int batchnorm_backward_sums(cattl3_ctx* ctx, int per_channel, int n, int h, int w, int c, const S* x,
+		const S* saved_mean, const S* saved_inv_sd, const S* dy, S* dgamma, S* dbeta, double* sums) {
 	CATTL3_CHECK(check_ctx(ctx));
-	CATTL3_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && x && gamma && saved_mean && saved_inv_sd && dy &&
-			dgamma && dbeta, "batchnorm_backward: bad arguments");
+	CATTL3_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && x && saved_mean && saved_inv_sd && dy && dgamma && dbeta && sums,
+			"batchnorm_backward_sums: bad arguments");
 	const long long groups = per_channel ? c : (long long) h * w * c;
 	const long long L = per_channel ? (long long) n * h * w : n;
 	CATTL3_REQUIRE(groups <= 2147483647ll, "batchnorm: too many groups");
@@ -662,20 +672,63 @@ int batchnorm_backward(cattl3_ctx* ctx, int per_channel, int n, int h, int w, in
 	long long chunk;
 	bn_partition(ctx, groups, L, &chunks, &chunk, &threads);
 	dim3 grid((unsigned) groups, (unsigned) chunks);
-	const int vec = L % V16<S>::G == 0 && aligned16(x) && aligned16(dy) && (!dx || aligned16(dx));
+	const int vec = L % V16<S>::G == 0 && aligned16(x) && aligned16(dy);
 	CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, sizeof(BnPartial) * groups * chunks));
 	bn_bwd_partial_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, vec, x, saved_mean, saved_inv_sd, dy,
 			(BnPartial*) ctx->ws);
 	CATTL3_LAUNCHED(ctx);
 	bn_bwd_final_kernel<S><<<(unsigned) ceil_div(groups, 128), 128, 0, ctx->stream>>>(groups, chunks,
-			(BnPartial*) ctx->ws, dgamma, dbeta);
+			(const BnPartial*) ctx->ws, dgamma, dbeta, sums);
 	CATTL3_LAUNCHED(ctx);
-	if (dx) {
-		bn_bwd_apply_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, chunk, chunks, vec, x, saved_mean, saved_inv_sd,
-				gamma, (const BnPartial*) ctx->ws, dy, dx);
-		CATTL3_LAUNCHED(ctx);
-	}
 	return CATTL3_OK;
+}
+
+template<typename S>
+int batchnorm_backward_apply(cattl3_ctx* ctx, int per_channel, int n, int h, int w, int c, const double* global_count,
+		const S* x, const S* gamma, const S* saved_mean, const S* saved_inv_sd, const S* dy, const double* sums, S* dx) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && x && gamma && saved_mean && saved_inv_sd && dy && sums && dx,
+			"batchnorm_backward_apply: bad arguments");
+	const long long groups = per_channel ? c : (long long) h * w * c;
+	const long long L = per_channel ? (long long) n * h * w : n;
+	CATTL3_REQUIRE(groups <= 2147483647ll, "batchnorm: too many groups");
+	int chunks, threads;
+	long long chunk;
+	bn_partition(ctx, groups, L, &chunks, &chunk, &threads);
+	dim3 grid((unsigned) groups, (unsigned) chunks);
+	const int vec = L % V16<S>::G == 0 && aligned16(x) && aligned16(dy) && aligned16(dx);
+	bn_bwd_apply_kernel<S><<<grid, threads, 0, ctx->stream>>>(L, global_count, chunk, vec, x, saved_mean, saved_inv_sd,
+			gamma, sums, dy, dx);
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+
+template<typename S>
+int batchnorm_backward(cattl3_ctx* ctx, int per_channel, int n, int h, int w, int c, const S* x,
+		const S* gamma, const S* saved_mean, const S* saved_inv_sd, const S* dy, S* dgamma, S* dbeta, S* dx) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && gamma, "batchnorm_backward: bad arguments");
+	const long long groups = per_channel ? c : (long long) h * w * c;
+	CATTL3_CHECK(ensure_buffer(ctx, &ctx->stat_ws, &ctx->stat_ws_bytes, sizeof(double) * 2 * groups));
+	CATTL3_CHECK(batchnorm_backward_sums<S>(ctx, per_channel, n, h, w, c, x, saved_mean, saved_inv_sd, dy, dgamma, dbeta,
+			(double*) ctx->stat_ws));
+	if (!dx)
+		return CATTL3_OK;
+	return batchnorm_backward_apply<S>(ctx, per_channel, n, h, w, c, (const double*) nullptr, x, gamma, saved_mean,
+			saved_inv_sd, dy, (const double*) ctx->stat_ws, dx);
+}
+
+// Per-group shifted sums of a batch-norm input (the first reduction of the training forward pass) on their own: what a
+// kernel layer's fused epilogue would have produced (cattl3_epilogue::col_stats), for inputs that come from
+// elsewhere and for synchronised statistics (all-reduce them, then cattl3_batchnorm_forward_stats).
+template<typename S>
+int batchnorm_stats(cattl3_ctx* ctx, int per_channel, int n, int h, int w, int c, const S* x, const S* shift,
+		double* col_stats) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && x && shift && col_stats, "batchnorm_stats: bad arguments");
+	const long long groups = per_channel ? c : (long long) h * w * c;
+	const long long L = per_channel ? (long long) n * h * w : n;
+	return colstats_shifted<S>(ctx, L, groups, x, shift, col_stats);
 }
 
 // ---- fused optimizer step ------------------------------------------------------------------------
@@ -974,10 +1027,22 @@ int cattl3_batchnorm_forward_f32(cattl3_ctx* c, int pc, int32_t n, int32_t h, in
 	return batchnorm_forward<float>(c, pc, n, h, w, ch, training, rinit, decay, eps, x, gamma, beta, rm, rs, sm, ss, y); }
 int cattl3_batchnorm_forward_f64(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, int training, int rinit, double decay, double eps, const double* x, const double* gamma, const double* beta, double* rm, double* rs, double* sm, double* ss, double* y) {
 	return batchnorm_forward<double>(c, pc, n, h, w, ch, training, rinit, decay, eps, x, gamma, beta, rm, rs, sm, ss, y); }
-int cattl3_batchnorm_forward_stats_f32(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, int rinit, float decay, float eps, const float* x, const double* cs, const float* shift, const float* gamma, const float* beta, float* rm, float* rs, float* sm, float* ss, float* y, int ak, float ap, float* ao) {
-	return batchnorm_forward_stats<float>(c, pc, n, h, w, ch, rinit, decay, eps, x, cs, shift, gamma, beta, rm, rs, sm, ss, y, ak, ap, ao); }
-int cattl3_batchnorm_forward_stats_f64(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, int rinit, double decay, double eps, const double* x, const double* cs, const double* shift, const double* gamma, const double* beta, double* rm, double* rs, double* sm, double* ss, double* y, int ak, double ap, double* ao) {
-	return batchnorm_forward_stats<double>(c, pc, n, h, w, ch, rinit, decay, eps, x, cs, shift, gamma, beta, rm, rs, sm, ss, y, ak, ap, ao); }
+int cattl3_batchnorm_forward_stats_f32(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, int rinit, float decay, float eps, const float* x, const double* cs, const double* gc, const float* shift, const float* gamma, const float* beta, float* rm, float* rs, float* sm, float* ss, float* y, int ak, float ap, float* ao) {
+	return batchnorm_forward_stats<float>(c, pc, n, h, w, ch, rinit, decay, eps, x, cs, gc, shift, gamma, beta, rm, rs, sm, ss, y, ak, ap, ao); }
+int cattl3_batchnorm_forward_stats_f64(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, int rinit, double decay, double eps, const double* x, const double* cs, const double* gc, const double* shift, const double* gamma, const double* beta, double* rm, double* rs, double* sm, double* ss, double* y, int ak, double ap, double* ao) {
+	return batchnorm_forward_stats<double>(c, pc, n, h, w, ch, rinit, decay, eps, x, cs, gc, shift, gamma, beta, rm, rs, sm, ss, y, ak, ap, ao); }
+int cattl3_batchnorm_stats_f32(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, const float* x, const float* shift, double* cs) {
+	return batchnorm_stats<float>(c, pc, n, h, w, ch, x, shift, cs); }
+int cattl3_batchnorm_stats_f64(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, const double* x, const double* shift, double* cs) {
+	return batchnorm_stats<double>(c, pc, n, h, w, ch, x, shift, cs); }
+int cattl3_batchnorm_backward_sums_f32(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, const float* x, const float* sm, const float* ss, const float* dy, float* dgamma, float* dbeta, double* sums) {
+	return batchnorm_backward_sums<float>(c, pc, n, h, w, ch, x, sm, ss, dy, dgamma, dbeta, sums); }
+int cattl3_batchnorm_backward_sums_f64(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, const double* x, const double* sm, const double* ss, const double* dy, double* dgamma, double* dbeta, double* sums) {
+	return batchnorm_backward_sums<double>(c, pc, n, h, w, ch, x, sm, ss, dy, dgamma, dbeta, sums); }
+int cattl3_batchnorm_backward_apply_f32(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, const double* total, const float* x, const float* gamma, const float* sm, const float* ss, const float* dy, const double* sums, float* dx) {
+	return batchnorm_backward_apply<float>(c, pc, n, h, w, ch, total, x, gamma, sm, ss, dy, sums, dx); }
+int cattl3_batchnorm_backward_apply_f64(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, const double* total, const double* x, const double* gamma, const double* sm, const double* ss, const double* dy, const double* sums, double* dx) {
+	return batchnorm_backward_apply<double>(c, pc, n, h, w, ch, total, x, gamma, sm, ss, dy, sums, dx); }
 int cattl3_batchnorm_backward_f32(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, const float* x, const float* gamma, const float* sm, const float* ss, const float* dy, float* dgamma, float* dbeta, float* dx) {
 	return batchnorm_backward<float>(c, pc, n, h, w, ch, x, gamma, sm, ss, dy, dgamma, dbeta, dx); }
 int cattl3_batchnorm_backward_f64(cattl3_ctx* c, int pc, int32_t n, int32_t h, int32_t w, int32_t ch, const double* x, const double* gamma, const double* sm, const double* ss, const double* dy, double* dgamma, double* dbeta, double* dx) {

@@ -285,13 +285,34 @@ int cattl3_batchnorm_forward_f64(cattl3_ctx*, int per_channel, int32_t n, int32_
 /*
  * Training forward pass whose statistics reduction already happened in the producing kernel layer's epilogue:
  * col_stats (2 * groups doubles, cattl3_epilogue) are the sums of (x - shift) and (x - shift)^2 per group, shift = the
- * producer's bias (groups elements).  mean = shift + S1/L, var = S2/L - (S1/L)^2 in double; the rest (saved
+ * producer's bias (groups elements).  mean = shift + S1/L, var = S2/L - (S1/L)^2 in double, where L = n*h*w (or n)
+ * unless global_count (a DEVICE scalar: the elements behind all-reduced sums, see cattl3_batchnorm_stats) is
+ * given; the rest (saved
  * statistics, running averages, y) is cattl3_batchnorm_forward with training = 1.  The normalise pass can apply a
  * following element-wise activation as well: act_kind != CATTL3_ACT_NONE writes act_out = f(y) (y, the activation's
  * cached input, is still written unless NULL).
  */
-int cattl3_batchnorm_forward_stats_f32(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, int running_initialised, float decay, float eps, const float* x, const double* col_stats, const float* shift, const float* gamma, const float* beta, float* running_mean, float* running_inv_sd, float* saved_mean, float* saved_inv_sd, float* y, int act_kind, float act_param, float* act_out);
-int cattl3_batchnorm_forward_stats_f64(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, int running_initialised, double decay, double eps, const double* x, const double* col_stats, const double* shift, const double* gamma, const double* beta, double* running_mean, double* running_inv_sd, double* saved_mean, double* saved_inv_sd, double* y, int act_kind, double act_param, double* act_out);
+int cattl3_batchnorm_forward_stats_f32(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, int running_initialised, float decay, float eps, const float* x, const double* col_stats, const double* global_count, const float* shift, const float* gamma, const float* beta, float* running_mean, float* running_inv_sd, float* saved_mean, float* saved_inv_sd, float* y, int act_kind, float act_param, float* act_out);
+int cattl3_batchnorm_forward_stats_f64(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, int running_initialised, double decay, double eps, const double* x, const double* col_stats, const double* global_count, const double* shift, const double* gamma, const double* beta, double* running_mean, double* running_inv_sd, double* saved_mean, double* saved_inv_sd, double* y, int act_kind, double act_param, double* act_out);
+/*
+ * The per-group shifted sums on their own (what cattl3_epilogue::col_stats holds): col_stats[g] = sum (x - shift[g]),
+ * col_stats[groups + g] = sum (x - shift[g])^2, in double.  For batch-norm inputs that do not come out of a kernel
+ * layer's epilogue and for SYNCHRONISED statistics in data-parallel training: all-reduce the sums
+ * over the ranks together with the element count and call cattl3_batchnorm_forward_stats with global_count.
+ */
+int cattl3_batchnorm_stats_f32(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, const float* x, const float* shift, double* col_stats);
+int cattl3_batchnorm_stats_f64(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, const double* x, const double* shift, double* col_stats);
+/*
+ * cattl3_batchnorm_backward in two halves, for synchronised statistics: _sums writes sums[g] = sum dy,
+ * sums[groups + g] = sum dy * xhat (double) and ACCUMULATES the local sums into dbeta / dgamma (the gradient
+ * all-reduce adds the ranks' shares later); _apply computes dx from sums that were all-reduced in between,
+ * global_count = a DEVICE scalar holding the elements per group over all ranks, all-reduced with the sums so that
+ * no host synchronisation is needed (NULL = the local count) (BatchNormLayer.hpp:257-261 with L = the global batch).
+ */
+int cattl3_batchnorm_backward_sums_f32(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, const float* x, const float* saved_mean, const float* saved_inv_sd, const float* dy, float* dgamma, float* dbeta, double* sums);
+int cattl3_batchnorm_backward_sums_f64(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, const double* x, const double* saved_mean, const double* saved_inv_sd, const double* dy, double* dgamma, double* dbeta, double* sums);
+int cattl3_batchnorm_backward_apply_f32(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, const double* global_count, const float* x, const float* gamma, const float* saved_mean, const float* saved_inv_sd, const float* dy, const double* sums, float* dx);
+int cattl3_batchnorm_backward_apply_f64(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, const double* global_count, const double* x, const double* gamma, const double* saved_mean, const double* saved_inv_sd, const double* dy, const double* sums, double* dx);
 /* dgamma / dbeta ACCUMULATE; dx may be NULL (input layer). */
 int cattl3_batchnorm_backward_f32(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, const float* x, const float* gamma, const float* saved_mean, const float* saved_inv_sd, const float* dy, float* dgamma, float* dbeta, float* dx);
 int cattl3_batchnorm_backward_f64(cattl3_ctx*, int per_channel, int32_t n, int32_t h, int32_t w, int32_t c, const double* x, const double* gamma, const double* saved_mean, const double* saved_inv_sd, const double* dy, double* dgamma, double* dbeta, double* dx);

@@ -118,3 +118,113 @@ def test_two_process_training_equals_one_process(tmp_path, golden, suf):
     print("1 vs 2 processes (%s): param err %.2e, loss %.7f vs %.7f" % (suf, err, loss1[0], loss2[0]))
     assert err < tol, err
     assert abs(loss1[0] - loss2[0]) < 1e-5 * max(1.0, abs(loss1[0]))
+
+
+_DP_RESNET_WORKER = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import cases as C
+from oracle import binding
+lib = binding.Oracle("ref", path={shim!r})
+dt = np.float32 if sys.argv[1] == "f32" else np.float64
+x, obj = C.resnet_inputs(dt, total=128, seed=4003)
+n = lib.train_resnet(x, obj, 64, -1, C.RESNET_SMALL)
+p, loss, ms = lib.train_resnet(x, obj, 64, 2, C.RESNET_SMALL, params_in=C.seeded_params(n, dt, 4002))
+np.save(sys.argv[2], p)
+print("LOSS %.9f" % loss)
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_two_process_resnet_with_synchronised_batchnorm_equals_one_process(tmp_path, suf):
+    """Config 4 at test size on 2 GPUs: with the BatchNorm statistics all-reduced (forward sums + count, backward
+    sums) two processes on half-batches must reproduce the single-process run on the full batch -- parameters
+    INCLUDING the running mean / inverse standard deviation -- and both ranks must hold identical parameters."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    shim = os.path.join(ROOT, "tests", "cpp", "_build", "libcattle_b200_shim.so")
+    script = tmp_path / "dp_resnet_worker.py"
+    script.write_text(_DP_RESNET_WORKER.format(root=ROOT, shim=shim))
+
+    def run(world):
+        procs = []
+        for r in range(world):
+            env = dict(os.environ, WORLD_SIZE=str(world), RANK=str(r), LOCAL_RANK=str(r), MASTER_PORT="29543",
+                       CATTL3_COMM_ID_FILE=str(tmp_path / ("rid_%d" % world)))
+            procs.append(subprocess.Popen([sys.executable, str(script), suf, str(tmp_path / ("rp_%d_%d.npy" % (world, r)))],
+                                          env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+        outs = [p.communicate(timeout=600)[0] for p in procs]
+        for p, o in zip(procs, outs):
+            assert p.returncode == 0, o[-3000:]
+        losses = [float(o.split("LOSS")[1].split()[0]) for o in outs]
+        return [np.load(tmp_path / ("rp_%d_%d.npy" % (world, r))) for r in range(world)], losses
+
+    one, loss1 = run(1)
+    two, loss2 = run(2)
+    assert np.array_equal(two[0], two[1]), "ranks diverged"
+    err = C.relerr(two[0], one[0])
+    print("ResNet, 1 vs 2 processes (%s): param err %.2e, loss %.7f vs %.7f" % (suf, err, loss1[0], loss2[0]))
+    assert err < (1e-4 if suf == "f32" else 1e-9), err
+    assert abs(loss1[0] - loss2[0]) < 1e-5 * max(1.0, abs(loss1[0]))
+
+
+_GLOO_BN_WORKER = r"""
+import os, sys
+import numpy as np
+import torch, torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import cases as C
+from oracle import binding
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+orc = binding.Oracle("orc")
+rng = np.random.default_rng(91)
+n, h, w, c = 10, 4, 3, 5
+x = C.rand(rng, (n, h, w, c), np.float64, -1, 3)
+gm, bt, dy = C.rand(rng, (c,), np.float64, 0.5, 1.5), C.rand(rng, (c,), np.float64), C.rand(rng, (n, h, w, c), np.float64)
+full = orc.batchnorm(1, [x], gm, bt, dy)
+lo, hi = (0, 4) if rank == 0 else (4, 10)                 # uneven shards
+xs, dys = x[lo:hi], dy[lo:hi]
+shift = np.linspace(-1, 1, c)                              # any rank-invariant shift (the layer uses its running mean)
+# forward: [sum (x - shift) | sum (x - shift)^2 | count] all-reduced in one message (cattle/layer/BatchNormLayer.hpp)
+d = xs.reshape(-1, c, order="F") - shift
+msg = torch.from_numpy(np.concatenate([d.sum(0), (d * d).sum(0), [d.shape[0]]]))
+dist.all_reduce(msg)
+s1, s2, L = msg[:c].numpy(), msg[c:2 * c].numpy(), float(msg[2 * c])
+mean = shift + s1 / L
+inv_sd = 1.0 / np.sqrt(s2 / L - (s1 / L) ** 2 + 1e-5)
+xhat = (xs - mean) * inv_sd
+y = xhat * gm + bt
+# backward: local sums -> dgamma / dbeta shares; all-reduced sums -> dx with the GLOBAL count
+g = (dys * gm)
+sums = torch.from_numpy(np.concatenate([dys.reshape(-1, c, order="F").sum(0), (dys * xhat).reshape(-1, c, order="F").sum(0)]))
+grads = sums.clone()
+dist.all_reduce(sums)
+dist.all_reduce(grads)                                      # what the optimizer's gradient all-reduce does
+sg, sxg = gm * sums[:c].numpy(), gm * sums[c:].numpy()
+dx = (L * g - sg - xhat * sxg) * inv_sd / L
+err = max(C.relerr(y, full["y"][lo:hi]), C.relerr(dx, full["dx"][lo:hi]), C.relerr(mean, full["run_mean"]),
+          C.relerr(inv_sd, full["run_inv_sd"]), C.relerr(grads[:c].numpy(), full["dbeta"]),
+          C.relerr(grads[c:].numpy(), full["dgamma"]))
+print("RESULT", rank, err)
+assert err < 1e-11, err
+dist.destroy_process_group()
+"""
+
+
+def test_synchronised_batchnorm_contract_gloo(tmp_path):
+    """CPU, world size 2, uneven shards: the message layout and arithmetic of synchronised BatchNorm (shifted sums
+    + element count forward, two sums backward, local dgamma / dbeta shares) reproduce the single-process layer
+    (the oracle on the full batch)."""
+    script = tmp_path / "bn_worker.py"
+    script.write_text(_GLOO_BN_WORKER.format(root=ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29544", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o[-3000:]
+        assert "RESULT" in o

@@ -146,3 +146,52 @@ def test_fused_epilogue_rejects_bad_requests(U):
     with pytest.raises(U.pkg.Cattl3Error):   # statistics without y
         c.conv_forward_fused(cg, xd, wd, bd, None, act_kind=0, act_out=yd,
                              col_stats=torch.zeros(2 * g.f, dtype=torch.float64, device="cuda"))
+
+
+@pytest.mark.parametrize("dt", [np.float32, np.float64])
+@pytest.mark.parametrize("pc", [1, 0])
+def test_batchnorm_split_entries_reproduce_full_batch(U, orc, dt, pc):
+    """The synchronised-statistics protocol on one GPU: two uneven shards of a batch, their shifted sums and counts
+    added (what the all-reduce does), forward from the global sums, backward from the global sums with local
+    dgamma / dbeta shares -- against the oracle's BatchNormLayer on the whole batch."""
+    import torch
+    c = U.ctx()
+    rng = np.random.default_rng(47)
+    n, h, w, ch = 12, 5, 4, 6
+    G = ch if pc else h * w * ch
+    x = C.rand(rng, (n, h, w, ch), dt, -1, 3)
+    gm, bt, dy = C.rand(rng, (G,), dt, 0.5, 1.5), C.rand(rng, (G,), dt), C.rand(rng, (n, h, w, ch), dt)
+    r = orc.batchnorm(pc, [x], gm, bt, dy)
+    shift = U.dev(C.rand(rng, (G,), dt))
+    gmd, btd = U.dev(gm), U.dev(bt)
+    shards = [(0, 5), (5, 12)]
+    xs = [U.dev(np.asfortranarray(x[lo:hi])) for lo, hi in shards]
+    dys = [U.dev(np.asfortranarray(dy[lo:hi])) for lo, hi in shards]
+    stats = [torch.zeros(2 * G, dtype=torch.float64, device="cuda") for _ in shards]
+    for (lo, hi), xd, st in zip(shards, xs, stats):
+        c.batchnorm_stats(pc, hi - lo, h, w, ch, xd, shift, st)
+    total = stats[0] + stats[1]
+    count = torch.tensor([float(n * (h * w if pc else 1))], dtype=torch.float64, device="cuda")
+    dg, db = U.zeros((G,), dt), U.zeros((G,), dt)
+    outs, saved, sums = [], [], []
+    for (lo, hi), xd, dyd in zip(shards, xs, dys):
+        rm, rs, sm, ss = (U.zeros((G,), dt) for _ in range(4))
+        yd = U.zeros((hi - lo, h, w, ch), dt)
+        c.batchnorm_forward_stats(pc, hi - lo, h, w, ch, 0, 0.1, 1e-5, xd, total, shift, gmd, btd, rm, rs, sm, ss, yd,
+                                  global_count=count)
+        s = torch.zeros(2 * G, dtype=torch.float64, device="cuda")
+        c.batchnorm_backward_sums(pc, hi - lo, h, w, ch, xd, sm, ss, dyd, dg, db, s)
+        outs.append(yd); saved.append((rm, rs, sm, ss)); sums.append(s)
+    gsum = sums[0] + sums[1]
+    dxs = []
+    for (lo, hi), xd, dyd, (rm, rs, sm, ss) in zip(shards, xs, dys, saved):
+        dxd = U.zeros((hi - lo, h, w, ch), dt)
+        c.batchnorm_backward_apply(pc, hi - lo, h, w, ch, count, xd, gmd, sm, ss, dyd, gsum, dxd)
+        dxs.append(dxd)
+    c.synchronize()
+    tol = 10 * _tol(dt) if dt == np.float64 else _tol(dt)
+    for (lo, hi), yd, dxd in zip(shards, outs, dxs):
+        assert C.relerr(U.host(yd, (hi - lo, h, w, ch)), r["y"][lo:hi]) < tol
+        assert C.relerr(U.host(dxd, (hi - lo, h, w, ch)), r["dx"][lo:hi]) < tol
+    assert C.relerr(U.host(saved[0][0], (G,)), r["run_mean"]) < tol and C.relerr(U.host(saved[1][1], (G,)), r["run_inv_sd"]) < tol
+    assert C.relerr(U.host(dg, (G,)), r["dgamma"]) < tol and C.relerr(U.host(db, (G,)), r["dbeta"]) < tol
