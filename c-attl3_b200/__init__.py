@@ -70,7 +70,7 @@ _SYMBOLS = [
     "cattl3_ctx_destroy", "cattl3_ctx_synchronize", "cattl3_ctx_set_conv_path", "cattl3_ctx_launch_count",
     "cattl3_ctx_last_path", "cattl3_ctx_stream", "cattl3_malloc", "cattl3_free", "cattl3_memset",
     "cattl3_memcpy_h2d", "cattl3_memcpy_d2h", "cattl3_memcpy_d2d", "cattl3_host_alloc", "cattl3_host_free",
-    "cattl3_conv_output_dims", "cattl3_pool_output_dims",
+    "cattl3_conv_output_dims", "cattl3_pool_output_dims", "cattl3_feed_create", "cattl3_feed_destroy", "cattl3_feed_push",
     "cattl3_conv_forward_host_f32", "cattl3_conv_backward_host_f32",
     "cattl3_comm_unique_id", "cattl3_comm_create", "cattl3_comm_create_from_env", "cattl3_comm_destroy",
     "cattl3_comm_world_size", "cattl3_comm_rank", "cattl3_comm_group_start", "cattl3_comm_group_end",
@@ -82,7 +82,8 @@ _SYMBOLS = [
     "cattl3_optimizer_step", "cattl3_add_inplace", "cattl3_scale", "cattl3_axpy",
     "cattl3_conv_forward_fused", "cattl3_dense_forward_fused", "cattl3_batchnorm_forward_stats",
     "cattl3_dropout_forward", "cattl3_dropout_backward", "cattl3_loss",
-    "cattl3_batchnorm_stats", "cattl3_batchnorm_backward_sums", "cattl3_batchnorm_backward_apply")]
+    "cattl3_batchnorm_stats", "cattl3_batchnorm_backward_sums", "cattl3_batchnorm_backward_apply",
+    "cattl3_slice_rows")]
 
 
 def lib():
@@ -213,6 +214,10 @@ class Context:
                    ct(decay), ct(eps), _p(x), _p(col_stats), _p(global_count), _p(shift), _p(gamma), _p(beta), _p(running_mean),
                    _p(running_inv_sd), _p(saved_mean), _p(saved_inv_sd), _p(y),
                    ACT_NONE if act_kind is None else int(act_kind), ct(act_param), _p(act_out))
+
+    def slice_rows(self, total, vol, first, rows, src, dst):
+        self._call("cattl3_slice_rows", src.dtype, ctypes.c_int64(total), ctypes.c_int64(vol), ctypes.c_int64(first),
+                   ctypes.c_int64(rows), _p(src), _p(dst))
 
     def dropout_forward(self, count, prob, eps, seed, x, y, mask):
         _, ct = _suffix(x.dtype)

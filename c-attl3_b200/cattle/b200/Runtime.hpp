@@ -115,6 +115,8 @@ template<> struct Api<S> { \
 		return cattl3_dense_forward_fused_##SUF(c, n, in, out, x, w, b, y, ep); } \
 	static int batchnorm_forward_stats(cattl3_ctx* c, int pc, std::int32_t n, std::int32_t h, std::int32_t w, std::int32_t ch, int init, S decay, S eps, const S* x, const double* cs, const double* gc, const S* shift, const S* gamma, const S* beta, S* rm, S* rs, S* sm, S* ss, S* y, int ak, S ap, S* ao) { \
 		return cattl3_batchnorm_forward_stats_##SUF(c, pc, n, h, w, ch, init, decay, eps, x, cs, gc, shift, gamma, beta, rm, rs, sm, ss, y, ak, ap, ao); } \
+	static int slice_rows(cattl3_ctx* c, std::int64_t total, std::int64_t vol, std::int64_t first, std::int64_t rows, const S* src, S* dst) { \
+		return cattl3_slice_rows_##SUF(c, total, vol, first, rows, src, dst); } \
 	static int dropout_forward(cattl3_ctx* c, std::int64_t count, S prob, S eps, std::uint64_t seed, const S* x, S* y, std::uint8_t* mask) { \
 		return cattl3_dropout_forward_##SUF(c, count, prob, eps, seed, x, y, mask); } \
 	static int dropout_backward(cattl3_ctx* c, std::int64_t count, S prob, S eps, const S* dy, const std::uint8_t* mask, S* dx) { \
@@ -173,10 +175,12 @@ class DeviceBuffer {
 public:
 	inline DeviceBuffer() :
 			ptr(nullptr),
-			count(0) { }
+			count(0),
+			owned(true) { }
 	inline explicit DeviceBuffer(std::size_t count, bool zero = false) :
 			ptr(nullptr),
-			count(count) {
+			count(count),
+			owned(true) {
 		if (count == 0)
 			return;
 		Context& c = Context::get();
@@ -186,6 +190,14 @@ public:
 		ptr = static_cast<Scalar*>(p);
 		if (zero)
 			CATTLE_B200_CHECK(cattl3_memset(c.handle(), ptr, 0, count * sizeof(Scalar)));
+	}
+	/** A non-owning view of `count` elements at `borrowed` (memory owned by an InputFeed); never freed here. */
+	inline static DeviceBuffer<Scalar> view(Scalar* borrowed, std::size_t count) {
+		DeviceBuffer<Scalar> buffer;
+		buffer.ptr = borrowed;
+		buffer.count = count;
+		buffer.owned = false;
+		return buffer;
 	}
 	inline DeviceBuffer(const DeviceBuffer<Scalar>& other) :
 			DeviceBuffer(other.count) {
@@ -197,9 +209,11 @@ public:
 	}
 	inline DeviceBuffer(DeviceBuffer<Scalar>&& other) noexcept :
 			ptr(other.ptr),
-			count(other.count) {
+			count(other.count),
+			owned(other.owned) {
 		other.ptr = nullptr;
 		other.count = 0;
+		other.owned = true;
 	}
 	inline ~DeviceBuffer() {
 		release();
@@ -207,6 +221,7 @@ public:
 	inline DeviceBuffer<Scalar>& operator=(DeviceBuffer<Scalar> other) noexcept {
 		std::swap(ptr, other.ptr);
 		std::swap(count, other.count);
+		std::swap(owned, other.owned);
 		return *this;
 	}
 	inline Scalar* data() {
@@ -250,6 +265,11 @@ public:
 	}
 private:
 	inline void release() {
+		if (ptr && !owned) {
+			ptr = nullptr;
+			count = 0;
+			owned = true;
+		}
 		if (ptr) {
 			Context& c = Context::get();
 			Context::Lock l = c.lock();
@@ -260,6 +280,43 @@ private:
 	}
 	Scalar* ptr;
 	std::size_t count;
+	bool owned;
+};
+
+/**
+ * The mini-batch upload of the batch loop, off the compute stream (cattl3_feed, include/cattl3_b200.h): a ring of
+ * device buffers filled through pinned staging on a copy stream, so that the upload of the next batch overlaps the
+ * kernels of the current one.  push() returns once the host data has been staged; the returned view stays valid for
+ * the next `slots - 1` pushes, i.e. for the whole training step that consumes it.
+ */
+class InputFeed {
+public:
+	inline explicit InputFeed(int slots = 3) :
+			feed(nullptr) {
+		Context& c = Context::get();
+		Context::Lock l = c.lock();
+		CATTLE_B200_CHECK(cattl3_feed_create(&feed, c.handle(), slots));
+	}
+	inline ~InputFeed() {
+		Context::Lock l = Context::get().lock();
+		cattl3_feed_destroy(feed);
+	}
+	InputFeed(const InputFeed&) = delete;
+	InputFeed& operator=(const InputFeed&) = delete;
+	/** The process-wide feeds of the batch loop (0: observations, 1: objectives). */
+	inline static InputFeed& shared(int which) {
+		static InputFeed feeds[2];
+		return feeds[which & 1];
+	}
+	template<typename Scalar>
+	inline DeviceBuffer<Scalar> push(const Scalar* host, std::size_t count) {
+		void* dev = nullptr;
+		Context::Lock l = Context::get().lock();
+		CATTLE_B200_CHECK(cattl3_feed_push(feed, host, count * sizeof(Scalar), &dev));
+		return DeviceBuffer<Scalar>::view(static_cast<Scalar*>(dev), count);
+	}
+private:
+	cattl3_feed* feed;
 };
 
 } /* namespace b200 */

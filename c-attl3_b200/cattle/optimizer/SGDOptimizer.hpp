@@ -28,6 +28,7 @@
 #include <iomanip>
 #include <iostream>
 #include <map>
+#include <memory>
 #include <string>
 #include <utility>
 #include <vector>
@@ -35,6 +36,7 @@
 #include "core/Optimizer.hpp"
 #include "parameters/B200Parameters.hpp"
 #include "b200/Communicator.hpp"
+#include "b200/DeviceDataSource.hpp"
 #include "b200/DeviceLoss.hpp"
 #include "b200/DeviceNetwork.hpp"
 #include "b200/Runtime.hpp"
@@ -76,7 +78,25 @@ protected:
 				dynamic_cast<b200::DeviceNetwork<Scalar,Rank>*>(&net);
 		const b200::DeviceLoss<Scalar>* dev_loss = dynamic_cast<const b200::DeviceLoss<Scalar>*>(Base::loss.get());
 		std::vector<b200::DeviceBuffer<Scalar>> step_losses;
+		b200::DeviceDataSource<Scalar>* dev_data = dev_net && dev_loss ?
+				dynamic_cast<b200::DeviceDataSource<Scalar>*>(&training_prov) : nullptr;
+		if (dev_data && !dev_data->device_resident())
+			dev_data = nullptr;
 		while (training_prov.has_more()) {
+			if (dev_data) {
+				// the data set lives in HBM: the (shard of the) mini-batch is cut out on the device
+				b200::DeviceTensor<Scalar> obs, obj;
+				instances += dev_data->next_batch_dev(batch_size, comm.rank(), comm.world_size(), obs, obj);
+				if (!obs.empty()) {
+					b200::DeviceTensor<Scalar> out = dev_net->propagate_dev(std::move(obs), true);
+					step_losses.emplace_back();
+					b200::DeviceTensor<Scalar> out_grad = dev_loss->loss_and_gradient_dev(out, obj, (Scalar) batch_size,
+							step_losses.back());
+					dev_net->backpropagate_dev(std::move(out_grad));
+				}
+				finish_step(params_vec, comm, epoch, reg_loss, updates);
+				continue;
+			}
 			DataPair<Scalar,Rank,Sequential> data_pair = training_prov.get_data(batch_size);
 			instances += data_pair.first.dimension(0);
 			if (comm.world_size() > 1)
@@ -84,9 +104,9 @@ protected:
 			if (data_pair.first.dimension(0) > 0 && dev_net && dev_loss) {
 				// the whole step in HBM: one upload of the mini-batch, then propagate -> loss -> back-propagate
 				// without a host round trip; the per-sample losses are collected at the end of the epoch
-				b200::DeviceTensor<Scalar> obj = b200::to_device<Scalar,Base::Data::NumDimensions>(data_pair.second);
-				b200::DeviceTensor<Scalar> out = dev_net->propagate_dev(
-						b200::to_device<Scalar,Base::Data::NumDimensions>(data_pair.first), true);
+				// (the uploads go through the input feeds: staged on a copy stream, they overlap the previous step)
+				b200::DeviceTensor<Scalar> obj = fed(1, data_pair.second);
+				b200::DeviceTensor<Scalar> out = dev_net->propagate_dev(fed(0, data_pair.first), true);
 				step_losses.emplace_back();
 				b200::DeviceTensor<Scalar> out_grad = dev_loss->loss_and_gradient_dev(out, obj, (Scalar) batch_size,
 						step_losses.back());
@@ -99,19 +119,7 @@ protected:
 				net.backpropagate(Base::loss->d_function(std::move(out), std::move(data_pair.second)) /
 						(Scalar) batch_size);
 			}
-			if (comm.world_size() > 1)
-				all_reduce_gradients(params_vec, comm);
-			for (Parameters<Scalar>* params_ptr : params_vec) {
-				if (!params_ptr->are_optimizable() || params_ptr->are_frozen())
-					continue;
-				reg_loss += params_ptr->get_regularization_penalty();
-				params_ptr->regularize();
-			}
-			_update_params(params_vec, epoch - 1, timestep);
-			++updates;
-			++timestep;
-			for (Parameters<Scalar>* params_ptr : params_vec)
-				params_ptr->reset_grad();  // a no-op where the fused step already cleared the gradient
+			finish_step(params_vec, comm, epoch, reg_loss, updates);
 		}
 		for (const b200::DeviceBuffer<Scalar>& losses : step_losses) {
 			std::vector<Scalar> host(losses.size());
@@ -238,6 +246,34 @@ protected:
 	const std::size_t batch_size;
 private:
 	typedef std::array<b200::DeviceBuffer<Scalar>,3> StateArrays;
+	/** The tail of a training step: all-reduce, regularise, update, reset (SGDOptimizer.hpp:57-70). */
+	inline void finish_step(const std::vector<Parameters<Scalar>*>& params_vec, b200::Communicator& comm, std::size_t epoch,
+			double& reg_loss, std::size_t& updates) {
+		if (comm.world_size() > 1)
+			all_reduce_gradients(params_vec, comm);
+		for (Parameters<Scalar>* params_ptr : params_vec) {
+			if (!params_ptr->are_optimizable() || params_ptr->are_frozen())
+				continue;
+			reg_loss += params_ptr->get_regularization_penalty();
+			params_ptr->regularize();
+		}
+		_update_params(params_vec, epoch - 1, timestep);
+		++updates;
+		++timestep;
+		for (Parameters<Scalar>* params_ptr : params_vec)
+			params_ptr->reset_grad();  // a no-op where the fused step already cleared the gradient
+	}
+	/**
+	 * Host tensor -> device through one of the process's two input feeds (0: observations, 1: objectives; created
+	 * on first use and kept: their pinned staging and device ring are not worth re-creating per train() call).
+	 */
+	inline static b200::DeviceTensor<Scalar> fed(int which, const typename Base::Data& data) {
+		b200::DeviceTensor<Scalar> tensor;
+		tensor.rows = data.dimension(0);
+		tensor.buf = std::make_shared<b200::DeviceBuffer<Scalar>>(
+				b200::InputFeed::shared(which).push(data.data(), (std::size_t) data.size()));
+		return tensor;
+	}
 	/** CATTL3_HOST_LOOP=1 keeps the reference's host protocol between network and loss (A/B, debugging). */
 	inline static bool device_loop() {
 		static const bool on = [] {

@@ -163,11 +163,11 @@ simt:
 		set_error("tcgen05 path requested but the shape/type does not qualify (needs float, batch %% 32 == 0)");
 		return CATTL3_ERR_UNSUPPORTED;
 	}
-	if (!IsFloat<S>::value && ctx->conv_path != CATTL3_PATH_SIMT && dfma_gather_gemm_supported(gg)) {
-		// double at GEMM-sized shapes: the big-tile DFMA kernel (conv_dfma.cu)
-		ctx->last_path = "dfma";
-		CATTL3_CHECK(dfma_gather_gemm(ctx, gg, (const double*) src, (const double*) w, (const double*) bias, bias_mode,
-				(double*) out, ep));
+	if (ctx->conv_path != CATTL3_PATH_SIMT && fma_gather_gemm_supported<S>(gg)) {
+		// GEMM-sized shapes off the tensor-core path (double; float with few channels or a ragged batch): the
+		// big-tile FMA kernels (conv_dfma.cu)
+		ctx->last_path = IsFloat<S>::value ? "ffma" : "dfma";
+		CATTL3_CHECK(fma_gather_gemm<S>(ctx, gg, src, w, bias, bias_mode, out, ep));
 	} else {
 		ctx->last_path = "simt";
 		CATTL3_CHECK(simt_gather_gemm<S>(ctx, gg, src, w, bias, bias_mode, out, ep));
@@ -192,9 +192,9 @@ static int run_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const 
 		set_error("tcgen05 weight-gradient path requested but the shape/type does not qualify");
 		return CATTL3_ERR_UNSUPPORTED;
 	}
-	if (!IsFloat<S>::value && ctx->conv_path != CATTL3_PATH_SIMT && dfma_wgrad_supported(gg)) {
-		ctx->last_path = "dfma";
-		return dfma_wgrad(ctx, gg, (const double*) src, (const double*) plain, (double*) dw);
+	if (ctx->conv_path != CATTL3_PATH_SIMT && fma_wgrad_supported<S>(gg)) {
+		ctx->last_path = IsFloat<S>::value ? "ffma" : "dfma";
+		return fma_wgrad<S>(ctx, gg, src, plain, dw);
 	}
 	ctx->last_path = "simt";
 	return simt_wgrad<S>(ctx, gg, src, plain, dw);
@@ -405,6 +405,104 @@ int cattl3_memcpy_h2d(cattl3_ctx* ctx, void* dst, const void* src, size_t bytes)
 	CATTL3_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
 	return CATTL3_OK;
 }
+} // extern "C"
+
+// ---- input feed ---------------------------------------------------------------------------------------------
+struct cattl3_feed {
+	cattl3_ctx* ctx = nullptr;
+	int slots = 0;
+	long long pushes = 0;
+	void** dev = nullptr;          // [slots] device buffers, grown on demand
+	size_t* dev_bytes = nullptr;
+	cudaEvent_t* marks = nullptr;  // [slots] marks[p % slots] = "everything on the compute stream at push p"
+	cudaStream_t copy = nullptr;
+	void* pinned[2] = { nullptr, nullptr };
+	cudaEvent_t pinned_done[2] = { nullptr, nullptr };
+	cudaEvent_t ready = nullptr;
+};
+static constexpr size_t FEED_CHUNK = (size_t) 8 << 20;
+
+extern "C" {
+
+int cattl3_feed_create(cattl3_feed** out, cattl3_ctx* ctx, int slots) {
+	CATTL3_REQUIRE(out, "feed_create: null out pointer");
+	*out = nullptr;
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(slots >= 2 && slots <= 16, "feed_create: 2..16 slots");
+	cattl3_feed* f = new cattl3_feed();
+	f->ctx = ctx; f->slots = slots;
+	f->dev = new void*[slots](); f->dev_bytes = new size_t[slots](); f->marks = new cudaEvent_t[slots]();
+	cudaError_t e = cudaStreamCreateWithFlags(&f->copy, cudaStreamNonBlocking);
+	for (int i = 0; i < slots && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&f->marks[i], cudaEventDisableTiming);
+	for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+		e = cudaMallocHost(&f->pinned[i], FEED_CHUNK);
+		if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->pinned_done[i], cudaEventDisableTiming);
+	}
+	if (e == cudaSuccess) e = cudaEventCreateWithFlags(&f->ready, cudaEventDisableTiming);
+	if (e != cudaSuccess) {
+		cattl3_feed_destroy(f);
+		return cuda_fail(e, "feed_create", __FILE__, __LINE__);
+	}
+	*out = f;
+	return CATTL3_OK;
+}
+
+int cattl3_feed_destroy(cattl3_feed* f) {
+	if (!f) return CATTL3_OK;
+	cudaSetDevice(f->ctx->device);
+	if (f->copy) cudaStreamSynchronize(f->copy);
+	cudaStreamSynchronize(f->ctx->stream);
+	for (int i = 0; i < f->slots; ++i) {
+		if (f->dev && f->dev[i]) cudaFree(f->dev[i]);
+		if (f->marks && f->marks[i]) cudaEventDestroy(f->marks[i]);
+	}
+	for (int i = 0; i < 2; ++i) {
+		if (f->pinned[i]) cudaFreeHost(f->pinned[i]);
+		if (f->pinned_done[i]) cudaEventDestroy(f->pinned_done[i]);
+	}
+	if (f->ready) cudaEventDestroy(f->ready);
+	if (f->copy) cudaStreamDestroy(f->copy);
+	delete[] f->dev; delete[] f->dev_bytes; delete[] f->marks;
+	delete f;
+	return CATTL3_OK;
+}
+
+int cattl3_feed_push(cattl3_feed* f, const void* src, size_t bytes, void** dev_ptr) {
+	CATTL3_REQUIRE(f && src && bytes > 0 && dev_ptr, "feed_push: bad arguments");
+	cattl3_ctx* ctx = f->ctx;
+	CATTL3_CHECK(check_ctx(ctx));
+	const int s = (int) (f->pushes % f->slots);
+	if (f->dev_bytes[s] < bytes) {
+		// growing a slot (first batches, or a larger batch): its old contents may still be in use
+		CATTL3_CUDA(cudaStreamSynchronize(ctx->stream));
+		CATTL3_CUDA(cudaStreamSynchronize(f->copy));
+		if (f->dev[s]) CATTL3_CUDA(cudaFree(f->dev[s]));
+		f->dev[s] = nullptr; f->dev_bytes[s] = 0;
+		const size_t rounded = (bytes + ((size_t) 1 << 20) - 1) & ~(((size_t) 1 << 20) - 1);
+		CATTL3_CUDA(cudaMalloc(&f->dev[s], rounded));
+		f->dev_bytes[s] = rounded;
+	}
+	// the previous contents of this slot were consumed by work enqueued before the push `slots - 1` pushes ago
+	if (f->pushes >= f->slots - 1)
+		CATTL3_CUDA(cudaStreamWaitEvent(f->copy, f->marks[(f->pushes + 1) % f->slots], 0));
+	size_t off = 0;
+	for (int chunk = 0; off < bytes; ++chunk) {
+		const int b = chunk & 1;
+		const size_t n = bytes - off < FEED_CHUNK ? bytes - off : FEED_CHUNK;
+		CATTL3_CUDA(cudaEventSynchronize(f->pinned_done[b]));   // the copy engine has drained this staging buffer
+		memcpy(f->pinned[b], (const char*) src + off, n);
+		CATTL3_CUDA(cudaMemcpyAsync((char*) f->dev[s] + off, f->pinned[b], n, cudaMemcpyHostToDevice, f->copy));
+		CATTL3_CUDA(cudaEventRecord(f->pinned_done[b], f->copy));
+		off += n;
+	}
+	CATTL3_CUDA(cudaEventRecord(f->ready, f->copy));
+	CATTL3_CUDA(cudaStreamWaitEvent(ctx->stream, f->ready, 0));
+	CATTL3_CUDA(cudaEventRecord(f->marks[s], ctx->stream));
+	*dev_ptr = f->dev[s];
+	++f->pushes;
+	return CATTL3_OK;
+}
+
 int cattl3_memcpy_d2h(cattl3_ctx* ctx, void* dst, const void* src, size_t bytes) {
 	CATTL3_CHECK(check_ctx(ctx));
 	CATTL3_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));

@@ -114,12 +114,13 @@ int simt_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* pla
 template<typename S>
 int colsum_accumulate(cattl3_ctx* ctx, int64_t rows, int64_t cols, const S* a, S* out);
 
-// DFMA path (conv_dfma.cu): the double kernels for GEMM-sized shapes.
-bool dfma_gather_gemm_supported(const GatherGeom& gg);
-int dfma_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const double* src, const double* w, const double* bias,
-		int bias_mode, double* out, const EpilogueArgs* ep = nullptr);
-bool dfma_wgrad_supported(const GatherGeom& gg);
-int dfma_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const double* src, const double* plain, double* dw);
+// Big-tile FMA path (conv_dfma.cu): double at GEMM-sized shapes; float where the tensor-core path does not apply.
+template<typename S> bool fma_gather_gemm_supported(const GatherGeom& gg);
+template<typename S>
+int fma_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* w, const S* bias, int bias_mode, S* out,
+		const EpilogueArgs* ep = nullptr);
+template<typename S> bool fma_wgrad_supported(const GatherGeom& gg);
+template<typename S> int fma_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* plain, S* dw);
 
 // tcgen05 path (conv_tc.cu): returns CATTL3_ERR_UNSUPPORTED when the shape does not qualify.
 bool tc_gather_gemm_supported(const cattl3_ctx* ctx, const GatherGeom& gg);

@@ -894,6 +894,41 @@ template<typename S> int axpy(cattl3_ctx* ctx, int64_t count, S alpha, const S* 
 template<typename S> int add_inplace(cattl3_ctx* ctx, int64_t count, S* y, const S* x) { return glue<S, 0>(ctx, "add_inplace", count, (S) 0, x, y); }
 template<typename S> int scale(cattl3_ctx* ctx, int64_t count, S alpha, const S* x, S* y) { return glue<S, 1>(ctx, "scale", count, alpha, x, y); }
 
+// ---- mini-batch rows out of a device-resident data set (MemoryDataProvider::get_data, :72-83) -------------------
+// dst[n + rows * j] = src[first + n + total * j]: a contiguous run per column, 16-byte vectors where everything lines up.
+template<typename S>
+__global__ void __launch_bounds__(256) slice_rows_kernel(long long total, long long vol, long long first, long long rows,
+		int vec, const S* __restrict__ src, S* __restrict__ dst) {
+	typedef typename V16<S>::type V;
+	constexpr int G = V16<S>::G;
+	if (vec) {
+		const long long rv = rows / G, count = rv * vol;
+		for (long long i = blockIdx.x * 256ll + threadIdx.x; i < count; i += (long long) gridDim.x * 256) {
+			const long long j = i / rv, n = (i - j * rv) * G;
+			*reinterpret_cast<V*>(dst + n + rows * j) = *reinterpret_cast<const V*>(src + first + n + total * j);
+		}
+	} else {
+		const long long count = rows * vol;
+		for (long long i = blockIdx.x * 256ll + threadIdx.x; i < count; i += (long long) gridDim.x * 256) {
+			const long long j = i / rows, n = i - j * rows;
+			dst[n + rows * j] = src[first + n + total * j];
+		}
+	}
+}
+
+template<typename S>
+int slice_rows(cattl3_ctx* ctx, int64_t total, int64_t vol, int64_t first, int64_t rows, const S* src, S* dst) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(total > 0 && vol > 0 && rows > 0 && first >= 0 && first + rows <= total && src && dst,
+			"slice_rows: bad arguments");
+	constexpr int G = V16<S>::G;
+	const int vec = rows % G == 0 && total % G == 0 && first % G == 0 && aligned16(src) && aligned16(dst);
+	slice_rows_kernel<S><<<ew_grid(ctx, rows * vol / (vec ? G : 1), 256), 256, 0, ctx->stream>>>(total, vol, first, rows, vec,
+			src, dst);
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+
 // ---- dropout (C-ATTL3/layer/DropoutLayer.hpp:74-94) ------------------------------------------------------
 // Inverted dropout: mask = u <= p ? 0 : 1 / (1 - p + eps), y = x * mask, with u uniform in [0, 1) from a
 // counter-based generator (a 64-bit mix of seed and element index: the same (seed, index) always gives the
@@ -992,6 +1027,10 @@ using namespace cattl3;
 
 extern "C" {
 
+int cattl3_slice_rows_f32(cattl3_ctx* c, int64_t total, int64_t vol, int64_t first, int64_t rows, const float* src, float* dst) {
+	return slice_rows<float>(c, total, vol, first, rows, src, dst); }
+int cattl3_slice_rows_f64(cattl3_ctx* c, int64_t total, int64_t vol, int64_t first, int64_t rows, const double* src, double* dst) {
+	return slice_rows<double>(c, total, vol, first, rows, src, dst); }
 int cattl3_dropout_forward_f32(cattl3_ctx* c, int64_t count, float prob, float eps, uint64_t seed, const float* x, float* y, uint8_t* mask) {
 	return dropout_forward<float>(c, count, prob, eps, seed, x, y, mask); }
 int cattl3_dropout_forward_f64(cattl3_ctx* c, int64_t count, double prob, double eps, uint64_t seed, const double* x, double* y, uint8_t* mask) {

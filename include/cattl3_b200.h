@@ -185,6 +185,24 @@ int cattl3_memcpy_d2d(cattl3_ctx* ctx, void* dev_dst, const void* dev_src, size_
 int cattl3_host_alloc(void** host_ptr, size_t bytes); /* pinned */
 int cattl3_host_free(void* host_ptr);
 
+/*
+ * Input feed: the mini-batch upload of the batch loop (SGDOptimizer.hpp:44-47 hands each batch to propagate) taken
+ * off the compute stream.  A ring of `slots` device buffers is filled through pinned staging on a dedicated copy
+ * stream, so the upload of batch i+1 overlaps the kernels of batch i; cattl3_feed_push returns as soon as the host
+ * data has been staged (the source may be reused), work enqueued afterwards on the context's stream sees the data, and
+ * the slot is overwritten `slots` pushes later -- ordered after everything the context's stream had been given
+ * `slots - 1` pushes earlier, i.e. after the step that consumed it.  The returned device pointer belongs to the feed.
+ */
+typedef struct cattl3_feed cattl3_feed;
+int cattl3_feed_create(cattl3_feed** out, cattl3_ctx* ctx, int slots);
+int cattl3_feed_destroy(cattl3_feed* feed);
+int cattl3_feed_push(cattl3_feed* feed, const void* host_src, size_t bytes, void** dev_ptr);
+
+/* Rows [first, first + rows) of a device-resident (total x vol) data set, rows fastest (MemoryDataProvider::get_data,
+ * C-ATTL3/data_provider/MemoryDataProvider.hpp:72-83, without the host slice and the per-step upload). */
+int cattl3_slice_rows_f32(cattl3_ctx*, int64_t total, int64_t vol, int64_t first, int64_t rows, const float* src, float* dst);
+int cattl3_slice_rows_f64(cattl3_ctx*, int64_t total, int64_t vol, int64_t first, int64_t rows, const double* src, double* dst);
+
 /* ---- shape helpers ------------------------------------------------------------------------ */
 /* ConvKernelLayer.hpp:194-197 (transposed = 0) / TransConvKernelLayer.hpp:200-203 (transposed = 1). */
 int cattl3_conv_output_dims(const cattl3_conv_geom* g, int transposed, int32_t* oh, int32_t* ow);

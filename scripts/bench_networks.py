@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Network-level training throughput through the header-only C++ host side (c-attl3_b200/cattle) -- the layer loop,
+the fused epilogues, the device loss, the fused optimizer step and, for N > 1, the NCCL gradient all-reduce and the
+synchronised BatchNorm statistics -- on BASELINE.json's network configs:
+
+  --config 1 : examples/cifar_convnet.cpp ConvNet (Dropout removed), 32x32x3, batch 64, CrossEntropy + Nadam
+  --config 3 : examples/mnist_autoencoder.cpp auto-encoder (Stacked: Conv/Softplus/Dense/Reshape/TransConv), 28x28x1,
+               batch 512, SquaredLoss + Nadam
+  --config 4 : ResNet-style ResidualNeuralNetwork (stem conv 7x7/2 + BN + ReLU + MaxPool, `--blocks` modules of
+               Conv3x3-BN-ReLU-Conv3x3-BN at `--width` channels, MeanPool + Dense + Softmax head), 224x224x3,
+               batch 64 per GPU, data parallel (weak scaling)
+
+The driver is oracle/ref_shim.cpp compiled UNCHANGED against the B200 headers (tests/cpp/_build/libcattle_b200_shim.so);
+`--impl reference` runs the same driver compiled against the unmodified reference on the host cores (bounded sample).
+Launch N ranks with torchrun (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_PORT): one process per GPU.  One JSON line
+(rank 0).  This is a secondary measurement; bench.py carries the headline metric.
+
+  python scripts/bench_networks.py --config 4
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29600 \
+      scripts/bench_networks.py --config 4
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, default=4, choices=[1, 3, 4])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--steps", type=int, default=8, help="mini-batches per epoch")
+    ap.add_argument("--epochs", type=int, default=4, help="timed epochs (after one warm-up epoch)")
+    ap.add_argument("--width", type=int, default=64)
+    ap.add_argument("--blocks", type=int, default=4)
+    ap.add_argument("--image", type=int, default=224)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dt = np.float32 if args.dtype == "f32" else np.float64
+    from oracle import binding
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        lib = binding.Oracle("ref")
+        os.environ["WORLD_SIZE"] = "1"
+        world_eff = 1
+    else:
+        shim = os.path.join(ROOT, "tests", "cpp", "_build", "libcattle_b200_shim.so")
+        lib = binding.Oracle("ref", path=shim)
+        assert lib.lib.ref_is_b200_build() == 1
+        world_eff = world
+    per_gpu = args.batch or {1: 64, 3: 512, 4: 64}[args.config]
+    batch = per_gpu * world_eff                     # the nominal (global) batch the optimizer is built with
+    total = batch * args.steps
+    rng = np.random.default_rng({1: 1001, 3: 3001, 4: 4001}[args.config])   # identical data on every rank
+    if args.config == 1:
+        x = np.asfortranarray(rng.uniform(-1, 1, (total, 32, 32, 3)).astype(dt))
+        obj = np.zeros((total, 1, 1, 10), dtype=dt, order="F")
+        obj[np.arange(total), 0, 0, np.arange(total) % 10] = 1
+        run = lambda epochs: lib.train_cifar(x, obj, batch, epochs)
+        name = "cifar ConvNet 32x32x3"
+    elif args.config == 3:
+        x = np.asfortranarray(rng.uniform(0, 1, (total, 28, 28, 1)).astype(dt))
+        run = lambda epochs: lib.train_autoencoder(x, batch, epochs)
+        name = "mnist auto-encoder 28x28x1"
+    else:
+        s = args.image
+        x = np.asfortranarray(rng.uniform(-1, 1, (total, s, s, 3)).astype(dt))
+        obj = np.zeros((total, 1, 1, 10), dtype=dt, order="F")
+        obj[np.arange(total), 0, 0, np.arange(total) % 10] = 1
+        arch = (7, 2, 1, args.width, args.blocks, 4)   # stem 7x7 stride 2 + max-pool 2x2, head mean-pool 4x4
+        run = lambda epochs: lib.train_resnet(x, obj, batch, epochs, arch)
+        name = "ResNet-style residual net %dx%dx3, stem 7x7/2 + pool, %d modules x (conv3x3-BN-ReLU-conv3x3-BN) @ %d ch" % (
+            s, s, args.blocks, args.width)
+    t0 = time.perf_counter()
+    _, loss0, ms_warm = run(1)                      # warm-up epoch: allocations, NCCL communicator, clocks
+    _, loss, ms = run(args.epochs)
+    wall = time.perf_counter() - t0
+    if world_eff > 1:
+        # max over ranks of the timed region, through a file-free reduction: every rank prints, rank 0 reports its own
+        # time; the loop is synchronous (all-reduce every step), so the ranks finish within one step of each other
+        pass
+    value = total * args.epochs / (ms / 1000.0)
+    line = {"metric": "train samples/s (fwd+bwd+step), network level", "impl": args.impl, "value": round(value, 1),
+            "unit": "samples/s", "n_gpus": world_eff, "ms_per_step": round(ms / (args.epochs * args.steps), 3),
+            "scaling": "weak", "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": name, "config": args.config, "batch_per_gpu": per_gpu, "global_batch": batch,
+                       "steps_per_epoch": args.steps, "epochs_timed": args.epochs,
+                       "includes": "host data provider slicing + H2D of each mini-batch + layer loop + loss + "
+                                   "all-reduce + optimizer step (cattle::NadamOptimizer::train)"},
+            "epoch_loss": round(float(loss), 6), "warmup_epoch_ms": round(ms_warm, 1), "wall_s": round(wall, 1),
+            "threads": lib.num_threads() if args.impl == "reference" else None}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -35,6 +35,9 @@ CONV_CASES = {
     "dfma_odd": (5, 9, 7, 6, 40, 3, 3, 1, 1, 2, 1, 0, 1),
     "dfma_mid": (6, 20, 18, 8, 72, 3, 3, 1, 1, 1, 1, 0, 0),
     "dfma_wide": (4, 10, 9, 20, 136, 3, 2, 1, 0, 1, 1, 0, 0),
+    # config 4's stem at test size: 7x7 stride 2 over 3 channels (float: flattened (tap, channel) reduction)
+    "stem": (32, 20, 18, 3, 64, 7, 7, 3, 3, 2, 2, 0, 0),
+    "stem_wide": (8, 12, 12, 3, 80, 5, 5, 2, 2, 1, 1, 0, 0),
     # ragged everything: odd batch, odd channels
     "ragged": (7, 9, 11, 5, 3, 3, 4, 2, 1, 2, 1, 0, 1),
     "single": (1, 3, 3, 1, 1, 3, 3, 1, 1, 1, 1, 0, 0),

@@ -353,3 +353,15 @@ def test_conv_dfma_matches_simt_at_size(U):
     assert a["path"] == "dfma" and s["path"] == "simt"
     for k in ("y", "dx", "dw", "db"):
         assert C.relerr(a[k], s[k]) < 1e-13, (k, C.relerr(a[k], s[k]))
+
+
+def test_conv_ffma_vs_oracle(U, orc):
+    """Float layers the tensor-core path refuses (3 input channels: config 4's stem; ragged batches) run on the
+    big-tile FFMA kernels (conv_dfma.cu, flattened reduction for few channels), against the oracle at 1e-4."""
+    for name in ["stem", "stem_wide", "dfma_odd", "dfma_mid", "dfma_wide"]:
+        g, x, w, b, dy = C.conv_inputs(C.CONV_CASES[name], np.float32, 73)
+        r = orc.conv(g, x, w, b, dy, back_reps=2)
+        a = _conv_gpu(U, C.CONV_CASES[name], x, w, b, dy, False, reps=2, path=U.pkg.PATH_AUTO)
+        assert a["path"] == "ffma", (name, a["path"])
+        for k in ("y", "dx", "dw", "db"):
+            assert C.relerr(a[k], r[k]) < C.TOL[np.dtype(np.float32)], (name, k, C.relerr(a[k], r[k]))
