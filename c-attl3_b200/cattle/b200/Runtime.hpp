@@ -115,6 +115,8 @@ template<> struct Api<S> { \
 		return cattl3_dense_forward_fused_##SUF(c, n, in, out, x, w, b, y, ep); } \
 	static int batchnorm_forward_stats(cattl3_ctx* c, int pc, std::int32_t n, std::int32_t h, std::int32_t w, std::int32_t ch, int init, S decay, S eps, const S* x, const double* cs, const double* gc, const S* shift, const S* gamma, const S* beta, S* rm, S* rs, S* sm, S* ss, S* y, int ak, S ap, S* ao) { \
 		return cattl3_batchnorm_forward_stats_##SUF(c, pc, n, h, w, ch, init, decay, eps, x, cs, gc, shift, gamma, beta, rm, rs, sm, ss, y, ak, ap, ao); } \
+	static int fill(cattl3_ctx* c, std::int64_t count, S value, S* y) { \
+		return cattl3_fill_##SUF(c, count, value, y); } \
 	static int slice_rows(cattl3_ctx* c, std::int64_t total, std::int64_t vol, std::int64_t first, std::int64_t rows, const S* src, S* dst) { \
 		return cattl3_slice_rows_##SUF(c, total, vol, first, rows, src, dst); } \
 	static int dropout_forward(cattl3_ctx* c, std::int64_t count, S prob, S eps, std::uint64_t seed, const S* x, S* y, std::uint8_t* mask) { \

@@ -254,12 +254,16 @@ public:
 		const double* count_ptr = nullptr;
 		if (synchronised()) {
 			// [sums | element count] summed over the ranks in one message; the count stays on the device
+			// (written by a kernel: a host -> device copy from pageable memory would synchronise with the stream)
 			const double local_count = (double) in.rows * (double) geom_h();
-			ep.col_stats->upload(&local_count, 1, 2 * groups);
+			b200::Context& c = b200::Context::get();
+			{
+				b200::Context::Lock l = c.lock();
+				CATTLE_B200_CHECK(b200::Api<double>::fill(c.handle(), 1, local_count, ep.col_stats->data() + 2 * groups));
+			}
 			b200::Communicator::get().all_reduce_sum(ep.col_stats->data(), 2 * groups + 1);
 			global_count = b200::DeviceBuffer<double>(1);
 			{
-				b200::Context& c = b200::Context::get();
 				b200::Context::Lock l = c.lock();
 				CATTLE_B200_CHECK(cattl3_memcpy_d2d(c.handle(), global_count.data(), ep.col_stats->data() + 2 * groups,
 						sizeof(double)));

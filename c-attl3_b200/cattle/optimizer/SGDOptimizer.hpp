@@ -262,6 +262,11 @@ private:
 		++timestep;
 		for (Parameters<Scalar>* params_ptr : params_vec)
 			params_ptr->reset_grad();  // a no-op where the fused step already cleared the gradient
+		// the loop is asynchronous: keep the host at most two steps ahead of the device (bounded queues and
+		// scratch, ranks of a data-parallel job stay within a step of each other)
+		b200::Context& c = b200::Context::get();
+		b200::Context::Lock l = c.lock();
+		CATTLE_B200_CHECK(cattl3_ctx_throttle(c.handle(), 2));
 	}
 	/**
 	 * Host tensor -> device through one of the process's two input feeds (0: observations, 1: objectives; created

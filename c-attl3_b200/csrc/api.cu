@@ -358,10 +358,27 @@ int cattl3_ctx_destroy(cattl3_ctx* ctx) {
 	if (ctx->ws) cudaFree(ctx->ws);
 	if (ctx->tc_w) cudaFree(ctx->tc_w);
 	if (ctx->stat_ws) cudaFree(ctx->stat_ws);
+	for (int i = 0; i < 8; ++i)
+		if (ctx->throttle_ev[i]) cudaEventDestroy(ctx->throttle_ev[i]);
 	for (int i = 0; i < 3; ++i)
 		if (ctx->stage_dev[i]) cudaFree(ctx->stage_dev[i]);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
+	return CATTL3_OK;
+}
+
+int cattl3_ctx_throttle(cattl3_ctx* ctx, int max_in_flight) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(max_in_flight >= 1 && max_in_flight <= 7, "ctx_throttle: 1..7 steps in flight");
+	const int ring = 8;
+	const long long p = ctx->throttle_calls++;
+	cudaEvent_t& ev = ctx->throttle_ev[p % ring];
+	if (!ev) CATTL3_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming | cudaEventBlockingSync));
+	CATTL3_CUDA(cudaEventRecord(ev, ctx->stream));
+	if (p >= max_in_flight) {
+		cudaEvent_t old = ctx->throttle_ev[(p - max_in_flight) % ring];
+		if (old) CATTL3_CUDA(cudaEventSynchronize(old));
+	}
 	return CATTL3_OK;
 }
 

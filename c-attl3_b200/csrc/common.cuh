@@ -25,6 +25,9 @@ struct cattl3_ctx {
 	// per-CTA column sums of a fused batch-norm statistics epilogue (conv_tc.cu)
 	void* stat_ws = nullptr;
 	size_t stat_ws_bytes = 0;
+	// cattl3_ctx_throttle: one event per recent call
+	cudaEvent_t throttle_ev[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+	long long throttle_calls = 0;
 	// pinned staging for the *_host entry points
 	void* stage_dev[3] = { nullptr, nullptr, nullptr };
 	size_t stage_dev_bytes[3] = { 0, 0, 0 };

@@ -894,6 +894,21 @@ template<typename S> int axpy(cattl3_ctx* ctx, int64_t count, S alpha, const S* 
 template<typename S> int add_inplace(cattl3_ctx* ctx, int64_t count, S* y, const S* x) { return glue<S, 0>(ctx, "add_inplace", count, (S) 0, x, y); }
 template<typename S> int scale(cattl3_ctx* ctx, int64_t count, S alpha, const S* x, S* y) { return glue<S, 1>(ctx, "scale", count, alpha, x, y); }
 
+// y[i] = value: device-side constants (e.g. the element count that travels with synchronised batch-norm sums) without a
+// host -> device copy, which from pageable memory would synchronise the host with the stream.
+template<typename S>
+__global__ void __launch_bounds__(256) fill_kernel(long long count, S value, S* __restrict__ y) {
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < count; i += (long long) gridDim.x * 256) y[i] = value;
+}
+template<typename S>
+int fill(cattl3_ctx* ctx, int64_t count, S value, S* y) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(count > 0 && y, "fill: bad arguments");
+	fill_kernel<S><<<ew_grid(ctx, count, 256), 256, 0, ctx->stream>>>(count, value, y);
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+
 // ---- mini-batch rows out of a device-resident data set (MemoryDataProvider::get_data, :72-83) -------------------
 // dst[n + rows * j] = src[first + n + total * j]: a contiguous run per column, 16-byte vectors where everything lines up.
 template<typename S>
@@ -1027,6 +1042,8 @@ using namespace cattl3;
 
 extern "C" {
 
+int cattl3_fill_f32(cattl3_ctx* c, int64_t count, float value, float* y) { return fill<float>(c, count, value, y); }
+int cattl3_fill_f64(cattl3_ctx* c, int64_t count, double value, double* y) { return fill<double>(c, count, value, y); }
 int cattl3_slice_rows_f32(cattl3_ctx* c, int64_t total, int64_t vol, int64_t first, int64_t rows, const float* src, float* dst) {
 	return slice_rows<float>(c, total, vol, first, rows, src, dst); }
 int cattl3_slice_rows_f64(cattl3_ctx* c, int64_t total, int64_t vol, int64_t first, int64_t rows, const double* src, double* dst) {

@@ -166,6 +166,9 @@ int cattl3_device_count(void);
 int cattl3_ctx_create(cattl3_ctx** out, int device, void* cuda_stream);
 int cattl3_ctx_destroy(cattl3_ctx* ctx);
 int cattl3_ctx_synchronize(cattl3_ctx* ctx);
+/* Bounded run-ahead for an asynchronous step loop: marks "now" on the context's stream and blocks the host until the
+ * mark made max_in_flight calls earlier has been reached (call once per training step). */
+int cattl3_ctx_throttle(cattl3_ctx* ctx, int max_in_flight);
 int cattl3_ctx_set_conv_path(cattl3_ctx* ctx, int path);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t cattl3_ctx_launch_count(const cattl3_ctx* ctx);
@@ -198,6 +201,9 @@ int cattl3_feed_create(cattl3_feed** out, cattl3_ctx* ctx, int slots);
 int cattl3_feed_destroy(cattl3_feed* feed);
 int cattl3_feed_push(cattl3_feed* feed, const void* host_src, size_t bytes, void** dev_ptr);
 
+/* y[i] = value on the device (no host -> device copy, hence no host synchronisation). */
+int cattl3_fill_f32(cattl3_ctx*, int64_t count, float value, float* y);
+int cattl3_fill_f64(cattl3_ctx*, int64_t count, double value, double* y);
 /* Rows [first, first + rows) of a device-resident (total x vol) data set, rows fastest (MemoryDataProvider::get_data,
  * C-ATTL3/data_provider/MemoryDataProvider.hpp:72-83, without the host slice and the per-step upload). */
 int cattl3_slice_rows_f32(cattl3_ctx*, int64_t total, int64_t vol, int64_t first, int64_t rows, const float* src, float* dst);
