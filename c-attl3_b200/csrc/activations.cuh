@@ -69,4 +69,17 @@ __device__ __forceinline__ S act_fwd_rt(int kind, S x, S a) {
 	}
 }
 
+// N values at once with the switch hoisted out of the element loop (straight-line code per kind in an epilogue).
+template<typename S, int N>
+__device__ __forceinline__ void act_fwd_rt_n(int kind, S* v, S a) {
+#define CATTL3_ACT_CASE(K) case K: _Pragma("unroll") for (int i = 0; i < N; ++i) v[i] = act_fwd<S, K>(v[i], a); break;
+	switch (kind) {
+		CATTL3_ACT_CASE(CATTL3_ACT_RELU) CATTL3_ACT_CASE(CATTL3_ACT_LEAKY_RELU) CATTL3_ACT_CASE(CATTL3_ACT_ELU)
+		CATTL3_ACT_CASE(CATTL3_ACT_SWISH) CATTL3_ACT_CASE(CATTL3_ACT_SIGMOID) CATTL3_ACT_CASE(CATTL3_ACT_TANH)
+		CATTL3_ACT_CASE(CATTL3_ACT_SOFTPLUS)
+		default: break;
+	}
+#undef CATTL3_ACT_CASE
+}
+
 } // namespace cattl3

@@ -470,8 +470,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 						}
 					}
 					if (act_m) {
-						#pragma unroll
-						for (int i = 0; i < 16; ++i) v[i] = act_fwd_rt<float>(p.act_kind, v[i], p.act_param);
+						act_fwd_rt_n<float, 16>(p.act_kind, v, p.act_param);
 						if (c0 + 16 <= jn) {
 							#pragma unroll
 							for (int i = 0; i < 16; ++i) act_m[p.out_cs * (long long) (c0 + i)] = v[i];
@@ -594,7 +593,11 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 	CATTL3_REQUIRE(out || want_act, "gather GEMM: no output tensor");
 	CATTL3_REQUIRE(!want_stats || bias_mode == 1, "column statistics need a per-column bias");
 	const int T = gg.RH * gg.RW;
-	const int BN = gg.J >= 256 ? 256 : round_up(gg.J, 16);
+	// 256-wide tiles leave room for ONE accumulator only, so the epilogue sits on the critical path: with column
+	// statistics (the longest epilogue) take 128-wide tiles, whose two accumulators let it hide behind the next
+	// tile's MMAs (measured at config 2: 1.45 -> see profiles/README.md r1e)
+	const bool want_stats_early = ep && ep->col_stats;
+	const int BN = gg.J >= 256 ? (want_stats_early ? 128 : 256) : round_up(gg.J, 16);
 	// 32-element k-blocks (128 B weight rows) where shared and tensor memory allow four stages of them
 	const int KB = BN <= 128 ? 32 : 16;
 	const int r_pad = round_up(gg.SC, KB);

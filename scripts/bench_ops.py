@@ -34,7 +34,7 @@ def timed(stream, fn, reps):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="all", choices=["all", "conv", "mem"])
+    ap.add_argument("--only", default="all", choices=["all", "conv", "mem", "fused"])
     ap.add_argument("--double", action="store_true", help="also run the double (DFMA) kernel-layer sweep")
     ap.add_argument("--reps", type=int, default=5)
     args = ap.parse_args()
@@ -78,6 +78,46 @@ def main():
                      "fwd_ms": round(t_f, 4), "wgrad_ms": round(t_w, 4), "dgrad_ms": round(t_b - t_w, 4),
                      "fwd_tflops": tf(t_f), "wgrad_tflops": tf(t_w), "dgrad_tflops": tf(t_b - t_w)})
                 del x, dy, wt, y, dx
+
+    if args.only in ("all", "fused"):
+        # The forward chains of a network, fused epilogue against layer by layer (config 2 geometry, float, tcgen05):
+        #   ConvKernelLayer -> ReLU                and   ConvKernelLayer -> BatchNormLayer (training) -> ReLU.
+        for geom in ((256, 56, 56, 64, 256, 3, 3, 1, 1, 1, 1, 0, 0), (256, 56, 56, 64, 64, 3, 3, 1, 1, 1, 1, 0, 0)):
+            g = pkg.ConvGeom(*geom)
+            n, h, w, c, f = geom[:5]
+            m, k = n * h * w, 9 * c
+            dt = torch.float32
+            x = torch.rand(m * c, device=dev, dtype=dt) * 2 - 1
+            wt = torch.randn(k * f, device=dev, dtype=dt) * (2.0 / k) ** 0.5
+            b = torch.rand(f, device=dev, dtype=dt)
+            y, a, z = (torch.empty(m * f, device=dev, dtype=dt) for _ in range(3))
+            gm, bt = torch.ones(f, device=dev, dtype=dt), torch.zeros(f, device=dev, dtype=dt)
+            rm, rs, sm, ss = (torch.zeros(f, device=dev, dtype=dt) for _ in range(4))
+            stats = torch.zeros(2 * f, device=dev, dtype=torch.float64)
+            E = m * f * 4
+            relu = pkg.ACT["relu"]
+            cases = [
+                ("conv -> ReLU, layer by layer", lambda: (ctx.conv_forward(g, x, wt, b, y),
+                                                          ctx.activation_forward(relu, 0.0, n, h * w * f, y, a)), 3 * E),
+                ("conv -> ReLU, fused epilogue (pre-activation kept for backward)",
+                 lambda: ctx.conv_forward_fused(g, x, wt, b, y, act_kind=relu, act_out=a), 2 * E),
+                ("conv -> ReLU, fused epilogue (inference: activated output only)",
+                 lambda: ctx.conv_forward_fused(g, x, wt, b, None, act_kind=relu, act_out=a), E),
+                ("conv -> BatchNorm(train) -> ReLU, layer by layer",
+                 lambda: (ctx.conv_forward(g, x, wt, b, y),
+                          ctx.batchnorm_forward(1, n, h, w, f, 1, 1, 0.1, 1e-5, y, gm, bt, rm, rs, sm, ss, z),
+                          ctx.activation_forward(relu, 0.0, n, h * w * f, z, a)), 6 * E),
+                ("conv (statistics in the epilogue) -> BatchNorm apply + ReLU in one pass",
+                 lambda: (ctx.conv_forward_fused(g, x, wt, b, y, col_stats=stats),
+                          ctx.batchnorm_forward_stats(1, n, h, w, f, 1, 0.1, 1e-5, y, stats, b, gm, bt, rm, rs, sm, ss, z,
+                                                      act_kind=relu, act_out=a)), 4 * E),
+            ]
+            for name, fn, act_bytes in cases:
+                t = timed(stream, fn, args.reps)
+                out({"op": name, "shape": "N=%d %dx%dx%d -> %d, 3x3" % (n, h, w, c, f), "dtype": "float32", "ms": round(t, 4), "path": ctx.last_path,
+                     "activation_tensor_bytes_moved": act_bytes,
+                     "conv_gflop": round(2.0 * m * k * f / 1e9, 2)})
+            del x, wt, y, a, z
 
     if args.only in ("all", "mem"):
         hbm = pk["hbm"]
