@@ -64,7 +64,9 @@ public:
 		target_net_ptr = &net;
 		device_states.clear();
 		host_states.clear();
-		_fit(net.get_all_unique_params());
+		std::vector<Parameters<Scalar>*> params_vec = net.get_all_unique_params();
+		pack_parameters(params_vec);
+		_fit(params_vec);
 	}
 protected:
 	inline Scalar _train(typename Base::Net& net, typename Base::Provider& training_prov, std::size_t epoch,
@@ -246,6 +248,46 @@ protected:
 	const std::size_t batch_size;
 private:
 	typedef std::array<b200::DeviceBuffer<Scalar>,3> StateArrays;
+	/**
+	 * Lays the value storages of all optimizable, non-frozen device parameters out next to each other in one array,
+	 * and their gradient storages in another with the same offsets ("one contiguous gradient
+	 * arena").  fused_step() and all_reduce_gradients() merge adjacent arrays, so a whole network is then updated
+	 * by one or two kernel launches and all-reduced as one or two messages instead of one per Parameters object.
+	 * CATTL3_NO_ARENA=1 leaves the storages where they are.
+	 */
+	inline static void pack_parameters(const std::vector<Parameters<Scalar>*>& params_vec) {
+		static const bool enabled = [] {
+			const char* v = std::getenv("CATTL3_NO_ARENA");
+			return !(v && v[0] && v[0] != '0');
+		}();
+		if (!enabled)
+			return;
+		typedef std::shared_ptr<b200::ParameterStorage<Scalar>> StoragePtr;
+		std::vector<std::pair<StoragePtr,StoragePtr>> stores;
+		std::size_t total = 0;
+		for (Parameters<Scalar>* params_ptr : params_vec) {
+			B200Parameters<Scalar>* dev = dynamic_cast<B200Parameters<Scalar>*>(params_ptr);
+			if (!dev || !dev->are_optimizable() || dev->are_frozen() || dev->has_value_constraints())
+				continue;
+			bool seen = false;
+			for (const std::pair<StoragePtr,StoragePtr>& s : stores)
+				seen = seen || s.first == dev->value_storage();
+			if (seen)
+				continue;
+			stores.emplace_back(dev->value_storage(), dev->grad_storage());
+			total += dev->value_storage()->size();
+		}
+		if (stores.size() < 2)
+			return;
+		auto values = std::make_shared<b200::DeviceBuffer<Scalar>>(total);
+		auto grads = std::make_shared<b200::DeviceBuffer<Scalar>>(total);
+		std::size_t offset = 0;
+		for (const std::pair<StoragePtr,StoragePtr>& s : stores) {
+			s.first->relocate(values, offset);
+			s.second->relocate(grads, offset);
+			offset += s.first->size();
+		}
+	}
 	/** The tail of a training step: all-reduce, regularise, update, reset (SGDOptimizer.hpp:57-70). */
 	inline void finish_step(const std::vector<Parameters<Scalar>*>& params_vec, b200::Communicator& comm, std::size_t epoch,
 			double& reg_loss, std::size_t& updates) {

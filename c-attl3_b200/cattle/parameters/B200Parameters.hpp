@@ -79,6 +79,23 @@ public:
 		++dev_version;
 		host_version = dev_version;
 	}
+	/**
+	 * Moves the device copy to [arena_offset, arena_offset + size()) of `arena` (contents preserved): the optimizer
+	 * packs the storages of a network next to each other so that one fused kernel updates, and one message
+	 * all-reduces, all of them.  The storage keeps the arena alive.
+	 */
+	inline void relocate(std::shared_ptr<DeviceBuffer<Scalar>> new_arena, std::size_t arena_offset) {
+		if (host.empty())
+			return;
+		Scalar* dst = new_arena->data() + arena_offset;
+		Context& c = Context::get();
+		{
+			Context::Lock l = c.lock();
+			CATTLE_B200_CHECK(cattl3_memcpy_d2d(c.handle(), dst, dev.data(), host.size() * sizeof(Scalar)));
+		}
+		dev = DeviceBuffer<Scalar>::view(dst, host.size());  // releases the private array (stream ordered)
+		arena = std::move(new_arena);
+	}
 	inline void zero(std::size_t offset, std::size_t n) {
 		if (offset == 0 && n == host.size()) {
 			dev.zero();
@@ -91,6 +108,7 @@ public:
 		}
 	}
 private:
+	std::shared_ptr<DeviceBuffer<Scalar>> arena;  // set once relocated; declared first: outlives the view in `dev`
 	DeviceBuffer<Scalar> dev;
 	std::vector<Scalar> host;
 	std::uint64_t dev_version, host_version;
@@ -185,6 +203,13 @@ public:
 		}
 		view->frozen = frozen;
 		return view;
+	}
+	/** The shared storages behind this view (the optimizer packs them into one arena). */
+	inline const StorageSharedPtr& value_storage() const {
+		return value_store;
+	}
+	inline const StorageSharedPtr& grad_storage() const {
+		return grad_store;
 	}
 	inline bool are_optimizable() const {
 		return optimizable;

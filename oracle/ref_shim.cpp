@@ -23,6 +23,7 @@
  *                conv + BatchNorm + ReLU modules (config 4)
  */
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -410,6 +411,11 @@ int train_and_export(NeuralNetwork<S,3,false>& net, Opt& opt, TensorPtr<S,4> obs
 	}
 	MemoryDataProvider<S,3,false,false> prov(std::move(obs), std::move(objs));
 	opt.fit(net);
+	/* benchmarks only: REF_SHIM_WARMUP_EPOCHS untimed epochs first (one-time costs: allocations, data set placement) */
+	if (const char* warm = std::getenv("REF_SHIM_WARMUP_EPOCHS")) {
+		if (std::atoi(warm) > 0 && epochs > 0)
+			opt.train(net, prov, std::atoi(warm));
+	}
 	double t0 = now_ms();
 	S l = epochs > 0 ? opt.train(net, prov, epochs) : (S) 0;
 	double t1 = now_ms();
