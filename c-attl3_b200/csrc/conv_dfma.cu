@@ -22,6 +22,17 @@ namespace {
 
 constexpr int DF_BM = 128, DF_BK = 8, DF_THREADS = 256;
 
+// One element global -> shared without passing through a register (LDGSTS); !pred zero-fills the destination.
+template<typename S>
+__device__ __forceinline__ void cp_async_elem(S* dst, const S* src, bool pred) {
+	const uint32_t d = (uint32_t) __cvta_generic_to_shared(dst);
+	const int bytes = pred ? (int) sizeof(S) : 0;
+	if (sizeof(S) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(d), "l"(src), "r"(bytes) : "memory");
+	else asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_all() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template<typename S> struct Pair;
 template<> struct Pair<double> { typedef double2 type; };
 template<> struct Pair<float> { typedef float2 type; };
@@ -70,7 +81,6 @@ __global__ void __launch_bounds__(DF_THREADS, (TN == 4 || sizeof(S) == 4) ? 2 : 
 		for (int j = 0; j < TN; ++j) acc[i][j] = (S) 0;
 
 	const int T = gg.RH * gg.RW;
-	S pa[4], pb[B_ITERS];
 	// Source address of (this thread's row, tap (rh, rw)), or null outside the tensor / off the stride lattice.
 	auto tap_src = [&](int rh, int rw) -> const S* {
 		const int th = aoh * gg.ah + rh * gg.bh + gg.ch;
@@ -80,12 +90,8 @@ __global__ void __launch_bounds__(DF_THREADS, (TN == 4 || sizeof(S) == 4) ? 2 : 
 		if (ih >= gg.SH || iw >= gg.SW) return nullptr;
 		return src + an + (long long) gg.N * (ih + (long long) gg.SH * iw);
 	};
-	auto stash = [&](int buf) {
-		#pragma unroll
-		for (int i = 0; i < 4; ++i) As[buf][a_k0 + 2 * i][a_ml] = pa[i];
-		#pragma unroll
-		for (int i = 0; i < B_ITERS; ++i) Bs[buf][b_k0 + B_KSTEP * i][b_j] = pb[i];
-	};
+	// The tiles go global -> shared with cp.async (no staging registers: they are all needed by the accumulators and
+	// the fragments): the copies of k-block ks + 1 are issued before the multiply of k-block ks and awaited after it.
 	auto multiply = [&](int buf) {
 		#pragma unroll
 		for (int kk = 0; kk < DF_BK; ++kk) {
@@ -118,11 +124,11 @@ __global__ void __launch_bounds__(DF_THREADS, (TN == 4 || sizeof(S) == 4) ? 2 : 
 			const int k = b_k0 + B_KSTEP * i;
 			b_tap[i] = k / R; b_r[i] = k - b_tap[i] * R;
 		}
-		auto fetch = [&]() {
+		auto fetch = [&](int buf) {
 			#pragma unroll
 			for (int i = 0; i < 4; ++i) {
 				const S* ps = a_rw[i] < gg.RW ? tap_src(a_rh[i], a_rw[i]) : nullptr;
-				pa[i] = ps ? __ldg(ps + a_r[i] * plane) : (S) 0;
+				cp_async_elem(&As[buf][a_k0 + 2 * i][a_ml], ps ? ps + a_r[i] * plane : src, ps != nullptr);
 				a_r[i] += DF_BK;
 				while (a_r[i] >= R) {
 					a_r[i] -= R;
@@ -131,19 +137,21 @@ __global__ void __launch_bounds__(DF_THREADS, (TN == 4 || sizeof(S) == 4) ? 2 : 
 			}
 			#pragma unroll
 			for (int i = 0; i < B_ITERS; ++i) {
-				pb[i] = (j_ok && b_tap[i] < T) ? __ldg(w + wj + b_tap[i] * gg.w_stap + b_r[i] * gg.w_sr) : (S) 0;
+				const bool ok = j_ok && b_tap[i] < T;
+				cp_async_elem(&Bs[buf][b_k0 + B_KSTEP * i][b_j], ok ? w + wj + b_tap[i] * gg.w_stap + b_r[i] * gg.w_sr : w, ok);
 				b_r[i] += DF_BK;
 				while (b_r[i] >= R) { b_r[i] -= R; ++b_tap[i]; }
 			}
+			cp_async_commit_all();
 		};
-		fetch();
-		stash(0);
+		fetch(0);
+		cp_async_wait_all();
 		__syncthreads();
 		for (int ks = 0; ks < ksteps; ++ks) {
 			const int buf = ks & 1;
-			if (ks + 1 < ksteps) fetch();
+			if (ks + 1 < ksteps) fetch(buf ^ 1);
 			multiply(buf);
-			if (ks + 1 < ksteps) stash(buf ^ 1);
+			cp_async_wait_all();
 			__syncthreads();
 		}
 	} else {
@@ -155,17 +163,20 @@ __global__ void __launch_bounds__(DF_THREADS, (TN == 4 || sizeof(S) == 4) ? 2 : 
 		int f_tap = 0, f_r0 = 0;
 		const S* f_src = tap_src(0, 0);
 		const S* f_w = w + wj;
-		auto fetch = [&]() {
+		auto fetch = [&](int buf) {
 			#pragma unroll
 			for (int i = 0; i < 4; ++i) {
 				const int r = f_r0 + a_k0 + 2 * i;
-				pa[i] = (f_src && r < R) ? __ldg(f_src + r * plane) : (S) 0;
+				const bool ok = f_src && r < R;
+				cp_async_elem(&As[buf][a_k0 + 2 * i][a_ml], ok ? f_src + r * plane : src, ok);
 			}
 			#pragma unroll
 			for (int i = 0; i < B_ITERS; ++i) {
 				const int r = f_r0 + b_k0 + B_KSTEP * i;
-				pb[i] = (j_ok && r < R) ? __ldg(f_w + r * gg.w_sr) : (S) 0;
+				const bool ok = j_ok && r < R;
+				cp_async_elem(&Bs[buf][b_k0 + B_KSTEP * i][b_j], ok ? f_w + r * gg.w_sr : w, ok);
 			}
+			cp_async_commit_all();
 			f_r0 += DF_BK;
 			if (f_r0 >= R) {
 				f_r0 = 0;
@@ -176,14 +187,14 @@ __global__ void __launch_bounds__(DF_THREADS, (TN == 4 || sizeof(S) == 4) ? 2 : 
 				}
 			}
 		};
-		fetch();
-		stash(0);
+		fetch(0);
+		cp_async_wait_all();
 		__syncthreads();
 		for (int ks = 0; ks < ksteps; ++ks) {
 			const int buf = ks & 1;
-			if (ks + 1 < ksteps) fetch();
+			if (ks + 1 < ksteps) fetch(buf ^ 1);
 			multiply(buf);
-			if (ks + 1 < ksteps) stash(buf ^ 1);
+			cp_async_wait_all();
 			__syncthreads();
 		}
 	}
@@ -275,8 +286,7 @@ __global__ void __launch_bounds__(DF_THREADS, (TN == 4 || sizeof(S) == 4) ? 2 : 
 		#pragma unroll
 		for (int j = 0; j < TN; ++j) acc[i][j] = (S) 0;
 
-	S pa[4], pb[B_ITERS];
-	auto fetch = [&](long long mc) {
+	auto fetch = [&](long long mc, int buf) {
 		const long long m = mc + l_mm;
 		const bool ok = m < me;
 		// M < 2^31 (dfma_wgrad_supported): 32-bit divisions
@@ -286,35 +296,30 @@ __global__ void __launch_bounds__(DF_THREADS, (TN == 4 || sizeof(S) == 4) ? 2 : 
 		const int bh = oh * gg.ah, bw = ow * gg.aw;
 		#pragma unroll
 		for (int i = 0; i < 4; ++i) {
-			S v = (S) 0;
 			const int th = bh + row_dh[i], tw = bw + row_dw[i];
-			// weight gradients only ever gather forward-style (denh = denw = 1, dfma_wgrad_supported)
-			if (ok && row_r[i] >= 0 && th >= 0 && tw >= 0 && th < gg.SH && tw < gg.SW)
-				v = __ldg(src + n + (long long) gg.N * (th + (long long) gg.SH * tw) + row_r[i] * plane);
-			pa[i] = v;
+			// weight gradients only ever gather forward-style (denh = denw = 1, fma_wgrad_supported)
+			const bool aok = ok && row_r[i] >= 0 && th >= 0 && tw >= 0 && th < gg.SH && tw < gg.SW;
+			cp_async_elem(&As[buf][l_mm][l_r0 + 32 * i],
+					aok ? src + n + (long long) gg.N * (th + (long long) gg.SH * tw) + row_r[i] * plane : src, aok);
 		}
 		#pragma unroll
 		for (int i = 0; i < B_ITERS; ++i) {
 			const int j = j0 + l_r0 + 32 * i;
-			pb[i] = (ok && j < J) ? __ldg(plain + m + M * j) : (S) 0;
+			const bool bok = ok && j < J;
+			cp_async_elem(&Bs[buf][l_mm][l_r0 + 32 * i], bok ? plain + m + M * j : plain, bok);
 		}
-	};
-	auto stash = [&](int buf) {
-		#pragma unroll
-		for (int i = 0; i < 4; ++i) As[buf][l_mm][l_r0 + 32 * i] = pa[i];
-		#pragma unroll
-		for (int i = 0; i < B_ITERS; ++i) Bs[buf][l_mm][l_r0 + 32 * i] = pb[i];
+		cp_async_commit_all();
 	};
 
 	const long long steps = me > ms ? (me - ms + DW_BKM - 1) / DW_BKM : 0;
 	if (steps > 0) {
-		fetch(ms);
-		stash(0);
+		fetch(ms, 0);
+		cp_async_wait_all();
 	}
 	__syncthreads();
 	for (long long st = 0; st < steps; ++st) {
 		const int buf = (int) (st & 1);
-		if (st + 1 < steps) fetch(ms + (st + 1) * DW_BKM);
+		if (st + 1 < steps) fetch(ms + (st + 1) * DW_BKM, buf ^ 1);
 		#pragma unroll
 		for (int mk = 0; mk < DW_BKM; ++mk) {
 			S a[8], b[TN];
@@ -329,7 +334,7 @@ __global__ void __launch_bounds__(DF_THREADS, (TN == 4 || sizeof(S) == 4) ? 2 : 
 				#pragma unroll
 				for (int j = 0; j < TN; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
 		}
-		if (st + 1 < steps) stash(buf ^ 1);
+		cp_async_wait_all();
 		__syncthreads();
 	}
 

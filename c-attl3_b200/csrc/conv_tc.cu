@@ -16,6 +16,7 @@
 // The output tile sits in TMEM with lane = m and column = filter, so the epilogue stores each
 // column as 32 consecutive floats per warp: y(m + M*f) is written fully coalesced.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "activations.cuh"
 
@@ -256,6 +257,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 	float* sbias = reinterpret_cast<float*>(bars + 32);  // 256 floats behind the barriers
 	double* sstat = reinterpret_cast<double*>(sbias + 256);  // [4 warps][2][BN] column sums (only with stat_partial)
+	float* spatch = reinterpret_cast<float*>(sstat + 8 * p.BN);  // [4 warps][32][17] transpose patches (likewise)
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int T = p.RH * p.RW;
@@ -426,35 +428,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 				}
 				tmem_ld_wait();
 				if (stats && warp_ok) {
-					// Per column: sum and sum of squares of the 32 accumulators (= y - bias) of this warp's rows.
-					// Shifted by lane 0's value so that the fp32 part works on magnitudes ~ sigma; 32 values
-					// (16 sums, 16 square sums) are reduced over the 32 lanes by recursive halving (31 shuffles:
-					// lane L ends up with value L), then re-based to shift 0 and accumulated in double.
-					float t[32];
-					float kk = 0.f;
+					// Per column: sum and sum of squares of the 32 accumulators (= y - bias) of this warp's rows.  The
+					// 32 x 16 chunk is transposed through a padded shared-memory patch (conflict free both ways):
+					// lane L then owns column L % 16 over rows 16 * (L / 16) ..., sums d = value - first value and
+					// d^2 in fp32 (magnitudes ~ sigma), re-bases to shift 0 in double, and the two half-columns
+					// meet in lanes 0..15, which accumulate in double.
+					float* patch = spatch + q * (32 * 17);
 					#pragma unroll
-					for (int i = 0; i < 16; ++i) {
-						const float k = __shfl_sync(0xffffffffu, v[i], 0);
-						const float d = v[i] - k;
-						t[i] = d; t[16 + i] = d * d;
-						if ((lane & 15) == i) kk = k;
-					}
+					for (int i = 0; i < 16; ++i) patch[lane * 17 + i] = v[i];
+					__syncwarp();
+					const float* colp = patch + (lane >> 4) * (16 * 17) + (lane & 15);
+					const float k0 = colp[0];
+					float s1 = 0.f, s2 = 0.f;
 					#pragma unroll
-					for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
-						const bool upper = (lane & off) != 0;
-						#pragma unroll
-						for (int i = 0; i < n / 2; ++i) {
-							const float send = upper ? t[i] : t[i + n / 2];
-							const float keep = upper ? t[i + n / 2] : t[i];
-							t[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-						}
+					for (int r = 1; r < 16; ++r) {
+						const float d = colp[r * 17] - k0;
+						s1 += d;
+						s2 = fmaf(d, d, s2);
 					}
-					const float other = __shfl_xor_sync(0xffffffffu, t[0], 16);
+					const double K = (double) k0, d1 = (double) s1;
+					double S1 = d1 + 16.0 * K;
+					double S2 = (double) s2 + 2.0 * K * d1 + 16.0 * K * K;
+					S1 += __shfl_down_sync(0xffffffffu, S1, 16);
+					S2 += __shfl_down_sync(0xffffffffu, S2, 16);
 					if (lane < 16) {
-						const double K = (double) kk, s1 = (double) t[0], s2 = (double) other;
-						my_stat[c0 + lane] += s1 + 32.0 * K;
-						my_stat[p.BN + c0 + lane] += s2 + 2.0 * K * s1 + 32.0 * K * K;
+						my_stat[c0 + lane] += S1;
+						my_stat[p.BN + c0 + lane] += S2;
 					}
+					__syncwarp();   // the patch is rewritten by the next chunk
 				}
 				if (m_ok) {
 					#pragma unroll
@@ -597,7 +598,8 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 	// statistics (the longest epilogue) take 128-wide tiles, whose two accumulators let it hide behind the next
 	// tile's MMAs (measured at config 2: 1.45 -> see profiles/README.md r1e)
 	const bool want_stats_early = ep && ep->col_stats;
-	const int BN = gg.J >= 256 ? (want_stats_early ? 128 : 256) : round_up(gg.J, 16);
+	static const bool stats_wide = getenv("CATTL3_STATS_BN256") != nullptr;   // experiment knob
+	const int BN = gg.J >= 256 ? (want_stats_early && !stats_wide ? 128 : 256) : round_up(gg.J, 16);
 	// 32-element k-blocks (128 B weight rows) where shared and tensor memory allow four stages of them
 	const int KB = BN <= 128 ? 32 : 16;
 	const int r_pad = round_up(gg.SC, KB);
@@ -643,7 +645,7 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 	// epilogue of one tile overlaps the MMAs of the next
 	p.nacc = 2 * BN + 4 * 2 * KB <= 512 ? 2 : 1;
 	const int stage_bytes = TC_BM * KB * 4 + 2 * BN * KB * 4;
-	const int stat_bytes = want_stats ? 4 * 2 * BN * 8 : 0;
+	const int stat_bytes = want_stats ? 4 * 2 * BN * 8 + 4 * 32 * 17 * 4 : 0;
 	int stages = (TC_SMEM_LIMIT - stat_bytes) / stage_bytes;
 	const int tmem_stages = (512 - p.nacc * BN) / (2 * KB);
 	if (stages > tmem_stages) stages = tmem_stages;
