@@ -80,7 +80,7 @@ _SYMBOLS = [
     "cattl3_dense_forward", "cattl3_dense_backward", "cattl3_activation_forward", "cattl3_activation_backward",
     "cattl3_pool_forward", "cattl3_pool_backward", "cattl3_batchnorm_forward", "cattl3_batchnorm_backward",
     "cattl3_optimizer_step", "cattl3_add_inplace", "cattl3_scale", "cattl3_axpy",
-    "cattl3_conv_forward_fused", "cattl3_dense_forward_fused", "cattl3_batchnorm_forward_stats",
+    "cattl3_conv_forward_fused", "cattl3_dense_forward_fused", "cattl3_transconv_forward_fused", "cattl3_batchnorm_forward_stats",
     "cattl3_dropout_forward", "cattl3_dropout_backward", "cattl3_loss",
     "cattl3_batchnorm_stats", "cattl3_batchnorm_backward_sums", "cattl3_batchnorm_backward_apply",
     "cattl3_slice_rows", "cattl3_fill")]
@@ -197,10 +197,11 @@ class Context:
         ep.col_stats = col_stats.data_ptr() if col_stats is not None else None
         return ep
 
-    def conv_forward_fused(self, g, x, w, b, y, act_kind=None, act_param=0.0, act_out=None, col_stats=None):
+    def conv_forward_fused(self, g, x, w, b, y, act_kind=None, act_param=0.0, act_out=None, col_stats=None,
+                           transposed=False):
         """Forward with a fused epilogue: act_out = f(y) and / or col_stats (2*F float64) for a BatchNormLayer."""
         ep = self._epilogue(act_kind, act_param, act_out, col_stats)
-        self._call("cattl3_conv_forward_fused", x.dtype, ctypes.byref(g), _p(x), _p(w), _p(b), _p(y), ctypes.byref(ep))
+        self._call("cattl3_transconv_forward_fused" if transposed else "cattl3_conv_forward_fused", x.dtype, ctypes.byref(g), _p(x), _p(w), _p(b), _p(y), ctypes.byref(ep))
 
     def dense_forward_fused(self, n, i, o, x, w, b, y, act_kind=None, act_param=0.0, act_out=None, col_stats=None):
         ep = self._epilogue(act_kind, act_param, act_out, col_stats)

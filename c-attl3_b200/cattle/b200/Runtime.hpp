@@ -111,6 +111,8 @@ template<> struct Api<S> { \
 		return cattl3_conv_forward_##SUF(c, g, x, w, b, y); } \
 	static int conv_forward_fused(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y, const cattl3_epilogue* ep) { \
 		return cattl3_conv_forward_fused_##SUF(c, g, x, w, b, y, ep); } \
+	static int transconv_forward_fused(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y, const cattl3_epilogue* ep) { \
+		return cattl3_transconv_forward_fused_##SUF(c, g, x, w, b, y, ep); } \
 	static int dense_forward_fused(cattl3_ctx* c, std::int32_t n, std::int32_t in, std::int32_t out, const S* x, const S* w, const S* b, S* y, const cattl3_epilogue* ep) { \
 		return cattl3_dense_forward_fused_##SUF(c, n, in, out, x, w, b, y, ep); } \
 	static int batchnorm_forward_stats(cattl3_ctx* c, int pc, std::int32_t n, std::int32_t h, std::int32_t w, std::int32_t ch, int init, S decay, S eps, const S* x, const double* cs, const double* gc, const S* shift, const S* gamma, const S* beta, S* rm, S* rs, S* sm, S* ss, S* y, int ak, S ap, S* ao) { \

@@ -69,16 +69,16 @@ public:
 		in_cache = std::move(in);
 		return out;
 	}
-	/** The convolution's epilogue can do the next layer's work; the transposed layer's (per-element bias) does not. */
+	/** Both directions fuse a following activation; only the convolution (per-filter bias) produces column statistics. */
 	inline bool can_fuse_epilogue() const {
-		return !Transposed;
+		return true;
 	}
 	inline std::size_t stat_columns() const {
 		return Transposed ? 0 : filters;
 	}
 	inline DeviceTensor<Scalar> pass_forward_dev_fused(DeviceTensor<Scalar> in, bool training, FusedEpilogue<Scalar>& ep) {
-		if (Transposed)
-			throw Error(CATTL3_ERR_UNSUPPORTED, "TransConvKernelLayer has no fused epilogue");
+		if (Transposed && ep.want_stats)
+			throw Error(CATTL3_ERR_UNSUPPORTED, "TransConvKernelLayer produces no column statistics");
 		cattl3_conv_geom g = geometry(in.rows);
 		const std::size_t volume = Base::output_dims.get_volume();
 		const bool act = ep.act_kind != CATTL3_ACT_NONE;
@@ -102,8 +102,13 @@ public:
 		Context& c = Context::get();
 		{
 			Context::Lock l = c.lock();
-			CATTLE_B200_CHECK(Device::conv_forward_fused(c.handle(), &g, in.data(), w.device_values(),
-					b.device_values(), out.data(), &e));
+			if (Transposed) {
+				CATTLE_B200_CHECK(Device::transconv_forward_fused(c.handle(), &g, in.data(), w.device_values(),
+						b.device_values(), out.data(), &e));
+			} else {
+				CATTLE_B200_CHECK(Device::conv_forward_fused(c.handle(), &g, in.data(), w.device_values(),
+						b.device_values(), out.data(), &e));
+			}
 		}
 		in_cache = std::move(in);
 		return out;

@@ -254,15 +254,19 @@ static int conv_backward(cattl3_ctx* ctx, const cattl3_conv_geom* g, const S* x,
 }
 
 template<typename S>
-static int transconv_forward(cattl3_ctx* ctx, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y) {
+static int transconv_forward(cattl3_ctx* ctx, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y,
+		const cattl3_epilogue* ep = nullptr) {
 	CATTL3_CHECK(check_ctx(ctx));
 	int oh, ow;
 	CATTL3_CHECK(check_geom(g, 1, &oh, &ow));
-	CATTL3_REQUIRE(x && w && b && y, "transconv_forward: null tensor");
+	CATTL3_REQUIRE(x && w && b, "transconv_forward: null tensor");
+	CATTL3_REQUIRE(!ep || !ep->col_stats, "transconv_forward: column statistics need a per-filter bias (convolution / dense only)");
+	EpilogueArgs ea;
+	CATTL3_CHECK(check_epilogue(ep, y, &ea));
 	const long long T = (long long) g->rh * g->rw;
 	GatherGeom gg = bwd_gather(g->n, g->h, g->w, g->c, oh, ow, g->f, g);
 	gg.w_stap = g->c; gg.w_sr = 1; gg.w_sj = (long long) g->c * T;
-	return run_gather_gemm<S>(ctx, gg, x, w, b, 2, y);
+	return run_gather_gemm<S>(ctx, gg, x, w, b, 2, y, ep ? &ea : nullptr);
 }
 
 template<typename S>
@@ -574,6 +578,10 @@ int cattl3_dense_forward_fused_##SUF(cattl3_ctx* c, int32_t n, int32_t in, int32
 	CATTL3_REQUIRE(ep, "dense_forward_fused: null epilogue"); \
 	cattl3_conv_geom g = dense_geom(n, in, out); \
 	return conv_forward<S>(c, &g, x, w, b, y, ep); } \
+int cattl3_transconv_forward_fused_##SUF(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y, \
+		const cattl3_epilogue* ep) { \
+	CATTL3_REQUIRE(ep, "transconv_forward_fused: null epilogue"); \
+	return transconv_forward<S>(c, g, x, w, b, y, ep); } \
 int cattl3_transconv_forward_##SUF(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* b, S* y) { \
 	return transconv_forward<S>(c, g, x, w, b, y); } \
 int cattl3_transconv_backward_##SUF(cattl3_ctx* c, const cattl3_conv_geom* g, const S* x, const S* w, const S* dy, S* dw, S* db, S* dx) { \

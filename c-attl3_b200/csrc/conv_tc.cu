@@ -596,10 +596,9 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 	const int T = gg.RH * gg.RW;
 	// 256-wide tiles leave room for ONE accumulator only, so the epilogue sits on the critical path: with column
 	// statistics (the longest epilogue) take 128-wide tiles, whose two accumulators let it hide behind the next
-	// tile's MMAs (measured at config 2: 1.45 -> see profiles/README.md r1e)
+	// tile's MMAs (profiles/README.md, r1e)
 	const bool want_stats_early = ep && ep->col_stats;
-	static const bool stats_wide = getenv("CATTL3_STATS_BN256") != nullptr;   // experiment knob
-	const int BN = gg.J >= 256 ? (want_stats_early && !stats_wide ? 128 : 256) : round_up(gg.J, 16);
+	const int BN = gg.J >= 256 ? (want_stats_early ? 128 : 256) : round_up(gg.J, 16);
 	// 32-element k-blocks (128 B weight rows) where shared and tensor memory allow four stages of them
 	const int KB = BN <= 128 ? 32 : 16;
 	const int r_pad = round_up(gg.SC, KB);

@@ -256,6 +256,8 @@ int cattl3_dense_backward_f64(cattl3_ctx*, int32_t n, int32_t in, int32_t out, c
  */
 int cattl3_conv_forward_fused_f32(cattl3_ctx*, const cattl3_conv_geom*, const float* x, const float* w, const float* b, float* y, const cattl3_epilogue* ep);
 int cattl3_conv_forward_fused_f64(cattl3_ctx*, const cattl3_conv_geom*, const double* x, const double* w, const double* b, double* y, const cattl3_epilogue* ep);
+int cattl3_transconv_forward_fused_f32(cattl3_ctx*, const cattl3_conv_geom*, const float* x, const float* w, const float* b, float* y, const cattl3_epilogue* ep);   /* activation only */
+int cattl3_transconv_forward_fused_f64(cattl3_ctx*, const cattl3_conv_geom*, const double* x, const double* w, const double* b, double* y, const cattl3_epilogue* ep);
 int cattl3_dense_forward_fused_f32(cattl3_ctx*, int32_t n, int32_t in, int32_t out, const float* x, const float* w, const float* b, float* y, const cattl3_epilogue* ep);
 int cattl3_dense_forward_fused_f64(cattl3_ctx*, int32_t n, int32_t in, int32_t out, const double* x, const double* w, const double* b, double* y, const cattl3_epilogue* ep);
 

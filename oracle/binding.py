@@ -176,6 +176,15 @@ class Oracle:
         return out, loss.value, ms.value
 
 
+    def dropout(self, prob, x, dy):
+        """DropoutLayer: training forward + backward, inference forward.  Returns dict(y, dx, y_infer)."""
+        dt = x.dtype
+        n, h, w, c = x.shape
+        y, dx, yi = F(x.shape, dt), F(x.shape, dt), F(x.shape, dt)
+        rc = self._fn("dropout", dt)(n, h, w, c, _CT[np.dtype(dt)](prob), _ptr(x), _ptr(dy), _ptr(y), _ptr(dx), _ptr(yi))
+        assert rc == 0, rc
+        return dict(y=y, dx=dx, y_infer=yi)
+
     def train_autoencoder(self, x, batch, epochs, params_in=None):
         """Config-3 auto-encoder (mnist_autoencoder.cpp), SquaredLoss against the input, Nadam.
         epochs < 0: only returns the parameter count.  Returns (params, loss, train_ms)."""

@@ -390,6 +390,24 @@ int cifar_impl(int total, int batch, int epochs, const S* x, const S* obj, const
 	return 0;
 }
 
+/*
+ * DropoutLayer<S,3> (C-ATTL3/layer/DropoutLayer.hpp:74-94): one training forward + backward and one inference
+ * forward on an n x h x w x c tensor.  The masks are random (not reproducible across implementations), so callers
+ * check the layer's contract: y = x * mask, dx = dy * mask with the SAME mask, mask in {0, 1 / (1 - p + eps)},
+ * drop rate ~ p, inference = identity.
+ */
+template<typename S>
+int dropout_impl(int n, int h, int w, int c, S prob, const S* x, const S* dy, S* y, S* dx, S* y_infer) {
+	DropoutLayer<S,3> layer({ (std::size_t) h, (std::size_t) w, (std::size_t) c }, prob);
+	Tensor<S,4> out = layer.pass_forward(make4(x, n, h, w, c), true);
+	std::memcpy(y, out.data(), sizeof(S) * out.size());
+	Tensor<S,4> grad = layer.pass_back(make4(dy, n, h, w, c));
+	std::memcpy(dx, grad.data(), sizeof(S) * grad.size());
+	Tensor<S,4> inf = layer.pass_forward(make4(x, n, h, w, c), false);
+	std::memcpy(y_infer, inf.data(), sizeof(S) * inf.size());
+	return 0;
+}
+
 /* Shared tail of the network trainers: inject parameters, train without shuffling, copy the parameters out. */
 template<typename S, typename Opt>
 int train_and_export(NeuralNetwork<S,3,false>& net, Opt& opt, TensorPtr<S,4> obs, TensorPtr<S,4> objs, int epochs,
@@ -570,6 +588,8 @@ int ref_optimizer_hostparams_##SUF(int kind, const S* hyper, S l2_lambda, int ro
 int ref_train_cifar_##SUF(int total, int batch, int epochs, const S* x, const S* obj, const S* params_in, \
 		S* params_out, double* loss_out, double* train_ms) { \
 	return cifar_impl<S>(total, batch, epochs, x, obj, params_in, params_out, loss_out, train_ms); } \
+int ref_dropout_##SUF(int n, int h, int w, int c, S prob, const S* x, const S* dy, S* y, S* dx, S* y_infer) { \
+	return dropout_impl<S>(n, h, w, c, prob, x, dy, y, dx, y_infer); } \
 int ref_train_autoencoder_##SUF(int total, int batch, int epochs, const S* x, const S* params_in, S* params_out, \
 		int* n_params, double* loss_out, double* train_ms) { \
 	return autoencoder_impl<S>(total, batch, epochs, x, params_in, params_out, n_params, loss_out, train_ms); } \

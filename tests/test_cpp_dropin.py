@@ -222,6 +222,52 @@ def test_fused_and_unfused_network_loops_agree(dt):
     assert err < (2e-5 if dt == np.float32 else 1e-10)
 
 
+@pytest.mark.parametrize("dt", DTYPES)
+def test_dropout_layer_contract(b200, dt):
+    """The B200 DropoutLayer class (device RNG) honours the reference layer's contract (DropoutLayer.hpp:74-94):
+    inverted dropout with the same mask forward and backward, survivors scaled by 1 / (1 - p + eps), inference = identity;
+    where the reference travelled, its own layer is held to the same checks (its masks differ: host RNG)."""
+    rng = np.random.default_rng(81)
+    x = C.rand(rng, (64, 12, 11, 7), dt, 0.5, 1.5)
+    dy = C.rand(rng, x.shape, dt, 0.5, 1.5)
+    p = 0.3
+    libs = [b200] + ([binding.Oracle("ref")] if binding.have_ref() else [])
+    for lib in libs:
+        r = lib.dropout(p, x, dy)
+        scale = dt(1) / (dt(1) - dt(p) + dt(1e-5))
+        keep = r["y"] != 0
+        assert np.allclose(r["y"][keep], (x * scale)[keep], rtol=1e-6 if dt == np.float32 else 1e-14)
+        assert np.array_equal(r["dx"] != 0, keep), "backward used a different mask"
+        assert np.allclose(r["dx"][keep], (dy * scale)[keep], rtol=1e-6 if dt == np.float32 else 1e-14)
+        rate = 1.0 - keep.mean()
+        assert abs(rate - p) < 5 * np.sqrt(p * (1 - p) / x.size), rate
+        assert np.array_equal(r["y_infer"], x)
+
+
+@pytest.mark.parametrize("dt", [np.float32])
+def test_host_provider_path_through_the_input_feed(dt):
+    """CATTL3_DEVICE_DATASET_GB=0 keeps the data set on the host: mini-batches then reach the device through the input
+    feed (pinned staging + copy stream ring).  Same training run, same parameters as with the HBM-resident data set."""
+    code = (
+        "import sys, numpy as np; sys.path[:0] = [%r, %r]\n"
+        "import cases as C; from oracle import binding\n"
+        "lib = binding.Oracle('ref', path=%r); dt = np.%s\n"
+        "x, obj = C.resnet_inputs(dt, total=192); n = lib.train_resnet(x, obj, 32, -1, C.RESNET_SMALL)\n"
+        "p, l, _ = lib.train_resnet(x, obj, 32, 2, C.RESNET_SMALL, params_in=C.seeded_params(n, dt, 4002))\n"
+        "np.save(sys.argv[1], p)\n" % (ROOT, os.path.join(ROOT, "tests"), SHIM, np.dtype(dt).name))
+    import tempfile
+    outs = []
+    with tempfile.TemporaryDirectory() as d:
+        for i, env in enumerate(({}, {"CATTL3_DEVICE_DATASET_GB": "0"}, {"CATTL3_NO_ARENA": "1"})):
+            path = os.path.join(d, "p%d.npy" % i)
+            r = subprocess.run([os.sys.executable, "-c", code, path], env=dict(os.environ, **env), capture_output=True,
+                               text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append(np.load(path))
+    assert np.array_equal(outs[0], outs[1]), C.relerr(outs[0], outs[1])      # where the data comes from changes nothing
+    assert np.array_equal(outs[0], outs[2]), C.relerr(outs[0], outs[2])      # nor does the parameter arena
+
+
 def test_reference_gradient_test_passes():
     """The reference's own gradient_test.cpp, compiled unchanged against the B200 headers."""
     if not os.path.exists(GRADIENT_TEST):

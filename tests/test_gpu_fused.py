@@ -55,6 +55,31 @@ def test_conv_fused_activation_matches_layer_chain(U, orc, name, dt, path):
         assert np.array_equal(U.host(a2, shape), U.host(ad, shape)), (name, aname)
 
 
+@pytest.mark.parametrize("name,dt", [("mnist_t0", np.float32), ("wide", np.float32), ("wide_s3_k2", np.float32),
+                                     ("gt_rank3", np.float64), ("dfma_t", np.float64)])
+def test_transconv_fused_activation_matches_layer_chain(U, orc, name, dt):
+    """TransConvKernelLayer -> activation (config 3: TransConv -> Softplus) in the epilogue, bias per output element."""
+    case = C.TCONV_CASES[name]
+    g, x, w, b, dy = C.conv_inputs(case, dt, 42, True)
+    oh, ow = conv_out_dims(g, True)
+    shape = (g.n, oh, ow, g.f)
+    ref_y = orc.conv(g, x, w, b, transposed=True)["y"]
+    c = U.ctx()
+    cg = U.pkg.ConvGeom(*case)
+    xd, wd, bd = U.dev(x), U.dev(w), U.dev(b)
+    for aname in ("softplus", "leaky", "tanh"):
+        kind, alpha = C.ACT_CASES[aname]
+        yd, ad = U.zeros(shape, dt), U.zeros(shape, dt)
+        c.conv_forward_fused(cg, xd, wd, bd, yd, act_kind=kind, act_param=alpha, act_out=ad, transposed=True)
+        c.synchronize()
+        assert C.relerr(U.host(yd, shape), ref_y) < _tol(dt), (name, aname)
+        assert C.relerr(U.host(ad, shape), orc.activation(kind, alpha, ref_y)["y"]) < _tol(dt), (name, aname)
+    import torch
+    with pytest.raises(U.pkg.Cattl3Error):   # no per-filter bias, no column statistics
+        c.conv_forward_fused(cg, xd, wd, bd, yd, col_stats=torch.zeros(2 * g.f, dtype=torch.float64, device="cuda"),
+                             transposed=True)
+
+
 @pytest.mark.parametrize("name,dt,path", FUSED_CONV)
 def test_conv_fused_batchnorm_statistics(U, orc, name, dt, path):
     """conv (epilogue: column sums) -> batchnorm_forward_stats (+ fused ReLU) equals conv -> BatchNormLayer -> ReLU,
