@@ -163,7 +163,11 @@ simt:
 		set_error("tcgen05 path requested but the shape/type does not qualify (needs float, batch %% 32 == 0)");
 		return CATTL3_ERR_UNSUPPORTED;
 	}
-	if (ctx->conv_path != CATTL3_PATH_SIMT && fma_gather_gemm_supported<S>(gg)) {
+	if (ctx->conv_path != CATTL3_PATH_SIMT && tiny_gather_gemm_supported(gg, sizeof(S))) {
+		// a handful of output columns: the streaming kernel (conv_simt.cu)
+		ctx->last_path = "tiny";
+		CATTL3_CHECK(tiny_gather_gemm<S>(ctx, gg, src, w, bias, bias_mode, out, ep));
+	} else if (ctx->conv_path != CATTL3_PATH_SIMT && fma_gather_gemm_supported<S>(gg)) {
 		// GEMM-sized shapes off the tensor-core path (double; float with few channels or a ragged batch): the
 		// big-tile FMA kernels (conv_dfma.cu)
 		ctx->last_path = IsFloat<S>::value ? "ffma" : "dfma";
@@ -191,6 +195,10 @@ static int run_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const 
 	if (ctx->conv_path == CATTL3_PATH_TCGEN05) {
 		set_error("tcgen05 weight-gradient path requested but the shape/type does not qualify");
 		return CATTL3_ERR_UNSUPPORTED;
+	}
+	if (ctx->conv_path != CATTL3_PATH_SIMT && tiny_wgrad_supported(gg, sizeof(S))) {
+		ctx->last_path = "tiny";
+		return tiny_wgrad<S>(ctx, gg, src, plain, dw);
 	}
 	if (ctx->conv_path != CATTL3_PATH_SIMT && fma_wgrad_supported<S>(gg)) {
 		ctx->last_path = IsFloat<S>::value ? "ffma" : "dfma";

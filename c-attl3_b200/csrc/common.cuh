@@ -117,6 +117,14 @@ int simt_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* pla
 template<typename S>
 int colsum_accumulate(cattl3_ctx* ctx, int64_t rows, int64_t cols, const S* a, S* out);
 
+// Tiny-channel streaming kernels (conv_simt.cu): 1-8 output columns / K x J <= 2048 gradients (configs 1 and 3).
+bool tiny_gather_gemm_supported(const GatherGeom& gg, size_t scalar_bytes);
+template<typename S>
+int tiny_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* w, const S* bias, int bias_mode, S* out,
+		const EpilogueArgs* ep = nullptr);
+bool tiny_wgrad_supported(const GatherGeom& gg, size_t scalar_bytes);
+template<typename S> int tiny_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* plain, S* dw);
+
 // Big-tile FMA path (conv_dfma.cu): double at GEMM-sized shapes; float where the tensor-core path does not apply.
 template<typename S> bool fma_gather_gemm_supported(const GatherGeom& gg);
 template<typename S>

@@ -254,6 +254,190 @@ template int simt_wgrad<float>(cattl3_ctx*, const GatherGeom&, const float*, con
 template int simt_wgrad<double>(cattl3_ctx*, const GatherGeom&, const double*, const double*, double*);
 
 // ------------------------------------------------------------------------------------------------
+// Tiny-channel layers (configs 1 and 3: 1-8 filters or input channels): a GEMM tile would be almost
+// empty, the work is a few FMAs per byte, so these are written as streaming kernels.
+//
+// tiny_gather_gemm_kernel: one thread per output row m keeps all J <= JT outputs in registers; the
+// weights sit in shared memory as [k][JT] (every lane reads the same word: broadcast), the source is
+// read once per (tap, channel), coalesced along m.  Forward of few-filter convolutions, input
+// gradient of few-channel ones, transposed convolutions with few output channels.
+// ------------------------------------------------------------------------------------------------
+template<typename S, int JT>
+__global__ void __launch_bounds__(256) tiny_gather_gemm_kernel(GatherGeom gg, const S* __restrict__ src,
+		const S* __restrict__ w, const S* __restrict__ bias, int bias_mode, S* __restrict__ out, int act_kind, S act_param,
+		S* __restrict__ act_out) {
+	extern __shared__ __align__(16) unsigned char tiny_smem[];
+	S* ws = reinterpret_cast<S*>(tiny_smem);
+	const int T = gg.RH * gg.RW, R = gg.SC, J = gg.J, K = T * R;
+	for (int i = threadIdx.x; i < K * JT; i += 256) {
+		const int j = i % JT, k = i / JT, tap = k / R, r = k - tap * R;
+		ws[i] = j < J ? w[tap * gg.w_stap + r * gg.w_sr + j * gg.w_sj] : (S) 0;
+	}
+	__syncthreads();
+	const long long M = (long long) gg.N * gg.OH * gg.OW;
+	const long long m = (long long) blockIdx.x * 256 + threadIdx.x;
+	if (m >= M) return;
+	const int n = (int) (m % gg.N);
+	const long long pix = m / gg.N;
+	const int oh = (int) (pix % gg.OH), ow = (int) (pix / gg.OH);
+	const long long plane = (long long) gg.N * gg.SH * gg.SW;
+	S acc[JT];
+	#pragma unroll
+	for (int j = 0; j < JT; ++j) acc[j] = (S) 0;
+	for (int tap = 0; tap < T; ++tap) {
+		const int rw = tap / gg.RH, rh = tap - rw * gg.RH;
+		const int th = oh * gg.ah + rh * gg.bh + gg.ch, tw = ow * gg.aw + rw * gg.bw + gg.cw;
+		if (th < 0 || tw < 0 || th % gg.denh != 0 || tw % gg.denw != 0) continue;
+		const int ih = th / gg.denh, iw = tw / gg.denw;
+		if (ih >= gg.SH || iw >= gg.SW) continue;
+		const S* ps = src + n + (long long) gg.N * (ih + (long long) gg.SH * iw);
+		const S* pw = ws + tap * R * JT;
+		for (int r = 0; r < R; ++r) {
+			const S v = __ldg(ps + r * plane);
+			#pragma unroll
+			for (int j = 0; j < JT; ++j) acc[j] = fma(v, pw[r * JT + j], acc[j]);
+		}
+	}
+	const long long P = (long long) gg.OH * gg.OW;
+	#pragma unroll
+	for (int j = 0; j < JT; ++j) {
+		if (j >= J) break;
+		S v = acc[j];
+		if (bias_mode == 1) v += __ldg(bias + j);
+		else if (bias_mode == 2) v += __ldg(bias + pix + P * j);
+		if (out) out[m + M * j] = v;
+		if (act_out) act_out[m + M * j] = act_fwd_rt<S>(act_kind, v, act_param);
+	}
+}
+
+bool tiny_gather_gemm_supported(const GatherGeom& gg, size_t scalar_bytes) {
+	const long long K = (long long) gg.RH * gg.RW * gg.SC;
+	return gg.J <= 8 && K * 8 * (long long) scalar_bytes <= 40 * 1024;
+}
+
+template<typename S>
+int tiny_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* w, const S* bias, int bias_mode, S* out,
+		const EpilogueArgs* ep) {
+	const long long M = (long long) gg.N * gg.OH * gg.OW;
+	const bool act = ep && ep->act_kind != CATTL3_ACT_NONE;
+	CATTL3_REQUIRE(out || act, "gather GEMM: no output tensor");
+	const int K = gg.RH * gg.RW * gg.SC;
+	const int JT = gg.J <= 1 ? 1 : (gg.J <= 2 ? 2 : (gg.J <= 4 ? 4 : 8));
+	const unsigned grid = (unsigned) ceil_div(M, 256);
+	const size_t smem = (size_t) K * JT * sizeof(S);
+	const int kind = act ? ep->act_kind : CATTL3_ACT_NONE;
+	const S ap = act ? (S) ep->act_param : (S) 0;
+	S* ao = act ? (S*) ep->act_out : nullptr;
+#define LAUNCH(JTV) tiny_gather_gemm_kernel<S, JTV><<<grid, 256, smem, ctx->stream>>>(gg, src, w, bias, bias_mode, out, kind, ap, ao)
+	if (JT == 1) LAUNCH(1); else if (JT == 2) LAUNCH(2); else if (JT == 4) LAUNCH(4); else LAUNCH(8);
+#undef LAUNCH
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+template int tiny_gather_gemm<float>(cattl3_ctx*, const GatherGeom&, const float*, const float*, const float*, int, float*,
+		const EpilogueArgs*);
+template int tiny_gather_gemm<double>(cattl3_ctx*, const GatherGeom&, const double*, const double*, const double*, int, double*,
+		const EpilogueArgs*);
+
+// tiny_wgrad_kernel: the whole K x J gradient (K = taps * channels <= 256, K * J <= 2048) is one CTA's
+// output; the CTAs split the reduction over m.  Per chunk of MC rows the gathered source rows [MC][K]
+// and the plain rows [MC][J] go to shared memory (coalesced along m), then every thread adds the chunk
+// into its <= 8 outputs.  Partials per CTA, deterministic reduce (wgrad_reduce_kernel).
+template<typename S>
+__global__ void __launch_bounds__(256) tiny_wgrad_kernel(GatherGeom gg, const S* __restrict__ src,
+		const S* __restrict__ plain, S* __restrict__ partial, long long m_per_cta, long long dw_elems) {
+	constexpr int MC = 32;
+	extern __shared__ __align__(16) unsigned char tiny_smem[];
+	const int T = gg.RH * gg.RW, R = gg.SC, J = gg.J, K = T * R, KJ = K * J;
+	const int Kp = K | 1;   // odd pitch: the transposing stores spread over the banks
+	S* As = reinterpret_cast<S*>(tiny_smem);       // [MC][Kp]
+	S* Bs = As + MC * Kp;                           // [MC][J]
+	int* ktab = reinterpret_cast<int*>(Bs + MC * J); // per k: rh*bh + ch (16 bits) | rw*bw + cw (16 bits), and the channel
+	for (int k = threadIdx.x; k < K; k += 256) {
+		const int tap = k / R, r = k - tap * R, rw = tap / gg.RH, rh = tap - rw * gg.RH;
+		ktab[2 * k] = ((rh * gg.bh + gg.ch) << 16) | ((rw * gg.bw + gg.cw) & 0xFFFF);
+		ktab[2 * k + 1] = r;
+	}
+	const long long M = (long long) gg.N * gg.OH * gg.OW;
+	const long long ms = (long long) blockIdx.x * m_per_cta;
+	const long long me = ms + m_per_cta < M ? ms + m_per_cta : M;
+	const long long plane = (long long) gg.N * gg.SH * gg.SW;
+	const int mm = threadIdx.x % MC, l0 = threadIdx.x / MC;   // loader: row mm of the chunk, items l0 + 8 * i
+	S acc[8];
+	#pragma unroll
+	for (int i = 0; i < 8; ++i) acc[i] = (S) 0;
+	__syncthreads();
+	for (long long mc = ms; mc < me; mc += MC) {
+		const long long m = mc + mm;
+		const bool ok = m < me;
+		const int n = (int) (m % gg.N);
+		const long long pix = m / gg.N;
+		const int oh = (int) (pix % gg.OH), ow = (int) (pix / gg.OH);
+		for (int k = l0; k < K; k += 256 / MC) {
+			const int packed = ktab[2 * k];
+			const int th = oh * gg.ah + (packed >> 16), tw = ow * gg.aw + (int) (short) (packed & 0xFFFF);
+			S v = (S) 0;
+			if (ok && th >= 0 && tw >= 0 && th < gg.SH && tw < gg.SW)   // forward-style gathers only (denh = denw = 1)
+				v = __ldg(src + n + (long long) gg.N * (th + (long long) gg.SH * tw) + ktab[2 * k + 1] * plane);
+			As[mm * Kp + k] = v;
+		}
+		for (int j = l0; j < J; j += 256 / MC) Bs[mm * J + j] = ok ? __ldg(plain + m + M * j) : (S) 0;
+		__syncthreads();
+		#pragma unroll
+		for (int i = 0; i < 8; ++i) {
+			const int o = threadIdx.x + 256 * i;
+			if (o < KJ) {
+				const int j = o / K, k = o - j * K;
+				S a = acc[i];
+				#pragma unroll 8
+				for (int r = 0; r < MC; ++r) a = fma(As[r * Kp + k], Bs[r * J + j], a);
+				acc[i] = a;
+			}
+		}
+		__syncthreads();
+	}
+	S* dst = partial + (long long) blockIdx.x * dw_elems;
+	#pragma unroll
+	for (int i = 0; i < 8; ++i) {
+		const int o = threadIdx.x + 256 * i;
+		if (o < KJ) {
+			const int j = o / K, k = o - j * K, tap = k / R, r = k - tap * R;
+			dst[tap * gg.w_stap + r * gg.w_sr + j * gg.w_sj] = acc[i];
+		}
+	}
+}
+
+bool tiny_wgrad_supported(const GatherGeom& gg, size_t scalar_bytes) {
+	const long long K = (long long) gg.RH * gg.RW * gg.SC;
+	const long long M = (long long) gg.N * gg.OH * gg.OW;
+	const long long smem = (32 * ((K | 1) + gg.J)) * (long long) scalar_bytes + 8 * K;
+	// |rh*bh + ch| and |rw*bw + cw| are packed into 16 bits each
+	const long long reach = (long long) (gg.RH > gg.RW ? gg.RH : gg.RW) * (gg.bh > gg.bw ? gg.bh : gg.bw) + gg.SH + gg.SW;
+	return gg.J <= 32 && K <= 256 && K * gg.J <= 2048 && smem <= 44 * 1024 && gg.denh == 1 && gg.denw == 1 && M >= 512 &&
+			reach < 30000 && gg.bh > 0 && gg.bw > 0;
+}
+
+template<typename S>
+int tiny_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* plain, S* dw) {
+	const int K = gg.RH * gg.RW * gg.SC;
+	const long long M = (long long) gg.N * gg.OH * gg.OW;
+	const long long elems = (long long) K * gg.J;
+	long long ctas = ceil_div(M, 512);
+	if (ctas > 4ll * ctx->sm_count) ctas = 4ll * ctx->sm_count;
+	const long long m_per_cta = ceil_div(ceil_div(M, ctas), 32) * 32;
+	ctas = ceil_div(M, m_per_cta);
+	CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, (size_t) (ctas * elems) * sizeof(S)));
+	const size_t smem = (size_t) (32 * ((K | 1) + gg.J)) * sizeof(S) + 8 * (size_t) K;
+	tiny_wgrad_kernel<S><<<(unsigned) ctas, 256, smem, ctx->stream>>>(gg, src, plain, (S*) ctx->ws, m_per_cta, elems);
+	CATTL3_LAUNCHED(ctx);
+	wgrad_reduce_kernel<S><<<ew_grid(ctx, elems, 256), 256, 0, ctx->stream>>>((const S*) ctx->ws, (int) ctas, elems, dw);
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+template int tiny_wgrad<float>(cattl3_ctx*, const GatherGeom&, const float*, const float*, float*);
+template int tiny_wgrad<double>(cattl3_ctx*, const GatherGeom&, const double*, const double*, double*);
+
+// ------------------------------------------------------------------------------------------------
 // out[col] += sum_{row} a[row + rows*col]   (bias gradients: ConvKernelLayer.hpp:155,
 // TransConvKernelLayer.hpp:160-161, DenseKernelLayer.hpp:109).  Fixed reduction tree => deterministic.
 // ------------------------------------------------------------------------------------------------

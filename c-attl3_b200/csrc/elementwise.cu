@@ -997,13 +997,21 @@ int dropout_backward(cattl3_ctx* ctx, int64_t count, S prob, S eps, const S* dy,
 // ---- losses (C-ATTL3/loss/SquaredLoss.hpp:25-34, CrossEntropyLoss.hpp:33-42, UniversalLoss.hpp:24-58) ----
 // out, obj: rows x vol (rows = batch, fastest).  loss[r] = sum_j (out - obj)^2  |  -sum_j log(out + eps) * obj;
 // grad = 2 (out - obj)  |  -obj / (out + eps), divided by grad_div (the batch loop's nominal batch size,
-// SGDOptimizer.hpp:55-56).  One thread per row keeps a warp's accesses coalesced.
+// SGDOptimizer.hpp:55-56).
+// A CTA = 32 rows x 8 column lanes over one chunk of columns: loads and stores are coalesced along the rows, the per-row
+// loss of the chunk is reduced over the column lanes in shared memory and written to partial[chunk][row]; the chunks
+// are then added in order (deterministic).  One thread per row would leave a 512-row batch with 512 threads.
 template<typename S, int KIND>
-__global__ void __launch_bounds__(128) loss_kernel(long long rows, long long vol, S eps, S grad_div,
-		const S* __restrict__ out, const S* __restrict__ obj, S* __restrict__ loss, S* __restrict__ grad) {
-	for (long long r = blockIdx.x * 128ll + threadIdx.x; r < rows; r += (long long) gridDim.x * 128) {
-		S acc = 0;
-		for (long long j = 0; j < vol; ++j) {
+__global__ void __launch_bounds__(256) loss_kernel(long long rows, long long vol, long long chunk_cols, S eps, S grad_div,
+		const S* __restrict__ out, const S* __restrict__ obj, S* __restrict__ partial, S* __restrict__ grad) {
+	__shared__ S red[8][33];
+	const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+	const long long r = blockIdx.x * 32ll + tx;
+	const long long j0 = (long long) blockIdx.y * chunk_cols;
+	const long long j1 = j0 + chunk_cols < vol ? j0 + chunk_cols : vol;
+	S acc = 0;
+	if (r < rows) {
+		for (long long j = j0 + ty; j < j1; j += 8) {
 			const S o = out[r + rows * j], t = obj[r + rows * j];
 			if (KIND == CATTL3_LOSS_SQUARED) {
 				const S d = o - t;
@@ -1014,8 +1022,25 @@ __global__ void __launch_bounds__(128) loss_kernel(long long rows, long long vol
 				if (grad) grad[r + rows * j] = (-t / (o + eps)) / grad_div;
 			}
 		}
-		if (loss) loss[r] = KIND == CATTL3_LOSS_SQUARED ? acc : -acc;
 	}
+	red[ty][tx] = acc;
+	__syncthreads();
+	if (ty == 0 && r < rows && partial) {
+		S s = red[0][tx];
+		#pragma unroll
+		for (int k = 1; k < 8; ++k) s += red[k][tx];
+		partial[(long long) blockIdx.y * rows + r] = KIND == CATTL3_LOSS_SQUARED ? s : -s;
+	}
+}
+
+template<typename S>
+__global__ void __launch_bounds__(256) loss_sum_kernel(long long rows, int chunks, const S* __restrict__ partial,
+		S* __restrict__ loss) {
+	const long long r = blockIdx.x * 256ll + threadIdx.x;
+	if (r >= rows) return;
+	S s = 0;
+	for (int c = 0; c < chunks; ++c) s += partial[(long long) c * rows + r];
+	loss[r] = s;
 }
 
 template<typename S>
@@ -1023,16 +1048,29 @@ int loss_forward_backward(cattl3_ctx* ctx, int kind, int64_t rows, int64_t vol, 
 		const S* obj, S* loss, S* grad) {
 	CATTL3_CHECK(check_ctx(ctx));
 	CATTL3_REQUIRE(rows > 0 && vol > 0 && out && obj && (loss || grad) && grad_div != (S) 0, "loss: bad arguments");
-	const int grid = ew_grid(ctx, rows, 128);
-	if (kind == CATTL3_LOSS_SQUARED)
-		loss_kernel<S, CATTL3_LOSS_SQUARED><<<grid, 128, 0, ctx->stream>>>(rows, vol, eps, grad_div, out, obj, loss, grad);
-	else if (kind == CATTL3_LOSS_CROSS_ENTROPY)
-		loss_kernel<S, CATTL3_LOSS_CROSS_ENTROPY><<<grid, 128, 0, ctx->stream>>>(rows, vol, eps, grad_div, out, obj, loss, grad);
-	else {
-		set_error("loss: unknown kind %d", kind);
-		return CATTL3_ERR_INVALID;
+	CATTL3_REQUIRE(kind == CATTL3_LOSS_SQUARED || kind == CATTL3_LOSS_CROSS_ENTROPY, "loss: unknown kind %d", kind);
+	const long long row_blocks = ceil_div(rows, 32);
+	long long chunks = ceil_div(4ll * ctx->sm_count, row_blocks);
+	const long long max_chunks = ceil_div(vol, 16);
+	if (chunks > max_chunks) chunks = max_chunks;
+	if (chunks < 1) chunks = 1;
+	const long long chunk_cols = ceil_div(vol, chunks);
+	chunks = ceil_div(vol, chunk_cols);
+	S* partial = loss;
+	if (loss && chunks > 1) {
+		CATTL3_CHECK(ensure_buffer(ctx, &ctx->stat_ws, &ctx->stat_ws_bytes, sizeof(S) * (size_t) (chunks * rows)));
+		partial = (S*) ctx->stat_ws;
 	}
+	dim3 grid((unsigned) row_blocks, (unsigned) chunks);
+	if (kind == CATTL3_LOSS_SQUARED)
+		loss_kernel<S, CATTL3_LOSS_SQUARED><<<grid, 256, 0, ctx->stream>>>(rows, vol, chunk_cols, eps, grad_div, out, obj, partial, grad);
+	else
+		loss_kernel<S, CATTL3_LOSS_CROSS_ENTROPY><<<grid, 256, 0, ctx->stream>>>(rows, vol, chunk_cols, eps, grad_div, out, obj, partial, grad);
 	CATTL3_LAUNCHED(ctx);
+	if (loss && chunks > 1) {
+		loss_sum_kernel<S><<<(unsigned) ceil_div(rows, 256), 256, 0, ctx->stream>>>(rows, (int) chunks, partial, loss);
+		CATTL3_LAUNCHED(ctx);
+	}
 	return CATTL3_OK;
 }
 

@@ -24,8 +24,8 @@ def _tol(dt):
 # (case, dtype, path it must take)
 FUSED_CONV = [("c2_small", np.float32, "tcgen05"), ("c2_small_f256", np.float32, "tcgen05"),
               ("ragged_c", np.float32, "tcgen05"), ("c2_stride2", np.float32, "tcgen05"),
-              ("cifar_conv1", np.float32, "simt"), ("gt_rank3", np.float64, "simt"), ("c2_small", np.float64, "simt"),
-              ("ragged", np.float64, "simt")]
+              ("cifar_conv1", np.float32, "tiny"), ("gt_rank3", np.float64, "tiny"), ("c2_small", np.float64, "simt"),
+              ("ragged", np.float64, "tiny")]
 
 
 @pytest.mark.parametrize("name,dt,path", FUSED_CONV)

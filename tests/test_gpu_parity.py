@@ -365,3 +365,23 @@ def test_conv_ffma_vs_oracle(U, orc):
         assert a["path"] == "ffma", (name, a["path"])
         for k in ("y", "dx", "dw", "db"):
             assert C.relerr(a[k], r[k]) < C.TOL[np.dtype(np.float32)], (name, k, C.relerr(a[k], r[k]))
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+@pytest.mark.parametrize("tr", [False, True])
+def test_conv_tiny_channel_kernels_vs_oracle(U, orc, dt, tr):
+    """Configs 1 and 3 (1-8 filters / channels): the streaming kernels the AUTO path picks for them, every case of the
+    tables whose forward has at most 8 output columns, against the oracle; two backward passes (accumulation)."""
+    table = C.TCONV_CASES if tr else C.CONV_CASES
+    ran = 0
+    for name, case in table.items():
+        if case[4] > 8:
+            continue
+        g, x, w, b, dy = C.conv_inputs(case, dt, 74, tr)
+        r = orc.conv(g, x, w, b, dy, transposed=tr, back_reps=2)
+        a = _conv_gpu(U, case, x, w, b, dy, tr, reps=2, path=U.pkg.PATH_AUTO)
+        assert a["path"] == "tiny", (name, a["path"])
+        ran += 1
+        for k in ("y", "dx", "dw", "db"):
+            assert C.relerr(a[k], r[k]) < C.TOL[np.dtype(dt)], (name, k, C.relerr(a[k], r[k]))
+    assert ran >= 3
