@@ -216,6 +216,27 @@ class Context:
                    _p(running_inv_sd), _p(saved_mean), _p(saved_inv_sd), _p(y),
                    ACT_NONE if act_kind is None else int(act_kind), ct(act_param), _p(act_out))
 
+    def fill(self, count, value, y):
+        _, ct = _suffix(y.dtype)
+        self._call("cattl3_fill", y.dtype, ctypes.c_int64(count), ct(value), _p(y))
+
+    def throttle(self, max_in_flight=2):
+        self._chk(self.L.cattl3_ctx_throttle(self.h, int(max_in_flight)))
+
+    def feed_create(self, slots=3):
+        f = ctypes.c_void_p()
+        self._chk(self.L.cattl3_feed_create(ctypes.byref(f), self.h, int(slots)))
+        return f
+
+    def feed_push(self, feed, host_array):
+        """Stages a host numpy array through the feed; returns the device address of its slot."""
+        dev = ctypes.c_void_p()
+        self._chk(self.L.cattl3_feed_push(feed, _p(host_array), ctypes.c_size_t(host_array.nbytes), ctypes.byref(dev)))
+        return dev.value
+
+    def feed_destroy(self, feed):
+        self._chk(self.L.cattl3_feed_destroy(feed))
+
     def slice_rows(self, total, vol, first, rows, src, dst):
         self._call("cattl3_slice_rows", src.dtype, ctypes.c_int64(total), ctypes.c_int64(vol), ctypes.c_int64(first),
                    ctypes.c_int64(rows), _p(src), _p(dst))

@@ -163,7 +163,11 @@ simt:
 		set_error("tcgen05 path requested but the shape/type does not qualify (needs float, batch %% 32 == 0)");
 		return CATTL3_ERR_UNSUPPORTED;
 	}
-	if (ctx->conv_path != CATTL3_PATH_SIMT && tiny_gather_gemm_supported(gg, sizeof(S))) {
+	if (ctx->conv_path != CATTL3_PATH_SIMT && skinny_gather_gemm_supported(ctx, gg)) {
+		// a classifier head: small batch, long reduction, a few outputs -- split over the reduction
+		ctx->last_path = "skinny";
+		CATTL3_CHECK(skinny_gather_gemm<S>(ctx, gg, src, w, bias, bias_mode, out, ep));
+	} else if (ctx->conv_path != CATTL3_PATH_SIMT && tiny_gather_gemm_supported(gg, sizeof(S))) {
 		// a handful of output columns: the streaming kernel (conv_simt.cu)
 		ctx->last_path = "tiny";
 		CATTL3_CHECK(tiny_gather_gemm<S>(ctx, gg, src, w, bias, bias_mode, out, ep));

@@ -122,6 +122,11 @@ bool tiny_gather_gemm_supported(const GatherGeom& gg, size_t scalar_bytes);
 template<typename S>
 int tiny_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* w, const S* bias, int bias_mode, S* out,
 		const EpilogueArgs* ep = nullptr);
+// small batch x long reduction x <= 16 outputs (classifier heads): split-K dense forward
+bool skinny_gather_gemm_supported(const cattl3_ctx* ctx, const GatherGeom& gg);
+template<typename S>
+int skinny_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* w, const S* bias, int bias_mode, S* out,
+		const EpilogueArgs* ep = nullptr);
 bool tiny_wgrad_supported(const GatherGeom& gg, size_t scalar_bytes);
 template<typename S> int tiny_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* plain, S* dw);
 

@@ -339,6 +339,96 @@ template int tiny_gather_gemm<float>(cattl3_ctx*, const GatherGeom&, const float
 template int tiny_gather_gemm<double>(cattl3_ctx*, const GatherGeom&, const double*, const double*, const double*, int, double*,
 		const EpilogueArgs*);
 
+// skinny_gather_gemm_kernel: a dense layer over a small batch (M = N rows, a long reduction, J <= 16 outputs: the
+// classifier heads of configs 1 and 4) would be a single CTA walking K serially.  Here the reduction is split over
+// grid.y; every CTA keeps its slice of the weights in shared memory, a thread owns one row and JT partial outputs,
+// and skinny_reduce_kernel adds the slices in order (deterministic) and applies bias and activation.  T = 1 only.
+template<typename S, int JT>
+__global__ void __launch_bounds__(256) skinny_gather_gemm_kernel(GatherGeom gg, int k_per_slice, const S* __restrict__ src,
+		const S* __restrict__ w, S* __restrict__ partial) {
+	extern __shared__ __align__(16) unsigned char tiny_smem[];
+	S* ws = reinterpret_cast<S*>(tiny_smem);
+	const int R = gg.SC, J = gg.J;
+	const int k0 = blockIdx.y * k_per_slice, k1 = k0 + k_per_slice < R ? k0 + k_per_slice : R;
+	for (int i = threadIdx.x; i < (k1 - k0) * JT; i += 256) {
+		const int j = i % JT, r = k0 + i / JT;
+		ws[i] = j < J ? w[r * gg.w_sr + j * gg.w_sj] : (S) 0;
+	}
+	__syncthreads();
+	const long long M = (long long) gg.N * gg.OH * gg.OW;
+	const long long m = (long long) blockIdx.x * 256 + threadIdx.x;
+	if (m >= M) return;
+	// T = 1, stride 1, no padding (dense / 1x1): row m of the source is m itself
+	const long long plane = (long long) gg.N * gg.SH * gg.SW;
+	S acc[JT];
+	#pragma unroll
+	for (int j = 0; j < JT; ++j) acc[j] = (S) 0;
+	const S* ps = src + m + (long long) k0 * plane;
+	for (int r = 0; r < k1 - k0; ++r) {
+		const S v = __ldg(ps + r * plane);
+		#pragma unroll
+		for (int j = 0; j < JT; ++j) acc[j] = fma(v, ws[r * JT + j], acc[j]);
+	}
+	S* dst = partial + ((long long) blockIdx.y * J) * M + m;
+	#pragma unroll
+	for (int j = 0; j < JT; ++j)
+		if (j < J) dst[(long long) j * M] = acc[j];
+}
+
+template<typename S>
+__global__ void __launch_bounds__(256) skinny_reduce_kernel(long long M, int J, int slices, const S* __restrict__ partial,
+		const S* __restrict__ bias, int bias_mode, long long N, S* __restrict__ out, int act_kind, S act_param,
+		S* __restrict__ act_out) {
+	const long long total = M * J;
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long) gridDim.x * 256) {
+		S v = 0;
+		for (int z = 0; z < slices; ++z) v += partial[(long long) z * total + i];
+		const long long j = i / M, m = i - j * M;
+		if (bias_mode == 1) v += __ldg(bias + j);
+		else if (bias_mode == 2) v += __ldg(bias + m / N + (M / N) * j);
+		if (out) out[i] = v;
+		if (act_out) act_out[i] = act_fwd_rt<S>(act_kind, v, act_param);
+	}
+}
+
+bool skinny_gather_gemm_supported(const cattl3_ctx* ctx, const GatherGeom& gg) {
+	const long long M = (long long) gg.N * gg.OH * gg.OW;
+	return gg.RH == 1 && gg.RW == 1 && gg.J <= 16 && gg.SC >= 1024 && ceil_div(M, 256) * 4 <= ctx->sm_count &&
+			gg.SH == gg.OH && gg.SW == gg.OW && gg.ah == 1 && gg.aw == 1 && gg.ch == 0 && gg.cw == 0 && gg.denh == 1 && gg.denw == 1;
+}
+
+template<typename S>
+int skinny_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* w, const S* bias, int bias_mode, S* out,
+		const EpilogueArgs* ep) {
+	const long long M = (long long) gg.N * gg.OH * gg.OW;
+	const bool act = ep && ep->act_kind != CATTL3_ACT_NONE;
+	CATTL3_REQUIRE(out || act, "gather GEMM: no output tensor");
+	const int JT = gg.J <= 4 ? 4 : (gg.J <= 8 ? 8 : 16);
+	const long long row_blocks = ceil_div(M, 256);
+	long long slices = 2ll * ctx->sm_count / row_blocks;
+	const long long max_slices = ceil_div(gg.SC, 128);
+	if (slices > max_slices) slices = max_slices;
+	int k_per_slice = (int) ceil_div(gg.SC, slices);
+	if ((size_t) k_per_slice * JT * sizeof(S) > 40 * 1024) k_per_slice = (int) (40 * 1024 / (JT * sizeof(S)));
+	slices = ceil_div(gg.SC, k_per_slice);
+	CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, (size_t) (slices * M * gg.J) * sizeof(S)));
+	dim3 grid((unsigned) row_blocks, (unsigned) slices);
+	const size_t smem = (size_t) k_per_slice * JT * sizeof(S);
+#define LAUNCH(JTV) skinny_gather_gemm_kernel<S, JTV><<<grid, 256, smem, ctx->stream>>>(gg, k_per_slice, src, w, (S*) ctx->ws)
+	if (JT == 4) LAUNCH(4); else if (JT == 8) LAUNCH(8); else LAUNCH(16);
+#undef LAUNCH
+	CATTL3_LAUNCHED(ctx);
+	skinny_reduce_kernel<S><<<ew_grid(ctx, M * gg.J, 256), 256, 0, ctx->stream>>>(M, gg.J, (int) slices, (const S*) ctx->ws, bias,
+			bias_mode, gg.N, out, act ? ep->act_kind : CATTL3_ACT_NONE, act ? (S) ep->act_param : (S) 0,
+			act ? (S*) ep->act_out : (S*) nullptr);
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+template int skinny_gather_gemm<float>(cattl3_ctx*, const GatherGeom&, const float*, const float*, const float*, int, float*,
+		const EpilogueArgs*);
+template int skinny_gather_gemm<double>(cattl3_ctx*, const GatherGeom&, const double*, const double*, const double*, int, double*,
+		const EpilogueArgs*);
+
 // tiny_wgrad_kernel: the whole K x J gradient (K = taps * channels <= 256, K * J <= 2048) is one CTA's
 // output; the CTAs split the reduction over m.  Per chunk of MC rows the gathered source rows [MC][K]
 // and the plain rows [MC][J] go to shared memory (coalesced along m), then every thread adds the chunk

@@ -68,6 +68,8 @@ DENSE_CASES = {
     "mnist_fc": (32, 300, 100),
     "ragged": (7, 13, 3),
     "single": (1, 1, 1),
+    "head": (64, 3136, 10),     # a classifier head: small batch, long reduction, few outputs (split-K forward)
+    "head_ragged": (5, 1030, 3),
 }
 
 # (kind, alpha) -- kinds as CATTL3_ACT_*; test/gradient_test.cpp:215-282 uses 0.2 / 0.2 / 1.2

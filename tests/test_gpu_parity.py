@@ -87,6 +87,8 @@ def test_dense_vs_oracle(U, orc, dt):
         xd, wd, bd, dyd = U.dev(x), U.dev(w), U.dev(b), U.dev(dy)
         yd, dxd, dwd, dbd = U.zeros((n, o), dt), U.zeros((n, i), dt), U.zeros((i, o), dt), U.zeros((1, o), dt)
         c.dense_forward(n, i, o, xd, wd, bd, yd)
+        if name.startswith("head"):
+            assert c.last_path == "skinny", (name, c.last_path)   # split-K forward of a classifier head
         c.dense_backward(n, i, o, xd, wd, dyd, dwd, dbd, dxd)
         c.synchronize()
         got = dict(y=U.host(yd, (n, o)), dx=U.host(dxd, (n, i)), dw=U.host(dwd, (i, o)), db=U.host(dbd, (1, o)))
@@ -385,3 +387,83 @@ def test_conv_tiny_channel_kernels_vs_oracle(U, orc, dt, tr):
         for k in ("y", "dx", "dw", "db"):
             assert C.relerr(a[k], r[k]) < C.TOL[np.dtype(dt)], (name, k, C.relerr(a[k], r[k]))
     assert ran >= 3
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_slice_rows_and_fill(U, dt):
+    """Mini-batch rows out of a device-resident data set (MemoryDataProvider::get_data, :72-83) and device-side fill."""
+    c = U.ctx()
+    rng = np.random.default_rng(63)
+    for total, vol, first, rows in ((64, 7, 8, 16), (37, 5, 3, 11), (512, 12, 0, 512), (9, 1, 8, 1)):
+        data = C.rand(rng, (total, vol), dt)
+        src = U.dev(data)
+        dst = U.zeros((rows, vol), dt)
+        c.slice_rows(total, vol, first, rows, src, dst)
+        c.synchronize()
+        assert np.array_equal(U.host(dst, (rows, vol)), data[first:first + rows])
+    y = U.zeros((1000,), dt)
+    c.fill(1000, 2.5, y)
+    c.synchronize()
+    assert np.array_equal(U.host(y, (1000,)), np.full(1000, 2.5, dt))
+    with pytest.raises(U.pkg.Cattl3Error):
+        c.slice_rows(10, 3, 8, 5, src, dst)   # rows past the end of the data set
+
+
+def test_input_feed_ring(U):
+    """cattl3_feed: staged uploads on the copy stream.  Every push lands intact (also across the 8 MB staging chunks),
+    a slot stays valid for the next slots - 1 pushes while kernels on the compute stream consume it, and is then reused."""
+    import torch
+    c = U.ctx()
+    feed = c.feed_create(3)
+    rng = np.random.default_rng(64)
+    sizes = [1 << 10, 5 << 20, 3 << 10, (9 << 20) + 13, 1 << 10, 1 << 10, 7 << 20]   # floats; 5M, 9M, 7M floats cross chunks
+    addrs, sums = [], []
+    for i, n in enumerate(sizes):
+        host = rng.uniform(-1, 1, n).astype(np.float32)
+        addr = c.feed_push(feed, host)
+        addrs.append(addr)
+        # consume on the compute stream: copy the slot out
+        got = U.zeros((n,), np.float32)
+        U.pkg.lib().cattl3_memcpy_d2d(c.h, U.pkg._p(got), ctypes_ptr(addr), ctypes_size(4 * n))
+        c.synchronize()
+        assert np.array_equal(got.cpu().numpy(), host), i
+        host[:] = 0   # the source may be reused as soon as push returns
+    # sizes 0 / 3 / 6 share slot 0, which grew twice (a grown slot moves); 1 / 4 share slot 1, which did not grow
+    assert addrs[1] == addrs[4] and len(set(addrs[:3])) == 3
+    c.feed_destroy(feed)
+
+
+def ctypes_ptr(addr):
+    import ctypes
+    return ctypes.c_void_p(addr)
+
+
+def ctypes_size(n):
+    import ctypes
+    return ctypes.c_size_t(n)
+
+
+def test_c_abi_rejects_bad_arguments(U):
+    """Errors come back as status codes with a message, never as a crash: null tensors, zero sizes, geometry that
+    cannot be ("Errors")."""
+    c = U.ctx()
+    x = U.zeros((16,), np.float32)
+    g = U.pkg.ConvGeom(0, 4, 4, 1, 1, 3, 3, 1, 1, 1, 1, 0, 0)           # batch 0
+    with pytest.raises(U.pkg.Cattl3Error) as e:
+        c.conv_forward(g, x, x, x, x)
+    assert e.value.code == U.pkg.ERR_INVALID
+    g = U.pkg.ConvGeom(1, 2, 2, 1, 1, 5, 5, 0, 0, 1, 1, 0, 0)           # receptor larger than the padded input
+    with pytest.raises(U.pkg.Cattl3Error):
+        c.conv_forward(g, x, x, x, x)
+    g = U.pkg.ConvGeom(1, 4, 4, 1, 1, 3, 3, 1, 1, 1, 1, 0, 0)
+    with pytest.raises(U.pkg.Cattl3Error):
+        c.conv_forward(g, x, None, x, x)                                  # null weights
+    with pytest.raises(U.pkg.Cattl3Error):
+        c.activation_forward(99, 0.0, 4, 4, x, x)                         # unknown activation kind
+    with pytest.raises(U.pkg.Cattl3Error):
+        c.dense_forward(0, 4, 4, x, x, x, x)                              # empty batch
+    with pytest.raises(U.pkg.Cattl3Error):
+        c.loss(7, 4, 4, 0.0, 1.0, x, x, x, x)                             # unknown loss
+    with pytest.raises(U.pkg.Cattl3Error):
+        c.dropout_forward(16, 1.5, 1e-5, 1, x, x, x)                      # probability out of range
+    assert U.pkg.lib().cattl3_last_error()
