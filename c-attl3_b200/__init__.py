@@ -26,7 +26,7 @@ POOL = dict(max=0, mean=1)
 LOSS = dict(squared=0, cross_entropy=1)
 OPT = dict(sgd=0, momentum=1, nesterov=2, adagrad=3, rmsprop=4, adadelta=5, adam=6, adamax=7, nadam=8,
            amsgrad=9)
-PATH_AUTO, PATH_SIMT, PATH_TCGEN05 = 0, 1, 2
+PATH_AUTO, PATH_SIMT, PATH_TCGEN05, PATH_FMA = 0, 1, 2, 3
 
 
 class Cattl3Error(RuntimeError):

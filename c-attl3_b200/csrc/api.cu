@@ -114,13 +114,14 @@ static int run_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, 
 		int bias_mode, S* out, const EpilogueArgs* ep = nullptr) {
 	// ep: fused activation and / or column statistics.  The tcgen05 kernel does both in its epilogue; the SIMT kernel
 	// fuses the activation, and the statistics are then one reduction pass over the finished output.
-	if (IsFloat<S>::value && ctx->conv_path != CATTL3_PATH_SIMT && tc_gather_gemm_supported(ctx, gg)) {
+	const bool tensor_ok = ctx->conv_path != CATTL3_PATH_SIMT && ctx->conv_path != CATTL3_PATH_FMA;
+	if (IsFloat<S>::value && tensor_ok && tc_gather_gemm_supported(ctx, gg)) {
 		ctx->last_path = "tcgen05";
 		return tc_gather_gemm_f32(ctx, gg, (const float*) src, (const float*) w, (const float*) bias, bias_mode,
 				(float*) out, ep);
 	}
 	CATTL3_REQUIRE(!(ep && ep->col_stats) || (bias_mode == 1 && out), "column statistics need a per-column bias and y");
-	if (IsFloat<S>::value && ctx->conv_path != CATTL3_PATH_SIMT && (gg.denh > 1 || gg.denw > 1) && gg.ah == 1 && gg.aw == 1) {
+	if (IsFloat<S>::value && tensor_ok && (gg.denh > 1 || gg.denw > 1) && gg.ah == 1 && gg.aw == 1) {
 		// strided transposed gather (input gradient of a strided convolution, forward of a strided transposed
 		// convolution): denh * denw stride-1 sub-problems, one per residue class of the output pixel, each writing
 		// its own sub-lattice of the output through the tensor-core kernel
@@ -171,6 +172,11 @@ simt:
 		// a handful of output columns: the streaming kernel (conv_simt.cu)
 		ctx->last_path = "tiny";
 		CATTL3_CHECK(tiny_gather_gemm<S>(ctx, gg, src, w, bias, bias_mode, out, ep));
+	} else if (!IsFloat<S>::value && tensor_ok && dmma_gather_gemm_supported(gg)) {
+		// double at GEMM-sized shapes: FP64 tensor cores (conv_dmma.cu)
+		ctx->last_path = "dmma";
+		CATTL3_CHECK(dmma_gather_gemm(ctx, gg, (const double*) src, (const double*) w, (const double*) bias, bias_mode,
+				(double*) out, ep));
 	} else if (ctx->conv_path != CATTL3_PATH_SIMT && fma_gather_gemm_supported<S>(gg)) {
 		// GEMM-sized shapes off the tensor-core path (double; float with few channels or a ragged batch): the
 		// big-tile FMA kernels (conv_dfma.cu)
@@ -191,7 +197,8 @@ template<typename S>
 static int run_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* plain, S* dw, S* db_colsum = nullptr,
 		bool* db_done = nullptr) {
 	if (db_done) *db_done = false;
-	if (IsFloat<S>::value && ctx->conv_path != CATTL3_PATH_SIMT && tc_wgrad_supported(ctx, gg)) {
+	const bool tensor_ok = ctx->conv_path != CATTL3_PATH_SIMT && ctx->conv_path != CATTL3_PATH_FMA;
+	if (IsFloat<S>::value && tensor_ok && tc_wgrad_supported(ctx, gg)) {
 		ctx->last_path = "tcgen05";
 		if (db_done) *db_done = db_colsum != nullptr;
 		return tc_wgrad_f32(ctx, gg, (const float*) src, (const float*) plain, (float*) dw, (float*) db_colsum);
@@ -203,6 +210,10 @@ static int run_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const 
 	if (ctx->conv_path != CATTL3_PATH_SIMT && tiny_wgrad_supported(gg, sizeof(S))) {
 		ctx->last_path = "tiny";
 		return tiny_wgrad<S>(ctx, gg, src, plain, dw);
+	}
+	if (!IsFloat<S>::value && tensor_ok && dmma_wgrad_supported(gg)) {
+		ctx->last_path = "dmma";
+		return dmma_wgrad(ctx, gg, (const double*) src, (const double*) plain, (double*) dw);
 	}
 	if (ctx->conv_path != CATTL3_PATH_SIMT && fma_wgrad_supported<S>(gg)) {
 		ctx->last_path = IsFloat<S>::value ? "ffma" : "dfma";
@@ -405,7 +416,7 @@ int cattl3_ctx_synchronize(cattl3_ctx* ctx) {
 }
 
 int cattl3_ctx_set_conv_path(cattl3_ctx* ctx, int path) {
-	CATTL3_REQUIRE(ctx && path >= CATTL3_PATH_AUTO && path <= CATTL3_PATH_TCGEN05, "set_conv_path: bad arguments");
+	CATTL3_REQUIRE(ctx && path >= CATTL3_PATH_AUTO && path <= CATTL3_PATH_FMA, "set_conv_path: bad arguments");
 	ctx->conv_path = path;
 	return CATTL3_OK;
 }

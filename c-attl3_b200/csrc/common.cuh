@@ -138,6 +138,13 @@ int fma_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S
 template<typename S> bool fma_wgrad_supported(const GatherGeom& gg);
 template<typename S> int fma_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* plain, S* dw);
 
+// FP64 tensor-core path (conv_dmma.cu): mma.sync.m8n8k4.f64.
+bool dmma_gather_gemm_supported(const GatherGeom& gg);
+int dmma_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const double* src, const double* w, const double* bias,
+		int bias_mode, double* out, const EpilogueArgs* ep = nullptr);
+bool dmma_wgrad_supported(const GatherGeom& gg);
+int dmma_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const double* src, const double* plain, double* dw);
+
 // tcgen05 path (conv_tc.cu): returns CATTL3_ERR_UNSUPPORTED when the shape does not qualify.
 bool tc_gather_gemm_supported(const cattl3_ctx* ctx, const GatherGeom& gg);
 int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const float* w,

@@ -81,12 +81,17 @@ __global__ void __launch_bounds__(DF_THREADS, (TN == 4 || sizeof(S) == 4) ? 2 : 
 		for (int j = 0; j < TN; ++j) acc[i][j] = (S) 0;
 
 	const int T = gg.RH * gg.RW;
+	const bool unit_den = gg.denh == 1 && gg.denw == 1;
 	// Source address of (this thread's row, tap (rh, rw)), or null outside the tensor / off the stride lattice.
 	auto tap_src = [&](int rh, int rw) -> const S* {
 		const int th = aoh * gg.ah + rh * gg.bh + gg.ch;
 		const int tw = aow * gg.aw + rw * gg.bw + gg.cw;
-		if (!m_ok || th < 0 || tw < 0 || th % gg.denh != 0 || tw % gg.denw != 0) return nullptr;
-		const int ih = th / gg.denh, iw = tw / gg.denw;
+		if (!m_ok || th < 0 || tw < 0) return nullptr;
+		int ih = th, iw = tw;
+		if (!unit_den) {   // strided transposed gathers only: the divisions stay out of every other layer's loop
+			if (th % gg.denh != 0 || tw % gg.denw != 0) return nullptr;
+			ih = th / gg.denh; iw = tw / gg.denw;
+		}
 		if (ih >= gg.SH || iw >= gg.SW) return nullptr;
 		return src + an + (long long) gg.N * (ih + (long long) gg.SH * iw);
 	};

@@ -85,9 +85,11 @@ enum {
 
 /* Which kernel family a kernel-layer call may use (cattl3_ctx_set_conv_path). */
 enum {
-	CATTL3_PATH_AUTO = 0,       /* tcgen05 where the shape allows it (float only), else SIMT */
+	CATTL3_PATH_AUTO = 0,       /* float: tcgen05 where the shape allows it; double: FP64 tensor cores (DMMA); then the
+	                             * big-tile FMA, streaming ("tiny", "skinny") and small-tile SIMT kernels */
 	CATTL3_PATH_SIMT = 1,       /* FFMA / DFMA implicit GEMM (any shape, float and double) */
-	CATTL3_PATH_TCGEN05 = 2     /* TMA + tcgen05 3xTF32 implicit GEMM; CATTL3_ERR_UNSUPPORTED if not applicable */
+	CATTL3_PATH_TCGEN05 = 2,    /* TMA + tcgen05 3xTF32 implicit GEMM; CATTL3_ERR_UNSUPPORTED if not applicable */
+	CATTL3_PATH_FMA = 3         /* no tensor cores: the big-tile FFMA / DFMA kernels where they apply, else SIMT */
 };
 
 /*

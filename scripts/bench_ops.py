@@ -37,11 +37,13 @@ def main():
     ap.add_argument("--only", default="all", choices=["all", "conv", "mem", "fused"])
     ap.add_argument("--double", action="store_true", help="also run the double (DFMA) kernel-layer sweep")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 SIMT, 3 big-tile FMA (no tensor cores)")
     args = ap.parse_args()
     pkg = load_package()
     dev = torch.device("cuda", 0)
     stream = torch.cuda.current_stream()
     ctx = pkg.Context(0, stream.cuda_stream)
+    ctx.set_conv_path(args.path)
     pk = peaks()
     out = lambda d: print(json.dumps(d), flush=True)
 

@@ -331,30 +331,34 @@ DFMA_CASES = ["c2_small_f256", "c2_stride2", "c2_1x1", "dfma_odd", "dfma_mid", "
 
 
 @pytest.mark.parametrize("tr", [False, True])
-def test_conv_dfma_vs_oracle(U, orc, tr):
-    """The big-tile DFMA kernels (conv_dfma.cu): double, AUTO path, against the oracle at 1e-10; checks that the
-    DFMA path is the one that ran for the forward pass."""
+@pytest.mark.parametrize("path,name_of_path", [("AUTO", "dmma"), ("FMA", "dfma")])
+def test_conv_double_gemm_paths_vs_oracle(U, orc, tr, path, name_of_path):
+    """Double at GEMM-sized shapes against the oracle at 1e-10: the FP64 tensor-core kernels (conv_dmma.cu, what AUTO
+    picks) and the big-tile DFMA kernels (conv_dfma.cu, PATH_FMA); checks which one ran."""
     table = C.TCONV_CASES if tr else C.CONV_CASES
     names = ["dfma_t"] if tr else DFMA_CASES
+    sel = U.pkg.PATH_AUTO if path == "AUTO" else U.pkg.PATH_FMA
     for name in names:
         g, x, w, b, dy = C.conv_inputs(table[name], np.float64, 71, tr)
         r = orc.conv(g, x, w, b, dy, transposed=tr, back_reps=2)
-        a = _conv_gpu(U, table[name], x, w, b, dy, tr, reps=2, path=U.pkg.PATH_AUTO)
-        assert a["path"] == "dfma", (name, a["path"])
+        a = _conv_gpu(U, table[name], x, w, b, dy, tr, reps=2, path=sel)
+        assert a["path"] == name_of_path, (name, a["path"])
         for k in ("y", "dx", "dw", "db"):
             assert C.relerr(a[k], r[k]) < C.TOL[np.dtype(np.float64)], (name, k, C.relerr(a[k], r[k]))
 
 
 def test_conv_dfma_matches_simt_at_size(U):
-    """A mid-size double convolution (N=64, 14x14x64 -> 256, M = 12544, K = 576): the DFMA kernels against the
-    any-shape SIMT kernels, two independent implementations with different summation orders."""
+    """A mid-size double convolution (N=64, 14x14x64 -> 256, M = 12544, K = 576): the DMMA and DFMA kernels against the
+    any-shape SIMT kernels, three independent implementations with different summation orders."""
     case = (64, 14, 14, 64, 256, 3, 3, 1, 1, 1, 1, 0, 0)
     g, x, w, b, dy = C.conv_inputs(case, np.float64, 72)
     a = _conv_gpu(U, case, x, w, b, dy, False, path=U.pkg.PATH_AUTO)
+    f = _conv_gpu(U, case, x, w, b, dy, False, path=U.pkg.PATH_FMA)
     s = _conv_gpu(U, case, x, w, b, dy, False, path=U.pkg.PATH_SIMT)
-    assert a["path"] == "dfma" and s["path"] == "simt"
+    assert a["path"] == "dmma" and f["path"] == "dfma" and s["path"] == "simt"
     for k in ("y", "dx", "dw", "db"):
         assert C.relerr(a[k], s[k]) < 1e-13, (k, C.relerr(a[k], s[k]))
+        assert C.relerr(f[k], s[k]) < 1e-13, (k, C.relerr(f[k], s[k]))
 
 
 def test_conv_ffma_vs_oracle(U, orc):
