@@ -307,7 +307,8 @@ int dmma_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const double* src, const d
 	const int Ktot = gg.RH * gg.RW * gg.SC;
 	const long long M = (long long) gg.N * gg.OH * gg.OW;
 	const long long elems = (long long) Ktot * gg.J;
-	// here the wide tile wins (19.3 against 17.0 TFLOP/s at 256 filters): half as many passes over the gathered rows
+	// here the wide tile wins (19.3 against 17.0 TFLOP/s at 256 filters; a 512-thread 128 x 128 variant with 64 x 16 warp
+	// tiles measured 17.2): half as many passes over the gathered rows
 	const int BN = gg.J > 64 ? 128 : 64;
 	const long long gx = ceil_div(Ktot, DM_BM), gy = ceil_div(gg.J, BN);
 	long long splits = (long long) (BN == 128 ? 1 : 2) * ctx->sm_count / (gx * gy);
