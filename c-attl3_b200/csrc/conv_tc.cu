@@ -571,7 +571,11 @@ bool tc_gather_gemm_supported(const cattl3_ctx*, const GatherGeom& gg) {
 	if (gg.N % 32 != 0 || gg.denh != 1 || gg.denw != 1) return false;
 	// tiny reduce / filter counts cannot fill a tensor-core tile: those layers are HBM / latency
 	// bound and stay on the SIMT kernel ("Tiny-channel configs")
-	if (gg.SC < 16 || gg.J < 16) return false;
+	if (gg.J < 16) return false;
+	// few reduce channels are zero-padded to a 16-channel k-block (TMA fills out-of-bounds channels with zeros): worth it
+	// when the padding is cheaper than leaving the tensor cores -- a many-tap stem convolution (7x7 over 3 channels:
+	// 5.3x padded MMAs still beat the FFMA kernel), not a 1x1 over 3 channels
+	if (gg.SC < 16 && (gg.SC < 3 || gg.RH * gg.RW < 9 || getenv("CATTL3_NO_TC_STEM"))) return false;
 	return get_encode() != nullptr;
 }
 
@@ -600,7 +604,7 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 	const bool want_stats_early = ep && ep->col_stats;
 	const int BN = gg.J >= 256 ? (want_stats_early ? 128 : 256) : round_up(gg.J, 16);
 	// 32-element k-blocks (128 B weight rows) where shared and tensor memory allow four stages of them
-	const int KB = BN <= 128 ? 32 : 16;
+	const int KB = (BN <= 128 && gg.SC > 16) ? 32 : 16;
 	const int r_pad = round_up(gg.SC, KB);
 	// the A operand goes through registers into tensor memory, so its shared-memory image needs no MMA layout:
 	// take the longest contiguous run of batch entries TMA can deliver per row (up to 128 = 512 B)

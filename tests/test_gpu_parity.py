@@ -190,7 +190,8 @@ def test_optimizer_vs_golden(U, golden, dt):
             assert C.relerr(U.host(pd, p0.shape), golden[k + "p"]) < tol, (name, lam)
 
 
-TC_CASES = ["c2_small", "c2_small_f256", "c2_stride2", "c2_dil1", "c2_1x1", "ragged_c"]
+# "stem": 3 input channels, zero-padded to a 16-channel k-block by TMA out-of-bounds fill (forward on tcgen05)
+TC_CASES = ["c2_small", "c2_small_f256", "c2_stride2", "c2_dil1", "c2_1x1", "ragged_c", "stem"]
 
 
 def test_conv_tcgen05_vs_oracle(U, orc):
@@ -367,7 +368,7 @@ def test_conv_ffma_vs_oracle(U, orc):
     for name in ["stem", "stem_wide", "dfma_odd", "dfma_mid", "dfma_wide"]:
         g, x, w, b, dy = C.conv_inputs(C.CONV_CASES[name], np.float32, 73)
         r = orc.conv(g, x, w, b, dy, back_reps=2)
-        a = _conv_gpu(U, C.CONV_CASES[name], x, w, b, dy, False, reps=2, path=U.pkg.PATH_AUTO)
+        a = _conv_gpu(U, C.CONV_CASES[name], x, w, b, dy, False, reps=2, path=U.pkg.PATH_FMA)
         assert a["path"] == "ffma", (name, a["path"])
         for k in ("y", "dx", "dw", "db"):
             assert C.relerr(a[k], r[k]) < C.TOL[np.dtype(np.float32)], (name, k, C.relerr(a[k], r[k]))
