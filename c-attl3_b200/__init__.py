@@ -69,7 +69,7 @@ _SYMBOLS = [
     "cattl3_abi_version", "cattl3_last_error", "cattl3_device_count", "cattl3_ctx_create",
     "cattl3_ctx_destroy", "cattl3_ctx_synchronize", "cattl3_ctx_throttle", "cattl3_ctx_set_conv_path", "cattl3_ctx_launch_count",
     "cattl3_ctx_last_path", "cattl3_ctx_stream", "cattl3_malloc", "cattl3_free", "cattl3_memset",
-    "cattl3_memcpy_h2d", "cattl3_memcpy_d2h", "cattl3_memcpy_d2d", "cattl3_host_alloc", "cattl3_host_free",
+    "cattl3_memcpy_h2d", "cattl3_memcpy_d2h", "cattl3_memcpy_d2d", "cattl3_memcpy_2d", "cattl3_host_alloc", "cattl3_host_free",
     "cattl3_conv_output_dims", "cattl3_pool_output_dims", "cattl3_feed_create", "cattl3_feed_destroy", "cattl3_feed_push",
     "cattl3_conv_forward_host_f32", "cattl3_conv_backward_host_f32",
     "cattl3_comm_unique_id", "cattl3_comm_create", "cattl3_comm_create_from_env", "cattl3_comm_destroy",

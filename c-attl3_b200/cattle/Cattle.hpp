@@ -47,6 +47,7 @@
 #include "loss/SquaredLoss.hpp"
 #include "loss/CrossEntropyLoss.hpp"
 #include "neural_network/StackedNeuralNetwork.hpp"
+#include "neural_network/DenseNeuralNetwork.hpp"
 #include "data_provider/MemoryDataProvider.hpp"
 #include "neural_network/FeedforwardNeuralNetwork.hpp"
 #include "neural_network/ResidualNeuralNetwork.hpp"

@@ -558,6 +558,16 @@ int cattl3_memcpy_d2d(cattl3_ctx* ctx, void* dst, const void* src, size_t bytes)
 	CATTL3_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
 	return CATTL3_OK;
 }
+int cattl3_memcpy_2d(cattl3_ctx* ctx, void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t width, size_t height) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(dst && src && width > 0 && height > 0 && dst_pitch >= width && src_pitch >= width, "memcpy_2d: bad arguments");
+	if (height == 1 || (dst_pitch == width && src_pitch == width)) {
+		CATTL3_CUDA(cudaMemcpyAsync(dst, src, width * height, cudaMemcpyDeviceToDevice, ctx->stream));
+	} else {
+		CATTL3_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width, height, cudaMemcpyDeviceToDevice, ctx->stream));
+	}
+	return CATTL3_OK;
+}
 int cattl3_host_alloc(void** p, size_t bytes) {
 	CATTL3_REQUIRE(p, "host_alloc: null out pointer");
 	CATTL3_CUDA(cudaMallocHost(p, bytes ? bytes : 1));

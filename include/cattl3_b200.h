@@ -187,6 +187,10 @@ int cattl3_memset(cattl3_ctx* ctx, void* dev_ptr, int value, size_t bytes);
 int cattl3_memcpy_h2d(cattl3_ctx* ctx, void* dev_dst, const void* host_src, size_t bytes);
 int cattl3_memcpy_d2h(cattl3_ctx* ctx, void* host_dst, const void* dev_src, size_t bytes); /* synchronises */
 int cattl3_memcpy_d2d(cattl3_ctx* ctx, void* dev_dst, const void* dev_src, size_t bytes);
+/* `height` blocks of `width` bytes, device to device, with row pitches: joining / splitting tensors along a rank
+ * (DenseNeuralNetwork.hpp:131-160 concatenate / slice; a concatenation along rank r of these column-major tensors is
+ * one contiguous block per index of the ranks above r). */
+int cattl3_memcpy_2d(cattl3_ctx* ctx, void* dev_dst, size_t dst_pitch, const void* dev_src, size_t src_pitch, size_t width, size_t height);
 int cattl3_host_alloc(void** host_ptr, size_t bytes); /* pinned */
 int cattl3_host_free(void* host_ptr);
 
