@@ -48,6 +48,7 @@
 #include "loss/CrossEntropyLoss.hpp"
 #include "neural_network/StackedNeuralNetwork.hpp"
 #include "neural_network/DenseNeuralNetwork.hpp"
+#include "neural_network/ParallelNeuralNetwork.hpp"
 #include "data_provider/MemoryDataProvider.hpp"
 #include "neural_network/FeedforwardNeuralNetwork.hpp"
 #include "neural_network/ResidualNeuralNetwork.hpp"

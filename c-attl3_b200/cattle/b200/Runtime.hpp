@@ -159,6 +159,8 @@ template<> struct Api<S> { \
 		return cattl3_optimizer_step_##SUF(c, st, count, p, g, s1, s2, s3); } \
 	static int add_inplace(cattl3_ctx* c, std::int64_t count, S* y, const S* x) { \
 		return cattl3_add_inplace_##SUF(c, count, y, x); } \
+	static int mul_inplace(cattl3_ctx* c, std::int64_t count, S* y, const S* x) { \
+		return cattl3_mul_inplace_##SUF(c, count, y, x); } \
 	static int scale(cattl3_ctx* c, std::int64_t count, S alpha, const S* x, S* y) { \
 		return cattl3_scale_##SUF(c, count, alpha, x, y); } \
 	static int axpy(cattl3_ctx* c, std::int64_t count, S alpha, const S* x, S* y) { \

@@ -863,7 +863,7 @@ int optimizer_step(cattl3_ctx* ctx, const cattl3_opt_step* st, int64_t count, S*
 }
 
 // ---- glue ----------------------------------------------------------------------------------------
-// y = OP(x, y) over 16-byte vectors with a scalar tail; OP 0: y + x, 1: x * alpha, 2: fma(alpha, x, y)
+// y = OP(x, y) over 16-byte vectors with a scalar tail; OP 0: y + x, 1: x * alpha, 2: fma(alpha, x, y), 3: y * x
 template<typename S, int OP>
 __global__ void __launch_bounds__(256) glue_kernel(long long count, int vec_ok, S alpha, const S* __restrict__ x, S* __restrict__ y) {
 	typedef typename V16<S>::type V;
@@ -875,11 +875,11 @@ __global__ void __launch_bounds__(256) glue_kernel(long long count, int vec_ok, 
 		if (OP != 1) vy = reinterpret_cast<V*>(y)[i];
 		S* ex = reinterpret_cast<S*>(&vx); S* ey = reinterpret_cast<S*>(&vy);
 		#pragma unroll
-		for (int k = 0; k < G; ++k) ey[k] = OP == 0 ? ey[k] + ex[k] : (OP == 1 ? ex[k] * alpha : fma(alpha, ex[k], ey[k]));
+		for (int k = 0; k < G; ++k) ey[k] = OP == 0 ? ey[k] + ex[k] : (OP == 1 ? ex[k] * alpha : (OP == 2 ? fma(alpha, ex[k], ey[k]) : ey[k] * ex[k]));
 		reinterpret_cast<V*>(y)[i] = vy;
 	}
 	for (long long i = nvec * G + blockIdx.x * 256ll + threadIdx.x; i < count; i += stride)
-		y[i] = OP == 0 ? y[i] + x[i] : (OP == 1 ? x[i] * alpha : fma(alpha, x[i], y[i]));
+		y[i] = OP == 0 ? y[i] + x[i] : (OP == 1 ? x[i] * alpha : (OP == 2 ? fma(alpha, x[i], y[i]) : y[i] * x[i]));
 }
 template<typename S, int OP>
 static int glue(cattl3_ctx* ctx, const char* what, int64_t count, S alpha, const S* x, S* y) {
@@ -893,6 +893,7 @@ static int glue(cattl3_ctx* ctx, const char* what, int64_t count, S alpha, const
 template<typename S> int axpy(cattl3_ctx* ctx, int64_t count, S alpha, const S* x, S* y) { return glue<S, 2>(ctx, "axpy", count, alpha, x, y); }
 template<typename S> int add_inplace(cattl3_ctx* ctx, int64_t count, S* y, const S* x) { return glue<S, 0>(ctx, "add_inplace", count, (S) 0, x, y); }
 template<typename S> int scale(cattl3_ctx* ctx, int64_t count, S alpha, const S* x, S* y) { return glue<S, 1>(ctx, "scale", count, alpha, x, y); }
+template<typename S> int mul_inplace(cattl3_ctx* ctx, int64_t count, S* y, const S* x) { return glue<S, 3>(ctx, "mul_inplace", count, (S) 0, x, y); }
 
 // y[i] = value: device-side constants (e.g. the element count that travels with synchronised batch-norm sums) without a
 // host -> device copy, which from pageable memory would synchronise the host with the stream.
@@ -1149,6 +1150,8 @@ int cattl3_optimizer_step_f64(cattl3_ctx* c, const cattl3_opt_step* st, int64_t 
 
 int cattl3_add_inplace_f32(cattl3_ctx* c, int64_t count, float* y, const float* x) { return add_inplace<float>(c, count, y, x); }
 int cattl3_add_inplace_f64(cattl3_ctx* c, int64_t count, double* y, const double* x) { return add_inplace<double>(c, count, y, x); }
+int cattl3_mul_inplace_f32(cattl3_ctx* c, int64_t count, float* y, const float* x) { return mul_inplace<float>(c, count, y, x); }
+int cattl3_mul_inplace_f64(cattl3_ctx* c, int64_t count, double* y, const double* x) { return mul_inplace<double>(c, count, y, x); }
 int cattl3_scale_f32(cattl3_ctx* c, int64_t count, float alpha, const float* x, float* y) { return scale<float>(c, count, alpha, x, y); }
 int cattl3_scale_f64(cattl3_ctx* c, int64_t count, double alpha, const double* x, double* y) { return scale<double>(c, count, alpha, x, y); }
 int cattl3_axpy_f32(cattl3_ctx* c, int64_t count, float alpha, const float* x, float* y) { return axpy<float>(c, count, alpha, x, y); }

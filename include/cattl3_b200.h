@@ -359,6 +359,9 @@ int cattl3_optimizer_step_f64(cattl3_ctx*, const cattl3_opt_step*, int64_t count
 /* y += x (ResidualNeuralNetwork::propagate, C-ATTL3/neural_network/ResidualNeuralNetwork.hpp:112-117). */
 int cattl3_add_inplace_f32(cattl3_ctx*, int64_t count, float* y, const float* x);
 int cattl3_add_inplace_f64(cattl3_ctx*, int64_t count, double* y, const double* x);
+/* y *= x: the PARALLEL_MUL merge of ParallelNeuralNetwork (ParallelNeuralNetwork.hpp:170-173, 286-291). */
+int cattl3_mul_inplace_f32(cattl3_ctx*, int64_t count, float* y, const float* x);
+int cattl3_mul_inplace_f64(cattl3_ctx*, int64_t count, double* y, const double* x);
 /* y = alpha * x (the 1/batch_size scaling of the loss gradient, SGDOptimizer.hpp:55-56). */
 int cattl3_scale_f32(cattl3_ctx*, int64_t count, float alpha, const float* x, float* y);
 int cattl3_scale_f64(cattl3_ctx*, int64_t count, double alpha, const double* x, double* y);
