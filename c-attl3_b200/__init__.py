@@ -71,6 +71,7 @@ _SYMBOLS = [
     "cattl3_ctx_last_path", "cattl3_ctx_stream", "cattl3_malloc", "cattl3_free", "cattl3_memset",
     "cattl3_memcpy_h2d", "cattl3_memcpy_d2h", "cattl3_memcpy_d2d", "cattl3_memcpy_2d", "cattl3_host_alloc", "cattl3_host_free",
     "cattl3_conv_output_dims", "cattl3_pool_output_dims", "cattl3_feed_create", "cattl3_feed_destroy", "cattl3_feed_push",
+    "cattl3_ctx_allocated_bytes", "cattl3_graph_begin", "cattl3_graph_end", "cattl3_graph_launch", "cattl3_graph_destroy",
     "cattl3_conv_forward_host_f32", "cattl3_conv_backward_host_f32",
     "cattl3_comm_unique_id", "cattl3_comm_create", "cattl3_comm_create_from_env", "cattl3_comm_destroy",
     "cattl3_comm_world_size", "cattl3_comm_rank", "cattl3_comm_group_start", "cattl3_comm_group_end",
@@ -79,7 +80,7 @@ _SYMBOLS = [
     "cattl3_conv_forward", "cattl3_conv_backward", "cattl3_transconv_forward", "cattl3_transconv_backward",
     "cattl3_dense_forward", "cattl3_dense_backward", "cattl3_activation_forward", "cattl3_activation_backward",
     "cattl3_pool_forward", "cattl3_pool_backward", "cattl3_batchnorm_forward", "cattl3_batchnorm_backward",
-    "cattl3_optimizer_step", "cattl3_add_inplace", "cattl3_mul_inplace", "cattl3_scale", "cattl3_axpy",
+    "cattl3_optimizer_step", "cattl3_optimizer_step_indirect", "cattl3_add_inplace", "cattl3_mul_inplace", "cattl3_scale", "cattl3_axpy",
     "cattl3_conv_forward_fused", "cattl3_dense_forward_fused", "cattl3_transconv_forward_fused", "cattl3_batchnorm_forward_stats",
     "cattl3_dropout_forward", "cattl3_dropout_backward", "cattl3_loss",
     "cattl3_batchnorm_stats", "cattl3_batchnorm_backward_sums", "cattl3_batchnorm_backward_apply",

@@ -24,6 +24,9 @@ public:
 	 * The next mini-batch of up to `batch_size` instances, as DataProvider::get_data would return it, but only the
 	 * rows [n * rank / world, n * (rank + 1) / world) of its n instances (the data-parallel shard), on the device.
 	 *
+	 * Tensors that arrive with exactly the shard's shape are overwritten in place instead of being replaced (the fixed
+	 * input buffers of a captured training step); pass empty tensors otherwise.
+	 *
 	 * @return n, the number of instances the whole mini-batch has; the tensors are empty if the shard is.
 	 */
 	virtual std::size_t next_batch_dev(std::size_t batch_size, std::size_t rank, std::size_t world,

@@ -157,6 +157,8 @@ template<> struct Api<S> { \
 		return cattl3_batchnorm_backward_##SUF(c, pc, n, h, w, ch, x, gamma, sm, ss, dy, dg, db, dx); } \
 	static int optimizer_step(cattl3_ctx* c, const cattl3_opt_step* st, std::int64_t count, S* p, S* g, S* s1, S* s2, S* s3) { \
 		return cattl3_optimizer_step_##SUF(c, st, count, p, g, s1, s2, s3); } \
+	static int optimizer_step_indirect(cattl3_ctx* c, int kind, const cattl3_opt_step* dev, std::int64_t count, S* p, S* g, S* s1, S* s2, S* s3) { \
+		return cattl3_optimizer_step_indirect_##SUF(c, kind, dev, count, p, g, s1, s2, s3); } \
 	static int add_inplace(cattl3_ctx* c, std::int64_t count, S* y, const S* x) { \
 		return cattl3_add_inplace_##SUF(c, count, y, x); } \
 	static int mul_inplace(cattl3_ctx* c, std::int64_t count, S* y, const S* x) { \

@@ -110,8 +110,8 @@ public:
 			throw b200::Error(CATTL3_ERR_UNSUPPORTED, "MemoryDataProvider: the data set is not device resident");
 		const std::size_t rows = std::min(batch_size, instances - offset);
 		const std::size_t lo = rows * rank / world, hi = rows * (rank + 1) / world;
-		obs_batch = cut(dev_obs, (std::size_t) obs->size() / instances, offset + lo, hi - lo);
-		obj_batch = cut(dev_obj, (std::size_t) obj->size() / instances, offset + lo, hi - lo);
+		cut(dev_obs, (std::size_t) obs->size() / instances, offset + lo, hi - lo, obs_batch);
+		cut(dev_obj, (std::size_t) obj->size() / instances, offset + lo, hi - lo, obj_batch);
 		offset += rows;
 		return rows;
 	}
@@ -128,17 +128,19 @@ private:
 			std::memcpy(dst + j * rows, src + j * instances, rows * sizeof(Scalar));
 		return batch;
 	}
-	inline b200::DeviceTensor<Scalar> cut(const b200::DeviceBuffer<Scalar>& data, std::size_t volume, std::size_t first,
-			std::size_t rows) const {
-		b200::DeviceTensor<Scalar> batch;
-		if (rows == 0)
-			return batch;
-		batch = b200::DeviceTensor<Scalar>(rows, volume);
+	/** `batch` is overwritten in place if it arrives with the slice's shape (DeviceDataSource.hpp), else replaced. */
+	inline void cut(const b200::DeviceBuffer<Scalar>& data, std::size_t volume, std::size_t first, std::size_t rows,
+			b200::DeviceTensor<Scalar>& batch) const {
+		if (rows == 0) {
+			batch = b200::DeviceTensor<Scalar>();
+			return;
+		}
+		if (batch.rows != rows || batch.size() != rows * volume)
+			batch = b200::DeviceTensor<Scalar>(rows, volume);
 		b200::Context& c = b200::Context::get();
 		b200::Context::Lock l = c.lock();
 		CATTLE_B200_CHECK(b200::Api<Scalar>::slice_rows(c.handle(), (std::int64_t) instances, (std::int64_t) volume,
 				(std::int64_t) first, (std::int64_t) rows, data.data(), batch.data()));
-		return batch;
 	}
 	/** The reference's shuffle (:96-107): row i moves to position p[i], p = std::random_shuffle of the identity. */
 	inline void shuffle_rows() {

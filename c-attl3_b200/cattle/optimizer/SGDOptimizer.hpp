@@ -40,6 +40,7 @@
 #include "b200/DeviceLoss.hpp"
 #include "b200/DeviceNetwork.hpp"
 #include "b200/Runtime.hpp"
+#include "layer/DropoutLayer.hpp"
 
 namespace cattle {
 
@@ -64,6 +65,10 @@ public:
 		target_net_ptr = &net;
 		device_states.clear();
 		host_states.clear();
+		drop_graph();
+		carried_graph_loss = 0;
+		graphs_failed = false;
+		eager_steps_at_shape = 0;
 		std::vector<Parameters<Scalar>*> params_vec = net.get_all_unique_params();
 		pack_parameters(params_vec);
 		_fit(params_vec);
@@ -84,11 +89,42 @@ protected:
 				dynamic_cast<b200::DeviceDataSource<Scalar>*>(&training_prov) : nullptr;
 		if (dev_data && !dev_data->device_resident())
 			dev_data = nullptr;
+		const bool use_graphs = dev_data != nullptr && graph_eligible(net, params_vec);
 		while (training_prov.has_more()) {
 			if (dev_data) {
 				// the data set lives in HBM: the (shard of the) mini-batch is cut out on the device
 				b200::DeviceTensor<Scalar> obs, obj;
+				if (graph && use_graphs) {
+					// a nominal mini-batch is cut straight into the step graph's input buffers
+					obs.buf = graph->obs; obs.rows = graph->rows;
+					obj.buf = graph->obj; obj.rows = graph->rows;
+				}
 				instances += dev_data->next_batch_dev(batch_size, comm.rank(), comm.world_size(), obs, obj);
+				if (!obs.empty() && use_graphs && !graphs_failed) {
+					// launch-bound steps: after two eager steps at a shape (every scratch buffer has its size, BatchNorm
+					// has seen a batch) the step is captured as a CUDA graph and replayed
+					if (graph && graph->rows != obs.rows && obs.rows == batch_size)
+						drop_graph();   // the nominal batch changed shape: capture again
+					if (!graph && obs.rows == batch_size) {
+						if (eager_shape_rows != obs.rows) {
+							eager_shape_rows = obs.rows;
+							eager_steps_at_shape = 0;
+						}
+						if (eager_steps_at_shape >= 2)
+							graph.reset(new StepGraph(obs.rows, obs.size(), obj.size()));
+					}
+					if (graph && graph->rows == obs.rows &&
+							graph_step(*dev_net, *dev_loss, net, params_vec, obs, obj, epoch)) {
+						++updates;
+						++timestep;
+						b200::Context& c = b200::Context::get();
+						b200::Context::Lock l = c.lock();
+						CATTLE_B200_CHECK(cattl3_ctx_throttle(c.handle(), 2));
+						continue;
+					}
+					++eager_steps_at_shape;
+				}
+				const std::int64_t allocated_before = cattl3_ctx_allocated_bytes(b200::Context::get().handle());
 				if (!obs.empty()) {
 					b200::DeviceTensor<Scalar> out = dev_net->propagate_dev(std::move(obs), true);
 					step_losses.emplace_back();
@@ -97,6 +133,8 @@ protected:
 					dev_net->backpropagate_dev(std::move(out_grad));
 				}
 				finish_step(params_vec, comm, epoch, reg_loss, updates);
+				// what one step takes from cattl3_malloc: the size of a step graph's arena
+				eager_step_bytes = (std::size_t) (cattl3_ctx_allocated_bytes(b200::Context::get().handle()) - allocated_before);
 				continue;
 			}
 			DataPair<Scalar,Rank,Sequential> data_pair = training_prov.get_data(batch_size);
@@ -123,6 +161,8 @@ protected:
 			}
 			finish_step(params_vec, comm, epoch, reg_loss, updates);
 		}
+		obj_loss += collect_graph_loss() + carried_graph_loss;
+		carried_graph_loss = 0;
 		for (const b200::DeviceBuffer<Scalar>& losses : step_losses) {
 			std::vector<Scalar> host(losses.size());
 			losses.download(host.data(), host.size());
@@ -189,6 +229,11 @@ protected:
 	inline void fused_step(const std::vector<Parameters<Scalar>*>& params_vec, cattl3_opt_step step) {
 		step.reset_grad = 1;
 		step.l2_lambda = 0;  // Parameters::regularize() has already added the penalty's derivative
+		if (step_mode == STEP_SCALARS_ONLY) {
+			// a step graph replays the launches; only this step's scalars travel (one small upload from pinned memory)
+			graph->publish_scalars(step);
+			return;
+		}
 		struct Run { B200Parameters<Scalar>* first; std::size_t count; std::vector<B200Parameters<Scalar>*> members; };
 		std::vector<Run> runs;
 		b200::Context& c = b200::Context::get();
@@ -225,9 +270,15 @@ protected:
 			}
 			{
 				b200::Context::Lock l = c.lock();
-				CATTLE_B200_CHECK(b200::Api<Scalar>::optimizer_step(c.handle(), &step, (std::int64_t) run.count,
-						run.first->device_values(), run.first->device_grad(), state[0].data(), state[1].data(),
-						state[2].data()));
+				if (step_mode == STEP_CAPTURE) {
+					CATTLE_B200_CHECK(b200::Api<Scalar>::optimizer_step_indirect(c.handle(), step.kind, graph->device_scalars(),
+							(std::int64_t) run.count, run.first->device_values(), run.first->device_grad(), state[0].data(),
+							state[1].data(), state[2].data()));
+				} else {
+					CATTLE_B200_CHECK(b200::Api<Scalar>::optimizer_step(c.handle(), &step, (std::int64_t) run.count,
+							run.first->device_values(), run.first->device_grad(), state[0].data(), state[1].data(),
+							state[2].data()));
+				}
 			}
 			for (B200Parameters<Scalar>* member : run.members) {
 				member->values_written_on_device();
@@ -248,6 +299,211 @@ protected:
 	const std::size_t batch_size;
 private:
 	typedef std::array<b200::DeviceBuffer<Scalar>,3> StateArrays;
+	enum StepMode { STEP_EAGER, STEP_SCALARS_ONLY, STEP_CAPTURE };
+	/**
+	 * A training step captured as a CUDA graph (cattl3_graph, include/cattl3_b200.h): forward, loss, backward and the
+	 * fused update of one mini-batch shape, replayed with a single launch.  The mini-batch is copied into fixed input
+	 * buffers in front of the graph, the optimizer's step scalars go through a device struct fed from a ring of pinned
+	 * slots, the per-sample losses are accumulated on the device.
+	 */
+	struct StepGraph {
+		inline StepGraph(std::size_t rows, std::size_t obs_count, std::size_t obj_count) :
+				graph(nullptr),
+				rows(rows),
+				obs(std::make_shared<b200::DeviceBuffer<Scalar>>(obs_count)),
+				obj(std::make_shared<b200::DeviceBuffer<Scalar>>(obj_count)),
+				loss_rows(rows),
+				loss_accum(rows, true),
+				dev_scalars(1),
+				pinned(nullptr),
+				slot(0) {
+			void* p = nullptr;
+			CATTLE_B200_CHECK(cattl3_host_alloc(&p, SLOTS * sizeof(cattl3_opt_step)));
+			pinned = static_cast<cattl3_opt_step*>(p);
+		}
+		inline ~StepGraph() {
+			if (graph && trace())
+				std::cerr << "cattl3: step graph of " << rows << " rows destroyed after " << replays << " replays" << std::endl;
+			b200::Context::Lock l = b200::Context::get().lock();
+			cattl3_graph_destroy(graph);
+			cattl3_host_free(pinned);
+		}
+		StepGraph(const StepGraph&) = delete;
+		StepGraph& operator=(const StepGraph&) = delete;
+		inline void publish_scalars(const cattl3_opt_step& step) {
+			// the slot is reused four steps later; the loop keeps the host at most two steps ahead of the device
+			pinned[slot] = step;
+			b200::Context& c = b200::Context::get();
+			b200::Context::Lock l = c.lock();
+			CATTLE_B200_CHECK(cattl3_memcpy_h2d(c.handle(), dev_scalars.data(), &pinned[slot], sizeof(cattl3_opt_step)));
+			slot = (slot + 1) % SLOTS;
+		}
+		inline const cattl3_opt_step* device_scalars() const {
+			return dev_scalars.data();
+		}
+		/** CATTL3_GRAPH_TRACE=1: one line on stderr per capture and per destroyed graph. */
+		inline static bool trace() {
+			static const bool on = [] {
+				const char* v = std::getenv("CATTL3_GRAPH_TRACE");
+				return v && v[0] && v[0] != '0';
+			}();
+			return on;
+		}
+		static constexpr int SLOTS = 4;
+		std::size_t replays = 0;
+		cattl3_graph* graph;
+		std::size_t rows;
+		std::shared_ptr<b200::DeviceBuffer<Scalar>> obs, obj;   // the graph's fixed inputs
+		b200::DeviceBuffer<Scalar> loss_rows, loss_accum;
+		b200::DeviceBuffer<cattl3_opt_step> dev_scalars;
+		cattl3_opt_step* pinned;
+		int slot;
+	};
+	/**
+	 * Whether the training step of `net` can be captured: one process, every layer and every parameter on the device,
+	 * nothing whose host-side arguments change from step to step (dropout seeds) and nothing that reads parameters on
+	 * the host in the step (regularisation penalties, value or gradient constraints).  CATTL3_NO_GRAPH=1 disables it.
+	 */
+	inline static bool graph_eligible(typename Base::Net& net, const std::vector<Parameters<Scalar>*>& params_vec) {
+		static const bool enabled = [] {
+			const char* v = std::getenv("CATTL3_NO_GRAPH");
+			return !(v && v[0] && v[0] != '0');
+		}();
+		if (!enabled || Sequential || b200::Communicator::get().world_size() > 1)
+			return false;
+		for (Layer<Scalar,Rank>* layer : net.get_layers()) {
+			if (!dynamic_cast<b200::DeviceLayer<Scalar,Rank>*>(layer) || dynamic_cast<DropoutLayer<Scalar,Rank>*>(layer))
+				return false;
+		}
+		for (Parameters<Scalar>* params_ptr : params_vec) {
+			B200Parameters<Scalar>* dev = dynamic_cast<B200Parameters<Scalar>*>(params_ptr);
+			if (!dev || dev->has_regularization() || dev->has_value_constraints() || dev->has_grad_constraints())
+				return false;
+		}
+		return true;
+	}
+	/** The per-sample losses the step graph has accumulated on the device since the last call (synchronises). */
+	inline double collect_graph_loss() {
+		double sum = 0;
+		if (graph) {
+			std::vector<Scalar> host(graph->loss_accum.size());
+			graph->loss_accum.download(host.data(), host.size());
+			for (Scalar l : host)
+				sum += l;
+			graph->loss_accum.zero();
+		}
+		return sum;
+	}
+	/** Destroys the step graph; the losses it holds are carried to the end of the epoch. */
+	inline void drop_graph() {
+		carried_graph_loss += collect_graph_loss();
+		graph.reset();
+	}
+	/** Steps that allocate more than this are not captured (CATTL3_GRAPH_MAX_MB, default 2048): they are not launch bound. */
+	inline static std::size_t max_arena_bytes() {
+		static const std::size_t bytes = [] {
+			const char* v = std::getenv("CATTL3_GRAPH_MAX_MB");
+			const long mb = v && v[0] ? std::atol(v) : 2048;
+			return (std::size_t) (mb > 0 ? mb : 0) << 20;
+		}();
+		return bytes;
+	}
+	/** One step at `graph`'s shape: captured on first use, replayed afterwards.  False = run this step eagerly. */
+	inline bool graph_step(b200::DeviceNetwork<Scalar,Rank>& dev_net, const b200::DeviceLoss<Scalar>& dev_loss,
+			typename Base::Net& net, const std::vector<Parameters<Scalar>*>& params_vec, const b200::DeviceTensor<Scalar>& obs,
+			const b200::DeviceTensor<Scalar>& obj, std::size_t epoch) {
+		b200::Context& c = b200::Context::get();
+		StepGraph& g = *graph;
+		if (obs.data() != g.obs->data() || obj.data() != g.obj->data()) {
+			if (obs.size() != g.obs->size() || obj.size() != g.obj->size())
+				return false;
+			b200::Context::Lock l = c.lock();
+			CATTLE_B200_CHECK(cattl3_memcpy_d2d(c.handle(), g.obs->data(), obs.data(), obs.size() * sizeof(Scalar)));
+			CATTLE_B200_CHECK(cattl3_memcpy_d2d(c.handle(), g.obj->data(), obj.data(), obj.size() * sizeof(Scalar)));
+		}
+		step_mode = STEP_SCALARS_ONLY;
+		_update_params(params_vec, epoch - 1, timestep);
+		step_mode = STEP_EAGER;
+		if (!g.graph) {
+			// capture: allocations made before the capture must not be released inside it
+			net.empty_caches();
+			cattl3_graph* captured = nullptr;
+			{
+				// the arena holds everything an eager step allocated (blocks released inside the step are recycled, so
+				// this is an upper bound) plus slack for the 256-byte granules of buffers the eager step did not make
+				const std::size_t arena_bytes = eager_step_bytes + eager_step_bytes / 8 + (1u << 20);
+				b200::Context::Lock l = c.lock();
+				if (arena_bytes > max_arena_bytes() || cattl3_graph_begin(c.handle(), arena_bytes) != CATTL3_OK) {
+					graphs_failed = true;   // too large to be launch bound, or no arena left: stay eager
+					return false;
+				}
+			}
+			bool ok = true;
+			try {
+				b200::DeviceTensor<Scalar> obs_view, obj_view;
+				obs_view.rows = obj_view.rows = g.rows;
+				obs_view.buf = std::make_shared<b200::DeviceBuffer<Scalar>>(
+						b200::DeviceBuffer<Scalar>::view(g.obs->data(), g.obs->size()));
+				obj_view.buf = std::make_shared<b200::DeviceBuffer<Scalar>>(
+						b200::DeviceBuffer<Scalar>::view(g.obj->data(), g.obj->size()));
+				b200::DeviceTensor<Scalar> out = dev_net.propagate_dev(std::move(obs_view), true);
+				b200::DeviceTensor<Scalar> out_grad = dev_loss.loss_and_gradient_dev(out, obj_view, (Scalar) batch_size,
+						g.loss_rows);
+				out = b200::DeviceTensor<Scalar>();
+				{
+					b200::Context::Lock l = c.lock();
+					CATTLE_B200_CHECK(b200::Api<Scalar>::add_inplace(c.handle(), (std::int64_t) g.rows, g.loss_accum.data(),
+							g.loss_rows.data()));
+				}
+				dev_net.backpropagate_dev(std::move(out_grad));
+				step_mode = STEP_CAPTURE;
+				_update_params(params_vec, epoch - 1, timestep);
+				step_mode = STEP_EAGER;
+			} catch (const b200::Error&) {
+				step_mode = STEP_EAGER;
+				ok = false;
+			}
+			{
+				b200::Context::Lock l = c.lock();
+				const int rc = cattl3_graph_end(c.handle(), &captured);
+				ok = ok && rc == CATTL3_OK && captured != nullptr;
+			}
+			if (!ok) {
+				// nothing was executed: forget every handle created during the capture and fall back for good
+				if (captured) {
+					b200::Context::Lock l = c.lock();
+					cattl3_graph_destroy(captured);
+				}
+				net.empty_caches();
+				graphs_failed = true;
+				return false;
+			}
+			g.graph = captured;
+			if (StepGraph::trace())
+				std::cerr << "cattl3: step graph captured (" << g.rows << " rows, arena of " <<
+						(eager_step_bytes + eager_step_bytes / 8 + (1u << 20)) << " bytes)" << std::endl;
+		}
+		{
+			b200::Context::Lock l = c.lock();
+			const int rc = cattl3_graph_launch(c.handle(), g.graph);
+			if (rc == CATTL3_ERR_UNSUPPORTED) {
+				// library scratch moved since the capture (a larger problem ran on this context in between): start over
+				l.unlock();
+				drop_graph();
+				eager_steps_at_shape = 0;
+				return false;
+			}
+			CATTLE_B200_CHECK(rc);
+			++g.replays;
+		}
+		for (Parameters<Scalar>* params_ptr : params_vec) {
+			B200Parameters<Scalar>* dev = static_cast<B200Parameters<Scalar>*>(params_ptr);
+			dev->values_written_on_device();
+			if (dev->are_optimizable() && !dev->are_frozen())
+				dev->grad_zeroed_on_device();
+		}
+		return true;
+	}
 	/**
 	 * Lays the value storages of all optimizable, non-frozen device parameters out next to each other in one array,
 	 * and their gradient storages in another with the same offsets ("one contiguous gradient
@@ -408,6 +664,12 @@ private:
 	}
 	std::size_t timestep;
 	const typename Base::Net* target_net_ptr;
+	// the captured training step (device-resident loop only) and how the optimizer's update is being issued
+	std::unique_ptr<StepGraph> graph;
+	std::size_t eager_steps_at_shape = 0, eager_shape_rows = 0, eager_step_bytes = 0;
+	bool graphs_failed = false;
+	double carried_graph_loss = 0;
+	StepMode step_mode = STEP_EAGER;
 	// optimizer state per device parameter array (keyed by the device address of its first value) and
 	// per host-resident Parameters object
 	std::map<const Scalar*,StateArrays> device_states;

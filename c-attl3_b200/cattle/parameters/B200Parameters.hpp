@@ -335,6 +335,10 @@ public:
 		grad_store->device_written();
 		grad_known_zero = true;
 	}
+	/** Whether a regularisation is attached (its penalty and derivative are evaluated per step). */
+	inline bool has_regularization() const {
+		return (bool) param_reg;
+	}
 	inline bool has_value_constraints() const {
 		return active(value_clip) || active(value_max_l1_norm) || active(value_max_l2_norm);
 	}

@@ -28,12 +28,17 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 int ensure_buffer(cattl3_ctx* ctx, void** buf, size_t* cur, size_t need) {
 	if (*cur >= need)
 		return CATTL3_OK;
+	if (ctx->capturing) {
+		set_error("scratch buffer would have to grow during graph capture (run the step eagerly at this shape first)");
+		return CATTL3_ERR_UNSUPPORTED;
+	}
 	if (*buf) {
 		// the old buffer may still be in use by work queued on the stream
 		CATTL3_CUDA(cudaStreamSynchronize(ctx->stream));
 		CATTL3_CUDA(cudaFree(*buf));
 		*buf = nullptr;
 		*cur = 0;
+		ctx->scratch_generation++;   // step graphs captured so far hold the old address: cattl3_graph_launch refuses them
 	}
 	size_t bytes = (need + ((size_t) 1 << 20) - 1) & ~(((size_t) 1 << 20) - 1);
 	CATTL3_CUDA(cudaMalloc(buf, bytes));
@@ -385,12 +390,133 @@ int cattl3_ctx_destroy(cattl3_ctx* ctx) {
 	if (ctx->ws) cudaFree(ctx->ws);
 	if (ctx->tc_w) cudaFree(ctx->tc_w);
 	if (ctx->stat_ws) cudaFree(ctx->stat_ws);
+	for (int a = 0; a < ctx->arena_count; ++a)
+		cudaFree(ctx->arenas[a].base);
 	for (int i = 0; i < 8; ++i)
 		if (ctx->throttle_ev[i]) cudaEventDestroy(ctx->throttle_ev[i]);
 	for (int i = 0; i < 3; ++i)
 		if (ctx->stage_dev[i]) cudaFree(ctx->stage_dev[i]);
 	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
+	return CATTL3_OK;
+}
+
+} // extern "C"
+
+// ---- step graphs ------------------------------------------------------------------------------------------------
+struct cattl3_graph {
+	cattl3_ctx* ctx = nullptr;
+	cudaGraph_t graph = nullptr;
+	cudaGraphExec_t exec = nullptr;
+	int arena = -1;
+	int64_t scratch_generation = 0;   // the context's when the graph was captured
+};
+
+namespace {
+
+inline size_t granule(size_t bytes) { return ((bytes ? bytes : 1) + 255) & ~(size_t) 255; }
+
+// index of the arena that holds p, or -1
+inline int arena_of(const cattl3_ctx* ctx, const void* p) {
+	for (int a = 0; a < ctx->arena_count; ++a) {
+		if ((const char*) p >= ctx->arenas[a].base && (const char*) p < ctx->arenas[a].base + ctx->arenas[a].size)
+			return a;
+	}
+	return -1;
+}
+
+}
+
+extern "C" {
+
+int64_t cattl3_ctx_allocated_bytes(cattl3_ctx* ctx) {
+	return ctx ? ctx->allocated_bytes : 0;
+}
+
+int cattl3_graph_begin(cattl3_ctx* ctx, size_t arena_bytes) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(!ctx->capturing, "graph_begin: already capturing");
+	CATTL3_REQUIRE(arena_bytes > 0, "graph_begin: the arena needs a size (cattl3_ctx_allocated_bytes over one eager step)");
+	arena_bytes = granule(arena_bytes);
+	// smallest retired arena that is large enough, else a new one
+	int pick = -1;
+	for (int a = 0; a < ctx->arena_count; ++a) {
+		if (!ctx->arenas[a].in_use && ctx->arenas[a].size >= arena_bytes &&
+				(pick < 0 || ctx->arenas[a].size < ctx->arenas[pick].size))
+			pick = a;
+	}
+	if (pick < 0) {
+		if (ctx->arena_count == cattl3_ctx::MAX_ARENAS) {
+			set_error("graph_begin: all %d step-graph arenas are taken", cattl3_ctx::MAX_ARENAS);
+			return CATTL3_ERR_UNSUPPORTED;
+		}
+		void* base = nullptr;
+		CATTL3_CUDA(cudaMalloc(&base, arena_bytes));
+		pick = ctx->arena_count++;
+		ctx->arenas[pick].base = (char*) base;
+		ctx->arenas[pick].size = arena_bytes;
+	}
+	CATTL3_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+	ctx->arenas[pick].in_use = true;
+	ctx->cap_arena = pick;
+	ctx->cap_used = 0;
+	ctx->cap_block_count = 0;
+	ctx->capturing = true;
+	return CATTL3_OK;
+}
+
+int cattl3_graph_end(cattl3_ctx* ctx, cattl3_graph** out) {
+	CATTL3_REQUIRE(ctx && out, "graph_end: bad arguments");
+	*out = nullptr;
+	CATTL3_REQUIRE(ctx->capturing, "graph_end: not capturing");
+	const int arena = ctx->cap_arena;
+	ctx->capturing = false;
+	ctx->cap_arena = -1;
+	ctx->cap_block_count = 0;
+	cudaGraph_t graph = nullptr;
+	cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+	if (e != cudaSuccess || !graph) {
+		cudaGetLastError();
+		if (graph) cudaGraphDestroy(graph);
+		ctx->arenas[arena].in_use = false;
+		return cuda_fail(e != cudaSuccess ? e : cudaErrorUnknown, "cudaStreamEndCapture (the capture was invalidated)", __FILE__, __LINE__);
+	}
+	cudaGraphExec_t exec = nullptr;
+	e = cudaGraphInstantiate(&exec, graph, 0);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		cudaGraphDestroy(graph);
+		ctx->arenas[arena].in_use = false;
+		return cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__);
+	}
+	cattl3_graph* g = new cattl3_graph();
+	g->ctx = ctx; g->graph = graph; g->exec = exec; g->arena = arena;
+	g->scratch_generation = ctx->scratch_generation;
+	*out = g;
+	return CATTL3_OK;
+}
+
+int cattl3_graph_launch(cattl3_ctx* ctx, cattl3_graph* g) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(g && g->exec && g->ctx == ctx && !ctx->capturing, "graph_launch: bad arguments");
+	if (g->scratch_generation != ctx->scratch_generation) {
+		set_error("graph_launch: library scratch moved since the capture (a larger problem ran in between); capture again");
+		return CATTL3_ERR_UNSUPPORTED;
+	}
+	CATTL3_CUDA(cudaGraphLaunch(g->exec, ctx->stream));
+	ctx->launches++;
+	return CATTL3_OK;
+}
+
+int cattl3_graph_destroy(cattl3_graph* g) {
+	if (!g) return CATTL3_OK;
+	cudaSetDevice(g->ctx->device);
+	cudaStreamSynchronize(g->ctx->stream);
+	if (g->exec) cudaGraphExecDestroy(g->exec);
+	if (g->graph) cudaGraphDestroy(g->graph);
+	if (g->arena >= 0)
+		g->ctx->arenas[g->arena].in_use = false;   // retired: the next graph_begin may take it
+	delete g;
 	return CATTL3_OK;
 }
 
@@ -428,6 +554,31 @@ void* cattl3_ctx_stream(const cattl3_ctx* ctx) { return ctx ? (void*) ctx->strea
 int cattl3_malloc(cattl3_ctx* ctx, void** p, size_t bytes) {
 	CATTL3_CHECK(check_ctx(ctx));
 	CATTL3_REQUIRE(p, "malloc: null out pointer");
+	const size_t size = granule(bytes);
+	ctx->allocated_bytes += (int64_t) size;
+	if (ctx->capturing) {
+		// a step graph's activations come out of its arena (fixed addresses, no allocation nodes in the graph)
+		cattl3_ctx::Arena& arena = ctx->arenas[ctx->cap_arena];
+		for (int i = 0; i < ctx->cap_block_count; ++i) {
+			cattl3_ctx::CapBlock& blk = ctx->cap_blocks[i];
+			if (blk.free && blk.size == size) {   // released earlier in the step: stream order makes the reuse safe
+				blk.free = false;
+				*p = blk.ptr;
+				return CATTL3_OK;
+			}
+		}
+		if (ctx->cap_used + size > arena.size || ctx->cap_block_count == cattl3_ctx::MAX_CAP_BLOCKS) {
+			set_error("step-graph arena exhausted (%zu of %zu bytes, %d blocks)", ctx->cap_used, arena.size, ctx->cap_block_count);
+			return CATTL3_ERR_UNSUPPORTED;
+		}
+		cattl3_ctx::CapBlock& blk = ctx->cap_blocks[ctx->cap_block_count++];
+		blk.ptr = arena.base + ctx->cap_used;
+		blk.size = size;
+		blk.free = false;
+		ctx->cap_used += size;
+		*p = blk.ptr;
+		return CATTL3_OK;
+	}
 	// stream-ordered allocation from the device's default pool (kept warm: see ctx_create), so a
 	// layer's activation buffers are recycled without a cudaMalloc / cudaFree synchronisation per call
 	CATTL3_CUDA(cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream));
@@ -435,8 +586,26 @@ int cattl3_malloc(cattl3_ctx* ctx, void** p, size_t bytes) {
 }
 int cattl3_free(cattl3_ctx* ctx, void* p) {
 	CATTL3_CHECK(check_ctx(ctx));
-	if (p)
-		CATTL3_CUDA(cudaFreeAsync(p, ctx->stream));
+	if (!p)
+		return CATTL3_OK;
+	const int a = arena_of(ctx, p);
+	if (a >= 0) {
+		// arena memory belongs to a step graph: recycled within the capture that handed it out, otherwise nothing to do
+		if (ctx->capturing && a == ctx->cap_arena) {
+			for (int i = 0; i < ctx->cap_block_count; ++i) {
+				if (ctx->cap_blocks[i].ptr == (char*) p) {
+					ctx->cap_blocks[i].free = true;
+					break;
+				}
+			}
+		}
+		return CATTL3_OK;
+	}
+	cudaError_t e = cudaFreeAsync(p, ctx->stream);
+	if (e != cudaSuccess) {
+		cudaGetLastError();   // callers are destructors: do not leave the error for the next launch check
+		return cuda_fail(e, "cudaFreeAsync", __FILE__, __LINE__);
+	}
 	return CATTL3_OK;
 }
 int cattl3_memset(cattl3_ctx* ctx, void* p, int value, size_t bytes) {
@@ -549,6 +718,7 @@ int cattl3_feed_push(cattl3_feed* f, const void* src, size_t bytes, void** dev_p
 
 int cattl3_memcpy_d2h(cattl3_ctx* ctx, void* dst, const void* src, size_t bytes) {
 	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(!ctx->capturing, "memcpy_d2h synchronises: not possible during graph capture");
 	CATTL3_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
 	CATTL3_CUDA(cudaStreamSynchronize(ctx->stream));
 	return CATTL3_OK;

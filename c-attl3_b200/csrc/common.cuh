@@ -25,6 +25,23 @@ struct cattl3_ctx {
 	// per-CTA column sums of a fused batch-norm statistics epilogue (conv_tc.cu)
 	void* stat_ws = nullptr;
 	size_t stat_ws_bytes = 0;
+	// between cattl3_graph_begin and cattl3_graph_end: the stream is capturing (nothing may synchronise or grow scratch)
+	bool capturing = false;
+	// Step graphs keep their activations in a private arena (graphs with allocation nodes launch slowly): while capturing,
+	// cattl3_malloc carves blocks out of arena `cap_arena` and cattl3_free recycles them (one stream: program order makes
+	// the reuse safe); outside a capture cattl3_free of an arena address is a no-op.  An arena is owned by its graph;
+	// cattl3_graph_destroy retires it (in_use = false) for the next cattl3_graph_begin, the memory goes at ctx_destroy.
+	static constexpr int MAX_CAP_BLOCKS = 1024, MAX_ARENAS = 16;
+	struct Arena { char* base; size_t size; bool in_use; };
+	Arena arenas[MAX_ARENAS];
+	int arena_count = 0;
+	int cap_arena = -1;
+	size_t cap_used = 0;
+	struct CapBlock { char* ptr; size_t size; bool free; };
+	CapBlock cap_blocks[MAX_CAP_BLOCKS];
+	int cap_block_count = 0;
+	int64_t scratch_generation = 0;   // bumped whenever ensure_buffer moves a scratch buffer (captured graphs hold the old address)
+	int64_t allocated_bytes = 0;   // running total of cattl3_malloc in 256-byte granules (sizes an arena from an eager step)
 	// cattl3_ctx_throttle: one event per recent call
 	cudaEvent_t throttle_ev[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 	long long throttle_calls = 0;

@@ -795,9 +795,18 @@ __device__ __forceinline__ void opt_update(const OptScalars<S>& h, S& pv, S& gv,
 
 // 16-byte vector body (every stream of the arena is 16-byte aligned at the same element offsets) + scalar tail.
 template<typename S, int KIND>
-__global__ void __launch_bounds__(256) opt_step_kernel(long long count, int vec_ok, OptScalars<S> h, S* __restrict__ p,
-		S* __restrict__ g, S* __restrict__ s1, S* __restrict__ s2, S* __restrict__ s3) {
+__global__ void __launch_bounds__(256) opt_step_kernel(long long count, int vec_ok, OptScalars<S> h_value,
+		const cattl3_opt_step* __restrict__ dev_step, S* __restrict__ p, S* __restrict__ g, S* __restrict__ s1,
+		S* __restrict__ s2, S* __restrict__ s3) {
 	typedef typename V16<S>::type V;
+	// dev_step != null: the step scalars live in device memory (a captured step graph replays this launch with new
+	// scalars every step: cattl3_optimizer_step_indirect)
+	OptScalars<S> h = h_value;
+	if (dev_step) {
+		h.lr = (S) dev_step->lr; h.a = (S) dev_step->a; h.b = (S) dev_step->b; h.eps = (S) dev_step->eps;
+		h.lr_epoch = (S) dev_step->lr_epoch; h.c1 = (S) dev_step->c1; h.c1n = (S) dev_step->c1n; h.c2 = (S) dev_step->c2;
+		h.l2 = (S) dev_step->l2_lambda; h.reset = dev_step->reset_grad;
+	}
 	constexpr int G = V16<S>::G;
 	constexpr int NS = KIND == CATTL3_OPT_VANILLA_SGD ? 0 : (KIND <= CATTL3_OPT_RMSPROP ? 1 : (KIND == CATTL3_OPT_AMSGRAD ? 3 : 2));
 	const long long nvec = vec_ok ? count / G : 0;
@@ -836,8 +845,10 @@ __global__ void __launch_bounds__(256) opt_step_kernel(long long count, int vec_
 	}
 }
 
+// st: host scalars (dev_step == null), or only `kind` is taken from the host and the scalars from dev_step.
 template<typename S>
-int optimizer_step(cattl3_ctx* ctx, const cattl3_opt_step* st, int64_t count, S* p, S* g, S* s1, S* s2, S* s3) {
+int optimizer_step(cattl3_ctx* ctx, const cattl3_opt_step* st, int64_t count, S* p, S* g, S* s1, S* s2, S* s3,
+		const cattl3_opt_step* dev_step = nullptr) {
 	CATTL3_CHECK(check_ctx(ctx));
 	CATTL3_REQUIRE(st && count > 0 && p && g, "optimizer_step: bad arguments");
 	OptScalars<S> h{ (S) st->lr, (S) st->a, (S) st->b, (S) st->eps, (S) st->lr_epoch, (S) st->c1, (S) st->c1n,
@@ -849,7 +860,7 @@ int optimizer_step(cattl3_ctx* ctx, const cattl3_opt_step* st, int64_t count, S*
 	const int vec_ok = aligned16(p) && aligned16(g) && (need < 1 || aligned16(s1)) && (need < 2 || aligned16(s2)) &&
 			(need < 3 || aligned16(s3));
 	switch (k) {
-#define CASE(K) case K: opt_step_kernel<S, K><<<grid, 256, 0, ctx->stream>>>(count, vec_ok, h, p, g, s1, s2, s3); break;
+#define CASE(K) case K: opt_step_kernel<S, K><<<grid, 256, 0, ctx->stream>>>(count, vec_ok, h, dev_step, p, g, s1, s2, s3); break;
 		CASE(CATTL3_OPT_VANILLA_SGD) CASE(CATTL3_OPT_MOMENTUM) CASE(CATTL3_OPT_NESTEROV) CASE(CATTL3_OPT_ADAGRAD)
 		CASE(CATTL3_OPT_RMSPROP) CASE(CATTL3_OPT_ADADELTA) CASE(CATTL3_OPT_ADAM) CASE(CATTL3_OPT_ADAMAX)
 		CASE(CATTL3_OPT_NADAM) CASE(CATTL3_OPT_AMSGRAD)
@@ -1148,6 +1159,14 @@ int cattl3_optimizer_step_f32(cattl3_ctx* c, const cattl3_opt_step* st, int64_t 
 int cattl3_optimizer_step_f64(cattl3_ctx* c, const cattl3_opt_step* st, int64_t count, double* p, double* g, double* s1, double* s2, double* s3) {
 	return optimizer_step<double>(c, st, count, p, g, s1, s2, s3); }
 
+int cattl3_optimizer_step_indirect_f32(cattl3_ctx* c, int kind, const cattl3_opt_step* dev_step, int64_t count, float* p, float* g, float* s1, float* s2, float* s3) {
+	CATTL3_REQUIRE(dev_step, "optimizer_step_indirect: null scalars");
+	cattl3_opt_step st = {}; st.kind = kind;
+	return optimizer_step<float>(c, &st, count, p, g, s1, s2, s3, dev_step); }
+int cattl3_optimizer_step_indirect_f64(cattl3_ctx* c, int kind, const cattl3_opt_step* dev_step, int64_t count, double* p, double* g, double* s1, double* s2, double* s3) {
+	CATTL3_REQUIRE(dev_step, "optimizer_step_indirect: null scalars");
+	cattl3_opt_step st = {}; st.kind = kind;
+	return optimizer_step<double>(c, &st, count, p, g, s1, s2, s3, dev_step); }
 int cattl3_add_inplace_f32(cattl3_ctx* c, int64_t count, float* y, const float* x) { return add_inplace<float>(c, count, y, x); }
 int cattl3_add_inplace_f64(cattl3_ctx* c, int64_t count, double* y, const double* x) { return add_inplace<double>(c, count, y, x); }
 int cattl3_mul_inplace_f32(cattl3_ctx* c, int64_t count, float* y, const float* x) { return mul_inplace<float>(c, count, y, x); }

@@ -215,6 +215,26 @@ int cattl3_fill_f64(cattl3_ctx*, int64_t count, double value, double* y);
 int cattl3_slice_rows_f32(cattl3_ctx*, int64_t total, int64_t vol, int64_t first, int64_t rows, const float* src, float* dst);
 int cattl3_slice_rows_f64(cattl3_ctx*, int64_t total, int64_t vol, int64_t first, int64_t rows, const double* src, double* dst);
 
+/*
+ * Step graphs: a launch-bound training step (tens of small kernels: configs 1 and 3) captured once into a CUDA graph and
+ * replayed with one launch per step (the batch loop of C-ATTL3/optimizer/SGDOptimizer.hpp:34-81 pays one launch per
+ * layer pass otherwise).  Between _begin and _end everything enqueued on the context's stream is recorded instead of run:
+ * kernels, memsets and device-to-device copies.  cattl3_malloc hands out blocks of a private arena of `arena_bytes`
+ * (fixed addresses, recycled by cattl3_free within the capture; the graph holds no allocation nodes) -- size it with
+ * cattl3_ctx_allocated_bytes() taken before and after one eager run of the same step.  Nothing may synchronise or
+ * grow library scratch (the step must have run eagerly at the same shape before), and host-side arguments are frozen
+ * into the graph -- step-dependent scalars therefore go through device memory (cattl3_optimizer_step_indirect).
+ * Blocks still held when the capture ends stay valid for the life of the graph; freeing them later is a no-op.
+ * Errors: CATTL3_ERR_UNSUPPORTED when the arena is too small or scratch would have to grow (the capture must still be
+ * closed with _end, which then reports the invalidated capture).
+ */
+typedef struct cattl3_graph cattl3_graph;
+int64_t cattl3_ctx_allocated_bytes(cattl3_ctx* ctx);   /* running total handed out by cattl3_malloc, in 256-byte granules */
+int cattl3_graph_begin(cattl3_ctx* ctx, size_t arena_bytes);
+int cattl3_graph_end(cattl3_ctx* ctx, cattl3_graph** out);   /* *out = NULL and an error if the capture was invalidated */
+int cattl3_graph_launch(cattl3_ctx* ctx, cattl3_graph* graph);   /* CATTL3_ERR_UNSUPPORTED: library scratch moved since the capture -- destroy and capture again */
+int cattl3_graph_destroy(cattl3_graph* graph);
+
 /* ---- shape helpers ------------------------------------------------------------------------ */
 /* ConvKernelLayer.hpp:194-197 (transposed = 0) / TransConvKernelLayer.hpp:200-203 (transposed = 1). */
 int cattl3_conv_output_dims(const cattl3_conv_geom* g, int transposed, int32_t* oh, int32_t* ow);
@@ -354,6 +374,10 @@ int cattl3_batchnorm_backward_f64(cattl3_ctx*, int per_channel, int32_t n, int32
  * s1/s2/s3: optimizer state vectors (unused ones may be NULL). */
 int cattl3_optimizer_step_f32(cattl3_ctx*, const cattl3_opt_step*, int64_t count, float* p, float* g, float* s1, float* s2, float* s3);
 int cattl3_optimizer_step_f64(cattl3_ctx*, const cattl3_opt_step*, int64_t count, double* p, double* g, double* s1, double* s2, double* s3);
+/* The same update with the scalars of `cattl3_opt_step` read from DEVICE memory at run time (only `kind` is a host
+ * argument): what a captured step graph replays. */
+int cattl3_optimizer_step_indirect_f32(cattl3_ctx*, int kind, const cattl3_opt_step* dev_step, int64_t count, float* p, float* g, float* s1, float* s2, float* s3);
+int cattl3_optimizer_step_indirect_f64(cattl3_ctx*, int kind, const cattl3_opt_step* dev_step, int64_t count, double* p, double* g, double* s1, double* s2, double* s3);
 
 /* ---- small element-wise helpers for the network glue ---------------------------------------- */
 /* y += x (ResidualNeuralNetwork::propagate, C-ATTL3/neural_network/ResidualNeuralNetwork.hpp:112-117). */

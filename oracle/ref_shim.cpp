@@ -375,6 +375,11 @@ int cifar_impl(int total, int batch, int epochs, const S* x, const S* obj, const
 	auto loss = std::make_shared<CrossEntropyLoss<S,3,false>>();
 	NadamOptimizer<S,3,false> opt(loss, batch);
 	opt.fit(net);
+	/* benchmarks only: REF_SHIM_WARMUP_EPOCHS untimed epochs first (one-time costs: allocations, data set placement) */
+	if (const char* warm = std::getenv("REF_SHIM_WARMUP_EPOCHS")) {
+		if (std::atoi(warm) > 0 && epochs > 0)
+			opt.train(net, prov, std::atoi(warm));
+	}
 	double t0 = now_ms();
 	S l = opt.train(net, prov, epochs);
 	double t1 = now_ms();

@@ -222,6 +222,49 @@ def test_fused_and_unfused_network_loops_agree(dt):
     assert err < (2e-5 if dt == np.float32 else 1e-10)
 
 
+@pytest.mark.parametrize("net", ["cifar", "autoencoder", "resnet"])
+@pytest.mark.parametrize("dt", DTYPES)
+def test_step_graph_equals_eager_loop(dt, net):
+    """The batch loop captures a launch-bound training step as a CUDA graph after two eager steps at a shape
+    (cattl3_graph_*, SGDOptimizer.hpp StepGraph) and replays it; CATTL3_NO_GRAPH=1 keeps every step eager.  Same run,
+    same parameters and the same epoch loss either way -- including a ragged last batch (run eagerly between replays),
+    a second epoch (the graph outlives the epoch) and BatchNorm's running statistics (resnet)."""
+    body = {
+        "cifar": "x = C.rand(np.random.default_rng(1003), (72, 32, 32, 3), dt)\n"
+                 "obj = np.zeros((72, 1, 1, 10), dtype=dt, order='F'); obj[np.arange(72), 0, 0, np.arange(72) % 10] = 1\n"
+                 "p, l, _ = lib.train_cifar(x, obj, 16, 2, params_in=np.ascontiguousarray(G['cifar/%s/p0']))\n",
+        "autoencoder": "x = C.autoencoder_inputs(dt, total=200, seed=3004); n = lib.train_autoencoder(x, 32, -1)\n"
+                       "p, l, _ = lib.train_autoencoder(x, 32, 2, params_in=C.seeded_params(n, dt, 3002))\n",
+        "resnet": "x, obj = C.resnet_inputs(dt, total=176); n = lib.train_resnet(x, obj, 32, -1, C.RESNET_SMALL)\n"
+                  "p, l, _ = lib.train_resnet(x, obj, 32, 2, C.RESNET_SMALL, params_in=C.seeded_params(n, dt, 4002))\n",
+    }[net]
+    if net == "cifar":
+        body = body.replace("%s", "f32" if dt == np.float32 else "f64")
+    code = (
+        "import os, sys, numpy as np; sys.path[:0] = [%r, %r]\n"
+        "import cases as C; from oracle import binding\n"
+        "lib = binding.Oracle('ref', path=%r); dt = np.%s\n"
+        "G = np.load(%r)\n" % (ROOT, os.path.join(ROOT, "tests"), SHIM, np.dtype(dt).name,
+                                os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+        + body + "np.save(sys.argv[1], np.concatenate([np.asarray(p, dtype=np.float64).ravel(), [l]]))\n")
+    import tempfile
+    outs = []
+    with tempfile.TemporaryDirectory() as d:
+        for i, env in enumerate(({"CATTL3_GRAPH_TRACE": "1"}, {"CATTL3_NO_GRAPH": "1"})):
+            path = os.path.join(d, "p%d.npy" % i)
+            r = subprocess.run([os.sys.executable, "-c", code, path], env=dict(os.environ, **env), capture_output=True,
+                               text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            if i == 0:
+                assert "step graph captured" in r.stderr, "the graph path did not engage:\n" + r.stderr[-2000:]
+                assert "replays" in r.stderr
+            outs.append(np.load(path))
+    err = C.relerr(outs[0][:-1], outs[1][:-1])
+    print("%s: step graph vs eager parameters %.2e, loss %.8f vs %.8f" % (net, err, outs[0][-1], outs[1][-1]))
+    assert err < (1e-6 if dt == np.float32 else 1e-13)
+    assert abs(outs[0][-1] - outs[1][-1]) < (1e-5 if dt == np.float32 else 1e-12) * max(1.0, abs(outs[1][-1]))
+
+
 @pytest.mark.parametrize("dt", DTYPES)
 def test_dropout_layer_contract(b200, dt):
     """The B200 DropoutLayer class (device RNG) honours the reference layer's contract (DropoutLayer.hpp:74-94):
