@@ -221,6 +221,25 @@ class Oracle:
         assert rc == 0, rc
         return out, loss.value, ms.value
 
+    def train_seqnet(self, x, obj, batch, epochs, width, state, params_in=None):
+        """Config-5 composite network over frame sequences (SequentialNeuralNetwork{Parallel conv lanes, DenseNet
+        modules, MaxPool} -> convolutional LSTMNeuralNetwork), SquaredLoss, Nadam.
+        x: total x seq x hw x hw x 3, obj: total x 1 x hw/2 x hw/2 x state.  epochs < 0: parameter count only."""
+        dt = x.dtype
+        total, seq, hw = x.shape[:3]
+        n = ctypes.c_int()
+        fn = self._fn("train_seqnet", dt)
+        rc = fn(0, 1, 1, -1, hw, width, state, None, None, None, None, ctypes.byref(n), None, None)
+        assert rc == 0, rc
+        if epochs < 0:
+            return n.value
+        out = np.zeros(n.value, dt)
+        loss, ms = ctypes.c_double(), ctypes.c_double()
+        rc = fn(total, seq, batch, epochs, hw, width, state, _ptr(x), _ptr(obj), _ptr(params_in), _ptr(out),
+                ctypes.byref(n), ctypes.byref(loss), ctypes.byref(ms))
+        assert rc == 0, rc
+        return out, loss.value, ms.value
+
 
 def have_ref():
     return os.path.exists(REF_PATH)

@@ -414,8 +414,8 @@ int dropout_impl(int n, int h, int w, int c, S prob, const S* x, const S* dy, S*
 }
 
 /* Shared tail of the network trainers: inject parameters, train without shuffling, copy the parameters out. */
-template<typename S, typename Opt>
-int train_and_export(NeuralNetwork<S,3,false>& net, Opt& opt, TensorPtr<S,4> obs, TensorPtr<S,4> objs, int epochs,
+template<typename S, bool Seq, typename Opt>
+int train_and_export(NeuralNetwork<S,3,Seq>& net, Opt& opt, TensorPtr<S,4 + Seq> obs, TensorPtr<S,4 + Seq> objs, int epochs,
 		const S* params_in, S* params_out, int* n_params, double* loss_out, double* train_ms) {
 	net.init();
 	auto params = net.get_all_unique_params();
@@ -432,7 +432,7 @@ int train_and_export(NeuralNetwork<S,3,false>& net, Opt& opt, TensorPtr<S,4> obs
 			src += p->get_rows() * p->get_cols();
 		}
 	}
-	MemoryDataProvider<S,3,false,false> prov(std::move(obs), std::move(objs));
+	MemoryDataProvider<S,3,Seq,false> prov(std::move(obs), std::move(objs));
 	opt.fit(net);
 	/* benchmarks only: REF_SHIM_WARMUP_EPOCHS untimed epochs first (one-time costs: allocations, data set placement) */
 	if (const char* warm = std::getenv("REF_SHIM_WARMUP_EPOCHS")) {
@@ -489,7 +489,7 @@ int autoencoder_impl(int total, int batch, int epochs, const S* x, const S* para
 	TensorPtr<S,4> objs(new Tensor<S,4>(*obs));
 	auto loss = std::make_shared<SquaredLoss<S,3,false>>();
 	NadamOptimizer<S,3,false> opt(loss, batch > 0 ? batch : 1);
-	return train_and_export<S>(net, opt, std::move(obs), std::move(objs), epochs, params_in, params_out, n_params,
+	return train_and_export<S,false>(net, opt, std::move(obs), std::move(objs), epochs, params_in, params_out, n_params,
 			loss_out, train_ms);
 }
 
@@ -541,7 +541,76 @@ int resnet_impl(int total, int batch, int epochs, int h, int w, int c, int stem_
 	if (obj) std::memcpy(objs->data(), obj, sizeof(S) * objs->size());
 	auto loss = std::make_shared<CrossEntropyLoss<S,3,false>>();
 	NadamOptimizer<S,3,false> opt(loss, batch > 0 ? batch : 1);
-	return train_and_export<S>(net, opt, std::move(obs), std::move(objs), epochs, params_in, params_out, n_params,
+	return train_and_export<S,false>(net, opt, std::move(obs), std::move(objs), epochs, params_in, params_out, n_params,
+			loss_out, train_ms);
+}
+
+/*
+ * BASELINE.json configs[4]: a composite network over sequences of frames -- a SequentialNeuralNetwork (the time
+ * steps folded into the batch, SequentialNeuralNetwork.hpp:95-124) around a StackedNeuralNetwork of
+ *   an Inception-style ParallelNeuralNetwork (lanes Conv 3x3 p1 -> ReLU and Conv 1x1 -> ReLU on the same input,
+ *   outputs concatenated along the channel rank, ParallelNeuralNetwork.hpp:176-194),
+ *   a DenseNeuralNetwork of two modules Conv 3x3 p1 -> ReLU (each sees the input and all earlier module outputs
+ *   concatenated along the channel rank, DenseNeuralNetwork.hpp:131-158) and
+ *   a 2x2 MaxPool,
+ * feeding a convolutional LSTMNeuralNetwork whose eight kernels are ConvKernelLayers (3x3 p1) as in
+ * test/gradient_test.cpp:700-734, which emits one output frame after the last time step; SquaredLoss,
+ * NadamOptimizer, both sequential.  x: total x seq x hw x hw x 3, obj: total x 1 x hw/2 x hw/2 x state.
+ */
+template<typename S>
+int seqnet_impl(int total, int seq, int batch, int epochs, int hw, int width, int state, const S* x, const S* obj,
+		const S* params_in, S* params_out, int* n_params, double* loss_out, double* train_ms) {
+	typedef std::size_t sz;
+	auto he = std::make_shared<HeParameterInitialization<S>>(1e-1);
+	auto glorot = std::make_shared<GlorotParameterInitialization<S>>(1e-1);
+	const Dimensions<sz,3> in({ (sz) hw, (sz) hw, 3u });
+	std::vector<NeuralNetPtr<S,3,false>> lanes;
+	{
+		std::vector<LayerPtr<S,3>> a, b;
+		a.emplace_back(new ConvKernelLayer<S>(in, width, he));
+		a.emplace_back(new ReLUActivationLayer<S,3>(a.back()->get_output_dims()));
+		b.emplace_back(new ConvKernelLayer<S>(in, width, he, 1, 1, 0, 0));
+		b.emplace_back(new ReLUActivationLayer<S,3>(b.back()->get_output_dims()));
+		lanes.emplace_back(new FeedforwardNeuralNetwork<S,3>(std::move(a)));
+		lanes.emplace_back(new FeedforwardNeuralNetwork<S,3>(std::move(b)));
+	}
+	std::vector<NeuralNetPtr<S,3,false>> front;
+	front.emplace_back(new ParallelNeuralNetwork<S,3>(std::move(lanes)));
+	const Dimensions<sz,3> merged = front.back()->get_output_dims();
+	std::vector<NeuralNetPtr<S,3,false>> modules;
+	{
+		std::vector<LayerPtr<S,3>> m0, m1;
+		m0.emplace_back(new ConvKernelLayer<S>(merged, width, he));
+		m0.emplace_back(new ReLUActivationLayer<S,3>(m0.back()->get_output_dims()));
+		modules.emplace_back(new FeedforwardNeuralNetwork<S,3>(std::move(m0)));
+		m1.emplace_back(new ConvKernelLayer<S>(merged.add_along_rank(modules[0]->get_output_dims(), 2), width, he));
+		m1.emplace_back(new ReLUActivationLayer<S,3>(m1.back()->get_output_dims()));
+		modules.emplace_back(new FeedforwardNeuralNetwork<S,3>(std::move(m1)));
+	}
+	front.emplace_back(new DenseNeuralNetwork<S,3,DENSE_HIGHEST_RANK>(std::move(modules)));
+	front.emplace_back(new FeedforwardNeuralNetwork<S,3>(LayerPtr<S,3>(
+			new MaxPoolLayer<S>(front.back()->get_output_dims()))));
+	NeuralNetPtr<S,3,false> frames(new StackedNeuralNetwork<S,3,false>(std::move(front)));
+	const Dimensions<sz,3> lstm_in = frames->get_output_dims();
+	const Dimensions<sz,3> lstm_out({ lstm_in(0), lstm_in(1), (sz) state });
+	auto in_kernel = [&]() { return KernelPtr<S,3>(new ConvKernelLayer<S>(lstm_in, state, glorot)); };
+	auto out_kernel = [&]() { return KernelPtr<S,3>(new ConvKernelLayer<S>(lstm_out, state, glorot)); };
+	auto sigmoid = [&]() { return ActivationPtr<S,3>(new SigmoidActivationLayer<S,3>(lstm_out)); };
+	auto tanh_act = [&]() { return ActivationPtr<S,3>(new TanhActivationLayer<S,3>(lstm_out)); };
+	std::vector<NeuralNetPtr<S,3,true>> stack;
+	stack.emplace_back(new SequentialNeuralNetwork<S,3>(std::move(frames)));
+	stack.emplace_back(new LSTMNeuralNetwork<S,3>(in_kernel(), out_kernel(), in_kernel(), out_kernel(), in_kernel(),
+			out_kernel(), in_kernel(), out_kernel(), sigmoid(), sigmoid(), tanh_act(), tanh_act(), sigmoid(),
+			[](sz input_seq_length) { return std::make_pair((sz) 1, input_seq_length - 1); }));
+	StackedNeuralNetwork<S,3,true> net(std::move(stack));
+	const sz rows = (sz) (total > 0 ? total : 1), steps = (sz) (seq > 0 ? seq : 1);
+	TensorPtr<S,5> obs(new Tensor<S,5>(rows, steps, (sz) hw, (sz) hw, 3u));
+	if (x) std::memcpy(obs->data(), x, sizeof(S) * obs->size());
+	TensorPtr<S,5> objs(new Tensor<S,5>(rows, 1u, lstm_out(0), lstm_out(1), lstm_out(2)));
+	if (obj) std::memcpy(objs->data(), obj, sizeof(S) * objs->size());
+	auto loss = std::make_shared<SquaredLoss<S,3,true>>();
+	NadamOptimizer<S,3,true> opt(loss, batch > 0 ? batch : 1);
+	return train_and_export<S,true>(net, opt, std::move(obs), std::move(objs), epochs, params_in, params_out, n_params,
 			loss_out, train_ms);
 }
 
@@ -602,7 +671,11 @@ int ref_train_resnet_##SUF(int total, int batch, int epochs, int h, int w, int c
 		int width, int blocks, int head_pool, int classes, const S* x, const S* obj, const S* params_in, S* params_out, \
 		int* n_params, double* loss_out, double* train_ms) { \
 	return resnet_impl<S>(total, batch, epochs, h, w, c, stem_r, stem_s, stem_pool, width, blocks, head_pool, classes, x, \
-			obj, params_in, params_out, n_params, loss_out, train_ms); }
+			obj, params_in, params_out, n_params, loss_out, train_ms); } \
+int ref_train_seqnet_##SUF(int total, int seq, int batch, int epochs, int hw, int width, int state, const S* x, const S* obj, \
+		const S* params_in, S* params_out, int* n_params, double* loss_out, double* train_ms) { \
+	return seqnet_impl<S>(total, seq, batch, epochs, hw, width, state, x, obj, params_in, params_out, n_params, loss_out, \
+			train_ms); }
 
 DEFINE_FOR(float, f32)
 DEFINE_FOR(double, f64)

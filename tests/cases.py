@@ -171,3 +171,15 @@ def resnet_inputs(dtype, total=64, hw=8, seed=4001):
 def seeded_params(n, dtype, seed):
     """Deterministic starting parameters (so that fixtures need not store them): uniform +-0.15."""
     return np.random.default_rng(seed).uniform(-0.15, 0.15, n).astype(dtype)
+
+
+def seqnet_inputs(dtype, total=16, seq=3, hw=8, state=4, seed=5001):
+    """BASELINE.json configs[4] at test size: synthetic sequences of hw x hw x 3 frames, uniform [-1, 1); the objective
+    is one hw/2 x hw/2 x state frame per sequence, uniform [-0.5, 0.5) (inside the range of the LSTM's output)."""
+    rng = np.random.default_rng(seed)
+    x = rand(rng, (total, seq, hw, hw, 3), dtype)
+    obj = rand(rng, (total, 1, hw // 2, hw // 2, state), dtype, -0.5, 0.5)
+    return x, obj
+
+
+SEQNET_SMALL = dict(width=4, state=4)

@@ -2,7 +2,8 @@
 """Regenerates tests/golden/reference_networks.npz from the UNMODIFIED reference (oracle/_ref/libcattle_ref.so,
 compiled from /root/reference by oracle/Makefile): parameters and epoch loss of BASELINE.json configs[2] (the
 mnist auto-encoder, StackedNeuralNetwork + SquaredLoss) and configs[3] (a ResNet-style ResidualNeuralNetwork of
-conv + BatchNorm + ReLU modules, CrossEntropyLoss) after a few Nadam steps from seeded inputs and seeded starting
+conv + BatchNorm + ReLU modules, CrossEntropyLoss) and configs[4] (SequentialNeuralNetwork{Parallel conv lanes, DenseNet
+modules, MaxPool} -> convolutional LSTMNeuralNetwork, SquaredLoss) after a few Nadam steps from seeded inputs and seeded starting
 parameters (tests/cases.py), float and double.  Run in the build container (needs /root/reference):
 
     python tests/golden/make_golden_networks.py
@@ -36,6 +37,12 @@ def main():
         p1, loss, _ = ref.train_resnet(x, obj, 32, 2, C.RESNET_SMALL, params_in=C.seeded_params(n, dt, 4002))
         out["resnet/%s/p1" % suf] = p1
         out["resnet/%s/loss" % suf] = np.array([loss])
+        x, obj = C.seqnet_inputs(dt)
+        n5 = ref.train_seqnet(x, obj, 8, -1, **C.SEQNET_SMALL)
+        p1, loss5, _ = ref.train_seqnet(x, obj, 8, 2, params_in=C.seeded_params(n5, dt, 5002), **C.SEQNET_SMALL)
+        out["seqnet/%s/p1" % suf] = p1
+        out["seqnet/%s/loss" % suf] = np.array([loss5])
+        print(suf, "seqnet params", n5, "loss", loss5)
         print(suf, "autoencoder params", out["autoencoder/%s/p1" % suf].size, "resnet params", n, "loss", loss)
     path = os.path.join(HERE, "reference_networks.npz")
     np.savez_compressed(path, **out)

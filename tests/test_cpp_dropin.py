@@ -198,6 +198,33 @@ def test_config4_resnet_training_matches_reference(b200, golden_nets, dt):
 
 
 @pytest.mark.parametrize("dt", DTYPES)
+def test_config5_sequence_network_training_matches_reference(b200, golden_nets, dt):
+    """BASELINE.json configs[4] at test size: SequentialNeuralNetwork{ParallelNeuralNetwork of conv lanes,
+    DenseNeuralNetwork, MaxPool} feeding a convolutional LSTMNeuralNetwork (ConvKernelLayer kernels, shared across the
+    time steps), sequential SquaredLoss + Nadam: parameters and epoch loss after 4 steps against the unmodified
+    reference (fixture; live where oracle/_ref travelled)."""
+    suf = "f32" if dt == np.float32 else "f64"
+    x, obj = C.seqnet_inputs(dt)
+    n = b200.train_seqnet(x, obj, 8, -1, **C.SEQNET_SMALL)
+    assert n == golden_nets["seqnet/%s/p1" % suf].size
+    p0 = C.seeded_params(n, dt, 5002)
+    p1, loss, _ = b200.train_seqnet(x, obj, 8, 2, params_in=p0, **C.SEQNET_SMALL)
+    tol = 1e-4 if dt == np.float32 else 1e-9
+    err = C.relerr(p1, golden_nets["seqnet/%s/p1" % suf])
+    print("config 5 sequence network, 4 Nadam steps: loss %.6f (ref %.6f), param err %.2e"
+          % (loss, float(golden_nets["seqnet/%s/loss" % suf][0]), err))
+    assert err < tol
+    assert abs(loss - float(golden_nets["seqnet/%s/loss" % suf][0])) < tol * max(1.0, abs(loss))
+    if binding.have_ref():
+        ref = binding.Oracle("ref")
+        x, obj = C.seqnet_inputs(dt, total=24, seq=4, seed=5003)
+        pr, lr, _ = ref.train_seqnet(x, obj, 8, 2, params_in=p0, **C.SEQNET_SMALL)
+        pb, lb, _ = b200.train_seqnet(x, obj, 8, 2, params_in=p0, **C.SEQNET_SMALL)
+        assert C.relerr(pb, pr) < (5e-4 if dt == np.float32 else 1e-8), C.relerr(pb, pr)
+        assert abs(lr - lb) < (1e-4 if dt == np.float32 else 1e-9) * max(1.0, abs(lr))
+
+
+@pytest.mark.parametrize("dt", DTYPES)
 def test_fused_and_unfused_network_loops_agree(dt):
     """CATTL3_NO_FUSION=1 / CATTL3_HOST_LOOP=1 switch the epilogue fusion and the device batch loop off: the same
     training run must give the same parameters either way (fusion changes where work happens, not what is computed)."""
