@@ -23,6 +23,7 @@
 #include "b200/Communicator.hpp"
 #include "b200/DeviceLayer.hpp"
 #include "b200/DeviceNetwork.hpp"
+#include "b200/DeviceSequenceNetwork.hpp"
 #include "b200/DeviceLoss.hpp"
 #include "parameters/B200Parameters.hpp"
 
@@ -49,6 +50,8 @@
 #include "neural_network/StackedNeuralNetwork.hpp"
 #include "neural_network/DenseNeuralNetwork.hpp"
 #include "neural_network/ParallelNeuralNetwork.hpp"
+#include "neural_network/SequentialNeuralNetwork.hpp"
+#include "neural_network/LSTMNeuralNetwork.hpp"
 #include "data_provider/MemoryDataProvider.hpp"
 #include "neural_network/FeedforwardNeuralNetwork.hpp"
 #include "neural_network/ResidualNeuralNetwork.hpp"

@@ -85,8 +85,8 @@ public:
 		offset = std::min(this->instances, offset + instances);
 	}
 	inline bool device_resident() {
-		if (Sequential || instances == 0)
-			return false;
+		if (instances == 0)
+			return false;   // (sequences included: samples are the fastest rank, a mini-batch is a row slice either way)
 		if (!dev_obs.empty())
 			return true;
 		static const double budget_gb = [] {

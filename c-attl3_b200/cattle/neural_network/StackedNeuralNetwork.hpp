@@ -8,7 +8,9 @@
  * Feedforward / Residual / Stacked networks) pass their activations on in HBM, and the stack is itself a
  * device network, so e.g. the encoder / decoder pair of examples/mnist_autoencoder.cpp:26-46 trains without
  * a host round trip between the two halves.  Blocks that only speak the host API are bridged with a round
- * trip around them; sequential stacks (rank + 2 tensors: the recurrent networks) keep the host protocol.
+ * trip around them.  Sequential stacks (rank + 2 tensors) do the same over b200::DeviceSequenceNetwork blocks (the
+ * B200 SequentialNeuralNetwork / LSTMNeuralNetwork / sequential stacks); a sequential stack without any such block
+ * keeps the reference's host protocol.
  */
 #ifndef C_ATTL3_NEURAL_NETWORK_STACKEDNEURALNETWORK_H_
 #define C_ATTL3_NEURAL_NETWORK_STACKEDNEURALNETWORK_H_
@@ -20,13 +22,15 @@
 
 #include "neural_network/CompositeNeuralNetwork.hpp"
 #include "b200/DeviceNetwork.hpp"
+#include "b200/DeviceSequenceNetwork.hpp"
 
 namespace cattle {
 
 namespace b200 {
-/** The device face exists for non-sequential stacks only. */
+/** The device face of a stack: a device network, or (sequential stacks) a device sequence network. */
 template<typename Scalar, std::size_t Rank, bool Sequential> struct StackDeviceFace { };
 template<typename Scalar, std::size_t Rank> struct StackDeviceFace<Scalar,Rank,false> : public DeviceNetwork<Scalar,Rank> { };
+template<typename Scalar, std::size_t Rank> struct StackDeviceFace<Scalar,Rank,true> : public DeviceSequenceNetwork<Scalar,Rank> { };
 }
 
 template<typename Scalar, std::size_t Rank, bool Sequential>
@@ -37,6 +41,7 @@ class StackedNeuralNetwork :
 	typedef StackedNeuralNetwork<Scalar,Rank,Sequential> Self;
 	typedef NeuralNetPtr<Scalar,Rank,Sequential> Block;
 	typedef b200::DeviceNetwork<Scalar,Rank> DevNet;
+	typedef b200::DeviceSequenceNetwork<Scalar,Rank> DevSeqNet;
 	typedef b200::DeviceTensor<Scalar> DevTensor;
 	typedef std::integral_constant<bool,Sequential> IsSequential;
 public:
@@ -148,6 +153,39 @@ public:
 		}
 		return out_grad;
 	}
+	/** b200::DeviceSequenceNetwork (sequential stacks): block to block in HBM, rows = samples * time steps. */
+	inline DevTensor propagate_seq_dev(DevTensor input, std::size_t samples, bool training) {
+		for (const Block& block : blocks) {
+			if (DevSeqNet* dev_block = dynamic_cast<DevSeqNet*>(block.get())) {
+				input = dev_block->propagate_seq_dev(std::move(input), samples, training);
+			} else {
+				input = b200::sequence_to_device<Scalar,Rank + 2>(block->propagate(
+						b200::sequence_to_host<Scalar,Rank>(input, samples, block->get_input_dims()), training));
+			}
+		}
+		return input;
+	}
+	inline DevTensor backpropagate_seq_dev(DevTensor out_grad, std::size_t samples) {
+		for (std::size_t i = blocks.size(); i > 0 && !out_grad.empty(); --i) {
+			Base& block = *blocks[i - 1];
+			if (DevSeqNet* dev_block = dynamic_cast<DevSeqNet*>(&block)) {
+				out_grad = dev_block->backpropagate_seq_dev(std::move(out_grad), samples);
+			} else {
+				out_grad = b200::sequence_to_device<Scalar,Rank + 2>(block.backpropagate(
+						b200::sequence_to_host<Scalar,Rank>(out_grad, samples, block.get_output_dims())));
+			}
+		}
+		return out_grad;
+	}
+	/** b200::DeviceSequenceNetwork: a step graph needs every block on the device and none carrying state across steps. */
+	inline bool graph_safe() const {
+		for (const Block& block : blocks) {
+			const DevSeqNet* dev_block = dynamic_cast<const DevSeqNet*>(block.get());
+			if (!dev_block || !dev_block->graph_safe())
+				return false;
+		}
+		return true;
+	}
 	inline friend void swap(Self& network1, Self& network2) {
 		using std::swap;
 		swap(network1.blocks, network2.blocks);
@@ -161,13 +199,31 @@ private:
 		vec.push_back(std::move(block));
 		return vec;
 	}
-	// sequential stacks: the reference's host protocol (StackedNeuralNetwork.hpp:111-121)
+	// sequential stacks: one upload, the device chain, one download -- or, without any device sequence block, the
+	// reference's host protocol (StackedNeuralNetwork.hpp:111-121)
+	inline bool has_device_sequence_block() const {
+		for (const Block& block : blocks) {
+			if (dynamic_cast<DevSeqNet*>(block.get()))
+				return true;
+		}
+		return false;
+	}
 	inline typename Base::Data propagate_host(typename Base::Data input, bool training, std::true_type) {
+		if (has_device_sequence_block()) {
+			const std::size_t samples = input.dimension(0);
+			DevTensor out = propagate_seq_dev(b200::sequence_to_device<Scalar,Rank + 2>(input), samples, training);
+			return b200::sequence_to_host<Scalar,Rank>(out, samples, output_dims);
+		}
 		for (const Block& block : blocks)
 			input = block->propagate(std::move(input), training);
 		return input;
 	}
 	inline typename Base::Data backpropagate_host(typename Base::Data out_grad, std::true_type) {
+		if (has_device_sequence_block()) {
+			const std::size_t samples = out_grad.dimension(0);
+			DevTensor prev_out_grad = backpropagate_seq_dev(b200::sequence_to_device<Scalar,Rank + 2>(out_grad), samples);
+			return b200::sequence_to_host<Scalar,Rank>(prev_out_grad, samples, input_dims);
+		}
 		for (std::size_t i = blocks.size(); i > 0; --i)
 			out_grad = blocks[i - 1]->backpropagate(std::move(out_grad));
 		return out_grad;

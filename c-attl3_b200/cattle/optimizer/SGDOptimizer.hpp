@@ -81,8 +81,8 @@ protected:
 		double obj_loss = 0, reg_loss = 0;
 		std::size_t instances = 0, updates = 0;
 		std::vector<Parameters<Scalar>*> params_vec = net.get_all_unique_params();
-		b200::DeviceNetwork<Scalar,Rank>* dev_net = Sequential || !device_loop() ? nullptr :
-				dynamic_cast<b200::DeviceNetwork<Scalar,Rank>*>(&net);
+		DeviceFace face(net, device_loop());
+		DeviceFace* dev_net = face ? &face : nullptr;
 		const b200::DeviceLoss<Scalar>* dev_loss = dynamic_cast<const b200::DeviceLoss<Scalar>*>(Base::loss.get());
 		std::vector<b200::DeviceBuffer<Scalar>> step_losses;
 		b200::DeviceDataSource<Scalar>* dev_data = dev_net && dev_loss ?
@@ -299,6 +299,49 @@ protected:
 	const std::size_t batch_size;
 private:
 	typedef std::array<b200::DeviceBuffer<Scalar>,3> StateArrays;
+	/**
+	 * The device face of the network being trained: a b200::DeviceNetwork, or for sequential data a
+	 * b200::DeviceSequenceNetwork, whose tensors carry samples * time steps rows (b200/DeviceSequenceNetwork.hpp) while
+	 * the data provider and the loss see one row per sample -- the same array, a different row count.
+	 */
+	class DeviceFace {
+	public:
+		inline DeviceFace(typename Base::Net& net, bool enabled) :
+				plain(nullptr),
+				seq(nullptr),
+				in_volume(net.get_input_dims().get_volume()),
+				out_volume(net.get_output_dims().get_volume()),
+				samples(0) {
+			if (!enabled)
+				return;
+			if (Sequential)
+				seq = dynamic_cast<b200::DeviceSequenceNetwork<Scalar,Rank>*>(&net);
+			else
+				plain = dynamic_cast<b200::DeviceNetwork<Scalar,Rank>*>(&net);
+		}
+		inline explicit operator bool() const {
+			return plain || seq;
+		}
+		inline b200::DeviceTensor<Scalar> propagate_dev(b200::DeviceTensor<Scalar> input, bool training) {
+			if (plain)
+				return plain->propagate_dev(std::move(input), training);
+			samples = input.rows;
+			input.rows = samples * (input.size() / samples / in_volume);
+			b200::DeviceTensor<Scalar> out = seq->propagate_seq_dev(std::move(input), samples, training);
+			out.rows = samples;
+			return out;
+		}
+		inline b200::DeviceTensor<Scalar> backpropagate_dev(b200::DeviceTensor<Scalar> out_grad) {
+			if (plain)
+				return plain->backpropagate_dev(std::move(out_grad));
+			out_grad.rows = samples * (out_grad.size() / samples / out_volume);
+			return seq->backpropagate_seq_dev(std::move(out_grad), samples);
+		}
+	private:
+		b200::DeviceNetwork<Scalar,Rank>* plain;
+		b200::DeviceSequenceNetwork<Scalar,Rank>* seq;
+		std::size_t in_volume, out_volume, samples;
+	};
 	enum StepMode { STEP_EAGER, STEP_SCALARS_ONLY, STEP_CAPTURE };
 	/**
 	 * A training step captured as a CUDA graph (cattl3_graph, include/cattl3_b200.h): forward, loss, backward and the
@@ -361,16 +404,22 @@ private:
 	};
 	/**
 	 * Whether the training step of `net` can be captured: one process, every layer and every parameter on the device,
-	 * nothing whose host-side arguments change from step to step (dropout seeds) and nothing that reads parameters on
-	 * the host in the step (regularisation penalties, value or gradient constraints).  CATTL3_NO_GRAPH=1 disables it.
+	 * nothing whose host-side arguments change from step to step (dropout seeds), nothing that reads parameters on
+	 * the host in the step (regularisation penalties, value or gradient constraints) and, for sequential networks,
+	 * nothing carried across steps on the device (DeviceSequenceNetwork::graph_safe).  CATTL3_NO_GRAPH=1 disables it.
 	 */
 	inline static bool graph_eligible(typename Base::Net& net, const std::vector<Parameters<Scalar>*>& params_vec) {
 		static const bool enabled = [] {
 			const char* v = std::getenv("CATTL3_NO_GRAPH");
 			return !(v && v[0] && v[0] != '0');
 		}();
-		if (!enabled || Sequential || b200::Communicator::get().world_size() > 1)
+		if (!enabled || b200::Communicator::get().world_size() > 1)
 			return false;
+		if (Sequential) {
+			const b200::DeviceSequenceNetwork<Scalar,Rank>* seq = dynamic_cast<const b200::DeviceSequenceNetwork<Scalar,Rank>*>(&net);
+			if (!seq || !seq->graph_safe())
+				return false;
+		}
 		for (Layer<Scalar,Rank>* layer : net.get_layers()) {
 			if (!dynamic_cast<b200::DeviceLayer<Scalar,Rank>*>(layer) || dynamic_cast<DropoutLayer<Scalar,Rank>*>(layer))
 				return false;
@@ -409,7 +458,7 @@ private:
 		return bytes;
 	}
 	/** One step at `graph`'s shape: captured on first use, replayed afterwards.  False = run this step eagerly. */
-	inline bool graph_step(b200::DeviceNetwork<Scalar,Rank>& dev_net, const b200::DeviceLoss<Scalar>& dev_loss,
+	inline bool graph_step(DeviceFace& dev_net, const b200::DeviceLoss<Scalar>& dev_loss,
 			typename Base::Net& net, const std::vector<Parameters<Scalar>*>& params_vec, const b200::DeviceTensor<Scalar>& obs,
 			const b200::DeviceTensor<Scalar>& obj, std::size_t epoch) {
 		b200::Context& c = b200::Context::get();

@@ -874,6 +874,11 @@ int optimizer_step(cattl3_ctx* ctx, const cattl3_opt_step* st, int64_t count, S*
 }
 
 // ---- glue ----------------------------------------------------------------------------------------
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+
 // y = OP(x, y) over 16-byte vectors with a scalar tail; OP 0: y + x, 1: x * alpha, 2: fma(alpha, x, y), 3: y * x
 template<typename S, int OP>
 __global__ void __launch_bounds__(256) glue_kernel(long long count, int vec_ok, S alpha, const S* __restrict__ x, S* __restrict__ y) {
@@ -905,6 +910,47 @@ template<typename S> int axpy(cattl3_ctx* ctx, int64_t count, S alpha, const S* 
 template<typename S> int add_inplace(cattl3_ctx* ctx, int64_t count, S* y, const S* x) { return glue<S, 0>(ctx, "add_inplace", count, (S) 0, x, y); }
 template<typename S> int scale(cattl3_ctx* ctx, int64_t count, S alpha, const S* x, S* y) { return glue<S, 1>(ctx, "scale", count, alpha, x, y); }
 template<typename S> int mul_inplace(cattl3_ctx* ctx, int64_t count, S* y, const S* x) { return glue<S, 3>(ctx, "mul_inplace", count, (S) 0, x, y); }
+
+// out = (accumulate ? out : 0) + a * b + (c ? c * d : 0): the gate arithmetic of an LSTM cell (state = forget * previous +
+// write * candidate, hidden = read * activated state, and the products of its backward pass) in one pass over 16-byte
+// vectors.  Products and sums are rounded separately (no contraction), as Eigen's expression `a * b + c * d` is.
+template<typename S>
+__global__ void __launch_bounds__(256) muladd_kernel(long long count, int vec_ok, int accumulate, const S* __restrict__ a,
+		const S* __restrict__ b, const S* __restrict__ c, const S* __restrict__ d, S* out) {
+	typedef typename V16<S>::type V;
+	constexpr int G = V16<S>::G;
+	const long long nvec = vec_ok ? count / G : 0;
+	const long long stride = (long long) gridDim.x * 256;
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < nvec; i += stride) {
+		V va = reinterpret_cast<const V*>(a)[i], vb = reinterpret_cast<const V*>(b)[i], vc, vd, vo;
+		if (c) { vc = reinterpret_cast<const V*>(c)[i]; vd = reinterpret_cast<const V*>(d)[i]; }
+		if (accumulate) vo = reinterpret_cast<const V*>(out)[i];
+		S* ea = reinterpret_cast<S*>(&va); S* eb = reinterpret_cast<S*>(&vb); S* ec = reinterpret_cast<S*>(&vc);
+		S* ed = reinterpret_cast<S*>(&vd); S* eo = reinterpret_cast<S*>(&vo);
+		#pragma unroll
+		for (int k = 0; k < G; ++k) {
+			S r = mul_rn(ea[k], eb[k]);
+			if (c) r = add_rn(r, mul_rn(ec[k], ed[k]));
+			eo[k] = accumulate ? add_rn(eo[k], r) : r;
+		}
+		reinterpret_cast<V*>(out)[i] = vo;
+	}
+	for (long long i = nvec * G + blockIdx.x * 256ll + threadIdx.x; i < count; i += stride) {
+		S r = mul_rn(a[i], b[i]);
+		if (c) r = add_rn(r, mul_rn(c[i], d[i]));
+		out[i] = accumulate ? add_rn(out[i], r) : r;
+	}
+}
+template<typename S>
+static int muladd(cattl3_ctx* ctx, int64_t count, int accumulate, const S* a, const S* b, const S* c, const S* d, S* out) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(count > 0 && a && b && out && ((c == nullptr) == (d == nullptr)), "muladd: bad arguments");
+	const int vec_ok = aligned16(a) && aligned16(b) && aligned16(out) && (!c || (aligned16(c) && aligned16(d)));
+	muladd_kernel<S><<<ew_grid(ctx, ceil_div(count, V16<S>::G), 256), 256, 0, ctx->stream>>>(count, vec_ok, accumulate, a, b, c,
+			d, out);
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
 
 // y[i] = value: device-side constants (e.g. the element count that travels with synchronised batch-norm sums) without a
 // host -> device copy, which from pageable memory would synchronise the host with the stream.
@@ -1169,6 +1215,10 @@ int cattl3_optimizer_step_indirect_f64(cattl3_ctx* c, int kind, const cattl3_opt
 	return optimizer_step<double>(c, &st, count, p, g, s1, s2, s3, dev_step); }
 int cattl3_add_inplace_f32(cattl3_ctx* c, int64_t count, float* y, const float* x) { return add_inplace<float>(c, count, y, x); }
 int cattl3_add_inplace_f64(cattl3_ctx* c, int64_t count, double* y, const double* x) { return add_inplace<double>(c, count, y, x); }
+int cattl3_muladd_f32(cattl3_ctx* c, int64_t count, int accumulate, const float* a, const float* b, const float* cc, const float* d, float* out) {
+	return muladd<float>(c, count, accumulate, a, b, cc, d, out); }
+int cattl3_muladd_f64(cattl3_ctx* c, int64_t count, int accumulate, const double* a, const double* b, const double* cc, const double* d, double* out) {
+	return muladd<double>(c, count, accumulate, a, b, cc, d, out); }
 int cattl3_mul_inplace_f32(cattl3_ctx* c, int64_t count, float* y, const float* x) { return mul_inplace<float>(c, count, y, x); }
 int cattl3_mul_inplace_f64(cattl3_ctx* c, int64_t count, double* y, const double* x) { return mul_inplace<double>(c, count, y, x); }
 int cattl3_scale_f32(cattl3_ctx* c, int64_t count, float alpha, const float* x, float* y) { return scale<float>(c, count, alpha, x, y); }

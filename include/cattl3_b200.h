@@ -386,6 +386,11 @@ int cattl3_add_inplace_f64(cattl3_ctx*, int64_t count, double* y, const double* 
 /* y *= x: the PARALLEL_MUL merge of ParallelNeuralNetwork (ParallelNeuralNetwork.hpp:170-173, 286-291). */
 int cattl3_mul_inplace_f32(cattl3_ctx*, int64_t count, float* y, const float* x);
 int cattl3_mul_inplace_f64(cattl3_ctx*, int64_t count, double* y, const double* x);
+/* out = (accumulate ? out : 0) + a * b + (c ? c * d : 0), c and d both NULL or both set; `out` may alias an operand.  The gate
+ * arithmetic of an LSTM cell and of its backward pass (C-ATTL3/neural_network/LSTMNeuralNetwork.hpp:290-296, 369-371,
+ * 441-447): products and sums are rounded separately, as in the reference's Eigen expressions. */
+int cattl3_muladd_f32(cattl3_ctx*, int64_t count, int accumulate, const float* a, const float* b, const float* c, const float* d, float* out);
+int cattl3_muladd_f64(cattl3_ctx*, int64_t count, int accumulate, const double* a, const double* b, const double* c, const double* d, double* out);
 /* y = alpha * x (the 1/batch_size scaling of the loss gradient, SGDOptimizer.hpp:55-56). */
 int cattl3_scale_f32(cattl3_ctx*, int64_t count, float alpha, const float* x, float* y);
 int cattl3_scale_f64(cattl3_ctx*, int64_t count, double alpha, const double* x, double* y);

@@ -9,6 +9,9 @@ synchronised BatchNorm statistics -- on BASELINE.json's network configs:
   --config 4 : ResNet-style ResidualNeuralNetwork (stem conv 7x7/2 + BN + ReLU + MaxPool, `--blocks` modules of
                Conv3x3-BN-ReLU-Conv3x3-BN at `--width` channels, MeanPool + Dense + Softmax head), 224x224x3,
                batch 64 per GPU, data parallel (weak scaling)
+  --config 5 : sequences of `--seq` 32x32x3 frames through SequentialNeuralNetwork{ParallelNeuralNetwork of conv lanes,
+               DenseNeuralNetwork, MaxPool} and a convolutional LSTMNeuralNetwork head (`--width` channels, default 16),
+               batch 64 per GPU, sequential SquaredLoss + Nadam
 
 The driver is oracle/ref_shim.cpp compiled UNCHANGED against the B200 headers (tests/cpp/_build/libcattle_b200_shim.so);
 `--impl reference` runs the same driver compiled against the unmodified reference on the host cores (bounded sample).
@@ -34,7 +37,7 @@ import numpy as np  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, default=4, choices=[1, 3, 4])
+    ap.add_argument("--config", type=int, default=4, choices=[1, 3, 4, 5])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
@@ -43,6 +46,7 @@ def main():
     ap.add_argument("--width", type=int, default=64)
     ap.add_argument("--blocks", type=int, default=4)
     ap.add_argument("--image", type=int, default=224)
+    ap.add_argument("--seq", type=int, default=8, help="config 5: frames per sequence")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -59,10 +63,10 @@ def main():
         lib = binding.Oracle("ref", path=shim)
         assert lib.lib.ref_is_b200_build() == 1
         world_eff = world
-    per_gpu = args.batch or {1: 64, 3: 512, 4: 64}[args.config]
+    per_gpu = args.batch or {1: 64, 3: 512, 4: 64, 5: 64}[args.config]
     batch = per_gpu * world_eff                     # the nominal (global) batch the optimizer is built with
     total = batch * args.steps
-    rng = np.random.default_rng({1: 1001, 3: 3001, 4: 4001}[args.config])   # identical data on every rank
+    rng = np.random.default_rng({1: 1001, 3: 3001, 4: 4001, 5: 5001}[args.config])   # identical data on every rank
     if args.config == 1:
         x = np.asfortranarray(rng.uniform(-1, 1, (total, 32, 32, 3)).astype(dt))
         obj = np.zeros((total, 1, 1, 10), dtype=dt, order="F")
@@ -73,6 +77,15 @@ def main():
         x = np.asfortranarray(rng.uniform(0, 1, (total, 28, 28, 1)).astype(dt))
         run = lambda epochs: lib.train_autoencoder(x, batch, epochs)
         name = "mnist auto-encoder 28x28x1"
+    elif args.config == 5:
+        # BASELINE.json configs[4]: sequences of 32x32x3 frames through Sequential{Parallel conv lanes, DenseNet modules,
+        # MaxPool} and a convolutional LSTM head (oracle/ref_shim.cpp seqnet_impl); --width lanes / modules / state channels
+        width = args.width if args.width != 64 else 16
+        x = np.asfortranarray(rng.uniform(-1, 1, (total, args.seq, 32, 32, 3)).astype(dt))
+        obj = np.asfortranarray(rng.uniform(-0.5, 0.5, (total, 1, 16, 16, width)).astype(dt))
+        run = lambda epochs: lib.train_seqnet(x, obj, batch, epochs, width, width)
+        name = ("sequence net: %d frames 32x32x3, Parallel{conv3x3, conv1x1} -> DenseNet x2 -> MaxPool -> conv LSTM, %d ch"
+                % (args.seq, width))
     else:
         s = args.image
         x = np.asfortranarray(rng.uniform(-1, 1, (total, s, s, 3)).astype(dt))

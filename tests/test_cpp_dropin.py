@@ -34,7 +34,7 @@ DTYPES = [np.float32, np.float64]
 # the hot-path tests of the reference's gradient_test.cpp and the networks built on them
 GTEST_FILTER = ":".join("GradientTest." + t for t in (
     "DenseKernelLayer", "ConvKernelLayer", "TransConvKernelLayer", "ActivationLayer", "PoolLayer",
-    "BatchNormLayer", "ResidualNet", "DenseNet", "ParallelNet", "SequentialNet", "LSTMNet"))
+    "BatchNormLayer", "ResidualNet", "DenseNet", "ParallelNet", "SequentialNet", "RecurrentNet", "LSTMNet", "BidirectionalNet"))
 
 
 @pytest.fixture(scope="module")
@@ -225,6 +225,32 @@ def test_config5_sequence_network_training_matches_reference(b200, golden_nets, 
 
 
 @pytest.mark.parametrize("dt", DTYPES)
+def test_sequence_network_device_loop_equals_host_loop(dt):
+    """Config 5 trains through the device sequence path (b200::DeviceSequenceNetwork: the time-step fold as a view, the
+    LSTM unrolled in HBM, device loss); CATTL3_HOST_LOOP=1 keeps the reference's host protocol between network and loss
+    (every network then uploads / downloads around itself).  Same run, same parameters."""
+    code = (
+        "import sys, numpy as np; sys.path[:0] = [%r, %r]\n"
+        "import cases as C; from oracle import binding\n"
+        "lib = binding.Oracle('ref', path=%r); dt = np.%s\n"
+        "x, obj = C.seqnet_inputs(dt, total=24, seq=4, seed=5004); n = lib.train_seqnet(x, obj, 8, -1, **C.SEQNET_SMALL)\n"
+        "p, l, _ = lib.train_seqnet(x, obj, 8, 2, params_in=C.seeded_params(n, dt, 5002), **C.SEQNET_SMALL)\n"
+        "np.save(sys.argv[1], p)\n" % (ROOT, os.path.join(ROOT, "tests"), SHIM, np.dtype(dt).name))
+    import tempfile
+    outs = []
+    with tempfile.TemporaryDirectory() as d:
+        for i, env in enumerate(({}, {"CATTL3_HOST_LOOP": "1"})):
+            path = os.path.join(d, "p%d.npy" % i)
+            r = subprocess.run([os.sys.executable, "-c", code, path], env=dict(os.environ, **env), capture_output=True,
+                               text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            outs.append(np.load(path))
+    err = C.relerr(outs[0], outs[1])
+    print("config 5: device loop vs host loop parameters after 6 steps: %.2e" % err)
+    assert err < (2e-6 if dt == np.float32 else 1e-13)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
 def test_fused_and_unfused_network_loops_agree(dt):
     """CATTL3_NO_FUSION=1 / CATTL3_HOST_LOOP=1 switch the epilogue fusion and the device batch loop off: the same
     training run must give the same parameters either way (fusion changes where work happens, not what is computed)."""
@@ -249,13 +275,14 @@ def test_fused_and_unfused_network_loops_agree(dt):
     assert err < (2e-5 if dt == np.float32 else 1e-10)
 
 
-@pytest.mark.parametrize("net", ["cifar", "autoencoder", "resnet"])
+@pytest.mark.parametrize("net", ["cifar", "autoencoder", "resnet", "seqnet"])
 @pytest.mark.parametrize("dt", DTYPES)
 def test_step_graph_equals_eager_loop(dt, net):
     """The batch loop captures a launch-bound training step as a CUDA graph after two eager steps at a shape
     (cattl3_graph_*, SGDOptimizer.hpp StepGraph) and replays it; CATTL3_NO_GRAPH=1 keeps every step eager.  Same run,
     same parameters and the same epoch loss either way -- including a ragged last batch (run eagerly between replays),
-    a second epoch (the graph outlives the epoch) and BatchNorm's running statistics (resnet)."""
+    a second epoch (the graph outlives the epoch), BatchNorm's running statistics (resnet) and the unrolled convolutional
+    LSTM of config 5 (seqnet: its time-step copies and gate kernels are nodes of the graph)."""
     body = {
         "cifar": "x = C.rand(np.random.default_rng(1003), (72, 32, 32, 3), dt)\n"
                  "obj = np.zeros((72, 1, 1, 10), dtype=dt, order='F'); obj[np.arange(72), 0, 0, np.arange(72) % 10] = 1\n"
@@ -264,6 +291,8 @@ def test_step_graph_equals_eager_loop(dt, net):
                        "p, l, _ = lib.train_autoencoder(x, 32, 2, params_in=C.seeded_params(n, dt, 3002))\n",
         "resnet": "x, obj = C.resnet_inputs(dt, total=176); n = lib.train_resnet(x, obj, 32, -1, C.RESNET_SMALL)\n"
                   "p, l, _ = lib.train_resnet(x, obj, 32, 2, C.RESNET_SMALL, params_in=C.seeded_params(n, dt, 4002))\n",
+        "seqnet": "x, obj = C.seqnet_inputs(dt, total=44, seq=4, seed=5005); n = lib.train_seqnet(x, obj, 8, -1, **C.SEQNET_SMALL)\n"
+                  "p, l, _ = lib.train_seqnet(x, obj, 8, 2, params_in=C.seeded_params(n, dt, 5002), **C.SEQNET_SMALL)\n",
     }[net]
     if net == "cifar":
         body = body.replace("%s", "f32" if dt == np.float32 else "f64")
@@ -347,4 +376,4 @@ def test_reference_gradient_test_passes():
     tail = "\n".join(r.stdout.splitlines()[-25:])
     print(tail)
     assert r.returncode == 0, tail + "\n" + r.stderr[-2000:]
-    assert "[  PASSED  ] 11 tests" in r.stdout, tail
+    assert "[  PASSED  ] 13 tests" in r.stdout, tail
