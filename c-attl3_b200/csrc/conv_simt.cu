@@ -12,6 +12,7 @@
 // The weight gradient is a split-K reduction over m = N*OH*OW with a deterministic second stage
 // that ACCUMULATES into the gradient (Parameters::accumulate_grad semantics,
 // C-ATTL3/parameters/StandardParameters.hpp:115-123).
+#include <algorithm>
 #include "activations.cuh"
 
 namespace cattl3 {
@@ -557,9 +558,48 @@ __global__ void __launch_bounds__(256) colsum_thread_kernel(long long rows, long
 	}
 }
 
+// Few long columns (the bias gradient of a layer with a handful of filters over many pixels: 16 columns of 524 288
+// rows left 132 SMs idle with one block per column): grid (columns, chunks) of per-chunk sums into scratch, then one
+// thread per column adds the chunks in order.  Deterministic.
+template<typename S>
+__global__ void __launch_bounds__(256) colsum_chunk_kernel(long long rows, long long chunk, const S* __restrict__ a,
+		S* __restrict__ partial) {
+	__shared__ S red[256];
+	const S* col = a + rows * (long long) blockIdx.x;
+	const long long lo = (long long) blockIdx.y * chunk, hi = lo + chunk < rows ? lo + chunk : rows;
+	S s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+	long long i = lo + threadIdx.x;
+	for (; i + 768 < hi; i += 1024) { s0 += col[i]; s1 += col[i + 256]; s2 += col[i + 512]; s3 += col[i + 768]; }
+	for (; i < hi; i += 256) s0 += col[i];
+	red[threadIdx.x] = (s0 + s1) + (s2 + s3);
+	__syncthreads();
+	for (int o = 128; o > 0; o >>= 1) {
+		if ((int) threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) partial[(long long) blockIdx.x * gridDim.y + blockIdx.y] = red[0];
+}
+template<typename S>
+__global__ void __launch_bounds__(256) colsum_final_kernel(long long cols, int chunks, const S* __restrict__ partial,
+		S* __restrict__ out) {
+	const long long c = blockIdx.x * 256ll + threadIdx.x;
+	if (c >= cols) return;
+	S s = 0;
+	for (int k = 0; k < chunks; ++k) s += partial[c * chunks + k];
+	out[c] += s;
+}
+
 template<typename S>
 int colsum_accumulate(cattl3_ctx* ctx, int64_t rows, int64_t cols, const S* a, S* out) {
-	if (rows >= 128) {
+	const int64_t chunks = std::min<int64_t>(ceil_div((int64_t) 4 * ctx->sm_count, cols), rows / 4096);
+	if (chunks > 1 && cols <= 65535) {
+		CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, (size_t) (cols * chunks) * sizeof(S)));
+		const int64_t chunk = ceil_div(ceil_div(rows, chunks), 256) * 256;
+		const int64_t used = ceil_div(rows, chunk);
+		colsum_chunk_kernel<S><<<dim3((unsigned) cols, (unsigned) used), 256, 0, ctx->stream>>>(rows, chunk, a, (S*) ctx->ws);
+		CATTL3_LAUNCHED(ctx);
+		colsum_final_kernel<S><<<(unsigned) ceil_div(cols, 256), 256, 0, ctx->stream>>>(cols, (int) used, (const S*) ctx->ws, out);
+	} else if (rows >= 128) {
 		colsum_block_kernel<S><<<(unsigned) cols, 256, 0, ctx->stream>>>(rows, a, out);
 	} else {
 		colsum_thread_kernel<S><<<ew_grid(ctx, cols, 256), 256, 0, ctx->stream>>>(rows, cols, a, out);

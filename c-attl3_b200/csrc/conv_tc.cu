@@ -951,30 +951,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 	if (warp == 1) tmem_dealloc(tmem_base, 512u);
 }
 
-// dw(tap, r, j) += sum over splits of the scratch tiles, in split order (deterministic).
-__global__ void __launch_bounds__(256) wgrad_reduce_tc_kernel(const TcWgradParams p, int T, float* __restrict__ dw,
+// dw(tap, r, j) += sum over splits of the scratch tiles; db(j) += sum over splits of the column sums.  Small layers
+// (an LSTM gate kernel: 2 304 weights, 128 splits) made the one-thread-per-weight loop over the splits a chain of
+// dependent strided loads (20 us for 1 MB); here eight warps of a block share 32 outputs, each summing every eighth
+// split, and the eight partial sums are added in a fixed order: deterministic, and a few loads deep.
+constexpr int WR_ZL = 8;
+__global__ void __launch_bounds__(32 * WR_ZL) wgrad_reduce_tc_kernel(const TcWgradParams p, int T, float* __restrict__ dw,
 		float* __restrict__ db) {
-	const long long total = (long long) T * p.R * p.J;
+	__shared__ float red[WR_ZL][32];
+	const long long n_dw = (long long) T * p.R * p.J;
+	const long long total = n_dw + (db != nullptr ? p.J : 0);   // the bias gradient's columns follow the weights
 	const int tiles = p.col_tiles * p.j_tiles;
-	if (db != nullptr && blockIdx.x == 0) {
-		for (int j = threadIdx.x; j < p.J; j += 256) {
-			float s = 0.f;
-			for (int z = 0; z < p.splits; ++z) s += p.db_partial[(long long) z * p.j_tiles * TC_BM + j];
-			db[j] += s;
+	const int lane = threadIdx.x & 31, zl = threadIdx.x >> 5;
+	for (long long base = blockIdx.x * 32ll; base < total; base += (long long) gridDim.x * 32) {
+		const long long i = base + lane;
+		const float* src = nullptr;
+		long long z_stride = 0;
+		float* dst = nullptr;
+		if (i < n_dw) {
+			const int j = (int) (i % p.J);
+			const int r = (int) ((i / p.J) % p.R);
+			const int tap = (int) (i / ((long long) p.J * p.R));
+			const int box = tap * p.rchunks + r / p.RB;
+			const int ct = box / p.boxes_per_tile;
+			const int col = (box % p.boxes_per_tile) * p.RB + r % p.RB;
+			const int jt = j / TC_BM, row = j % TC_BM;
+			src = p.partial + ((long long) (ct + p.col_tiles * jt) * p.BNW + col) * 128 + row;
+			z_stride = (long long) tiles * p.BNW * 128;
+			dst = dw + tap * p.w_stap + r * p.w_sr + j * p.w_sj;
+		} else if (i < total) {
+			const int j = (int) (i - n_dw);
+			src = p.db_partial + j;
+			z_stride = (long long) p.j_tiles * TC_BM;
+			dst = db + j;
 		}
-	}
-	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long) gridDim.x * 256) {
-		const int j = (int) (i % p.J);
-		const int r = (int) ((i / p.J) % p.R);
-		const int tap = (int) (i / ((long long) p.J * p.R));
-		const int box = tap * p.rchunks + r / p.RB;
-		const int ct = box / p.boxes_per_tile;
-		const int col = (box % p.boxes_per_tile) * p.RB + r % p.RB;
-		const int jt = j / TC_BM, row = j % TC_BM;
-		const long long off = ((long long) (ct + p.col_tiles * jt) * p.BNW + col) * 128 + row;
 		float s = 0.f;
-		for (int z = 0; z < p.splits; ++z) s += p.partial[(long long) z * tiles * p.BNW * 128 + off];
-		dw[tap * p.w_stap + r * p.w_sr + j * p.w_sj] += s;
+		if (src) {
+			#pragma unroll 4
+			for (int z = zl; z < p.splits; z += WR_ZL) s += src[z * z_stride];
+		}
+		red[zl][lane] = s;
+		__syncthreads();
+		if (zl == 0 && dst) {
+			float t = red[0][lane];
+			#pragma unroll
+			for (int k = 1; k < WR_ZL; ++k) t += red[k][lane];
+			*dst += t;
+		}
+		__syncthreads();
 	}
 }
 
@@ -1037,7 +1061,7 @@ int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const 
 	CATTL3_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 	tc_wgrad_kernel<<<tiles * p.splits, TC_THREADS, smem_bytes, ctx->stream>>>(tm_b, p);
 	CATTL3_LAUNCHED(ctx);
-	wgrad_reduce_tc_kernel<<<ew_grid(ctx, p.dw_elems, 256), 256, 0, ctx->stream>>>(p, T, dw, db);
+	wgrad_reduce_tc_kernel<<<ew_grid(ctx, ceil_div(p.dw_elems + (db ? gg.J : 0), 32), 1), 32 * WR_ZL, 0, ctx->stream>>>(p, T, dw, db);
 	CATTL3_LAUNCHED(ctx);
 	return CATTL3_OK;
 }

@@ -34,7 +34,7 @@ def timed(stream, fn, reps):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="all", choices=["all", "conv", "mem", "fused"])
+    ap.add_argument("--only", default="all", choices=["all", "conv", "small", "mem", "fused"])
     ap.add_argument("--double", action="store_true", help="also run the double (DFMA) kernel-layer sweep")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 SIMT, 3 big-tile FMA (no tensor cores)")
@@ -47,12 +47,20 @@ def main():
     pk = peaks()
     out = lambda d: print(json.dumps(d), flush=True)
 
-    if args.only in ("all", "conv"):
+    if args.only in ("all", "conv", "small"):
         sweeps = [("3x3 s1 d0 (config 2)", (256, 56, 56, 64, 256, 3, 3, 1, 1, 1, 1, 0, 0)),
                   ("3x3 s2 d0", (256, 56, 56, 64, 256, 3, 3, 1, 1, 2, 2, 0, 0)),
                   ("3x3 s1 d1", (256, 56, 56, 64, 256, 3, 3, 2, 2, 1, 1, 1, 1)),
                   ("1x1 s1", (256, 56, 56, 64, 256, 1, 1, 0, 0, 1, 1, 0, 0)),
                   ("3x3 s1 d0 256->256 28x28", (256, 28, 28, 256, 256, 3, 3, 1, 1, 1, 1, 0, 0))]
+        if args.only == "small":
+            # the kernel layers of the network configs (4: ResNet modules at batch 64; 5: conv lanes over 512 frames and the
+            # LSTM gate kernels at batch 64): small GEMMs where fixed costs decide; run with --reps 50 and --path 0 / 1 / 3
+            sweeps = [("config 5 LSTM input kernel 16x16x64->16", (64, 16, 16, 64, 16, 3, 3, 1, 1, 1, 1, 0, 0)),
+                      ("config 5 LSTM state kernel 16x16x16->16", (64, 16, 16, 16, 16, 3, 3, 1, 1, 1, 1, 0, 0)),
+                      ("config 5 dense module 32x32x32->16", (512, 32, 32, 32, 16, 3, 3, 1, 1, 1, 1, 0, 0)),
+                      ("config 5 lane 32x32x3->16", (512, 32, 32, 3, 16, 3, 3, 1, 1, 1, 1, 0, 0)),
+                      ("config 4 module 56x56x64->64 n64", (64, 56, 56, 64, 64, 3, 3, 1, 1, 1, 1, 0, 0))]
         for dtype in [torch.float32] + ([torch.float64] if args.double else []):
             for name, geom in sweeps:
                 g = pkg.ConvGeom(*geom)
