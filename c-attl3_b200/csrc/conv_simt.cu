@@ -220,13 +220,31 @@ __global__ void __launch_bounds__(256) wgrad_kernel(GatherGeom gg, const S* __re
 	}
 }
 
+// dw[i] += sum over splits of partial[split][i].  A small gradient with many splits (432 weights, 592 CTAs' partials)
+// is a long chain of dependent loads for one thread per weight: eight warps of a block share 32 weights instead, each
+// summing every eighth split, and the eight sums are added in a fixed order (deterministic).
 template<typename S>
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const S* __restrict__ partial, int splits,
 		long long elems, S* __restrict__ dw) {
-	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < elems; i += (long long) gridDim.x * 256) {
-		S s = 0;
-		for (int z = 0; z < splits; ++z) s += partial[(long long) z * elems + i];
-		dw[i] += s;
+	__shared__ S red[8][32];
+	const int lane = threadIdx.x & 31, zl = threadIdx.x >> 5;
+	for (long long base = blockIdx.x * 32ll; base < elems; base += (long long) gridDim.x * 32) {
+		const long long i = base + lane;
+		S s0 = 0, s1 = 0;
+		if (i < elems) {
+			int z = zl;
+			for (; z + 8 < splits; z += 16) { s0 += partial[(long long) z * elems + i]; s1 += partial[(long long) (z + 8) * elems + i]; }
+			if (z < splits) s0 += partial[(long long) z * elems + i];
+		}
+		red[zl][lane] = s0 + s1;
+		__syncthreads();
+		if (zl == 0 && i < elems) {
+			S t = red[0][lane];
+			#pragma unroll
+			for (int k = 1; k < 8; ++k) t += red[k][lane];
+			dw[i] += t;
+		}
+		__syncthreads();
 	}
 }
 
@@ -246,7 +264,7 @@ int simt_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* pla
 	dim3 grid((unsigned) gx, (unsigned) gy, (unsigned) splits);
 	wgrad_kernel<S><<<grid, 256, 0, ctx->stream>>>(gg, src, plain, (S*) ctx->ws, m_per_split, elems);
 	CATTL3_LAUNCHED(ctx);
-	wgrad_reduce_kernel<S><<<ew_grid(ctx, elems, 256), 256, 0, ctx->stream>>>((const S*) ctx->ws,
+	wgrad_reduce_kernel<S><<<ew_grid(ctx, ceil_div(elems, 32), 1), 256, 0, ctx->stream>>>((const S*) ctx->ws,
 			(int) splits, elems, dw);
 	CATTL3_LAUNCHED(ctx);
 	return CATTL3_OK;
@@ -433,17 +451,20 @@ template int skinny_gather_gemm<double>(cattl3_ctx*, const GatherGeom&, const do
 // tiny_wgrad_kernel: the whole K x J gradient (K = taps * channels <= 256, K * J <= 2048) is one CTA's
 // output; the CTAs split the reduction over m.  Per chunk of MC rows the gathered source rows [MC][K]
 // and the plain rows [MC][J] go to shared memory (coalesced along m), then every thread adds the chunk
-// into its <= 8 outputs.  Partials per CTA, deterministic reduce (wgrad_reduce_kernel).
-template<typename S>
+// into its <= 8 outputs: <= 8 / JT items of one reduction index k and JT consecutive filters, so that one
+// read of the source value and one (vector) read of the JT plain values feed JT FMAs (with one output per
+// item the loop was two shared-memory reads per FMA and bound by them).  Partials per CTA, deterministic
+// reduce (wgrad_reduce_kernel).
+template<typename S, int JT>
 __global__ void __launch_bounds__(256) tiny_wgrad_kernel(GatherGeom gg, const S* __restrict__ src,
 		const S* __restrict__ plain, S* __restrict__ partial, long long m_per_cta, long long dw_elems) {
-	constexpr int MC = 32;
+	constexpr int MC = 32, ITEMS = 8 / JT;
 	extern __shared__ __align__(16) unsigned char tiny_smem[];
-	const int T = gg.RH * gg.RW, R = gg.SC, J = gg.J, K = T * R, KJ = K * J;
+	const int T = gg.RH * gg.RW, R = gg.SC, J = gg.J, K = T * R, JG = J / JT, KG = K * JG;
 	const int Kp = K | 1;   // odd pitch: the transposing stores spread over the banks
-	S* As = reinterpret_cast<S*>(tiny_smem);       // [MC][Kp]
-	S* Bs = As + MC * Kp;                           // [MC][J]
-	int* ktab = reinterpret_cast<int*>(Bs + MC * J); // per k: rh*bh + ch (16 bits) | rw*bw + cw (16 bits), and the channel
+	S* Bs = reinterpret_cast<S*>(tiny_smem);       // [MC][J] (first: 16-byte aligned rows when J % 4 == 0)
+	S* As = Bs + MC * J;                            // [MC][Kp]
+	int* ktab = reinterpret_cast<int*>(As + MC * Kp); // per k: rh*bh + ch (16 bits) | rw*bw + cw (16 bits), and the channel
 	for (int k = threadIdx.x; k < K; k += 256) {
 		const int tap = k / R, r = k - tap * R, rw = tap / gg.RH, rh = tap - rw * gg.RH;
 		ktab[2 * k] = ((rh * gg.bh + gg.ch) << 16) | ((rw * gg.bw + gg.cw) & 0xFFFF);
@@ -454,9 +475,16 @@ __global__ void __launch_bounds__(256) tiny_wgrad_kernel(GatherGeom gg, const S*
 	const long long me = ms + m_per_cta < M ? ms + m_per_cta : M;
 	const long long plane = (long long) gg.N * gg.SH * gg.SW;
 	const int mm = threadIdx.x % MC, l0 = threadIdx.x / MC;   // loader: row mm of the chunk, items l0 + 8 * i
-	S acc[8];
+	S acc[ITEMS][JT];
+	int item_k[ITEMS], item_j[ITEMS];
 	#pragma unroll
-	for (int i = 0; i < 8; ++i) acc[i] = (S) 0;
+	for (int i = 0; i < ITEMS; ++i) {
+		const int o = threadIdx.x + 256 * i;
+		item_j[i] = o < KG ? (o / K) * JT : -1;
+		item_k[i] = o < KG ? o % K : 0;
+		#pragma unroll
+		for (int t = 0; t < JT; ++t) acc[i][t] = (S) 0;
+	}
 	__syncthreads();
 	for (long long mc = ms; mc < me; mc += MC) {
 		const long long m = mc + mm;
@@ -475,25 +503,36 @@ __global__ void __launch_bounds__(256) tiny_wgrad_kernel(GatherGeom gg, const S*
 		for (int j = l0; j < J; j += 256 / MC) Bs[mm * J + j] = ok ? __ldg(plain + m + M * j) : (S) 0;
 		__syncthreads();
 		#pragma unroll
-		for (int i = 0; i < 8; ++i) {
-			const int o = threadIdx.x + 256 * i;
-			if (o < KJ) {
-				const int j = o / K, k = o - j * K;
-				S a = acc[i];
+		for (int i = 0; i < ITEMS; ++i) {
+			if (item_j[i] >= 0) {
+				const S* ap = As + item_k[i];
+				const S* bp = Bs + item_j[i];
 				#pragma unroll 8
-				for (int r = 0; r < MC; ++r) a = fma(As[r * Kp + k], Bs[r * J + j], a);
-				acc[i] = a;
+				for (int r = 0; r < MC; ++r) {
+					const S a = ap[r * Kp];
+					S bv[JT];
+					if constexpr (JT == 4 && sizeof(S) == 4) {
+						const float4 v = *reinterpret_cast<const float4*>(bp + r * J);
+						bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
+					} else {
+						#pragma unroll
+						for (int t = 0; t < JT; ++t) bv[t] = bp[r * J + t];
+					}
+					#pragma unroll
+					for (int t = 0; t < JT; ++t) acc[i][t] = fma(a, bv[t], acc[i][t]);
+				}
 			}
 		}
 		__syncthreads();
 	}
 	S* dst = partial + (long long) blockIdx.x * dw_elems;
 	#pragma unroll
-	for (int i = 0; i < 8; ++i) {
-		const int o = threadIdx.x + 256 * i;
-		if (o < KJ) {
-			const int j = o / K, k = o - j * K, tap = k / R, r = k - tap * R;
-			dst[tap * gg.w_stap + r * gg.w_sr + j * gg.w_sj] = acc[i];
+	for (int i = 0; i < ITEMS; ++i) {
+		if (item_j[i] >= 0) {
+			const int k = item_k[i], tap = k / R, r = k - tap * R;
+			#pragma unroll
+			for (int t = 0; t < JT; ++t)
+				dst[tap * gg.w_stap + r * gg.w_sr + (item_j[i] + t) * gg.w_sj] = acc[i][t];
 		}
 	}
 }
@@ -514,14 +553,19 @@ int tiny_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* pla
 	const long long M = (long long) gg.N * gg.OH * gg.OW;
 	const long long elems = (long long) K * gg.J;
 	long long ctas = ceil_div(M, 512);
-	if (ctas > 4ll * ctx->sm_count) ctas = 4ll * ctx->sm_count;
+	if (ctas > 8ll * ctx->sm_count) ctas = 8ll * ctx->sm_count;
 	const long long m_per_cta = ceil_div(ceil_div(M, ctas), 32) * 32;
 	ctas = ceil_div(M, m_per_cta);
 	CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, (size_t) (ctas * elems) * sizeof(S)));
 	const size_t smem = (size_t) (32 * ((K | 1) + gg.J)) * sizeof(S) + 8 * (size_t) K;
-	tiny_wgrad_kernel<S><<<(unsigned) ctas, 256, smem, ctx->stream>>>(gg, src, plain, (S*) ctx->ws, m_per_cta, elems);
+	if (gg.J % 4 == 0)
+		tiny_wgrad_kernel<S, 4><<<(unsigned) ctas, 256, smem, ctx->stream>>>(gg, src, plain, (S*) ctx->ws, m_per_cta, elems);
+	else if (gg.J % 2 == 0)
+		tiny_wgrad_kernel<S, 2><<<(unsigned) ctas, 256, smem, ctx->stream>>>(gg, src, plain, (S*) ctx->ws, m_per_cta, elems);
+	else
+		tiny_wgrad_kernel<S, 1><<<(unsigned) ctas, 256, smem, ctx->stream>>>(gg, src, plain, (S*) ctx->ws, m_per_cta, elems);
 	CATTL3_LAUNCHED(ctx);
-	wgrad_reduce_kernel<S><<<ew_grid(ctx, elems, 256), 256, 0, ctx->stream>>>((const S*) ctx->ws, (int) ctas, elems, dw);
+	wgrad_reduce_kernel<S><<<ew_grid(ctx, ceil_div(elems, 32), 1), 256, 0, ctx->stream>>>((const S*) ctx->ws, (int) ctas, elems, dw);
 	CATTL3_LAUNCHED(ctx);
 	return CATTL3_OK;
 }
