@@ -171,6 +171,57 @@ def test_two_process_resnet_with_synchronised_batchnorm_equals_one_process(tmp_p
     assert abs(loss1[0] - loss2[0]) < 1e-5 * max(1.0, abs(loss1[0]))
 
 
+_DP_SEQNET_WORKER = r"""
+import os, sys
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import cases as C
+from oracle import binding
+lib = binding.Oracle("ref", path={shim!r})
+dt = np.float32 if sys.argv[1] == "f32" else np.float64
+x, obj = C.seqnet_inputs(dt, total=48, seq=4, seed=5006)
+n = lib.train_seqnet(x, obj, 16, -1, **C.SEQNET_SMALL)
+p, loss, ms = lib.train_seqnet(x, obj, 16, 2, params_in=C.seeded_params(n, dt, 5002), **C.SEQNET_SMALL)
+np.save(sys.argv[2], p)
+print("LOSS %.9f" % loss)
+"""
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("suf", ["f32", "f64"])
+def test_two_process_sequence_network_equals_one_process(tmp_path, suf):
+    """Config 5 at test size on 2 GPUs: the sequence batch is sharded by samples (rows of the (samples * steps) x volume
+    layout stay together per sample), the LSTM's shared-parameter gradients are all-reduced with the rest of the
+    arena; two processes on half-batches must reproduce the single-process run and hold identical parameters."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    shim = os.path.join(ROOT, "tests", "cpp", "_build", "libcattle_b200_shim.so")
+    script = tmp_path / "dp_seqnet_worker.py"
+    script.write_text(_DP_SEQNET_WORKER.format(root=ROOT, shim=shim))
+
+    def run(world):
+        procs = []
+        for r in range(world):
+            env = dict(os.environ, WORLD_SIZE=str(world), RANK=str(r), LOCAL_RANK=str(r), MASTER_PORT="29547",
+                       CATTL3_COMM_ID_FILE=str(tmp_path / ("sid_%d" % world)))
+            procs.append(subprocess.Popen([sys.executable, str(script), suf, str(tmp_path / ("sp_%d_%d.npy" % (world, r)))],
+                                          env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+        outs = [p.communicate(timeout=600)[0] for p in procs]
+        for p, o in zip(procs, outs):
+            assert p.returncode == 0, o[-3000:]
+        losses = [float(o.split("LOSS")[1].split()[0]) for o in outs]
+        return [np.load(tmp_path / ("sp_%d_%d.npy" % (world, r))) for r in range(world)], losses
+
+    one, loss1 = run(1)
+    two, loss2 = run(2)
+    assert np.array_equal(two[0], two[1]), "ranks diverged"
+    err = C.relerr(two[0], one[0])
+    print("sequence network, 1 vs 2 processes (%s): param err %.2e, loss %.7f vs %.7f" % (suf, err, loss1[0], loss2[0]))
+    assert err < (1e-4 if suf == "f32" else 1e-9), err
+    assert abs(loss1[0] - loss2[0]) < 1e-5 * max(1.0, abs(loss1[0]))
+
+
 _GLOO_BN_WORKER = r"""
 import os, sys
 import numpy as np
