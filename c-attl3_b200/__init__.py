@@ -80,7 +80,7 @@ _SYMBOLS = [
     "cattl3_conv_forward", "cattl3_conv_backward", "cattl3_transconv_forward", "cattl3_transconv_backward",
     "cattl3_dense_forward", "cattl3_dense_backward", "cattl3_activation_forward", "cattl3_activation_backward",
     "cattl3_pool_forward", "cattl3_pool_backward", "cattl3_batchnorm_forward", "cattl3_batchnorm_backward",
-    "cattl3_optimizer_step", "cattl3_optimizer_step_indirect", "cattl3_add_inplace", "cattl3_mul_inplace", "cattl3_muladd", "cattl3_scale", "cattl3_axpy",
+    "cattl3_optimizer_step", "cattl3_optimizer_step_indirect", "cattl3_add_inplace", "cattl3_mul_inplace", "cattl3_muladd", "cattl3_regularize", "cattl3_scale", "cattl3_axpy",
     "cattl3_conv_forward_fused", "cattl3_dense_forward_fused", "cattl3_transconv_forward_fused", "cattl3_batchnorm_forward_stats",
     "cattl3_dropout_forward", "cattl3_dropout_backward", "cattl3_loss",
     "cattl3_batchnorm_stats", "cattl3_batchnorm_backward_sums", "cattl3_batchnorm_backward_apply",
@@ -312,6 +312,12 @@ class Context:
 
     def add_inplace(self, count, y, x):
         self._call("cattl3_add_inplace", y.dtype, ctypes.c_int64(count), _p(y), _p(x))
+
+    def regularize(self, count, l1, l2, values, grad, penalty):
+        """grad += sign(values) * l1 + l2 * values; penalty (float64 device scalar) += l1 |values|_1 + l2 / 2 |values|^2."""
+        _, ct = _suffix(values.dtype)
+        self._call("cattl3_regularize", values.dtype, ctypes.c_int64(count), ct(l1), ct(l2), _p(values), _p(grad),
+                   _p(penalty))
 
     def scale(self, count, alpha, x, y):
         _, ct = _suffix(x.dtype)

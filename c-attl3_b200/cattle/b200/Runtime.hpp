@@ -163,6 +163,8 @@ template<> struct Api<S> { \
 		return cattl3_add_inplace_##SUF(c, count, y, x); } \
 	static int mul_inplace(cattl3_ctx* c, std::int64_t count, S* y, const S* x) { \
 		return cattl3_mul_inplace_##SUF(c, count, y, x); } \
+	static int regularize(cattl3_ctx* c, std::int64_t count, S l1, S l2, const S* values, S* grad, double* penalty) { \
+		return cattl3_regularize_##SUF(c, count, l1, l2, values, grad, penalty); } \
 	static int muladd(cattl3_ctx* c, std::int64_t count, int accumulate, const S* a, const S* b, const S* cc, const S* d, S* out) { \
 		return cattl3_muladd_##SUF(c, count, accumulate, a, b, cc, d, out); } \
 	static int scale(cattl3_ctx* c, std::int64_t count, S alpha, const S* x, S* y) { \

@@ -163,6 +163,7 @@ protected:
 		}
 		obj_loss += collect_graph_loss() + carried_graph_loss;
 		carried_graph_loss = 0;
+		reg_loss += collect_device_penalty();
 		for (const b200::DeviceBuffer<Scalar>& losses : step_losses) {
 			std::vector<Scalar> host(losses.size());
 			losses.download(host.data(), host.size());
@@ -405,7 +406,7 @@ private:
 	/**
 	 * Whether the training step of `net` can be captured: one process, every layer and every parameter on the device,
 	 * nothing whose host-side arguments change from step to step (dropout seeds), nothing that reads parameters on
-	 * the host in the step (regularisation penalties, value or gradient constraints) and, for sequential networks,
+	 * the host in the step (penalties other than L1 / L2 / ElasticNet, value or gradient constraints) and, for sequential networks,
 	 * nothing carried across steps on the device (DeviceSequenceNetwork::graph_safe).  CATTL3_NO_GRAPH=1 disables it.
 	 */
 	inline static bool graph_eligible(typename Base::Net& net, const std::vector<Parameters<Scalar>*>& params_vec) {
@@ -426,7 +427,7 @@ private:
 		}
 		for (Parameters<Scalar>* params_ptr : params_vec) {
 			B200Parameters<Scalar>* dev = dynamic_cast<B200Parameters<Scalar>*>(params_ptr);
-			if (!dev || dev->has_regularization() || dev->has_value_constraints() || dev->has_grad_constraints())
+			if (!dev || dev->has_host_regularization() || dev->has_value_constraints() || dev->has_grad_constraints())
 				return false;
 		}
 		return true;
@@ -505,6 +506,8 @@ private:
 							g.loss_rows.data()));
 				}
 				dev_net.backpropagate_dev(std::move(out_grad));
+				double no_host_penalty = 0;
+				regularize_all(params_vec, no_host_penalty);   // device penalties only (graph_eligible)
 				step_mode = STEP_CAPTURE;
 				_update_params(params_vec, epoch - 1, timestep);
 				step_mode = STEP_EAGER;
@@ -598,12 +601,7 @@ private:
 			double& reg_loss, std::size_t& updates) {
 		if (comm.world_size() > 1)
 			all_reduce_gradients(params_vec, comm);
-		for (Parameters<Scalar>* params_ptr : params_vec) {
-			if (!params_ptr->are_optimizable() || params_ptr->are_frozen())
-				continue;
-			reg_loss += params_ptr->get_regularization_penalty();
-			params_ptr->regularize();
-		}
+		regularize_all(params_vec, reg_loss);
 		_update_params(params_vec, epoch - 1, timestep);
 		++updates;
 		++timestep;
@@ -614,6 +612,35 @@ private:
 		b200::Context& c = b200::Context::get();
 		b200::Context::Lock l = c.lock();
 		CATTLE_B200_CHECK(cattl3_ctx_throttle(c.handle(), 2));
+	}
+	/**
+	 * Penalty and penalty derivative of every optimizable, non-frozen parameter (SGDOptimizer.hpp:59-64).  L1 / L2 /
+	 * ElasticNet penalties of device parameters are one kernel each (cattl3_regularize) that also adds the penalty to
+	 * a device accumulator, fetched once per epoch; anything else takes the reference's host route.
+	 */
+	inline void regularize_all(const std::vector<Parameters<Scalar>*>& params_vec, double& reg_loss) {
+		for (Parameters<Scalar>* params_ptr : params_vec) {
+			if (!params_ptr->are_optimizable() || params_ptr->are_frozen())
+				continue;
+			B200Parameters<Scalar>* dev = dynamic_cast<B200Parameters<Scalar>*>(params_ptr);
+			if (dev && dev->has_device_regularization()) {
+				if (reg_accum.empty())
+					reg_accum = b200::DeviceBuffer<double>(1, true);
+				dev->regularize_dev(reg_accum.data());
+			} else {
+				reg_loss += params_ptr->get_regularization_penalty();
+				params_ptr->regularize();
+			}
+		}
+	}
+	/** The penalties accumulated on the device since the last call (synchronises). */
+	inline double collect_device_penalty() {
+		if (reg_accum.empty())
+			return 0;
+		double host = 0;
+		reg_accum.download(&host, 1);
+		reg_accum.zero();
+		return host;
 	}
 	/**
 	 * Host tensor -> device through one of the process's two input feeds (0: observations, 1: objectives; created
@@ -718,6 +745,7 @@ private:
 	std::size_t eager_steps_at_shape = 0, eager_shape_rows = 0, eager_step_bytes = 0;
 	bool graphs_failed = false;
 	double carried_graph_loss = 0;
+	b200::DeviceBuffer<double> reg_accum;   // penalties of the device-regularised parameters, summed over the epoch's steps
 	StepMode step_mode = STEP_EAGER;
 	// optimizer state per device parameter array (keyed by the device address of its first value) and
 	// per host-resident Parameters object

@@ -28,6 +28,8 @@
 #include "core/ParameterInitialization.hpp"
 #include "core/ParameterRegularization.hpp"
 #include "core/Parameters.hpp"
+#include "parameter_regularization/ElasticNetParameterRegularization.hpp"
+#include "parameter_regularization/L1ParameterRegularization.hpp"
 #include "parameter_regularization/L2ParameterRegularization.hpp"
 #include "b200/Runtime.hpp"
 
@@ -148,7 +150,8 @@ public:
 				grad_clip(grad_clip),
 				grad_max_l1_norm(grad_max_l1_norm),
 				grad_max_l2_norm(grad_max_l2_norm),
-				l2_lambda(probe_l2_lambda(reg)),
+				l1_lambda(probe_lambdas(reg).first),
+				l2_lambda(probe_lambdas(reg).second),
 				value_store(value_store ? value_store : std::make_shared<Storage>(rows * cols)),
 				grad_store(!optimizable ? nullptr : (grad_store ? grad_store : std::make_shared<Storage>(rows * cols))),
 				offset(offset),
@@ -172,6 +175,7 @@ public:
 			grad_clip(other.grad_clip),
 			grad_max_l1_norm(other.grad_max_l1_norm),
 			grad_max_l2_norm(other.grad_max_l2_norm),
+			l1_lambda(other.l1_lambda),
 			l2_lambda(other.l2_lambda),
 			value_store(std::make_shared<Storage>(other.rows * other.cols)),
 			grad_store(other.optimizable ? std::make_shared<Storage>(other.rows * other.cols) : nullptr),
@@ -277,16 +281,29 @@ public:
 	inline void regularize() {
 		if (!optimizable || !param_reg)
 			return;
-		if (l2_lambda > 0 && !has_grad_constraints()) {
-			// L2: grad += lambda * values (L2ParameterRegularization.hpp:31-33), on the device
-			b200::Context& c = b200::Context::get();
-			b200::Context::Lock l = c.lock();
-			CATTLE_B200_CHECK(b200::Api<Scalar>::axpy(c.handle(), (std::int64_t) count(), l2_lambda,
-					device_values(), device_grad()));
-			grad_written_on_device();
-		} else {
+		if (has_device_regularization())
+			regularize_dev(nullptr);
+		else
 			accumulate_grad(param_reg->d_function(get_values()));
-		}
+	}
+	/**
+	 * Whether the regularisation runs on the device: an L1, L2 or ElasticNet penalty (their derivative and value are
+	 * one kernel, cattl3_regularize) and no gradient constraint that would have to be re-applied on the host
+	 * (accumulate_grad, StandardParameters.hpp:115-123).
+	 */
+	inline bool has_device_regularization() const {
+		return optimizable && param_reg && (l1_lambda > 0 || l2_lambda > 0) && !has_grad_constraints();
+	}
+	/**
+	 * regularize() and get_regularization_penalty() in one pass on the device: grad += d penalty / d values and, if
+	 * `penalty` is given, *penalty += the penalty (a device double: the batch loop reads it once per epoch).
+	 */
+	inline void regularize_dev(double* penalty) {
+		b200::Context& c = b200::Context::get();
+		b200::Context::Lock l = c.lock();
+		CATTLE_B200_CHECK(b200::Api<Scalar>::regularize(c.handle(), (std::int64_t) count(), l1_lambda, l2_lambda,
+				device_values(), device_grad(), penalty));
+		grad_written_on_device();
 	}
 	inline bool are_frozen() const {
 		return frozen;
@@ -339,6 +356,10 @@ public:
 	inline bool has_regularization() const {
 		return (bool) param_reg;
 	}
+	/** A regularisation that is evaluated on the host (any other than L1 / L2 / ElasticNet, or one next to gradient constraints). */
+	inline bool has_host_regularization() const {
+		return optimizable && param_reg && !has_device_regularization();
+	}
 	inline bool has_value_constraints() const {
 		return active(value_clip) || active(value_max_l1_norm) || active(value_max_l2_norm);
 	}
@@ -350,7 +371,7 @@ public:
 		return l2_lambda;
 	}
 	inline bool has_non_l2_regularization() const {
-		return param_reg && !(l2_lambda > 0);
+		return param_reg && !(l2_lambda > 0 && !(l1_lambda > 0));
 	}
 private:
 	inline static bool active(Scalar limit) {
@@ -377,10 +398,23 @@ private:
 		}
 	}
 	/** L2ParameterRegularization keeps lambda private; d_function([1]) = [lambda] reveals it. */
-	inline static Scalar probe_l2_lambda(const ParamRegSharedPtr<Scalar>& reg) {
-		if (!reg || !dynamic_cast<const L2ParameterRegularization<Scalar>*>(reg.get()))
-			return 0;
-		return reg->d_function(Matrix<Scalar>::Ones(1, 1))(0, 0);
+	/**
+	 * (l1 lambda, l2 lambda) of an L1 / L2 / ElasticNet regularisation, read off its derivative (the classes keep their
+	 * constants private): d(1) = l1 + l2 and d(2) = l1 + 2 l2.  (0, 0) for anything else.
+	 */
+	inline static std::pair<Scalar,Scalar> probe_lambdas(const ParamRegSharedPtr<Scalar>& reg) {
+		if (!reg)
+			return std::make_pair((Scalar) 0, (Scalar) 0);
+		const Scalar d1 = reg->d_function(Matrix<Scalar>::Ones(1, 1))(0, 0);
+		if (dynamic_cast<const L2ParameterRegularization<Scalar>*>(reg.get()))
+			return std::make_pair((Scalar) 0, d1);
+		if (dynamic_cast<const L1ParameterRegularization<Scalar>*>(reg.get()))
+			return std::make_pair(d1, (Scalar) 0);
+		if (dynamic_cast<const ElasticNetParameterRegularization<Scalar>*>(reg.get())) {
+			const Scalar d2 = reg->d_function(Matrix<Scalar>::Constant(1, 1, (Scalar) 2))(0, 0);
+			return std::make_pair(2 * d1 - d2, d2 - d1);
+		}
+		return std::make_pair((Scalar) 0, (Scalar) 0);
 	}
 	const std::size_t rows, cols;
 	const bool optimizable;
@@ -388,7 +422,7 @@ private:
 	const ParamRegSharedPtr<Scalar> param_reg;
 	const Scalar value_clip, value_max_l1_norm, value_max_l2_norm;
 	const Scalar grad_clip, grad_max_l1_norm, grad_max_l2_norm;
-	const Scalar l2_lambda;
+	const Scalar l1_lambda, l2_lambda;
 	StorageSharedPtr value_store, grad_store;
 	const std::size_t offset;
 	mutable Matrix<Scalar> values_host, grad_host;

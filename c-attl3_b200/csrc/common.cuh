@@ -25,6 +25,8 @@ struct cattl3_ctx {
 	// per-CTA column sums of a fused batch-norm statistics epilogue (conv_tc.cu)
 	void* stat_ws = nullptr;
 	size_t stat_ws_bytes = 0;
+	// cattl3_regularize: 256 per-block partial penalties + the "blocks done" counter
+	void* reg_ws = nullptr;
 	// between cattl3_graph_begin and cattl3_graph_end: the stream is capturing (nothing may synchronise or grow scratch)
 	bool capturing = false;
 	// Step graphs keep their activations in a private arena (graphs with allocation nodes launch slowly): while capturing,

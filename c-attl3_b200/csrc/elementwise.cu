@@ -952,6 +952,62 @@ static int muladd(cattl3_ctx* ctx, int64_t count, int accumulate, const S* a, co
 	return CATTL3_OK;
 }
 
+// Parameter regularisation on the device (L1 / L2 / ElasticNet: C-ATTL3/parameter_regularization/*.hpp):
+//   grad[i] += (v >= 0 ? l1 : -l1) + l2 * v      (Parameters::regularize, StandardParameters.hpp:133-136)
+//   penalty += l1 * sum |v| + l2 / 2 * sum v^2   (get_regularization_penalty; accumulated in double on the device, so that
+//                                                 the batch loop needs no host read of the parameters per step)
+// Per-block partial penalties go to scratch; the last block to finish (a counter) adds them in block order: deterministic.
+template<typename S>
+__global__ void __launch_bounds__(256) regularize_kernel(long long count, S l1, S l2, const S* __restrict__ v, S* __restrict__ g,
+		double* __restrict__ partial, unsigned int* __restrict__ done, double* __restrict__ penalty) {
+	__shared__ double red[256];
+	__shared__ bool last;
+	double abs_sum = 0, sq_sum = 0;
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < count; i += (long long) gridDim.x * 256) {
+		const S x = v[i];
+		if (g) g[i] = add_rn(g[i], add_rn(x >= (S) 0 ? l1 : -l1, mul_rn(x, l2)));
+		abs_sum += fabs((double) x);
+		sq_sum += (double) x * (double) x;
+	}
+	if (!penalty) return;
+	red[threadIdx.x] = (double) l1 * abs_sum + 0.5 * (double) l2 * sq_sum;
+	__syncthreads();
+	for (int o = 128; o > 0; o >>= 1) {
+		if ((int) threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		partial[blockIdx.x] = red[0];
+		__threadfence();
+		last = atomicAdd(done, 1u) == gridDim.x - 1;
+	}
+	__syncthreads();
+	if (last && threadIdx.x == 0) {
+		__threadfence();
+		double s = 0;
+		for (unsigned int b = 0; b < gridDim.x; ++b) s += ((volatile double*) partial)[b];
+		*penalty += s;
+		*done = 0;   // ready for the next launch
+	}
+}
+template<typename S>
+static int regularize(cattl3_ctx* ctx, int64_t count, S l1, S l2, const S* values, S* grad, double* penalty) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(count > 0 && values && (grad || penalty), "regularize: bad arguments");
+	int grid = ew_grid(ctx, count, 1024);
+	if (grid > 256) grid = 256;
+	// scratch: 256 partials + the counter, private to this kernel (zeroed once: the kernel leaves the counter at 0)
+	if (!ctx->reg_ws) {
+		CATTL3_REQUIRE(!ctx->capturing, "regularize: first use during graph capture (run the step eagerly first)");
+		CATTL3_CUDA(cudaMalloc(&ctx->reg_ws, 257 * sizeof(double)));
+		CATTL3_CUDA(cudaMemsetAsync(ctx->reg_ws, 0, 257 * sizeof(double), ctx->stream));
+	}
+	regularize_kernel<S><<<grid, 256, 0, ctx->stream>>>(count, l1, l2, values, grad, (double*) ctx->reg_ws,
+			(unsigned int*) ((double*) ctx->reg_ws + 256), penalty);
+	CATTL3_LAUNCHED(ctx);
+	return CATTL3_OK;
+}
+
 // y[i] = value: device-side constants (e.g. the element count that travels with synchronised batch-norm sums) without a
 // host -> device copy, which from pageable memory would synchronise the host with the stream.
 template<typename S>
@@ -1219,6 +1275,10 @@ int cattl3_muladd_f32(cattl3_ctx* c, int64_t count, int accumulate, const float*
 	return muladd<float>(c, count, accumulate, a, b, cc, d, out); }
 int cattl3_muladd_f64(cattl3_ctx* c, int64_t count, int accumulate, const double* a, const double* b, const double* cc, const double* d, double* out) {
 	return muladd<double>(c, count, accumulate, a, b, cc, d, out); }
+int cattl3_regularize_f32(cattl3_ctx* c, int64_t count, float l1, float l2, const float* values, float* grad, double* penalty) {
+	return regularize<float>(c, count, l1, l2, values, grad, penalty); }
+int cattl3_regularize_f64(cattl3_ctx* c, int64_t count, double l1, double l2, const double* values, double* grad, double* penalty) {
+	return regularize<double>(c, count, l1, l2, values, grad, penalty); }
 int cattl3_mul_inplace_f32(cattl3_ctx* c, int64_t count, float* y, const float* x) { return mul_inplace<float>(c, count, y, x); }
 int cattl3_mul_inplace_f64(cattl3_ctx* c, int64_t count, double* y, const double* x) { return mul_inplace<double>(c, count, y, x); }
 int cattl3_scale_f32(cattl3_ctx* c, int64_t count, float alpha, const float* x, float* y) { return scale<float>(c, count, alpha, x, y); }

@@ -379,6 +379,14 @@ int cattl3_optimizer_step_f64(cattl3_ctx*, const cattl3_opt_step*, int64_t count
 int cattl3_optimizer_step_indirect_f32(cattl3_ctx*, int kind, const cattl3_opt_step* dev_step, int64_t count, float* p, float* g, float* s1, float* s2, float* s3);
 int cattl3_optimizer_step_indirect_f64(cattl3_ctx*, int kind, const cattl3_opt_step* dev_step, int64_t count, double* p, double* g, double* s1, double* s2, double* s3);
 
+/* Parameter regularisation (C-ATTL3/parameter_regularization/{L1,L2,ElasticNet}ParameterRegularization.hpp behind
+ * Parameters::regularize / get_regularization_penalty, C-ATTL3/parameters/StandardParameters.hpp:126-136):
+ *   grad[i]  += (values[i] >= 0 ? l1 : -l1) + l2 * values[i]            (grad may be NULL: penalty only)
+ *   *penalty += l1 * sum |values| + l2 / 2 * sum values^2               (device double; may be NULL; deterministic)
+ * L1 = (lambda, 0), L2 = (0, lambda), ElasticNet = (l1_lambda, l2_lambda). */
+int cattl3_regularize_f32(cattl3_ctx*, int64_t count, float l1, float l2, const float* values, float* grad, double* penalty);
+int cattl3_regularize_f64(cattl3_ctx*, int64_t count, double l1, double l2, const double* values, double* grad, double* penalty);
+
 /* ---- small element-wise helpers for the network glue ---------------------------------------- */
 /* y += x (ResidualNeuralNetwork::propagate, C-ATTL3/neural_network/ResidualNeuralNetwork.hpp:112-117). */
 int cattl3_add_inplace_f32(cattl3_ctx*, int64_t count, float* y, const float* x);

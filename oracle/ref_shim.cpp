@@ -25,6 +25,7 @@
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <memory>
 #include <vector>
 
@@ -347,15 +348,27 @@ int cifar_impl(int total, int batch, int epochs, const S* x, const S* obj, const
 	auto he = std::make_shared<HeParameterInitialization<S>>(1e-1);
 	auto glorot = std::make_shared<GlorotParameterInitialization<S>>(1e-1);
 	std::vector<LayerPtr<S,3>> layers;
-	layers.emplace_back(new ConvKernelLayer<S>({ 32u, 32u, 3u }, 8, he));
+	/* tests only: REF_SHIM_REG = "l1:<lambda>" | "l2:<lambda>" | "en:<l1>,<l2>" puts that penalty on every weight matrix */
+	ParamRegSharedPtr<S> reg;
+	if (const char* spec = std::getenv("REF_SHIM_REG")) {
+		const std::string text(spec);
+		if (text.compare(0, 3, "l1:") == 0)
+			reg = std::make_shared<L1ParameterRegularization<S>>((S) std::atof(spec + 3));
+		else if (text.compare(0, 3, "l2:") == 0)
+			reg = std::make_shared<L2ParameterRegularization<S>>((S) std::atof(spec + 3));
+		else if (text.compare(0, 3, "en:") == 0)
+			reg = std::make_shared<ElasticNetParameterRegularization<S>>((S) std::atof(spec + 3),
+					(S) std::atof(spec + text.find(',') + 1));
+	}
+	layers.emplace_back(new ConvKernelLayer<S>({ 32u, 32u, 3u }, 8, he, 3, 3, 1, 1, 1, 1, 0, 0, reg));
 	layers.emplace_back(new ReLUActivationLayer<S,3>(layers.back()->get_output_dims()));
 	layers.emplace_back(new MaxPoolLayer<S>(layers.back()->get_output_dims()));
-	layers.emplace_back(new ConvKernelLayer<S>(layers.back()->get_output_dims(), 8, he));
+	layers.emplace_back(new ConvKernelLayer<S>(layers.back()->get_output_dims(), 8, he, 3, 3, 1, 1, 1, 1, 0, 0, reg));
 	layers.emplace_back(new ReLUActivationLayer<S,3>(layers.back()->get_output_dims()));
 	layers.emplace_back(new MaxPoolLayer<S>(layers.back()->get_output_dims()));
-	layers.emplace_back(new DenseKernelLayer<S,3>(layers.back()->get_output_dims(), 50, glorot));
+	layers.emplace_back(new DenseKernelLayer<S,3>(layers.back()->get_output_dims(), 50, glorot, reg));
 	layers.emplace_back(new ReLUActivationLayer<S,3>(layers.back()->get_output_dims()));
-	layers.emplace_back(new DenseKernelLayer<S,3>(layers.back()->get_output_dims(), 10, glorot));
+	layers.emplace_back(new DenseKernelLayer<S,3>(layers.back()->get_output_dims(), 10, glorot, reg));
 	layers.emplace_back(new SoftmaxActivationLayer<S,3>(layers.back()->get_output_dims()));
 	FeedforwardNeuralNetwork<S,3> net(std::move(layers));
 	net.init();

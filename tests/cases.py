@@ -183,3 +183,15 @@ def seqnet_inputs(dtype, total=16, seq=3, hw=8, state=4, seed=5001):
 
 
 SEQNET_SMALL = dict(width=4, state=4)
+
+
+CIFAR_REG = "en:0.003,0.01"   # REF_SHIM_REG: ElasticNet (l1, l2) on every weight matrix of the config-1 network
+
+
+def cifar_inputs(dtype, total=64, seed=1004):
+    """BASELINE.json configs[0] at test size: synthetic 32x32x3 uniform [-1, 1), one-hot objectives i mod 10."""
+    rng = np.random.default_rng(seed)
+    x = rand(rng, (total, 32, 32, 3), dtype)
+    obj = np.zeros((total, 1, 1, 10), dtype=dtype, order="F")
+    obj[np.arange(total), 0, 0, np.arange(total) % 10] = 1
+    return x, obj

@@ -25,6 +25,7 @@ from oracle.binding import Oracle  # noqa: E402
 
 def main():
     ref = Oracle("ref")
+    vectors = np.load(os.path.join(HERE, "reference_vectors.npz"))
     out = {}
     for suf, dt in (("f32", np.float32), ("f64", np.float64)):
         x = C.autoencoder_inputs(dt)
@@ -43,6 +44,14 @@ def main():
         out["seqnet/%s/p1" % suf] = p1
         out["seqnet/%s/loss" % suf] = np.array([loss5])
         print(suf, "seqnet params", n5, "loss", loss5)
+        # config 1 with an ElasticNet penalty on every weight matrix (REF_SHIM_REG, tests only): the device regularisation
+        x, obj = C.cifar_inputs(dt)
+        os.environ["REF_SHIM_REG"] = C.CIFAR_REG
+        p1, loss_reg, _ = ref.train_cifar(x, obj, 16, 2, params_in=np.ascontiguousarray(vectors["cifar/%s/p0" % suf]))
+        del os.environ["REF_SHIM_REG"]
+        out["cifar_reg/%s/p1" % suf] = p1
+        out["cifar_reg/%s/loss" % suf] = np.array([loss_reg])
+        print(suf, "cifar + ElasticNet loss", loss_reg)
         print(suf, "autoencoder params", out["autoencoder/%s/p1" % suf].size, "resnet params", n, "loss", loss)
     path = os.path.join(HERE, "reference_networks.npz")
     np.savez_compressed(path, **out)

@@ -198,6 +198,43 @@ def test_config4_resnet_training_matches_reference(b200, golden_nets, dt):
 
 
 @pytest.mark.parametrize("dt", DTYPES)
+def test_regularised_training_matches_reference(golden, golden_nets, dt):
+    """Config 1 with an ElasticNet penalty on every weight matrix (REF_SHIM_REG): Parameters::regularize and
+    get_regularization_penalty run as one device kernel per parameter (cattl3_regularize; the penalty is accumulated on
+    the device and read once per epoch), also inside the captured step graph.  Parameters and the epoch loss
+    (objective + penalty) against the unmodified reference; graph and eager runs agree."""
+    suf = "f32" if dt == np.float32 else "f64"
+    code = (
+        "import os, sys, numpy as np; sys.path[:0] = [%r, %r]\n"
+        "import cases as C; from oracle import binding\n"
+        "lib = binding.Oracle('ref', path=%r); dt = np.%s\n"
+        "x, obj = C.cifar_inputs(dt); os.environ['REF_SHIM_REG'] = C.CIFAR_REG\n"
+        "p0 = np.ascontiguousarray(np.load(%r)['cifar/%s/p0'])\n"
+        "p, l, _ = lib.train_cifar(x, obj, 16, 2, params_in=p0)\n"
+        "np.save(sys.argv[1], np.concatenate([np.asarray(p, dtype=np.float64).ravel(), [l]]))\n"
+        % (ROOT, os.path.join(ROOT, "tests"), SHIM, np.dtype(dt).name,
+           os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"), suf))
+    import tempfile
+    outs = []
+    with tempfile.TemporaryDirectory() as d:
+        for i, env in enumerate(({"CATTL3_GRAPH_TRACE": "1"}, {"CATTL3_NO_GRAPH": "1"})):
+            path = os.path.join(d, "p%d.npy" % i)
+            r = subprocess.run([os.sys.executable, "-c", code, path], env=dict(os.environ, **env), capture_output=True,
+                               text=True, timeout=600)
+            assert r.returncode == 0, r.stderr[-2000:]
+            if i == 0:
+                assert "step graph captured" in r.stderr, "regularised parameters kept the step out of the graph:\n" + r.stderr[-2000:]
+            outs.append(np.load(path))
+    ref_p, ref_loss = golden_nets["cifar_reg/%s/p1" % suf], float(golden_nets["cifar_reg/%s/loss" % suf][0])
+    err = C.relerr(outs[0][:-1], ref_p)
+    print("config 1 + ElasticNet, 8 Nadam steps: loss %.6f (ref %.6f), param err %.2e, graph vs eager %.2e"
+          % (outs[0][-1], ref_loss, err, C.relerr(outs[0][:-1], outs[1][:-1])))
+    assert err < (1e-4 if dt == np.float32 else 1e-9)
+    assert abs(outs[0][-1] - ref_loss) < (1e-4 if dt == np.float32 else 1e-9) * max(1.0, abs(ref_loss))
+    assert C.relerr(outs[0][:-1], outs[1][:-1]) < (1e-6 if dt == np.float32 else 1e-13)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
 def test_config5_sequence_network_training_matches_reference(b200, golden_nets, dt):
     """BASELINE.json configs[4] at test size: SequentialNeuralNetwork{ParallelNeuralNetwork of conv lanes,
     DenseNeuralNetwork, MaxPool} feeding a convolutional LSTMNeuralNetwork (ConvKernelLayer kernels, shared across the

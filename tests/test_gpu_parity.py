@@ -190,6 +190,35 @@ def test_optimizer_vs_golden(U, golden, dt):
             assert C.relerr(U.host(pd, p0.shape), golden[k + "p"]) < tol, (name, lam)
 
 
+@pytest.mark.parametrize("dt", DTYPES)
+def test_regularize_kernel(U, dt):
+    """cattl3_regularize against the reference's formulas (L1 / L2 / ElasticNet ParameterRegularization.hpp:
+    d_function = (v >= 0 ? l1 : -l1) + l2 v, function = l1 |v|_1 + l2 / 2 |v|^2), the penalty accumulating across
+    calls in a device double; sizes from one block to many, a zero among the values (sign(0) = +1 in the reference)."""
+    import torch
+    c = U.ctx()
+    rng = np.random.default_rng(77)
+    penalty = torch.zeros(1, dtype=torch.float64, device="cuda")
+    expect = 0.0
+    for count, (l1, l2) in ((5, (0.01, 0.0)), (1000, (0.0, 0.02)), (300001, (0.003, 0.01))):
+        v = rng.uniform(-1, 1, count).astype(dt)
+        v[0] = 0
+        g = rng.uniform(-1, 1, count).astype(dt)
+        vd, gd = U.dev(v), U.dev(g)
+        c.regularize(count, l1, l2, vd, gd, penalty)
+        c.synchronize()
+        want = g + (np.where(v >= 0, dt(l1), dt(-l1)) + v * dt(l2))
+        assert C.relerr(U.host(gd, (count,)), want) < (1e-6 if dt == np.float32 else 1e-15)
+        expect += float(dt(l1)) * np.abs(v.astype(np.float64)).sum() + 0.5 * float(dt(l2)) * (v.astype(np.float64) ** 2).sum()
+        assert abs(float(penalty.cpu()[0]) - expect) < 1e-12 * max(1.0, expect), (count, float(penalty.cpu()[0]), expect)
+        # penalty only: the gradient is left alone
+        c.regularize(count, l1, l2, vd, None, penalty)
+        c.synchronize()
+        expect += float(dt(l1)) * np.abs(v.astype(np.float64)).sum() + 0.5 * float(dt(l2)) * (v.astype(np.float64) ** 2).sum()
+        assert C.relerr(U.host(gd, (count,)), want) < (1e-6 if dt == np.float32 else 1e-15)
+        assert abs(float(penalty.cpu()[0]) - expect) < 1e-12 * max(1.0, expect)
+
+
 # "stem": 3 input channels, zero-padded to a 16-channel k-block by TMA out-of-bounds fill (forward on tcgen05)
 TC_CASES = ["c2_small", "c2_small_f256", "c2_stride2", "c2_dil1", "c2_1x1", "ragged_c", "stem"]
 
