@@ -33,7 +33,7 @@ struct cattl3_ctx {
 	// cattl3_malloc carves blocks out of arena `cap_arena` and cattl3_free recycles them (one stream: program order makes
 	// the reuse safe); outside a capture cattl3_free of an arena address is a no-op.  An arena is owned by its graph;
 	// cattl3_graph_destroy retires it (in_use = false) for the next cattl3_graph_begin, the memory goes at ctx_destroy.
-	static constexpr int MAX_CAP_BLOCKS = 8192, MAX_ARENAS = 16;
+	static constexpr int MAX_CAP_BLOCKS = 8192, MAX_ARENAS = 64;
 	struct Arena { char* base; size_t size; bool in_use; };
 	Arena arenas[MAX_ARENAS];
 	int arena_count = 0;
