@@ -319,6 +319,44 @@ class Context:
         self._call("cattl3_regularize", values.dtype, ctypes.c_int64(count), ct(l1), ct(l2), _p(values), _p(grad),
                    _p(penalty))
 
+    def muladd(self, count, accumulate, a, b, c, d, out):
+        """out = (accumulate ? out : 0) + a * b + (c ? c * d : 0)."""
+        self._call("cattl3_muladd", out.dtype, ctypes.c_int64(count), int(bool(accumulate)), _p(a), _p(b), _p(c), _p(d),
+                   _p(out))
+
+    def optimizer_step_indirect(self, kind, dev_step, count, p, g, s1=None, s2=None, s3=None):
+        """The fused update with the step scalars read from device memory (``dev_step``: a device copy of cattl3_opt_step)."""
+        self._call("cattl3_optimizer_step_indirect", p.dtype, int(kind), _p(dev_step), ctypes.c_int64(count), _p(p), _p(g),
+                   _p(s1), _p(s2), _p(s3))
+
+    # ---- step graphs and the stream-ordered allocator behind them -------------------------------------------------
+    def malloc(self, nbytes):
+        ptr = ctypes.c_void_p()
+        self._chk(self.L.cattl3_malloc(self.h, ctypes.byref(ptr), ctypes.c_size_t(nbytes)))
+        return ptr.value
+
+    def free(self, ptr):
+        self._chk(self.L.cattl3_free(self.h, ctypes.c_void_p(ptr)))
+
+    def allocated_bytes(self):
+        fn = self.L.cattl3_ctx_allocated_bytes
+        fn.restype = ctypes.c_int64
+        return int(fn(self.h))
+
+    def graph_begin(self, arena_bytes):
+        self._chk(self.L.cattl3_graph_begin(self.h, ctypes.c_size_t(arena_bytes)))
+
+    def graph_end(self):
+        g = ctypes.c_void_p()
+        self._chk(self.L.cattl3_graph_end(self.h, ctypes.byref(g)))
+        return g
+
+    def graph_launch(self, graph):
+        self._chk(self.L.cattl3_graph_launch(self.h, graph))
+
+    def graph_destroy(self, graph):
+        self._chk(self.L.cattl3_graph_destroy(graph))
+
     def scale(self, count, alpha, x, y):
         _, ct = _suffix(x.dtype)
         self._call("cattl3_scale", x.dtype, ctypes.c_int64(count), ct(alpha), _p(x), _p(y))

@@ -476,6 +476,12 @@ int cattl3_graph_end(cattl3_ctx* ctx, cattl3_graph** out) {
 	ctx->cap_block_count = 0;
 	cudaGraph_t graph = nullptr;
 	cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+	// what the host released during the capture goes back to the pool now, in stream order behind everything queued
+	for (int i = 0; i < ctx->deferred_free_count; ++i) {
+		if (cudaFreeAsync(ctx->deferred_free[i], ctx->stream) != cudaSuccess)
+			cudaGetLastError();
+	}
+	ctx->deferred_free_count = 0;
 	if (e != cudaSuccess || !graph) {
 		cudaGetLastError();
 		if (graph) cudaGraphDestroy(graph);
@@ -600,6 +606,15 @@ int cattl3_free(cattl3_ctx* ctx, void* p) {
 				}
 			}
 		}
+		return CATTL3_OK;
+	}
+	if (ctx->capturing) {
+		// memory from before the capture: released once the capture has ended (see cattl3_graph_end)
+		if (ctx->deferred_free_count == cattl3_ctx::MAX_DEFERRED_FREES) {
+			set_error("free: too many releases of pool memory during one graph capture");
+			return CATTL3_ERR_UNSUPPORTED;   // the block stays allocated; the caller's capture is abandoned by the host side
+		}
+		ctx->deferred_free[ctx->deferred_free_count++] = p;
 		return CATTL3_OK;
 	}
 	cudaError_t e = cudaFreeAsync(p, ctx->stream);

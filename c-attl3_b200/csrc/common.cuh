@@ -42,6 +42,11 @@ struct cattl3_ctx {
 	struct CapBlock { char* ptr; size_t size; bool free; };
 	CapBlock cap_blocks[MAX_CAP_BLOCKS];
 	int cap_block_count = 0;
+	// pool memory released while the stream is capturing: the release must not become a node of the graph (a replay would
+	// free it again), so it waits here until the capture has ended
+	static constexpr int MAX_DEFERRED_FREES = 4096;
+	void* deferred_free[MAX_DEFERRED_FREES];
+	int deferred_free_count = 0;
 	int64_t scratch_generation = 0;   // bumped whenever ensure_buffer moves a scratch buffer (captured graphs hold the old address)
 	int64_t allocated_bytes = 0;   // running total of cattl3_malloc in 256-byte granules (sizes an arena from an eager step)
 	// cattl3_ctx_throttle: one event per recent call

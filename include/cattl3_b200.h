@@ -224,7 +224,8 @@ int cattl3_slice_rows_f64(cattl3_ctx*, int64_t total, int64_t vol, int64_t first
  * cattl3_ctx_allocated_bytes() taken before and after one eager run of the same step.  Nothing may synchronise or
  * grow library scratch (the step must have run eagerly at the same shape before), and host-side arguments are frozen
  * into the graph -- step-dependent scalars therefore go through device memory (cattl3_optimizer_step_indirect).
- * Blocks still held when the capture ends stay valid for the life of the graph; freeing them later is a no-op.
+ * Blocks still held when the capture ends stay valid for the life of the graph; freeing them later is a no-op.  Memory
+ * from before the capture that is released during it is returned to the pool when the capture ends (never by the graph).
  * Errors: CATTL3_ERR_UNSUPPORTED when the arena is too small or scratch would have to grow (the capture must still be
  * closed with _end, which then reports the invalidated capture).
  */
