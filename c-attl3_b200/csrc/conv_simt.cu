@@ -552,7 +552,9 @@ int tiny_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* pla
 	const int K = gg.RH * gg.RW * gg.SC;
 	const long long M = (long long) gg.N * gg.OH * gg.OW;
 	const long long elems = (long long) K * gg.J;
-	long long ctas = ceil_div(M, 512);
+	// a CTA's chunks of 32 rows run one after the other (load, barrier, accumulate, barrier), so short row ranges -- four
+	// chunks -- and many CTAs are what keeps the SMs busy on the small layers this kernel exists for
+	long long ctas = ceil_div(M, 128);
 	if (ctas > 8ll * ctx->sm_count) ctas = 8ll * ctx->sm_count;
 	const long long m_per_cta = ceil_div(ceil_div(M, ctas), 32) * 32;
 	ctas = ceil_div(M, m_per_cta);
