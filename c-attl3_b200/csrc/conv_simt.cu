@@ -457,13 +457,14 @@ template int skinny_gather_gemm<double>(cattl3_ctx*, const GatherGeom&, const do
 // reduce (wgrad_reduce_kernel).
 template<typename S, int JT>
 __global__ void __launch_bounds__(256) tiny_wgrad_kernel(GatherGeom gg, const S* __restrict__ src,
-		const S* __restrict__ plain, S* __restrict__ partial, long long m_per_cta, long long dw_elems) {
+		const S* __restrict__ plain, S* __restrict__ partial, long long m_per_cta, long long dw_elems, int Jp) {
+	// Jp: the filter count rounded up to a multiple of JT; the plain rows are zero padded to it in shared memory
 	constexpr int MC = 32, ITEMS = 8 / JT;
 	extern __shared__ __align__(16) unsigned char tiny_smem[];
-	const int T = gg.RH * gg.RW, R = gg.SC, J = gg.J, K = T * R, JG = J / JT, KG = K * JG;
+	const int T = gg.RH * gg.RW, R = gg.SC, J = gg.J, K = T * R, JG = Jp / JT, KG = K * JG;
 	const int Kp = K | 1;   // odd pitch: the transposing stores spread over the banks
-	S* Bs = reinterpret_cast<S*>(tiny_smem);       // [MC][J] (first: 16-byte aligned rows when J % 4 == 0)
-	S* As = Bs + MC * J;                            // [MC][Kp]
+	S* Bs = reinterpret_cast<S*>(tiny_smem);       // [MC][Jp] (first: 16-byte aligned rows when Jp % 4 == 0)
+	S* As = Bs + MC * Jp;                           // [MC][Kp]
 	int* ktab = reinterpret_cast<int*>(As + MC * Kp); // per k: rh*bh + ch (16 bits) | rw*bw + cw (16 bits), and the channel
 	for (int k = threadIdx.x; k < K; k += 256) {
 		const int tap = k / R, r = k - tap * R, rw = tap / gg.RH, rh = tap - rw * gg.RH;
@@ -500,7 +501,7 @@ __global__ void __launch_bounds__(256) tiny_wgrad_kernel(GatherGeom gg, const S*
 				v = __ldg(src + n + (long long) gg.N * (th + (long long) gg.SH * tw) + ktab[2 * k + 1] * plane);
 			As[mm * Kp + k] = v;
 		}
-		for (int j = l0; j < J; j += 256 / MC) Bs[mm * J + j] = ok ? __ldg(plain + m + M * j) : (S) 0;
+		for (int j = l0; j < Jp; j += 256 / MC) Bs[mm * Jp + j] = ok && j < J ? __ldg(plain + m + M * j) : (S) 0;
 		__syncthreads();
 		#pragma unroll
 		for (int i = 0; i < ITEMS; ++i) {
@@ -512,11 +513,11 @@ __global__ void __launch_bounds__(256) tiny_wgrad_kernel(GatherGeom gg, const S*
 					const S a = ap[r * Kp];
 					S bv[JT];
 					if constexpr (JT == 4 && sizeof(S) == 4) {
-						const float4 v = *reinterpret_cast<const float4*>(bp + r * J);
+						const float4 v = *reinterpret_cast<const float4*>(bp + r * Jp);
 						bv[0] = v.x; bv[1] = v.y; bv[2] = v.z; bv[3] = v.w;
 					} else {
 						#pragma unroll
-						for (int t = 0; t < JT; ++t) bv[t] = bp[r * J + t];
+						for (int t = 0; t < JT; ++t) bv[t] = bp[r * Jp + t];
 					}
 					#pragma unroll
 					for (int t = 0; t < JT; ++t) acc[i][t] = fma(a, bv[t], acc[i][t]);
@@ -532,7 +533,7 @@ __global__ void __launch_bounds__(256) tiny_wgrad_kernel(GatherGeom gg, const S*
 			const int k = item_k[i], tap = k / R, r = k - tap * R;
 			#pragma unroll
 			for (int t = 0; t < JT; ++t)
-				dst[tap * gg.w_stap + r * gg.w_sr + (item_j[i] + t) * gg.w_sj] = acc[i][t];
+				if (item_j[i] + t < J) dst[tap * gg.w_stap + r * gg.w_sr + (item_j[i] + t) * gg.w_sj] = acc[i][t];
 		}
 	}
 }
@@ -540,10 +541,11 @@ __global__ void __launch_bounds__(256) tiny_wgrad_kernel(GatherGeom gg, const S*
 bool tiny_wgrad_supported(const GatherGeom& gg, size_t scalar_bytes) {
 	const long long K = (long long) gg.RH * gg.RW * gg.SC;
 	const long long M = (long long) gg.N * gg.OH * gg.OW;
-	const long long smem = (32 * ((K | 1) + gg.J)) * (long long) scalar_bytes + 8 * K;
+	const long long Jp = (gg.J + 3) / 4 * 4;   // the plain rows are padded to four filters per thread
+	const long long smem = (32 * ((K | 1) + Jp)) * (long long) scalar_bytes + 8 * K;
 	// |rh*bh + ch| and |rw*bw + cw| are packed into 16 bits each
 	const long long reach = (long long) (gg.RH > gg.RW ? gg.RH : gg.RW) * (gg.bh > gg.bw ? gg.bh : gg.bw) + gg.SH + gg.SW;
-	return gg.J <= 32 && K <= 256 && K * gg.J <= 2048 && smem <= 44 * 1024 && gg.denh == 1 && gg.denw == 1 && M >= 512 &&
+	return gg.J <= 32 && K <= 256 && K * Jp <= 2048 && smem <= 44 * 1024 && gg.denh == 1 && gg.denw == 1 && M >= 512 &&
 			reach < 30000 && gg.bh > 0 && gg.bw > 0;
 }
 
@@ -559,13 +561,14 @@ int tiny_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* pla
 	const long long m_per_cta = ceil_div(ceil_div(M, ctas), 32) * 32;
 	ctas = ceil_div(M, m_per_cta);
 	CATTL3_CHECK(ensure_buffer(ctx, &ctx->ws, &ctx->ws_bytes, (size_t) (ctas * elems) * sizeof(S)));
-	const size_t smem = (size_t) (32 * ((K | 1) + gg.J)) * sizeof(S) + 8 * (size_t) K;
-	if (gg.J % 4 == 0)
-		tiny_wgrad_kernel<S, 4><<<(unsigned) ctas, 256, smem, ctx->stream>>>(gg, src, plain, (S*) ctx->ws, m_per_cta, elems);
-	else if (gg.J % 2 == 0)
-		tiny_wgrad_kernel<S, 2><<<(unsigned) ctas, 256, smem, ctx->stream>>>(gg, src, plain, (S*) ctx->ws, m_per_cta, elems);
+	// four filters per thread whenever there is more than one (three filters: one lane of the four idles, still three FMAs
+	// per two shared-memory reads instead of one); a single filter keeps one output per item
+	const int Jp = gg.J == 1 ? 1 : (gg.J + 3) / 4 * 4;
+	const size_t smem = (size_t) (32 * ((K | 1) + Jp)) * sizeof(S) + 8 * (size_t) K;
+	if (Jp > 1)
+		tiny_wgrad_kernel<S, 4><<<(unsigned) ctas, 256, smem, ctx->stream>>>(gg, src, plain, (S*) ctx->ws, m_per_cta, elems, Jp);
 	else
-		tiny_wgrad_kernel<S, 1><<<(unsigned) ctas, 256, smem, ctx->stream>>>(gg, src, plain, (S*) ctx->ws, m_per_cta, elems);
+		tiny_wgrad_kernel<S, 1><<<(unsigned) ctas, 256, smem, ctx->stream>>>(gg, src, plain, (S*) ctx->ws, m_per_cta, elems, Jp);
 	CATTL3_LAUNCHED(ctx);
 	wgrad_reduce_kernel<S><<<ew_grid(ctx, ceil_div(elems, 32), 1), 256, 0, ctx->stream>>>((const S*) ctx->ws, (int) ctas, elems, dw);
 	CATTL3_LAUNCHED(ctx);
