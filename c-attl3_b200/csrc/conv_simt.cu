@@ -284,18 +284,25 @@ template int simt_wgrad<double>(cattl3_ctx*, const GatherGeom&, const double*, c
 template<typename S, int JT>
 __global__ void __launch_bounds__(256) tiny_gather_gemm_kernel(GatherGeom gg, const S* __restrict__ src,
 		const S* __restrict__ w, const S* __restrict__ bias, int bias_mode, S* __restrict__ out, int act_kind, S act_param,
-		S* __restrict__ act_out) {
+		S* __restrict__ act_out, int ks) {
+	// ks (1, 2 or 4) threads share an output row, each walking a contiguous ks-th of the reduction index k = tap * R + r;
+	// their partial sums meet in shared memory and are added in slice order.  Small layers (fewer rows than the GPU has
+	// thread slots) get ks times the threads in flight -- the thread is a chain of load latencies -- at the price of
+	// one barrier.
 	extern __shared__ __align__(16) unsigned char tiny_smem[];
 	S* ws = reinterpret_cast<S*>(tiny_smem);
 	const int T = gg.RH * gg.RW, R = gg.SC, J = gg.J, K = T * R;
+	S* red = ws + K * JT;   // [ks][rows][JT], only if ks > 1
 	for (int i = threadIdx.x; i < K * JT; i += 256) {
 		const int j = i % JT, k = i / JT, tap = k / R, r = k - tap * R;
 		ws[i] = j < J ? w[tap * gg.w_stap + r * gg.w_sr + j * gg.w_sj] : (S) 0;
 	}
 	__syncthreads();
 	const long long M = (long long) gg.N * gg.OH * gg.OW;
-	const long long m = (long long) blockIdx.x * 256 + threadIdx.x;
-	if (m >= M) return;
+	const int rows = 256 / ks;
+	const int row = threadIdx.x % rows, slice = threadIdx.x / rows;
+	const long long m = (long long) blockIdx.x * rows + row;
+	const bool live = m < M;
 	const int n = (int) (m % gg.N);
 	const long long pix = m / gg.N;
 	const int oh = (int) (pix % gg.OH), ow = (int) (pix / gg.OH);
@@ -303,20 +310,35 @@ __global__ void __launch_bounds__(256) tiny_gather_gemm_kernel(GatherGeom gg, co
 	S acc[JT];
 	#pragma unroll
 	for (int j = 0; j < JT; ++j) acc[j] = (S) 0;
-	for (int tap = 0; tap < T; ++tap) {
-		const int rw = tap / gg.RH, rh = tap - rw * gg.RH;
-		const int th = oh * gg.ah + rh * gg.bh + gg.ch, tw = ow * gg.aw + rw * gg.bw + gg.cw;
-		if (th < 0 || tw < 0 || th % gg.denh != 0 || tw % gg.denw != 0) continue;
-		const int ih = th / gg.denh, iw = tw / gg.denw;
-		if (ih >= gg.SH || iw >= gg.SW) continue;
-		const S* ps = src + n + (long long) gg.N * (ih + (long long) gg.SH * iw);
-		const S* pw = ws + tap * R * JT;
-		for (int r = 0; r < R; ++r) {
-			const S v = __ldg(ps + r * plane);
-			#pragma unroll
-			for (int j = 0; j < JT; ++j) acc[j] = fma(v, pw[r * JT + j], acc[j]);
+	if (live) {
+		const int kb = (int) ((long long) K * slice / ks), ke = (int) ((long long) K * (slice + 1) / ks);
+		for (int tap = kb / R; tap * R < ke; ++tap) {
+			const int rw = tap / gg.RH, rh = tap - rw * gg.RH;
+			const int th = oh * gg.ah + rh * gg.bh + gg.ch, tw = ow * gg.aw + rw * gg.bw + gg.cw;
+			if (th < 0 || tw < 0 || th % gg.denh != 0 || tw % gg.denw != 0) continue;
+			const int ih = th / gg.denh, iw = tw / gg.denw;
+			if (ih >= gg.SH || iw >= gg.SW) continue;
+			const S* ps = src + n + (long long) gg.N * (ih + (long long) gg.SH * iw);
+			const S* pw = ws + tap * R * JT;
+			const int r0 = kb > tap * R ? kb - tap * R : 0, r1 = ke - tap * R < R ? ke - tap * R : R;
+			for (int r = r0; r < r1; ++r) {
+				const S v = __ldg(ps + r * plane);
+				#pragma unroll
+				for (int j = 0; j < JT; ++j) acc[j] = fma(v, pw[r * JT + j], acc[j]);
+			}
 		}
 	}
+	if (ks > 1) {
+		#pragma unroll
+		for (int j = 0; j < JT; ++j) red[(slice * rows + row) * JT + j] = acc[j];
+		__syncthreads();
+		if (slice != 0) return;
+		for (int z = 1; z < ks; ++z) {
+			#pragma unroll
+			for (int j = 0; j < JT; ++j) acc[j] += red[(z * rows + row) * JT + j];
+		}
+	}
+	if (!live) return;
 	const long long P = (long long) gg.OH * gg.OW;
 	#pragma unroll
 	for (int j = 0; j < JT; ++j) {
@@ -342,12 +364,16 @@ int tiny_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const 
 	CATTL3_REQUIRE(out || act, "gather GEMM: no output tensor");
 	const int K = gg.RH * gg.RW * gg.SC;
 	const int JT = gg.J <= 1 ? 1 : (gg.J <= 2 ? 2 : (gg.J <= 4 ? 4 : 8));
-	const unsigned grid = (unsigned) ceil_div(M, 256);
-	const size_t smem = (size_t) K * JT * sizeof(S);
+	// fewer CTAs than two per SM: let 4 (fewer than four per SM: 2) threads share a row (see the kernel)
+	const long long full_ctas = ceil_div(M, 256);
+	int ks = K < 8 ? 1 : (full_ctas < 2ll * ctx->sm_count ? 4 : (full_ctas < 4ll * ctx->sm_count ? 2 : 1));
+	if ((size_t) (K * JT + 256 * JT) * sizeof(S) > 48 * 1024) ks = 1;   // the exchange buffer must fit the default limit
+	const unsigned grid = (unsigned) ceil_div(M, 256 / ks);
+	const size_t smem = (size_t) (K * JT + (ks > 1 ? 256 * JT : 0)) * sizeof(S);
 	const int kind = act ? ep->act_kind : CATTL3_ACT_NONE;
 	const S ap = act ? (S) ep->act_param : (S) 0;
 	S* ao = act ? (S*) ep->act_out : nullptr;
-#define LAUNCH(JTV) tiny_gather_gemm_kernel<S, JTV><<<grid, 256, smem, ctx->stream>>>(gg, src, w, bias, bias_mode, out, kind, ap, ao)
+#define LAUNCH(JTV) tiny_gather_gemm_kernel<S, JTV><<<grid, 256, smem, ctx->stream>>>(gg, src, w, bias, bias_mode, out, kind, ap, ao, ks)
 	if (JT == 1) LAUNCH(1); else if (JT == 2) LAUNCH(2); else if (JT == 4) LAUNCH(4); else LAUNCH(8);
 #undef LAUNCH
 	CATTL3_LAUNCHED(ctx);
