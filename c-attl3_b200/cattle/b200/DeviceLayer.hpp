@@ -104,6 +104,24 @@ public:
 };
 
 /**
+ * A kernel layer whose backward pass can be taken apart: the input gradient now, the parameter gradients later and for
+ * many batches at once.  The cells of an unrolled recurrent network share their kernels' parameters, so
+ * dW = sum over steps of in_t^T dY_t is ONE weight-gradient GEMM over the rows of all steps instead of one small GEMM
+ * (plus its split-K reduction) per step.
+ */
+template<typename Scalar, std::size_t Rank>
+class SplitBackwardLayer {
+public:
+	virtual ~SplitBackwardLayer() = default;
+	/** Whether the two halves below are available for this layer instance. */
+	virtual bool can_split_backward() const = 0;
+	/** pass_back_dev without the parameter gradients; empty for an input layer.  Needs no forward cache. */
+	virtual DeviceTensor<Scalar> pass_back_input_dev(const DeviceTensor<Scalar>& out_grad) = 0;
+	/** dW += in^T dY, db += column sums of dY for `in.rows` (= out_grad.rows, any number of) samples. */
+	virtual void accumulate_param_grads_dev(const DeviceTensor<Scalar>& in, const DeviceTensor<Scalar>& out_grad) = 0;
+};
+
+/**
  * What the layer FOLLOWING a kernel layer asks that layer's epilogue to do while the output tile is still
  * on chip (cattl3_epilogue, include/cattl3_b200.h): apply its element-wise activation and / or produce the
  * per-column sums a BatchNormLayer starts with.  The consumer fills in the request, the producer the results.

@@ -28,6 +28,7 @@ namespace b200 {
 
 template<typename Scalar, std::size_t Rank, bool Transposed>
 class SpatialKernelLayer : public KernelLayer<Scalar,Rank>, public DeviceLayer<Scalar,Rank>,
+		public SplitBackwardLayer<Scalar,Rank>,
 		public EpilogueProducer<Scalar> {
 	typedef Layer<Scalar,Rank> Root;
 	typedef KernelLayer<Scalar,Rank> Base;
@@ -136,6 +137,40 @@ public:
 		w.grad_written_on_device();
 		b.grad_written_on_device();
 		return prev_out_grad;
+	}
+	/** b200::SplitBackwardLayer (convolutions; the transposed layer keeps its single backward call). */
+	inline bool can_split_backward() const {
+		return !Transposed;
+	}
+	inline DeviceTensor<Scalar> pass_back_input_dev(const DeviceTensor<Scalar>& out_grad) {
+		if (Transposed)
+			throw Error(CATTL3_ERR_UNSUPPORTED, "kernel layer: the transposed convolution's backward pass is not split");
+		DeviceTensor<Scalar> prev_out_grad;
+		if (Base::is_input_layer())
+			return prev_out_grad;
+		cattl3_conv_geom g = geometry(out_grad.rows);
+		prev_out_grad = DeviceTensor<Scalar>(out_grad.rows, Base::input_dims.get_volume());
+		B200Parameters<Scalar>& w = device_params(*Base::weights);
+		Context& c = Context::get();
+		Context::Lock l = c.lock();
+		CATTLE_B200_CHECK(Device::conv_backward(c.handle(), &g, nullptr, w.device_values(), out_grad.data(), nullptr,
+				nullptr, prev_out_grad.data()));
+		return prev_out_grad;
+	}
+	inline void accumulate_param_grads_dev(const DeviceTensor<Scalar>& in, const DeviceTensor<Scalar>& out_grad) {
+		if (Transposed || in.empty() || in.rows != out_grad.rows)
+			throw Error(CATTL3_ERR_INVALID, "kernel layer: parameter gradients need matching input and gradient batches");
+		cattl3_conv_geom g = geometry(out_grad.rows);
+		B200Parameters<Scalar>& w = device_params(*Base::weights);
+		B200Parameters<Scalar>& b = device_params(*Base::bias);
+		Context& c = Context::get();
+		{
+			Context::Lock l = c.lock();
+			CATTLE_B200_CHECK(Device::conv_backward(c.handle(), &g, in.data(), w.device_values(), out_grad.data(),
+					w.device_grad(), b.device_grad(), nullptr));
+		}
+		w.grad_written_on_device();
+		b.grad_written_on_device();
 	}
 protected:
 	inline SpatialKernelLayer(const typename Root::Dims& input_dims, std::size_t filters, std::size_t receptor_height,

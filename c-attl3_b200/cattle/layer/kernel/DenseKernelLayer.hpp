@@ -24,7 +24,7 @@ namespace cattle {
 
 template<typename Scalar, std::size_t Rank = 1>
 class DenseKernelLayer : public KernelLayer<Scalar,Rank>, public b200::DeviceLayer<Scalar,Rank>,
-		public b200::EpilogueProducer<Scalar> {
+		public b200::SplitBackwardLayer<Scalar,Rank>, public b200::EpilogueProducer<Scalar> {
 	typedef Layer<Scalar,Rank> Root;
 	typedef KernelLayer<Scalar,Rank> Base;
 	typedef b200::DeviceTensor<Scalar> DevTensor;
@@ -122,6 +122,38 @@ public:
 		}
 		in_cache = std::move(in);
 		return out;
+	}
+	/** b200::SplitBackwardLayer: dX = dY W^T alone, and dW += X^T dY, db += sum dY for any batch. */
+	inline bool can_split_backward() const {
+		return true;
+	}
+	inline DevTensor pass_back_input_dev(const DevTensor& out_grad) {
+		DevTensor prev_out_grad;
+		if (Base::is_input_layer())
+			return prev_out_grad;
+		prev_out_grad = DevTensor(out_grad.rows, Base::input_dims.get_volume());
+		B200Parameters<Scalar>& w = static_cast<B200Parameters<Scalar>&>(*Base::weights);
+		b200::Context& c = b200::Context::get();
+		b200::Context::Lock l = c.lock();
+		CATTLE_B200_CHECK(b200::Api<Scalar>::dense_backward(c.handle(), (std::int32_t) out_grad.rows,
+				(std::int32_t) Base::input_dims.get_volume(), (std::int32_t) Base::output_dims.get_volume(), nullptr,
+				w.device_values(), out_grad.data(), nullptr, nullptr, prev_out_grad.data()));
+		return prev_out_grad;
+	}
+	inline void accumulate_param_grads_dev(const DevTensor& in, const DevTensor& out_grad) {
+		if (in.empty() || in.rows != out_grad.rows)
+			throw b200::Error(CATTL3_ERR_INVALID, "DenseKernelLayer: parameter gradients need matching input and gradient batches");
+		B200Parameters<Scalar>& w = static_cast<B200Parameters<Scalar>&>(*Base::weights);
+		B200Parameters<Scalar>& b = static_cast<B200Parameters<Scalar>&>(*Base::bias);
+		b200::Context& c = b200::Context::get();
+		{
+			b200::Context::Lock l = c.lock();
+			CATTLE_B200_CHECK(b200::Api<Scalar>::dense_backward(c.handle(), (std::int32_t) out_grad.rows,
+					(std::int32_t) Base::input_dims.get_volume(), (std::int32_t) Base::output_dims.get_volume(), in.data(),
+					w.device_values(), out_grad.data(), w.device_grad(), b.device_grad(), nullptr));
+		}
+		w.grad_written_on_device();
+		b.grad_written_on_device();
 	}
 	inline DevTensor pass_back_dev(DevTensor out_grad) {
 		if (in_cache.empty() || in_cache.rows != out_grad.rows)

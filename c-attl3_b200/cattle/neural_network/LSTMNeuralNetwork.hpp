@@ -15,7 +15,9 @@
  * What changes is where they run: the whole sequence stays in HBM.  A time step is one strided copy out of the
  * (samples * steps) x volume sequence (b200::time_step_of), the kernels and activations are driven through their
  * device faces (b200::DeviceLayer; layers that only speak the host API are bridged with a round trip), and the gate
- * arithmetic is the cattl3_muladd kernel.  The host API (propagate / backpropagate on rank + 2 tensors) is one upload,
+ * arithmetic is the cattl3_muladd kernel.  The cells share their kernels' parameters, so the eight weight gradients are
+ * taken once over the whole sequence (one GEMM over samples * steps rows each, b200::SplitBackwardLayer) instead of
+ * once per time step; CATTL3_LSTM_STEPWISE_WGRAD=1 keeps the per-step form (A/B, tests).  The host API (propagate / backpropagate on rank + 2 tensors) is one upload,
  * the device path and one download; b200::DeviceSequenceNetwork lets a sequential stack and the batch loop skip
  * even that.
  *
@@ -30,6 +32,7 @@
 #include <algorithm>
 #include <array>
 #include <cassert>
+#include <cstdlib>
 #include <functional>
 #include <memory>
 #include <utility>
@@ -166,6 +169,7 @@ public:
 		// the hidden state and the unrolled cells go as well (:243-249)
 		batch_size = -1;
 		state = DevTensor();
+		input_seq = hidden_seq = DevTensor();
 		input_seq_length = -1;
 		output_seq_length = -1;
 		output_seq_delay = -1;
@@ -201,6 +205,10 @@ public:
 		DevTensor out;
 		if (out_len > 1)
 			out = DevTensor(samples * out_len, out_volume);
+		// batched weight gradients (see backpropagate_seq_dev): the input sequence and the hidden outputs as sequences
+		const bool batched = training && batched_weight_gradients();
+		input_seq = batched ? input : DevTensor();
+		hidden_seq = batched && time_steps > 1 ? DevTensor(samples * (time_steps - 1), out_volume) : DevTensor();
 		DevTensor hidden_out;
 		int out_step = 0;
 		for (int i = 0; i < time_steps; ++i) {
@@ -221,6 +229,8 @@ public:
 			cell.activated_state = forward(*cell.state_act, state, training);
 			hidden_out = DevTensor(samples, out_volume);
 			muladd(false, cell.read_filter, cell.activated_state, nullptr, nullptr, hidden_out);
+			if (batched && i + 1 < time_steps)
+				b200::set_time_step(hidden_seq, samples, (std::size_t) (time_steps - 1), (std::size_t) i, hidden_out);
 			if (i >= out_delay && i < out_end) {
 				if (out_len > 1)
 					b200::set_time_step(out, samples, (std::size_t) out_len, (std::size_t) out_step++, hidden_out);
@@ -247,6 +257,19 @@ public:
 			prev_out_grad = DevTensor(samples * in_len, input_dims.get_volume());
 		DevTensor state_grad(samples, out_volume, true), hidden_out_grad(samples, out_volume, true);
 		int out_step = out_len - 1, in_step = in_len - 1;
+		// The cells share their kernels' parameters, so a kernel's weight gradient over the whole sequence is one GEMM
+		// over samples * steps rows (b200::SplitBackwardLayer) instead of one small GEMM and split-K reduction per step:
+		// per step only the input gradients are taken, the gate gradients are collected as sequences, and the eight
+		// weight (and bias) gradients follow the loop.  Not with multiplicative integration (its kernels see products).
+		const bool batched = !input_seq.empty();
+		DevTensor gate_grads_in[GATES], gate_grads_out[GATES];
+		if (batched) {
+			for (int g = 0; g < GATES; ++g) {
+				gate_grads_in[g] = DevTensor(samples * in_len, out_volume);
+				if (time_steps > 1)
+					gate_grads_out[g] = DevTensor(samples * (time_steps - 1), out_volume);
+			}
+		}
 		for (int i = time_steps - 1; i >= 0; --i) {
 			Cell& cell = i == 0 ? main_cell : cells[i - 1];
 			// the gradient of a non-hidden output at this step joins the hidden output's (:420-428)
@@ -264,10 +287,20 @@ public:
 			static const Gate order[GATES] = { READ, CANDIDATE, WRITE, FORGET };
 			const bool has_input = i < in_len, has_hidden = i > 0;
 			const bool integrated = MulInt && has_input && has_hidden;
+			if (batched) {
+				for (int g = 0; g < GATES; ++g) {
+					if (has_input)
+						b200::set_time_step(gate_grads_in[g], samples, (std::size_t) in_len,
+								(std::size_t) (reversed ? in_len - 1 - i : i), grad[g]);
+					if (has_hidden)
+						b200::set_time_step(gate_grads_out[g], samples, (std::size_t) (time_steps - 1), (std::size_t) (i - 1), grad[g]);
+				}
+			}
 			if (has_hidden) {
 				DevTensor sum;
 				for (Gate g : order) {
-					DevTensor part = backward(*cell.out_kernel[g], integrated ? product(cell.weighted_in[g], grad[g]) : grad[g]);
+					DevTensor part = batched ? split(*main_cell.out_kernel[g]).pass_back_input_dev(grad[g]) :
+							backward(*cell.out_kernel[g], integrated ? product(cell.weighted_in[g], grad[g]) : grad[g]);
 					if (sum.empty())
 						sum = std::move(part);
 					else
@@ -278,7 +311,10 @@ public:
 			if (has_input) {
 				DevTensor sum;
 				for (Gate g : order) {
-					DevTensor part = backward(*cell.in_kernel[g], integrated ? product(cell.weighted_out[g], grad[g]) : grad[g]);
+					if (batched && foremost)
+						continue;   // input layers: no input gradient, and the weight gradients follow the loop
+					DevTensor part = batched ? split(*main_cell.in_kernel[g]).pass_back_input_dev(grad[g]) :
+							backward(*cell.in_kernel[g], integrated ? product(cell.weighted_out[g], grad[g]) : grad[g]);
 					if (foremost || part.empty())
 						continue;   // input layers return nothing (C-ATTL3/core/Layer.hpp:82-90)
 					if (sum.empty())
@@ -292,6 +328,13 @@ public:
 					else
 						prev_out_grad = std::move(sum);
 				}
+			}
+		}
+		if (batched) {
+			for (int g = 0; g < GATES; ++g) {
+				split(*main_cell.in_kernel[g]).accumulate_param_grads_dev(input_seq, gate_grads_in[g]);
+				if (time_steps > 1)
+					split(*main_cell.out_kernel[g]).accumulate_param_grads_dev(hidden_seq, gate_grads_out[g]);
 			}
 		}
 		return prev_out_grad;
@@ -310,6 +353,8 @@ public:
 		swap(network1.output_dims, network2.output_dims);
 		swap(network1.cells, network2.cells);
 		swap(network1.state, network2.state);
+		swap(network1.input_seq, network2.input_seq);
+		swap(network1.hidden_seq, network2.hidden_seq);
 		swap(network1.batch_size, network2.batch_size);
 		swap(network1.input_seq_length, network2.input_seq_length);
 		swap(network1.output_seq_length, network2.output_seq_length);
@@ -453,6 +498,27 @@ private:
 			return DevTensor();
 		return b200::to_device<Scalar,Rank + 1>(prev_out_grad);
 	}
+	/** Whether every kernel's backward pass can be split (and the network does not integrate multiplicatively). */
+	inline bool batched_weight_gradients() const {
+		static const bool enabled = [] {
+			const char* v = std::getenv("CATTL3_LSTM_STEPWISE_WGRAD");
+			return !(v && v[0] && v[0] != '0');
+		}();
+		if (MulInt || !enabled)
+			return false;
+		for (int g = 0; g < GATES; ++g) {
+			const b200::SplitBackwardLayer<Scalar,Rank>* in = dynamic_cast<const b200::SplitBackwardLayer<Scalar,Rank>*>(
+					main_cell.in_kernel[g].get());
+			const b200::SplitBackwardLayer<Scalar,Rank>* out = dynamic_cast<const b200::SplitBackwardLayer<Scalar,Rank>*>(
+					main_cell.out_kernel[g].get());
+			if (!in || !out || !in->can_split_backward() || !out->can_split_backward())
+				return false;
+		}
+		return true;
+	}
+	inline static b200::SplitBackwardLayer<Scalar,Rank>& split(KernelLayer<Scalar,Rank>& kernel) {
+		return dynamic_cast<b200::SplitBackwardLayer<Scalar,Rank>&>(kernel);
+	}
 	/** out = (accumulate ? out : 0) + a * b (+ c * d). */
 	inline static void muladd(bool accumulate, const DevTensor& a, const DevTensor& b, const DevTensor* c_factor,
 			const DevTensor* d_factor, DevTensor& out) {
@@ -484,6 +550,8 @@ private:
 	typename Root::Dims input_dims, output_dims;
 	std::vector<Cell> cells;
 	DevTensor state;
+	// the last training pass's input sequence and hidden outputs h_0 ... h_{steps - 2} as sequences (batched weight gradients)
+	DevTensor input_seq, hidden_seq;
 	int batch_size, input_seq_length, output_seq_length, output_seq_delay;
 };
 

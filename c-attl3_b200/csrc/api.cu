@@ -263,16 +263,20 @@ static int conv_backward(cattl3_ctx* ctx, const cattl3_conv_geom* g, const S* x,
 	CATTL3_CHECK(check_ctx(ctx));
 	int oh, ow;
 	CATTL3_CHECK(check_geom(g, 0, &oh, &ow));
-	CATTL3_REQUIRE(x && w && dy && dw && db, "conv_backward: null tensor");
+	// dw == db == NULL: the input gradient alone (an unrolled recurrent network takes its shared kernels' weight gradients
+	// once over all time steps instead of once per step)
+	CATTL3_REQUIRE(w && dy && ((x && dw && db) || (!dw && !db && dx)), "conv_backward: null tensor");
 	const long long T = (long long) g->rh * g->rw;
-	// dW += cols^T dY (ConvKernelLayer.hpp:154)
-	GatherGeom gw = fwd_gather(g->n, g->h, g->w, g->c, oh, ow, g->f, g);
-	gw.w_stap = 1; gw.w_sr = T; gw.w_sj = T * g->c;
-	bool db_done = false;
-	CATTL3_CHECK(run_wgrad<S>(ctx, gw, x, dy, dw, db, &db_done));
-	// db += colsum(dY) (:155), unless the weight-gradient kernel already produced it from its own read of dY
-	if (!db_done)
-		CATTL3_CHECK(colsum_accumulate<S>(ctx, (int64_t) g->n * oh * ow, g->f, dy, db));
+	if (dw) {
+		// dW += cols^T dY (ConvKernelLayer.hpp:154)
+		GatherGeom gw = fwd_gather(g->n, g->h, g->w, g->c, oh, ow, g->f, g);
+		gw.w_stap = 1; gw.w_sr = T; gw.w_sj = T * g->c;
+		bool db_done = false;
+		CATTL3_CHECK(run_wgrad<S>(ctx, gw, x, dy, dw, db, &db_done));
+		// db += colsum(dY) (:155), unless the weight-gradient kernel already produced it from its own read of dY
+		if (!db_done)
+			CATTL3_CHECK(colsum_accumulate<S>(ctx, (int64_t) g->n * oh * ow, g->f, dy, db));
+	}
 	if (!dx)
 		return CATTL3_OK;  // input layer (:156-157)
 	// dX = crop(col2im(dY W^T)) (:159-188) as a gather over (tap, f)

@@ -254,6 +254,10 @@ int cattl3_conv_forward_f64(cattl3_ctx*, const cattl3_conv_geom*, const double* 
  * ConvKernelLayerBase::_pass_back (ConvKernelLayer.hpp:149-189).  dw and db ACCUMULATE (beta = 1,
  * Parameters::accumulate_grad, StandardParameters.hpp:115-123); dx is overwritten and may be NULL
  * for an input layer (Layer.hpp:82-90).  The weight gradient is a deterministic split-K reduction.
+ * dw = db = NULL (then x may be NULL too): only the input gradient -- the cells of an unrolled recurrent network
+ * share their kernels' parameters (LSTMNeuralNetwork.hpp:537-573), so their weight gradients are taken in one call
+ * over all time steps (n = samples * steps: the sequence layout makes that a plain batch).  The same holds for
+ * cattl3_dense_backward.
  */
 int cattl3_conv_backward_f32(cattl3_ctx*, const cattl3_conv_geom*, const float* x, const float* w, const float* dy, float* dw, float* db, float* dx);
 int cattl3_conv_backward_f64(cattl3_ctx*, const cattl3_conv_geom*, const double* x, const double* w, const double* dy, double* dw, double* db, double* dx);
