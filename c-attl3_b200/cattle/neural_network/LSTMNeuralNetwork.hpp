@@ -209,23 +209,37 @@ public:
 		const bool batched = training && batched_weight_gradients();
 		input_seq = batched ? input : DevTensor();
 		hidden_seq = batched && time_steps > 1 ? DevTensor(samples * (time_steps - 1), out_volume) : DevTensor();
+		// The input kernels do not depend on the recurrence: in the batched mode each runs ONCE over the whole input
+		// sequence (samples * steps rows), and a step takes its slice of that output.
+		DevTensor input_parts[GATES];
+		if (batched) {
+			for (int g = 0; g < GATES; ++g)
+				input_parts[g] = forward(*main_cell.in_kernel[g], input, training);
+		}
 		DevTensor hidden_out;
 		int out_step = 0;
 		for (int i = 0; i < time_steps; ++i) {
 			Cell& cell = !training || i == 0 ? main_cell : cells[i - 1];
 			const bool has_input = i < in_len, has_hidden = i > 0;
-			DevTensor x;
-			if (has_input)
-				x = b200::time_step_of(input, samples, (std::size_t) in_len, (std::size_t) (reversed ? in_len - 1 - i : i));
+			const std::size_t in_slot = (std::size_t) (reversed ? in_len - 1 - i : i);
+			DevTensor x, part[GATES];
+			if (has_input && batched) {
+				for (int g = 0; g < GATES; ++g)
+					part[g] = b200::time_step_of(input_parts[g], samples, (std::size_t) in_len, in_slot);
+			} else if (has_input) {
+				x = b200::time_step_of(input, samples, (std::size_t) in_len, in_slot);
+			}
+			const bool sliced = has_input && batched;
 			// state update: selective remembrance, then the filtered candidates (:290-296, :318-347, :352-361)
-			cell.forget_filter = gate(cell, FORGET, x, hidden_out, has_input, has_hidden, training);
+			cell.forget_filter = gate(cell, FORGET, x, hidden_out, has_input, has_hidden, training, sliced ? &part[FORGET] : nullptr);
 			cell.prev_state = std::move(state);
-			cell.write_filter = gate(cell, WRITE, x, hidden_out, has_input, has_hidden, training);
-			cell.candidates = gate(cell, CANDIDATE, x, hidden_out, has_input, has_hidden, training);
+			cell.write_filter = gate(cell, WRITE, x, hidden_out, has_input, has_hidden, training, sliced ? &part[WRITE] : nullptr);
+			cell.candidates = gate(cell, CANDIDATE, x, hidden_out, has_input, has_hidden, training,
+					sliced ? &part[CANDIDATE] : nullptr);
 			state = DevTensor(samples, out_volume);
 			muladd(false, cell.forget_filter, cell.prev_state, &cell.write_filter, &cell.candidates, state);
 			// output computation (:364-385)
-			cell.read_filter = gate(cell, READ, x, hidden_out, has_input, has_hidden, training);
+			cell.read_filter = gate(cell, READ, x, hidden_out, has_input, has_hidden, training, sliced ? &part[READ] : nullptr);
 			cell.activated_state = forward(*cell.state_act, state, training);
 			hidden_out = DevTensor(samples, out_volume);
 			muladd(false, cell.read_filter, cell.activated_state, nullptr, nullptr, hidden_out);
@@ -253,7 +267,7 @@ public:
 		const int time_steps = std::max(in_len, out_end);
 		const std::size_t out_volume = output_dims.get_volume();
 		DevTensor prev_out_grad;
-		if (!foremost && in_len > 1)
+		if (!foremost && in_len > 1 && (input_seq.empty() || reversed))
 			prev_out_grad = DevTensor(samples * in_len, input_dims.get_volume());
 		DevTensor state_grad(samples, out_volume, true), hidden_out_grad(samples, out_volume, true);
 		int out_step = out_len - 1, in_step = in_len - 1;
@@ -308,7 +322,7 @@ public:
 				}
 				hidden_out_grad = std::move(sum);
 			}
-			if (has_input) {
+			if (has_input && !(batched && !reversed)) {
 				DevTensor sum;
 				for (Gate g : order) {
 					if (batched && foremost)
@@ -328,6 +342,18 @@ public:
 					else
 						prev_out_grad = std::move(sum);
 				}
+			}
+		}
+		if (batched && !reversed && !foremost) {
+			// the input gradient of the input kernels, once over the whole sequence, in the per-step order of summation.
+			// (A reversed network keeps the per-step form above: the reference returns its gradient in loop order, :483-489.)
+			static const Gate order[GATES] = { READ, CANDIDATE, WRITE, FORGET };
+			for (Gate g : order) {
+				DevTensor part = split(*main_cell.in_kernel[g]).pass_back_input_dev(gate_grads_in[g]);
+				if (prev_out_grad.empty() || g == READ)
+					prev_out_grad = std::move(part);
+				else
+					add(prev_out_grad, part);
 			}
 		}
 		if (batched) {
@@ -458,10 +484,11 @@ private:
 	 * (multiplicative integration) multiplied where both exist.
 	 */
 	inline static DevTensor gate(Cell& cell, int g, const DevTensor& x, const DevTensor& hidden_out, bool has_input,
-			bool has_hidden, bool training) {
+			bool has_hidden, bool training, const DevTensor* input_part = nullptr) {
+		// input_part: this step's slice of the input kernel's output over the whole sequence (batched input kernels)
 		DevTensor weighted;
 		if (has_input && has_hidden) {
-			DevTensor from_input = forward(*cell.in_kernel[g], x, training);
+			DevTensor from_input = input_part ? *input_part : forward(*cell.in_kernel[g], x, training);
 			DevTensor from_hidden = forward(*cell.out_kernel[g], hidden_out, training);
 			if (MulInt) {
 				weighted = DevTensor(from_input.rows, from_input.size() / from_input.rows);
@@ -476,7 +503,7 @@ private:
 				weighted = std::move(from_input);
 			}
 		} else if (has_input) {
-			weighted = forward(*cell.in_kernel[g], x, training);
+			weighted = input_part ? *input_part : forward(*cell.in_kernel[g], x, training);
 		} else {
 			weighted = forward(*cell.out_kernel[g], hidden_out, training);
 		}
