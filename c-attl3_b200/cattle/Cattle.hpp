@@ -52,6 +52,7 @@
 #include "neural_network/ParallelNeuralNetwork.hpp"
 #include "neural_network/SequentialNeuralNetwork.hpp"
 #include "neural_network/LSTMNeuralNetwork.hpp"
+#include "neural_network/RecurrentNeuralNetwork.hpp"
 #include "data_provider/MemoryDataProvider.hpp"
 #include "neural_network/FeedforwardNeuralNetwork.hpp"
 #include "neural_network/ResidualNeuralNetwork.hpp"

@@ -13,6 +13,7 @@
 #include <array>
 #include <cstddef>
 
+#include "core/Layer.hpp"
 #include "b200/DeviceLayer.hpp"
 
 namespace cattle {
@@ -91,6 +92,61 @@ inline void set_time_step(DeviceTensor<Scalar>& seq, std::size_t samples, std::s
 	Context::Lock l = c.lock();
 	CATTLE_B200_CHECK(cattl3_memcpy_2d(c.handle(), seq.data() + samples * step, samples * steps * sizeof(Scalar),
 			slice.data(), samples * sizeof(Scalar), samples * sizeof(Scalar), volume));
+}
+
+// ---- what the cells of an unrolled recurrent network are made of (LSTMNeuralNetwork, RecurrentNeuralNetwork) ----------
+
+/** Layer::pass_forward on the device; a layer without a device face is bridged through the host. */
+template<typename Scalar, std::size_t Rank>
+inline DeviceTensor<Scalar> layer_forward_dev(Layer<Scalar,Rank>& layer, DeviceTensor<Scalar> in, bool training) {
+	if (DeviceLayer<Scalar,Rank>* dev = dynamic_cast<DeviceLayer<Scalar,Rank>*>(&layer))
+		return dev->pass_forward_dev(std::move(in), training);
+	return to_device<Scalar,Rank + 1>(layer.pass_forward(to_host<Scalar,Rank + 1>(in,
+			batch_extents<Rank>(in.rows, layer.get_input_dims())), training));
+}
+
+/** Layer::pass_back on the device (host bridge as above); an empty tensor where the layer returns none. */
+template<typename Scalar, std::size_t Rank>
+inline DeviceTensor<Scalar> layer_backward_dev(Layer<Scalar,Rank>& layer, DeviceTensor<Scalar> out_grad) {
+	if (DeviceLayer<Scalar,Rank>* dev = dynamic_cast<DeviceLayer<Scalar,Rank>*>(&layer))
+		return dev->pass_back_dev(std::move(out_grad));
+	Tensor<Scalar,Rank + 1> prev_out_grad = layer.pass_back(to_host<Scalar,Rank + 1>(out_grad,
+			batch_extents<Rank>(out_grad.rows, layer.get_output_dims())));
+	if (prev_out_grad.size() == 0)
+		return DeviceTensor<Scalar>();
+	return to_device<Scalar,Rank + 1>(prev_out_grad);
+}
+
+/** out = (accumulate ? out : 0) + a * b (+ c * d): cattl3_muladd; `out` may be one of the operands. */
+template<typename Scalar>
+inline void tensor_muladd(bool accumulate, const DeviceTensor<Scalar>& a, const DeviceTensor<Scalar>& b,
+		const DeviceTensor<Scalar>* c_factor, const DeviceTensor<Scalar>* d_factor, DeviceTensor<Scalar>& out) {
+	if (a.size() != out.size() || b.size() != out.size() || (c_factor && (!d_factor || c_factor->size() != out.size() ||
+			d_factor->size() != out.size())))
+		throw Error(CATTL3_ERR_INVALID, "tensor_muladd: the tensors differ in size");
+	Context& c = Context::get();
+	Context::Lock l = c.lock();
+	CATTLE_B200_CHECK(Api<Scalar>::muladd(c.handle(), (std::int64_t) out.size(), accumulate ? 1 : 0, a.data(), b.data(),
+			c_factor ? c_factor->data() : nullptr, d_factor ? d_factor->data() : nullptr, out.data()));
+}
+
+/** a * b as a new tensor. */
+template<typename Scalar>
+inline DeviceTensor<Scalar> tensor_product(const DeviceTensor<Scalar>& a, const DeviceTensor<Scalar>& b) {
+	DeviceTensor<Scalar> out(a.rows, a.size() / a.rows);
+	tensor_muladd<Scalar>(false, a, b, nullptr, nullptr, out);
+	return out;
+}
+
+/** y += x; y is exclusively owned afterwards (copy on write if it shared its buffer). */
+template<typename Scalar>
+inline void tensor_add(DeviceTensor<Scalar>& y, const DeviceTensor<Scalar>& x) {
+	if (x.size() != y.size())
+		throw Error(CATTL3_ERR_INVALID, "tensor_add: the tensors differ in size");
+	y.make_exclusive();
+	Context& c = Context::get();
+	Context::Lock l = c.lock();
+	CATTLE_B200_CHECK(Api<Scalar>::add_inplace(c.handle(), (std::int64_t) y.size(), y.data(), x.data()));
 }
 
 } /* namespace b200 */

@@ -509,21 +509,22 @@ private:
 		}
 		return forward(*cell.act[g], std::move(weighted), training);
 	}
-	/** Layer::pass_forward on the device; a layer without a device face is bridged through the host. */
+	// the cell's building blocks (b200/DeviceSequenceNetwork.hpp)
 	inline static DevTensor forward(Layer<Scalar,Rank>& layer, DevTensor in, bool training) {
-		if (b200::DeviceLayer<Scalar,Rank>* dev = dynamic_cast<b200::DeviceLayer<Scalar,Rank>*>(&layer))
-			return dev->pass_forward_dev(std::move(in), training);
-		return b200::to_device<Scalar,Rank + 1>(layer.pass_forward(b200::to_host<Scalar,Rank + 1>(in,
-				b200::batch_extents<Rank>(in.rows, layer.get_input_dims())), training));
+		return b200::layer_forward_dev<Scalar,Rank>(layer, std::move(in), training);
 	}
 	inline static DevTensor backward(Layer<Scalar,Rank>& layer, DevTensor out_grad) {
-		if (b200::DeviceLayer<Scalar,Rank>* dev = dynamic_cast<b200::DeviceLayer<Scalar,Rank>*>(&layer))
-			return dev->pass_back_dev(std::move(out_grad));
-		Tensor<Scalar,Rank + 1> prev_out_grad = layer.pass_back(b200::to_host<Scalar,Rank + 1>(out_grad,
-				b200::batch_extents<Rank>(out_grad.rows, layer.get_output_dims())));
-		if (prev_out_grad.size() == 0)
-			return DevTensor();
-		return b200::to_device<Scalar,Rank + 1>(prev_out_grad);
+		return b200::layer_backward_dev<Scalar,Rank>(layer, std::move(out_grad));
+	}
+	inline static void muladd(bool accumulate, const DevTensor& a, const DevTensor& b, const DevTensor* c_factor,
+			const DevTensor* d_factor, DevTensor& out) {
+		b200::tensor_muladd<Scalar>(accumulate, a, b, c_factor, d_factor, out);
+	}
+	inline static DevTensor product(const DevTensor& a, const DevTensor& b) {
+		return b200::tensor_product<Scalar>(a, b);
+	}
+	inline static void add(DevTensor& y, const DevTensor& x) {
+		b200::tensor_add<Scalar>(y, x);
 	}
 	/** Whether every kernel's backward pass can be split (and the network does not integrate multiplicatively). */
 	inline bool batched_weight_gradients() const {
@@ -545,31 +546,6 @@ private:
 	}
 	inline static b200::SplitBackwardLayer<Scalar,Rank>& split(KernelLayer<Scalar,Rank>& kernel) {
 		return dynamic_cast<b200::SplitBackwardLayer<Scalar,Rank>&>(kernel);
-	}
-	/** out = (accumulate ? out : 0) + a * b (+ c * d). */
-	inline static void muladd(bool accumulate, const DevTensor& a, const DevTensor& b, const DevTensor* c_factor,
-			const DevTensor* d_factor, DevTensor& out) {
-		if (a.size() != out.size() || b.size() != out.size() || (c_factor && (c_factor->size() != out.size() ||
-				d_factor->size() != out.size())))
-			throw b200::Error(CATTL3_ERR_INVALID, "LSTMNeuralNetwork: gate tensors differ in size");
-		b200::Context& c = b200::Context::get();
-		b200::Context::Lock l = c.lock();
-		CATTLE_B200_CHECK(b200::Api<Scalar>::muladd(c.handle(), (std::int64_t) out.size(), accumulate ? 1 : 0, a.data(), b.data(),
-				c_factor ? c_factor->data() : nullptr, d_factor ? d_factor->data() : nullptr, out.data()));
-	}
-	inline static DevTensor product(const DevTensor& a, const DevTensor& b) {
-		DevTensor out(a.rows, a.size() / a.rows);
-		muladd(false, a, b, nullptr, nullptr, out);
-		return out;
-	}
-	/** y += x (y exclusively owned afterwards). */
-	inline static void add(DevTensor& y, const DevTensor& x) {
-		if (x.size() != y.size())
-			throw b200::Error(CATTL3_ERR_INVALID, "LSTMNeuralNetwork: gradient tensors differ in size");
-		y.make_exclusive();
-		b200::Context& c = b200::Context::get();
-		b200::Context::Lock l = c.lock();
-		CATTLE_B200_CHECK(b200::Api<Scalar>::add_inplace(c.handle(), (std::int64_t) y.size(), y.data(), x.data()));
 	}
 	Cell main_cell;
 	OutputSeqSizeFunc output_seq_size_func;
