@@ -115,7 +115,7 @@ def test_golden_reproducible_from_reference(ref, golden):
 
 @pytest.mark.parametrize("suf,dt", DTYPES)
 def test_network_fixtures_reproduce_from_the_reference(ref, suf, dt):
-    """tests/golden/reference_networks.npz (configs 3 and 4) is what the unmodified reference computes from the
+    """tests/golden/reference_networks.npz (configs 3, 4, 5 and the regularised config 1) is what the unmodified reference computes from the
     seeded inputs of tests/cases.py: re-run it where oracle/_ref exists."""
     import os
     nets = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_networks.npz"))
@@ -128,3 +128,19 @@ def test_network_fixtures_reproduce_from_the_reference(ref, suf, dt):
     p1, loss, _ = ref.train_resnet(x, obj, 32, 2, C.RESNET_SMALL, params_in=C.seeded_params(n, dt, 4002))
     assert C.relerr(p1, nets["resnet/%s/p1" % suf]) < 10 * OTOL[dt]
     assert abs(loss - float(nets["resnet/%s/loss" % suf][0])) < 1e-5
+    # config 5: Sequential{Parallel conv lanes, DenseNet, MaxPool} -> convolutional LSTM
+    x, obj = C.seqnet_inputs(dt)
+    n = ref.train_seqnet(x, obj, 8, -1, **C.SEQNET_SMALL)
+    p1, loss, _ = ref.train_seqnet(x, obj, 8, 2, params_in=C.seeded_params(n, dt, 5002), **C.SEQNET_SMALL)
+    assert C.relerr(p1, nets["seqnet/%s/p1" % suf]) < 10 * OTOL[dt]
+    assert abs(loss - float(nets["seqnet/%s/loss" % suf][0])) < 1e-5
+    # config 1 with an ElasticNet penalty on every weight matrix (REF_SHIM_REG)
+    vectors = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.npz"))
+    x, obj = C.cifar_inputs(dt)
+    os.environ["REF_SHIM_REG"] = C.CIFAR_REG
+    try:
+        p1, loss, _ = ref.train_cifar(x, obj, 16, 2, params_in=np.ascontiguousarray(vectors["cifar/%s/p0" % suf]))
+    finally:
+        del os.environ["REF_SHIM_REG"]
+    assert C.relerr(p1, nets["cifar_reg/%s/p1" % suf]) < 10 * OTOL[dt]
+    assert abs(loss - float(nets["cifar_reg/%s/loss" % suf][0])) < 1e-5
