@@ -236,13 +236,16 @@ def main():
     xkeep = torch.empty(M * C, device=dev)
 
     def e2e_step():
-        ctx.conv_forward_host(g, xh, w, b, yh, xkeep)
-        ctx.conv_backward_host(g, xkeep, w, dyh, dw, db, dxh)
+        # enqueue the whole step (uploads, kernels, downloads on the library's three streams), then wait for the host
+        # tensors: y and dX are complete in pinned host memory when the step ends
+        ctx.conv_forward_host_async(g, xh, w, b, yh, xkeep)
+        ctx.conv_backward_host_async(g, xkeep, w, dyh, dw, db, dxh)
         if dist is not None:
             dist.all_reduce(grads)
         st = pkg.make_opt_step(pkg.OPT["nadam"], NADAM, tstep[0], 0, 0.0, True)
         ctx.optimizer_step(st, arena.numel(), arena, grads, m_state, v_state)
         tstep[0] += 1
+        ctx.host_wait()
 
     e2e_step()
     barrier()
@@ -310,7 +313,8 @@ def main():
                    "conv_tflops_per_gpu": round(3 * FLOP_PER_PASS / (ms_per_step * 1e-3) / 1e12, 2)},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "cattl3_conv_forward_host_f32 + cattl3_conv_backward_host_f32 + optimizer step"},
+                "steps": e2e_steps, "api": "cattl3_conv_forward_host_async_f32 + cattl3_conv_backward_host_async_f32 + optimizer step + "
+                       "cattl3_host_wait per step (uploads / kernels / downloads pipelined over filter chunks on three streams)"},
         "gpu_launches": launches,
         "roofline": roofline,
         "kernels": kernels,

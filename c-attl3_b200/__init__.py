@@ -73,6 +73,7 @@ _SYMBOLS = [
     "cattl3_conv_output_dims", "cattl3_pool_output_dims", "cattl3_feed_create", "cattl3_feed_destroy", "cattl3_feed_push",
     "cattl3_ctx_allocated_bytes", "cattl3_graph_begin", "cattl3_graph_end", "cattl3_graph_launch", "cattl3_graph_destroy",
     "cattl3_conv_forward_host_f32", "cattl3_conv_backward_host_f32",
+    "cattl3_conv_forward_host_async_f32", "cattl3_conv_backward_host_async_f32", "cattl3_host_wait",
     "cattl3_comm_unique_id", "cattl3_comm_create", "cattl3_comm_create_from_env", "cattl3_comm_destroy",
     "cattl3_comm_world_size", "cattl3_comm_rank", "cattl3_comm_group_start", "cattl3_comm_group_end",
     "cattl3_comm_allreduce_sum_f32", "cattl3_comm_allreduce_sum_f64",
@@ -264,6 +265,17 @@ class Context:
     def conv_backward_host(self, g, x_dev, w, dy_host, dw, db, dx_host):
         self._chk(self.L.cattl3_conv_backward_host_f32(self.h, ctypes.byref(g), _p(x_dev), _p(w), _p(dy_host),
                                                        _p(dw), _p(db), _p(dx_host)))
+
+    def conv_forward_host_async(self, g, x_host, w, b, y_host, x_dev_keep=None):
+        self._chk(self.L.cattl3_conv_forward_host_async_f32(self.h, ctypes.byref(g), _p(x_host), _p(w), _p(b),
+                                                            _p(y_host), _p(x_dev_keep)))
+
+    def conv_backward_host_async(self, g, x_dev, w, dy_host, dw, db, dx_host):
+        self._chk(self.L.cattl3_conv_backward_host_async_f32(self.h, ctypes.byref(g), _p(x_dev), _p(w), _p(dy_host),
+                                                             _p(dw), _p(db), _p(dx_host)))
+
+    def host_wait(self):
+        self._chk(self.L.cattl3_host_wait(self.h))
 
     def activation_forward(self, kind, alpha, rows, vol, x, y):
         _, ct = _suffix(x.dtype)

@@ -399,8 +399,16 @@ int cattl3_ctx_destroy(cattl3_ctx* ctx) {
 		cudaFree(ctx->arenas[a].base);
 	for (int i = 0; i < 8; ++i)
 		if (ctx->throttle_ev[i]) cudaEventDestroy(ctx->throttle_ev[i]);
-	for (int i = 0; i < 3; ++i)
+	for (int i = 0; i < 5; ++i)
 		if (ctx->stage_dev[i]) cudaFree(ctx->stage_dev[i]);
+	if (ctx->up_stream) {
+		cudaStreamSynchronize(ctx->up_stream);
+		cudaStreamSynchronize(ctx->down_stream);
+		for (int i = 0; i < cattl3_ctx::HOST_EVENTS; ++i)
+			if (ctx->host_ev[i]) cudaEventDestroy(ctx->host_ev[i]);
+		cudaStreamDestroy(ctx->up_stream);
+		cudaStreamDestroy(ctx->down_stream);
+	}
 	if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 	return CATTL3_OK;
@@ -821,52 +829,156 @@ int cattl3_dense_backward_##SUF(cattl3_ctx* c, int32_t n, int32_t in, int32_t ou
 KERNEL_LAYER_API(float, f32)
 KERNEL_LAYER_API(double, f64)
 
-// Host-buffer convolution: H2D of the activations, the device kernels, D2H of the result, all on
-// the context's stream; the final D2H synchronises.  x_dev_keep (n*h*w*c floats, optional) receives
-// the device copy of x so that the matching backward call needs no second upload.
-int cattl3_conv_forward_host_f32(cattl3_ctx* ctx, const cattl3_conv_geom* g, const float* x_host, const float* w_dev,
+// Host-buffer convolution (what the reference's Layer API hands over: host tensors in, host tensors out), as a
+// three-stream pipeline: uploads on `up`, kernels on the context's stream, downloads on `down`, chained by events.
+// The work is cut into chunks of FILTERS -- the slowest dimension of y and dY, so a chunk of either is one contiguous
+// block, and a chunk of W / b / dW / db as well -- so that PCIe runs in both directions while the kernels work:
+//   forward : x up | chunk k: y[:, k] = conv(x, W[:, k]) -> y[:, k] down while chunk k + 1 computes
+//   backward: chunk k: dY[:, k] up while chunk k - 1 computes | dW[:, k], db[k] += ...; dX += dY[:, k] * W[:, k]^T | dX down
+// The *_async entry points return once everything is enqueued (a forward's download of y then overlaps the
+// following backward's upload of dY: full-duplex PCIe); cattl3_host_wait() is the point after which the host
+// buffers hold the results.  The plain entry points are *_async + cattl3_host_wait.
+// x_dev_keep (n*h*w*c floats, optional) receives the device copy of x so that the backward call needs no second upload.
+namespace {
+
+enum { ST_X = 0, ST_Y = 1, ST_DX = 2, ST_DY = 3, ST_DXT = 4 };
+
+int host_pipe_init(cattl3_ctx* ctx) {
+	if (ctx->up_stream) return CATTL3_OK;
+	CATTL3_CUDA(cudaStreamCreateWithFlags(&ctx->up_stream, cudaStreamNonBlocking));
+	CATTL3_CUDA(cudaStreamCreateWithFlags(&ctx->down_stream, cudaStreamNonBlocking));
+	for (int i = 0; i < cattl3_ctx::HOST_EVENTS; ++i)
+		CATTL3_CUDA(cudaEventCreateWithFlags(&ctx->host_ev[i], cudaEventDisableTiming));
+	return CATTL3_OK;
+}
+
+// filters per chunk: whole tensor-core tiles, at most CATTL3_HOST_CHUNKS (default 4) chunks
+int host_chunk_filters(const cattl3_conv_geom* g) {
+	const char* env = getenv("CATTL3_HOST_CHUNKS");
+	const int want = env ? atoi(env) : 4;
+	int chunks = want < 1 ? 1 : (want > cattl3_ctx::HOST_MAX_CHUNKS ? cattl3_ctx::HOST_MAX_CHUNKS : want);
+	while (chunks > 1 && (g->f % chunks != 0 || (g->f / chunks) % 64 != 0)) --chunks;
+	return g->f / chunks;
+}
+
+}  // namespace
+
+int cattl3_host_wait(cattl3_ctx* ctx) {
+	CATTL3_CHECK(check_ctx(ctx));
+	if (ctx->up_stream) {
+		CATTL3_CUDA(cudaStreamSynchronize(ctx->up_stream));
+		CATTL3_CUDA(cudaStreamSynchronize(ctx->stream));
+		CATTL3_CUDA(cudaStreamSynchronize(ctx->down_stream));
+	} else {
+		CATTL3_CUDA(cudaStreamSynchronize(ctx->stream));
+	}
+	return CATTL3_OK;
+}
+
+int cattl3_conv_forward_host_async_f32(cattl3_ctx* ctx, const cattl3_conv_geom* g, const float* x_host, const float* w_dev,
 		const float* b_dev, float* y_host, float* x_dev_keep) {
 	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(!ctx->capturing, "conv_forward_host: not inside a step graph");
 	int oh, ow;
 	CATTL3_CHECK(check_geom(g, 0, &oh, &ow));
 	CATTL3_REQUIRE(x_host && y_host, "conv_forward_host: null host tensor");
+	CATTL3_CHECK(host_pipe_init(ctx));
 	const size_t xb = sizeof(float) * (size_t) g->n * g->h * g->w * g->c;
-	const size_t yb = sizeof(float) * (size_t) g->n * oh * ow * g->f;
+	const size_t M = (size_t) g->n * oh * ow;
+	const size_t K = (size_t) g->rh * g->rw * g->c;
 	float* xd = x_dev_keep;
 	if (!xd) {
-		CATTL3_CHECK(ensure_buffer(ctx, &ctx->stage_dev[0], &ctx->stage_dev_bytes[0], xb));
-		xd = (float*) ctx->stage_dev[0];
+		CATTL3_CHECK(ensure_buffer(ctx, &ctx->stage_dev[ST_X], &ctx->stage_dev_bytes[ST_X], xb));
+		xd = (float*) ctx->stage_dev[ST_X];
 	}
-	CATTL3_CHECK(ensure_buffer(ctx, &ctx->stage_dev[1], &ctx->stage_dev_bytes[1], yb));
-	float* yd = (float*) ctx->stage_dev[1];
-	CATTL3_CUDA(cudaMemcpyAsync(xd, x_host, xb, cudaMemcpyHostToDevice, ctx->stream));
-	CATTL3_CHECK(conv_forward<float>(ctx, g, xd, w_dev, b_dev, yd));
-	CATTL3_CUDA(cudaMemcpyAsync(y_host, yd, yb, cudaMemcpyDeviceToHost, ctx->stream));
-	CATTL3_CUDA(cudaStreamSynchronize(ctx->stream));
+	CATTL3_CHECK(ensure_buffer(ctx, &ctx->stage_dev[ST_Y], &ctx->stage_dev_bytes[ST_Y], sizeof(float) * M * g->f));
+	float* yd = (float*) ctx->stage_dev[ST_Y];
+	cudaEvent_t* ev = ctx->host_ev;
+	// the upload of x follows everything enqueued so far that may still read the buffer it lands in
+	CATTL3_CUDA(cudaEventRecord(ev[cattl3_ctx::EV_ENTRY], ctx->stream));
+	CATTL3_CUDA(cudaStreamWaitEvent(ctx->up_stream, ev[cattl3_ctx::EV_ENTRY], 0));
+	CATTL3_CUDA(cudaMemcpyAsync(xd, x_host, xb, cudaMemcpyHostToDevice, ctx->up_stream));
+	CATTL3_CUDA(cudaEventRecord(ev[cattl3_ctx::EV_UP], ctx->up_stream));
+	CATTL3_CUDA(cudaStreamWaitEvent(ctx->stream, ev[cattl3_ctx::EV_UP], 0));
+	if (ctx->host_ev_used[cattl3_ctx::EV_Y_FREE])   // an earlier forward's download of the y stage
+		CATTL3_CUDA(cudaStreamWaitEvent(ctx->stream, ev[cattl3_ctx::EV_Y_FREE], 0));
+	const int fc = host_chunk_filters(g);
+	cattl3_conv_geom gc = *g;
+	gc.f = fc;
+	for (int f0 = 0, k = 0; f0 < g->f; f0 += fc, ++k) {
+		CATTL3_CHECK(conv_forward<float>(ctx, &gc, xd, w_dev + K * f0, b_dev ? b_dev + f0 : nullptr, yd + M * f0));
+		CATTL3_CUDA(cudaEventRecord(ev[cattl3_ctx::EV_CHUNK + k], ctx->stream));
+		CATTL3_CUDA(cudaStreamWaitEvent(ctx->down_stream, ev[cattl3_ctx::EV_CHUNK + k], 0));
+		CATTL3_CUDA(cudaMemcpyAsync(y_host + M * f0, yd + M * f0, sizeof(float) * M * fc, cudaMemcpyDeviceToHost, ctx->down_stream));
+	}
+	CATTL3_CUDA(cudaEventRecord(ev[cattl3_ctx::EV_Y_FREE], ctx->down_stream));
+	ctx->host_ev_used[cattl3_ctx::EV_Y_FREE] = true;
 	return CATTL3_OK;
+}
+
+int cattl3_conv_backward_host_async_f32(cattl3_ctx* ctx, const cattl3_conv_geom* g, const float* x_dev, const float* w_dev,
+		const float* dy_host, float* dw_dev, float* db_dev, float* dx_host) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(!ctx->capturing, "conv_backward_host: not inside a step graph");
+	int oh, ow;
+	CATTL3_CHECK(check_geom(g, 0, &oh, &ow));
+	CATTL3_REQUIRE(x_dev && dy_host, "conv_backward_host: null tensor");
+	CATTL3_CHECK(host_pipe_init(ctx));
+	const size_t x_elems = (size_t) g->n * g->h * g->w * g->c;
+	const size_t xb = sizeof(float) * x_elems;
+	const size_t M = (size_t) g->n * oh * ow;
+	const size_t K = (size_t) g->rh * g->rw * g->c;
+	CATTL3_CHECK(ensure_buffer(ctx, &ctx->stage_dev[ST_DY], &ctx->stage_dev_bytes[ST_DY], sizeof(float) * M * g->f));
+	float* dyd = (float*) ctx->stage_dev[ST_DY];
+	const int fc = host_chunk_filters(g);
+	float* dxd = nullptr;
+	float* dxt = nullptr;
+	if (dx_host) {
+		CATTL3_CHECK(ensure_buffer(ctx, &ctx->stage_dev[ST_DX], &ctx->stage_dev_bytes[ST_DX], xb));
+		dxd = (float*) ctx->stage_dev[ST_DX];
+		if (fc < g->f) {
+			CATTL3_CHECK(ensure_buffer(ctx, &ctx->stage_dev[ST_DXT], &ctx->stage_dev_bytes[ST_DXT], xb));
+			dxt = (float*) ctx->stage_dev[ST_DXT];
+		}
+	}
+	cudaEvent_t* ev = ctx->host_ev;
+	if (ctx->host_ev_used[cattl3_ctx::EV_DY_FREE])   // an earlier backward's kernels still reading the dY stage
+		CATTL3_CUDA(cudaStreamWaitEvent(ctx->up_stream, ev[cattl3_ctx::EV_DY_FREE], 0));
+	if (dxd && ctx->host_ev_used[cattl3_ctx::EV_DX_FREE])   // an earlier backward's download of the dX stage
+		CATTL3_CUDA(cudaStreamWaitEvent(ctx->stream, ev[cattl3_ctx::EV_DX_FREE], 0));
+	cattl3_conv_geom gc = *g;
+	gc.f = fc;
+	for (int f0 = 0, k = 0; f0 < g->f; f0 += fc, ++k) {
+		CATTL3_CUDA(cudaMemcpyAsync(dyd + M * f0, dy_host + M * f0, sizeof(float) * M * fc, cudaMemcpyHostToDevice, ctx->up_stream));
+		CATTL3_CUDA(cudaEventRecord(ev[cattl3_ctx::EV_CHUNK + k], ctx->up_stream));
+		CATTL3_CUDA(cudaStreamWaitEvent(ctx->stream, ev[cattl3_ctx::EV_CHUNK + k], 0));
+		// this chunk's share of every gradient: dW[:, chunk], db[chunk] (accumulating) and dY[:, chunk] * W[:, chunk]^T of dX
+		CATTL3_CHECK(conv_backward<float>(ctx, &gc, x_dev, w_dev + K * f0, dyd + M * f0, dw_dev ? dw_dev + K * f0 : nullptr,
+				db_dev ? db_dev + f0 : nullptr, dxd ? (k == 0 ? dxd : dxt) : nullptr));
+		if (dxd && k > 0)
+			CATTL3_CHECK(cattl3_add_inplace_f32(ctx, (int64_t) x_elems, dxd, dxt));
+	}
+	CATTL3_CUDA(cudaEventRecord(ev[cattl3_ctx::EV_DY_FREE], ctx->stream));
+	ctx->host_ev_used[cattl3_ctx::EV_DY_FREE] = true;
+	if (dx_host) {
+		CATTL3_CUDA(cudaStreamWaitEvent(ctx->down_stream, ev[cattl3_ctx::EV_DY_FREE], 0));
+		CATTL3_CUDA(cudaMemcpyAsync(dx_host, dxd, xb, cudaMemcpyDeviceToHost, ctx->down_stream));
+		CATTL3_CUDA(cudaEventRecord(ev[cattl3_ctx::EV_DX_FREE], ctx->down_stream));
+		ctx->host_ev_used[cattl3_ctx::EV_DX_FREE] = true;
+	}
+	return CATTL3_OK;
+}
+
+int cattl3_conv_forward_host_f32(cattl3_ctx* ctx, const cattl3_conv_geom* g, const float* x_host, const float* w_dev,
+		const float* b_dev, float* y_host, float* x_dev_keep) {
+	CATTL3_CHECK(cattl3_conv_forward_host_async_f32(ctx, g, x_host, w_dev, b_dev, y_host, x_dev_keep));
+	return cattl3_host_wait(ctx);
 }
 
 int cattl3_conv_backward_host_f32(cattl3_ctx* ctx, const cattl3_conv_geom* g, const float* x_dev, const float* w_dev,
 		const float* dy_host, float* dw_dev, float* db_dev, float* dx_host) {
-	CATTL3_CHECK(check_ctx(ctx));
-	int oh, ow;
-	CATTL3_CHECK(check_geom(g, 0, &oh, &ow));
-	CATTL3_REQUIRE(x_dev && dy_host, "conv_backward_host: null tensor");
-	const size_t xb = sizeof(float) * (size_t) g->n * g->h * g->w * g->c;
-	const size_t yb = sizeof(float) * (size_t) g->n * oh * ow * g->f;
-	CATTL3_CHECK(ensure_buffer(ctx, &ctx->stage_dev[1], &ctx->stage_dev_bytes[1], yb));
-	float* dyd = (float*) ctx->stage_dev[1];
-	float* dxd = nullptr;
-	if (dx_host) {
-		CATTL3_CHECK(ensure_buffer(ctx, &ctx->stage_dev[2], &ctx->stage_dev_bytes[2], xb));
-		dxd = (float*) ctx->stage_dev[2];
-	}
-	CATTL3_CUDA(cudaMemcpyAsync(dyd, dy_host, yb, cudaMemcpyHostToDevice, ctx->stream));
-	CATTL3_CHECK(conv_backward<float>(ctx, g, x_dev, w_dev, dyd, dw_dev, db_dev, dxd));
-	if (dx_host)
-		CATTL3_CUDA(cudaMemcpyAsync(dx_host, dxd, xb, cudaMemcpyDeviceToHost, ctx->stream));
-	CATTL3_CUDA(cudaStreamSynchronize(ctx->stream));
-	return CATTL3_OK;
+	CATTL3_CHECK(cattl3_conv_backward_host_async_f32(ctx, g, x_dev, w_dev, dy_host, dw_dev, db_dev, dx_host));
+	return cattl3_host_wait(ctx);
 }
 
 }

@@ -52,9 +52,15 @@ struct cattl3_ctx {
 	// cattl3_ctx_throttle: one event per recent call
 	cudaEvent_t throttle_ev[8] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
 	long long throttle_calls = 0;
-	// pinned staging for the *_host entry points
-	void* stage_dev[3] = { nullptr, nullptr, nullptr };
-	size_t stage_dev_bytes[3] = { 0, 0, 0 };
+	// device staging for the *_host entry points (x, y, dX, dY, a second dX for chunked input gradients) and their
+	// transfer pipeline: an upload and a download stream beside `stream`, chained by events (api.cu)
+	void* stage_dev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
+	size_t stage_dev_bytes[5] = { 0, 0, 0, 0, 0 };
+	cudaStream_t up_stream = nullptr, down_stream = nullptr;
+	static constexpr int HOST_MAX_CHUNKS = 8;
+	enum { EV_ENTRY = 0, EV_UP, EV_Y_FREE, EV_DY_FREE, EV_DX_FREE, EV_CHUNK, HOST_EVENTS = EV_CHUNK + HOST_MAX_CHUNKS };
+	cudaEvent_t host_ev[HOST_EVENTS] = {};
+	bool host_ev_used[HOST_EVENTS] = {};
 };
 
 namespace cattl3 {

@@ -79,21 +79,63 @@ __device__ __forceinline__ void cp_async_16(void* dst, const void* src, uint32_t
 	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ float4 lds_128(uint32_t addr) {
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+	return v;
+}
+__device__ __forceinline__ void sts_128(uint32_t addr, float4 v) {
+	asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 template<int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
 	asm volatile("prefetch.tensormap [%0];" :: "l"((uint64_t) tm) : "memory");
 }
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
-	asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(dst_smem)), "r"(cols) : "memory");
-	asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+// ---- CTA pairs (cta_group::2) ------------------------------------------------------------------------------
+// Two CTAs of one cluster (the two SMs of a TPC) issue ONE tcgen05.mma of M = 256: each CTA holds its own 128 rows of A
+// (and of the accumulator) in its own tensor memory and HALF of the rows of B in its own shared memory, so every byte
+// of B in shared memory feeds 256 accumulator rows instead of 128 (measured: scripts/tf32_peak.cu verifies the
+// operand placement).  CTA 0 (the leader) issues the MMAs and the commits; barriers that both CTAs arrive on live in
+// the leader and are reached through mapa; commits are multicast to the same barrier offset in both CTAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+	asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+	asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-	asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
+// arrive on the barrier at this offset in CTA `cta` of the cluster (release at cluster scope)
+// Measured (profiles/README.md, r2): cluster-scope release / acquire on these per-k-block handshakes compile to
+// MEMBAR.ALL.GPU and cost more than the pair saves; the plain forms (what CUTLASS' ClusterBarrier uses) order the
+// tcgen05 and TMA traffic they guard through tcgen05.fence / the mbarrier itself.
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
+	asm volatile(
+		"{\n\t.reg .b32 ra;\n\t"
+		"mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+		"mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+		:: "r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+template<int CTAS> __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+	if (CTAS == 2) {
+		asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+	} else {
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+}
+template<int CTAS> __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+	if (CTAS == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
+	else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+// all MMAs issued so far by this thread -> one arrival on `bar` when they have completed; for a CTA pair the arrival
+// goes to the barrier at the same offset in both CTAs
+template<int CTAS> __device__ __forceinline__ void umma_commit(uint64_t* bar) {
+	if (CTAS == 2)
+		asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+				:: "r"(smem_u32(bar)), "h"((uint16_t) 3) : "memory");
+	else
+		asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by one thread.
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
@@ -104,13 +146,21 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
 		:: "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem]: the A operand (128 rows = TMEM lanes, K elements = consecutive columns)
-// is read from tensor memory, so only B costs shared-memory bandwidth.
-__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-	asm volatile(
-		"{\n\t.reg .pred p;\n\t"
-		"setp.ne.b32 p, %4, 0;\n\t"
-		"tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-		:: "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+// is read from tensor memory, so only B costs shared-memory bandwidth.  CTAS = 2: M = 256, the pair's MMA.
+template<int CTAS> __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+		uint32_t accumulate) {
+	if (CTAS == 2)
+		asm volatile(
+			"{\n\t.reg .pred p;\n\t"
+			"setp.ne.b32 p, %4, 0;\n\t"
+			"tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+			:: "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+	else
+		asm volatile(
+			"{\n\t.reg .pred p;\n\t"
+			"setp.ne.b32 p, %4, 0;\n\t"
+			"tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+			:: "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
 // registers -> 32 lanes x 16 consecutive columns of TMEM (lane = thread of the warp's lane quarter)
 __device__ __forceinline__ void tmem_st_16(uint32_t taddr, const uint32_t* r) {
@@ -161,8 +211,8 @@ __device__ __forceinline__ uint64_t kmajor_desc(uint32_t tile_addr, int kstep) {
 			: make_smem_desc(tile_addr + kstep * 32, 16, 512, LT_SW64);
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128, N runtime.
-__host__ __device__ inline uint32_t make_idesc_tf32(int n) {
-	return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (n >> 3) << 17) | ((uint32_t) (128 >> 4) << 24);
+__host__ __device__ inline uint32_t make_idesc_tf32(int n, int m = 128) {
+	return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (n >> 3) << 17) | ((uint32_t) (m >> 4) << 24);
 }
 
 // ---- 3xTF32 operand split -------------------------------------------------------------------------------
@@ -240,13 +290,13 @@ struct TcGemmParams {
 // The reduction walks channel chunks OUTER and taps INNER: the 148 CTAs then work on the same few channels
 // of neighbouring pixels at the same time, so every source byte is fetched from HBM once and the tap-shifted
 // re-reads hit L2.
-template<int KB>
+template<int KB, int CTAS>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tm_a,
 		const __grid_constant__ CUtensorMap tm_b, const TcGemmParams p) {
 	extern __shared__ __align__(1024) uint8_t smem_raw[];
 	uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
 	constexpr int A_BYTES = TC_BM * KB * 4;
-	const int b_bytes = p.BN * KB * 4;
+	const int b_bytes = p.BN / CTAS * KB * 4;   // a CTA of a pair holds half of the rows of B
 	const int stage_bytes = A_BYTES + 2 * b_bytes;
 	uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t) p.stages * stage_bytes);
 	uint64_t* full = bars;
@@ -262,18 +312,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int T = p.RH * p.RW;
 	const int kblocks = T * (p.r_pad / KB);
-	const int tiles = p.m_tiles * p.j_tiles;
+	const int tiles = p.m_tiles * p.j_tiles;   // m_tiles counts tiles of 128 * CTAS rows: a pair works on one together
 	const uint32_t a_col0 = (uint32_t) (p.nacc * p.BN);
+	const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
+	const int unit = blockIdx.x / CTAS, units = gridDim.x / CTAS;   // CTA (pair) index and count
+	constexpr int TILE_M = TC_BM * CTAS;
 
 	if (warp == 0 && elect_one()) {
 		tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b);
-		for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
-		for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+		// full: this CTA's TMA bytes; ready: one arrival per converter warp of the pair (in the leader); empty / acc_full:
+		// the leader's commit, multicast; acc_empty: one arrival per epilogue warp of the pair (in the leader)
+		for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 4 * CTAS); mbar_init(&empty[s], 1); }
+		for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4 * CTAS); }
 		fence_barrier_init();
 	}
-	if (warp == 1) tmem_alloc(tmem_slot, 512u);
+	if (warp == 1) tmem_alloc<CTAS>(tmem_slot, 512u);
 	tc_fence_before();
-	__syncthreads();
+	if (CTAS == 2) cluster_sync(); else __syncthreads();   // the peer's barriers exist before anything arrives on them
 	tc_fence_after();
 	const uint32_t tmem_base = *tmem_slot;
 
@@ -281,13 +336,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 		// ===== TMA producer =====
 		if (elect_one()) {
 			int s = 0; uint32_t ph = 0;
-			for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+			for (int tile = unit; tile < tiles; tile += units) {
 				const int mt = tile % p.m_tiles, jt = tile / p.m_tiles;
 				int gn[4], goh[4], gow[4];  // the 128 / nb row groups of this tile: (n0, oh, ow) each, or out of range
 				const int ngroups = TC_BM / p.nb;
 				#pragma unroll
 				for (int g = 0; g < 4; ++g) {
-					const long long m = (long long) mt * TC_BM + p.nb * g;
+					const long long m = (long long) mt * TILE_M + rank * TC_BM + p.nb * g;
 					if (g < ngroups && m < p.M) {
 						gn[g] = (int) (m % p.N);
 						const long long pix = m / p.N;
@@ -311,8 +366,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 							tma_load_4d(st + g * (KB * p.nb * 4), &tm_a, &full[s], gn[g], ih, iw, c0);
 						}
 					}
-					tma_load_4d(st + A_BYTES, &tm_b, &full[s], c0, jt * p.BN, tap, 0);
-					tma_load_4d(st + A_BYTES + b_bytes, &tm_b, &full[s], c0, jt * p.BN, tap, 1);
+					const int j0 = jt * p.BN + (int) rank * (p.BN / CTAS);   // this CTA's rows of B
+					tma_load_4d(st + A_BYTES, &tm_b, &full[s], c0, j0, tap, 0);
+					tma_load_4d(st + A_BYTES + b_bytes, &tm_b, &full[s], c0, j0, tap, 1);
 					if (++s == p.stages) { s = 0; ph ^= 1; }
 					// next k-block: taps inner, channel chunks outer
 					++tap;
@@ -321,12 +377,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 			}
 		}
 	} else if (warp == 1) {
-		// ===== MMA issuer (one elected thread) =====
-		if (elect_one()) {
-			const uint32_t idesc = make_idesc_tf32(p.BN);
+		// ===== MMA issuer (one elected thread; of a pair, the leader's) =====
+		if (rank == 0 && elect_one()) {
+			const uint32_t idesc = make_idesc_tf32(p.BN, TILE_M);
 			int s = 0; uint32_t ph = 0;
 			int acc = 0; uint32_t acc_ph = 0;
-			for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+			for (int tile = unit; tile < tiles; tile += units) {
 				mbar_wait(&acc_empty[acc], acc_ph ^ 1);
 				tc_fence_after();
 				const uint32_t d = tmem_base + (uint32_t) (acc * p.BN);
@@ -343,12 +399,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 						const uint32_t b = pass == 1 ? b_lo : b_hi;
 						#pragma unroll
 						for (int ks = 0; ks < KB / 8; ++ks)
-							umma_tf32_ts(d, a + 8 * ks, kmajor_desc<KB>(b, ks), idesc, (kb | pass | ks) != 0 ? 1u : 0u);
+							umma_tf32_ts<CTAS>(d, a + 8 * ks, kmajor_desc<KB>(b, ks), idesc, (kb | pass | ks) != 0 ? 1u : 0u);
 					}
-					umma_commit(&empty[s]);   // frees the smem stage and its TMEM columns once these MMAs have read them
+					umma_commit<CTAS>(&empty[s]);   // frees the smem stage and its TMEM columns once these MMAs have read them
 					if (++s == p.stages) { s = 0; ph ^= 1; }
 				}
-				umma_commit(&acc_full[acc]);  // accumulator complete -> epilogue
+				umma_commit<CTAS>(&acc_full[acc]);  // accumulator complete -> epilogue
 				if (++acc == p.nacc) { acc = 0; acc_ph ^= 1; }
 			}
 		}
@@ -381,7 +437,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 			}
 			asm volatile("bar.sync 1, 128;" ::: "memory");
 		};
-		for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+		for (int tile = unit; tile < tiles; tile += units) {
 			const int mt = tile % p.m_tiles, jt = tile / p.m_tiles;
 			if (jt != staged_jt) {
 				if (stats && staged_jt >= 0) flush_stats(staged_jt);
@@ -397,10 +453,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 			}
 			mbar_wait(&acc_full[acc], acc_ph);
 			tc_fence_after();
-			const long long m = (long long) mt * TC_BM + 32 * q + lane;
+			const long long m = (long long) mt * TILE_M + rank * TC_BM + 32 * q + lane;
 			const bool m_ok = m < p.M;
 			// M is a multiple of 32 (N % 32 == 0), so the 32 rows of a warp are valid or invalid together
-			const bool warp_ok = (long long) mt * TC_BM + 32 * q < p.M;
+			const bool warp_ok = (long long) mt * TILE_M + rank * TC_BM + 32 * q < p.M;
 			const long long gpix = m / p.N;
 			const int gi = (int) (gpix % p.OH), gj = (int) (gpix / p.OH);
 			const long long pix = (p.h0 + p.hs * gi) + (long long) p.oH * (p.w0 + p.ws * gj);  // pixel in the output tensor
@@ -485,7 +541,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 			}
 			tc_fence_before();
 			__syncwarp();
-			if (lane == 0) mbar_arrive(&acc_empty[acc]);
+			if (lane == 0) { if (CTAS == 2) mbar_arrive_cta(&acc_empty[acc], 0); else mbar_arrive(&acc_empty[acc]); }
 			if (++acc == p.nacc) { acc = 0; acc_ph ^= 1; }
 		}
 		if (stats && staged_jt >= 0) flush_stats(staged_jt);
@@ -499,7 +555,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 		const uint32_t row_off = (uint32_t) ((row / p.nb) * (KB * p.nb * 4) + (row % p.nb) * 4);
 		const uint32_t k_stride = (uint32_t) (p.nb * 4);
 		int s = 0; uint32_t ph = 0;
-		for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+		for (int tile = unit; tile < tiles; tile += units) {
 			for (int kb = 0; kb < kblocks; ++kb) {
 				mbar_wait(&full[s], ph);
 				const uint8_t* grp = smem + (size_t) s * stage_bytes + row_off;
@@ -518,14 +574,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 				}
 				tmem_st_wait();
 				tc_fence_before();
-				mbar_arrive(&ready[s]);
+				__syncwarp();
+				if (lane == 0) { if (CTAS == 2) mbar_arrive_cta(&ready[s], 0); else mbar_arrive(&ready[s]); }
 				if (++s == p.stages) { s = 0; ph ^= 1; }
 			}
 		}
 	}
 	tc_fence_before();
-	__syncthreads();
-	if (warp == 1) tmem_dealloc(tmem_base, 512u);
+	if (CTAS == 2) cluster_sync(); else __syncthreads();   // nothing of the pair is in flight towards this CTA any more
+	if (warp == 1) tmem_dealloc<CTAS>(tmem_base, 512u);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
@@ -564,6 +621,24 @@ static int encode_map(CUtensorMap* tm, const void* base, int rank, const cuuint6
 }
 
 static int round_up(int v, int m) { return (v + m - 1) / m * m; }
+// CATTL3_TC_PAIRS: bit 0 = CTA pairs in the gather GEMM, bit 1 = in the weight gradient (default: both)
+static int pair_mask() {
+	static const int mask = getenv("CATTL3_TC_PAIRS") ? atoi(getenv("CATTL3_TC_PAIRS")) : 3;
+	return mask;
+}
+
+// <<<grid, threads, smem, stream>>> with clusters of `ctas` consecutive CTAs (a CTA pair must be the two SMs of one TPC)
+template<typename... P, typename... A>
+static cudaError_t launch_clustered(void (*kern)(P...), int grid, int threads, size_t smem, cudaStream_t stream, int ctas, A... args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned) grid); cfg.blockDim = dim3((unsigned) threads);
+	cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = (unsigned) ctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr; cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kern, args...);
+}
 constexpr int TC_SMEM_LIMIT = 227 * 1024 - 2560;
 
 bool tc_gather_gemm_supported(const cattl3_ctx*, const GatherGeom& gg) {
@@ -602,16 +677,20 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 	// statistics (the longest epilogue) take 128-wide tiles, whose two accumulators let it hide behind the next
 	// tile's MMAs (profiles/README.md, r1e)
 	const bool want_stats_early = ep && ep->col_stats;
+	const long long M = (long long) gg.N * gg.OH * gg.OW;
+	// CTA pairs (cta_group::2, M = 256): whenever there are two 128-row tiles to pair and the filter tile splits into two
+	// halves of whole 8-row swizzle atoms with N % 32 == 0 (CATTL3_TC_1CTA=1 keeps single CTAs, for A/B measurements)
+	static const bool no_pairs = (pair_mask() & 1) == 0;
+	const int ctas = (!no_pairs && M > TC_BM && (gg.J >= 256 || round_up(gg.J, 16) % 32 == 0)) ? 2 : 1;
 	const int BN = gg.J >= 256 ? (want_stats_early ? 128 : 256) : round_up(gg.J, 16);
 	// 32-element k-blocks (128 B weight rows) where shared and tensor memory allow four stages of them
-	const int KB = (BN <= 128 && gg.SC > 16) ? 32 : 16;
+	const int KB = (BN / ctas <= 128 && gg.SC > 16) ? 32 : 16;
 	const int r_pad = round_up(gg.SC, KB);
 	// the A operand goes through registers into tensor memory, so its shared-memory image needs no MMA layout:
 	// take the longest contiguous run of batch entries TMA can deliver per row (up to 128 = 512 B)
 	const int nb = gg.N % 128 == 0 ? 128 : (gg.N % 64 == 0 ? 64 : 32);
 	const int j_tiles = (gg.J + BN - 1) / BN;
 	const int j_pad = j_tiles * BN;
-	const long long M = (long long) gg.N * gg.OH * gg.OW;
 	const long long w_elems = (long long) T * j_pad * r_pad;
 
 	CATTL3_CHECK(ensure_buffer(ctx, &ctx->tc_w, &ctx->tc_w_bytes, (size_t) w_elems * 8));
@@ -629,7 +708,7 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 	{
 		cuuint64_t dims[4] = { (cuuint64_t) r_pad, (cuuint64_t) j_pad, (cuuint64_t) T, 2 };
 		cuuint64_t str[3] = { (cuuint64_t) r_pad * 4, (cuuint64_t) r_pad * j_pad * 4, (cuuint64_t) w_elems * 4 };
-		cuuint32_t box[4] = { (cuuint32_t) KB, (cuuint32_t) BN, 1, 1 };
+		cuuint32_t box[4] = { (cuuint32_t) KB, (cuuint32_t) (BN / ctas), 1, 1 };
 		CATTL3_CHECK(encode_map(&tm_b, w_packed, 4, dims, str, box,
 				KB == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B));
 	}
@@ -642,12 +721,12 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 	p.oH = gg.out_H ? gg.out_H : gg.OH; p.oW = gg.out_H ? gg.out_W : gg.OW;
 	p.P = (long long) p.oH * p.oW;
 	p.out_cs = (long long) gg.N * p.P;
-	p.m_tiles = (int) ceil_div(M, TC_BM); p.j_tiles = j_tiles;
+	p.m_tiles = (int) ceil_div(M, TC_BM * ctas); p.j_tiles = j_tiles;
 	p.BN = BN; p.r_pad = r_pad; p.nb = nb;
 	// one accumulator of 256 columns leaves room for the A stages; narrower tiles double-buffer it so that the
 	// epilogue of one tile overlaps the MMAs of the next
 	p.nacc = 2 * BN + 4 * 2 * KB <= 512 ? 2 : 1;
-	const int stage_bytes = TC_BM * KB * 4 + 2 * BN * KB * 4;
+	const int stage_bytes = TC_BM * KB * 4 + 2 * (BN / ctas) * KB * 4;
 	const int stat_bytes = want_stats ? 4 * 2 * BN * 8 + 4 * 32 * 17 * 4 : 0;
 	int stages = (TC_SMEM_LIMIT - stat_bytes) / stage_bytes;
 	const int tmem_stages = (512 - p.nacc * BN) / (2 * KB);
@@ -659,7 +738,7 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 	size_t smem_bytes = (size_t) stages * stage_bytes + 1024 + 256 + 1024 + stat_bytes;  // alignment slack, barriers, bias, sums
 	if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
 	const int tiles = p.m_tiles * p.j_tiles;
-	const int grid = tiles < ctx->sm_count ? tiles : ctx->sm_count;
+	const int grid = ctas * (tiles < ctx->sm_count / ctas ? tiles : ctx->sm_count / ctas);
 	p.act_kind = want_act ? ep->act_kind : CATTL3_ACT_NONE;
 	p.act_param = want_act ? (float) ep->act_param : 0.f;
 	p.act_out = want_act ? (float*) ep->act_out : nullptr;
@@ -670,13 +749,11 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 		CATTL3_CUDA(cudaMemsetAsync(ctx->stat_ws, 0, bytes, ctx->stream));
 		p.stat_partial = (double*) ctx->stat_ws;
 	}
-	if (KB == 32) {
-		CATTL3_CUDA(cudaFuncSetAttribute(tc_gather_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-		tc_gather_gemm_kernel<32><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(tm_a, tm_b, p);
-	} else {
-		CATTL3_CUDA(cudaFuncSetAttribute(tc_gather_gemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-		tc_gather_gemm_kernel<16><<<grid, TC_THREADS, smem_bytes, ctx->stream>>>(tm_a, tm_b, p);
-	}
+	void (*kern)(const CUtensorMap, const CUtensorMap, const TcGemmParams) =
+			ctas == 2 ? (KB == 32 ? tc_gather_gemm_kernel<32, 2> : tc_gather_gemm_kernel<16, 2>)
+			: (KB == 32 ? tc_gather_gemm_kernel<32, 1> : tc_gather_gemm_kernel<16, 1>);
+	CATTL3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+	CATTL3_CUDA(launch_clustered(kern, grid, TC_THREADS, smem_bytes, ctx->stream, ctas, tm_a, tm_b, p));
 	CATTL3_LAUNCHED(ctx);
 	if (want_stats) {
 		colstats_reduce_tc_kernel<<<(unsigned) ceil_div(2 * gg.J, 256), 256, 0, ctx->stream>>>(p.stat_partial, grid, j_pad,
@@ -727,11 +804,12 @@ struct TcWgradParams {
 constexpr int WG_KB = 32;
 constexpr uint32_t WG_A_COL0 = 256;   // TMEM: accumulator in columns [0, 192], A stages from column 256
 constexpr int WG_RING = 4;             // k-blocks of dY in flight per converter warp (cp.async ring of 4 KB patches)
+template<int CTAS>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_b,
 		const TcWgradParams p) {
 	extern __shared__ __align__(1024) uint8_t smem_raw[];
 	uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
-	const int b_bytes = p.BNW * WG_KB * 4;
+	const int b_bytes = p.BNW / CTAS * WG_KB * 4;   // a CTA of a pair holds half of the accumulator's columns (= rows of B)
 	const int stage_bytes = 2 * b_bytes;   // [B raw][B lo]; the A operand has its own cp.async ring
 	uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t) p.stages * stage_bytes);
 	uint64_t* full = bars;
@@ -742,12 +820,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	// A unit = one CTA, or one pair working on 256 output channels (the leader on the first 128, its peer on the next)
+	// and each loading half of the unit's boxes.  p.j_tiles counts 128-row tiles (a multiple of CTAS).
+	const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
 	const int tiles = p.col_tiles * p.j_tiles;
-	const int tile = blockIdx.x % tiles, z = blockIdx.x / tiles;
-	const int ct = tile % p.col_tiles, jt = tile / p.col_tiles;  // CTAs sharing a dY tile are neighbours
-	const int box0 = ct * p.boxes_per_tile;
+	const int unit_tiles = tiles / CTAS;
+	const int unit = blockIdx.x / CTAS;
+	const int utile = unit % unit_tiles, z = unit / unit_tiles;
+	const int ct = utile % p.col_tiles, jt = (utile / p.col_tiles) * CTAS + (int) rank;  // units sharing a dY tile are neighbours
+	const int tile = ct + p.col_tiles * jt;
+	const int my_boxes = p.boxes_per_tile / CTAS;
+	const int box0 = ct * p.boxes_per_tile + (int) rank * my_boxes;
 	int nboxes = p.boxes - box0;
-	if (nboxes > p.boxes_per_tile) nboxes = p.boxes_per_tile;
+	if (nboxes > my_boxes) nboxes = my_boxes;
+	if (nboxes < 0) nboxes = 0;
 	const long long mg0 = (long long) z * p.mg_per_split;
 	long long mg1 = mg0 + p.mg_per_split;
 	if (mg1 > p.mgroups) mg1 = p.mgroups;
@@ -756,13 +842,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 
 	if (warp == 0 && elect_one()) {
 		tma_prefetch_desc(&tm_b);
-		for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
-		mbar_init(&acc_full[0], 1); mbar_init(&acc_empty[0], 4);
+		for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 4 * CTAS); mbar_init(&empty[s], 1); }
+		mbar_init(&acc_full[0], 1); mbar_init(&acc_empty[0], 4 * CTAS);
 		fence_barrier_init();
 	}
-	if (warp == 1) tmem_alloc(tmem_slot, 512u);
+	if (warp == 1) tmem_alloc<CTAS>(tmem_slot, 512u);
 	tc_fence_before();
-	__syncthreads();
+	if (CTAS == 2) cluster_sync(); else __syncthreads();
 	tc_fence_after();
 	const uint32_t tmem_base = *tmem_slot;
 
@@ -777,7 +863,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 				const int oh = (int) (pix % p.OH), ow = (int) (pix / p.OH);
 				mbar_wait(&empty[s], ph ^ 1);
 				uint8_t* st = smem + (size_t) s * stage_bytes;
-				mbar_expect_tx(&full[s], tx);
+				if (tx) mbar_expect_tx(&full[s], tx); else mbar_arrive(&full[s]);
 				for (int bx = 0; bx < nboxes; ++bx) {
 					const int box = box0 + bx;
 					const int tap = box / p.rchunks, c0 = (box % p.rchunks) * p.RB;
@@ -789,8 +875,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 			}
 		}
 	} else if (warp == 1) {
-		if (elect_one()) {
-			const uint32_t idesc = make_idesc_tf32(p.BNW);
+		if (rank == 0 && elect_one()) {
+			const uint32_t idesc = make_idesc_tf32(p.BNW, TC_BM * CTAS);
 			int s = 0; uint32_t ph = 0;
 			uint32_t acc_ph = 0;
 			long long kb = 0;
@@ -812,13 +898,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 						const uint32_t b = pass == 1 ? b_lo : b_hi;
 						#pragma unroll
 						for (int ks = 0; ks < WG_KB / 8; ++ks)
-							umma_tf32_ts(d, a + 8 * ks, kmajor_desc<WG_KB>(b, ks), idesc, (first && pass == 0 && ks == 0) ? 0u : 1u);
+							umma_tf32_ts<CTAS>(d, a + 8 * ks, kmajor_desc<WG_KB>(b, ks), idesc, (first && pass == 0 && ks == 0) ? 0u : 1u);
 					}
 					first = false;
-					umma_commit(&empty[s]);
+					umma_commit<CTAS>(&empty[s]);
 					if (++s == p.stages) { s = 0; ph ^= 1; }
 				}
-				umma_commit(&acc_full[0]);
+				umma_commit<CTAS>(&acc_full[0]);
 				acc_ph ^= 1;
 			}
 		}
@@ -847,7 +933,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 			}
 			tc_fence_before();
 			__syncwarp();
-			if (lane == 0) mbar_arrive(&acc_empty[0]);
+			if (lane == 0) { if (CTAS == 2) mbar_arrive_cta(&acc_empty[0], 0); else mbar_arrive(&acc_empty[0]); }
 			acc_ph ^= 1;
 		}
 	} else {
@@ -927,28 +1013,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 				tmem_st_16(taddr + WG_KB + 16 * h, lo);
 			}
 			{
-				const float4* src = reinterpret_cast<const float4*>(st);
-				float4* dst = reinterpret_cast<float4*>(st + b_bytes);
-				#pragma unroll 4
-				for (int i = tid; i < (b_bytes >> 4); i += 128) {
-					float4 v = src[i];
-					v.x = __uint_as_float(tf32_lo_bits(v.x)); v.y = __uint_as_float(tf32_lo_bits(v.y));
-					v.z = __uint_as_float(tf32_lo_bits(v.z)); v.w = __uint_as_float(tf32_lo_bits(v.w));
-					dst[i] = v;
+				// lo tile of B: 16-byte vectors, this thread's are 2 KB apart; all loads of a batch are issued before the first
+				// is used (one shared-memory latency per batch of six instead of one per vector)
+				const uint32_t src = smem_u32(st) + (uint32_t) tid * 16u;
+				const int vecs = b_bytes >> 11;   // vectors per thread: b_bytes / (128 threads * 16 B); b_bytes is a multiple of 2 KB
+				for (int v0 = 0; v0 < vecs; v0 += 6) {
+					float4 v[6];
+					#pragma unroll
+					for (int u = 0; u < 6; ++u)
+						if (v0 + u < vecs) v[u] = lds_128(src + (uint32_t) (v0 + u) * 2048u);
+					#pragma unroll
+					for (int u = 0; u < 6; ++u) {
+						if (v0 + u < vecs) {
+							float4 t = v[u];
+							t.x = __uint_as_float(tf32_lo_bits(t.x)); t.y = __uint_as_float(tf32_lo_bits(t.y));
+							t.z = __uint_as_float(tf32_lo_bits(t.z)); t.w = __uint_as_float(tf32_lo_bits(t.w));
+							sts_128(src + (uint32_t) b_bytes + (uint32_t) (v0 + u) * 2048u, t);
+						}
+					}
 				}
 			}
 			db_sum += blk_sum;
-			fence_proxy_async();  // the lo tile was written through the generic proxy; the MMA reads it through the async proxy
+			// the lo tile was written through the generic proxy; the MMA (of either CTA of a pair) reads it through the async proxy
+			// (.shared::cta: the unqualified fence compiles to MEMBAR.ALL.GPU and took 47 % of the converters' time)
+			fence_proxy_async();
 			tmem_st_wait();
 			tc_fence_before();
-			mbar_arrive(&ready[s]);
+			__syncwarp();
+			if (lane == 0) { if (CTAS == 2) mbar_arrive_cta(&ready[s], 0); else mbar_arrive(&ready[s]); }
 			if (++s == p.stages) { s = 0; ph ^= 1; }
 		}
 		if (want_db) p.db_partial[(long long) z * p.j_tiles * TC_BM + jt * TC_BM + row] = db_sum;
 	}
 	tc_fence_before();
-	__syncthreads();
-	if (warp == 1) tmem_dealloc(tmem_base, 512u);
+	if (CTAS == 2) cluster_sync(); else __syncthreads();
+	if (warp == 1) tmem_dealloc<CTAS>(tmem_base, 512u);
 }
 
 // dw(tap, r, j) += sum over splits of the scratch tiles; db(j) += sum over splits of the column sums.  Small layers
@@ -1014,8 +1113,13 @@ int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const 
 	CATTL3_REQUIRE(aligned16(src) && aligned16(plain), "tcgen05 path needs 16-byte aligned tensors");
 	const int T = gg.RH * gg.RW;
 	const int r_pad = round_up(gg.SC, 16);
-	const int RB = r_pad % 64 == 0 ? 64 : (r_pad % 32 == 0 ? 32 : 16);
 	const long long M = (long long) gg.N * gg.OH * gg.OW;
+	// CTA pairs (cta_group::2): 256 output channels per unit, each CTA loading and splitting half of the gathered tile --
+	// half the shared-memory traffic per MMA.  Needs a second 128-row tile of output channels to pair with.
+	static const bool no_pairs = (pair_mask() & 2) == 0;
+	const int ctas = (!no_pairs && gg.J > TC_BM) ? 2 : 1;
+	// boxes of 32 channel rows for a pair (a tile of 192 columns = 6 boxes, 3 per CTA)
+	const int RB = (ctas == 1 && r_pad % 64 == 0) ? 64 : (r_pad % 32 == 0 ? 32 : 16);
 
 	CUtensorMap tm_b;
 	{
@@ -1032,9 +1136,11 @@ int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const 
 	const int max_boxes = 192 / RB;
 	p.col_tiles = (p.boxes + max_boxes - 1) / max_boxes;
 	p.boxes_per_tile = (p.boxes + p.col_tiles - 1) / p.col_tiles;  // balanced: 9 boxes of 64 -> 3 tiles of 192 columns
+	if (ctas == 2 && p.boxes_per_tile % 2) ++p.boxes_per_tile;     // each CTA of a pair takes half of a tile's boxes
 	p.col_tiles = (p.boxes + p.boxes_per_tile - 1) / p.boxes_per_tile;
 	p.BNW = p.boxes_per_tile * RB;
-	p.j_tiles = (gg.J + TC_BM - 1) / TC_BM;
+	if (ctas == 2 && p.BNW % 32) { set_error("wgrad: pair tile of %d columns", p.BNW); return CATTL3_ERR_UNSUPPORTED; }
+	p.j_tiles = round_up((gg.J + TC_BM - 1) / TC_BM, ctas);   // 128-row tiles, whole pairs
 	p.mgroups = M / WG_KB;
 	const int tiles = p.col_tiles * p.j_tiles;
 	long long splits = ctx->sm_count / tiles;
@@ -1043,7 +1149,7 @@ int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const 
 	p.mg_per_split = ceil_div(p.mgroups, splits);
 	p.splits = (int) ceil_div(p.mgroups, p.mg_per_split);
 	const int ring_bytes = 4 * WG_RING * 4096;   // the converters' dY rings
-	const int stage_bytes = 2 * p.BNW * WG_KB * 4;
+	const int stage_bytes = 2 * (p.BNW / ctas) * WG_KB * 4;
 	int stages = (TC_SMEM_LIMIT - ring_bytes) / stage_bytes;
 	const int tmem_stages = (512 - (int) WG_A_COL0) / (2 * WG_KB);
 	if (stages > tmem_stages) stages = tmem_stages;
@@ -1058,8 +1164,9 @@ int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const 
 	p.plain = plain; p.M = M;
 	size_t smem_bytes = (size_t) stages * stage_bytes + 1024 + 512 + ring_bytes;
 	if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
-	CATTL3_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-	tc_wgrad_kernel<<<tiles * p.splits, TC_THREADS, smem_bytes, ctx->stream>>>(tm_b, p);
+	void (*kern)(const CUtensorMap, const TcWgradParams) = ctas == 2 ? tc_wgrad_kernel<2> : tc_wgrad_kernel<1>;
+	CATTL3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+	CATTL3_CUDA(launch_clustered(kern, tiles * p.splits, TC_THREADS, smem_bytes, ctx->stream, ctas, tm_b, p));
 	CATTL3_LAUNCHED(ctx);
 	wgrad_reduce_tc_kernel<<<ew_grid(ctx, ceil_div(p.dw_elems + (db ? gg.J : 0), 32), 1), 32 * WR_ZL, 0, ctx->stream>>>(p, T, dw, db);
 	CATTL3_LAUNCHED(ctx);

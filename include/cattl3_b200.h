@@ -294,9 +294,17 @@ int cattl3_dense_forward_fused_f64(cattl3_ctx*, int32_t n, int32_t in, int32_t o
 
 /* Host-buffer forms of the convolution layer: what the reference's Layer API hands over
  * (pass_forward(Data in, bool) / pass_back(Data out_grad), Layer.hpp:126,137) -- host tensors in,
- * host tensors out, host<->device copies inside the call.  Parameters stay device resident. */
+ * host tensors out, host<->device copies inside the call.  Parameters stay device resident.
+ * The copies are pipelined with the kernels over chunks of filters on an upload and a download stream (PCIe in both
+ * directions at once).  The plain forms return with the host tensors complete (the reference's semantics); the
+ * _async forms return once the work is enqueued and cattl3_host_wait() completes every outstanding transfer, so a
+ * forward's download of y overlaps the following backward's upload of dY.  Host tensors should be pinned
+ * (cattl3_host_alloc).  x_dev_keep (optional) receives the device copy of x for the backward call. */
 int cattl3_conv_forward_host_f32(cattl3_ctx*, const cattl3_conv_geom*, const float* x_host, const float* w_dev, const float* b_dev, float* y_host, float* x_dev_keep);
 int cattl3_conv_backward_host_f32(cattl3_ctx*, const cattl3_conv_geom*, const float* x_dev, const float* w_dev, const float* dy_host, float* dw_dev, float* db_dev, float* dx_host);
+int cattl3_conv_forward_host_async_f32(cattl3_ctx*, const cattl3_conv_geom*, const float* x_host, const float* w_dev, const float* b_dev, float* y_host, float* x_dev_keep);
+int cattl3_conv_backward_host_async_f32(cattl3_ctx*, const cattl3_conv_geom*, const float* x_dev, const float* w_dev, const float* dy_host, float* dw_dev, float* db_dev, float* dx_host);
+int cattl3_host_wait(cattl3_ctx*);
 
 /* ---- activation layers -------------------------------------------------------------------- */
 /* x, y: rows x vol elements, rows (= batch) fastest.  Softmax normalises each row over `vol`. */

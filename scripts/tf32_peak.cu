@@ -6,13 +6,14 @@
 //   2sm_ss : cta_group::2, M = 256 (128 rows per CTA of the pair), N = 256 (128 rows of B per CTA)
 //   2sm_ts : cta_group::2, A from each CTA's tensor memory
 // One elected thread per CTA (per pair) issues `iters` k-blocks of four MMAs on one resident tile and commits once;
-// one CTA per SM, all SMs.  burst = best of 7 launches of ~1 ms, sustained = 1.5 s of back-to-back launches (the
-// power cap pulls the SM clock down under a continuous tensor load).  Prints one JSON line.
+// one CTA per SM, all SMs.  burst = best of 7 launches of ~1 ms after 3 s of idling, sustained = 1.5 s of back-to-back
+// launches (the power cap pulls the SM clock down under a continuous tensor load).  Prints one JSON line.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <unistd.h>
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr) {   // K-major, 128 B rows, SWIZZLE_128B, 8-row atoms 1024 B apart
@@ -190,7 +191,8 @@ int main(int argc, char** argv) {
 		}
 		printf(", \"%s\": {\"launch_rc\": %d, \"sync\": \"%s\", \"verify_max_abs_err\": %g", md.name, rc, cudaGetErrorString(e), maxerr);
 		if (rc != 0 || e != cudaSuccess) { printf("}"); continue; }
-		// ---- timing on uniform(-1, 1) data
+		// ---- timing on uniform(-1, 1) data; every mode starts from an idle, cooled-down device
+		sleep(3);
 		const int grid = sms / md.ctas * md.ctas;
 		const int iters = 4000;   // x 4 MMAs of 128 x 256 x 8 per SM: about 1 ms
 		md.fn(grid, N, iters, 0, nullptr);

@@ -342,6 +342,46 @@ def test_config2_full_size_vs_unmodified_reference(U, ref, dt, n):
         assert e < C.TOL[np.dtype(dt)], (k, e)
 
 
+@pytest.mark.parametrize("chunks", ["1", "4"])
+def test_conv_host_entry_points_vs_oracle(U, orc, chunks, monkeypatch):
+    """cattl3_conv_forward_host_f32 / cattl3_conv_backward_host_f32 (+ the _async forms and cattl3_host_wait): host
+    tensors in and out, the copies pipelined with the kernels over chunks of filters on three streams, against the
+    oracle's ConvKernelLayer (ConvKernelLayer.hpp:115-189).  Two steps back to back: the second forward reuses the
+    staging buffers while the first step's downloads are still running; gradients accumulate across the two calls."""
+    import torch
+    case = (32, 9, 8, 16, 256, 3, 3, 1, 1, 1, 1, 0, 0)
+    g, x, w, b, dy = C.conv_inputs(case, np.float32, 77, False)
+    x2 = np.asfortranarray(x[::-1].copy())
+    r1 = orc.conv(g, x, w, b, dy, back_reps=1)
+    r2 = orc.conv(g, x2, w, b, dy, back_reps=1)
+    c = U.ctx()
+    cg = U.pkg.ConvGeom(*case)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a.ravel(order="F"))).pin_memory()
+    xh, x2h, dyh = pin(x), pin(x2), pin(dy)
+    yh = [torch.empty(dy.size).pin_memory() for _ in range(2)]
+    dxh = [torch.empty(x.size).pin_memory() for _ in range(2)]
+    wd, bd = U.dev(w), U.dev(b)
+    dwd, dbd = U.zeros(w.shape, np.float32), U.zeros(b.shape, np.float32)
+    xkeep = U.zeros(x.shape, np.float32)
+    monkeypatch.setenv("CATTL3_HOST_CHUNKS", chunks)
+    torch.cuda.synchronize()
+    c.conv_forward_host_async(cg, xh, wd, bd, yh[0], xkeep)
+    c.conv_backward_host_async(cg, xkeep, wd, dyh, dwd, dbd, dxh[0])
+    c.conv_forward_host_async(cg, x2h, wd, bd, yh[1], xkeep)
+    c.conv_backward_host_async(cg, xkeep, wd, dyh, dwd, dbd, dxh[1])
+    c.host_wait()
+    tol = C.TOL[np.dtype(np.float32)]
+    for i, r in enumerate((r1, r2)):
+        assert C.relerr(yh[i].numpy().reshape(dy.shape, order="F"), r["y"]) < tol, ("y", i)
+        assert C.relerr(dxh[i].numpy().reshape(x.shape, order="F"), r["dx"]) < tol, ("dx", i)
+    assert C.relerr(U.host(dwd, w.shape), r1["dw"] + r2["dw"]) < tol
+    assert C.relerr(U.host(dbd, b.shape), r1["db"] + r2["db"]) < tol
+    # the synchronous forms: complete on return
+    y3 = torch.empty(dy.size).pin_memory()
+    c.conv_forward_host(cg, xh, wd, bd, y3, None)
+    assert C.relerr(y3.numpy().reshape(dy.shape, order="F"), r1["y"]) < tol
+
+
 @pytest.mark.parametrize("dt", DTYPES)
 def test_loss_kernels_vs_numpy(U, dt):
     """SquaredLoss / CrossEntropyLoss on the device (loss/SquaredLoss.hpp:25-34, CrossEntropyLoss.hpp:33-42):
