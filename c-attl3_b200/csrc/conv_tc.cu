@@ -290,8 +290,12 @@ struct TcGemmParams {
 // The reduction walks channel chunks OUTER and taps INNER: the 148 CTAs then work on the same few channels
 // of neighbouring pixels at the same time, so every source byte is fetched from HBM once and the tap-shifted
 // re-reads hit L2.
-template<int KB, int CTAS>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tm_a,
+// Warps: 0 = TMA producer, 1 = MMA issuer, then NEPI epilogue warps, then NCONV converter warps (4 or 8 each: a warp
+// reaches the TMEM lane quarter warp % 4 only, so eight warps are two per quarter -- epilogue warps then split the
+// tile's columns, converter warps alternate k-blocks).  Short k-blocks (few filters: the input gradient) need the
+// second converter set, wide tiles the second epilogue set.
+template<int KB, int CTAS, int NEPI, int NCONV>
+__global__ void __launch_bounds__((2 + NEPI + NCONV) * 32, 1) tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap tm_a,
 		const __grid_constant__ CUtensorMap tm_b, const TcGemmParams p) {
 	extern __shared__ __align__(1024) uint8_t smem_raw[];
 	uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
@@ -306,8 +310,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 	uint64_t* acc_empty = acc_full + 2;
 	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 	float* sbias = reinterpret_cast<float*>(bars + 32);  // 256 floats behind the barriers
-	double* sstat = reinterpret_cast<double*>(sbias + 256);  // [4 warps][2][BN] column sums (only with stat_partial)
-	float* spatch = reinterpret_cast<float*>(sstat + 8 * p.BN);  // [4 warps][32][17] transpose patches (likewise)
+	double* sstat = reinterpret_cast<double*>(sbias + 256);  // [4 quarters][2][BN] column sums (only with stat_partial)
+	float* spatch = reinterpret_cast<float*>(sstat + 8 * p.BN);  // [NEPI warps][32][17] transpose patches (likewise)
+	constexpr int EPI_THREADS = NEPI * 32;
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int T = p.RH * p.RW;
@@ -323,7 +328,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 		// full: this CTA's TMA bytes; ready: one arrival per converter warp of the pair (in the leader); empty / acc_full:
 		// the leader's commit, multicast; acc_empty: one arrival per epilogue warp of the pair (in the leader)
 		for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&ready[s], 4 * CTAS); mbar_init(&empty[s], 1); }
-		for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4 * CTAS); }
+		for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], NEPI * CTAS); }
 		fence_barrier_init();
 	}
 	if (warp == 1) tmem_alloc<CTAS>(tmem_slot, 512u);
@@ -408,26 +413,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 				if (++acc == p.nacc) { acc = 0; acc_ph ^= 1; }
 			}
 		}
-	} else if (warp < 6) {
-		// ===== epilogue warps 2..5: TMEM -> registers -> (+bias, activation, column statistics) -> coalesced stores =====
+	} else if (warp < 2 + NEPI) {
+		// ===== epilogue warps: TMEM -> registers -> (+bias, activation, column statistics) -> coalesced stores =====
 		// The per-filter bias of the tile is staged in shared memory while the MMAs of the tile still run,
 		// so the drain itself is tcgen05.ld + add + store with no dependent global loads.
 		const int q = warp & 3;  // TMEM lane quarter this warp may access
-		const int et = threadIdx.x - 64;  // 0..127 among the epilogue threads
+		const int et = threadIdx.x - 64;  // index among the epilogue threads
+		const int ew = warp - 2;          // index among the epilogue warps
+		// two warps per lane quarter split the tile's columns (BN % 32 == 0 then)
+		const int c_begin = (ew >> 2) * (p.BN / (NEPI / 4)), c_end = c_begin + p.BN / (NEPI / 4);
 		int acc = 0; uint32_t acc_ph = 0;
 		int staged_jt = -1;
 		const bool stats = p.stat_partial != nullptr;
+		// c_end - c_begin is a multiple of 32 whenever the tile is (every pair tile is)
+		const bool fast = !stats && p.bias_mode == 1 && p.out != nullptr && p.act_out == nullptr && (c_end - c_begin) % 32 == 0;
 		const int j_pad = p.j_tiles * p.BN;
 		double* my_stat = sstat + q * 2 * p.BN;
 		if (stats) {
-			for (int c = et; c < 8 * p.BN; c += 128) sstat[c] = 0.0;
-			asm volatile("bar.sync 1, 128;" ::: "memory");
+			for (int c = et; c < 8 * p.BN; c += EPI_THREADS) sstat[c] = 0.0;
+			asm volatile("bar.sync 1, %0;" :: "n"(EPI_THREADS) : "memory");
 		}
 		// Column sums of this CTA's tiles of filter tile `jt` -> its slot of the partial buffer (plain stores:
 		// the tile order of a CTA visits every jt at most once, in increasing order).
 		auto flush_stats = [&](int jt) {
-			asm volatile("bar.sync 1, 128;" ::: "memory");
-			for (int c = et; c < 2 * p.BN; c += 128) {
+			asm volatile("bar.sync 1, %0;" :: "n"(EPI_THREADS) : "memory");
+			for (int c = et; c < 2 * p.BN; c += EPI_THREADS) {
 				const int k = c / p.BN, col = c % p.BN;
 				const double t = ((sstat[(0 * 2 + k) * p.BN + col] + sstat[(1 * 2 + k) * p.BN + col]) +
 						sstat[(2 * 2 + k) * p.BN + col]) + sstat[(3 * 2 + k) * p.BN + col];
@@ -435,19 +445,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 				sstat[(0 * 2 + k) * p.BN + col] = 0.0; sstat[(1 * 2 + k) * p.BN + col] = 0.0;
 				sstat[(2 * 2 + k) * p.BN + col] = 0.0; sstat[(3 * 2 + k) * p.BN + col] = 0.0;
 			}
-			asm volatile("bar.sync 1, 128;" ::: "memory");
+			asm volatile("bar.sync 1, %0;" :: "n"(EPI_THREADS) : "memory");
 		};
 		for (int tile = unit; tile < tiles; tile += units) {
 			const int mt = tile % p.m_tiles, jt = tile / p.m_tiles;
 			if (jt != staged_jt) {
 				if (stats && staged_jt >= 0) flush_stats(staged_jt);
 				if (p.bias_mode == 1) {
-					asm volatile("bar.sync 1, 128;" ::: "memory");  // nobody still reads the previous tile's bias
-					for (int c = et; c < p.BN; c += 128) {
+					asm volatile("bar.sync 1, %0;" :: "n"(EPI_THREADS) : "memory");  // nobody still reads the previous tile's bias
+					for (int c = et; c < p.BN; c += EPI_THREADS) {
 						const int j = jt * p.BN + c;
 						sbias[c] = j < p.J ? __ldg(p.bias + j) : 0.f;
 					}
-					asm volatile("bar.sync 1, 128;" ::: "memory");
+					asm volatile("bar.sync 1, %0;" :: "n"(EPI_THREADS) : "memory");
 				}
 				staged_jt = jt;
 			}
@@ -465,7 +475,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 			float* out_m = p.out ? p.out + out_off : nullptr;
 			float* act_m = p.act_out ? p.act_out + out_off : nullptr;
 			const int jn = p.J - jt * p.BN < p.BN ? p.J - jt * p.BN : p.BN;  // valid columns of this tile
-			for (int c0 = 0; c0 < p.BN; c0 += 16) {
+			if (fast && m_ok && jn == p.BN) {
+				// the plain layer (per-filter bias, nothing fused, whole tile): two 16-column loads in flight, the stores of
+				// one overlapping the tensor-memory latency of the next
+				float va[16], vb[16];
+				tmem_ld_16(taddr + c_begin, va);
+				for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+					tmem_ld_wait();
+					tmem_ld_16(taddr + c0 + 16, vb);
+					#pragma unroll
+					for (int i = 0; i < 16; ++i) out_m[p.out_cs * (long long) (c0 + i)] = va[i] + sbias[c0 + i];
+					tmem_ld_wait();
+					if (c0 + 32 < c_end) tmem_ld_16(taddr + c0 + 32, va);
+					#pragma unroll
+					for (int i = 0; i < 16; ++i) out_m[p.out_cs * (long long) (c0 + 16 + i)] = vb[i] + sbias[c0 + 16 + i];
+				}
+			} else
+			for (int c0 = c_begin; c0 < c_end; c0 += 16) {
 				float v[16], bv[16];
 				tmem_ld_16(taddr + c0, v);
 				if (p.bias_mode == 1) {
@@ -489,7 +515,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 					// lane L then owns column L % 16 over rows 16 * (L / 16) ..., sums d = value - first value and
 					// d^2 in fp32 (magnitudes ~ sigma), re-bases to shift 0 in double, and the two half-columns
 					// meet in lanes 0..15, which accumulate in double.
-					float* patch = spatch + q * (32 * 17);
+					float* patch = spatch + ew * (32 * 17);
 					#pragma unroll
 					for (int i = 0; i < 16; ++i) patch[lane * 17 + i] = v[i];
 					__syncwarp();
@@ -551,12 +577,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gather_gemm_kernel(const __g
 		// tile is entry m % nb of box m / nb.  Lane = row within the quarter, so a warp reads 32 consecutive
 		// floats per k (conflict free) and owns TMEM lanes 32q .. 32q+31.
 		const int q = warp & 3;
+		const int cset = (warp - 2 - NEPI) >> 2;   // with eight converter warps, set 0 takes the even k-blocks, set 1 the odd ones
 		const int row = 32 * q + lane;
 		const uint32_t row_off = (uint32_t) ((row / p.nb) * (KB * p.nb * 4) + (row % p.nb) * 4);
 		const uint32_t k_stride = (uint32_t) (p.nb * 4);
 		int s = 0; uint32_t ph = 0;
+		int turn = 0;
 		for (int tile = unit; tile < tiles; tile += units) {
 			for (int kb = 0; kb < kblocks; ++kb) {
+				if (NCONV == 8 && (turn ^= 1) == cset) {   // the other set's k-block
+					if (++s == p.stages) { s = 0; ph ^= 1; }
+					continue;
+				}
 				mbar_wait(&full[s], ph);
 				const uint8_t* grp = smem + (size_t) s * stage_bytes + row_off;
 				const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16) + a_col0 + (uint32_t) (s * 2 * KB);
@@ -727,7 +759,13 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 	// epilogue of one tile overlaps the MMAs of the next
 	p.nacc = 2 * BN + 4 * 2 * KB <= 512 ? 2 : 1;
 	const int stage_bytes = TC_BM * KB * 4 + 2 * (BN / ctas) * KB * 4;
-	const int stat_bytes = want_stats ? 4 * 2 * BN * 8 + 4 * 32 * 17 * 4 : 0;
+	// converter / epilogue warp sets: a k-block's MMAs take 3 * (KB / 8) * BN / 2 clocks per SM; below ~800 the four
+	// converter warps (~350 clocks per k-block each) cannot keep up, so a second set alternates with them; otherwise the
+	// second set of four goes to the epilogue of wide tiles (one accumulator: the drain is exposed)
+	const bool short_kblocks = 3 * (KB / 8) * BN / 2 < 800;
+	const int nconv = short_kblocks ? 8 : 4;
+	const int nepi = (!short_kblocks && BN % 32 == 0 && BN >= 128) ? 8 : 4;
+	const int stat_bytes = want_stats ? 4 * 2 * BN * 8 + nepi * 32 * 17 * 4 : 0;
 	int stages = (TC_SMEM_LIMIT - stat_bytes) / stage_bytes;
 	const int tmem_stages = (512 - p.nacc * BN) / (2 * KB);
 	if (stages > tmem_stages) stages = tmem_stages;
@@ -749,11 +787,19 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 		CATTL3_CUDA(cudaMemsetAsync(ctx->stat_ws, 0, bytes, ctx->stream));
 		p.stat_partial = (double*) ctx->stat_ws;
 	}
-	void (*kern)(const CUtensorMap, const CUtensorMap, const TcGemmParams) =
-			ctas == 2 ? (KB == 32 ? tc_gather_gemm_kernel<32, 2> : tc_gather_gemm_kernel<16, 2>)
-			: (KB == 32 ? tc_gather_gemm_kernel<32, 1> : tc_gather_gemm_kernel<16, 1>);
+	typedef void (*GemmKernel)(const CUtensorMap, const CUtensorMap, const TcGemmParams);
+	GemmKernel kern;
+	if (nconv == 8)
+		kern = ctas == 2 ? (KB == 32 ? (GemmKernel) tc_gather_gemm_kernel<32, 2, 4, 8> : tc_gather_gemm_kernel<16, 2, 4, 8>)
+				: (KB == 32 ? (GemmKernel) tc_gather_gemm_kernel<32, 1, 4, 8> : tc_gather_gemm_kernel<16, 1, 4, 8>);
+	else if (nepi == 8)
+		kern = ctas == 2 ? (KB == 32 ? (GemmKernel) tc_gather_gemm_kernel<32, 2, 8, 4> : tc_gather_gemm_kernel<16, 2, 8, 4>)
+				: (KB == 32 ? (GemmKernel) tc_gather_gemm_kernel<32, 1, 8, 4> : tc_gather_gemm_kernel<16, 1, 8, 4>);
+	else
+		kern = ctas == 2 ? (KB == 32 ? (GemmKernel) tc_gather_gemm_kernel<32, 2, 4, 4> : tc_gather_gemm_kernel<16, 2, 4, 4>)
+				: (KB == 32 ? (GemmKernel) tc_gather_gemm_kernel<32, 1, 4, 4> : tc_gather_gemm_kernel<16, 1, 4, 4>);
 	CATTL3_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-	CATTL3_CUDA(launch_clustered(kern, grid, TC_THREADS, smem_bytes, ctx->stream, ctas, tm_a, tm_b, p));
+	CATTL3_CUDA(launch_clustered(kern, grid, (2 + nepi + nconv) * 32, smem_bytes, ctx->stream, ctas, tm_a, tm_b, p));
 	CATTL3_LAUNCHED(ctx);
 	if (want_stats) {
 		colstats_reduce_tc_kernel<<<(unsigned) ceil_div(2 * gg.J, 256), 256, 0, ctx->stream>>>(p.stat_partial, grid, j_pad,
@@ -854,24 +900,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 
 	if (warp == 0) {
 		if (elect_one()) {
+			// One thread feeds the whole pipeline, so its loop is kept to a handful of instructions per box: the boxes'
+			// tap offsets and channel origins are tabulated once, and the k-block's (n0, oh, ow) advances incrementally
+			// (the 64-bit divisions this loop used to do per k-block made it as slow as the MMAs it feeds).
 			int s = 0; uint32_t ph = 0;
 			const uint32_t tx = (uint32_t) (nboxes * p.RB * WG_KB * 4);
+			int* box_tab = reinterpret_cast<int*>(bars + 40);   // [12][3]: dh, dw, c0 (behind the barriers and the TMEM slot)
+			for (int bx = 0; bx < nboxes; ++bx) {
+				const int box = box0 + bx;
+				const int tap = box / p.rchunks;
+				const int rh = tap % p.RH, rw = tap / p.RH;
+				box_tab[3 * bx + 0] = rh * p.bh + p.ch;
+				box_tab[3 * bx + 1] = rw * p.bw + p.cw;
+				box_tab[3 * bx + 2] = (box % p.rchunks) * p.RB;
+			}
+			const long long m_first = mg0 * WG_KB;
+			int n0 = (int) (m_first % p.N);
+			const long long pix0 = m_first / p.N;
+			int oh = (int) (pix0 % p.OH), ow = (int) (pix0 / p.OH);
+			const uint32_t box_bytes = (uint32_t) (p.RB * WG_KB * 4);
 			for (long long kb = 0; kb < kblocks; ++kb) {
-				const long long m = (mg0 + kb) * WG_KB;
-				const int n0 = (int) (m % p.N);
-				const long long pix = m / p.N;
-				const int oh = (int) (pix % p.OH), ow = (int) (pix / p.OH);
 				mbar_wait(&empty[s], ph ^ 1);
 				uint8_t* st = smem + (size_t) s * stage_bytes;
 				if (tx) mbar_expect_tx(&full[s], tx); else mbar_arrive(&full[s]);
-				for (int bx = 0; bx < nboxes; ++bx) {
-					const int box = box0 + bx;
-					const int tap = box / p.rchunks, c0 = (box % p.rchunks) * p.RB;
-					const int rh = tap % p.RH, rw = tap / p.RH;
-					const int ih = oh * p.ah + rh * p.bh + p.ch, iw = ow * p.aw + rw * p.bw + p.cw;
-					tma_load_4d(st + bx * p.RB * (WG_KB * 4), &tm_b, &full[s], n0, ih, iw, c0);
-				}
+				const int ih0 = oh * p.ah, iw0 = ow * p.aw;
+				for (int bx = 0; bx < nboxes; ++bx)
+					tma_load_4d(st + bx * box_bytes, &tm_b, &full[s], n0, ih0 + box_tab[3 * bx], iw0 + box_tab[3 * bx + 1], box_tab[3 * bx + 2]);
 				if (++s == p.stages) { s = 0; ph ^= 1; }
+				n0 += WG_KB;
+				if (n0 >= p.N) { n0 = 0; if (++oh == p.OH) { oh = 0; ++ow; } }
 			}
 		}
 	} else if (warp == 1) {
