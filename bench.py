@@ -90,7 +90,7 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def reference_sample(n_sample, reps):
+def reference_sample(n_sample, reps, keep=None):
     """Times the unmodified reference (or, if its shim is absent, the C restatement) on config 2 at
     batch n_sample: returns (samples/s, cores, kind, description)."""
     import numpy as np
@@ -114,7 +114,49 @@ def reference_sample(n_sample, reps):
     desc = "batch %d of 256 (same layer), fwd+bwd+Nadam, best of %d after 1 warm-up, %s" % (
         n_sample, reps, "C-ATTL3 Eigen path, -O3 -mavx2 -mfma -fopenmp" if kind == "reference"
         else "C restatement of the reference (reference shim not built)")
+    if keep is not None:
+        keep.update(x=x, w=w, b=b, dy=dy, out=r)
     return n_sample / best, lib.num_threads(), kind, desc
+
+
+def parity_against(ctx, pkg, keep, n_sample):
+    """The CPU baseline's own outputs against the CUDA path on the same inputs (the sample batch of the same layer):
+    norm-relative max|a - b| / max|b| per tensor, the metric of tests/cases.py."""
+    import numpy as np
+    import torch
+    g = pkg.ConvGeom(n_sample, *GEOM[1:])
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a.ravel(order="F"))).cuda()
+    xd, wd, bd, dyd = dev(keep["x"]), dev(keep["w"]), dev(keep["b"]), dev(keep["dy"])
+    yd = torch.empty(keep["dy"].size, device="cuda")
+    dxd = torch.empty(keep["x"].size, device="cuda")
+    dwd, dbd = torch.zeros(keep["w"].size, device="cuda"), torch.zeros(keep["b"].size, device="cuda")
+    ctx.conv_forward(g, xd, wd, bd, yd)
+    ctx.conv_backward(g, xd, wd, dyd, dwd, dbd, dxd)
+    torch.cuda.synchronize()
+    out = {}
+    for k, t in (("y", yd), ("dx", dxd), ("dw", dwd), ("db", dbd)):
+        ref = keep["out"][k].ravel(order="F").astype(np.float64)
+        out[k] = float(np.max(np.abs(t.cpu().numpy().astype(np.float64) - ref)) / np.max(np.abs(ref)))
+    out["tolerance"] = 1e-4
+    out["against"] = "cpu_baseline outputs (same inputs, batch %d), kernel path %s" % (n_sample, ctx.last_path)
+    return out
+
+
+def measured_tf32_peak():
+    """scripts/tf32_peak (built by __graft_entry__.build()): dense tcgen05.mma kind::tf32 with A from tensor memory, the
+    instruction the kernels issue, verified and timed on this GPU right now.  None if the probe is not there."""
+    import subprocess
+    exe = os.path.join(ROOT, "scripts", "tf32_peak")
+    if not os.path.exists(exe):
+        return None
+    try:
+        out = subprocess.run([exe, "0.5", "1sm_ts"], capture_output=True, text=True, timeout=60).stdout
+        d = json.loads(out.strip().splitlines()[-1])["1sm_ts"]
+        if d.get("verify_max_abs_err") != 0:
+            return None
+        return {"burst": d["burst_tflops"], "sustained": d["sustained_tflops"]}
+    except Exception:
+        return None
 
 
 def run_reference(args, rank):
@@ -142,6 +184,22 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+def network_extras(world):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_networks", os.path.join(ROOT, "scripts", "bench_networks.py"))
+    bn = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bn)
+    out = {}
+    steps = 8 if world <= 2 else 4
+    for cfg in (4, 5):
+        try:
+            r = bn.run_network(cfg, steps=steps, epochs=3)
+            out["config%d" % cfg] = {k: r[k] for k in ("value", "unit", "n_gpus", "ms_per_step", "epoch_ms", "scaling", "config")}
+        except Exception as e:   # the shim is built by __graft_entry__.build(); say why if it cannot run
+            out["config%d" % cfg] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -150,6 +208,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 auto (tcgen05), 1 SIMT only")
+    ap.add_argument("--no-networks", action="store_true", help="skip the network-level extras (configs 4 and 5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -189,12 +248,20 @@ def main():
     y = torch.empty(M * F, device=dev)
     dx = torch.empty(M * C, device=dev)
     tstep = [0]
+    # the product's communicator (cattl3_comm_*: NCCL behind the C ABI); torch.distributed only synchronises the ranks
+    # around the timed region and takes the max of their times
+    comm = pkg.Comm(ctx) if world > 1 else None
 
     def step():
         ctx.conv_forward(g, x, w, b, y)
-        ctx.conv_backward(g, x, w, dy, dw, db, dx)
-        if dist is not None:
-            dist.all_reduce(grads)  # sum over ranks: the loss gradient is divided by the GLOBAL batch upstream
+        ctx.conv_backward(g, x, w, dy, dw, db, None)        # weight + bias gradient
+        if comm is not None:
+            # sum over ranks (the loss gradient is divided by the GLOBAL batch upstream), on the communicator's side
+            # stream: the exchange overlaps the input gradient, which does not depend on it
+            comm.allreduce(grads, asynchronous=True)
+        ctx.conv_backward(g, x, w, dy, None, None, dx)      # input gradient
+        if comm is not None:
+            comm.wait()
         st = pkg.make_opt_step(pkg.OPT["nadam"], NADAM, tstep[0], 0, 0.0, True)
         ctx.optimizer_step(st, arena.numel(), arena, grads, m_state, v_state)
         tstep[0] += 1
@@ -240,8 +307,8 @@ def main():
         # tensors: y and dX are complete in pinned host memory when the step ends
         ctx.conv_forward_host_async(g, xh, w, b, yh, xkeep)
         ctx.conv_backward_host_async(g, xkeep, w, dyh, dw, db, dxh)
-        if dist is not None:
-            dist.all_reduce(grads)
+        if comm is not None:
+            comm.allreduce(grads)
         st = pkg.make_opt_step(pkg.OPT["nadam"], NADAM, tstep[0], 0, 0.0, True)
         ctx.optimizer_step(st, arena.numel(), arena, grads, m_state, v_state)
         tstep[0] += 1
@@ -264,7 +331,15 @@ def main():
 
     # ---- per-kernel rooflines: each device pass timed alone on the launching stream ---------------------
     pk = peaks()
-    tf32_peak = pk["bf16_burst"] / 2.0
+    torch.cuda.synchronize()
+    probe = measured_tf32_peak() if (rank == 0 and world == 1) else None
+    if probe:
+        tf32_peak = probe["burst"]
+        peak_source = ("dense tcgen05.mma kind::tf32 (M128 N256 K8, A from tensor memory) measured by scripts/tf32_peak in this "
+                       "run: %.1f TFLOP/s burst (kernels timed alone), %.1f sustained" % (probe["burst"], probe["sustained"]))
+    else:
+        tf32_peak = pk["bf16_burst"] / 2.0
+        peak_source = "TF32 dense = bf16 burst %.1f / 2, %s (scripts/tf32_peak not run)" % (pk["bf16_burst"], pk["source"])
 
     def time_alone(fn, reps=5):
         fn()
@@ -279,14 +354,14 @@ def main():
 
     t_fwd = time_alone(lambda: ctx.conv_forward(g, x, w, b, y))
     t_bwd_nodx = time_alone(lambda: ctx.conv_backward(g, x, w, dy, dw, db, None))
-    t_bwd = time_alone(lambda: ctx.conv_backward(g, x, w, dy, dw, db, dx))
     grads.zero_()
     st = pkg.make_opt_step(pkg.OPT["nadam"], NADAM, tstep[0], 0, 0.0, True)
     t_opt = time_alone(lambda: ctx.optimizer_step(st, arena.numel(), arena, grads, m_state, v_state))
     kernels = []
+    t_dgrad = time_alone(lambda: ctx.conv_backward(g, x, w, dy, None, None, dx))
     for name, t, flop in (("conv forward (pack_weights + tc_gather_gemm_kernel)", t_fwd, FLOP_PER_PASS),
                           ("weight+bias gradient (tc_wgrad_kernel + wgrad_reduce_tc_kernel)", t_bwd_nodx, FLOP_PER_PASS),
-                          ("input gradient (pack_weights + tc_gather_gemm_kernel)", t_bwd - t_bwd_nodx, FLOP_PER_PASS)):
+                          ("input gradient (pack_weights + tc_gather_gemm_kernel)", t_dgrad, FLOP_PER_PASS)):
         ach = flop / (t * 1e-3) / 1e12
         kernels.append({"pass": name, "ms": round(t, 4), "achieved_tflops": round(ach, 2),
                         "frac": round(ach / tf32_peak, 4), "tensor_pipe_frac": round(3 * ach / tf32_peak, 4)})
@@ -301,8 +376,8 @@ def main():
     roofline = {"bound": "tensor", "achieved": dom["achieved_tflops"], "peak": round(tf32_peak, 1), "unit": "TFLOP/s",
                 "frac": dom["frac"], "traffic": traffic, "kernel": dom["pass"],
                 "tensor_pipe_frac": dom["tensor_pipe_frac"],
-                "peak_source": "TF32 dense = bf16 burst %.1f / 2, %s; 3xTF32 issues 3 MMAs per algorithmic MAC, "
-                               "so frac <= 1/3 and tensor_pipe_frac = 3*frac" % (pk["bf16_burst"], pk["source"])}
+                "peak_source": peak_source + "; 3xTF32 issues 3 MMAs per algorithmic MAC, so frac <= 1/3 and "
+                               "tensor_pipe_frac = 3*frac"}
 
     line = {
         "metric": "train samples/s (fwd+bwd+step)", "value": round(value, 1), "unit": "samples/s", "n_gpus": world,
@@ -320,8 +395,17 @@ def main():
         "kernels": kernels,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, kind, desc = reference_sample(32, 2)
+        keep = {}
+        v, cores, kind, desc = reference_sample(32, 2, keep)
         line["cpu_baseline"] = {"value": round(v, 2), "unit": "samples/s", "cores": cores, "kind": kind, "sample": desc}
+        line["parity"] = parity_against(ctx, pkg, keep, 32)
+    if comm is not None:
+        comm.destroy()
+    if not args.no_networks:
+        # BASELINE.json configs[3] and [4] through the product's own data-parallel batch loop (cattle::SGDOptimizer::_train
+        # sharding + cattl3_comm_* exchange overlapped with the backward pass + synchronised BatchNorm; C++ host side,
+        # scripts/bench_networks.py), same launch, weak scaling at 64 samples per GPU: secondary numbers beside the headline
+        line["networks"] = network_extras(world)
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

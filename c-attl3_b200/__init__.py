@@ -77,6 +77,7 @@ _SYMBOLS = [
     "cattl3_comm_unique_id", "cattl3_comm_create", "cattl3_comm_create_from_env", "cattl3_comm_destroy",
     "cattl3_comm_world_size", "cattl3_comm_rank", "cattl3_comm_group_start", "cattl3_comm_group_end",
     "cattl3_comm_allreduce_sum_f32", "cattl3_comm_allreduce_sum_f64",
+    "cattl3_comm_allreduce_sum_async_f32", "cattl3_comm_allreduce_sum_async_f64", "cattl3_comm_wait",
 ] + [n + s for s in ("_f32", "_f64") for n in (
     "cattl3_conv_forward", "cattl3_conv_backward", "cattl3_transconv_forward", "cattl3_transconv_backward",
     "cattl3_dense_forward", "cattl3_dense_backward", "cattl3_activation_forward", "cattl3_activation_backward",
@@ -372,6 +373,38 @@ class Context:
     def scale(self, count, alpha, x, y):
         _, ct = _suffix(x.dtype)
         self._call("cattl3_scale", x.dtype, ctypes.c_int64(count), ct(alpha), _p(x), _p(y))
+
+
+class Comm:
+    """One cattl3_comm: this process's seat in the data-parallel exchange (one process per GPU; WORLD_SIZE / RANK from
+    the environment, NCCL underneath).  All-reduces are in place, sums, on the context's stream or -- the _async form --
+    on the communicator's side stream, joined by wait()."""
+
+    def __init__(self, ctx):
+        self.ctx, self.L = ctx, ctx.L
+        self.h = ctypes.c_void_p()
+        ctx._chk(self.L.cattl3_comm_create_from_env(ctypes.byref(self.h), ctx.h))
+
+    @property
+    def world_size(self):
+        return int(self.L.cattl3_comm_world_size(self.h))
+
+    @property
+    def rank(self):
+        return int(self.L.cattl3_comm_rank(self.h))
+
+    def allreduce(self, t, asynchronous=False):
+        suf, _ = _suffix(t.dtype)
+        fn = getattr(self.L, "cattl3_comm_allreduce_sum_%s%s" % ("async_" if asynchronous else "", suf))
+        self.ctx._chk(fn(self.h, _p(t), ctypes.c_int64(t.numel())))
+
+    def wait(self):
+        self.ctx._chk(self.L.cattl3_comm_wait(self.h))
+
+    def destroy(self):
+        if self.h:
+            self.L.cattl3_comm_destroy(self.h)
+            self.h = None
 
 
 def make_opt_step(kind, hyper, timestep, epoch, l2_lambda=0.0, reset_grad=True, dtype="float32"):

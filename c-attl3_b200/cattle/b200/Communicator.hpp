@@ -43,6 +43,22 @@ public:
 		Context::Lock l = Context::get().lock();
 		CATTLE_B200_CHECK(cattl3_comm_allreduce_sum_f64(comm, dev, (std::int64_t) count));
 	}
+	/**
+	 * The same sum on the communicator's side stream: it starts when everything enqueued so far has finished and runs
+	 * beside what is enqueued next; wait() makes the context's stream wait for every exchange started this way.
+	 */
+	inline void all_reduce_sum_async(float* dev, std::size_t count) {
+		Context::Lock l = Context::get().lock();
+		CATTLE_B200_CHECK(cattl3_comm_allreduce_sum_async_f32(comm, dev, (std::int64_t) count));
+	}
+	inline void all_reduce_sum_async(double* dev, std::size_t count) {
+		Context::Lock l = Context::get().lock();
+		CATTLE_B200_CHECK(cattl3_comm_allreduce_sum_async_f64(comm, dev, (std::int64_t) count));
+	}
+	inline void wait() {
+		Context::Lock l = Context::get().lock();
+		CATTLE_B200_CHECK(cattl3_comm_wait(comm));
+	}
 	/** Sum over all ranks of a host scalar (loss bookkeeping); synchronises. */
 	inline double all_reduce_sum(double value) {
 		if (world_size() == 1)

@@ -109,7 +109,8 @@ public:
 		if (!device_resident())
 			throw b200::Error(CATTL3_ERR_UNSUPPORTED, "MemoryDataProvider: the data set is not device resident");
 		const std::size_t rows = std::min(batch_size, instances - offset);
-		const std::size_t lo = rows * rank / world, hi = rows * (rank + 1) / world;
+		// fewer rows than ranks (a ragged last batch): every rank takes all of them (SGDOptimizer::_train rescales)
+		const std::size_t lo = rows < world ? 0 : rows * rank / world, hi = rows < world ? rows : rows * (rank + 1) / world;
 		cut(dev_obs, (std::size_t) obs->size() / instances, offset + lo, hi - lo, obs_batch);
 		cut(dev_obj, (std::size_t) obj->size() / instances, offset + lo, hi - lo, obj_batch);
 		offset += rows;

@@ -27,6 +27,7 @@
 #include <cstdlib>
 #include <iomanip>
 #include <iostream>
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <string>
@@ -69,6 +70,7 @@ public:
 		carried_graph_loss = 0;
 		graphs_failed = false;
 		eager_steps_at_shape = 0;
+		exchange = GradientExchange();
 		std::vector<Parameters<Scalar>*> params_vec = net.get_all_unique_params();
 		pack_parameters(params_vec);
 		_fit(params_vec);
@@ -85,6 +87,12 @@ protected:
 		DeviceFace* dev_net = face ? &face : nullptr;
 		const b200::DeviceLoss<Scalar>* dev_loss = dynamic_cast<const b200::DeviceLoss<Scalar>*>(Base::loss.get());
 		std::vector<b200::DeviceBuffer<Scalar>> step_losses;
+		// A ragged last batch with fewer rows than ranks cannot be sharded without leaving ranks empty-handed, and a rank
+		// that skips a step skips the collectives of a synchronised BatchNorm in it: every rank then takes the WHOLE batch,
+		// with the loss gradient divided by world size as well (the summed gradients and statistics come out the same) and
+		// the losses weighted 1 / world size.  step_loss_weights goes with step_losses.
+		std::vector<double> step_loss_weights;
+		const std::size_t world = comm.world_size();
 		b200::DeviceDataSource<Scalar>* dev_data = dev_net && dev_loss ?
 				dynamic_cast<b200::DeviceDataSource<Scalar>*>(&training_prov) : nullptr;
 		if (dev_data && !dev_data->device_resident())
@@ -99,13 +107,16 @@ protected:
 					obs.buf = graph->obs; obs.rows = graph->rows;
 					obj.buf = graph->obj; obj.rows = graph->rows;
 				}
-				instances += dev_data->next_batch_dev(batch_size, comm.rank(), comm.world_size(), obs, obj);
+				const std::size_t batch_rows = dev_data->next_batch_dev(batch_size, comm.rank(), comm.world_size(), obs, obj);
+				instances += batch_rows;
+				const std::size_t replicas = world > 1 && batch_rows < world ? world : 1;
 				if (!obs.empty() && use_graphs && !graphs_failed) {
 					// launch-bound steps: after two eager steps at a shape (every scratch buffer has its size, BatchNorm
 					// has seen a batch) the step is captured as a CUDA graph and replayed
-					if (graph && graph->rows != obs.rows && obs.rows == batch_size)
+					// (batch_rows counts the whole mini-batch, obs.rows this rank's shard of it)
+					if (graph && graph->rows != obs.rows && batch_rows == batch_size)
 						drop_graph();   // the nominal batch changed shape: capture again
-					if (!graph && obs.rows == batch_size) {
+					if (!graph && batch_rows == batch_size) {
 						if (eager_shape_rows != obs.rows) {
 							eager_shape_rows = obs.rows;
 							eager_steps_at_shape = 0;
@@ -128,8 +139,10 @@ protected:
 				if (!obs.empty()) {
 					b200::DeviceTensor<Scalar> out = dev_net->propagate_dev(std::move(obs), true);
 					step_losses.emplace_back();
-					b200::DeviceTensor<Scalar> out_grad = dev_loss->loss_and_gradient_dev(out, obj, (Scalar) batch_size,
+					step_loss_weights.push_back(1.0 / replicas);
+					b200::DeviceTensor<Scalar> out_grad = dev_loss->loss_and_gradient_dev(out, obj, (Scalar) (batch_size * replicas),
 							step_losses.back());
+					exchange_begin(params_vec, comm);
 					dev_net->backpropagate_dev(std::move(out_grad));
 				}
 				finish_step(params_vec, comm, epoch, reg_loss, updates);
@@ -138,8 +151,10 @@ protected:
 				continue;
 			}
 			DataPair<Scalar,Rank,Sequential> data_pair = training_prov.get_data(batch_size);
-			instances += data_pair.first.dimension(0);
-			if (comm.world_size() > 1)
+			const std::size_t batch_rows = data_pair.first.dimension(0);
+			instances += batch_rows;
+			const std::size_t replicas = world > 1 && batch_rows < world ? world : 1;
+			if (world > 1 && replicas == 1)
 				data_pair = shard(std::move(data_pair), comm);
 			if (data_pair.first.dimension(0) > 0 && dev_net && dev_loss) {
 				// the whole step in HBM: one upload of the mini-batch, then propagate -> loss -> back-propagate
@@ -148,27 +163,32 @@ protected:
 				b200::DeviceTensor<Scalar> obj = fed(1, data_pair.second);
 				b200::DeviceTensor<Scalar> out = dev_net->propagate_dev(fed(0, data_pair.first), true);
 				step_losses.emplace_back();
-				b200::DeviceTensor<Scalar> out_grad = dev_loss->loss_and_gradient_dev(out, obj, (Scalar) batch_size,
+				step_loss_weights.push_back(1.0 / replicas);
+				b200::DeviceTensor<Scalar> out_grad = dev_loss->loss_and_gradient_dev(out, obj, (Scalar) (batch_size * replicas),
 						step_losses.back());
+				exchange_begin(params_vec, comm);
 				dev_net->backpropagate_dev(std::move(out_grad));
 			} else if (data_pair.first.dimension(0) > 0) {
 				typename Base::Data out = net.propagate(std::move(data_pair.first), true);
-				obj_loss += Base::loss->function(out, data_pair.second).sum();
+				obj_loss += Base::loss->function(out, data_pair.second).sum() / (double) replicas;
 				// dividing by the nominal batch size decouples the learning rate from the batch size and
 				// makes the shard gradients add up to the full-batch gradient
 				net.backpropagate(Base::loss->d_function(std::move(out), std::move(data_pair.second)) /
-						(Scalar) batch_size);
+						(Scalar) (batch_size * replicas));
 			}
 			finish_step(params_vec, comm, epoch, reg_loss, updates);
 		}
 		obj_loss += collect_graph_loss() + carried_graph_loss;
 		carried_graph_loss = 0;
 		reg_loss += collect_device_penalty();
-		for (const b200::DeviceBuffer<Scalar>& losses : step_losses) {
+		for (std::size_t i = 0; i < step_losses.size(); ++i) {
+			const b200::DeviceBuffer<Scalar>& losses = step_losses[i];
 			std::vector<Scalar> host(losses.size());
 			losses.download(host.data(), host.size());
+			double sum = 0;
 			for (Scalar l : host)
-				obj_loss += l;
+				sum += l;
+			obj_loss += sum * step_loss_weights[i];
 		}
 		if (comm.world_size() > 1)
 			obj_loss = comm.all_reduce_sum(obj_loss);
@@ -414,7 +434,11 @@ private:
 			const char* v = std::getenv("CATTL3_NO_GRAPH");
 			return !(v && v[0] && v[0] != '0');
 		}();
-		if (!enabled || b200::Communicator::get().world_size() > 1)
+		static const bool dp_graphs = [] {
+			const char* v = std::getenv("CATTL3_NO_DP_GRAPH");
+			return !(v && v[0] && v[0] != '0');
+		}();
+		if (!enabled || (b200::Communicator::get().world_size() > 1 && !dp_graphs))
 			return false;
 		if (Sequential) {
 			const b200::DeviceSequenceNetwork<Scalar,Rank>* seq = dynamic_cast<const b200::DeviceSequenceNetwork<Scalar,Rank>*>(&net);
@@ -506,6 +530,10 @@ private:
 							g.loss_rows.data()));
 				}
 				dev_net.backpropagate_dev(std::move(out_grad));
+				// data parallel: the exchange (and the statistics all-reduces of synchronised BatchNorm layers inside the
+				// passes above) are NCCL operations on the capturing stream -- they become nodes of the step graph
+				if (b200::Communicator::get().world_size() > 1)
+					all_reduce_gradients(params_vec, b200::Communicator::get());
 				double no_host_penalty = 0;
 				regularize_all(params_vec, no_host_penalty);   // device penalties only (graph_eligible)
 				step_mode = STEP_CAPTURE;
@@ -599,7 +627,7 @@ private:
 	/** The tail of a training step: all-reduce, regularise, update, reset (SGDOptimizer.hpp:57-70). */
 	inline void finish_step(const std::vector<Parameters<Scalar>*>& params_vec, b200::Communicator& comm, std::size_t epoch,
 			double& reg_loss, std::size_t& updates) {
-		if (comm.world_size() > 1)
+		if (comm.world_size() > 1 && !exchange_finish(params_vec, comm))
 			all_reduce_gradients(params_vec, comm);
 		regularize_all(params_vec, reg_loss);
 		_update_params(params_vec, epoch - 1, timestep);
@@ -708,35 +736,160 @@ private:
 			return typename Base::Data();
 		return data.slice(offsets, extents);
 	}
-	/** Sum over ranks of every optimizable parameter gradient, in place, on the device. */
-	inline static void all_reduce_gradients(const std::vector<Parameters<Scalar>*>& params_vec,
-			b200::Communicator& comm) {
-		std::vector<B200Parameters<Scalar>*> reduced;
-		Scalar* run_begin = nullptr;
-		std::size_t run_count = 0;
-		comm.group_start();
+	/**
+	 * The device gradient arrays of all optimizable parameters as maximal contiguous stretches (sorted by address, adjacent
+	 * and overlapping views merged): the packed arena is ONE stretch, a per-channel BatchNormLayer's 2 C one-element views
+	 * over two vectors are two.
+	 */
+	inline static std::vector<std::pair<Scalar*,Scalar*>> gradient_stretches(const std::vector<Parameters<Scalar>*>& params_vec,
+			std::vector<B200Parameters<Scalar>*>* devs = nullptr) {
+		std::vector<std::pair<Scalar*,Scalar*>> ranges;
 		for (Parameters<Scalar>* params_ptr : params_vec) {
 			if (!params_ptr->are_optimizable())
 				continue;
 			B200Parameters<Scalar>* dev = dynamic_cast<B200Parameters<Scalar>*>(params_ptr);
 			if (!dev)
 				throw b200::Error(CATTL3_ERR_UNSUPPORTED, "data-parallel training needs device-resident parameters");
-			// adjacent views of one array (BatchNormLayer's per-channel parameters) travel as one message
-			if (run_count > 0 && run_begin + run_count == dev->device_grad()) {
-				run_count += dev->count();
-			} else {
-				if (run_count > 0)
-					comm.all_reduce_sum(run_begin, run_count);
-				run_begin = dev->device_grad();
-				run_count = dev->count();
-			}
-			reduced.push_back(dev);
+			ranges.emplace_back(dev->device_grad(), dev->device_grad() + dev->count());
+			if (devs)
+				devs->push_back(dev);
 		}
-		if (run_count > 0)
-			comm.all_reduce_sum(run_begin, run_count);
+		std::sort(ranges.begin(), ranges.end());
+		std::vector<std::pair<Scalar*,Scalar*>> merged;
+		for (const std::pair<Scalar*,Scalar*>& r : ranges) {
+			if (!merged.empty() && r.first <= merged.back().second)
+				merged.back().second = std::max(merged.back().second, r.second);
+			else
+				merged.push_back(r);
+		}
+		return merged;
+	}
+	/** Sum over ranks of every optimizable parameter gradient, in place, on the device: one message per stretch. */
+	inline static void all_reduce_gradients(const std::vector<Parameters<Scalar>*>& params_vec,
+			b200::Communicator& comm) {
+		std::vector<B200Parameters<Scalar>*> reduced;
+		const std::vector<std::pair<Scalar*,Scalar*>> stretches = gradient_stretches(params_vec, &reduced);
+		comm.group_start();
+		for (const std::pair<Scalar*,Scalar*>& r : stretches)
+			comm.all_reduce_sum(r.first, (std::size_t) (r.second - r.first));
 		comm.group_end();
 		for (B200Parameters<Scalar>* dev : reduced)
 			dev->grad_written_on_device();
+	}
+	/**
+	 * The exchange overlapped with the backward pass.  Layers are back-propagated last to first
+	 * (FeedforwardNeuralNetwork.hpp:120-127) and the arena holds their gradients first to last, so the finished part of
+	 * the arena is a suffix that grows towards the front: whenever it has grown by a bucket, that stretch goes on its way
+	 * on the communicator's side stream while the layers in front of it still compute.  A parameter written more than once
+	 * per step (shared by the cells of an LSTM) would be sent before it is complete, so the first data-parallel step only
+	 * COUNTS the writes and the overlap is used if every parameter is written exactly once; otherwise, and for unpacked or
+	 * constrained parameters, the exchange stays behind the backward pass (all_reduce_gradients).
+	 */
+	struct GradientExchange : public B200Parameters<Scalar>::GradientListener {
+		enum Mode { IDLE, COUNTING, SENDING };
+		Mode mode = IDLE;
+		bool decided = false, usable = false, violated = false;
+		b200::Communicator* comm = nullptr;
+		Scalar* lo = nullptr; Scalar* hi = nullptr;      // the arena
+		Scalar* sent_from = nullptr;                      // [sent_from, hi) is on its way
+		std::size_t bucket = 0;
+		std::vector<std::pair<Scalar*,Scalar*>> done;     // written, not yet sent
+		std::map<Scalar*,int> writes;
+		inline void gradient_written(Scalar* p, std::size_t n) override {
+			if (mode == COUNTING) {
+				++writes[p];
+			} else if (mode == SENDING) {
+				if (p < lo || p + n > hi)
+					return;
+				if (p + n > sent_from) {
+					violated = true;   // a second write into a stretch that has left: the warm-up count said this cannot happen
+					return;
+				}
+				done.emplace_back(p, p + n);
+				Scalar* frontier = sent_from;
+				for (bool grew = true; grew;) {
+					grew = false;
+					for (std::size_t i = 0; i < done.size(); ++i) {
+						if (done[i].second == frontier) {
+							frontier = done[i].first;
+							done[i] = done.back();
+							done.pop_back();
+							grew = true;
+							break;
+						}
+					}
+				}
+				// a stretch smaller than a bucket waits at the frontier: keep it in `done` as one range
+				if ((std::size_t) (sent_from - frontier) >= bucket) {
+					comm->all_reduce_sum_async(frontier, (std::size_t) (sent_from - frontier));
+					sent_from = frontier;
+				} else if (frontier != sent_from) {
+					done.emplace_back(frontier, sent_from);
+				}
+			}
+		}
+		inline void begin(Mode m) {
+			mode = m;
+			done.clear();
+			sent_from = hi;
+			violated = false;
+			B200Parameters<Scalar>::gradient_listener() = this;
+		}
+		inline void end() {
+			B200Parameters<Scalar>::gradient_listener() = nullptr;
+		}
+	};
+	GradientExchange exchange;
+	/** Before a data-parallel backward pass: count the writes (first step), or send finished stretches as they appear. */
+	inline void exchange_begin(const std::vector<Parameters<Scalar>*>& params_vec, b200::Communicator& comm) {
+		static const bool enabled = [] {
+			const char* v = std::getenv("CATTL3_NO_OVERLAP");
+			return !(v && v[0] && v[0] != '0');
+		}();
+		if (!enabled || comm.world_size() < 2)
+			return;
+		if (!exchange.decided) {
+			exchange.writes.clear();
+			exchange.begin(GradientExchange::COUNTING);
+		} else if (exchange.usable) {
+			exchange.begin(GradientExchange::SENDING);
+		}
+	}
+	/** After the backward pass: the rest of the gradients; true if the exchange has been taken care of here. */
+	inline bool exchange_finish(const std::vector<Parameters<Scalar>*>& params_vec, b200::Communicator& comm) {
+		if (exchange.mode == GradientExchange::IDLE)
+			return false;
+		exchange.end();
+		const typename GradientExchange::Mode mode = exchange.mode;
+		exchange.mode = GradientExchange::IDLE;
+		if (mode == GradientExchange::COUNTING) {
+			// decide once: one packed stretch, every parameter written exactly once, no constraints evaluated on the host
+			std::vector<B200Parameters<Scalar>*> devs;
+			const std::vector<std::pair<Scalar*,Scalar*>> stretches = gradient_stretches(params_vec, &devs);
+			bool ok = stretches.size() == 1;
+			for (B200Parameters<Scalar>* dev : devs) {
+				typename std::map<Scalar*,int>::const_iterator it = exchange.writes.find(dev->device_grad());
+				ok = ok && it != exchange.writes.end() && it->second == 1 && !dev->has_grad_constraints();
+			}
+			exchange.decided = true;
+			exchange.usable = ok;
+			if (ok) {
+				exchange.comm = &comm;
+				exchange.lo = stretches[0].first;
+				exchange.hi = stretches[0].second;
+				const char* v = std::getenv("CATTL3_BUCKET_KB");
+				const long kb = v && v[0] ? std::atol(v) : 1024;
+				exchange.bucket = (std::size_t) (kb > 0 ? kb : 1) * 1024 / sizeof(Scalar);
+			}
+			return false;
+		}
+		if (exchange.violated)
+			throw b200::Error(CATTL3_ERR_UNSUPPORTED, "data-parallel exchange: a gradient was written again after its bucket "
+					"had been sent (set CATTL3_NO_OVERLAP=1)");
+		if (exchange.sent_from > exchange.lo)
+			comm.all_reduce_sum_async(exchange.lo, (std::size_t) (exchange.sent_from - exchange.lo));
+		comm.wait();
+		return true;
 	}
 	std::size_t timestep;
 	const typename Base::Net* target_net_ptr;

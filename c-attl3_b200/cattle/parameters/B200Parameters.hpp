@@ -333,12 +333,26 @@ public:
 			set_values(std::move(v));
 		}
 	}
+	/**
+	 * Whoever wants to know that a layer's backward pass has enqueued its gradient (the data-parallel batch loop sends
+	 * finished stretches of the gradient arena on their way while the layers behind still compute).
+	 */
+	struct GradientListener {
+		virtual ~GradientListener() = default;
+		virtual void gradient_written(Scalar* dev_grad, std::size_t count) = 0;
+	};
+	inline static GradientListener*& gradient_listener() {
+		static GradientListener* listener = nullptr;
+		return listener;
+	}
 	/** After a kernel accumulated into the gradient (beta = 1, StandardParameters.hpp:115-123). */
 	inline void grad_written_on_device() {
 		if (!optimizable)
 			return;
 		grad_store->device_written();
 		grad_known_zero = false;
+		if (gradient_listener())
+			gradient_listener()->gradient_written(device_grad(), count());
 		if (has_grad_constraints()) {
 			Matrix<Scalar> g = get_grad();
 			enforce_constraints(g, grad_clip, grad_max_l1_norm, grad_max_l2_norm);

@@ -29,6 +29,7 @@ struct NcclApi {
 	int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
 	int (*GroupStart)() = nullptr;
 	int (*GroupEnd)() = nullptr;
+	int (*CommSplit)(NcclComm, int, int, NcclComm*, void*) = nullptr;   // NCCL >= 2.18; optional
 	const char* (*GetErrorString)(int) = nullptr;
 };
 
@@ -50,6 +51,7 @@ NcclApi* nccl() {
 			api.GroupStart = (int (*)()) dlsym(api.lib, "ncclGroupStart");
 			api.GroupEnd = (int (*)()) dlsym(api.lib, "ncclGroupEnd");
 			api.GetErrorString = (const char* (*)(int)) dlsym(api.lib, "ncclGetErrorString");
+			api.CommSplit = (int (*)(NcclComm, int, int, NcclComm*, void*)) dlsym(api.lib, "ncclCommSplit");
 			if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.GroupStart ||
 					!api.GroupEnd) {
 				dlclose(api.lib);
@@ -73,7 +75,16 @@ int nccl_fail(int rc, const char* what) {
 struct cattl3_comm {
 	cattl3_ctx* ctx = nullptr;
 	NcclComm comm = nullptr;
+	// a duplicate communicator for the side-stream exchanges (ncclCommSplit): operations on ONE communicator serialise
+	// in issue order whatever their streams, which would chain the main stream's BatchNorm-statistics all-reduces
+	// behind the gradient buckets travelling beside them; null = share `comm`
+	NcclComm comm_async = nullptr;
 	int world = 1, rank = 0;
+	// the side stream of the _async all-reduces: forked from the context's stream by an event per call, joined by
+	// cattl3_comm_wait (so the exchange of one layer's gradients overlaps the kernels of the layers behind it)
+	cudaStream_t side = nullptr;
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	bool pending = false;
 };
 
 using namespace cattl3;
@@ -119,6 +130,19 @@ int cattl3_comm_create(cattl3_comm** out, cattl3_ctx* ctx, int world_size, int r
 			delete c;
 			return nccl_fail(rc, "ncclCommInitRank");
 		}
+		if (n->CommSplit && !getenv("CATTL3_COMM_SINGLE")) {
+			if (n->CommSplit(c->comm, 0, rank, &c->comm_async, nullptr) != NCCL_SUCCESS)
+				c->comm_async = nullptr;
+		}
+		int lo = 0, hi = 0;
+		cudaDeviceGetStreamPriorityRange(&lo, &hi);   // the exchange is short and latency bound: highest priority
+		if (cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi) != cudaSuccess ||
+				cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+				cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+			cattl3_comm_destroy(c);
+			set_error("comm_create: side stream / events");
+			return CATTL3_ERR_CUDA;
+		}
 	}
 	*out = c;
 	return CATTL3_OK;
@@ -134,18 +158,25 @@ int cattl3_comm_create_from_env(cattl3_comm** out, cattl3_ctx* ctx) {
 	const int world = ws ? atoi(ws) : 1, rank = rk ? atoi(rk) : 0;
 	if (world <= 1)
 		return cattl3_comm_create(out, ctx, 1, 0, nullptr);
+	// The file is tied to the job: the ranks of one launch share their parent (the torchrun agent, or the test that
+	// spawned them), so a file left behind by a crashed run on the same port is never read by the next one.
 	std::string path;
 	if (const char* p = getenv("CATTL3_COMM_ID_FILE")) {
 		path = p;
 	} else {
 		const char* port = getenv("MASTER_PORT");
-		path = std::string("/tmp/cattl3_nccl_id.") + (port ? port : "0");
+		const char* run = getenv("TORCHELASTIC_RUN_ID");
+		static int sequence = 0;   // communicators are created in the same order on every rank
+		path = std::string("/tmp/cattl3_nccl_id.") + (port ? port : "0") + "." + std::to_string((long long) getppid()) +
+				(run ? std::string(".") + run : std::string()) + "." + std::to_string(sequence++);
+		for (char& ch : path) if (ch == ' ' || ch == ':') ch = '_';
 	}
 	NcclUniqueId id;
 	if (rank == 0) {
 		CATTL3_CHECK(cattl3_comm_unique_id(&id));
 		const std::string tmp = path + ".tmp";
-		FILE* f = fopen(tmp.c_str(), "wb");
+		unlink(tmp.c_str());
+		FILE* f = fopen(tmp.c_str(), "wbx");   // exclusive: never follows a planted link
 		CATTL3_REQUIRE(f, "cannot write %s", tmp.c_str());
 		fwrite(&id, sizeof(id), 1, f);
 		fclose(f);
@@ -172,9 +203,16 @@ int cattl3_comm_destroy(cattl3_comm* c) {
 	if (!c) return CATTL3_OK;
 	if (c->comm) {
 		cudaSetDevice(c->ctx->device);
+		if (c->side) cudaStreamSynchronize(c->side);
 		cudaStreamSynchronize(c->ctx->stream);
-		if (NcclApi* n = nccl()) n->CommDestroy(c->comm);
+		if (NcclApi* n = nccl()) {
+			if (c->comm_async) n->CommDestroy(c->comm_async);
+			n->CommDestroy(c->comm);
+		}
 	}
+	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+	if (c->ev_join) cudaEventDestroy(c->ev_join);
+	if (c->side) cudaStreamDestroy(c->side);
 	delete c;
 	return CATTL3_OK;
 }
@@ -199,6 +237,33 @@ static int allreduce(cattl3_comm* c, void* buf, int64_t count, int dtype) {
 	if (c->world == 1)
 		return CATTL3_OK;
 	CATTL3_NCCL(nccl()->AllReduce(buf, buf, (size_t) count, dtype, NCCL_SUM, c->comm, c->ctx->stream), "ncclAllReduce");
+	return CATTL3_OK;
+}
+// The same exchange on the communicator's side stream: it starts when everything enqueued on the context's stream so far
+// has finished (the weight gradients it sums) and runs beside whatever is enqueued next (the input gradient, the
+// layers further back); cattl3_comm_wait makes the context's stream wait for every exchange started this way.
+static int allreduce_async(cattl3_comm* c, void* buf, int64_t count, int dtype) {
+	CATTL3_REQUIRE(c && buf && count > 0, "comm_allreduce_async: bad arguments");
+	CATTL3_CHECK(check_ctx(c->ctx));
+	if (c->world == 1)
+		return CATTL3_OK;
+	CATTL3_REQUIRE(!c->ctx->capturing, "comm_allreduce_async: not inside a step graph");
+	CATTL3_CUDA(cudaEventRecord(c->ev_fork, c->ctx->stream));
+	CATTL3_CUDA(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+	CATTL3_NCCL(nccl()->AllReduce(buf, buf, (size_t) count, dtype, NCCL_SUM, c->comm_async ? c->comm_async : c->comm, c->side),
+			"ncclAllReduce");
+	c->pending = true;
+	return CATTL3_OK;
+}
+int cattl3_comm_allreduce_sum_async_f32(cattl3_comm* c, float* buf, int64_t count) { return allreduce_async(c, buf, count, NCCL_FLOAT32); }
+int cattl3_comm_allreduce_sum_async_f64(cattl3_comm* c, double* buf, int64_t count) { return allreduce_async(c, buf, count, NCCL_FLOAT64); }
+int cattl3_comm_wait(cattl3_comm* c) {
+	CATTL3_REQUIRE(c, "null communicator");
+	if (c->world == 1 || !c->pending)
+		return CATTL3_OK;
+	CATTL3_CUDA(cudaEventRecord(c->ev_join, c->side));
+	CATTL3_CUDA(cudaStreamWaitEvent(c->ctx->stream, c->ev_join, 0));
+	c->pending = false;
 	return CATTL3_OK;
 }
 int cattl3_comm_allreduce_sum_f32(cattl3_comm* c, float* buf, int64_t count) { return allreduce(c, buf, count, NCCL_FLOAT32); }

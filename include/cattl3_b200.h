@@ -432,7 +432,7 @@ typedef struct cattl3_comm cattl3_comm;
 int cattl3_comm_unique_id(void* id128);
 int cattl3_comm_create(cattl3_comm** out, cattl3_ctx* ctx, int world_size, int rank, const void* id128);
 /* WORLD_SIZE / RANK from the environment (torchrun convention); the id travels through the file
- * CATTL3_COMM_ID_FILE (default /tmp/cattl3_nccl_id.<MASTER_PORT>). */
+ * CATTL3_COMM_ID_FILE (default /tmp/cattl3_nccl_id.<MASTER_PORT>.<parent pid>[.<TORCHELASTIC_RUN_ID>]: tied to the launch). */
 int cattl3_comm_create_from_env(cattl3_comm** out, cattl3_ctx* ctx);
 int cattl3_comm_destroy(cattl3_comm* comm);
 int cattl3_comm_world_size(const cattl3_comm* comm);
@@ -441,6 +441,13 @@ int cattl3_comm_group_start(cattl3_comm* comm);
 int cattl3_comm_group_end(cattl3_comm* comm);
 int cattl3_comm_allreduce_sum_f32(cattl3_comm* comm, float* dev_buf, int64_t count);
 int cattl3_comm_allreduce_sum_f64(cattl3_comm* comm, double* dev_buf, int64_t count);
+/* The same exchange on the communicator's own high-priority stream: it starts once everything enqueued on the
+ * context's stream so far has finished and runs beside whatever is enqueued next (a layer's weight gradients travel
+ * while its input gradient and the layers behind it compute); cattl3_comm_wait() makes the context's stream wait for
+ * every exchange started this way (call it before the optimizer step). */
+int cattl3_comm_allreduce_sum_async_f32(cattl3_comm* comm, float* buf, int64_t count);
+int cattl3_comm_allreduce_sum_async_f64(cattl3_comm* comm, double* buf, int64_t count);
+int cattl3_comm_wait(cattl3_comm* comm);
 
 #ifdef __cplusplus
 }

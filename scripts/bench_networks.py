@@ -35,6 +35,84 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 
+def run_network(config, impl="b200", dtype="f32", batch=0, steps=8, epochs=5, width=64, blocks=4, image=224, seq=8):
+    """One network config through the C++ batch loop on this rank (every rank of a torchrun job calls it); returns the
+    result line (meaningful on rank 0)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dt = np.float32 if dtype == "f32" else np.float64
+    from oracle import binding
+    saved_world = os.environ.get("WORLD_SIZE")
+    if impl == "reference":
+        if rank != 0:
+            return None
+        lib = binding.Oracle("ref")
+        os.environ["WORLD_SIZE"] = "1"
+        world_eff = 1
+    else:
+        shim = os.path.join(ROOT, "tests", "cpp", "_build", "libcattle_b200_shim.so")
+        lib = binding.Oracle("ref", path=shim)
+        assert lib.lib.ref_is_b200_build() == 1
+        world_eff = world
+    per_gpu = batch or {1: 64, 3: 512, 4: 64, 5: 64}[config]
+    batch = per_gpu * world_eff                     # the nominal (global) batch the optimizer is built with
+    total = batch * steps
+    rng = np.random.default_rng({1: 1001, 3: 3001, 4: 4001, 5: 5001}[config])   # identical data on every rank
+    if config == 1:
+        x = np.asfortranarray(rng.uniform(-1, 1, (total, 32, 32, 3)).astype(dt))
+        obj = np.zeros((total, 1, 1, 10), dtype=dt, order="F")
+        obj[np.arange(total), 0, 0, np.arange(total) % 10] = 1
+        run = lambda n_epochs: lib.train_cifar(x, obj, batch, n_epochs)
+        name = "cifar ConvNet 32x32x3"
+    elif config == 3:
+        x = np.asfortranarray(rng.uniform(0, 1, (total, 28, 28, 1)).astype(dt))
+        run = lambda n_epochs: lib.train_autoencoder(x, batch, n_epochs)
+        name = "mnist auto-encoder 28x28x1"
+    elif config == 5:
+        # BASELINE.json configs[4]: sequences of 32x32x3 frames through Sequential{Parallel conv lanes, DenseNet modules,
+        # MaxPool} and a convolutional LSTM head (oracle/ref_shim.cpp seqnet_impl); --width lanes / modules / state channels
+        width = width if width != 64 else 16
+        x = np.asfortranarray(rng.random((total, seq, 32, 32, 3), dtype=np.float32).astype(dt) * 2 - 1)
+        obj = np.asfortranarray(rng.random((total, 1, 16, 16, width), dtype=np.float32).astype(dt) - 0.5)
+        run = lambda n_epochs: lib.train_seqnet(x, obj, batch, n_epochs, width, width)
+        name = ("sequence net: %d frames 32x32x3, Parallel{conv3x3, conv1x1} -> DenseNet x2 -> MaxPool -> conv LSTM, %d ch"
+                % (seq, width))
+    else:
+        s = image
+        x = np.asfortranarray(rng.random((total, s, s, 3), dtype=np.float32).astype(dt) * 2 - 1)
+        obj = np.zeros((total, 1, 1, 10), dtype=dt, order="F")
+        obj[np.arange(total), 0, 0, np.arange(total) % 10] = 1
+        arch = (7, 2, 1, width, blocks, 4)   # stem 7x7 stride 2 + max-pool 2x2, head mean-pool 4x4
+        run = lambda n_epochs: lib.train_resnet(x, obj, batch, n_epochs, arch)
+        name = "ResNet-style residual net %dx%dx3, stem 7x7/2 + pool, %d modules x (conv3x3-BN-ReLU-conv3x3-BN) @ %d ch" % (
+            s, s, blocks, width)
+    t0 = time.perf_counter()
+    _, loss0, ms_warm = run(1)                      # warm-up call: allocations, NCCL communicator, clocks
+    # every timed call = one untimed epoch (data set placement, this call's allocations) + one timed epoch; the value
+    # is the MEDIAN epoch: single epochs on a shared box occasionally stall for hundreds of ms (min / max reported)
+    os.environ["REF_SHIM_WARMUP_EPOCHS"] = "1"
+    times = []
+    for _ in range(max(3, epochs)):
+        _, loss, ms_epoch = run(1)
+        times.append(ms_epoch)
+    os.environ.pop("REF_SHIM_WARMUP_EPOCHS", None)
+    if saved_world is not None:
+        os.environ["WORLD_SIZE"] = saved_world
+    wall = time.perf_counter() - t0
+    ms = sorted(times)[len(times) // 2]
+    value = total / (ms / 1000.0)
+    return {"metric": "train samples/s (fwd+bwd+step), network level", "impl": impl, "value": round(value, 1),
+            "unit": "samples/s", "n_gpus": world_eff, "ms_per_step": round(ms / steps, 3),
+            "epoch_ms": {"median": round(ms, 2), "min": round(min(times), 2), "max": round(max(times), 2), "epochs": len(times)},
+            "scaling": "weak", "dtype": dtype, "data": "synthetic",
+            "config": {"workload": name, "config": config, "batch_per_gpu": per_gpu, "global_batch": batch,
+                       "steps_per_epoch": steps, "epochs_timed": epochs,
+                       "includes": "data-set slicing + layer loop + loss + gradient exchange (NCCL, cattl3_comm_*) + "
+                                   "optimizer step (cattle::NadamOptimizer::train)"},
+            "epoch_loss": round(float(loss), 6), "warmup_epoch_ms": round(ms_warm, 1), "wall_s": round(wall, 1),
+            "threads": lib.num_threads() if impl == "reference" else None}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", type=int, default=4, choices=[1, 3, 4, 5])
@@ -48,76 +126,9 @@ def main():
     ap.add_argument("--image", type=int, default=224)
     ap.add_argument("--seq", type=int, default=8, help="config 5: frames per sequence")
     args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    dt = np.float32 if args.dtype == "f32" else np.float64
-    from oracle import binding
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        lib = binding.Oracle("ref")
-        os.environ["WORLD_SIZE"] = "1"
-        world_eff = 1
-    else:
-        shim = os.path.join(ROOT, "tests", "cpp", "_build", "libcattle_b200_shim.so")
-        lib = binding.Oracle("ref", path=shim)
-        assert lib.lib.ref_is_b200_build() == 1
-        world_eff = world
-    per_gpu = args.batch or {1: 64, 3: 512, 4: 64, 5: 64}[args.config]
-    batch = per_gpu * world_eff                     # the nominal (global) batch the optimizer is built with
-    total = batch * args.steps
-    rng = np.random.default_rng({1: 1001, 3: 3001, 4: 4001, 5: 5001}[args.config])   # identical data on every rank
-    if args.config == 1:
-        x = np.asfortranarray(rng.uniform(-1, 1, (total, 32, 32, 3)).astype(dt))
-        obj = np.zeros((total, 1, 1, 10), dtype=dt, order="F")
-        obj[np.arange(total), 0, 0, np.arange(total) % 10] = 1
-        run = lambda epochs: lib.train_cifar(x, obj, batch, epochs)
-        name = "cifar ConvNet 32x32x3"
-    elif args.config == 3:
-        x = np.asfortranarray(rng.uniform(0, 1, (total, 28, 28, 1)).astype(dt))
-        run = lambda epochs: lib.train_autoencoder(x, batch, epochs)
-        name = "mnist auto-encoder 28x28x1"
-    elif args.config == 5:
-        # BASELINE.json configs[4]: sequences of 32x32x3 frames through Sequential{Parallel conv lanes, DenseNet modules,
-        # MaxPool} and a convolutional LSTM head (oracle/ref_shim.cpp seqnet_impl); --width lanes / modules / state channels
-        width = args.width if args.width != 64 else 16
-        x = np.asfortranarray(rng.uniform(-1, 1, (total, args.seq, 32, 32, 3)).astype(dt))
-        obj = np.asfortranarray(rng.uniform(-0.5, 0.5, (total, 1, 16, 16, width)).astype(dt))
-        run = lambda epochs: lib.train_seqnet(x, obj, batch, epochs, width, width)
-        name = ("sequence net: %d frames 32x32x3, Parallel{conv3x3, conv1x1} -> DenseNet x2 -> MaxPool -> conv LSTM, %d ch"
-                % (args.seq, width))
-    else:
-        s = args.image
-        x = np.asfortranarray(rng.uniform(-1, 1, (total, s, s, 3)).astype(dt))
-        obj = np.zeros((total, 1, 1, 10), dtype=dt, order="F")
-        obj[np.arange(total), 0, 0, np.arange(total) % 10] = 1
-        arch = (7, 2, 1, args.width, args.blocks, 4)   # stem 7x7 stride 2 + max-pool 2x2, head mean-pool 4x4
-        run = lambda epochs: lib.train_resnet(x, obj, batch, epochs, arch)
-        name = "ResNet-style residual net %dx%dx3, stem 7x7/2 + pool, %d modules x (conv3x3-BN-ReLU-conv3x3-BN) @ %d ch" % (
-            s, s, args.blocks, args.width)
-    t0 = time.perf_counter()
-    _, loss0, ms_warm = run(1)                      # warm-up call: allocations, NCCL communicator, clocks
-    # every timed call = one untimed epoch (data set placement, this call's allocations) + one timed epoch; the value
-    # is the MEDIAN epoch: single epochs on a shared box occasionally stall for hundreds of ms (min / max reported)
-    os.environ["REF_SHIM_WARMUP_EPOCHS"] = "1"
-    times = []
-    for _ in range(max(3, args.epochs)):
-        _, loss, ms_epoch = run(1)
-        times.append(ms_epoch)
-    wall = time.perf_counter() - t0
-    ms = sorted(times)[len(times) // 2]
-    value = total / (ms / 1000.0)
-    line = {"metric": "train samples/s (fwd+bwd+step), network level", "impl": args.impl, "value": round(value, 1),
-            "unit": "samples/s", "n_gpus": world_eff, "ms_per_step": round(ms / args.steps, 3),
-            "epoch_ms": {"median": round(ms, 2), "min": round(min(times), 2), "max": round(max(times), 2), "epochs": len(times)},
-            "scaling": "weak", "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": name, "config": args.config, "batch_per_gpu": per_gpu, "global_batch": batch,
-                       "steps_per_epoch": args.steps, "epochs_timed": args.epochs,
-                       "includes": "host data provider slicing + H2D of each mini-batch + layer loop + loss + "
-                                   "all-reduce + optimizer step (cattle::NadamOptimizer::train)"},
-            "epoch_loss": round(float(loss), 6), "warmup_epoch_ms": round(ms_warm, 1), "wall_s": round(wall, 1),
-            "threads": lib.num_threads() if args.impl == "reference" else None}
-    if rank == 0:
+    line = run_network(args.config, args.impl, args.dtype, args.batch, args.steps, args.epochs, args.width, args.blocks,
+                       args.image, args.seq)
+    if line is not None and int(os.environ.get("RANK", "0")) == 0:
         print(json.dumps(line), flush=True)
 
 

@@ -13,6 +13,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <unistd.h>
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -165,7 +166,9 @@ static int launch(int grid, int n_cols, int iters, int verify, float* out) {
 typedef int (*LaunchFn)(int, int, int, int, float*);
 
 int main(int argc, char** argv) {
+	// usage: tf32_peak [sustained seconds = 1.5] [mode filter, e.g. 1sm_ts]
 	const double sustain_s = argc > 1 ? atof(argv[1]) : 1.5;
+	const char* only = argc > 2 ? argv[2] : nullptr;
 	cudaDeviceProp prop;
 	cudaGetDeviceProperties(&prop, 0);
 	const int sms = prop.multiProcessorCount;
@@ -177,6 +180,7 @@ int main(int argc, char** argv) {
 	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 	printf("{\"device\": \"%s\", \"sms\": %d, \"shape\": \"M=128 per CTA, N=256, K=8, kind::tf32, fp32 accumulate in TMEM\"", prop.name, sms);
 	for (Mode& md : modes) {
+		if (only && !strstr(md.name, only)) continue;
 		// ---- verification: one k-block of exactly representable integers
 		cudaMemset(d_out, 0xff, 256 * N * 4);
 		int rc = md.fn(md.ctas, N, 1, 1, d_out);

@@ -128,7 +128,7 @@ import cases as C
 from oracle import binding
 lib = binding.Oracle("ref", path={shim!r})
 dt = np.float32 if sys.argv[1] == "f32" else np.float64
-x, obj = C.resnet_inputs(dt, total=128, seed=4003)
+x, obj = C.resnet_inputs(dt, total=int(sys.argv[3]), seed=4003)
 n = lib.train_resnet(x, obj, 64, -1, C.RESNET_SMALL)
 p, loss, ms = lib.train_resnet(x, obj, 64, 2, C.RESNET_SMALL, params_in=C.seeded_params(n, dt, 4002))
 np.save(sys.argv[2], p)
@@ -137,11 +137,14 @@ print("LOSS %.9f" % loss)
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("total", [128, 129])
 @pytest.mark.parametrize("suf", ["f32", "f64"])
-def test_two_process_resnet_with_synchronised_batchnorm_equals_one_process(tmp_path, suf):
+def test_two_process_resnet_with_synchronised_batchnorm_equals_one_process(tmp_path, suf, total):
     """Config 4 at test size on 2 GPUs: with the BatchNorm statistics all-reduced (forward sums + count, backward
     sums) two processes on half-batches must reproduce the single-process run on the full batch -- parameters
-    INCLUDING the running mean / inverse standard deviation -- and both ranks must hold identical parameters."""
+    INCLUDING the running mean / inverse standard deviation -- and both ranks must hold identical parameters.
+    total = 129 leaves a ragged last batch of ONE row for two ranks: no rank may sit the step out (it would skip the
+    BatchNorm collectives and hang the other), so both take the row and the loop rescales (SGDOptimizer::_train)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
@@ -154,8 +157,8 @@ def test_two_process_resnet_with_synchronised_batchnorm_equals_one_process(tmp_p
         for r in range(world):
             env = dict(os.environ, WORLD_SIZE=str(world), RANK=str(r), LOCAL_RANK=str(r), MASTER_PORT="29543",
                        CATTL3_COMM_ID_FILE=str(tmp_path / ("rid_%d" % world)))
-            procs.append(subprocess.Popen([sys.executable, str(script), suf, str(tmp_path / ("rp_%d_%d.npy" % (world, r)))],
-                                          env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+            procs.append(subprocess.Popen([sys.executable, str(script), suf, str(tmp_path / ("rp_%d_%d.npy" % (world, r))),
+                                           str(total)], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
         outs = [p.communicate(timeout=600)[0] for p in procs]
         for p, o in zip(procs, outs):
             assert p.returncode == 0, o[-3000:]
