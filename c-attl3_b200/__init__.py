@@ -82,7 +82,7 @@ _SYMBOLS = [
     "cattl3_conv_forward", "cattl3_conv_backward", "cattl3_transconv_forward", "cattl3_transconv_backward",
     "cattl3_dense_forward", "cattl3_dense_backward", "cattl3_activation_forward", "cattl3_activation_backward",
     "cattl3_pool_forward", "cattl3_pool_backward", "cattl3_batchnorm_forward", "cattl3_batchnorm_backward",
-    "cattl3_optimizer_step", "cattl3_optimizer_step_indirect", "cattl3_add_inplace", "cattl3_mul_inplace", "cattl3_muladd", "cattl3_regularize", "cattl3_scale", "cattl3_axpy",
+    "cattl3_optimizer_step", "cattl3_optimizer_step_indirect", "cattl3_add_inplace", "cattl3_mul_inplace", "cattl3_muladd", "cattl3_regularize", "cattl3_constrain", "cattl3_scale", "cattl3_axpy",
     "cattl3_conv_forward_fused", "cattl3_dense_forward_fused", "cattl3_transconv_forward_fused", "cattl3_batchnorm_forward_stats",
     "cattl3_dropout_forward", "cattl3_dropout_backward", "cattl3_loss",
     "cattl3_batchnorm_stats", "cattl3_batchnorm_backward_sums", "cattl3_batchnorm_backward_apply",
@@ -218,6 +218,10 @@ class Context:
                    ct(decay), ct(eps), _p(x), _p(col_stats), _p(global_count), _p(shift), _p(gamma), _p(beta), _p(running_mean),
                    _p(running_inv_sd), _p(saved_mean), _p(saved_inv_sd), _p(y),
                    ACT_NONE if act_kind is None else int(act_kind), ct(act_param), _p(act_out))
+
+    def constrain(self, x, clip=0.0, max_l1_norm=0.0, max_l2_norm=0.0):
+        _, ct = _suffix(x.dtype)
+        self._call("cattl3_constrain", x.dtype, ctypes.c_int64(x.numel()), ct(clip), ct(max_l1_norm), ct(max_l2_norm), _p(x))
 
     def fill(self, count, value, y):
         _, ct = _suffix(y.dtype)

@@ -119,6 +119,8 @@ template<> struct Api<S> { \
 		return cattl3_batchnorm_forward_stats_##SUF(c, pc, n, h, w, ch, init, decay, eps, x, cs, gc, shift, gamma, beta, rm, rs, sm, ss, y, ak, ap, ao); } \
 	static int fill(cattl3_ctx* c, std::int64_t count, S value, S* y) { \
 		return cattl3_fill_##SUF(c, count, value, y); } \
+	static int constrain(cattl3_ctx* c, std::int64_t count, S clip, S max_l1, S max_l2, S* x) { \
+		return cattl3_constrain_##SUF(c, count, clip, max_l1, max_l2, x); } \
 	static int slice_rows(cattl3_ctx* c, std::int64_t total, std::int64_t vol, std::int64_t first, std::int64_t rows, const S* src, S* dst) { \
 		return cattl3_slice_rows_##SUF(c, total, vol, first, rows, src, dst); } \
 	static int dropout_forward(cattl3_ctx* c, std::int64_t count, S prob, S eps, std::uint64_t seed, const S* x, S* y, std::uint8_t* mask) { \

@@ -451,7 +451,7 @@ private:
 		}
 		for (Parameters<Scalar>* params_ptr : params_vec) {
 			B200Parameters<Scalar>* dev = dynamic_cast<B200Parameters<Scalar>*>(params_ptr);
-			if (!dev || dev->has_host_regularization() || dev->has_value_constraints() || dev->has_grad_constraints())
+			if (!dev || dev->has_host_regularization())
 				return false;
 		}
 		return true;

@@ -288,11 +288,11 @@ public:
 	}
 	/**
 	 * Whether the regularisation runs on the device: an L1, L2 or ElasticNet penalty (their derivative and value are
-	 * one kernel, cattl3_regularize) and no gradient constraint that would have to be re-applied on the host
-	 * (accumulate_grad, StandardParameters.hpp:115-123).
+	 * one kernel, cattl3_regularize; gradient constraints are re-applied behind it on the device as accumulate_grad
+	 * does, StandardParameters.hpp:115-123).
 	 */
 	inline bool has_device_regularization() const {
-		return optimizable && param_reg && (l1_lambda > 0 || l2_lambda > 0) && !has_grad_constraints();
+		return optimizable && param_reg && (l1_lambda > 0 || l2_lambda > 0);
 	}
 	/**
 	 * regularize() and get_regularization_penalty() in one pass on the device: grad += d penalty / d values and, if
@@ -328,10 +328,8 @@ public:
 	/** After a kernel updated the values (optimizer step, running statistics). */
 	inline void values_written_on_device() {
 		value_store->device_written();
-		if (has_value_constraints()) {
-			Matrix<Scalar> v = get_values();
-			set_values(std::move(v));
-		}
+		if (has_value_constraints())
+			constrain_dev(device_values(), value_clip, value_max_l1_norm, value_max_l2_norm);
 	}
 	/**
 	 * Whoever wants to know that a layer's backward pass has enqueued its gradient (the data-parallel batch loop sends
@@ -353,11 +351,8 @@ public:
 		grad_known_zero = false;
 		if (gradient_listener())
 			gradient_listener()->gradient_written(device_grad(), count());
-		if (has_grad_constraints()) {
-			Matrix<Scalar> g = get_grad();
-			enforce_constraints(g, grad_clip, grad_max_l1_norm, grad_max_l2_norm);
-			grad_store->write(offset, count(), g.data());
-		}
+		if (has_grad_constraints())
+			constrain_dev(device_grad(), grad_clip, grad_max_l1_norm, grad_max_l2_norm);
 	}
 	/** After a fused optimizer step that also cleared the gradient (SGDOptimizer.hpp:69-70). */
 	inline void grad_zeroed_on_device() {
@@ -390,6 +385,16 @@ public:
 private:
 	inline static bool active(Scalar limit) {
 		return NumericUtils<Scalar>::decidedly_greater(limit, (Scalar) 0);
+	}
+	/**
+	 * The constraints on a device array, in place (cattl3_constrain: the device form of enforce_constraints below) --
+	 * a fused optimizer step or a layer's backward pass is followed by this instead of a round trip through the host.
+	 */
+	inline void constrain_dev(Scalar* dev, Scalar clip, Scalar max_l1, Scalar max_l2) const {
+		b200::Context& c = b200::Context::get();
+		b200::Context::Lock l = c.lock();
+		CATTLE_B200_CHECK(b200::Api<Scalar>::constrain(c.handle(), (std::int64_t) count(), active(clip) ? clip : (Scalar) 0,
+				active(max_l1) ? max_l1 : (Scalar) 0, active(max_l2) ? max_l2 : (Scalar) 0, dev));
 	}
 	/**
 	 * The three constraints in the reference's order and with its definitions

@@ -395,6 +395,7 @@ int cattl3_ctx_destroy(cattl3_ctx* ctx) {
 	if (ctx->tc_w) cudaFree(ctx->tc_w);
 	if (ctx->stat_ws) cudaFree(ctx->stat_ws);
 	if (ctx->reg_ws) cudaFree(ctx->reg_ws);
+	if (ctx->con_ws) cudaFree(ctx->con_ws);
 	for (int a = 0; a < ctx->arena_count; ++a)
 		cudaFree(ctx->arenas[a].base);
 	for (int i = 0; i < 8; ++i)

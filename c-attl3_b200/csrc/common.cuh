@@ -27,6 +27,8 @@ struct cattl3_ctx {
 	size_t stat_ws_bytes = 0;
 	// cattl3_regularize: 256 per-block partial penalties + the "blocks done" counter
 	void* reg_ws = nullptr;
+	// cattl3_constrain: 256 per-block partial squared norms, the counter, the scale factor
+	void* con_ws = nullptr;
 	// between cattl3_graph_begin and cattl3_graph_end: the stream is capturing (nothing may synchronise or grow scratch)
 	bool capturing = false;
 	// Step graphs keep their activations in a private arena (graphs with allocation nodes launch slowly): while capturing,

@@ -1008,6 +1008,95 @@ static int regularize(cattl3_ctx* ctx, int64_t count, S l1, S l2, const S* value
 	return CATTL3_OK;
 }
 
+// ---- value / gradient constraints (C-ATTL3/parameters/StandardParameters.hpp:150-182) ------------------------------
+// In the reference's order and with its definitions: clip every element to [-clip, clip]; the "L1" limit is compared with
+// the FROBENIUS norm and rescales by max / norm; the "L2" limit is compared with the SQUARED norm of the result and
+// rescales by max / squared norm.  The second rescaling's squared norm is f1^2 times the first's, so one reduction
+// (of the clipped elements, in double, per-block partials added in block order by the last block: deterministic)
+// decides both factors; a second pass applies their product.  0 switches a limit off.
+template<typename S>
+__global__ void __launch_bounds__(256) constrain_reduce_kernel(long long count, S clip, S max_l1, S max_l2, S* __restrict__ x,
+		double* __restrict__ partial, unsigned int* __restrict__ done, S* __restrict__ factor) {
+	__shared__ double red[256];
+	__shared__ bool last;
+	double sq_sum = 0;
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < count; i += (long long) gridDim.x * 256) {
+		S v = x[i];
+		if (clip > (S) 0) {
+			v = v > clip ? clip : (v < -clip ? -clip : v);
+			x[i] = v;
+		}
+		sq_sum += (double) v * (double) v;
+	}
+	red[threadIdx.x] = sq_sum;
+	__syncthreads();
+	for (int o = 128; o > 0; o >>= 1) {
+		if ((int) threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) {
+		partial[blockIdx.x] = red[0];
+		__threadfence();
+		last = atomicAdd(done, 1u) == gridDim.x - 1;
+	}
+	__syncthreads();
+	if (last && threadIdx.x == 0) {
+		__threadfence();
+		double sq = 0;
+		for (unsigned int b = 0; b < gridDim.x; ++b) sq += ((volatile double*) partial)[b];
+		S f = (S) 1;
+		if (max_l1 > (S) 0) {
+			const S norm = (S) sqrt(sq);
+			if (norm > max_l1) {
+				const S f1 = max_l1 / norm;
+				f = f1;
+				sq *= (double) f1 * (double) f1;
+			}
+		}
+		if (max_l2 > (S) 0) {
+			const S sq_norm = (S) sq;
+			if (sq_norm > max_l2) f *= max_l2 / sq_norm;
+		}
+		*factor = f;
+		*done = 0;   // ready for the next launch
+	}
+}
+template<typename S>
+__global__ void __launch_bounds__(256) constrain_scale_kernel(long long count, const S* __restrict__ factor, S* __restrict__ x) {
+	const S f = *factor;
+	if (f == (S) 1) return;
+	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < count; i += (long long) gridDim.x * 256) x[i] = mul_rn(x[i], f);
+}
+template<typename S>
+static int constrain(cattl3_ctx* ctx, int64_t count, S clip, S max_l1, S max_l2, S* x) {
+	CATTL3_CHECK(check_ctx(ctx));
+	CATTL3_REQUIRE(count > 0 && x && clip >= (S) 0 && max_l1 >= (S) 0 && max_l2 >= (S) 0, "constrain: bad arguments");
+	if (!(clip > (S) 0) && !(max_l1 > (S) 0) && !(max_l2 > (S) 0))
+		return CATTL3_OK;
+	int grid = ew_grid(ctx, count, 1024);
+	if (grid > 256) grid = 256;
+	// scratch shared with cattl3_regularize's layout: 256 partials, a counter, then the factor (one stream: calls are ordered)
+	if (!ctx->con_ws) {
+		CATTL3_REQUIRE(!ctx->capturing, "constrain: first use during graph capture (run the step eagerly first)");
+		CATTL3_CUDA(cudaMalloc(&ctx->con_ws, 258 * sizeof(double)));
+		CATTL3_CUDA(cudaMemsetAsync(ctx->con_ws, 0, 258 * sizeof(double), ctx->stream));
+	}
+	double* ws = (double*) ctx->con_ws;
+	if (max_l1 > (S) 0 || max_l2 > (S) 0) {
+		constrain_reduce_kernel<S><<<grid, 256, 0, ctx->stream>>>(count, clip, max_l1, max_l2, x, ws, (unsigned int*) (ws + 256),
+				(S*) (ws + 257));
+		CATTL3_LAUNCHED(ctx);
+		constrain_scale_kernel<S><<<ew_grid(ctx, count, 256), 256, 0, ctx->stream>>>(count, (const S*) (ws + 257), x);
+		CATTL3_LAUNCHED(ctx);
+	} else {
+		// clip only: no reduction needed; the reduce kernel's first loop does the clipping, its tail is cheap
+		constrain_reduce_kernel<S><<<grid, 256, 0, ctx->stream>>>(count, clip, (S) 0, (S) 0, x, ws, (unsigned int*) (ws + 256),
+				(S*) (ws + 257));
+		CATTL3_LAUNCHED(ctx);
+	}
+	return CATTL3_OK;
+}
+
 // y[i] = value: device-side constants (e.g. the element count that travels with synchronised batch-norm sums) without a
 // host -> device copy, which from pageable memory would synchronise the host with the stream.
 template<typename S>
@@ -1269,6 +1358,10 @@ int cattl3_optimizer_step_indirect_f64(cattl3_ctx* c, int kind, const cattl3_opt
 	CATTL3_REQUIRE(dev_step, "optimizer_step_indirect: null scalars");
 	cattl3_opt_step st = {}; st.kind = kind;
 	return optimizer_step<double>(c, &st, count, p, g, s1, s2, s3, dev_step); }
+int cattl3_constrain_f32(cattl3_ctx* c, int64_t count, float clip, float max_l1, float max_l2, float* x) {
+	return constrain<float>(c, count, clip, max_l1, max_l2, x); }
+int cattl3_constrain_f64(cattl3_ctx* c, int64_t count, double clip, double max_l1, double max_l2, double* x) {
+	return constrain<double>(c, count, clip, max_l1, max_l2, x); }
 int cattl3_add_inplace_f32(cattl3_ctx* c, int64_t count, float* y, const float* x) { return add_inplace<float>(c, count, y, x); }
 int cattl3_add_inplace_f64(cattl3_ctx* c, int64_t count, double* y, const double* x) { return add_inplace<double>(c, count, y, x); }
 int cattl3_muladd_f32(cattl3_ctx* c, int64_t count, int accumulate, const float* a, const float* b, const float* cc, const float* d, float* out) {

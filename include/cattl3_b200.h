@@ -401,6 +401,12 @@ int cattl3_regularize_f32(cattl3_ctx*, int64_t count, float l1, float l2, const 
 int cattl3_regularize_f64(cattl3_ctx*, int64_t count, double l1, double l2, const double* values, double* grad, double* penalty);
 
 /* ---- small element-wise helpers for the network glue ---------------------------------------- */
+/* The constraints of StandardParameters on a device array, values (set_values, StandardParameters.hpp:105-111) or
+ * gradient (accumulate_grad, :115-123), in the reference's order and with its definitions (:150-182): clip every element to
+ * [-clip, clip]; the "L1" limit is compared with the FROBENIUS norm and rescales by max / norm; the "L2" limit is compared
+ * with the SQUARED norm and rescales by max / squared norm.  0 switches a limit off. */
+int cattl3_constrain_f32(cattl3_ctx*, int64_t count, float clip, float max_l1_norm, float max_l2_norm, float* x);
+int cattl3_constrain_f64(cattl3_ctx*, int64_t count, double clip, double max_l1_norm, double max_l2_norm, double* x);
 /* y += x (ResidualNeuralNetwork::propagate, C-ATTL3/neural_network/ResidualNeuralNetwork.hpp:112-117). */
 int cattl3_add_inplace_f32(cattl3_ctx*, int64_t count, float* y, const float* x);
 int cattl3_add_inplace_f64(cattl3_ctx*, int64_t count, double* y, const double* x);

@@ -360,15 +360,30 @@ int cifar_impl(int total, int batch, int epochs, const S* x, const S* obj, const
 			reg = std::make_shared<ElasticNetParameterRegularization<S>>((S) std::atof(spec + 3),
 					(S) std::atof(spec + text.find(',') + 1));
 	}
-	layers.emplace_back(new ConvKernelLayer<S>({ 32u, 32u, 3u }, 8, he, 3, 3, 1, 1, 1, 1, 0, 0, reg));
+	/* tests only: REF_SHIM_CONSTRAINTS = "<value clip>,<value max L1>,<value max L2>,<grad clip>,<grad max L1>,<grad max L2>"
+	 * puts those constraints (StandardParameters.hpp:150-182; 0 = off) on every weight matrix */
+	S con[6] = { 0, 0, 0, 0, 0, 0 };
+	if (const char* spec = std::getenv("REF_SHIM_CONSTRAINTS")) {
+		const char* at = spec;
+		for (int i = 0; i < 6 && at; ++i) {
+			con[i] = (S) std::atof(at);
+			at = std::strchr(at, ',');
+			if (at) ++at;
+		}
+	}
+	layers.emplace_back(new ConvKernelLayer<S>({ 32u, 32u, 3u }, 8, he, 3, 3, 1, 1, 1, 1, 0, 0, reg,
+			con[0], con[1], con[2], con[3], con[4], con[5]));
 	layers.emplace_back(new ReLUActivationLayer<S,3>(layers.back()->get_output_dims()));
 	layers.emplace_back(new MaxPoolLayer<S>(layers.back()->get_output_dims()));
-	layers.emplace_back(new ConvKernelLayer<S>(layers.back()->get_output_dims(), 8, he, 3, 3, 1, 1, 1, 1, 0, 0, reg));
+	layers.emplace_back(new ConvKernelLayer<S>(layers.back()->get_output_dims(), 8, he, 3, 3, 1, 1, 1, 1, 0, 0, reg,
+			con[0], con[1], con[2], con[3], con[4], con[5]));
 	layers.emplace_back(new ReLUActivationLayer<S,3>(layers.back()->get_output_dims()));
 	layers.emplace_back(new MaxPoolLayer<S>(layers.back()->get_output_dims()));
-	layers.emplace_back(new DenseKernelLayer<S,3>(layers.back()->get_output_dims(), 50, glorot, reg));
+	layers.emplace_back(new DenseKernelLayer<S,3>(layers.back()->get_output_dims(), 50, glorot, reg,
+			con[0], con[1], con[2], con[3], con[4], con[5]));
 	layers.emplace_back(new ReLUActivationLayer<S,3>(layers.back()->get_output_dims()));
-	layers.emplace_back(new DenseKernelLayer<S,3>(layers.back()->get_output_dims(), 10, glorot, reg));
+	layers.emplace_back(new DenseKernelLayer<S,3>(layers.back()->get_output_dims(), 10, glorot, reg,
+			con[0], con[1], con[2], con[3], con[4], con[5]));
 	layers.emplace_back(new SoftmaxActivationLayer<S,3>(layers.back()->get_output_dims()));
 	FeedforwardNeuralNetwork<S,3> net(std::move(layers));
 	net.init();
@@ -380,6 +395,11 @@ int cifar_impl(int total, int batch, int epochs, const S* x, const S* obj, const
 			src += p->get_rows() * p->get_cols();
 		}
 	}
+	/* tests only: REF_SHIM_PRMS_LOAD / REF_SHIM_PRMS_SAVE = a directory of .prms files (NeuralNetwork.hpp:195-222,
+	 * EigenProxy.hpp:147-224), read after the injection above / written after training; REF_SHIM_PRMS_TEXT=1 = the text form */
+	const bool prms_binary = std::getenv("REF_SHIM_PRMS_TEXT") == nullptr;
+	if (const char* dir = std::getenv("REF_SHIM_PRMS_LOAD"))
+		net.load_all_unique_params_values(dir, prms_binary);
 	TensorPtr<S,4> obs(new Tensor<S,4>((sz) total, 32u, 32u, 3u));
 	std::memcpy(obs->data(), x, sizeof(S) * obs->size());
 	TensorPtr<S,4> objs(new Tensor<S,4>((sz) total, 1u, 1u, 10u));
@@ -394,10 +414,12 @@ int cifar_impl(int total, int batch, int epochs, const S* x, const S* obj, const
 			opt.train(net, prov, std::atoi(warm));
 	}
 	double t0 = now_ms();
-	S l = opt.train(net, prov, epochs);
+	S l = epochs > 0 ? opt.train(net, prov, epochs) : (S) 0;
 	double t1 = now_ms();
 	if (loss_out) *loss_out = (double) l;
 	if (train_ms) *train_ms = t1 - t0;
+	if (const char* dir = std::getenv("REF_SHIM_PRMS_SAVE"))
+		net.save_all_unique_params_values(dir, prms_binary);
 	if (params_out) {
 		S* dst = params_out;
 		for (auto p : params) {

@@ -185,6 +185,9 @@ def seqnet_inputs(dtype, total=16, seq=3, hw=8, state=4, seed=5001):
 SEQNET_SMALL = dict(width=4, state=4)
 
 
+# REF_SHIM_CONSTRAINTS: value clip / Frobenius ("L1") / squared-norm ("L2") limits and the same three on the gradient, on every
+# weight matrix of the config-1 network; chosen so that each of the six is active on the seeded parameters and gradients
+CIFAR_CON = "0.05,0.8,0.5,0.00003,0.0003,0.0000001"
 CIFAR_REG = "en:0.003,0.01"   # REF_SHIM_REG: ElasticNet (l1, l2) on every weight matrix of the config-1 network
 
 

@@ -52,6 +52,13 @@ def main():
         out["cifar_reg/%s/p1" % suf] = p1
         out["cifar_reg/%s/loss" % suf] = np.array([loss_reg])
         print(suf, "cifar + ElasticNet loss", loss_reg)
+        # config 1 with all six constraints of StandardParameters on every weight matrix (REF_SHIM_CONSTRAINTS, tests only)
+        os.environ["REF_SHIM_CONSTRAINTS"] = C.CIFAR_CON
+        p1, loss_con, _ = ref.train_cifar(x, obj, 16, 2, params_in=np.ascontiguousarray(vectors["cifar/%s/p0" % suf]))
+        del os.environ["REF_SHIM_CONSTRAINTS"]
+        out["cifar_con/%s/p1" % suf] = p1
+        out["cifar_con/%s/loss" % suf] = np.array([loss_con])
+        print(suf, "cifar + constraints loss", loss_con)
         print(suf, "autoencoder params", out["autoencoder/%s/p1" % suf].size, "resnet params", n, "loss", loss)
     path = os.path.join(HERE, "reference_networks.npz")
     np.savez_compressed(path, **out)

@@ -234,6 +234,94 @@ def test_regularised_training_matches_reference(golden, golden_nets, dt):
     assert C.relerr(outs[0][:-1], outs[1][:-1]) < (1e-6 if dt == np.float32 else 1e-13)
 
 
+def _run_cifar_shim(shim_path, dt, env, epochs, out_path, load_p0=True):
+    """The config-1 driver of oracle/ref_shim.cpp in a fresh process (its REF_SHIM_* switches are read from the environment)."""
+    suf = "f32" if dt == np.float32 else "f64"
+    code = (
+        "import os, sys, numpy as np; sys.path[:0] = [%r, %r]\n"
+        "import cases as C; from oracle import binding\n"
+        "lib = binding.Oracle('ref', path=%s); dt = np.%s\n"
+        "x, obj = C.cifar_inputs(dt)\n"
+        "p0 = np.ascontiguousarray(np.load(%r)['cifar/%s/p0']) if %r else None\n"
+        "p, l, _ = lib.train_cifar(x, obj, 16, %d, params_in=p0)\n"
+        "np.save(sys.argv[1], np.concatenate([np.asarray(p, dtype=np.float64).ravel(), [l]]))\n"
+        % (ROOT, os.path.join(ROOT, "tests"), repr(shim_path) if shim_path else "None", np.dtype(dt).name,
+           os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"), suf, load_p0, epochs))
+    r = subprocess.run([os.sys.executable, "-c", code, out_path], env=dict(os.environ, **env), capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return np.load(out_path), r.stderr
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_constrained_training_matches_reference(golden_nets, dt):
+    """Config 1 with all six constraints of StandardParameters on every weight matrix (REF_SHIM_CONSTRAINTS; value clip,
+    the Frobenius-norm "L1" limit, the squared-norm "L2" limit and the same three on the gradient,
+    StandardParameters.hpp:150-182): on the B200 build they run as cattl3_constrain behind each backward pass and each
+    optimizer step, also inside the captured step graph.  Parameters and loss against the unmodified reference."""
+    import tempfile
+    suf = "f32" if dt == np.float32 else "f64"
+    outs = []
+    with tempfile.TemporaryDirectory() as d:
+        for i, env in enumerate(({"CATTL3_GRAPH_TRACE": "1"}, {"CATTL3_NO_GRAPH": "1"})):
+            o, err = _run_cifar_shim(SHIM, dt, dict(env, REF_SHIM_CONSTRAINTS=C.CIFAR_CON), 2, os.path.join(d, "p%d.npy" % i))
+            if i == 0:
+                assert "step graph captured" in err, "constrained parameters kept the step out of the graph:\n" + err[-2000:]
+            outs.append(o)
+    ref_p, ref_loss = golden_nets["cifar_con/%s/p1" % suf], float(golden_nets["cifar_con/%s/loss" % suf][0])
+    e = C.relerr(outs[0][:-1], ref_p)
+    print("config 1 + six constraints, 8 Nadam steps: loss %.6f (ref %.6f), param err %.2e, graph vs eager %.2e"
+          % (outs[0][-1], ref_loss, e, C.relerr(outs[0][:-1], outs[1][:-1])))
+    assert e < (1e-4 if dt == np.float32 else 1e-10)
+    assert abs(outs[0][-1] - ref_loss) < (1e-4 if dt == np.float32 else 1e-10) * max(1.0, abs(ref_loss))
+    assert C.relerr(outs[0][:-1], outs[1][:-1]) < (1e-6 if dt == np.float32 else 1e-13)
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_prms_files_round_trip_and_interoperate_with_the_reference(dt, text=False):
+    """NeuralNetwork::save_all_unique_params_values / load_all_unique_params_values (NeuralNetwork.hpp:195-222; binary .prms
+    format of EigenProxy.hpp:147-224) through B200Parameters: a trained B200 network's files load back bit-identical into a
+    fresh B200 network AND into the unmodified reference, the files the reference writes for the same parameters are
+    byte-identical, and a reference-written directory loads into the B200 build.  (The reference's TEXT form does not round
+    trip in the reference itself: serialize() writes sizeof(Scalar) first, EigenProxy.hpp:117, deserialize() does not read
+    it, :176-179 -- that code is the reference's own on both sides and is left alone.)"""
+    import filecmp
+    import tempfile
+    from oracle import binding
+    tol_text = 1e-5 if dt == np.float32 else 1e-5   # operator<< prints 6 significant digits
+    fmt = {"REF_SHIM_PRMS_TEXT": "1"} if text else {}
+    with tempfile.TemporaryDirectory() as d:
+        a, b, c = (os.path.join(d, n) for n in ("saved_by_b200", "saved_by_ref", "resaved_by_b200"))
+        for p in (a, b, c):
+            os.mkdir(p)
+        # train one epoch on the B200 and save
+        trained, _ = _run_cifar_shim(SHIM, dt, dict(fmt, REF_SHIM_PRMS_SAVE=a), 1, os.path.join(d, "t.npy"))
+        files = sorted(os.listdir(a))
+        assert len(files) == 8 and all(f.endswith(".prms") for f in files), files
+        # a fresh B200 network (random init, no injected parameters) loads them
+        loaded, _ = _run_cifar_shim(SHIM, dt, dict(fmt, REF_SHIM_PRMS_LOAD=a, REF_SHIM_PRMS_SAVE=c), 0, os.path.join(d, "l.npy"),
+                                    load_p0=False)
+        if text:
+            assert C.relerr(loaded[:-1], trained[:-1]) < tol_text
+        else:
+            assert np.array_equal(loaded[:-1], trained[:-1])
+            for f in files:
+                assert filecmp.cmp(os.path.join(a, f), os.path.join(c, f), shallow=False), f
+        if binding.have_ref():
+            # the unmodified reference reads the B200's files, writes its own: same parameters, same bytes
+            ref_loaded, _ = _run_cifar_shim(None, dt, dict(fmt, REF_SHIM_PRMS_LOAD=a, REF_SHIM_PRMS_SAVE=b), 0,
+                                            os.path.join(d, "r.npy"), load_p0=False)
+            if text:
+                assert C.relerr(ref_loaded[:-1], trained[:-1]) < tol_text
+            else:
+                assert np.array_equal(ref_loaded[:-1], trained[:-1])
+            for f in files:
+                assert filecmp.cmp(os.path.join(a if not text else c, f), os.path.join(b, f), shallow=False), f
+            # and a directory written by the reference loads into the B200 build
+            back, _ = _run_cifar_shim(SHIM, dt, dict(fmt, REF_SHIM_PRMS_LOAD=b), 0, os.path.join(d, "k.npy"), load_p0=False)
+            assert np.array_equal(back[:-1], ref_loaded[:-1])
+
+
 @pytest.mark.parametrize("dt", DTYPES)
 def test_config5_sequence_network_training_matches_reference(b200, golden_nets, dt):
     """BASELINE.json configs[4] at test size: SequentialNeuralNetwork{ParallelNeuralNetwork of conv lanes,
