@@ -827,6 +827,8 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 struct TcWgradParams {
 	int N, OH, OW, R, J, RH, RW;
 	int ah, bh, ch, aw, bw, cw;
+	int tapbox;        // few channels: ONE box [32 m][RH][RWp][R] per k-block holds every (tap, channel) row; RWp = tap_wp
+	int tap_wp;
 	int RB;            // channel rows per TMA box (16 / 32 / 64)
 	int rchunks;       // r_pad / RB
 	int boxes;         // T * rchunks
@@ -904,7 +906,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 			// tap offsets and channel origins are tabulated once, and the k-block's (n0, oh, ow) advances incrementally
 			// (the 64-bit divisions this loop used to do per k-block made it as slow as the MMAs it feeds).
 			int s = 0; uint32_t ph = 0;
-			const uint32_t tx = (uint32_t) (nboxes * p.RB * WG_KB * 4);
+			const uint32_t tx = p.tapbox ? (uint32_t) (p.RH * p.tap_wp * p.R * WG_KB * 4) : (uint32_t) (nboxes * p.RB * WG_KB * 4);
 			int* box_tab = reinterpret_cast<int*>(bars + 40);   // [12][3]: dh, dw, c0 (behind the barriers and the TMEM slot)
 			for (int bx = 0; bx < nboxes; ++bx) {
 				const int box = box0 + bx;
@@ -914,6 +916,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 				box_tab[3 * bx + 1] = rw * p.bw + p.cw;
 				box_tab[3 * bx + 2] = (box % p.rchunks) * p.RB;
 			}
+			if (p.tapbox) { box_tab[0] = p.ch; box_tab[1] = p.cw; box_tab[2] = 0; }   // the one box starts at tap (0, 0), channel 0
 			const long long m_first = mg0 * WG_KB;
 			int n0 = (int) (m_first % p.N);
 			const long long pix0 = m_first / p.N;
@@ -1129,8 +1132,12 @@ __global__ void __launch_bounds__(32 * WR_ZL) wgrad_reduce_tc_kernel(const TcWgr
 			const int r = (int) ((i / p.J) % p.R);
 			const int tap = (int) (i / ((long long) p.J * p.R));
 			const int box = tap * p.rchunks + r / p.RB;
-			const int ct = box / p.boxes_per_tile;
-			const int col = (box % p.boxes_per_tile) * p.RB + r % p.RB;
+			int ct = box / p.boxes_per_tile;
+			int col = (box % p.boxes_per_tile) * p.RB + r % p.RB;
+			if (p.tapbox) {   // rows of the tap box: tap row fastest, then tap column, then channel (the tensor's own order)
+				ct = 0;
+				col = tap % p.RH + p.RH * (tap / p.RH + p.tap_wp * r);
+			}
 			const int jt = j / TC_BM, row = j % TC_BM;
 			src = p.partial + ((long long) (ct + p.col_tiles * jt) * p.BNW + col) * 128 + row;
 			z_stride = (long long) tiles * p.BNW * 128;
@@ -1158,9 +1165,23 @@ __global__ void __launch_bounds__(32 * WR_ZL) wgrad_reduce_tc_kernel(const TcWgr
 	}
 }
 
+// Few channels (the 3-channel stem of config 4): with undilated taps the RH x RW x C patch of a pixel is a BOX of the
+// source tensor, so one TMA box [32 m][RH][RWp][C] delivers every (tap, channel) row of a k-block -- no zero-padded
+// 16-channel boxes per tap (5.3x the MMAs and 16 boxes for a 7 x 7 x 3 stem), one accumulator tile for the whole dW.
+// RWp >= RW makes the row count a multiple of 8 (whole swizzle atoms); the extra columns map to no weight.
+static int tapbox_wp(const GatherGeom& gg) {
+	if (gg.SC >= 16 || gg.bh != 1 || gg.bw != 1 || getenv("CATTL3_NO_TC_STEM")) return 0;
+	for (int wp = gg.RW; wp <= gg.RW + 8; ++wp) {
+		const int rows = gg.RH * wp * gg.SC;
+		if (rows % 8 == 0 && rows <= 192 && wp <= gg.SW + 8) return wp;
+	}
+	return 0;
+}
+
 bool tc_wgrad_supported(const cattl3_ctx*, const GatherGeom& gg) {
 	if (gg.N % 32 != 0 || gg.denh != 1 || gg.denw != 1) return false;
-	if (gg.SC < 16 || gg.J < 16) return false;
+	if (gg.J < 16) return false;
+	if (gg.SC < 16 && (gg.RH * gg.RW < 9 || tapbox_wp(gg) == 0)) return false;
 	const long long M = (long long) gg.N * gg.OH * gg.OW;
 	if (M >= (1ll << 31)) return false;  // TMA coordinates are 32-bit
 	return get_encode() != nullptr;
@@ -1174,7 +1195,8 @@ int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const 
 	// CTA pairs (cta_group::2): 256 output channels per unit, each CTA loading and splitting half of the gathered tile --
 	// half the shared-memory traffic per MMA.  Needs a second 128-row tile of output channels to pair with.
 	static const bool no_pairs = (pair_mask() & 2) == 0;
-	const int ctas = (!no_pairs && gg.J > TC_BM) ? 2 : 1;
+	const int tap_wp = gg.SC < 16 ? tapbox_wp(gg) : 0;
+	const int ctas = (!no_pairs && gg.J > TC_BM && !tap_wp) ? 2 : 1;   // (a tap box is one TMA box: not split over a pair)
 	// boxes of 32 channel rows for a pair (a tile of 192 columns = 6 boxes, 3 per CTA)
 	const int RB = (ctas == 1 && r_pad % 64 == 0) ? 64 : (r_pad % 32 == 0 ? 32 : 16);
 
@@ -1183,6 +1205,7 @@ int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const 
 		cuuint64_t dims[4] = { (cuuint64_t) gg.N, (cuuint64_t) gg.SH, (cuuint64_t) gg.SW, (cuuint64_t) gg.SC };
 		cuuint64_t str[3] = { (cuuint64_t) gg.N * 4, (cuuint64_t) gg.N * gg.SH * 4, (cuuint64_t) gg.N * gg.SH * gg.SW * 4 };
 		cuuint32_t box[4] = { (cuuint32_t) WG_KB, 1, 1, (cuuint32_t) RB };
+		if (tap_wp) { box[1] = (cuuint32_t) gg.RH; box[2] = (cuuint32_t) tap_wp; box[3] = (cuuint32_t) gg.SC; }
 		CATTL3_CHECK(encode_map(&tm_b, src, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
 	}
 
@@ -1196,6 +1219,12 @@ int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const 
 	if (ctas == 2 && p.boxes_per_tile % 2) ++p.boxes_per_tile;     // each CTA of a pair takes half of a tile's boxes
 	p.col_tiles = (p.boxes + p.boxes_per_tile - 1) / p.boxes_per_tile;
 	p.BNW = p.boxes_per_tile * RB;
+	p.tapbox = tap_wp ? 1 : 0; p.tap_wp = tap_wp;
+	if (tap_wp) {
+		// one box, one column tile: the accumulator holds the whole (padded) dW of this j tile
+		p.boxes = 1; p.boxes_per_tile = 1; p.col_tiles = 1;
+		p.BNW = round_up(gg.RH * tap_wp * gg.SC, 16);
+	}
 	if (ctas == 2 && p.BNW % 32) { set_error("wgrad: pair tile of %d columns", p.BNW); return CATTL3_ERR_UNSUPPORTED; }
 	p.j_tiles = round_up((gg.J + TC_BM - 1) / TC_BM, ctas);   // 128-row tiles, whole pairs
 	p.mgroups = M / WG_KB;
