@@ -228,16 +228,22 @@ __device__ __forceinline__ uint32_t tf32_lo_bits(float v) {
 
 // The weights of the gather GEMM -- its shared-memory operand -- are split once in HBM while being repacked
 // K-major as [part][tap][j_pad][r_pad] (r contiguous, zero padded; part 0 = hi, 1 = lo).
-__global__ void __launch_bounds__(256) pack_weights_kernel(GatherGeom gg, int r_pad, int j_pad, const float* __restrict__ w,
+// tapbox: the k-blocks are tap ROWS; element r of k-block rh is tap column r % RW of channel r / RW (the row order of
+// the TMA box [n][1][RW][C] the activations arrive in).
+__global__ void __launch_bounds__(256) pack_weights_kernel(GatherGeom gg, int r_pad, int j_pad, int tapbox, const float* __restrict__ w,
 		float* __restrict__ packed) {
-	const int T = gg.RH * gg.RW;
+	const int T = tapbox ? gg.RH : gg.RH * gg.RW;
 	const long long total = (long long) T * j_pad * r_pad;
 	for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long) gridDim.x * 256) {
 		const int r = (int) (i % r_pad);
 		const int j = (int) ((i / r_pad) % j_pad);
 		const int tap = (int) (i / ((long long) r_pad * j_pad));
 		float v = 0.f;
-		if (r < gg.SC && j < gg.J) {
+		if (tapbox) {
+			if (r < gg.RW * gg.SC && j < gg.J)
+				v = w[gg.w_off + tap * gg.w_stap + (r % gg.RW) * (gg.w_srw ? gg.w_srw : gg.w_stap * gg.RH) + (r / gg.RW) * gg.w_sr +
+						j * gg.w_sj];
+		} else if (r < gg.SC && j < gg.J) {
 			const int rh = tap % gg.RH, rw = tap / gg.RH;
 			v = w[gg.w_off + rh * gg.w_stap + rw * (gg.w_srw ? gg.w_srw : gg.w_stap * gg.RH) + r * gg.w_sr + j * gg.w_sj];
 		}
@@ -267,6 +273,7 @@ struct TcGemmParams {
 	int BN;          // filter tile (multiple of 16, <= 256)
 	int r_pad;       // reduce channels, padded to a multiple of KB
 	int nb;          // batch entries per A box (32 / 64 / 128): a tile is 128 / nb boxes of [nb n][KB channels]
+	int a_rows;      // rows a TMA box of A delivers (KB; fewer for a tap box [nb n][1][RW][C]: the rest of the tile stays zero)
 	int stages, nacc;
 	int bias_mode;
 	const float* bias;
@@ -331,6 +338,13 @@ __global__ void __launch_bounds__((2 + NEPI + NCONV) * 32, 1) tc_gather_gemm_ker
 		for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], NEPI * CTAS); }
 		fence_barrier_init();
 	}
+	if (p.a_rows < KB) {
+		// tap boxes fill only the first a_rows k-rows of a tile: the others are zero for the whole kernel
+		for (int s = 0; s < p.stages; ++s) {
+			float4* a = reinterpret_cast<float4*>(smem + (size_t) s * stage_bytes);
+			for (int i = threadIdx.x; i < A_BYTES / 16; i += blockDim.x) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+		}
+	}
 	if (warp == 1) tmem_alloc<CTAS>(tmem_slot, 512u);
 	tc_fence_before();
 	if (CTAS == 2) cluster_sync(); else __syncthreads();   // the peer's barriers exist before anything arrives on them
@@ -361,7 +375,7 @@ __global__ void __launch_bounds__((2 + NEPI + NCONV) * 32, 1) tc_gather_gemm_ker
 				for (int kb = 0; kb < kblocks; ++kb) {
 					mbar_wait(&empty[s], ph ^ 1);
 					uint8_t* st = smem + (size_t) s * stage_bytes;
-					mbar_expect_tx(&full[s], (uint32_t) stage_bytes);
+					mbar_expect_tx(&full[s], (uint32_t) (TC_BM * p.a_rows * 4 + 2 * b_bytes));
 					#pragma unroll
 					for (int g = 0; g < 4; ++g) {
 						if (g < ngroups) {
@@ -704,7 +718,6 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 	const bool want_act = ep && ep->act_kind != CATTL3_ACT_NONE;
 	CATTL3_REQUIRE(out || want_act, "gather GEMM: no output tensor");
 	CATTL3_REQUIRE(!want_stats || bias_mode == 1, "column statistics need a per-column bias");
-	const int T = gg.RH * gg.RW;
 	// 256-wide tiles leave room for ONE accumulator only, so the epilogue sits on the critical path: with column
 	// statistics (the longest epilogue) take 128-wide tiles, whose two accumulators let it hide behind the next
 	// tile's MMAs (profiles/README.md, r1e)
@@ -716,18 +729,22 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 	const int ctas = (!no_pairs && M > TC_BM && (gg.J >= 256 || round_up(gg.J, 16) % 32 == 0)) ? 2 : 1;
 	const int BN = gg.J >= 256 ? (want_stats_early ? 128 : 256) : round_up(gg.J, 16);
 	// 32-element k-blocks (128 B weight rows) where shared and tensor memory allow four stages of them
-	const int KB = (BN / ctas <= 128 && gg.SC > 16) ? 32 : 16;
-	const int r_pad = round_up(gg.SC, KB);
+	// few channels with unit tap steps along W: one TMA box [nb n][1][RW][C] per tap ROW instead of a zero-padded 16-channel
+	// box per tap (a 7 x 7 x 3 stem: 7 k-blocks of 21 useful rows instead of 49 of 3)
+	const bool tapbox = gg.SC < 16 && gg.bw == 1 && gg.RW > 1 && gg.RW * gg.SC <= 32 && !getenv("CATTL3_NO_TAPBOX");
+	const int KB = tapbox ? (gg.RW * gg.SC > 16 ? 32 : 16) : (BN / ctas <= 128 && gg.SC > 16) ? 32 : 16;
+	const int r_pad = tapbox ? KB : round_up(gg.SC, KB);
 	// the A operand goes through registers into tensor memory, so its shared-memory image needs no MMA layout:
 	// take the longest contiguous run of batch entries TMA can deliver per row (up to 128 = 512 B)
 	const int nb = gg.N % 128 == 0 ? 128 : (gg.N % 64 == 0 ? 64 : 32);
 	const int j_tiles = (gg.J + BN - 1) / BN;
 	const int j_pad = j_tiles * BN;
+	const int T = tapbox ? gg.RH : gg.RH * gg.RW;   // k-blocks per channel chunk
 	const long long w_elems = (long long) T * j_pad * r_pad;
 
 	CATTL3_CHECK(ensure_buffer(ctx, &ctx->tc_w, &ctx->tc_w_bytes, (size_t) w_elems * 8));
 	float* w_packed = (float*) ctx->tc_w;
-	pack_weights_kernel<<<ew_grid(ctx, w_elems, 256), 256, 0, ctx->stream>>>(gg, r_pad, j_pad, w, w_packed);
+	pack_weights_kernel<<<ew_grid(ctx, w_elems, 256), 256, 0, ctx->stream>>>(gg, r_pad, j_pad, tapbox ? 1 : 0, w, w_packed);
 	CATTL3_LAUNCHED(ctx);
 
 	CUtensorMap tm_a, tm_b;
@@ -735,6 +752,7 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 		cuuint64_t dims[4] = { (cuuint64_t) gg.N, (cuuint64_t) gg.SH, (cuuint64_t) gg.SW, (cuuint64_t) gg.SC };
 		cuuint64_t str[3] = { (cuuint64_t) gg.N * 4, (cuuint64_t) gg.N * gg.SH * 4, (cuuint64_t) gg.N * gg.SH * gg.SW * 4 };
 		cuuint32_t box[4] = { (cuuint32_t) nb, 1, 1, (cuuint32_t) KB };
+		if (tapbox) { box[2] = (cuuint32_t) gg.RW; box[3] = (cuuint32_t) gg.SC; }
 		CATTL3_CHECK(encode_map(&tm_a, src, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE));
 	}
 	{
@@ -746,7 +764,8 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 	}
 
 	TcGemmParams p;
-	p.N = gg.N; p.OH = gg.OH; p.OW = gg.OW; p.J = gg.J; p.RH = gg.RH; p.RW = gg.RW;
+	p.N = gg.N; p.OH = gg.OH; p.OW = gg.OW; p.J = gg.J; p.RH = gg.RH; p.RW = tapbox ? 1 : gg.RW;
+	p.a_rows = tapbox ? gg.RW * gg.SC : KB;
 	p.ah = gg.ah; p.bh = gg.bh; p.ch = gg.ch; p.aw = gg.aw; p.bw = gg.bw; p.cw = gg.cw;
 	p.M = M;
 	p.h0 = gg.out_h0; p.hs = gg.out_hs; p.w0 = gg.out_w0; p.ws = gg.out_ws;
