@@ -184,6 +184,76 @@ def run_reference(args, rank):
     print(json.dumps(line))
 
 
+def pin_to_gpu_numa_node(index):
+    """Runs this rank on the CPU cores next to its GPU (NVML's ideal affinity) BEFORE any pinned host memory is allocated:
+    first touch then places the staging buffers of the host-buffer path on the GPU's own NUMA node, so that eight ranks
+    streaming 2 GB per step each do not all cross the socket interconnect.  Returns the number of cores, or None."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = nv.nvmlDeviceGetCpuAffinity(h, words)
+        cores = [64 * w + b for w in range(words) for b in range(64) if (mask[w] >> b) & 1]
+        allowed = sorted(set(cores) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return len(allowed)
+    except Exception:
+        pass
+    return None
+
+
+def double_extras(ctx, pkg, torch, dev, stream):
+    """BASELINE.json configs[1] names float AND double: the same layer at the same size in double (FP64 tensor cores,
+    mma.sync m8n8k4 -- tcgen05 has no fp64 kind), each pass timed alone, against the DMMA rate scripts/dmma_peak measures now."""
+    import subprocess
+    g = pkg.ConvGeom(*GEOM)
+    gen = torch.Generator(device=dev).manual_seed(4001)
+    x = torch.rand(M * C, device=dev, generator=gen, dtype=torch.float64) * 2 - 1
+    dy = torch.rand(M * F, device=dev, generator=gen, dtype=torch.float64) * 2 - 1
+    w = torch.randn(K * F, device=dev, generator=gen, dtype=torch.float64) * (2.0 / K) ** 0.5
+    b = torch.zeros(F, device=dev, dtype=torch.float64)
+    y = torch.empty(M * F, device=dev, dtype=torch.float64)
+    dx = torch.empty(M * C, device=dev, dtype=torch.float64)
+    dw, db = torch.zeros(K * F, device=dev, dtype=torch.float64), torch.zeros(F, device=dev, dtype=torch.float64)
+
+    def time_alone(fn, reps=2):
+        fn()
+        torch.cuda.synchronize()
+        a, bb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        bb.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(bb) / reps
+
+    t = {"forward": time_alone(lambda: ctx.conv_forward(g, x, w, b, y))}
+    path = ctx.last_path
+    t["weight+bias gradient"] = time_alone(lambda: ctx.conv_backward(g, x, w, dy, dw, db, None))
+    t["input gradient"] = time_alone(lambda: ctx.conv_backward(g, x, w, dy, None, None, dx))
+    del x, dy, y, dx
+    torch.cuda.empty_cache()
+    peak = None
+    exe = os.path.join(ROOT, "scripts", "dmma_peak")
+    if os.path.exists(exe):
+        try:
+            peak = json.loads(subprocess.run([exe], capture_output=True, text=True, timeout=60).stdout.strip().splitlines()[-1])[
+                "dmma_m8n8k4_tflops"]
+        except Exception:
+            peak = None
+    out = {"dtype": "f64", "kernel_path": path, "peak_tflops": peak,
+           "peak_source": "scripts/dmma_peak (mma.sync.m8n8k4.f64 chains on every SM) run now" if peak else "not measured",
+           "kernels": []}
+    for name, ms in t.items():
+        ach = FLOP_PER_PASS / (ms * 1e-3) / 1e12
+        out["kernels"].append({"pass": name, "ms": round(ms, 3), "achieved_tflops": round(ach, 2),
+                               "frac": round(ach / peak, 4) if peak else None})
+    out["samples_per_s"] = round(N_BATCH / (sum(t.values()) * 1e-3), 1)
+    return out
+
+
 def network_extras(world):
     import importlib.util
     spec = importlib.util.spec_from_file_location("bench_networks", os.path.join(ROOT, "scripts", "bench_networks.py"))
@@ -209,6 +279,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--path", type=int, default=0, help="0 auto (tcgen05), 1 SIMT only")
     ap.add_argument("--no-networks", action="store_true", help="skip the network-level extras (configs 4 and 5)")
+    ap.add_argument("--no-double", action="store_true", help="skip the double-precision extras (N = 1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -224,6 +295,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa_cores = pin_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -388,7 +460,7 @@ def main():
                    "conv_tflops_per_gpu": round(3 * FLOP_PER_PASS / (ms_per_step * 1e-3) / 1e12, 2)},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "api": "cattl3_conv_forward_host_async_f32 + cattl3_conv_backward_host_async_f32 + optimizer step + "
+                "steps": e2e_steps, "host_cores_near_gpu": numa_cores, "api": "cattl3_conv_forward_host_async_f32 + cattl3_conv_backward_host_async_f32 + optimizer step + "
                        "cattl3_host_wait per step (uploads / kernels / downloads pipelined over filter chunks on three streams)"},
         "gpu_launches": launches,
         "roofline": roofline,
@@ -399,6 +471,8 @@ def main():
         v, cores, kind, desc = reference_sample(32, 2, keep)
         line["cpu_baseline"] = {"value": round(v, 2), "unit": "samples/s", "cores": cores, "kind": kind, "sample": desc}
         line["parity"] = parity_against(ctx, pkg, keep, 32)
+    if rank == 0 and world == 1 and not args.no_double:
+        line["double"] = double_extras(ctx, pkg, torch, dev, stream)
     if comm is not None:
         comm.destroy()
     if not args.no_networks:

@@ -30,6 +30,7 @@ struct NcclApi {
 	int (*GroupStart)() = nullptr;
 	int (*GroupEnd)() = nullptr;
 	int (*CommSplit)(NcclComm, int, int, NcclComm*, void*) = nullptr;   // NCCL >= 2.18; optional
+	int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;   // optional (peer-memory set-up)
 	const char* (*GetErrorString)(int) = nullptr;
 };
 
@@ -52,6 +53,7 @@ NcclApi* nccl() {
 			api.GroupEnd = (int (*)()) dlsym(api.lib, "ncclGroupEnd");
 			api.GetErrorString = (const char* (*)(int)) dlsym(api.lib, "ncclGetErrorString");
 			api.CommSplit = (int (*)(NcclComm, int, int, NcclComm*, void*)) dlsym(api.lib, "ncclCommSplit");
+			api.AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t)) dlsym(api.lib, "ncclAllGather");
 			if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.GroupStart ||
 					!api.GroupEnd) {
 				dlclose(api.lib);
@@ -70,6 +72,53 @@ int nccl_fail(int rc, const char* what) {
 
 #define CATTL3_NCCL(call, what) do { int rc__ = (call); if (rc__ != NCCL_SUCCESS) return nccl_fail(rc__, what); } while (0)
 
+// ---- one-shot all-reduce of short vectors over NVLink peer memory ---------------------------------------------------
+// The statistics of a synchronised BatchNorm layer are 2 C + 1 doubles per direction, dozens of times per step: far below
+// the size where NCCL's ring / tree protocols pay, and each ncclAllReduce costs its launch plus a multi-hop handshake.
+// Every rank owns a mailbox in its HBM that its peers map (cudaIpc; NVSwitch makes every peer one hop away): a rank
+// WRITES its vector into its lane of every mailbox, raises a flag there, waits until its own mailbox has every lane's
+// flag and adds the lanes in rank order -- the same order on every rank, so the results are bit-identical everywhere.
+// One kernel of one CTA, no intermediate hops.  Two slots alternate: a rank can run at most one call ahead of its
+// slowest peer (it needs that peer's flag of the current call to finish it), so the slot it writes next is never the
+// one a peer still reads.  The call counter lives in the mailbox and is advanced by the kernel itself, so a captured
+// step graph replays correctly.
+constexpr int PEER_MAX_RANKS = 8, PEER_MAX_BYTES = 16384, PEER_SLOTS = 2;
+struct PeerMailbox {
+	unsigned long long epoch;                                           // calls completed by the owner
+	unsigned long long pad[15];
+	unsigned long long flags[PEER_SLOTS][PEER_MAX_RANKS * 16];          // [slot][lane * 16]: the call number the lane's data belong to (a line each)
+	unsigned char data[PEER_SLOTS][PEER_MAX_RANKS][PEER_MAX_BYTES];
+};
+struct PeerTable { PeerMailbox* box[PEER_MAX_RANKS]; };
+
+template<typename T>
+__global__ void __launch_bounds__(256) peer_allreduce_kernel(T* __restrict__ buf, int count, int rank, int world, PeerTable peers) {
+	PeerMailbox* mine = peers.box[rank];
+	const unsigned long long call = mine->epoch + 1;
+	const int slot = (int) (call & 1);
+	for (int r = 0; r < world; ++r) {
+		T* lane = reinterpret_cast<T*>(peers.box[r]->data[slot][rank]);
+		for (int i = threadIdx.x; i < count; i += 256) lane[i] = buf[i];
+	}
+	__threadfence_system();
+	__syncthreads();
+	if ((int) threadIdx.x < world)
+		*reinterpret_cast<volatile unsigned long long*>(&peers.box[threadIdx.x]->flags[slot][rank * 16]) = call;
+	if ((int) threadIdx.x < world) {
+		const volatile unsigned long long* flag = &mine->flags[slot][threadIdx.x * 16];
+		while (*flag != call) { }
+		__threadfence_system();
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < count; i += 256) {
+		T sum = reinterpret_cast<const volatile T*>(mine->data[slot][0])[i];
+		for (int r = 1; r < world; ++r) sum += reinterpret_cast<const volatile T*>(mine->data[slot][r])[i];
+		buf[i] = sum;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) mine->epoch = call;
+}
+
 } // namespace
 
 struct cattl3_comm {
@@ -85,7 +134,60 @@ struct cattl3_comm {
 	cudaStream_t side = nullptr;
 	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 	bool pending = false;
+	// peer-memory mailboxes for short vectors (null: not set up, every exchange goes through NCCL)
+	PeerMailbox* mailbox = nullptr;
+	PeerTable peers = {};
+	bool peer_ok = false;
 };
+
+// Maps every rank's mailbox into this process.  Any failure leaves peer_ok false (NCCL carries everything).
+static void peer_setup(cattl3_comm* c) {
+	NcclApi* n = nccl();
+	if (!n || !n->AllGather || c->world > PEER_MAX_RANKS || getenv("CATTL3_NO_PEER_REDUCE"))
+		return;
+	// (every rank reaches the two collectives below whatever fails locally: env and world size are the same everywhere)
+	bool ok = cudaMalloc((void**) &c->mailbox, sizeof(PeerMailbox)) == cudaSuccess;
+	if (!ok) { cudaGetLastError(); c->mailbox = nullptr; }
+	cudaIpcMemHandle_t mine;
+	if (ok) {
+		cudaMemset(c->mailbox, 0, sizeof(PeerMailbox));
+		ok = cudaIpcGetMemHandle(&mine, c->mailbox) == cudaSuccess;
+	}
+	// every rank takes part in the gather whatever happened locally (a rank that failed sends a zero handle)
+	unsigned char* dev = nullptr;
+	const size_t hb = sizeof(cudaIpcMemHandle_t) + 8;
+	unsigned char host[(sizeof(cudaIpcMemHandle_t) + 8) * PEER_MAX_RANKS] = {};
+	unsigned char rec[sizeof(cudaIpcMemHandle_t) + 8] = {};
+	if (ok) { memcpy(rec, &mine, sizeof(mine)); rec[sizeof(mine)] = 1; }
+	if (cudaMalloc((void**) &dev, hb * (c->world + 1)) != cudaSuccess) { cudaGetLastError(); return; }
+	cudaMemcpy(dev, rec, hb, cudaMemcpyHostToDevice);
+	const int rc = n->AllGather(dev, dev + hb, hb, /* ncclChar */ 0, c->comm, c->ctx->stream);
+	if (rc != NCCL_SUCCESS || cudaStreamSynchronize(c->ctx->stream) != cudaSuccess) { cudaGetLastError(); cudaFree(dev); return; }
+	cudaMemcpy(host, dev + hb, hb * c->world, cudaMemcpyDeviceToHost);
+	cudaFree(dev);
+	for (int r = 0; r < c->world; ++r) ok = ok && host[r * hb + sizeof(cudaIpcMemHandle_t)] == 1;
+	for (int r = 0; ok && r < c->world; ++r) {
+		if (r == c->rank) { c->peers.box[r] = c->mailbox; continue; }
+		cudaIpcMemHandle_t h;
+		memcpy(&h, host + r * hb, sizeof(h));
+		void* p = nullptr;
+		if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+		c->peers.box[r] = (PeerMailbox*) p;
+	}
+	// all or nothing: a rank that could not map a peer keeps everybody on NCCL
+	float* agree = nullptr;
+	if (cudaMalloc((void**) &agree, sizeof(float)) != cudaSuccess) { cudaGetLastError(); return; }
+	const float vote = ok ? 1.f : 0.f;
+	float votes = 0.f;
+	cudaMemcpy(agree, &vote, sizeof(float), cudaMemcpyHostToDevice);
+	if (n->AllReduce(agree, agree, 1, NCCL_FLOAT32, NCCL_SUM, c->comm, c->ctx->stream) == NCCL_SUCCESS &&
+			cudaStreamSynchronize(c->ctx->stream) == cudaSuccess)
+		cudaMemcpy(&votes, agree, sizeof(float), cudaMemcpyDeviceToHost);
+	else
+		cudaGetLastError();
+	cudaFree(agree);
+	c->peer_ok = ok && votes == (float) c->world;
+}
 
 using namespace cattl3;
 
@@ -134,6 +236,7 @@ int cattl3_comm_create(cattl3_comm** out, cattl3_ctx* ctx, int world_size, int r
 			if (n->CommSplit(c->comm, 0, rank, &c->comm_async, nullptr) != NCCL_SUCCESS)
 				c->comm_async = nullptr;
 		}
+		peer_setup(c);
 		int lo = 0, hi = 0;
 		cudaDeviceGetStreamPriorityRange(&lo, &hi);   // the exchange is short and latency bound: highest priority
 		if (cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi) != cudaSuccess ||
@@ -210,6 +313,11 @@ int cattl3_comm_destroy(cattl3_comm* c) {
 			n->CommDestroy(c->comm);
 		}
 	}
+	if (c->peer_ok) {
+		for (int r = 0; r < c->world; ++r)
+			if (r != c->rank && c->peers.box[r]) cudaIpcCloseMemHandle(c->peers.box[r]);
+	}
+	if (c->mailbox) cudaFree(c->mailbox);
 	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
 	if (c->ev_join) cudaEventDestroy(c->ev_join);
 	if (c->side) cudaStreamDestroy(c->side);
@@ -236,6 +344,16 @@ static int allreduce(cattl3_comm* c, void* buf, int64_t count, int dtype) {
 	CATTL3_CHECK(check_ctx(c->ctx));
 	if (c->world == 1)
 		return CATTL3_OK;
+	const size_t bytes = (size_t) count * (dtype == NCCL_FLOAT64 ? 8 : 4);
+	if (c->peer_ok && bytes <= (size_t) PEER_MAX_BYTES) {
+		// short vectors (BatchNorm statistics, scalars): one-shot exchange through the ranks' mailboxes
+		if (dtype == NCCL_FLOAT64)
+			peer_allreduce_kernel<double><<<1, 256, 0, c->ctx->stream>>>((double*) buf, (int) count, c->rank, c->world, c->peers);
+		else
+			peer_allreduce_kernel<float><<<1, 256, 0, c->ctx->stream>>>((float*) buf, (int) count, c->rank, c->world, c->peers);
+		CATTL3_LAUNCHED(c->ctx);
+		return CATTL3_OK;
+	}
 	CATTL3_NCCL(nccl()->AllReduce(buf, buf, (size_t) count, dtype, NCCL_SUM, c->comm, c->ctx->stream), "ncclAllReduce");
 	return CATTL3_OK;
 }
