@@ -869,7 +869,7 @@ struct TcWgradParams {
 // into a CTA-private fp32 tile with round-to-nearest adds (TMA and the converters keep filling the stages
 // meanwhile; the MMA warp idles for the few thousand clocks of the drain, ~4 % of a flush period).
 constexpr int WG_KB = 32;
-constexpr uint32_t WG_A_COL0 = 256;   // TMEM: accumulator in columns [0, 192], A stages from column 256
+constexpr uint32_t WG_A_COL0 = 192;   // TMEM: accumulator in columns [0, 192), A stages (64 columns each) from column 192: five fit
 constexpr int WG_RING = 4;             // k-blocks of dY in flight per converter warp (cp.async ring of 4 KB patches)
 template<int CTAS>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tm_b,
@@ -1003,12 +1003,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 				float v[16];
 				tmem_ld_16(taddr + c0, v);
 				tmem_ld_wait();
+				// fold into the CTA's fp32 partial tile: the first chunk stores, the later ones add with fire-and-forget
+				// reductions (RED.ADD.F32, round to nearest; one writer per address, program order = flush order, so the
+				// sum is the same sequence of additions as a read-modify-write, without its L2 round trip per 16 columns,
+				// which cost 12 % of the kernel)
 				if (c > 0) {
 					#pragma unroll
-					for (int i = 0; i < 16; ++i) v[i] += dst[(long long) (c0 + i) * 128];
+					for (int i = 0; i < 16; ++i) atomicAdd(&dst[(long long) (c0 + i) * 128], v[i]);
+				} else {
+					#pragma unroll
+					for (int i = 0; i < 16; ++i) dst[(long long) (c0 + i) * 128] = v[i];
 				}
-				#pragma unroll
-				for (int i = 0; i < 16; ++i) dst[(long long) (c0 + i) * 128] = v[i];
 			}
 			tc_fence_before();
 			__syncwarp();
@@ -1258,8 +1263,9 @@ int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const 
 	int stages = (TC_SMEM_LIMIT - ring_bytes) / stage_bytes;
 	const int tmem_stages = (512 - (int) WG_A_COL0) / (2 * WG_KB);
 	if (stages > tmem_stages) stages = tmem_stages;
+	if (getenv("CATTL3_WG_STAGES") && atoi(getenv("CATTL3_WG_STAGES")) < stages) stages = atoi(getenv("CATTL3_WG_STAGES"));
 	p.stages = stages;
-	p.flush = 32;
+	p.flush = getenv("CATTL3_WG_FLUSH") ? atoi(getenv("CATTL3_WG_FLUSH")) : 32;
 	p.w_stap = gg.w_stap; p.w_sr = gg.w_sr; p.w_sj = gg.w_sj;
 	p.dw_elems = (long long) T * gg.SC * gg.J;
 	const size_t partial_elems = (size_t) p.splits * tiles * p.BNW * 128;
