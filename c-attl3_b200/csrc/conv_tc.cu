@@ -595,14 +595,13 @@ __global__ void __launch_bounds__((2 + NEPI + NCONV) * 32, 1) tc_gather_gemm_ker
 		const int row = 32 * q + lane;
 		const uint32_t row_off = (uint32_t) ((row / p.nb) * (KB * p.nb * 4) + (row % p.nb) * 4);
 		const uint32_t k_stride = (uint32_t) (p.nb * 4);
-		int s = 0; uint32_t ph = 0;
-		int turn = 0;
-		for (int tile = unit; tile < tiles; tile += units) {
-			for (int kb = 0; kb < kblocks; ++kb) {
-				if (NCONV == 8 && (turn ^= 1) == cset) {   // the other set's k-block
-					if (++s == p.stages) { s = 0; ph ^= 1; }
-					continue;
-				}
+		// the k-blocks of all of this unit's tiles form one sequence; this set takes every (NCONV / 4)-th of them
+		constexpr int NSETS = NCONV / 4;
+		const long long my_tiles = tiles > unit ? (tiles - unit + units - 1) / units : 0;
+		const long long total = my_tiles * kblocks;
+		int s = cset % p.stages; uint32_t ph = (uint32_t) ((cset / p.stages) & 1);
+		{
+			for (long long g = cset; g < total; g += NSETS) {
 				mbar_wait(&full[s], ph);
 				const uint8_t* grp = smem + (size_t) s * stage_bytes + row_off;
 				const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16) + a_col0 + (uint32_t) (s * 2 * KB);
@@ -622,7 +621,8 @@ __global__ void __launch_bounds__((2 + NEPI + NCONV) * 32, 1) tc_gather_gemm_ker
 				tc_fence_before();
 				__syncwarp();
 				if (lane == 0) { if (CTAS == 2) mbar_arrive_cta(&ready[s], 0); else mbar_arrive(&ready[s]); }
-				if (++s == p.stages) { s = 0; ph ^= 1; }
+				s += NSETS;
+				if (s >= p.stages) { s -= p.stages; ph ^= 1; }   // (NSETS <= stages)
 			}
 		}
 	}
@@ -711,9 +711,15 @@ __global__ void __launch_bounds__(256) colstats_reduce_tc_kernel(const double* _
 	col_stats[i] = s;
 }
 
+static bool tc_rows_gemm_applies(const GatherGeom& gg, int bias_mode, const EpilogueArgs* ep);
+static int tc_rows_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const float* w, const float* bias,
+		int bias_mode, float* out);
+
 int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const float* w, const float* bias,
 		int bias_mode, float* out, const EpilogueArgs* ep) {
 	CATTL3_REQUIRE(aligned16(src) && (!out || aligned16(out)), "tcgen05 path needs 16-byte aligned tensors");
+	if (out && tc_rows_gemm_applies(gg, bias_mode, ep))
+		return tc_rows_gemm_f32(ctx, gg, src, w, bias, bias_mode, out);
 	const bool want_stats = ep && ep->col_stats;
 	const bool want_act = ep && ep->act_kind != CATTL3_ACT_NONE;
 	CATTL3_REQUIRE(out || want_act, "gather GEMM: no output tensor");
@@ -825,6 +831,270 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 				gg.J, ep->col_stats);
 		CATTL3_LAUNCHED(ctx);
 	}
+	return CATTL3_OK;
+}
+
+// ---- the row-sharing gather GEMM ------------------------------------------------------------------------------------
+// A stride-1 gather with few output channels (the input gradient of config 2: 256 -> 64 channels; the 64 -> 64 layers of
+// config 4) is bound by L2 -> SM bandwidth, not by the tensor pipe: every 128 x 32 tile of the big operand feeds only
+// 3 * 64 columns of MMAs, it is fetched once per tap (nine times), and the weights are streamed again for every tile --
+// measured 37 B/clk/SM against the ~42 B/clk/SM the L2 delivers (profiles/README.md, r2).  Here a tile is R = 3
+// vertically adjacent output pixels (x 256 batch entries for the pair) with one accumulator each: the R + RH - 1 source
+// rows they need are fetched ONCE per tap column and each source tile feeds the accumulator of every output row it
+// belongs to (15 fetches instead of 27), and the RH weight tiles of a tap column stay in shared memory for those
+// R + RH - 1 k-blocks (24 fetches instead of 72): 2.1x fewer bytes per MMA.
+// Always a CTA pair; warps: 0 = TMA, 1 = MMA (leader), 2-5 = epilogue, 6-9 = converters.
+struct TcRowsParams {
+	int N, OH, OW, J, RH, RW;
+	int bh, ch, aw, bw, cw;   // source row = oh + rh * bh + ch (bh = +-1), source column = ow * aw + rw * bw + cw
+	int BN, r_pad, R, IR, ohg, nblocks, tiles;
+	int bias_mode;
+	const float* bias;
+	float* out;
+	long long out_cs;
+};
+constexpr int ROWS_KB = 32, ROWS_ASTAGES = 5, ROWS_BSLOTS = 2, ROWS_R = 3;
+
+__global__ void __launch_bounds__(320, 1) tc_rows_gemm_kernel(const __grid_constant__ CUtensorMap tm_a,
+		const __grid_constant__ CUtensorMap tm_b, const TcRowsParams p) {
+	extern __shared__ __align__(1024) uint8_t smem_raw[];
+	uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t) 1023);
+	constexpr int A_BYTES = TC_BM * ROWS_KB * 4;
+	const int b_bytes = p.BN / 2 * ROWS_KB * 4;         // one weight tile (hi or lo) of this CTA's half of the columns
+	const int bslot_bytes = p.RH * 2 * b_bytes;         // [tap row][hi | lo]
+	uint8_t* a_smem = smem;
+	uint8_t* b_smem = smem + ROWS_ASTAGES * A_BYTES;
+	uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + ROWS_BSLOTS * bslot_bytes);
+	uint64_t* a_full = bars;
+	uint64_t* a_ready = bars + 8;
+	uint64_t* a_empty = bars + 16;
+	uint64_t* b_full = bars + 24;
+	uint64_t* b_empty = bars + 26;
+	uint64_t* acc_full = bars + 28;
+	uint64_t* acc_empty = bars + 29;
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 30);
+	float* sbias = reinterpret_cast<float*>(bars + 32);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const uint32_t rank = cluster_ctarank();
+	const int unit = blockIdx.x / 2, units = gridDim.x / 2;
+	const int chunks = p.r_pad / ROWS_KB;
+	const int base_off = p.bh > 0 ? 0 : -(p.RH - 1);
+	const uint32_t a_col0 = (uint32_t) (p.R * p.BN);
+
+	if (warp == 0 && elect_one()) {
+		tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_b);
+		for (int s = 0; s < ROWS_ASTAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_ready[s], 8); mbar_init(&a_empty[s], 1); }
+		for (int s = 0; s < ROWS_BSLOTS; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+		mbar_init(acc_full, 1); mbar_init(acc_empty, 8);
+		fence_barrier_init();
+	}
+	if (p.bias_mode == 1)
+		for (int c = threadIdx.x; c < p.BN; c += blockDim.x) sbias[c] = c < p.J ? __ldg(p.bias + c) : 0.f;
+	if (warp == 1) tmem_alloc<2>(tmem_slot, 512u);
+	tc_fence_before();
+	cluster_sync();
+	tc_fence_after();
+	const uint32_t tmem_base = *tmem_slot;
+
+	if (warp == 0) {
+		if (elect_one()) {
+			int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
+			for (int tile = unit; tile < p.tiles; tile += units) {
+				const int nb_i = tile % p.nblocks, rest = tile / p.nblocks;
+				const int oh0 = (rest % p.ohg) * p.R, ow = rest / p.ohg;
+				const int n0 = nb_i * (2 * TC_BM) + (int) rank * TC_BM;
+				const int ih_base = oh0 + p.ch + base_off;
+				for (int c0 = 0; c0 < p.r_pad; c0 += ROWS_KB) {
+					for (int rw = 0; rw < p.RW; ++rw) {
+						const int iw = ow * p.aw + rw * p.bw + p.cw;
+						mbar_wait(&b_empty[bs], bph ^ 1);
+						mbar_expect_tx(&b_full[bs], (uint32_t) bslot_bytes);
+						for (int rh = 0; rh < p.RH; ++rh) {
+							uint8_t* dst = b_smem + bs * bslot_bytes + rh * 2 * b_bytes;
+							tma_load_4d(dst, &tm_b, &b_full[bs], c0, (int) rank * (p.BN / 2), rh + p.RH * rw, 0);
+							tma_load_4d(dst + b_bytes, &tm_b, &b_full[bs], c0, (int) rank * (p.BN / 2), rh + p.RH * rw, 1);
+						}
+						if (++bs == ROWS_BSLOTS) { bs = 0; bph ^= 1; }
+						for (int t = 0; t < p.IR; ++t) {
+							mbar_wait(&a_empty[as], aph ^ 1);
+							mbar_expect_tx(&a_full[as], (uint32_t) A_BYTES);
+							tma_load_4d(a_smem + as * A_BYTES, &tm_a, &a_full[as], n0, ih_base + t, iw, c0);
+							if (++as == ROWS_ASTAGES) { as = 0; aph ^= 1; }
+						}
+					}
+				}
+			}
+		}
+	} else if (warp == 1) {
+		if (rank == 0 && elect_one()) {
+			const uint32_t idesc = make_idesc_tf32(p.BN, 2 * TC_BM);
+			int as = 0; uint32_t aph = 0; int bs = 0;
+			uint32_t acc_ph = 0;
+			for (int tile = unit; tile < p.tiles; tile += units) {
+				const int oh0 = ((tile / p.nblocks) % p.ohg) * p.R;
+				mbar_wait(acc_empty, acc_ph ^ 1);
+				tc_fence_after();
+				uint32_t started = 0;
+				for (int c = 0; c < chunks; ++c) {
+					for (int rw = 0; rw < p.RW; ++rw) {
+						const uint32_t bslot = smem_u32(b_smem + bs * bslot_bytes);
+						for (int t = 0; t < p.IR; ++t) {
+							mbar_wait(&a_ready[as], aph);
+							tc_fence_after();
+							const uint32_t a_hi = tmem_base + a_col0 + (uint32_t) (as * 2 * ROWS_KB);
+							const uint32_t a_lo = a_hi + ROWS_KB;
+							for (int i = 0; i < p.R; ++i) {
+								const int d = base_off + t - i;
+								const int rh = p.bh > 0 ? d : -d;
+								if (oh0 + i >= p.OH || rh < 0 || rh >= p.RH) continue;
+								const uint32_t acc = tmem_base + (uint32_t) (i * p.BN);
+								const uint32_t b_hi = bslot + (uint32_t) (rh * 2 * b_bytes);
+								const uint32_t b_lo = b_hi + (uint32_t) b_bytes;
+								uint32_t accumulate = (started >> i) & 1u;
+								#pragma unroll
+								for (int pass = 0; pass < 3; ++pass) {
+									const uint32_t a = pass == 0 ? a_lo : a_hi;
+									const uint32_t b = pass == 1 ? b_lo : b_hi;
+									#pragma unroll
+									for (int ks = 0; ks < ROWS_KB / 8; ++ks) {
+										umma_tf32_ts<2>(acc, a + 8 * ks, kmajor_desc<ROWS_KB>(b, ks), idesc, accumulate);
+										accumulate = 1u;
+									}
+								}
+								started |= 1u << i;
+							}
+							umma_commit<2>(&a_empty[as]);
+							if (++as == ROWS_ASTAGES) { as = 0; aph ^= 1; }
+						}
+						umma_commit<2>(&b_empty[bs]);   // the tap column's weight tiles have been read
+						if (++bs == ROWS_BSLOTS) bs = 0;
+					}
+				}
+				umma_commit<2>(acc_full);
+				acc_ph ^= 1;
+			}
+		}
+	} else if (warp < 6) {
+		const int q = warp & 3;
+		uint32_t acc_ph = 0;
+		for (int tile = unit; tile < p.tiles; tile += units) {
+			const int nb_i = tile % p.nblocks, rest = tile / p.nblocks;
+			const int oh0 = (rest % p.ohg) * p.R, ow = rest / p.ohg;
+			const int n = nb_i * (2 * TC_BM) + (int) rank * TC_BM + 32 * q + lane;
+			mbar_wait(acc_full, acc_ph);
+			tc_fence_after();
+			for (int i = 0; i < p.R; ++i) {
+				if (oh0 + i >= p.OH) break;
+				float* out_m = p.out + n + (long long) p.N * ((oh0 + i) + (long long) p.OH * ow);
+				const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16) + (uint32_t) (i * p.BN);
+				for (int c0 = 0; c0 < p.BN; c0 += 16) {
+					float v[16];
+					tmem_ld_16(taddr + c0, v);
+					tmem_ld_wait();
+					#pragma unroll
+					for (int k = 0; k < 16; ++k) {
+						if (c0 + k < p.J)
+							out_m[p.out_cs * (long long) (c0 + k)] = p.bias_mode == 1 ? v[k] + sbias[c0 + k] : v[k];
+					}
+				}
+			}
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) mbar_arrive_cta(acc_empty, 0);
+			acc_ph ^= 1;
+		}
+	} else {
+		const int q = warp & 3;
+		const int row = 32 * q + lane;
+		const uint32_t row_off = (uint32_t) (row * 4);            // the box is [32 k][128 n]: row m of the tile = entry m of each k-row
+		constexpr uint32_t k_stride = TC_BM * 4;
+		int as = 0; uint32_t aph = 0; int bs = 0; uint32_t bph = 0;
+		for (int tile = unit; tile < p.tiles; tile += units) {
+			for (int c = 0; c < chunks; ++c) {
+				for (int rw = 0; rw < p.RW; ++rw) {
+					for (int t = 0; t < p.IR; ++t) {
+						mbar_wait(&a_full[as], aph);
+						if (t == 0) mbar_wait(&b_full[bs], bph);   // this CTA's half of the tap column's weights has landed too
+						const uint8_t* grp = a_smem + as * A_BYTES + row_off;
+						const uint32_t taddr = tmem_base + ((uint32_t) (32 * q) << 16) + a_col0 + (uint32_t) (as * 2 * ROWS_KB);
+						#pragma unroll
+						for (int k0 = 0; k0 < ROWS_KB; k0 += 16) {
+							uint32_t hi[16], lo[16];
+							#pragma unroll
+							for (int k = 0; k < 16; ++k) {
+								const float v = *reinterpret_cast<const float*>(grp + (uint32_t) (k0 + k) * k_stride);
+								hi[k] = tf32_hi_bits(v);
+								lo[k] = tf32_lo_bits(v);
+							}
+							tmem_st_16(taddr + k0, hi);
+							tmem_st_16(taddr + ROWS_KB + k0, lo);
+						}
+						tmem_st_wait();
+						tc_fence_before();
+						__syncwarp();
+						if (lane == 0) mbar_arrive_cta(&a_ready[as], 0);
+						if (++as == ROWS_ASTAGES) { as = 0; aph ^= 1; }
+					}
+					if (++bs == ROWS_BSLOTS) { bs = 0; bph ^= 1; }
+				}
+			}
+		}
+	}
+	tc_fence_before();
+	cluster_sync();
+	if (warp == 1) tmem_dealloc<2>(tmem_base, 512u);
+}
+
+static bool tc_rows_gemm_applies(const GatherGeom& gg, int bias_mode, const EpilogueArgs* ep) {
+	static const bool off = getenv("CATTL3_NO_ROWS") != nullptr || (pair_mask() & 1) == 0;
+	if (off || ep || bias_mode > 1) return false;
+	if (gg.ah != 1 || gg.aw != 1 || (gg.bh != 1 && gg.bh != -1) || gg.denh != 1 || gg.denw != 1) return false;
+	if (gg.N % (2 * TC_BM) != 0 || gg.J > 64 || gg.J < 16 || gg.SC < 32 || gg.RH < 2 || gg.RH > 4 || gg.OH < ROWS_R) return false;
+	if (gg.out_H != 0 || gg.w_off != 0 || gg.w_srw != 0) return false;
+	return true;
+}
+
+static int tc_rows_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const float* w, const float* bias,
+		int bias_mode, float* out) {
+	const int T = gg.RH * gg.RW;
+	const int BN = round_up(gg.J, 32);
+	const int r_pad = round_up(gg.SC, ROWS_KB);
+	const long long w_elems = (long long) T * BN * r_pad;
+	CATTL3_CHECK(ensure_buffer(ctx, &ctx->tc_w, &ctx->tc_w_bytes, (size_t) w_elems * 8));
+	float* w_packed = (float*) ctx->tc_w;
+	pack_weights_kernel<<<ew_grid(ctx, w_elems, 256), 256, 0, ctx->stream>>>(gg, r_pad, BN, 0, w, w_packed);
+	CATTL3_LAUNCHED(ctx);
+	CUtensorMap tm_a, tm_b;
+	{
+		cuuint64_t dims[4] = { (cuuint64_t) gg.N, (cuuint64_t) gg.SH, (cuuint64_t) gg.SW, (cuuint64_t) gg.SC };
+		cuuint64_t str[3] = { (cuuint64_t) gg.N * 4, (cuuint64_t) gg.N * gg.SH * 4, (cuuint64_t) gg.N * gg.SH * gg.SW * 4 };
+		cuuint32_t box[4] = { (cuuint32_t) TC_BM, 1, 1, (cuuint32_t) ROWS_KB };
+		CATTL3_CHECK(encode_map(&tm_a, src, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE));
+	}
+	{
+		cuuint64_t dims[4] = { (cuuint64_t) r_pad, (cuuint64_t) BN, (cuuint64_t) T, 2 };
+		cuuint64_t str[3] = { (cuuint64_t) r_pad * 4, (cuuint64_t) r_pad * BN * 4, (cuuint64_t) w_elems * 4 };
+		cuuint32_t box[4] = { (cuuint32_t) ROWS_KB, (cuuint32_t) (BN / 2), 1, 1 };
+		CATTL3_CHECK(encode_map(&tm_b, w_packed, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B));
+	}
+	TcRowsParams p;
+	p.N = gg.N; p.OH = gg.OH; p.OW = gg.OW; p.J = gg.J; p.RH = gg.RH; p.RW = gg.RW;
+	p.bh = gg.bh; p.ch = gg.ch; p.aw = gg.aw; p.bw = gg.bw; p.cw = gg.cw;
+	p.BN = BN; p.r_pad = r_pad; p.R = ROWS_R; p.IR = ROWS_R + gg.RH - 1;
+	p.ohg = (gg.OH + ROWS_R - 1) / ROWS_R;
+	p.nblocks = gg.N / (2 * TC_BM);
+	p.tiles = p.nblocks * p.ohg * gg.OW;
+	p.bias_mode = bias_mode; p.bias = bias; p.out = out;
+	p.out_cs = (long long) gg.N * gg.OH * gg.OW;
+	const int pairs = p.tiles < ctx->sm_count / 2 ? p.tiles : ctx->sm_count / 2;
+	size_t smem_bytes = (size_t) ROWS_ASTAGES * TC_BM * ROWS_KB * 4 + (size_t) ROWS_BSLOTS * gg.RH * 2 * (BN / 2) * ROWS_KB * 4 +
+			1024 + 256 + 1024;
+	if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;
+	CATTL3_REQUIRE(smem_bytes <= 227 * 1024, "rows GEMM: shared memory");
+	CATTL3_CUDA(cudaFuncSetAttribute(tc_rows_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+	CATTL3_CUDA(launch_clustered(tc_rows_gemm_kernel, 2 * pairs, 320, smem_bytes, ctx->stream, 2, tm_a, tm_b, p));
+	CATTL3_LAUNCHED(ctx);
 	return CATTL3_OK;
 }
 

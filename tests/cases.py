@@ -24,6 +24,11 @@ CONV_CASES = {
     "c2_dil1": (32, 12, 10, 32, 16, 3, 3, 2, 2, 1, 1, 1, 1),
     "c2_1x1": (64, 9, 9, 64, 64, 1, 1, 0, 0, 1, 1, 0, 0),
     "ragged_c": (32, 9, 7, 20, 24, 3, 3, 1, 1, 1, 1, 0, 0),
+    # batch 256, few filters either way: the row-sharing gather GEMM (three output rows per tile) runs the forward pass
+    # of "rows64" / "rows_2x3" and the input gradient of all three; 7 and 5 rows leave a ragged last row group
+    "rows64": (256, 7, 6, 64, 64, 3, 3, 1, 1, 1, 1, 0, 0),
+    "rows_f256": (256, 5, 4, 48, 256, 3, 3, 1, 1, 1, 1, 0, 0),
+    "rows_2x3": (256, 6, 5, 64, 32, 2, 3, 0, 1, 1, 1, 0, 0),
     # strided input gradients on the tensor-core path (one stride-1 sub-problem per residue class of the input pixel)
     "s2_d1": (32, 11, 9, 32, 32, 3, 3, 2, 2, 2, 2, 1, 1),    # classes without taps: zero-filled
     "s3": (32, 13, 11, 16, 32, 3, 3, 1, 1, 3, 3, 0, 0),

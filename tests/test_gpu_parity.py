@@ -222,7 +222,7 @@ def test_regularize_kernel(U, dt):
 
 
 # "stem": 3 input channels, zero-padded to a 16-channel k-block by TMA out-of-bounds fill (forward on tcgen05)
-TC_CASES = ["c2_small", "c2_small_f256", "c2_stride2", "c2_dil1", "c2_1x1", "ragged_c", "stem"]
+TC_CASES = ["c2_small", "c2_small_f256", "c2_stride2", "c2_dil1", "c2_1x1", "ragged_c", "stem", "rows64", "rows_f256", "rows_2x3"]
 
 
 def test_conv_tcgen05_vs_oracle(U, orc):
