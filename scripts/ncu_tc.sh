@@ -5,8 +5,8 @@ TAG=${1:-rX}; shift
 MASKS=${@:-0 3}
 mkdir -p gpurun_out
 for m in $MASKS; do
-	CATTL3_TC_PAIRS=$m ncu --set full --clock-control none --import-source on -k regex:"tc_gather_gemm_kernel|tc_wgrad_kernel" -s 9 -c 3 \
-		-o gpurun_out/${TAG}_p$m python bench.py --steps 2 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
+	CATTL3_TC_PAIRS=$m ncu --set full --clock-control none --import-source on -k regex:"tc_gather_gemm_kernel|tc_wgrad_kernel|tc_rows_gemm_kernel" -s 9 -c 3 \
+		-o gpurun_out/${TAG}_p$m timeout 300 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-networks --no-double > /dev/null 2>&1
 	ncu -i gpurun_out/${TAG}_p$m.ncu-rep --page raw --csv > gpurun_out/${TAG}_p${m}_raw.csv 2>/dev/null
 	ncu -i gpurun_out/${TAG}_p$m.ncu-rep --page source --csv > gpurun_out/${TAG}_p${m}_source.csv 2>/dev/null
 	gzip -f gpurun_out/${TAG}_p${m}_source.csv

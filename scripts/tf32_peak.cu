@@ -166,19 +166,20 @@ static int launch(int grid, int n_cols, int iters, int verify, float* out) {
 typedef int (*LaunchFn)(int, int, int, int, float*);
 
 int main(int argc, char** argv) {
-	// usage: tf32_peak [sustained seconds = 1.5] [mode filter, e.g. 1sm_ts]
+	// usage: tf32_peak [sustained seconds = 1.5] [mode filter, e.g. 1sm_ts] [N = 256]
 	const double sustain_s = argc > 1 ? atof(argv[1]) : 1.5;
 	const char* only = argc > 2 ? argv[2] : nullptr;
+	const int n_arg = argc > 3 ? atoi(argv[3]) : 256;   // accumulator columns (a multiple of 32 up to 256)
 	cudaDeviceProp prop;
 	cudaGetDeviceProperties(&prop, 0);
 	const int sms = prop.multiProcessorCount;
-	const int N = 256;
-	float* d_out; cudaMalloc(&d_out, 256 * N * 4);
+	const int N = n_arg;
+	float* d_out; cudaMalloc(&d_out, 256 * 256 * 4);
 	static float h[256 * 256];
 	struct Mode { const char* name; LaunchFn fn; int ctas; } modes[] = {
 		{"1sm_ss", launch<1, false>, 1}, {"1sm_ts", launch<1, true>, 1}, {"2sm_ss", launch<2, false>, 2}, {"2sm_ts", launch<2, true>, 2} };
 	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-	printf("{\"device\": \"%s\", \"sms\": %d, \"shape\": \"M=128 per CTA, N=256, K=8, kind::tf32, fp32 accumulate in TMEM\"", prop.name, sms);
+	printf("{\"device\": \"%s\", \"sms\": %d, \"shape\": \"M=128 per CTA, N=%d, K=8, kind::tf32, fp32 accumulate in TMEM\"", prop.name, sms, N);
 	for (Mode& md : modes) {
 		if (only && !strstr(md.name, only)) continue;
 		// ---- verification: one k-block of exactly representable integers
