@@ -122,6 +122,16 @@ static int run_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, 
 	const bool tensor_ok = ctx->conv_path != CATTL3_PATH_SIMT && ctx->conv_path != CATTL3_PATH_FMA;
 	if (IsFloat<S>::value && tensor_ok && tc_gather_gemm_supported(ctx, gg)) {
 		ctx->last_path = "tcgen05";
+		if (ep && ep->col_stats && gg.J >= 256 && out && bias_mode == 1) {
+			// Wide layers: the statistics epilogue needs 128-wide tiles (two accumulators to hide behind), which converts the
+			// big operand twice -- measured slower than the plain 256-wide kernel followed by one reduction pass over the
+			// finished output (profiles/README.md, r2: 1.73 against 1.67 ms layer by layer).  The activation stays fused.
+			EpilogueArgs plain = *ep;
+			plain.col_stats = nullptr;
+			CATTL3_CHECK(tc_gather_gemm_f32(ctx, gg, (const float*) src, (const float*) w, (const float*) bias, bias_mode,
+					(float*) out, plain.act_kind != CATTL3_ACT_NONE ? &plain : nullptr));
+			return colstats_shifted<S>(ctx, (int64_t) gg.N * gg.OH * gg.OW, gg.J, out, bias, ep->col_stats);
+		}
 		return tc_gather_gemm_f32(ctx, gg, (const float*) src, (const float*) w, (const float*) bias, bias_mode,
 				(float*) out, ep);
 	}
