@@ -872,6 +872,124 @@ int host_chunk_filters(const cattl3_conv_geom* g) {
 	return g->f / chunks;
 }
 
+// ---- strips of image columns --------------------------------------------------------------------------------------
+// Chunks of filters leave a serial head (all of x must be up before anything computes) and tail (dX comes down after the
+// last chunk).  With a stride-1 convolution on the tensor-core path the work can be cut along the image WIDTH instead: a
+// strip of columns of x / y / dY / dX is, per channel, one contiguous block (N * H * columns elements), i.e. a 2-D copy of
+// `channels` long rows; a strip of y needs the strip of x plus a halo column either side, a strip of dW is the reduction over
+// the strip's rows of dY (accumulated strip by strip), a strip of dX needs the strip of dY plus its halo.  Uploads, kernels
+// and downloads then overlap from the first strip to the last, and only one strip's kernels and download are exposed at the end.
+struct Strips { int count; int w0[cattl3_ctx::HOST_MAX_CHUNKS + 1]; };
+
+static Strips cut_strips(int width) {
+	const char* env = getenv("CATTL3_HOST_STRIPS");
+	int want = env ? atoi(env) : 4;
+	if (want > cattl3_ctx::HOST_MAX_CHUNKS / 2) want = cattl3_ctx::HOST_MAX_CHUNKS / 2;
+	if (want > width / 2) want = width / 2;
+	Strips st;
+	st.count = want < 1 ? 1 : want;
+	for (int k = 0; k <= st.count; ++k) st.w0[k] = (int) ((long long) width * k / st.count);
+	return st;
+}
+
+// stride 1, undilated or dilated, every pass on the tcgen05 kernels (they are the ones that take sub-lattices / row ranges)
+static bool host_strips_ok(cattl3_ctx* ctx, const cattl3_conv_geom* g, int oh, int ow) {
+	if (getenv("CATTL3_NO_HOST_STRIPS") || g->sh != 1 || g->sw != 1 || ctx->conv_path == CATTL3_PATH_SIMT || ctx->conv_path == CATTL3_PATH_FMA)
+		return false;
+	if (g->w < 4 || ow < 4) return false;
+	const long long T = (long long) g->rh * g->rw;
+	GatherGeom gf = fwd_gather(g->n, g->h, g->w, g->c, oh, ow, g->f, g);
+	gf.w_stap = 1; gf.w_sr = T; gf.w_sj = T * g->c;
+	GatherGeom gd = bwd_gather(g->n, oh, ow, g->f, g->h, g->w, g->c, g);
+	gd.w_stap = 1; gd.w_sr = T * g->c; gd.w_sj = T;
+	return tc_gather_gemm_supported(ctx, gf) && tc_gather_gemm_supported(ctx, gd) && tc_wgrad_supported(ctx, gf);
+}
+
+static int host_forward_strips(cattl3_ctx* ctx, const cattl3_conv_geom* g, int oh, int ow, const float* x_host, const float* w_dev,
+		const float* b_dev, float* y_host, float* xd, float* yd) {
+	cudaEvent_t* ev = ctx->host_ev;
+	const Strips xs = cut_strips(g->w), ys = cut_strips(ow);
+	const size_t x_pitch = sizeof(float) * (size_t) g->n * g->h * g->w, y_pitch = sizeof(float) * (size_t) g->n * oh * ow;
+	const long long T = (long long) g->rh * g->rw;
+	for (int k = 0; k < xs.count; ++k) {
+		const size_t off = (size_t) g->n * g->h * xs.w0[k];
+		CATTL3_CUDA(cudaMemcpy2DAsync(xd + off, x_pitch, x_host + off, x_pitch, sizeof(float) * (size_t) g->n * g->h * (xs.w0[k + 1] - xs.w0[k]),
+				(size_t) g->c, cudaMemcpyHostToDevice, ctx->up_stream));
+		CATTL3_CUDA(cudaEventRecord(ev[cattl3_ctx::EV_CHUNK + k], ctx->up_stream));
+	}
+	int waited = 0;   // strips of x the compute stream has waited for
+	for (int k = 0; k < ys.count; ++k) {
+		// the last source column this strip of outputs reads
+		int need = (ys.w0[k + 1] - 1) + (g->rw - 1) * (g->dw + 1) - g->pw;
+		if (need > g->w - 1) need = g->w - 1;
+		while (waited < xs.count && xs.w0[waited] <= need) {
+			CATTL3_CUDA(cudaStreamWaitEvent(ctx->stream, ev[cattl3_ctx::EV_CHUNK + waited], 0));
+			++waited;
+		}
+		GatherGeom gg = fwd_gather(g->n, g->h, g->w, g->c, oh, ys.w0[k + 1] - ys.w0[k], g->f, g);
+		gg.w_stap = 1; gg.w_sr = T; gg.w_sj = T * g->c;
+		gg.cw += ys.w0[k] * gg.aw;                         // the strip's first output column
+		gg.out_H = oh; gg.out_W = ow; gg.out_w0 = ys.w0[k];
+		CATTL3_CHECK(tc_gather_gemm_f32(ctx, gg, xd, w_dev, b_dev, 1, yd, nullptr));
+		ctx->last_path = "tcgen05";
+		CATTL3_CUDA(cudaEventRecord(ev[cattl3_ctx::EV_CHUNK + xs.count + k], ctx->stream));
+		CATTL3_CUDA(cudaStreamWaitEvent(ctx->down_stream, ev[cattl3_ctx::EV_CHUNK + xs.count + k], 0));
+		const size_t off = (size_t) g->n * oh * ys.w0[k];
+		CATTL3_CUDA(cudaMemcpy2DAsync(y_host + off, y_pitch, yd + off, y_pitch, sizeof(float) * (size_t) g->n * oh * (ys.w0[k + 1] - ys.w0[k]),
+				(size_t) g->f, cudaMemcpyDeviceToHost, ctx->down_stream));
+	}
+	while (waited < xs.count) {   // (strips of x no output needed: still part of this call's upload)
+		CATTL3_CUDA(cudaStreamWaitEvent(ctx->stream, ev[cattl3_ctx::EV_CHUNK + waited], 0));
+		++waited;
+	}
+	return CATTL3_OK;
+}
+
+static int host_backward_strips(cattl3_ctx* ctx, const cattl3_conv_geom* g, int oh, int ow, const float* x_dev, const float* w_dev,
+		const float* dy_host, float* dw_dev, float* db_dev, float* dx_host, float* dyd, float* dxd) {
+	cudaEvent_t* ev = ctx->host_ev;
+	const Strips xs = cut_strips(g->w), ys = cut_strips(ow);
+	const size_t x_pitch = sizeof(float) * (size_t) g->n * g->h * g->w, y_pitch = sizeof(float) * (size_t) g->n * oh * ow;
+	const long long T = (long long) g->rh * g->rw;
+	for (int k = 0; k < ys.count; ++k) {
+		const size_t off = (size_t) g->n * oh * ys.w0[k];
+		CATTL3_CUDA(cudaMemcpy2DAsync(dyd + off, y_pitch, dy_host + off, y_pitch, sizeof(float) * (size_t) g->n * oh * (ys.w0[k + 1] - ys.w0[k]),
+				(size_t) g->f, cudaMemcpyHostToDevice, ctx->up_stream));
+		CATTL3_CUDA(cudaEventRecord(ev[cattl3_ctx::EV_CHUNK + k], ctx->up_stream));
+	}
+	int done_dx = 0;   // strips of dX computed so far
+	for (int k = 0; k < ys.count; ++k) {
+		CATTL3_CUDA(cudaStreamWaitEvent(ctx->stream, ev[cattl3_ctx::EV_CHUNK + k], 0));
+		if (dw_dev) {
+			// dW += (columns of the gathered x)^T dY over the strip's rows m = n + N * (oh + OH * ow); db from the same read
+			GatherGeom gw = fwd_gather(g->n, g->h, g->w, g->c, oh, ow, g->f, g);
+			gw.w_stap = 1; gw.w_sr = T; gw.w_sj = T * g->c;
+			gw.m_first = (long long) g->n * oh * ys.w0[k];
+			gw.m_count = (long long) g->n * oh * (ys.w0[k + 1] - ys.w0[k]);
+			CATTL3_CHECK(tc_wgrad_f32(ctx, gw, x_dev, dyd, dw_dev, db_dev));
+			ctx->last_path = "tcgen05";
+		}
+		// every strip of dX whose last needed column of dY has now arrived
+		while (dxd && done_dx < xs.count) {
+			int need = (xs.w0[done_dx + 1] - 1) + g->pw;   // source column = iw + pw - rw * (dw + 1), largest at rw = 0
+			if (need > ow - 1) need = ow - 1;
+			if (need >= ys.w0[k + 1]) break;
+			const int j = done_dx++;
+			GatherGeom gd = bwd_gather(g->n, oh, ow, g->f, g->h, xs.w0[j + 1] - xs.w0[j], g->c, g);
+			gd.w_stap = 1; gd.w_sr = T * g->c; gd.w_sj = T;
+			gd.cw += xs.w0[j] * gd.aw;
+			gd.out_H = g->h; gd.out_W = g->w; gd.out_w0 = xs.w0[j];
+			CATTL3_CHECK(tc_gather_gemm_f32(ctx, gd, dyd, w_dev, nullptr, 0, dxd, nullptr));
+			CATTL3_CUDA(cudaEventRecord(ev[cattl3_ctx::EV_CHUNK + ys.count + j], ctx->stream));
+			CATTL3_CUDA(cudaStreamWaitEvent(ctx->down_stream, ev[cattl3_ctx::EV_CHUNK + ys.count + j], 0));
+			const size_t off = (size_t) g->n * g->h * xs.w0[j];
+			CATTL3_CUDA(cudaMemcpy2DAsync(dx_host + off, x_pitch, dxd + off, x_pitch, sizeof(float) * (size_t) g->n * g->h * (xs.w0[j + 1] - xs.w0[j]),
+					(size_t) g->c, cudaMemcpyDeviceToHost, ctx->down_stream));
+		}
+	}
+	return CATTL3_OK;
+}
+
 }  // namespace
 
 int cattl3_host_wait(cattl3_ctx* ctx) {
@@ -908,11 +1026,18 @@ int cattl3_conv_forward_host_async_f32(cattl3_ctx* ctx, const cattl3_conv_geom* 
 	// the upload of x follows everything enqueued so far that may still read the buffer it lands in
 	CATTL3_CUDA(cudaEventRecord(ev[cattl3_ctx::EV_ENTRY], ctx->stream));
 	CATTL3_CUDA(cudaStreamWaitEvent(ctx->up_stream, ev[cattl3_ctx::EV_ENTRY], 0));
+	if (ctx->host_ev_used[cattl3_ctx::EV_Y_FREE])   // an earlier forward's download of the y stage
+		CATTL3_CUDA(cudaStreamWaitEvent(ctx->stream, ev[cattl3_ctx::EV_Y_FREE], 0));
+	if (b_dev && host_strips_ok(ctx, g, oh, ow)) {
+		// strips of image columns: uploads, kernels and downloads overlap from the first strip on
+		CATTL3_CHECK(host_forward_strips(ctx, g, oh, ow, x_host, w_dev, b_dev, y_host, xd, yd));
+		CATTL3_CUDA(cudaEventRecord(ev[cattl3_ctx::EV_Y_FREE], ctx->down_stream));
+		ctx->host_ev_used[cattl3_ctx::EV_Y_FREE] = true;
+		return CATTL3_OK;
+	}
 	CATTL3_CUDA(cudaMemcpyAsync(xd, x_host, xb, cudaMemcpyHostToDevice, ctx->up_stream));
 	CATTL3_CUDA(cudaEventRecord(ev[cattl3_ctx::EV_UP], ctx->up_stream));
 	CATTL3_CUDA(cudaStreamWaitEvent(ctx->stream, ev[cattl3_ctx::EV_UP], 0));
-	if (ctx->host_ev_used[cattl3_ctx::EV_Y_FREE])   // an earlier forward's download of the y stage
-		CATTL3_CUDA(cudaStreamWaitEvent(ctx->stream, ev[cattl3_ctx::EV_Y_FREE], 0));
 	const int fc = host_chunk_filters(g);
 	cattl3_conv_geom gc = *g;
 	gc.f = fc;
@@ -957,6 +1082,16 @@ int cattl3_conv_backward_host_async_f32(cattl3_ctx* ctx, const cattl3_conv_geom*
 		CATTL3_CUDA(cudaStreamWaitEvent(ctx->up_stream, ev[cattl3_ctx::EV_DY_FREE], 0));
 	if (dxd && ctx->host_ev_used[cattl3_ctx::EV_DX_FREE])   // an earlier backward's download of the dX stage
 		CATTL3_CUDA(cudaStreamWaitEvent(ctx->stream, ev[cattl3_ctx::EV_DX_FREE], 0));
+	if (host_strips_ok(ctx, g, oh, ow) && (!dw_dev) == (!db_dev)) {
+		CATTL3_CHECK(host_backward_strips(ctx, g, oh, ow, x_dev, w_dev, dy_host, dw_dev, db_dev, dx_host, dyd, dxd));
+		CATTL3_CUDA(cudaEventRecord(ev[cattl3_ctx::EV_DY_FREE], ctx->stream));
+		ctx->host_ev_used[cattl3_ctx::EV_DY_FREE] = true;
+		if (dx_host) {
+			CATTL3_CUDA(cudaEventRecord(ev[cattl3_ctx::EV_DX_FREE], ctx->down_stream));
+			ctx->host_ev_used[cattl3_ctx::EV_DX_FREE] = true;
+		}
+		return CATTL3_OK;
+	}
 	cattl3_conv_geom gc = *g;
 	gc.f = fc;
 	for (int f0 = 0, k = 0; f0 < g->f; f0 += fc, ++k) {

@@ -59,7 +59,7 @@ struct cattl3_ctx {
 	void* stage_dev[5] = { nullptr, nullptr, nullptr, nullptr, nullptr };
 	size_t stage_dev_bytes[5] = { 0, 0, 0, 0, 0 };
 	cudaStream_t up_stream = nullptr, down_stream = nullptr;
-	static constexpr int HOST_MAX_CHUNKS = 8;
+	static constexpr int HOST_MAX_CHUNKS = 16;
 	enum { EV_ENTRY = 0, EV_UP, EV_Y_FREE, EV_DY_FREE, EV_DX_FREE, EV_CHUNK, HOST_EVENTS = EV_CHUNK + HOST_MAX_CHUNKS };
 	cudaEvent_t host_ev[HOST_EVENTS] = {};
 	bool host_ev_used[HOST_EVENTS] = {};
@@ -126,6 +126,9 @@ struct GatherGeom {
 	// output lattice: element (n, i, j) of the OH x OW grid is stored at pixel (out_h0 + out_hs*i, out_w0 + out_ws*j)
 	// of an out_H x out_W tensor; out_H == 0 means the dense OH x OW tensor itself
 	int out_h0 = 0, out_hs = 1, out_H = 0, out_w0 = 0, out_ws = 1, out_W = 0;
+	// ---- used by the tcgen05 weight gradient only: the reduction covers rows [m_first, m_first + m_count) of the M = N*OH*OW rows
+	// of the plain tensor (a strip of output columns while the rest is still being uploaded, api.cu); m_count == 0 means all
+	long long m_first = 0, m_count = 0;
 };
 
 // A kernel layer's fused epilogue (cattl3_epilogue, already validated): activation and / or column statistics.

@@ -1123,7 +1123,7 @@ struct TcWgradParams {
 	int boxes;         // T * rchunks
 	int boxes_per_tile, col_tiles, j_tiles, splits;
 	int BNW;           // boxes_per_tile * RB: columns of the accumulator (<= 192)
-	long long mgroups, mg_per_split;
+	long long mgroups, mg_per_split, mg_base;   // the k-blocks [mg_base, mg_base + mgroups) of 32 rows are reduced
 	int stages;
 	int flush;         // k-blocks accumulated in TMEM before the partial tile is folded into fp32 scratch
 	long long w_stap, w_sr, w_sj, dw_elems;
@@ -1171,9 +1171,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_wgrad_kernel(const __grid_co
 	int nboxes = p.boxes - box0;
 	if (nboxes > my_boxes) nboxes = my_boxes;
 	if (nboxes < 0) nboxes = 0;
-	const long long mg0 = (long long) z * p.mg_per_split;
+	const long long mg0 = p.mg_base + (long long) z * p.mg_per_split;
 	long long mg1 = mg0 + p.mg_per_split;
-	if (mg1 > p.mgroups) mg1 = p.mgroups;
+	if (mg1 > p.mg_base + p.mgroups) mg1 = p.mg_base + p.mgroups;
 	const long long kblocks = mg1 > mg0 ? mg1 - mg0 : 0;
 	const long long chunks = (kblocks + p.flush - 1) / p.flush;
 
@@ -1521,7 +1521,8 @@ int tc_wgrad_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, const 
 	}
 	if (ctas == 2 && p.BNW % 32) { set_error("wgrad: pair tile of %d columns", p.BNW); return CATTL3_ERR_UNSUPPORTED; }
 	p.j_tiles = round_up((gg.J + TC_BM - 1) / TC_BM, ctas);   // 128-row tiles, whole pairs
-	p.mgroups = M / WG_KB;
+	p.mgroups = (gg.m_count ? gg.m_count : M) / WG_KB;
+	p.mg_base = gg.m_first / WG_KB;
 	const int tiles = p.col_tiles * p.j_tiles;
 	long long splits = ctx->sm_count / tiles;
 	if (splits < 1) splits = 1;

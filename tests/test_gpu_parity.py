@@ -342,7 +342,7 @@ def test_config2_full_size_vs_unmodified_reference(U, ref, dt, n):
         assert e < C.TOL[np.dtype(dt)], (k, e)
 
 
-@pytest.mark.parametrize("chunks", ["1", "4"])
+@pytest.mark.parametrize("chunks", ["1", "4", "strips2", "strips4"])
 def test_conv_host_entry_points_vs_oracle(U, orc, chunks, monkeypatch):
     """cattl3_conv_forward_host_f32 / cattl3_conv_backward_host_f32 (+ the _async forms and cattl3_host_wait): host
     tensors in and out, the copies pipelined with the kernels over chunks of filters on three streams, against the
@@ -363,7 +363,11 @@ def test_conv_host_entry_points_vs_oracle(U, orc, chunks, monkeypatch):
     wd, bd = U.dev(w), U.dev(b)
     dwd, dbd = U.zeros(w.shape, np.float32), U.zeros(b.shape, np.float32)
     xkeep = U.zeros(x.shape, np.float32)
-    monkeypatch.setenv("CATTL3_HOST_CHUNKS", chunks)
+    if chunks.startswith("strips"):   # strips of image columns (stride-1 layers on the tensor-core path), else chunks of filters
+        monkeypatch.setenv("CATTL3_HOST_STRIPS", chunks[6:])
+    else:
+        monkeypatch.setenv("CATTL3_NO_HOST_STRIPS", "1")
+        monkeypatch.setenv("CATTL3_HOST_CHUNKS", chunks)
     torch.cuda.synchronize()
     c.conv_forward_host_async(cg, xh, wd, bd, yh[0], xkeep)
     c.conv_backward_host_async(cg, xkeep, wd, dyh, dwd, dbd, dxh[0])
