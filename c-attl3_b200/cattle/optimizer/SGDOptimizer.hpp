@@ -539,7 +539,9 @@ private:
 				step_mode = STEP_CAPTURE;
 				_update_params(params_vec, epoch - 1, timestep);
 				step_mode = STEP_EAGER;
-			} catch (const b200::Error&) {
+			} catch (...) {
+				// whatever was thrown (a b200::Error, or anything a user-defined layer / optimizer throws): the stream must
+				// leave capture mode below before the step can be retried eagerly
 				step_mode = STEP_EAGER;
 				ok = false;
 			}

@@ -89,6 +89,8 @@ static GatherGeom bwd_gather(int N, int SH, int SW, int SC, int OH, int OW, int 
 	return gg;
 }
 
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 template<typename S> struct IsFloat { static constexpr bool value = false; };
 template<> struct IsFloat<float> { static constexpr bool value = true; };
 
@@ -119,7 +121,10 @@ static int run_gather_gemm(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, 
 		int bias_mode, S* out, const EpilogueArgs* ep = nullptr) {
 	// ep: fused activation and / or column statistics.  The tcgen05 kernel does both in its epilogue; the SIMT kernel
 	// fuses the activation, and the statistics are then one reduction pass over the finished output.
-	const bool tensor_ok = ctx->conv_path != CATTL3_PATH_SIMT && ctx->conv_path != CATTL3_PATH_FMA;
+	// (a tensor at an address that is not 16-byte aligned -- a slice of a larger buffer -- takes the FMA / SIMT kernels
+	// instead of failing in the TMA descriptor)
+	const bool tensor_ok = ctx->conv_path != CATTL3_PATH_SIMT && ctx->conv_path != CATTL3_PATH_FMA && aligned16(src) &&
+			(!out || aligned16(out));
 	if (IsFloat<S>::value && tensor_ok && tc_gather_gemm_supported(ctx, gg)) {
 		ctx->last_path = "tcgen05";
 		if (ep && ep->col_stats && gg.J >= 256 && out && bias_mode == 1) {
@@ -212,7 +217,7 @@ template<typename S>
 static int run_wgrad(cattl3_ctx* ctx, const GatherGeom& gg, const S* src, const S* plain, S* dw, S* db_colsum = nullptr,
 		bool* db_done = nullptr) {
 	if (db_done) *db_done = false;
-	const bool tensor_ok = ctx->conv_path != CATTL3_PATH_SIMT && ctx->conv_path != CATTL3_PATH_FMA;
+	const bool tensor_ok = ctx->conv_path != CATTL3_PATH_SIMT && ctx->conv_path != CATTL3_PATH_FMA && aligned16(src) && aligned16(plain);
 	if (IsFloat<S>::value && tensor_ok && tc_wgrad_supported(ctx, gg)) {
 		ctx->last_path = "tcgen05";
 		if (db_done) *db_done = db_colsum != nullptr;

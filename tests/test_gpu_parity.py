@@ -252,6 +252,32 @@ def test_conv_tcgen05_matches_simt_tightly(U):
     assert C.relerr(a["dw"], s["dw"]) < 1e-5
 
 
+def test_unaligned_tensors_fall_back_instead_of_failing(U, orc):
+    """A tensor that starts 4 bytes into a larger buffer cannot be described to TMA (16-byte alignment): the layer must run
+    on the FMA / SIMT kernels, not fail (a C-ABI caller passing a slice)."""
+    import torch
+    case = C.CONV_CASES["c2_small"]
+    g, x, w, b, dy = C.conv_inputs(case, np.float32, 34)
+    r = orc.conv(g, x, w, b, dy)
+    c = U.ctx()
+    cg = U.pkg.ConvGeom(*case)
+    big = torch.zeros(x.size + 1, device="cuda")
+    xd = big[1:]
+    xd.copy_(U.dev(x))
+    assert xd.data_ptr() % 16 == 4
+    wd, bd, dyd = U.dev(w), U.dev(b), U.dev(dy)
+    yd, dxd = U.zeros(dy.shape, np.float32), U.zeros(x.shape, np.float32)
+    dwd, dbd = U.zeros(w.shape, np.float32), U.zeros(b.shape, np.float32)
+    c.conv_forward(cg, xd, wd, bd, yd)
+    assert c.last_path != "tcgen05"
+    c.conv_backward(cg, xd, wd, dyd, dwd, dbd, dxd)
+    c.synchronize()
+    tol = C.TOL[np.dtype(np.float32)]
+    assert C.relerr(U.host(yd, dy.shape), r["y"]) < tol
+    assert C.relerr(U.host(dwd, w.shape), r["dw"]) < tol
+    assert C.relerr(U.host(dxd, x.shape), r["dx"]) < tol
+
+
 def test_tcgen05_path_refuses_unsupported_shapes(U):
     case = C.CONV_CASES["gt_rank3"]  # batch 5: no 32-row TMA boxes
     g, x, w, b, dy = C.conv_inputs(case, np.float32, 33)
