@@ -295,6 +295,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    all_cores = os.sched_getaffinity(0)
     numa_cores = pin_to_gpu_numa_node(local_rank)
     dist = None
     if world > 1:
@@ -468,6 +469,7 @@ def main():
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         keep = {}
+        os.sched_setaffinity(0, all_cores)   # the CPU baseline gets every host core again, not just the ones next to the GPU
         v, cores, kind, desc = reference_sample(32, 2, keep)
         line["cpu_baseline"] = {"value": round(v, 2), "unit": "samples/s", "cores": cores, "kind": kind, "sample": desc}
         line["parity"] = parity_against(ctx, pkg, keep, 32)
