@@ -69,6 +69,7 @@ public:
 		drop_graph();
 		carried_graph_loss = 0;
 		graphs_failed = false;
+		fused_step_seen = false;
 		eager_steps_at_shape = 0;
 		exchange = GradientExchange();
 		std::vector<Parameters<Scalar>*> params_vec = net.get_all_unique_params();
@@ -121,7 +122,9 @@ protected:
 							eager_shape_rows = obs.rows;
 							eager_steps_at_shape = 0;
 						}
-						if (eager_steps_at_shape >= 2)
+						// (only optimizers whose _update_params goes through fused_step() can be replayed: a user-defined
+						// subclass that updates through get_grad / set_values would apply a real host update per call)
+						if (eager_steps_at_shape >= 2 && fused_step_seen)
 							graph.reset(new StepGraph(obs.rows, obs.size(), obj.size()));
 					}
 					if (graph && graph->rows == obs.rows &&
@@ -250,6 +253,7 @@ protected:
 	inline void fused_step(const std::vector<Parameters<Scalar>*>& params_vec, cattl3_opt_step step) {
 		step.reset_grad = 1;
 		step.l2_lambda = 0;  // Parameters::regularize() has already added the penalty's derivative
+		fused_step_seen = true;
 		if (step_mode == STEP_SCALARS_ONLY) {
 			// a step graph replays the launches; only this step's scalars travel (one small upload from pinned memory)
 			graph->publish_scalars(step);
@@ -899,6 +903,7 @@ private:
 	std::unique_ptr<StepGraph> graph;
 	std::size_t eager_steps_at_shape = 0, eager_shape_rows = 0, eager_step_bytes = 0;
 	bool graphs_failed = false;
+	bool fused_step_seen = false;
 	double carried_graph_loss = 0;
 	b200::DeviceBuffer<double> reg_accum;   // penalties of the device-regularised parameters, summed over the epoch's steps
 	StepMode step_mode = STEP_EAGER;
