@@ -67,7 +67,7 @@ _lib = None
 _VOID_P = ctypes.c_void_p
 _SYMBOLS = [
     "cattl3_abi_version", "cattl3_last_error", "cattl3_device_count", "cattl3_ctx_create",
-    "cattl3_ctx_destroy", "cattl3_ctx_synchronize", "cattl3_ctx_throttle", "cattl3_ctx_set_conv_path", "cattl3_ctx_launch_count",
+    "cattl3_ctx_destroy", "cattl3_ctx_synchronize", "cattl3_ctx_throttle", "cattl3_ctx_set_conv_path", "cattl3_weights_stable_begin", "cattl3_weights_stable_end", "cattl3_ctx_launch_count",
     "cattl3_ctx_last_path", "cattl3_ctx_stream", "cattl3_malloc", "cattl3_free", "cattl3_memset",
     "cattl3_memcpy_h2d", "cattl3_memcpy_d2h", "cattl3_memcpy_d2d", "cattl3_memcpy_2d", "cattl3_host_alloc", "cattl3_host_free",
     "cattl3_conv_output_dims", "cattl3_pool_output_dims", "cattl3_feed_create", "cattl3_feed_destroy", "cattl3_feed_push",

@@ -103,6 +103,25 @@ private:
 };
 
 /** Scalar -> `_f32` / `_f64` entry points. */
+/**
+ * While one of these lives no parameter changes (a training step up to its update): the kernel layers keep their repacked
+ * weights per (array, geometry) and reuse them, e.g. across the time steps of an unrolled LSTM (cattl3_weights_stable_begin).
+ */
+struct WeightsStable {
+	inline WeightsStable() {
+		Context& c = Context::get();
+		Context::Lock l = c.lock();
+		CATTLE_B200_CHECK(cattl3_weights_stable_begin(c.handle()));
+	}
+	inline ~WeightsStable() {
+		Context& c = Context::get();
+		Context::Lock l = c.lock();
+		cattl3_weights_stable_end(c.handle());
+	}
+	WeightsStable(const WeightsStable&) = delete;
+	WeightsStable& operator=(const WeightsStable&) = delete;
+};
+
 template<typename Scalar> struct Api;
 
 #define CATTLE_B200_API(S, SUF) \

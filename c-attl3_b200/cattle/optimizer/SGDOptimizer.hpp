@@ -140,6 +140,7 @@ protected:
 				}
 				const std::int64_t allocated_before = cattl3_ctx_allocated_bytes(b200::Context::get().handle());
 				if (!obs.empty()) {
+					b200::WeightsStable no_update_until_the_end_of_the_passes;
 					b200::DeviceTensor<Scalar> out = dev_net->propagate_dev(std::move(obs), true);
 					step_losses.emplace_back();
 					step_loss_weights.push_back(1.0 / replicas);
@@ -163,6 +164,7 @@ protected:
 				// the whole step in HBM: one upload of the mini-batch, then propagate -> loss -> back-propagate
 				// without a host round trip; the per-sample losses are collected at the end of the epoch
 				// (the uploads go through the input feeds: staged on a copy stream, they overlap the previous step)
+				b200::WeightsStable no_update_until_the_end_of_the_passes;
 				b200::DeviceTensor<Scalar> obj = fed(1, data_pair.second);
 				b200::DeviceTensor<Scalar> out = dev_net->propagate_dev(fed(0, data_pair.first), true);
 				step_losses.emplace_back();
@@ -172,6 +174,7 @@ protected:
 				exchange_begin(params_vec, comm);
 				dev_net->backpropagate_dev(std::move(out_grad));
 			} else if (data_pair.first.dimension(0) > 0) {
+				b200::WeightsStable no_update_until_the_end_of_the_passes;
 				typename Base::Data out = net.propagate(std::move(data_pair.first), true);
 				obj_loss += Base::loss->function(out, data_pair.second).sum() / (double) replicas;
 				// dividing by the nominal batch size decouples the learning rate from the batch size and
@@ -524,6 +527,7 @@ private:
 						b200::DeviceBuffer<Scalar>::view(g.obs->data(), g.obs->size()));
 				obj_view.buf = std::make_shared<b200::DeviceBuffer<Scalar>>(
 						b200::DeviceBuffer<Scalar>::view(g.obj->data(), g.obj->size()));
+				std::unique_ptr<b200::WeightsStable> no_update(new b200::WeightsStable());
 				b200::DeviceTensor<Scalar> out = dev_net.propagate_dev(std::move(obs_view), true);
 				b200::DeviceTensor<Scalar> out_grad = dev_loss.loss_and_gradient_dev(out, obj_view, (Scalar) batch_size,
 						g.loss_rows);
@@ -534,6 +538,7 @@ private:
 							g.loss_rows.data()));
 				}
 				dev_net.backpropagate_dev(std::move(out_grad));
+				no_update.reset();
 				// data parallel: the exchange (and the statistics all-reduces of synchronised BatchNorm layers inside the
 				// passes above) are NCCL operations on the capturing stream -- they become nodes of the step graph
 				if (b200::Communicator::get().world_size() > 1)

@@ -408,6 +408,8 @@ int cattl3_ctx_destroy(cattl3_ctx* ctx) {
 	cudaStreamSynchronize(ctx->stream);
 	if (ctx->ws) cudaFree(ctx->ws);
 	if (ctx->tc_w) cudaFree(ctx->tc_w);
+	for (int i = 0; i < cattl3_ctx::MAX_PACK_SLOTS; ++i)
+		if (ctx->pack_slots[i].buf) cudaFree(ctx->pack_slots[i].buf);
 	if (ctx->stat_ws) cudaFree(ctx->stat_ws);
 	if (ctx->reg_ws) cudaFree(ctx->reg_ws);
 	if (ctx->con_ws) cudaFree(ctx->con_ws);
@@ -573,6 +575,19 @@ int cattl3_ctx_throttle(cattl3_ctx* ctx, int max_in_flight) {
 int cattl3_ctx_synchronize(cattl3_ctx* ctx) {
 	CATTL3_CHECK(check_ctx(ctx));
 	CATTL3_CUDA(cudaStreamSynchronize(ctx->stream));
+	return CATTL3_OK;
+}
+
+int cattl3_weights_stable_begin(cattl3_ctx* ctx) {
+	CATTL3_CHECK(check_ctx(ctx));
+	ctx->pack_stable = true;
+	ctx->pack_used = 0;
+	return CATTL3_OK;
+}
+int cattl3_weights_stable_end(cattl3_ctx* ctx) {
+	CATTL3_CHECK(check_ctx(ctx));
+	ctx->pack_stable = false;
+	ctx->pack_used = 0;
 	return CATTL3_OK;
 }
 

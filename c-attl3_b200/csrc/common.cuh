@@ -22,6 +22,16 @@ struct cattl3_ctx {
 	// tcgen05 path scratch: the weights repacked K-major and split hi | lo for TMA
 	void* tc_w = nullptr;
 	size_t tc_w_bytes = 0;
+	// Between cattl3_weights_stable_begin and _end the caller promises not to change any weights: a kernel layer's packed
+	// weights are then kept per (weight array, geometry) and reused by later calls (the cells of an unrolled LSTM share their
+	// kernels' weights: one repack per pass instead of one per time step).  Slots are handed out in call order and keep their
+	// buffers from scope to scope, so a step that repeats the previous one allocates nothing (a captured step never may).
+	struct PackKey { const void* w; int RH, RW, SC, J, r_pad, j_pad, tapbox, pad_; long long w_off, w_stap, w_srw, w_sr, w_sj; };
+	struct PackSlot { void* buf; size_t bytes; PackKey key; };
+	static constexpr int MAX_PACK_SLOTS = 96;
+	PackSlot pack_slots[MAX_PACK_SLOTS] = {};
+	int pack_used = 0;
+	bool pack_stable = false;
 	// per-CTA column sums of a fused batch-norm statistics epilogue (conv_tc.cu)
 	void* stat_ws = nullptr;
 	size_t stat_ws_bytes = 0;

@@ -17,6 +17,7 @@
 // column as 32 consecutive floats per warp: y(m + M*f) is written fully coalesced.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "activations.cuh"
 
@@ -632,6 +633,52 @@ __global__ void __launch_bounds__((2 + NEPI + NCONV) * 32, 1) tc_gather_gemm_ker
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
+// The packed (K-major, hi | lo) weights of a gather GEMM: repacked into the context's scratch, or -- inside a
+// cattl3_weights_stable scope -- found in / added to the scope's slots.
+static int packed_weights(cattl3_ctx* ctx, const GatherGeom& gg, int r_pad, int j_pad, int tapbox, const float* w, long long w_elems,
+		float** w_packed) {
+	const size_t bytes = (size_t) w_elems * 8;
+	float* dst = nullptr;
+	if (ctx->pack_stable) {
+		cattl3_ctx::PackKey key;
+		memset(&key, 0, sizeof(key));
+		key.w = w; key.RH = gg.RH; key.RW = gg.RW; key.SC = gg.SC; key.J = gg.J; key.r_pad = r_pad; key.j_pad = j_pad; key.tapbox = tapbox;
+		key.w_off = gg.w_off; key.w_stap = gg.w_stap; key.w_srw = gg.w_srw; key.w_sr = gg.w_sr; key.w_sj = gg.w_sj;
+		for (int i = 0; i < ctx->pack_used; ++i) {
+			if (memcmp(&ctx->pack_slots[i].key, &key, sizeof(key)) == 0) {
+				*w_packed = (float*) ctx->pack_slots[i].buf;
+				return CATTL3_OK;
+			}
+		}
+		if (ctx->pack_used < cattl3_ctx::MAX_PACK_SLOTS) {
+			cattl3_ctx::PackSlot& slot = ctx->pack_slots[ctx->pack_used];
+			if (slot.bytes < bytes) {
+				if (ctx->capturing) {
+					set_error("packed-weight slot %d would have to grow during a graph capture", ctx->pack_used);
+					return CATTL3_ERR_UNSUPPORTED;
+				}
+				if (slot.buf) CATTL3_CUDA(cudaFree(slot.buf));   // (synchronises: nothing in flight still reads it)
+				slot.buf = nullptr; slot.bytes = 0;
+				CATTL3_CUDA(cudaMalloc(&slot.buf, bytes));
+				slot.bytes = bytes;
+			}
+			slot.key = key;
+			++ctx->pack_used;
+			dst = (float*) slot.buf;
+		}
+	}
+	if (!dst) {
+		CATTL3_CHECK(ensure_buffer(ctx, &ctx->tc_w, &ctx->tc_w_bytes, bytes));
+		dst = (float*) ctx->tc_w;
+	}
+	const int T = tapbox ? gg.RH : gg.RH * gg.RW;
+	(void) T;
+	pack_weights_kernel<<<ew_grid(ctx, w_elems, 256), 256, 0, ctx->stream>>>(gg, r_pad, j_pad, tapbox, w, dst);
+	CATTL3_LAUNCHED(ctx);
+	*w_packed = dst;
+	return CATTL3_OK;
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
 		const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
 		CUtensorMapFloatOOBfill);
@@ -748,10 +795,8 @@ int tc_gather_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* src, 
 	const int T = tapbox ? gg.RH : gg.RH * gg.RW;   // k-blocks per channel chunk
 	const long long w_elems = (long long) T * j_pad * r_pad;
 
-	CATTL3_CHECK(ensure_buffer(ctx, &ctx->tc_w, &ctx->tc_w_bytes, (size_t) w_elems * 8));
-	float* w_packed = (float*) ctx->tc_w;
-	pack_weights_kernel<<<ew_grid(ctx, w_elems, 256), 256, 0, ctx->stream>>>(gg, r_pad, j_pad, tapbox ? 1 : 0, w, w_packed);
-	CATTL3_LAUNCHED(ctx);
+	float* w_packed = nullptr;
+	CATTL3_CHECK(packed_weights(ctx, gg, r_pad, j_pad, tapbox ? 1 : 0, w, w_elems, &w_packed));
 
 	CUtensorMap tm_a, tm_b;
 	{
@@ -1061,10 +1106,8 @@ static int tc_rows_gemm_f32(cattl3_ctx* ctx, const GatherGeom& gg, const float* 
 	const int BN = round_up(gg.J, 32);
 	const int r_pad = round_up(gg.SC, ROWS_KB);
 	const long long w_elems = (long long) T * BN * r_pad;
-	CATTL3_CHECK(ensure_buffer(ctx, &ctx->tc_w, &ctx->tc_w_bytes, (size_t) w_elems * 8));
-	float* w_packed = (float*) ctx->tc_w;
-	pack_weights_kernel<<<ew_grid(ctx, w_elems, 256), 256, 0, ctx->stream>>>(gg, r_pad, BN, 0, w, w_packed);
-	CATTL3_LAUNCHED(ctx);
+	float* w_packed = nullptr;
+	CATTL3_CHECK(packed_weights(ctx, gg, r_pad, BN, 0, w, w_elems, &w_packed));
 	CUtensorMap tm_a, tm_b;
 	{
 		cuuint64_t dims[4] = { (cuuint64_t) gg.N, (cuuint64_t) gg.SH, (cuuint64_t) gg.SW, (cuuint64_t) gg.SC };

@@ -171,6 +171,11 @@ int cattl3_ctx_synchronize(cattl3_ctx* ctx);
 /* Bounded run-ahead for an asynchronous step loop: marks "now" on the context's stream and blocks the host until the
  * mark made max_in_flight calls earlier has been reached (call once per training step). */
 int cattl3_ctx_throttle(cattl3_ctx* ctx, int max_in_flight);
+/* Between _begin and _end the caller promises that no weight array changes (a training step up to its optimizer update): the
+ * kernel layers then keep the repacked (K-major, hi | lo split) weights of each (array, geometry) they meet and reuse them, e.g.
+ * across the time steps of an unrolled LSTM whose cells share their kernels (LSTMNeuralNetwork.hpp:249-252).  Scopes do not nest. */
+int cattl3_weights_stable_begin(cattl3_ctx*);
+int cattl3_weights_stable_end(cattl3_ctx*);
 int cattl3_ctx_set_conv_path(cattl3_ctx* ctx, int path);
 /* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
 int64_t cattl3_ctx_launch_count(const cattl3_ctx* ctx);
