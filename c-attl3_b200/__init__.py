@@ -433,5 +433,14 @@ def make_opt_step(kind, hyper, timestep, epoch, l2_lambda=0.0, reset_grad=True, 
 def shard_rows(n, rank, world):
     """Rows [lo, hi) of an n-row mini-batch that rank `rank` of `world` keeps -- the same split as
     cattle::SGDOptimizer::shard (cattle/optimizer/SGDOptimizer.hpp): contiguous, covers every row once,
-    sizes differ by at most one."""
+    sizes differ by at most one.  A batch with fewer rows than ranks (a ragged last one) is not split at all: every rank
+    takes all of it and the loop divides the loss gradient by the world size as well (replicas(n, world)), so that no rank
+    sits out the collectives of the step."""
+    if n < world:
+        return 0, n
     return n * rank // world, n * (rank + 1) // world
+
+
+def replicas(n, world):
+    """How many ranks process the SAME rows of an n-row mini-batch (1, or `world` for a batch smaller than the world)."""
+    return world if world > 1 and n < world else 1

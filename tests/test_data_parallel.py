@@ -47,6 +47,17 @@ ok_y = np.allclose(part["y"], full["y"][lo:hi], rtol=0, atol=1e-13)
 ok_dx = np.allclose(part["dx"], full["dx"][lo:hi], rtol=0, atol=1e-13)
 sizes = [pkg.shard_rows(7, r, 3) for r in range(3)]
 assert sizes == [(0, 2), (2, 4), (4, 7)], sizes
+# a ragged last batch with fewer rows than ranks: every rank takes all of it, the loss gradient is divided by the world size as
+# well, and the all-reduced gradient is still the single-process one (no rank skips the step and its collectives)
+assert [pkg.shard_rows(1, r, 2) for r in range(2)] == [(0, 1), (0, 1)] and pkg.replicas(1, 2) == 2 and pkg.replicas(6, 2) == 1
+g1 = binding.Geom(1, *case[1:])
+one = orc.conv(g1, np.asfortranarray(x[:1]), w, b, np.asfortranarray(dy[:1]))
+lo1, hi1 = pkg.shard_rows(1, rank, world)
+rep = orc.conv(g1, np.asfortranarray(x[lo1:hi1]), w, b, np.asfortranarray(dy[lo1:hi1] / pkg.replicas(1, world)))
+small = torch.from_numpy(np.concatenate([rep["dw"].ravel(order="F"), rep["db"].ravel(order="F")]))
+dist.all_reduce(small)
+want1 = np.concatenate([one["dw"].ravel(order="F"), one["db"].ravel(order="F")])
+assert float(np.max(np.abs(small.numpy() - want1)) / np.max(np.abs(want1))) < 1e-13
 print("RESULT", rank, err, ok_y, ok_dx)
 assert err < 1e-13 and ok_y and ok_dx
 dist.destroy_process_group()
