@@ -254,17 +254,31 @@ def double_extras(ctx, pkg, torch, dev, stream):
     return out
 
 
-def network_extras(world):
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("bench_networks", os.path.join(ROOT, "scripts", "bench_networks.py"))
-    bn = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(bn)
+def network_extras(world, dist=None):
+    """Configs 4 and 5 through the C++ batch loop (scripts/bench_networks.py), each in a child process of this rank with a
+    time limit: a secondary number must never be able to take the headline line down with it.  The ranks' children find each
+    other through an explicit NCCL id file (their parents differ, so the default name, which is tied to the parent, would not match)."""
+    import subprocess
     out = {}
     steps = 8 if world <= 2 else 4
+    script = os.path.join(ROOT, "scripts", "bench_networks.py")
+    nonce = [os.getpid()]
+    if dist is not None:
+        dist.broadcast_object_list(nonce, src=0)   # rank 0's pid names the id files of this launch: a leftover file never matches
     for cfg in (4, 5):
+        env = dict(os.environ)
+        env["CATTL3_COMM_ID_FILE"] = "/tmp/cattl3_nccl_id.bench.%s.%d.%d" % (os.environ.get("MASTER_PORT", "0"), nonce[0], cfg)
         try:
-            r = bn.run_network(cfg, steps=steps, epochs=3)
-            out["config%d" % cfg] = {k: r[k] for k in ("value", "unit", "n_gpus", "ms_per_step", "epoch_ms", "scaling", "config")}
+            r = subprocess.run([sys.executable, script, "--config", str(cfg), "--steps", str(steps), "--epochs", "3"], env=env,
+                               capture_output=True, text=True, timeout=240)
+            lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            if r.returncode != 0:
+                out["config%d" % cfg] = {"error": "exit code %d: %s" % (r.returncode, r.stderr.strip()[-200:])}
+            elif lines:
+                d = json.loads(lines[-1])
+                out["config%d" % cfg] = {k: d[k] for k in ("value", "unit", "n_gpus", "ms_per_step", "epoch_ms", "scaling", "config")}
+        except subprocess.TimeoutExpired:
+            out["config%d" % cfg] = {"error": "no result within 240 s"}
         except Exception as e:   # the shim is built by __graft_entry__.build(); say why if it cannot run
             out["config%d" % cfg] = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
     return out
@@ -481,7 +495,7 @@ def main():
         # BASELINE.json configs[3] and [4] through the product's own data-parallel batch loop (cattle::SGDOptimizer::_train
         # sharding + cattl3_comm_* exchange overlapped with the backward pass + synchronised BatchNorm; C++ host side,
         # scripts/bench_networks.py), same launch, weak scaling at 64 samples per GPU: secondary numbers beside the headline
-        line["networks"] = network_extras(world)
+        line["networks"] = network_extras(world, dist)
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
