@@ -671,8 +671,6 @@ static int packed_weights(cattl3_ctx* ctx, const GatherGeom& gg, int r_pad, int 
 		CATTL3_CHECK(ensure_buffer(ctx, &ctx->tc_w, &ctx->tc_w_bytes, bytes));
 		dst = (float*) ctx->tc_w;
 	}
-	const int T = tapbox ? gg.RH : gg.RH * gg.RW;
-	(void) T;
 	pack_weights_kernel<<<ew_grid(ctx, w_elems, 256), 256, 0, ctx->stream>>>(gg, r_pad, j_pad, tapbox, w, dst);
 	CATTL3_LAUNCHED(ctx);
 	*w_packed = dst;
