@@ -64,6 +64,22 @@ TCONV_CASES = {
     "dfma_t": (8, 9, 8, 24, 48, 3, 3, 1, 1, 2, 2, 0, 0),
 }
 
+# double, sized so that the producer-warp DMMA kernels run (conv_dmma.cu version 2: the grid must fill the device; weight
+# gradient: even batch, M >= 16384): ragged rows / channels / filters, 64- and 128-wide column tiles, every weight-gradient
+# tile shape (256 x 64, 128 x 128, 64 x 256), an odd batch (8-byte copies), a strided input gradient (den = 2)
+DMMA2_CASES = {
+    "d2_ragged": (64, 29, 27, 36, 40, 3, 3, 1, 1, 1, 1, 0, 0),
+    "d2_wide": (34, 30, 28, 9, 96, 3, 3, 1, 1, 1, 1, 0, 0),
+    "d2_odd": (65, 28, 28, 40, 72, 3, 3, 1, 1, 1, 1, 0, 0),
+    "d2_s2": (32, 57, 55, 40, 130, 3, 3, 1, 1, 2, 2, 0, 0),
+    "d2_dil": (64, 30, 30, 48, 64, 3, 3, 2, 2, 1, 1, 1, 1),
+    "d2_1x1": (64, 28, 28, 64, 256, 1, 1, 0, 0, 1, 1, 0, 0),
+}
+DMMA2_TCONV_CASES = {
+    "d2_t_s2": (64, 20, 20, 40, 40, 3, 3, 1, 1, 2, 2, 0, 0),
+    "d2_t_s1": (64, 28, 28, 40, 40, 2, 2, 0, 0, 1, 1, 0, 0),
+}
+
 # (n, in, out)
 DENSE_CASES = {
     "gt_rank1": (5, 32, 16),   # test/gradient_test.cpp:143-156

@@ -486,6 +486,31 @@ def test_conv_double_gemm_paths_vs_oracle(U, orc, tr, path, name_of_path):
             assert C.relerr(a[k], r[k]) < C.TOL[np.dtype(np.float64)], (name, k, C.relerr(a[k], r[k]))
 
 
+@pytest.mark.parametrize("tr", [False, True])
+def test_conv_double_producer_warp_kernels_vs_oracle(U, orc, tr, capfd, monkeypatch):
+    """The producer-warp DMMA kernels (conv_dmma.cu, version 2: cp.async ring + mbarriers, channel-outer reduction,
+    swizzled weight-gradient tiles) against the oracle at 1e-10 on shapes large enough for them to be chosen; the
+    launch trace on stderr says which kernel ran."""
+    monkeypatch.setenv("CATTL3_DMMA_TRACE", "1")
+    table = C.DMMA2_TCONV_CASES if tr else C.DMMA2_CASES
+    seen = ""
+    for name, case in table.items():
+        g, x, w, b, dy = C.conv_inputs(case, np.float64, 73, tr)
+        r = orc.conv(g, x, w, b, dy, transposed=tr, back_reps=2)
+        capfd.readouterr()
+        a = _conv_gpu(U, case, x, w, b, dy, tr, reps=2)
+        err = capfd.readouterr().err
+        assert a["path"] == "dmma" and "dmma2 gather" in err, (name, a["path"], err)
+        assert "dmma2 wgrad" in err or case[0] % 2 == 1, (name, err)
+        seen += err
+        for k in ("y", "dx", "dw", "db"):
+            assert C.relerr(a[k], r[k]) < C.TOL[np.dtype(np.float64)], (name, k, C.relerr(a[k], r[k]))
+    if not tr:   # both gather tiles, 16- and 8-byte copies, all three weight-gradient tiles
+        for what in ("gather tile 128 x 128 vec", "gather tile 256 x 64 vec", "gather tile 128 x 128\n", "wgrad tile 256 x 64",
+                     "wgrad tile 128 x 128", "wgrad tile 64 x 256"):
+            assert what in seen, (what, seen)
+
+
 def test_conv_dfma_matches_simt_at_size(U):
     """A mid-size double convolution (N=64, 14x14x64 -> 256, M = 12544, K = 576): the DMMA and DFMA kernels against the
     any-shape SIMT kernels, three independent implementations with different summation orders."""
