@@ -516,26 +516,51 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dmma2_gather_gemm_kernel(Gather
 		if (lane == 0) d2_mbar_arrive(&empty[s]);
 	}
 
+	// Epilogue in three straight-line passes (bias, activation with the switch over the kind OUTSIDE the element loop, stores):
+	// with the switch inside, the 128 elements of a thread were 128 jumps through 400 KB of code -- a fifth of the forward
+	// kernel's stall samples were instruction fetches of this part (profiles/README.md, r2k).
 	const long long P = (long long) gg.OH * gg.OW;
 	const int g = lane >> 2, kq = lane & 3;
-	#pragma unroll
-	for (int ni = 0; ni < NI; ++ni) {
+	if (bias_mode != 0) {
 		#pragma unroll
-		for (int e = 0; e < 2; ++e) {
-			const int j = j0 + col0 + 8 * ni + 2 * kq + e;
-			if (j >= J) continue;
-			const double bj = bias_mode == 1 ? __ldg(bias + j) : 0.0;
+		for (int ni = 0; ni < NI; ++ni) {
 			#pragma unroll
-			for (int mi = 0; mi < 8; ++mi) {
-				const long long m = m0 + row0 + 8 * mi + g;
-				if (m >= M) continue;
-				double v = acc[mi][ni][e] + bj;
-				if (bias_mode == 2) v += __ldg(bias + m / gg.N + P * j);
-				const long long o = m + M * j;
-				if (out) out[o] = v;
-				if (act_out) act_out[o] = act_fwd_rt<double>(act_kind, v, act_param);
+			for (int e = 0; e < 2; ++e) {
+				const int j = j0 + col0 + 8 * ni + 2 * kq + e;
+				if (j >= J) continue;
+				if (bias_mode == 1) {
+					const double bj = __ldg(bias + j);
+					#pragma unroll
+					for (int mi = 0; mi < 8; ++mi) acc[mi][ni][e] += bj;
+				} else {
+					#pragma unroll
+					for (int mi = 0; mi < 8; ++mi) {
+						const long long m = m0 + row0 + 8 * mi + g;
+						if (m < M) acc[mi][ni][e] += __ldg(bias + m / gg.N + P * j);
+					}
+				}
 			}
 		}
+	}
+	auto store = [&](double* __restrict__ dst) {
+		#pragma unroll
+		for (int ni = 0; ni < NI; ++ni) {
+			#pragma unroll
+			for (int e = 0; e < 2; ++e) {
+				const int j = j0 + col0 + 8 * ni + 2 * kq + e;
+				if (j >= J) continue;
+				#pragma unroll
+				for (int mi = 0; mi < 8; ++mi) {
+					const long long m = m0 + row0 + 8 * mi + g;
+					if (m < M) dst[m + M * j] = acc[mi][ni][e];
+				}
+			}
+		}
+	};
+	if (out) store(out);
+	if (act_out) {
+		act_fwd_rt_n<double, 8 * NI * 2>(act_kind, &acc[0][0][0], act_param);
+		store(act_out);
 	}
 }
 

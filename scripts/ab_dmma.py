@@ -36,6 +36,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true", help="results only, no timing")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--config2", action="store_true", help="config 2 only (the ncu capture runs this with --quick)")
     args = ap.parse_args()
     pkg = load_package()
     dev = torch.device("cuda", 0)
@@ -54,6 +55,8 @@ def main():
         ("transposed 2x2 stride 1", (64, 28, 28, 40, 40, 2, 2, 0, 0, 1, 1, 0, 0), True, False),
         ("config 2 (256 x 56 x 56 x 64 -> 256, 3x3)", (256, 56, 56, 64, 256, 3, 3, 1, 1, 1, 1, 0, 0), False, True),
     ]
+    if args.config2:
+        cases = cases[-1:]
     worst = 0.0
     for name, geom, transposed, timed in cases:
         g = pkg.ConvGeom(*geom)

@@ -25,12 +25,14 @@ def _tol(dt):
 FUSED_CONV = [("c2_small", np.float32, "tcgen05"), ("c2_small_f256", np.float32, "tcgen05"),
               ("ragged_c", np.float32, "tcgen05"), ("c2_stride2", np.float32, "tcgen05"),
               ("cifar_conv1", np.float32, "tiny"), ("gt_rank3", np.float64, "tiny"), ("c2_small", np.float64, "simt"),
-              ("ragged", np.float64, "tiny")]
+              ("ragged", np.float64, "tiny"),
+              # the producer-warp DMMA gather GEMM (128 x 128 and 256 x 64 tiles): activation behind the switch-free epilogue
+              ("d2_wide", np.float64, "dmma"), ("d2_ragged", np.float64, "dmma")]
 
 
 @pytest.mark.parametrize("name,dt,path", FUSED_CONV)
 def test_conv_fused_activation_matches_layer_chain(U, orc, name, dt, path):
-    case = C.CONV_CASES[name]
+    case = C.CONV_CASES.get(name) or C.DMMA2_CASES[name]
     g, x, w, b, dy = C.conv_inputs(case, dt, 41)
     oh, ow = conv_out_dims(g)
     shape = (g.n, oh, ow, g.f)
@@ -84,7 +86,7 @@ def test_transconv_fused_activation_matches_layer_chain(U, orc, name, dt):
 def test_conv_fused_batchnorm_statistics(U, orc, name, dt, path):
     """conv (epilogue: column sums) -> batchnorm_forward_stats (+ fused ReLU) equals conv -> BatchNormLayer -> ReLU,
     over two training steps so that the running averages take both branches (assign, then decay)."""
-    case = C.CONV_CASES[name]
+    case = C.CONV_CASES.get(name) or C.DMMA2_CASES[name]
     oh, ow = conv_out_dims(Geom(*case))
     c = U.ctx()
     cg = U.pkg.ConvGeom(*case)
