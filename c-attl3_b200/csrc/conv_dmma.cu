@@ -54,6 +54,60 @@ __device__ __forceinline__ void dmma_block(const double* __restrict__ As, const 
 	}
 }
 
+// Epilogue of the gather GEMMs in three straight-line passes (bias, activation with the switch over the kind OUTSIDE the
+// element loop, stores): with the switch inside, the elements of a thread were as many jumps through hundreds of KB of
+// code -- a fifth of the forward kernel's stall samples at config 2 were instruction fetches of this part
+// (profiles/README.md, r2k).  The lane holds rows 8 mi + lane / 4, columns 8 ni + 2 (lane % 4) + {0, 1} of the warp tile
+// whose first row / column are mw / jw.
+template<int NI>
+__device__ __forceinline__ void dmma_epilogue(double (&acc)[8][NI][2], const GatherGeom& gg, long long M, int J, long long mw, int jw,
+		int lane, const double* __restrict__ bias, int bias_mode, double* __restrict__ out, int act_kind, double act_param,
+		double* __restrict__ act_out) {
+	const long long P = (long long) gg.OH * gg.OW;
+	const int g = lane >> 2, kq = lane & 3;
+	if (bias_mode != 0) {
+		#pragma unroll
+		for (int ni = 0; ni < NI; ++ni) {
+			#pragma unroll
+			for (int e = 0; e < 2; ++e) {
+				const int j = jw + 8 * ni + 2 * kq + e;
+				if (j >= J) continue;
+				if (bias_mode == 1) {
+					const double bj = __ldg(bias + j);
+					#pragma unroll
+					for (int mi = 0; mi < 8; ++mi) acc[mi][ni][e] += bj;
+				} else {
+					#pragma unroll
+					for (int mi = 0; mi < 8; ++mi) {
+						const long long m = mw + 8 * mi + g;
+						if (m < M) acc[mi][ni][e] += __ldg(bias + m / gg.N + P * j);
+					}
+				}
+			}
+		}
+	}
+	auto store = [&](double* __restrict__ dst) {
+		#pragma unroll
+		for (int ni = 0; ni < NI; ++ni) {
+			#pragma unroll
+			for (int e = 0; e < 2; ++e) {
+				const int j = jw + 8 * ni + 2 * kq + e;
+				if (j >= J) continue;
+				#pragma unroll
+				for (int mi = 0; mi < 8; ++mi) {
+					const long long m = mw + 8 * mi + g;
+					if (m < M) dst[m + M * j] = acc[mi][ni][e];
+				}
+			}
+		}
+	};
+	if (out) store(out);
+	if (act_out) {
+		act_fwd_rt_n<double, 8 * NI * 2>(act_kind, &acc[0][0][0], act_param);
+		store(act_out);
+	}
+}
+
 // Gather GEMM: out[m + M*j] = bias + sum_{tap, r} src(m, tap, r) * w(tap, r, j) (+ fused activation).
 template<int NI>
 __global__ void __launch_bounds__(DM_THREADS, NI == 2 ? 2 : 1) dmma_gather_gemm_kernel(GatherGeom gg,
@@ -145,28 +199,7 @@ __global__ void __launch_bounds__(DM_THREADS, NI == 2 ? 2 : 1) dmma_gather_gemm_
 		__syncthreads();
 	}
 
-	// epilogue: lane holds rows 8 mi + lane / 4, columns 8 ni + 2 (lane % 4) + {0, 1} of the warp tile
-	const long long P = (long long) gg.OH * gg.OW;
-	const int g = lane >> 2, kq = lane & 3;
-	#pragma unroll
-	for (int ni = 0; ni < NI; ++ni) {
-		#pragma unroll
-		for (int e = 0; e < 2; ++e) {
-			const int j = j0 + col0 + 8 * ni + 2 * kq + e;
-			if (j >= J) continue;
-			const double bj = bias_mode == 1 ? __ldg(bias + j) : 0.0;
-			#pragma unroll
-			for (int mi = 0; mi < 8; ++mi) {
-				const long long m = m0 + row0 + 8 * mi + g;
-				if (m >= M) continue;
-				double v = acc[mi][ni][e] + bj;
-				if (bias_mode == 2) v += __ldg(bias + m / gg.N + P * j);
-				const long long o = m + M * j;
-				if (out) out[o] = v;
-				if (act_out) act_out[o] = act_fwd_rt<double>(act_kind, v, act_param);
-			}
-		}
-	}
+	dmma_epilogue<NI>(acc, gg, M, J, m0 + row0, j0 + col0, lane, bias, bias_mode, out, act_kind, act_param, act_out);
 }
 
 // Weight gradient: dw(tap, r, j) += sum_m src(m, tap, r) * plain[m + M*j]; rows of the output tile are the flattened
@@ -516,52 +549,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dmma2_gather_gemm_kernel(Gather
 		if (lane == 0) d2_mbar_arrive(&empty[s]);
 	}
 
-	// Epilogue in three straight-line passes (bias, activation with the switch over the kind OUTSIDE the element loop, stores):
-	// with the switch inside, the 128 elements of a thread were 128 jumps through 400 KB of code -- a fifth of the forward
-	// kernel's stall samples were instruction fetches of this part (profiles/README.md, r2k).
-	const long long P = (long long) gg.OH * gg.OW;
-	const int g = lane >> 2, kq = lane & 3;
-	if (bias_mode != 0) {
-		#pragma unroll
-		for (int ni = 0; ni < NI; ++ni) {
-			#pragma unroll
-			for (int e = 0; e < 2; ++e) {
-				const int j = j0 + col0 + 8 * ni + 2 * kq + e;
-				if (j >= J) continue;
-				if (bias_mode == 1) {
-					const double bj = __ldg(bias + j);
-					#pragma unroll
-					for (int mi = 0; mi < 8; ++mi) acc[mi][ni][e] += bj;
-				} else {
-					#pragma unroll
-					for (int mi = 0; mi < 8; ++mi) {
-						const long long m = m0 + row0 + 8 * mi + g;
-						if (m < M) acc[mi][ni][e] += __ldg(bias + m / gg.N + P * j);
-					}
-				}
-			}
-		}
-	}
-	auto store = [&](double* __restrict__ dst) {
-		#pragma unroll
-		for (int ni = 0; ni < NI; ++ni) {
-			#pragma unroll
-			for (int e = 0; e < 2; ++e) {
-				const int j = j0 + col0 + 8 * ni + 2 * kq + e;
-				if (j >= J) continue;
-				#pragma unroll
-				for (int mi = 0; mi < 8; ++mi) {
-					const long long m = m0 + row0 + 8 * mi + g;
-					if (m < M) dst[m + M * j] = acc[mi][ni][e];
-				}
-			}
-		}
-	};
-	if (out) store(out);
-	if (act_out) {
-		act_fwd_rt_n<double, 8 * NI * 2>(act_kind, &acc[0][0][0], act_param);
-		store(act_out);
-	}
+	dmma_epilogue<NI>(acc, gg, M, J, m0 + row0, j0 + col0, lane, bias, bias_mode, out, act_kind, act_param, act_out);
 }
 
 // Weight gradient (even batch, M even): tile rows are (tap, r), columns j, the reduction runs over m in blocks of 8.

@@ -24,7 +24,7 @@ $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file $OUT/${TAG}_launch
 $NCU --set full --import-source on -k regex:"tc_gather_gemm_kernel|tc_wgrad_kernel|tc_rows_gemm_kernel" -s 9 -c 3 -o $OUT/${TAG}_tc \
 	python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-networks --no-double > /dev/null 2>&1
 # the double kernels of config 2: FP64 tensor cores (DMMA: what AUTO runs), then the DFMA kernels (--path 3)
-$NCU --set full --import-source on -k regex:"dmma_gather_gemm_kernel|dmma_wgrad_kernel" -s 30 -c 4 -o $OUT/${TAG}_dmma \
+$NCU --set full --import-source on -k regex:"dmma2?_gather_gemm_kernel|dmma2?_wgrad_kernel" -s 30 -c 4 -o $OUT/${TAG}_dmma \
 	python scripts/bench_ops.py --only conv --double --reps 1 > /dev/null 2>&1
 $NCU --set full --import-source on -k regex:"fma_gather_gemm_kernel|fma_wgrad_kernel" -s 0 -c 4 -o $OUT/${TAG}_dfma \
 	python scripts/bench_ops.py --only conv --double --reps 1 --path 3 > /dev/null 2>&1
