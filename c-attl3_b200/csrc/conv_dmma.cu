@@ -5,12 +5,16 @@
 // and stall on exactly those loads (profiles/README.md, r1e: FP64 pipe 51 % active, short-scoreboard stalls).
 // tcgen05 has no fp64 kind, so this is the tensor-core path there is for double.
 //
-// Same implicit GEMM, same tiling as conv_dfma.cu: 128 x 64 (weight gradient: also 128 x 128) block tiles, 256 threads =
-// 8 warps as 2 (rows) x 4 (columns), a warp owns 64 x 16 (64 x 32) as 8 x 2 (8 x 4) m8n8k4 tiles, accumulators in registers;
-// tiles staged global -> shared with cp.async, two buffers, one barrier per k-block of 8; no im2col buffer.
+// Two families.  Layers whose grid fills the device run the PRODUCER-WARP kernels further down (dmma2_*: a cp.async ring behind
+// mbarriers, eight warps that only read fragments and issue DMMAs; config 2: 0.88 / 0.78 / 0.88 of the DMMA rate).  Smaller
+// layers keep the first family, directly below: same implicit GEMM and tiling as conv_dfma.cu -- 128 x 64 (weight gradient:
+// also 128 x 128) block tiles, 256 threads = 8 warps as 2 (rows) x 4 (columns), a warp owns 64 x 16 (64 x 32) as 8 x 2 (8 x 4)
+// m8n8k4 tiles, accumulators in registers; tiles staged global -> shared with cp.async, two buffers, one barrier per k-block
+// of 8, two CTAs per SM; no im2col buffer.
 // Fragments (PTX ISA, mma.m8n8k4 .f64): A[row = lane / 4][k = lane % 4], B[k = lane % 4][col = lane / 4],
 // C[row = lane / 4][col = 2 * (lane % 4) + {0, 1}].  Shared-memory rows are k (the reduction index) with a pitch of
-// tile + 4 doubles, which makes both the fragment reads and the weight gradient's transposing writes conflict free.
+// tile + 4 doubles: conflict free for the fragment reads (the weight gradient's transposing 8-byte writes are 2-way
+// conflicts -- 301 M of them at config 2, one of the reasons for the second family's [row][8 m] layout).
 #include <stdlib.h>
 
 #include "activations.cuh"
