@@ -419,7 +419,10 @@ def main():
     # ---- per-kernel rooflines: each device pass timed alone on the launching stream ---------------------
     pk = peaks()
     torch.cuda.synchronize()
-    probe = measured_tf32_peak() if (rank == 0 and world == 1) else None
+    # rank 0 measures the denominator on its own GPU at every world size (the other ranks wait: their lines are not printed,
+    # and a probe on a busy box would not be a peak)
+    probe = measured_tf32_peak() if rank == 0 else None
+    barrier()
     if probe:
         tf32_peak = probe["burst"]
         peak_source = ("dense tcgen05.mma kind::tf32 (M128 N256 K8, A from tensor memory) measured by scripts/tf32_peak in this "
